@@ -1,0 +1,159 @@
+/* sequila_cuda.h — C ABI of the B200-native interval-overlap join (`alg=Cuda`).
+ *
+ * The reference (biodatageeks/sequila-native) has no FFI for this path: its seam is the
+ * private Rust enum `IntervalJoinAlgorithm` with `new()` / `get()`
+ * (sequila/sequila-core/src/physical_planner/joins/interval_join.rs, "IJ" below, IJ:767 and
+ * IJ:957-960).  A per-row callback is the wrong granularity for a GPU, so this ABI sits one
+ * level up: it replaces the tail of `collect_left_input` (IJ:662-683) and the body of
+ * `process_probe_batch` (IJ:1582-1632) with batch-level calls.  Every entry point names the
+ * reference lines whose work it takes over.  INTEGRATION.md shows the Rust `-sys` binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns 0 on success or an SQ_E* code,
+ *     never aborts; the message is read with sq_last_error / sq_stream_last_error;
+ *   - "host" entry points borrow caller memory for the duration of the call only;
+ *   - `_device` entry points take device pointers (used by the kernel-level benchmark so
+ *     that timing excludes PCIe) and enqueue on the sq_stream's CUDA stream;
+ *   - there is no CPU fallback: without a usable CUDA device sq_ctx_create fails.
+ */
+#ifndef SEQUILA_CUDA_H
+#define SEQUILA_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQ_OK 0
+#define SQ_EINVAL 1    /* bad argument                                  */
+#define SQ_ECUDA 2     /* CUDA runtime/driver error (message has detail) */
+#define SQ_ENOMEM 3    /* device or pinned-host allocation failed       */
+#define SQ_ESTATE 4    /* call order violated (emit without count, ...) */
+#define SQ_ECAPACITY 5 /* caller buffer smaller than the result         */
+#define SQ_ECAST 6     /* value does not fit Int32 (IJ:1661-1672)       */
+
+#define SQ_ABI_VERSION 1
+
+typedef struct sq_ctx sq_ctx;       /* per process+device: error slot, device id            */
+typedef struct sq_index sq_index;   /* immutable build-side index (+ resident build columns) */
+typedef struct sq_stream sq_stream; /* per DataFusion partition: CUDA stream, staging, scratch */
+
+/* ---- context ------------------------------------------------------------------------- */
+int32_t sq_abi_version(void);
+/* device = CUDA ordinal.  Fails (SQ_ECUDA) when no usable device exists: no CPU fallback. */
+int32_t sq_ctx_create(int32_t device, sq_ctx** out);
+void sq_ctx_destroy(sq_ctx* ctx);
+const char* sq_last_error(const sq_ctx* ctx);
+int32_t sq_device_count(void);
+
+/* Pinned host memory for Arrow buffers the host wants copied without a staging hop. */
+int32_t sq_host_alloc(sq_ctx* ctx, size_t bytes, void** out);
+void sq_host_free(sq_ctx* ctx, void* p);
+
+/* ---- build side ------------------------------------------------------------------------
+ * Replaces IJ:662-683: `update_hashmap` (bucket rows by the u64 key hash only, IJ:1042-1048)
+ * + `IntervalJoinAlgorithm::new` (one coitrees tree per key, IJ:769-793).
+ *   key_hash[i] = create_hashes(on_left, RandomState::with_seeds(0,0,0,0))   IJ:136, IJ:1037
+ *   start[i], end[i] = evaluate_as_i32(left_interval.start()/end())          IJ:1039-1040
+ *   row i  <->  left index i of the concatenated build batch                 IJ:685, IJ:1043
+ * n_rows must be < 2^32 - 1 (the reference truncates `pos as u32`, IJ:1590).
+ * The index is immutable after return and may be probed from many threads/streams. */
+int32_t sq_index_build(sq_ctx* ctx, const uint64_t* key_hash, const int32_t* start,
+                       const int32_t* end, uint64_t n_rows, sq_index** out);
+/* Same, inputs already in device memory; `cuda_stream` is a cudaStream_t (NULL = default). */
+int32_t sq_index_build_device(sq_ctx* ctx, const uint64_t* d_key_hash, const int32_t* d_start,
+                              const int32_t* d_end, uint64_t n_rows, void* cuda_stream,
+                              sq_index** out);
+uint64_t sq_index_bytes(const sq_index* idx); /* device bytes held (build_mem_used gauge, IJ:631) */
+uint64_t sq_index_rows(const sq_index* idx);
+uint64_t sq_index_keys(const sq_index* idx);  /* distinct key hashes = number of per-key trees    */
+/* device time of the last build's kernels in ms (sort, scan, ...); 0 if unknown */
+float sq_index_build_ms(const sq_index* idx);
+void sq_index_free(sq_index* idx);
+
+/* Build-side columns to materialise later (IJ:1623-1624 `take(build.batch.column(k), left)`).
+ * Fixed-width values of `width` bytes (4, 8 or 16) per row, n_rows of them; copied to the device. */
+int32_t sq_index_add_column(sq_index* idx, const void* values, uint32_t width, int32_t* col_id_out);
+int32_t sq_index_add_column_device(sq_index* idx, const void* d_values, uint32_t width,
+                                   int32_t* col_id_out); /* borrowed, must outlive the index */
+
+/* ---- probe side ------------------------------------------------------------------------
+ * One sq_stream per partition (IJ:528-556 creates one IntervalJoinStream per partition);
+ * not thread-safe by itself, but different sq_streams may probe one sq_index concurrently. */
+int32_t sq_stream_create(sq_ctx* ctx, sq_stream** out);
+/* Run on a caller-provided cudaStream_t (e.g. the host framework's current stream). */
+int32_t sq_stream_create_on(sq_ctx* ctx, void* cuda_stream, sq_stream** out);
+void sq_stream_free(sq_stream* s);
+const char* sq_stream_last_error(const sq_stream* s);
+uint64_t sq_stream_bytes(const sq_stream* s); /* device scratch + pinned staging held */
+
+/* Phase 1 of `process_probe_batch` full mode (IJ:1582-1609) for one probe tile (>= 1 probe
+ * batch, order preserved):
+ *   key_hash[i] = create_hashes(on_right)      IJ:1202-1211
+ *   start/end   = evaluate_as_i32(right ...)   IJ:1430-1431
+ * Computes, on the device, for every probe row the number of build rows with equal key hash
+ * and  build.start <= probe.end && build.end >= probe.start  (IV:95-137; coitrees
+ * nosimd.rs:647-649); a key hash absent from the build side yields zero (IJ:965).
+ * *n_pairs_out = total number of output rows, so the caller can allocate. */
+int32_t sq_probe_count(sq_stream* s, const sq_index* idx, const uint64_t* key_hash,
+                       const int32_t* start, const int32_t* end, uint32_t n_rows,
+                       uint64_t* n_pairs_out);
+/* Phase 2 (IJ:1604-1618): writes the pairs of the tile just counted.
+ *   left_idx_out[k]  = build row (== `pos as u32`, IJ:1590)
+ *   right_idx_out[k] = probe row within this tile, non-decreasing (IJ:1611-1618); may be NULL
+ *   counts_out[i]    = hits of probe row i (`rle_right`, IJ:1604); may be NULL
+ * The order of left hits inside one probe row is unspecified (as in the reference, where it
+ * is coitrees' traversal order and every test sorts, IJ:1808).
+ * capacity = number of elements left_idx_out/right_idx_out can hold (>= n_pairs). */
+int32_t sq_probe_emit_pairs(sq_stream* s, uint32_t* left_idx_out, uint32_t* right_idx_out,
+                            uint32_t* counts_out, uint64_t capacity);
+
+/* Device-pointer variants (kernel-level benchmark; outputs stay in HBM).  The count variant
+ * synchronises the stream to return n_pairs. */
+int32_t sq_probe_count_device(sq_stream* s, const sq_index* idx, const uint64_t* d_key_hash,
+                              const int32_t* d_start, const int32_t* d_end, uint32_t n_rows,
+                              uint64_t* n_pairs_out);
+int32_t sq_probe_emit_pairs_device(sq_stream* s, uint32_t* d_left_idx_out,
+                                   uint32_t* d_right_idx_out, uint64_t capacity);
+/* device pointer to the per-probe-row counts of the last sq_probe_count* on this stream */
+const uint32_t* sq_stream_counts_device(const sq_stream* s);
+
+/* ---- materialise (IJ:1620-1632: one arrow::compute::take per output column) -------------
+ * Gathers fixed-width values for the pairs of the last emit on this stream, on the device.
+ * side 0 = build column registered with sq_index_add_column (indexed by left_idx),
+ * side 1 = probe column of `width`-byte values for this tile (indexed by right_idx).
+ * Host variant: `probe_values` (side 1 only) and `out` are host pointers. */
+int32_t sq_gather_column(sq_stream* s, int32_t side, int32_t build_col_id,
+                         const void* probe_values, uint32_t width, void* out, uint64_t capacity);
+int32_t sq_gather_column_device(sq_stream* s, int32_t side, int32_t build_col_id,
+                                const void* d_probe_values, uint32_t width, void* d_out,
+                                uint64_t capacity);
+
+/* ---- helpers on the boundary -------------------------------------------------------------
+ * `evaluate_as_i32` for BIGINT columns (IJ:1661-1672): checked cast Int64 -> Int32 on the
+ * device, optionally subtracting `minus` first (the `end - 1` of strict comparisons,
+ * IV:67-69).  On overflow returns SQ_ECAST and the message is exactly the reference's
+ * "Arrow error: Cast error: Can't cast value {v} to type Int32" (IJ:1959-1965), v being the
+ * first offending value in row order. */
+int32_t sq_cast_i64_to_i32(sq_stream* s, const int64_t* values, uint64_t n, int64_t minus,
+                           int32_t* out);
+
+/* Order-independent multiset digest of (left,right+right_offset) pairs held in device memory:
+ * out3 = {count, sum of mix64(left<<32|right) mod 2^64, xor of the same}.  Parity at scale. */
+int32_t sq_pairs_digest_device(sq_stream* s, const uint32_t* d_left, const uint32_t* d_right,
+                               uint64_t n_pairs, uint64_t right_offset, uint64_t out3[3]);
+
+/* Per-phase device timings (ms) of the last count+emit on this stream, measured with CUDA
+ * events on the stream: [0]=h2d [1]=count kernel [2]=write kernel [3]=d2h [4]=gather.
+ * Enabled by sq_stream_set_profiling(s, 1); adds only event records to the stream. */
+int32_t sq_stream_set_profiling(sq_stream* s, int32_t enabled);
+int32_t sq_stream_phase_ms(sq_stream* s, float out5[5]);
+/* number of kernels this library launched on the stream since creation (bench: gpu_launches) */
+uint64_t sq_stream_launches(const sq_stream* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEQUILA_CUDA_H */

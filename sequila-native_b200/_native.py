@@ -1,0 +1,81 @@
+"""ctypes binding of libsequila_cuda.so — the same C ABI (include/sequila_cuda.h) a Rust
+`sequila-cuda-sys` crate would bind.  The library must exist: there is no
+CPU fallback and no oracle import anywhere in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsequila_cuda.so")
+
+SQ_OK, SQ_EINVAL, SQ_ECUDA, SQ_ENOMEM, SQ_ESTATE, SQ_ECAPACITY, SQ_ECAST = range(7)
+
+u64p = C.POINTER(C.c_uint64)
+i64p = C.POINTER(C.c_int64)
+i32p = C.POINTER(C.c_int32)
+u32p = C.POINTER(C.c_uint32)
+f32p = C.POINTER(C.c_float)
+vp = C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/sequila_cuda.h declares
+SIGNATURES = {
+    "sq_abi_version": (C.c_int32, []),
+    "sq_ctx_create": (C.c_int32, [C.c_int32, C.POINTER(vp)]),
+    "sq_ctx_destroy": (None, [vp]),
+    "sq_last_error": (C.c_char_p, [vp]),
+    "sq_device_count": (C.c_int32, []),
+    "sq_host_alloc": (C.c_int32, [vp, C.c_size_t, C.POINTER(vp)]),
+    "sq_host_free": (None, [vp, vp]),
+    "sq_index_build": (C.c_int32, [vp, vp, vp, vp, C.c_uint64, C.POINTER(vp)]),
+    "sq_index_build_device": (C.c_int32, [vp, vp, vp, vp, C.c_uint64, vp, C.POINTER(vp)]),
+    "sq_index_bytes": (C.c_uint64, [vp]),
+    "sq_index_rows": (C.c_uint64, [vp]),
+    "sq_index_keys": (C.c_uint64, [vp]),
+    "sq_index_build_ms": (C.c_float, [vp]),
+    "sq_index_free": (None, [vp]),
+    "sq_index_add_column": (C.c_int32, [vp, vp, C.c_uint32, C.POINTER(C.c_int32)]),
+    "sq_index_add_column_device": (C.c_int32, [vp, vp, C.c_uint32, C.POINTER(C.c_int32)]),
+    "sq_stream_create": (C.c_int32, [vp, C.POINTER(vp)]),
+    "sq_stream_create_on": (C.c_int32, [vp, vp, C.POINTER(vp)]),
+    "sq_stream_free": (None, [vp]),
+    "sq_stream_last_error": (C.c_char_p, [vp]),
+    "sq_stream_bytes": (C.c_uint64, [vp]),
+    "sq_probe_count": (C.c_int32, [vp, vp, vp, vp, vp, C.c_uint32, u64p]),
+    "sq_probe_emit_pairs": (C.c_int32, [vp, vp, vp, vp, C.c_uint64]),
+    "sq_probe_count_device": (C.c_int32, [vp, vp, vp, vp, vp, C.c_uint32, u64p]),
+    "sq_probe_emit_pairs_device": (C.c_int32, [vp, vp, vp, C.c_uint64]),
+    "sq_stream_counts_device": (vp, [vp]),
+    "sq_gather_column": (C.c_int32, [vp, C.c_int32, C.c_int32, vp, C.c_uint32, vp, C.c_uint64]),
+    "sq_gather_column_device": (C.c_int32, [vp, C.c_int32, C.c_int32, vp, C.c_uint32, vp, C.c_uint64]),
+    "sq_cast_i64_to_i32": (C.c_int32, [vp, vp, C.c_uint64, C.c_int64, vp]),
+    "sq_pairs_digest_device": (C.c_int32, [vp, vp, vp, C.c_uint64, C.c_uint64, u64p]),
+    "sq_stream_set_profiling": (C.c_int32, [vp, C.c_int32]),
+    "sq_stream_phase_ms": (C.c_int32, [vp, f32p]),
+    "sq_stream_launches": (C.c_uint64, [vp]),
+}
+
+_lib = None
+
+
+class SequilaCudaError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(message)
+        self.code = code
+
+
+def lib():
+    """Load the CUDA extension; raise loudly if it was not built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+                " (make -C sequila-native_b200/csrc). The cuda interval join has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib

@@ -1,0 +1,493 @@
+// C ABI of libsequila_cuda.so (declared in include/sequila_cuda.h): context / index / stream
+// objects, host<->device staging and the call protocol around the kernels in sq_build.cu,
+// sq_probe.cu and sq_gather.cu.  No CPU fallback exists anywhere in this library.
+#include <cstdarg>
+#include <cstring>
+
+#include "sq_internal.cuh"
+
+#define SQ_API extern "C" __attribute__((visibility("default")))
+
+namespace sq {
+
+int fail(ErrorSlot& e, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  e.set(buf);
+  return code;
+}
+
+void release(sq_buf& b) {
+  if (!b.p) return;
+  if (b.pinned) cudaFreeHost(b.p); else cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+int ensure(ErrorSlot& e, sq_buf& b, size_t bytes, bool pinned) {
+  if (bytes < 256) bytes = 256;
+  if (b.p && b.cap >= bytes) return SQ_OK;
+  release(b);
+  const size_t want = bytes + bytes / 4;  // grow-only with slack: tiles of similar size reuse it
+  cudaError_t err = pinned ? cudaHostAlloc(&b.p, want, cudaHostAllocDefault) : cudaMalloc(&b.p, want);
+  if (err != cudaSuccess) {
+    b.p = nullptr;
+    cudaGetLastError();
+    return fail(e, SQ_ENOMEM, "%s of %zu bytes failed: %s", pinned ? "cudaHostAlloc" : "cudaMalloc", want,
+                cudaGetErrorString(err));
+  }
+  b.cap = want;
+  b.pinned = pinned;
+  return SQ_OK;
+}
+
+static int ensure_events(sq_stream* s) {
+  if (s->ev_ready) return SQ_OK;
+  for (auto& e : s->ev) SQ_CUDA(s->err, cudaEventCreate(&e));
+  s->ev_ready = true;
+  return SQ_OK;
+}
+
+static inline void mark(sq_stream* s, int k) {
+  if (s->profiling && s->ev_ready) cudaEventRecord(s->ev[k], s->stream);
+}
+
+}  // namespace sq
+
+using namespace sq;
+
+SQ_API int32_t sq_abi_version(void) { return SQ_ABI_VERSION; }
+
+SQ_API int32_t sq_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+static ErrorSlot g_create_err;
+
+SQ_API int32_t sq_ctx_create(int32_t device, sq_ctx** out) {
+  if (!out) return SQ_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(g_create_err, SQ_ECUDA, "no usable CUDA device (%s); the cuda interval join has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+  }
+  if (device < 0 || device >= n) return fail(g_create_err, SQ_EINVAL, "device %d out of range [0,%d)", device, n);
+  sq_ctx* c = new sq_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    delete c;
+    return fail(g_create_err, SQ_ECUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+  }
+  c->sm_count = prop.multiProcessorCount;
+  *out = c;
+  return SQ_OK;
+}
+
+SQ_API void sq_ctx_destroy(sq_ctx* ctx) { delete ctx; }
+
+SQ_API const char* sq_last_error(const sq_ctx* ctx) {
+  // the returned pointer stays valid until the next failing call on the same object
+  return ctx ? ctx->err.msg.c_str() : g_create_err.msg.c_str();
+}
+
+SQ_API int32_t sq_host_alloc(sq_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return SQ_EINVAL;
+  SQ_CUDA(ctx->err, cudaSetDevice(ctx->device));
+  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx->err, SQ_ENOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+  return SQ_OK;
+}
+
+SQ_API void sq_host_free(sq_ctx*, void* p) { if (p) cudaFreeHost(p); }
+
+// ---- build ------------------------------------------------------------------------------------
+SQ_API int32_t sq_index_build_device(sq_ctx* ctx, const uint64_t* d_key_hash, const int32_t* d_start,
+                                     const int32_t* d_end, uint64_t n_rows, void* cuda_stream, sq_index** out) {
+  if (!ctx || !out) return SQ_EINVAL;
+  *out = nullptr;
+  if (n_rows && (!d_key_hash || !d_start || !d_end)) return fail(ctx->err, SQ_EINVAL, "null build column");
+  return build_index_device(ctx, d_key_hash, d_start, d_end, n_rows, static_cast<cudaStream_t>(cuda_stream), out);
+}
+
+SQ_API int32_t sq_index_build(sq_ctx* ctx, const uint64_t* key_hash, const int32_t* start, const int32_t* end,
+                              uint64_t n_rows, sq_index** out) {
+  if (!ctx || !out) return SQ_EINVAL;
+  *out = nullptr;
+  if (n_rows && (!key_hash || !start || !end)) return fail(ctx->err, SQ_EINVAL, "null build column");
+  ErrorSlot& E = ctx->err;
+  SQ_CUDA(E, cudaSetDevice(ctx->device));
+  void* d = nullptr;
+  const size_t n = n_rows ? n_rows : 1;
+  SQ_CUDA(E, cudaMalloc(&d, n * 16));
+  auto* dk = static_cast<uint64_t*>(d);
+  auto* ds = reinterpret_cast<int32_t*>(dk + n);
+  auto* de = ds + n;
+  cudaStream_t st;
+  cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { cudaFree(d); return fail(E, SQ_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+  int rc = SQ_OK;
+  if (n_rows) {
+    if ((e = cudaMemcpyAsync(dk, key_hash, n_rows * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(ds, start, n_rows * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(de, end, n_rows * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+      rc = fail(E, SQ_ECUDA, "H2D copy of build columns: %s", cudaGetErrorString(e));
+  }
+  if (rc == SQ_OK) rc = build_index_device(ctx, dk, ds, de, n_rows, st, out);
+  cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  cudaFree(d);
+  return rc;
+}
+
+SQ_API uint64_t sq_index_bytes(const sq_index* idx) { return idx ? idx->bytes : 0; }
+SQ_API uint64_t sq_index_rows(const sq_index* idx) { return idx ? idx->n_rows : 0; }
+SQ_API uint64_t sq_index_keys(const sq_index* idx) { return idx ? idx->n_keys : 0; }
+SQ_API float sq_index_build_ms(const sq_index* idx) { return idx ? idx->build_ms : 0.f; }
+SQ_API void sq_index_free(sq_index* idx) { free_index(idx); }
+
+SQ_API int32_t sq_index_add_column(sq_index* idx, const void* values, uint32_t width, int32_t* col_id_out) {
+  if (!idx || !col_id_out) return SQ_EINVAL;
+  ErrorSlot& E = idx->ctx->err;
+  if (width != 4 && width != 8 && width != 16) return fail(E, SQ_EINVAL, "column width %u not in {4,8,16}", width);
+  if (idx->n_rows && !values) return fail(E, SQ_EINVAL, "null column values");
+  SQ_CUDA(E, cudaSetDevice(idx->ctx->device));
+  sq_column c;
+  c.width = width;
+  c.owned = true;
+  const size_t bytes = size_t(idx->n_rows ? idx->n_rows : 1) * width;
+  SQ_CUDA(E, cudaMalloc(&c.d_values, bytes));
+  if (idx->n_rows) {
+    cudaError_t e = cudaMemcpy(c.d_values, values, size_t(idx->n_rows) * width, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(c.d_values); return fail(E, SQ_ECUDA, "H2D copy of build column: %s", cudaGetErrorString(e)); }
+  }
+  std::lock_guard<std::mutex> g(idx->col_mu);
+  idx->bytes += bytes;
+  idx->columns.push_back(c);
+  *col_id_out = int32_t(idx->columns.size() - 1);
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_index_add_column_device(sq_index* idx, const void* d_values, uint32_t width, int32_t* col_id_out) {
+  if (!idx || !col_id_out) return SQ_EINVAL;
+  ErrorSlot& E = idx->ctx->err;
+  if (width != 4 && width != 8 && width != 16) return fail(E, SQ_EINVAL, "column width %u not in {4,8,16}", width);
+  sq_column c;
+  c.width = width;
+  c.owned = false;
+  c.d_values = const_cast<void*>(d_values);
+  std::lock_guard<std::mutex> g(idx->col_mu);
+  idx->columns.push_back(c);
+  *col_id_out = int32_t(idx->columns.size() - 1);
+  return SQ_OK;
+}
+
+// ---- streams ----------------------------------------------------------------------------------
+static int32_t stream_create(sq_ctx* ctx, cudaStream_t ext, bool use_ext, sq_stream** out) {
+  if (!ctx || !out) return SQ_EINVAL;
+  *out = nullptr;
+  SQ_CUDA(ctx->err, cudaSetDevice(ctx->device));
+  sq_stream* s = new sq_stream();
+  s->ctx = ctx;
+  if (use_ext) {
+    s->stream = ext;
+  } else {
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete s; return fail(ctx->err, SQ_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    s->own_stream = true;
+  }
+  *out = s;
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_stream_create(sq_ctx* ctx, sq_stream** out) { return stream_create(ctx, nullptr, false, out); }
+SQ_API int32_t sq_stream_create_on(sq_ctx* ctx, void* cuda_stream, sq_stream** out) {
+  return stream_create(ctx, static_cast<cudaStream_t>(cuda_stream), true, out);
+}
+
+SQ_API void sq_stream_free(sq_stream* s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->stream);
+  for (sq_buf* b : {&s->d_in, &s->d_lo, &s->d_ncand, &s->d_cnt, &s->d_tile, &s->d_scalar, &s->d_left,
+                    &s->d_right, &s->d_gather, &s->h_in, &s->h_out, &s->h_scalar})
+    release(*b);
+  if (s->ev_ready) for (auto& e : s->ev) cudaEventDestroy(e);
+  if (s->own_stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+SQ_API const char* sq_stream_last_error(const sq_stream* s) { return s ? s->err.msg.c_str() : ""; }
+
+SQ_API uint64_t sq_stream_bytes(const sq_stream* s) {
+  if (!s) return 0;
+  uint64_t t = 0;
+  for (const sq_buf* b : {&s->d_in, &s->d_lo, &s->d_ncand, &s->d_cnt, &s->d_tile, &s->d_scalar, &s->d_left,
+                          &s->d_right, &s->d_gather, &s->h_in, &s->h_out, &s->h_scalar})
+    t += b->cap;
+  return t;
+}
+
+SQ_API int32_t sq_stream_set_profiling(sq_stream* s, int32_t enabled) {
+  if (!s) return SQ_EINVAL;
+  s->profiling = enabled != 0;
+  if (s->profiling) { SQ_CUDA(s->err, cudaSetDevice(s->ctx->device)); return ensure_events(s); }
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_stream_phase_ms(sq_stream* s, float out5[5]) {
+  if (!s || !out5) return SQ_EINVAL;
+  for (int k = 0; k < 5; ++k) out5[k] = s->phase_ms[k];
+  return SQ_OK;
+}
+
+SQ_API uint64_t sq_stream_launches(const sq_stream* s) { return s ? s->launches : 0; }
+SQ_API const uint32_t* sq_stream_counts_device(const sq_stream* s) {
+  return s ? static_cast<const uint32_t*>(s->d_cnt.p) : nullptr;
+}
+
+// ---- probe ------------------------------------------------------------------------------------
+static int32_t finish_count(sq_stream* s, uint64_t* n_pairs_out) {
+  ErrorSlot& E = s->err;
+  int rc;
+  if ((rc = ensure(E, s->h_scalar, 256, true))) return rc;
+  auto* h = static_cast<unsigned long long*>(s->h_scalar.p);
+  SQ_CUDA(E, cudaMemcpyAsync(h, s->d_scalar.p, 8, cudaMemcpyDeviceToHost, s->stream));
+  SQ_CUDA(E, cudaStreamSynchronize(s->stream));
+  s->n_pairs = h[0];
+  s->counted = true;
+  s->emitted = false;
+  if (s->profiling) {
+    cudaEventElapsedTime(&s->phase_ms[0], s->ev[0], s->ev[1]);
+    cudaEventElapsedTime(&s->phase_ms[1], s->ev[1], s->ev[2]);
+  }
+  *n_pairs_out = s->n_pairs;
+  return SQ_OK;
+}
+
+static int32_t check_probe_args(sq_stream* s, const sq_index* idx, const void* k, const void* a, const void* b,
+                                uint32_t n, uint64_t* out) {
+  if (!s) return SQ_EINVAL;
+  if (!idx || !out) return fail(s->err, SQ_EINVAL, "null index or output pointer");
+  if (n && (!k || !a || !b)) return fail(s->err, SQ_EINVAL, "null probe column");
+  if (idx->ctx->device != s->ctx->device) return fail(s->err, SQ_EINVAL, "index lives on device %d, stream on %d",
+                                                       idx->ctx->device, s->ctx->device);
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_probe_count_device(sq_stream* s, const sq_index* idx, const uint64_t* d_key_hash,
+                                     const int32_t* d_start, const int32_t* d_end, uint32_t n_rows,
+                                     uint64_t* n_pairs_out) {
+  int rc = check_probe_args(s, idx, d_key_hash, d_start, d_end, n_rows, n_pairs_out);
+  if (rc) return rc;
+  SQ_CUDA(s->err, cudaSetDevice(s->ctx->device));
+  s->idx = idx;
+  s->n_rows = n_rows;
+  s->d_q_start = d_start;
+  s->counted = false;
+  if (n_rows == 0) { s->n_pairs = 0; s->counted = true; s->emitted = false; *n_pairs_out = 0; return SQ_OK; }
+  mark(s, 0);
+  mark(s, 1);
+  if ((rc = launch_count(s, idx, d_key_hash, d_start, d_end, n_rows))) return rc;
+  mark(s, 2);
+  return finish_count(s, n_pairs_out);
+}
+
+SQ_API int32_t sq_probe_count(sq_stream* s, const sq_index* idx, const uint64_t* key_hash, const int32_t* start,
+                              const int32_t* end, uint32_t n_rows, uint64_t* n_pairs_out) {
+  int rc = check_probe_args(s, idx, key_hash, start, end, n_rows, n_pairs_out);
+  if (rc) return rc;
+  ErrorSlot& E = s->err;
+  SQ_CUDA(E, cudaSetDevice(s->ctx->device));
+  s->idx = idx;
+  s->n_rows = n_rows;
+  s->counted = false;
+  if (n_rows == 0) { s->n_pairs = 0; s->counted = true; s->emitted = false; *n_pairs_out = 0; return SQ_OK; }
+  const size_t n = n_rows;
+  if ((rc = ensure(E, s->d_in, n * 16, false))) return rc;
+  auto* dk = static_cast<uint64_t*>(s->d_in.p);
+  auto* ds = reinterpret_cast<int32_t*>(dk + n);
+  auto* de = ds + n;
+  mark(s, 0);
+  SQ_CUDA(E, cudaMemcpyAsync(dk, key_hash, n * 8, cudaMemcpyHostToDevice, s->stream));
+  SQ_CUDA(E, cudaMemcpyAsync(ds, start, n * 4, cudaMemcpyHostToDevice, s->stream));
+  SQ_CUDA(E, cudaMemcpyAsync(de, end, n * 4, cudaMemcpyHostToDevice, s->stream));
+  mark(s, 1);
+  s->d_q_start = ds;
+  if ((rc = launch_count(s, idx, dk, ds, de, n_rows))) return rc;
+  mark(s, 2);
+  return finish_count(s, n_pairs_out);
+}
+
+static int32_t check_emit(sq_stream* s, const void* left, uint64_t capacity) {
+  if (!s) return SQ_EINVAL;
+  if (!s->counted) return fail(s->err, SQ_ESTATE, "sq_probe_emit_pairs called without a preceding sq_probe_count");
+  if (capacity < s->n_pairs)
+    return fail(s->err, SQ_ECAPACITY, "output capacity %llu < %llu pairs", (unsigned long long)capacity,
+                (unsigned long long)s->n_pairs);
+  if (s->n_pairs && !left) return fail(s->err, SQ_EINVAL, "null left_idx_out");
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_probe_emit_pairs_device(sq_stream* s, uint32_t* d_left_idx_out, uint32_t* d_right_idx_out,
+                                          uint64_t capacity) {
+  int rc = check_emit(s, d_left_idx_out, capacity);
+  if (rc) return rc;
+  SQ_CUDA(s->err, cudaSetDevice(s->ctx->device));
+  mark(s, 3);
+  if (s->n_pairs && (rc = launch_write(s, d_left_idx_out, d_right_idx_out))) return rc;
+  mark(s, 4);
+  s->d_last_left = d_left_idx_out;
+  s->d_last_right = d_right_idx_out;
+  s->emitted = true;
+  if (s->profiling) {
+    SQ_CUDA(s->err, cudaStreamSynchronize(s->stream));
+    cudaEventElapsedTime(&s->phase_ms[2], s->ev[3], s->ev[4]);
+  }
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_probe_emit_pairs(sq_stream* s, uint32_t* left_idx_out, uint32_t* right_idx_out,
+                                   uint32_t* counts_out, uint64_t capacity) {
+  int rc = check_emit(s, left_idx_out, capacity);
+  if (rc) return rc;
+  ErrorSlot& E = s->err;
+  SQ_CUDA(E, cudaSetDevice(s->ctx->device));
+  const size_t np = s->n_pairs;
+  if ((rc = ensure(E, s->d_left, np * 4, false))) return rc;
+  // right_idx is needed on the device whenever a later gather of probe columns may follow
+  if ((rc = ensure(E, s->d_right, np * 4, false))) return rc;
+  auto* dl = static_cast<uint32_t*>(s->d_left.p);
+  auto* dr = static_cast<uint32_t*>(s->d_right.p);
+  mark(s, 3);
+  if (np && (rc = launch_write(s, dl, dr))) return rc;
+  mark(s, 4);
+  if (np) {
+    SQ_CUDA(E, cudaMemcpyAsync(left_idx_out, dl, np * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (right_idx_out) SQ_CUDA(E, cudaMemcpyAsync(right_idx_out, dr, np * 4, cudaMemcpyDeviceToHost, s->stream));
+  }
+  if (counts_out && s->n_rows)
+    SQ_CUDA(E, cudaMemcpyAsync(counts_out, s->d_cnt.p, size_t(s->n_rows) * 4, cudaMemcpyDeviceToHost, s->stream));
+  mark(s, 5);
+  SQ_CUDA(E, cudaStreamSynchronize(s->stream));
+  s->d_last_left = dl;
+  s->d_last_right = dr;
+  s->emitted = true;
+  if (s->profiling) {
+    cudaEventElapsedTime(&s->phase_ms[2], s->ev[3], s->ev[4]);
+    cudaEventElapsedTime(&s->phase_ms[3], s->ev[4], s->ev[5]);
+  }
+  return SQ_OK;
+}
+
+// ---- gather -----------------------------------------------------------------------------------
+static int32_t gather_source(sq_stream* s, int32_t side, int32_t build_col_id, uint32_t* width,
+                             const void** d_values, const uint32_t** d_idx) {
+  if (!s->emitted) return fail(s->err, SQ_ESTATE, "sq_gather_column called without a preceding emit");
+  if (side == 0) {
+    sq_index* idx = const_cast<sq_index*>(s->idx);
+    std::lock_guard<std::mutex> g(idx->col_mu);
+    if (build_col_id < 0 || size_t(build_col_id) >= idx->columns.size())
+      return fail(s->err, SQ_EINVAL, "unknown build column id %d", build_col_id);
+    *width = idx->columns[build_col_id].width;
+    *d_values = idx->columns[build_col_id].d_values;
+    *d_idx = s->d_last_left;
+  } else if (side == 1) {
+    if (!s->d_last_right && s->n_pairs) return fail(s->err, SQ_ESTATE, "right indices were not emitted on the device");
+    *d_idx = s->d_last_right;
+  } else {
+    return fail(s->err, SQ_EINVAL, "side must be 0 (build) or 1 (probe)");
+  }
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_gather_column_device(sq_stream* s, int32_t side, int32_t build_col_id, const void* d_probe_values,
+                                       uint32_t width, void* d_out, uint64_t capacity) {
+  if (!s) return SQ_EINVAL;
+  const void* src = d_probe_values;
+  const uint32_t* ix = nullptr;
+  int rc = gather_source(s, side, build_col_id, &width, &src, &ix);
+  if (rc) return rc;
+  if (capacity < s->n_pairs) return fail(s->err, SQ_ECAPACITY, "gather capacity %llu < %llu", (unsigned long long)capacity,
+                                         (unsigned long long)s->n_pairs);
+  SQ_CUDA(s->err, cudaSetDevice(s->ctx->device));
+  mark(s, 6);
+  rc = launch_gather(s, src, ix, s->n_pairs, width, d_out);
+  mark(s, 7);
+  if (rc == SQ_OK && s->profiling) {
+    SQ_CUDA(s->err, cudaStreamSynchronize(s->stream));
+    cudaEventElapsedTime(&s->phase_ms[4], s->ev[6], s->ev[7]);
+  }
+  return rc;
+}
+
+SQ_API int32_t sq_gather_column(sq_stream* s, int32_t side, int32_t build_col_id, const void* probe_values,
+                                uint32_t width, void* out, uint64_t capacity) {
+  if (!s) return SQ_EINVAL;
+  ErrorSlot& E = s->err;
+  const void* src = nullptr;
+  const uint32_t* ix = nullptr;
+  int rc = gather_source(s, side, build_col_id, &width, &src, &ix);
+  if (rc) return rc;
+  if (width != 4 && width != 8 && width != 16) return fail(E, SQ_EINVAL, "gather: unsupported value width %u", width);
+  if (capacity < s->n_pairs) return fail(E, SQ_ECAPACITY, "gather capacity %llu < %llu", (unsigned long long)capacity,
+                                         (unsigned long long)s->n_pairs);
+  if (s->n_pairs == 0) return SQ_OK;
+  if (!out) return fail(E, SQ_EINVAL, "null gather output");
+  SQ_CUDA(E, cudaSetDevice(s->ctx->device));
+  const size_t out_bytes = size_t(s->n_pairs) * width;
+  const size_t in_bytes = side == 1 ? size_t(s->n_rows) * width : 0;
+  if ((rc = ensure(E, s->d_gather, out_bytes + in_bytes + 32, false))) return rc;
+  char* d_out = static_cast<char*>(s->d_gather.p);
+  if (side == 1) {
+    if (!probe_values) return fail(E, SQ_EINVAL, "null probe column values");
+    char* d_src = d_out + ((out_bytes + 15) & ~size_t(15));
+    SQ_CUDA(E, cudaMemcpyAsync(d_src, probe_values, in_bytes, cudaMemcpyHostToDevice, s->stream));
+    src = d_src;
+  }
+  mark(s, 6);
+  if ((rc = launch_gather(s, src, ix, s->n_pairs, width, d_out))) return rc;
+  mark(s, 7);
+  SQ_CUDA(E, cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s->stream));
+  SQ_CUDA(E, cudaStreamSynchronize(s->stream));
+  if (s->profiling) cudaEventElapsedTime(&s->phase_ms[4], s->ev[6], s->ev[7]);
+  return SQ_OK;
+}
+
+// ---- boundary helpers -------------------------------------------------------------------------
+SQ_API int32_t sq_cast_i64_to_i32(sq_stream* s, const int64_t* values, uint64_t n, int64_t minus, int32_t* out) {
+  if (!s) return SQ_EINVAL;
+  ErrorSlot& E = s->err;
+  if (n && (!values || !out)) return fail(E, SQ_EINVAL, "null cast buffer");
+  if (n == 0) return SQ_OK;
+  SQ_CUDA(E, cudaSetDevice(s->ctx->device));
+  int rc;
+  if ((rc = ensure(E, s->d_gather, n * 12 + 32, false))) return rc;
+  auto* d_in = static_cast<int64_t*>(s->d_gather.p);
+  auto* d_out = reinterpret_cast<int32_t*>(d_in + n);
+  SQ_CUDA(E, cudaMemcpyAsync(d_in, values, n * 8, cudaMemcpyHostToDevice, s->stream));
+  int64_t bad_value = 0;
+  bool bad = false;
+  if ((rc = launch_cast_i64(s, d_in, n, minus, d_out, &bad_value, &bad))) return rc;
+  if (bad)  // exact text of the reference's failure (interval_join.rs:1959-1965)
+    return fail(E, SQ_ECAST, "Arrow error: Cast error: Can't cast value %lld to type Int32", (long long)bad_value);
+  SQ_CUDA(E, cudaMemcpyAsync(out, d_out, n * 4, cudaMemcpyDeviceToHost, s->stream));
+  SQ_CUDA(E, cudaStreamSynchronize(s->stream));
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_pairs_digest_device(sq_stream* s, const uint32_t* d_left, const uint32_t* d_right, uint64_t n_pairs,
+                                      uint64_t right_offset, uint64_t out3[3]) {
+  if (!s || !out3) return SQ_EINVAL;
+  if (n_pairs && (!d_left || !d_right)) return fail(s->err, SQ_EINVAL, "null pair buffer");
+  SQ_CUDA(s->err, cudaSetDevice(s->ctx->device));
+  return launch_digest(s, d_left, d_right, n_pairs, right_offset, out3);
+}

@@ -1,0 +1,350 @@
+// Build side of the `Cuda` interval join: replaces update_hashmap + IntervalJoinAlgorithm::new
+// (reference interval_join.rs:1023-1051 and :767-793) with a flat, tree-free index in HBM:
+//
+//   key hash --(device hash table)--> dense key id
+//   radix sort of (key id, start) carrying the build row
+//   per key segment: start[], end[], row[], runmax[] (running max of end inside the segment)
+//
+// A probe (qs, qe) against its key segment [sb, se) then has its hits inside the contiguous
+// candidate range [lo, hi):  hi = first j with start[j] >  qe  (all j < hi have start <= qe)
+//                            lo = first j with runmax[j] >= qs (the first row whose end >= qs)
+// and the hits are exactly the rows of [lo, hi) with end[j] >= qs — the same set coitrees'
+// pruned descent visits (nosimd.rs:343-384), for any input including inverted intervals.
+//
+// Kernels here are HBM-bound streaming passes; the sort is CUB's radix sort (library code, like
+// cuBLAS for a GEMM) restricted to the significant bits 32 + ceil(log2(#keys)).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "sq_internal.cuh"
+
+namespace sq {
+
+// ---------------------------------------------------------------------------------------------
+// Key hash -> dense id.  Open addressing, linear probing, capacity a power of two.  Genomic joins
+// have a few dozen keys (contigs), so after the first few warps every lookup is a read hit; only
+// the first occurrence of a key does an atomicCAS.  Lanes holding the same key elect one leader.
+// ---------------------------------------------------------------------------------------------
+struct HtStatus {
+  unsigned int distinct;
+  unsigned int overflow;
+  unsigned int has_sentinel;
+  unsigned int pad;
+};
+
+__global__ void __launch_bounds__(256) k_ht_insert(const uint64_t* __restrict__ keys, uint64_t n,
+                                                   uint64_t* __restrict__ ht_keys, uint32_t mask,
+                                                   HtStatus* st) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  // warp-uniform trip count so that the whole warp reaches the ballot together
+  const uint64_t first = uint64_t(blockIdx.x) * blockDim.x + (threadIdx.x & ~31u);
+  for (uint64_t i0 = first; i0 < n; i0 += stride) {
+    const uint64_t i = i0 + (threadIdx.x & 31);
+    const bool valid = i < n;
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    if (!valid) continue;
+    const uint64_t key = keys[i];
+    // one lane per distinct key in the warp does the table work
+    const unsigned peers = __match_any_sync(vmask, key);
+    if ((__ffs(peers) - 1) != int(threadIdx.x & 31)) continue;
+    if (key == kEmptyKey) { st->has_sentinel = 1; continue; }
+    uint32_t slot = uint32_t(mix64(key)) & mask;
+    for (uint32_t step = 0; step <= mask; ++step) {
+      uint64_t cur = *reinterpret_cast<volatile uint64_t*>(ht_keys + slot);
+      if (cur == key) break;
+      if (cur == kEmptyKey) {
+        const uint64_t old = atomicCAS(reinterpret_cast<unsigned long long*>(ht_keys + slot),
+                                       (unsigned long long)kEmptyKey, (unsigned long long)key);
+        if (old == kEmptyKey) {
+          const unsigned d = atomicAdd(&st->distinct, 1u) + 1u;
+          if (d > (mask + 1u) / 2u) st->overflow = 1;  // keep load factor <= 1/2
+          break;
+        }
+        if (old == key) break;
+      }
+      slot = (slot + 1) & mask;
+      if (step == mask) st->overflow = 1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ht_assign(const uint64_t* __restrict__ ht_keys,
+                                                   uint32_t* __restrict__ ht_ids, uint32_t cap,
+                                                   unsigned int* counter) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= cap) return;
+  ht_ids[slot] = (ht_keys[slot] != kEmptyKey) ? atomicAdd(counter, 1u) : kNoKey;
+}
+
+// sort key = (key id << 32) | (start with the sign bit flipped), value = build row
+__global__ void __launch_bounds__(256) k_make_sort_keys(const uint64_t* __restrict__ keys,
+                                                        const int32_t* __restrict__ start, uint64_t n,
+                                                        const uint64_t* __restrict__ ht_keys,
+                                                        const uint32_t* __restrict__ ht_ids,
+                                                        uint32_t mask, uint32_t sentinel_id,
+                                                        uint64_t* __restrict__ sort_key,
+                                                        uint32_t* __restrict__ sort_val) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t id = ht_lookup(ht_keys, ht_ids, mask, sentinel_id, keys[i]);
+    sort_key[i] = (uint64_t(id) << 32) | uint64_t(uint32_t(start[i]) ^ 0x80000000u);
+    sort_val[i] = uint32_t(i);
+  }
+}
+
+// After the sort: write start[], row[], end[] (gathered through the permutation) and the segment
+// boundaries seg_off[id] = first sorted position of key id.
+__global__ void __launch_bounds__(256) k_finalize(const uint64_t* __restrict__ sorted_key,
+                                                  const uint32_t* __restrict__ perm,
+                                                  const int32_t* __restrict__ end_in, uint64_t n,
+                                                  int32_t* __restrict__ s_start,
+                                                  int32_t* __restrict__ s_end,
+                                                  uint32_t* __restrict__ s_row,
+                                                  uint32_t* __restrict__ seg_off, uint32_t n_keys) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const uint64_t k = sorted_key[j];
+    const uint32_t r = perm[j];
+    s_start[j] = int32_t(uint32_t(k) ^ 0x80000000u);
+    s_row[j] = r;
+    s_end[j] = __ldg(end_in + r);
+    const uint32_t id = uint32_t(k >> 32);
+    if (j == 0 || uint32_t(sorted_key[j - 1] >> 32) != id) seg_off[id] = uint32_t(j);
+    if (j == n - 1) seg_off[n_keys] = uint32_t(n);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Segmented running max of end[] as ONE plain prefix-max over u64 words (id << 32 | end'):
+// key ids are non-decreasing along the sorted array, so a later segment's words dominate every
+// earlier one and the low half of the prefix max is the running max inside the current segment.
+// Reduce-then-scan: per-tile max, one-CTA exclusive scan of tile maxima, per-tile rescan.
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint64_t scan_word(const uint64_t* __restrict__ sorted_key,
+                                              const int32_t* __restrict__ s_end, uint64_t j) {
+  return (sorted_key[j] & 0xFFFFFFFF00000000ull) | uint64_t(uint32_t(s_end[j]) ^ 0x80000000u);
+}
+
+__device__ __forceinline__ uint64_t warp_incl_max(uint64_t v) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint64_t o = __shfl_up_sync(0xffffffffu, v, d);
+    if (int(threadIdx.x & 31) >= d) v = max(v, o);
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_runmax_reduce(const uint64_t* __restrict__ sorted_key,
+                                                                const int32_t* __restrict__ s_end,
+                                                                uint64_t n, uint64_t* __restrict__ tile_max) {
+  __shared__ uint64_t wmax[kScanThreads / 32];
+  const uint64_t base = uint64_t(blockIdx.x) * kScanTile;
+  uint64_t m = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const uint64_t j = base + uint64_t(k) * kScanThreads + threadIdx.x;
+    if (j < n) m = max(m, scan_word(sorted_key, s_end, j));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t r = 0;
+    for (int w = 0; w < kScanThreads / 32; ++w) r = max(r, wmax[w]);
+    tile_max[blockIdx.x] = r;
+  }
+}
+
+// exclusive prefix max over tile_max[0..n_tiles), in place, one CTA of 1024 threads
+__global__ void __launch_bounds__(1024) k_runmax_mid(uint64_t* __restrict__ tile_max, uint32_t n_tiles) {
+  __shared__ uint64_t wsum[32];
+  __shared__ uint64_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_tiles; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint64_t v = i < n_tiles ? tile_max[i] : 0;
+    uint64_t inc = warp_incl_max(v);
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint64_t w = wsum[threadIdx.x];
+      w = warp_incl_max(w);
+      wsum[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const uint64_t carry = carry_s;
+    const uint64_t wprev = (threadIdx.x >> 5) ? wsum[(threadIdx.x >> 5) - 1] : 0;
+    const uint64_t prev_in_warp = __shfl_up_sync(0xffffffffu, inc, 1);
+    uint64_t excl = max(carry, wprev);
+    if (threadIdx.x & 31) excl = max(excl, prev_in_warp);
+    if (i < n_tiles) tile_max[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = max(carry, max(wprev, inc));
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_runmax_final(const uint64_t* __restrict__ sorted_key,
+                                                               const int32_t* __restrict__ s_end,
+                                                               uint64_t n,
+                                                               const uint64_t* __restrict__ tile_excl,
+                                                               int32_t* __restrict__ runmax) {
+  __shared__ uint64_t wtot[kScanThreads / 32];
+  const uint64_t base = uint64_t(blockIdx.x) * kScanTile;
+  uint64_t carry = tile_excl[blockIdx.x];
+  // blocked over k: each pass scans kScanThreads consecutive rows, carry moves to the next pass
+#pragma unroll 1
+  for (int k = 0; k < kScanItems; ++k) {
+    const uint64_t j = base + uint64_t(k) * kScanThreads + threadIdx.x;
+    const uint64_t v = j < n ? scan_word(sorted_key, s_end, j) : 0;
+    uint64_t inc = warp_incl_max(v);
+    if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    uint64_t pre = carry;
+    for (int w = 0; w < int(threadIdx.x >> 5); ++w) pre = max(pre, wtot[w]);
+    inc = max(inc, pre);
+    if (j < n) runmax[j] = int32_t(uint32_t(inc) ^ 0x80000000u);
+    uint64_t tot = carry;
+    for (int w = 0; w < kScanThreads / 32; ++w) tot = max(tot, wtot[w]);
+    carry = tot;
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+static inline int grid_for(uint64_t n, int threads, int sm_count, int per_sm = 8) {
+  const uint64_t want = (n + threads - 1) / threads;
+  const uint64_t cap = uint64_t(sm_count) * per_sm;  // grid-stride kernels: a few CTAs per SM
+  return int(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+void free_index(sq_index* idx) {
+  if (!idx) return;
+  cudaSetDevice(idx->ctx->device);
+  cudaFree(idx->d_start); cudaFree(idx->d_end); cudaFree(idx->d_runmax); cudaFree(idx->d_row);
+  cudaFree(idx->d_seg_off); cudaFree(idx->d_ht_keys); cudaFree(idx->d_ht_ids);
+  for (auto& c : idx->columns) if (c.owned) cudaFree(c.d_values);
+  delete idx;
+}
+
+struct TmpFree {
+  std::vector<void*> ptrs;
+  ~TmpFree() { for (void* p : ptrs) cudaFree(p); }
+  template <class T> cudaError_t alloc(T** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), bytes ? bytes : 16);
+    if (e == cudaSuccess) ptrs.push_back(*p);
+    return e;
+  }
+};
+
+int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_start, const int32_t* d_end,
+                       uint64_t n, cudaStream_t st, sq_index** out) {
+  ErrorSlot& E = ctx->err;
+  if (n >= 0xFFFFFFFFull)
+    return fail(E, SQ_EINVAL, "build side has %llu rows; the interval join addresses rows as u32 "
+                "(reference interval_join.rs:1590)", (unsigned long long)n);
+  SQ_CUDA(E, cudaSetDevice(ctx->device));
+  sq_index* idx = new sq_index();
+  idx->ctx = ctx;
+  idx->n_rows = n;
+  struct Guard { sq_index* p; ~Guard() { if (p) free_index(p); } } guard{idx};
+  TmpFree tmp;
+
+  cudaEvent_t e0, e1;
+  SQ_CUDA(E, cudaEventCreate(&e0));
+  SQ_CUDA(E, cudaEventCreate(&e1));
+  struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{e0, e1};
+  SQ_CUDA(E, cudaEventRecord(e0, st));
+
+  // 1. key hash table (grow until the load factor fits)
+  HtStatus* d_status = nullptr;
+  SQ_CUDA(E, tmp.alloc(&d_status, sizeof(HtStatus) + sizeof(unsigned int) * 4));
+  unsigned int* d_counter = reinterpret_cast<unsigned int*>(d_status + 1);
+  uint32_t cap = 4096;
+  HtStatus hs{};
+  for (;;) {
+    SQ_CUDA(E, cudaMalloc(&idx->d_ht_keys, size_t(cap) * 8));
+    SQ_CUDA(E, cudaMemsetAsync(idx->d_ht_keys, 0xFF, size_t(cap) * 8, st));
+    SQ_CUDA(E, cudaMemsetAsync(d_status, 0, sizeof(HtStatus) + 16, st));
+    if (n) {
+      k_ht_insert<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(d_key, n, idx->d_ht_keys, cap - 1, d_status);
+      SQ_CUDA(E, cudaGetLastError());
+    }
+    SQ_CUDA(E, cudaMemcpyAsync(&hs, d_status, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    SQ_CUDA(E, cudaStreamSynchronize(st));
+    if (!hs.overflow) break;
+    cudaFree(idx->d_ht_keys);
+    idx->d_ht_keys = nullptr;
+    // distinct keys <= n, so a table of >= 2n+2 slots can never overflow
+    uint64_t max_cap = 4096;
+    while (max_cap < 2 * n + 2) max_cap <<= 1;
+    if (cap >= max_cap) return fail(E, SQ_ECUDA, "key hash table overflow at full capacity");
+    cap = uint32_t(uint64_t(cap) * 16 > max_cap ? max_cap : uint64_t(cap) * 16);
+  }
+  idx->ht_cap = cap;
+  SQ_CUDA(E, cudaMalloc(&idx->d_ht_ids, size_t(cap) * 4));
+  k_ht_assign<<<(cap + 255) / 256, 256, 0, st>>>(idx->d_ht_keys, idx->d_ht_ids, cap, d_counter);
+  SQ_CUDA(E, cudaGetLastError());
+  uint32_t n_keys = hs.distinct;
+  if (hs.has_sentinel) idx->sentinel_id = n_keys++;
+  idx->n_keys = n_keys;
+
+  // 2. sorted arrays
+  SQ_CUDA(E, cudaMalloc(&idx->d_start, (n ? n : 1) * 4));
+  SQ_CUDA(E, cudaMalloc(&idx->d_end, (n ? n : 1) * 4));
+  SQ_CUDA(E, cudaMalloc(&idx->d_runmax, (n ? n : 1) * 4));
+  SQ_CUDA(E, cudaMalloc(&idx->d_row, (n ? n : 1) * 4));
+  SQ_CUDA(E, cudaMalloc(&idx->d_seg_off, (size_t(n_keys) + 1) * 4));
+  SQ_CUDA(E, cudaMemsetAsync(idx->d_seg_off, 0, (size_t(n_keys) + 1) * 4, st));
+  idx->bytes = uint64_t(n ? n : 1) * 16 + (uint64_t(n_keys) + 1) * 4 + uint64_t(cap) * 12;
+
+  if (n) {
+    uint64_t *d_k0 = nullptr, *d_k1 = nullptr;
+    uint32_t *d_v0 = nullptr, *d_v1 = nullptr;
+    SQ_CUDA(E, tmp.alloc(&d_k0, n * 8));
+    SQ_CUDA(E, tmp.alloc(&d_k1, n * 8));
+    SQ_CUDA(E, tmp.alloc(&d_v0, n * 4));
+    SQ_CUDA(E, tmp.alloc(&d_v1, n * 4));
+    const int g = grid_for(n, 256, ctx->sm_count);
+    k_make_sort_keys<<<g, 256, 0, st>>>(d_key, d_start, n, idx->d_ht_keys, idx->d_ht_ids, cap - 1,
+                                        idx->sentinel_id, d_k0, d_v0);
+    SQ_CUDA(E, cudaGetLastError());
+
+    int key_bits = 0;
+    while ((1ull << key_bits) < uint64_t(n_keys)) ++key_bits;
+    const int end_bit = 32 + key_bits;
+    size_t temp_bytes = 0;
+    SQ_CUDA(E, ::sq_cub::cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_k0, d_k1, d_v0, d_v1, n, 0, end_bit, st));
+    void* d_temp = nullptr;
+    SQ_CUDA(E, tmp.alloc(&d_temp, temp_bytes));
+    SQ_CUDA(E, ::sq_cub::cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_k0, d_k1, d_v0, d_v1, n, 0, end_bit, st));
+
+    k_finalize<<<g, 256, 0, st>>>(d_k1, d_v1, d_end, n, idx->d_start, idx->d_end, idx->d_row,
+                                  idx->d_seg_off, n_keys);
+    SQ_CUDA(E, cudaGetLastError());
+
+    // 3. running max of end inside each key segment
+    const uint32_t n_tiles = uint32_t((n + kScanTile - 1) / kScanTile);
+    uint64_t* d_tile = nullptr;
+    SQ_CUDA(E, tmp.alloc(&d_tile, size_t(n_tiles) * 8));
+    k_runmax_reduce<<<n_tiles, kScanThreads, 0, st>>>(d_k1, idx->d_end, n, d_tile);
+    SQ_CUDA(E, cudaGetLastError());
+    k_runmax_mid<<<1, 1024, 0, st>>>(d_tile, n_tiles);
+    SQ_CUDA(E, cudaGetLastError());
+    k_runmax_final<<<n_tiles, kScanThreads, 0, st>>>(d_k1, idx->d_end, n, d_tile, idx->d_runmax);
+    SQ_CUDA(E, cudaGetLastError());
+  }
+  SQ_CUDA(E, cudaEventRecord(e1, st));
+  SQ_CUDA(E, cudaStreamSynchronize(st));
+  SQ_CUDA(E, cudaEventElapsedTime(&idx->build_ms, e0, e1));
+  guard.p = nullptr;
+  *out = idx;
+  return SQ_OK;
+}
+
+}  // namespace sq

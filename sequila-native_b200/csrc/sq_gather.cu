@@ -1,0 +1,153 @@
+// Materialise / boundary helper kernels of the `Cuda` interval join.
+//
+//   k_gather<T>      arrow::compute::take of one fixed-width column (interval_join.rs:1620-1632):
+//                    out[k] = values[idx[k]].  Right-side indices are non-decreasing (runs), left-side
+//                    indices are random into the build column: HBM/L2-bound gather, 4 elements per
+//                    thread in flight.
+//   k_cast_i64       evaluate_as_i32 for BIGINT columns (interval_join.rs:1661-1672) with the optional
+//                    `- 1` of strict comparisons (intervals.rs:67-69); reports the first row that does
+//                    not fit Int32 so the host can reproduce the reference's error text.
+//   k_pairs_digest   order-independent multiset digest of emitted pairs (test/bench parity at scale).
+#include "sq_internal.cuh"
+
+namespace sq {
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_gather(const T* __restrict__ values, const uint32_t* __restrict__ idx,
+                                                uint64_t n, T* __restrict__ out) {
+  constexpr int kPer = 4;
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x * kPer;
+  for (uint64_t base = (uint64_t(blockIdx.x) * blockDim.x) * kPer + threadIdx.x; base < n; base += stride) {
+    uint32_t ix[kPer];
+    T v[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const uint64_t i = base + uint64_t(k) * blockDim.x;
+      ix[k] = i < n ? __ldg(idx + i) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const uint64_t i = base + uint64_t(k) * blockDim.x;
+      if (i < n) v[k] = __ldg(values + ix[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const uint64_t i = base + uint64_t(k) * blockDim.x;
+      if (i < n) out[i] = v[k];
+    }
+  }
+}
+
+static inline int grid_for(uint64_t n, int per_block, int sm_count) {
+  const uint64_t want = (n + per_block - 1) / per_block;
+  const uint64_t cap = uint64_t(sm_count) * 16;
+  return int(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+int launch_gather(sq_stream* s, const void* d_values, const uint32_t* d_idx, uint64_t n, uint32_t width,
+                  void* d_out) {
+  if (n == 0) return SQ_OK;
+  const int g = grid_for(n, 256 * 4, s->ctx->sm_count);
+  switch (width) {
+    case 4:
+      k_gather<uint32_t><<<g, 256, 0, s->stream>>>(static_cast<const uint32_t*>(d_values), d_idx, n,
+                                                   static_cast<uint32_t*>(d_out));
+      break;
+    case 8:
+      k_gather<uint64_t><<<g, 256, 0, s->stream>>>(static_cast<const uint64_t*>(d_values), d_idx, n,
+                                                   static_cast<uint64_t*>(d_out));
+      break;
+    case 16:
+      k_gather<uint4><<<g, 256, 0, s->stream>>>(static_cast<const uint4*>(d_values), d_idx, n,
+                                                static_cast<uint4*>(d_out));
+      break;
+    default:
+      return fail(s->err, SQ_EINVAL, "gather: unsupported value width %u (4, 8 or 16)", width);
+  }
+  SQ_CUDA(s->err, cudaGetLastError());
+  s->launches += 1;
+  return SQ_OK;
+}
+
+// slot[0] = smallest row index whose value does not fit Int32 (UINT64_MAX when none)
+__global__ void __launch_bounds__(256) k_cast_i64(const int64_t* __restrict__ in, uint64_t n, int64_t minus,
+                                                  int32_t* __restrict__ out, unsigned long long* slot) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t v = int64_t(uint64_t(in[i]) - uint64_t(minus));
+    if (v < int64_t(INT32_MIN) || v > int64_t(INT32_MAX)) atomicMin(slot, (unsigned long long)i);
+    out[i] = int32_t(v);
+  }
+}
+
+int launch_cast_i64(sq_stream* s, const int64_t* d_in, uint64_t n, int64_t minus, int32_t* d_out,
+                    int64_t* bad_value, bool* bad) {
+  ErrorSlot& E = s->err;
+  *bad = false;
+  if (n == 0) return SQ_OK;
+  int rc;
+  if ((rc = ensure(E, s->d_scalar, 256, false))) return rc;
+  if ((rc = ensure(E, s->h_scalar, 256, true))) return rc;
+  auto* slot = reinterpret_cast<unsigned long long*>(static_cast<char*>(s->d_scalar.p) + 64);
+  SQ_CUDA(E, cudaMemsetAsync(slot, 0xFF, 8, s->stream));
+  k_cast_i64<<<grid_for(n, 256, s->ctx->sm_count), 256, 0, s->stream>>>(d_in, n, minus, d_out, slot);
+  SQ_CUDA(E, cudaGetLastError());
+  s->launches += 1;
+  auto* h = static_cast<unsigned long long*>(s->h_scalar.p);
+  SQ_CUDA(E, cudaMemcpyAsync(h, slot, 8, cudaMemcpyDeviceToHost, s->stream));
+  SQ_CUDA(E, cudaStreamSynchronize(s->stream));
+  if (h[0] != ~0ull) {
+    int64_t raw = 0;
+    SQ_CUDA(E, cudaMemcpy(&raw, d_in + h[0], 8, cudaMemcpyDeviceToHost));
+    *bad_value = int64_t(uint64_t(raw) - uint64_t(minus));
+    *bad = true;
+  }
+  return SQ_OK;
+}
+
+__global__ void __launch_bounds__(256) k_pairs_digest(const uint32_t* __restrict__ left,
+                                                      const uint32_t* __restrict__ right, uint64_t n,
+                                                      uint64_t right_offset, unsigned long long* out2) {
+  uint64_t sum = 0, x = 0;
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t r = (uint64_t(right[i]) + right_offset) & 0xFFFFFFFFull;
+    const uint64_t h = mix64((uint64_t(left[i]) << 32) | r);
+    sum += h;
+    x ^= h;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    x ^= __shfl_xor_sync(0xffffffffu, x, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out2, (unsigned long long)sum);
+    atomicXor(out2 + 1, (unsigned long long)x);
+  }
+}
+
+int launch_digest(sq_stream* s, const uint32_t* d_left, const uint32_t* d_right, uint64_t n,
+                  uint64_t right_offset, uint64_t out3[3]) {
+  ErrorSlot& E = s->err;
+  int rc;
+  if ((rc = ensure(E, s->d_scalar, 256, false))) return rc;
+  if ((rc = ensure(E, s->h_scalar, 256, true))) return rc;
+  auto* slot = reinterpret_cast<unsigned long long*>(static_cast<char*>(s->d_scalar.p) + 128);
+  SQ_CUDA(E, cudaMemsetAsync(slot, 0, 16, s->stream));
+  if (n) {
+    k_pairs_digest<<<grid_for(n, 256 * 8, s->ctx->sm_count), 256, 0, s->stream>>>(d_left, d_right, n,
+                                                                                  right_offset, slot);
+    SQ_CUDA(E, cudaGetLastError());
+    s->launches += 1;
+  }
+  auto* h = static_cast<unsigned long long*>(s->h_scalar.p) + 8;
+  SQ_CUDA(E, cudaMemcpyAsync(h, slot, 16, cudaMemcpyDeviceToHost, s->stream));
+  SQ_CUDA(E, cudaStreamSynchronize(s->stream));
+  out3[0] = n;
+  out3[1] = h[0];
+  out3[2] = h[1];
+  return SQ_OK;
+}
+
+}  // namespace sq

@@ -1,0 +1,183 @@
+// Internal declarations shared by the translation units of libsequila_cuda.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "sequila_cuda.h"
+
+namespace sq {
+
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;  // hash-table sentinel (handled out of band)
+constexpr uint32_t kNoKey = 0xFFFFFFFFu;               // probe key hash absent from the build side
+constexpr int kProbeBlock = 256;                       // threads per probe CTA = probe rows per CTA
+constexpr int kWarpsPerBlock = kProbeBlock / 32;
+
+// 64-bit finalizer used for the key hash table and the pair digest.
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  x ^= x >> 31; return x;
+}
+
+// Flat, tree-free build index in HBM (SoA, all arrays length n_rows, sorted by (key id, start)).
+struct IndexView {
+  const int32_t* __restrict__ start;    // sorted starts
+  const int32_t* __restrict__ end;      // end of the same row
+  const int32_t* __restrict__ runmax;   // running max of `end` inside the key segment
+  const uint32_t* __restrict__ row;     // original build row (left index)
+  const uint32_t* __restrict__ seg_off; // [n_keys + 1] segment boundaries
+  const uint64_t* __restrict__ ht_keys; // open-addressing table of key hashes
+  const uint32_t* __restrict__ ht_ids;  // slot -> dense key id
+  uint32_t ht_mask;                     // capacity - 1
+  uint32_t sentinel_id;                 // id of the key hash equal to kEmptyKey, or kNoKey
+  uint32_t n_keys;
+  uint32_t n_rows;
+};
+
+#ifdef __CUDACC__
+// key hash -> dense key id; kNoKey when the hash never occurred on the build side (IJ:965)
+__device__ __forceinline__ uint32_t ht_lookup(const uint64_t* __restrict__ ht_keys,
+                                              const uint32_t* __restrict__ ht_ids, uint32_t mask,
+                                              uint32_t sentinel_id, uint64_t key) {
+  if (key == kEmptyKey) return sentinel_id;
+  uint32_t slot = uint32_t(mix64(key)) & mask;
+  for (uint32_t step = 0; step <= mask; ++step) {
+    const uint64_t cur = __ldg(ht_keys + slot);
+    if (cur == key) return __ldg(ht_ids + slot);
+    if (cur == kEmptyKey) return kNoKey;
+    slot = (slot + 1) & mask;
+  }
+  return kNoKey;
+}
+#endif
+
+struct ErrorSlot {
+  mutable std::mutex mu;
+  std::string msg;
+  void set(const std::string& m) { std::lock_guard<std::mutex> g(mu); msg = m; }
+};
+
+}  // namespace sq
+
+struct sq_ctx {
+  int device = 0;
+  int sm_count = 148;
+  sq::ErrorSlot err;
+};
+
+struct sq_column {
+  void* d_values = nullptr;
+  uint32_t width = 0;
+  bool owned = false;
+};
+
+struct sq_index {
+  sq_ctx* ctx = nullptr;
+  uint64_t n_rows = 0;
+  uint32_t n_keys = 0;
+  // device arrays
+  int32_t* d_start = nullptr;
+  int32_t* d_end = nullptr;
+  int32_t* d_runmax = nullptr;
+  uint32_t* d_row = nullptr;
+  uint32_t* d_seg_off = nullptr;
+  uint64_t* d_ht_keys = nullptr;
+  uint32_t* d_ht_ids = nullptr;
+  uint32_t ht_cap = 0;
+  uint32_t sentinel_id = sq::kNoKey;
+  uint64_t bytes = 0;
+  float build_ms = 0.f;
+  std::mutex col_mu;
+  std::vector<sq_column> columns;
+
+  sq::IndexView view() const {
+    sq::IndexView v;
+    v.start = d_start; v.end = d_end; v.runmax = d_runmax; v.row = d_row; v.seg_off = d_seg_off;
+    v.ht_keys = d_ht_keys; v.ht_ids = d_ht_ids; v.ht_mask = ht_cap - 1; v.sentinel_id = sentinel_id;
+    v.n_keys = n_keys; v.n_rows = uint32_t(n_rows);
+    return v;
+  }
+};
+
+// Grow-only buffer (device or pinned host).
+struct sq_buf {
+  void* p = nullptr;
+  size_t cap = 0;
+  bool pinned = false;
+};
+
+struct sq_stream {
+  sq_ctx* ctx = nullptr;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  sq::ErrorSlot err;
+
+  // state of the tile currently between count and emit
+  const sq_index* idx = nullptr;
+  uint32_t n_rows = 0;
+  uint64_t n_pairs = 0;
+  bool counted = false;
+  bool emitted = false;
+  const int32_t* d_q_start = nullptr;  // probe starts of the tile (device)
+  const uint32_t* d_last_left = nullptr;
+  const uint32_t* d_last_right = nullptr;
+
+  // device scratch
+  sq_buf d_in;       // staged probe key/start/end (host entry points)
+  sq_buf d_lo;       // first candidate per probe row
+  sq_buf d_ncand;    // candidate count per probe row
+  sq_buf d_cnt;      // hit count per probe row
+  sq_buf d_tile;     // per-CTA look-back words + bases
+  sq_buf d_scalar;   // n_pairs, ticket counter, cast-error slot, digest
+  sq_buf d_left, d_right;  // emitted pairs (host entry points)
+  sq_buf d_gather;   // gather staging
+  // pinned staging
+  sq_buf h_in, h_out, h_scalar;
+
+  // profiling
+  bool profiling = false;
+  cudaEvent_t ev[8] = {};
+  bool ev_ready = false;
+  float phase_ms[5] = {0, 0, 0, 0, 0};
+  uint64_t launches = 0;
+};
+
+namespace sq {
+
+// error helpers ---------------------------------------------------------------------------
+int fail(ErrorSlot& e, int code, const char* fmt, ...);
+#define SQ_CUDA(slot, expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return sq::fail((slot), _e == cudaErrorMemoryAllocation ? SQ_ENOMEM : SQ_ECUDA,        \
+                      "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+int ensure(ErrorSlot& e, sq_buf& b, size_t bytes, bool pinned);
+void release(sq_buf& b);
+
+// build.cu
+int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_start, const int32_t* d_end,
+                       uint64_t n, cudaStream_t st, sq_index** out);
+void free_index(sq_index* idx);
+
+// probe.cu
+int launch_count(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
+                 const int32_t* d_end, uint32_t n);
+int launch_write(sq_stream* s, uint32_t* d_left, uint32_t* d_right);
+
+// gather.cu
+int launch_gather(sq_stream* s, const void* d_values, const uint32_t* d_idx, uint64_t n, uint32_t width,
+                  void* d_out);
+int launch_cast_i64(sq_stream* s, const int64_t* d_in, uint64_t n, int64_t minus, int32_t* d_out,
+                    int64_t* bad_value, bool* bad);
+int launch_digest(sq_stream* s, const uint32_t* d_left, const uint32_t* d_right, uint64_t n,
+                  uint64_t right_offset, uint64_t out3[3]);
+
+}  // namespace sq

@@ -1,0 +1,241 @@
+"""Thin object layer over the C ABI (include/sequila_cuda.h).
+
+Mirrors the two halves of the reference's private seam `IntervalJoinAlgorithm`
+(interval_join.rs:767 `new`, :957 `get`) at batch granularity:
+
+* :class:`CudaIndex`   = `IntervalJoinAlgorithm::new(&Algorithm::Cuda, hashmap)` — built once per
+  query from the concatenated build side (interval_join.rs:662-685);
+* :class:`CudaStream`  = what one `IntervalJoinStream` (one per partition, :528-556) calls per probe
+  batch instead of the `get` loop (:1586-1618).
+
+numpy arrays go through the host entry points (H2D/D2H inside the call); torch CUDA tensors go
+through the ``*_device`` entry points (kernel-level benchmark).  Nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _native as N
+
+
+def _check(rc: int, msg_fn):
+    if rc != N.SQ_OK:
+        msg = msg_fn()
+        raise N.SequilaCudaError(rc, msg.decode() if isinstance(msg, bytes) else str(msg))
+
+
+def _np(a, dtype):
+    a = np.asarray(a)
+    if a.dtype != dtype or not a.flags.c_contiguous:
+        a = np.ascontiguousarray(a, dtype=dtype)
+    return a
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a.size else C.c_void_p(0)
+
+
+def _tptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None and t.numel() else C.c_void_p(0)
+
+
+class CudaContext:
+    """sq_ctx: one per (process, device).  Raises if no CUDA device is usable (no CPU fallback)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = N.lib()
+        h = C.c_void_p()
+        rc = self._lib.sq_ctx_create(int(device), C.byref(h))
+        if rc != N.SQ_OK:
+            raise N.SequilaCudaError(rc, self._lib.sq_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+        self._fin = weakref.finalize(self, self._lib.sq_ctx_destroy, h)
+
+    def _err(self):
+        return self._lib.sq_last_error(self._h)
+
+    def pinned_empty(self, n: int, dtype) -> np.ndarray:
+        """numpy array in pinned host memory (sq_host_alloc); full-speed async copies."""
+        dtype = np.dtype(dtype)
+        nbytes = max(int(n) * dtype.itemsize, 1)
+        p = C.c_void_p()
+        _check(self._lib.sq_host_alloc(self._h, nbytes, C.byref(p)), self._err)
+        buf = (C.c_char * nbytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(n))
+        weakref.finalize(buf, self._lib.sq_host_free, self._h, p)
+        return arr
+
+    def pinned_copy(self, a) -> np.ndarray:
+        a = np.asarray(a)
+        out = self.pinned_empty(a.size, a.dtype)
+        out[...] = a.reshape(-1)
+        return out
+
+
+class CudaIndex:
+    """sq_index: the flat build-side index (sorted starts + running max end per key segment)."""
+
+    def __init__(self, ctx: CudaContext, handle, keep=None):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        self._h = handle
+        self._keep = keep  # device tensors borrowed by add_column_device
+        self._fin = weakref.finalize(self, self._lib.sq_index_free, handle)
+
+    @classmethod
+    def build(cls, ctx: CudaContext, key_hash, start, end) -> "CudaIndex":
+        k, s, e = _np(key_hash, np.uint64), _np(start, np.int32), _np(end, np.int32)
+        if not (k.shape == s.shape == e.shape and k.ndim == 1):
+            raise ValueError("key_hash/start/end must be 1-d arrays of equal length")
+        h = C.c_void_p()
+        _check(ctx._lib.sq_index_build(ctx._h, _ptr(k), _ptr(s), _ptr(e), k.shape[0], C.byref(h)), ctx._err)
+        return cls(ctx, h)
+
+    @classmethod
+    def build_device(cls, ctx: CudaContext, key_hash, start, end, cuda_stream: int = 0) -> "CudaIndex":
+        import torch
+        assert key_hash.dtype == torch.int64 or key_hash.dtype == torch.uint64
+        assert start.dtype == torch.int32 and end.dtype == torch.int32
+        assert key_hash.is_cuda and start.is_cuda and end.is_cuda
+        h = C.c_void_p()
+        _check(ctx._lib.sq_index_build_device(ctx._h, _tptr(key_hash), _tptr(start), _tptr(end),
+                                              key_hash.numel(), C.c_void_p(cuda_stream), C.byref(h)), ctx._err)
+        return cls(ctx, h)
+
+    def add_column(self, values) -> int:
+        v = np.ascontiguousarray(values)
+        if v.shape[0] != self.rows:
+            raise ValueError("column length differs from the build side")
+        width = v.dtype.itemsize if v.ndim == 1 else v.dtype.itemsize * int(np.prod(v.shape[1:]))
+        cid = C.c_int32(-1)
+        _check(self._lib.sq_index_add_column(self._h, _ptr(v), width, C.byref(cid)), self.ctx._err)
+        return int(cid.value)
+
+    def add_column_device(self, tensor) -> int:
+        cid = C.c_int32(-1)
+        _check(self._lib.sq_index_add_column_device(self._h, _tptr(tensor), tensor.element_size(), C.byref(cid)),
+               self.ctx._err)
+        self._keep = (self._keep or []) + [tensor]
+        return int(cid.value)
+
+    bytes = property(lambda self: int(self._lib.sq_index_bytes(self._h)))
+    rows = property(lambda self: int(self._lib.sq_index_rows(self._h)))
+    keys = property(lambda self: int(self._lib.sq_index_keys(self._h)))
+    build_ms = property(lambda self: float(self._lib.sq_index_build_ms(self._h)))
+
+
+class CudaStream:
+    """sq_stream: per-partition probe context (CUDA stream + staging + scratch)."""
+
+    def __init__(self, ctx: CudaContext, cuda_stream: int | None = None):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        h = C.c_void_p()
+        if cuda_stream is None:
+            _check(self._lib.sq_stream_create(ctx._h, C.byref(h)), ctx._err)
+        else:
+            _check(self._lib.sq_stream_create_on(ctx._h, C.c_void_p(cuda_stream), C.byref(h)), ctx._err)
+        self._h = h
+        self._fin = weakref.finalize(self, self._lib.sq_stream_free, h)
+        self.n_rows = 0
+        self.n_pairs = 0
+        self._keep = None
+
+    def _err(self):
+        return self._lib.sq_stream_last_error(self._h)
+
+    # ---- host (numpy) entry points: what the DataFusion exec node would call ----------------
+    def probe_count(self, index: CudaIndex, key_hash, start, end) -> int:
+        k, s, e = _np(key_hash, np.uint64), _np(start, np.int32), _np(end, np.int32)
+        if not (k.shape == s.shape == e.shape and k.ndim == 1):
+            raise ValueError("key_hash/start/end must be 1-d arrays of equal length")
+        n = C.c_uint64(0)
+        _check(self._lib.sq_probe_count(self._h, index._h, _ptr(k), _ptr(s), _ptr(e), k.shape[0], C.byref(n)),
+               self._err)
+        self._keep = index
+        self.n_rows, self.n_pairs = int(k.shape[0]), int(n.value)
+        return self.n_pairs
+
+    def emit_pairs(self, right: bool = True, counts: bool = True, out=None):
+        """-> (left_idx, right_idx | None, counts | None) as numpy uint32 arrays."""
+        if out is not None:
+            left, r, c = out
+        else:
+            left = np.empty(self.n_pairs, dtype=np.uint32)
+            r = np.empty(self.n_pairs, dtype=np.uint32) if right else None
+            c = np.empty(self.n_rows, dtype=np.uint32) if counts else None
+        _check(self._lib.sq_probe_emit_pairs(self._h, _ptr(left), _ptr(r) if r is not None else None,
+                                             _ptr(c) if c is not None else None, left.shape[0]), self._err)
+        return left[:self.n_pairs], (r[:self.n_pairs] if r is not None else None), c
+
+    def probe(self, index: CudaIndex, key_hash, start, end):
+        self.probe_count(index, key_hash, start, end)
+        return self.emit_pairs()
+
+    def gather_build(self, col_id: int, dtype, width: int | None = None) -> np.ndarray:
+        dtype = np.dtype(dtype)
+        out = np.empty(self.n_pairs, dtype=dtype)
+        _check(self._lib.sq_gather_column(self._h, 0, col_id, None, dtype.itemsize, _ptr(out), self.n_pairs),
+               self._err)
+        return out
+
+    def gather_probe(self, values) -> np.ndarray:
+        v = np.ascontiguousarray(values)
+        if v.shape[0] != self.n_rows:
+            raise ValueError("probe column length differs from the probe tile")
+        out = np.empty(self.n_pairs, dtype=v.dtype)
+        _check(self._lib.sq_gather_column(self._h, 1, -1, _ptr(v), v.dtype.itemsize, _ptr(out), self.n_pairs),
+               self._err)
+        return out
+
+    def cast_i64_to_i32(self, values, minus: int = 0) -> np.ndarray:
+        v = _np(values, np.int64)
+        out = np.empty(v.shape[0], dtype=np.int32)
+        _check(self._lib.sq_cast_i64_to_i32(self._h, _ptr(v), v.shape[0], int(minus), _ptr(out)), self._err)
+        return out
+
+    # ---- device (torch) entry points: kernel-level benchmark ---------------------------------
+    def probe_count_device(self, index: CudaIndex, key_hash, start, end) -> int:
+        n = C.c_uint64(0)
+        _check(self._lib.sq_probe_count_device(self._h, index._h, _tptr(key_hash), _tptr(start), _tptr(end),
+                                               key_hash.numel(), C.byref(n)), self._err)
+        self._keep = (index, key_hash, start, end)
+        self.n_rows, self.n_pairs = int(key_hash.numel()), int(n.value)
+        return self.n_pairs
+
+    def emit_pairs_device(self, left, right=None):
+        _check(self._lib.sq_probe_emit_pairs_device(self._h, _tptr(left), _tptr(right) if right is not None else None,
+                                                    left.numel()), self._err)
+
+    def gather_build_device(self, col_id: int, out):
+        _check(self._lib.sq_gather_column_device(self._h, 0, col_id, None, out.element_size(), _tptr(out),
+                                                 out.numel()), self._err)
+
+    def gather_probe_device(self, values, out):
+        _check(self._lib.sq_gather_column_device(self._h, 1, -1, _tptr(values), values.element_size(), _tptr(out),
+                                                 out.numel()), self._err)
+
+    def counts_device_ptr(self) -> int:
+        return int(self._lib.sq_stream_counts_device(self._h) or 0)
+
+    def digest_device(self, left, right, n_pairs: int, right_offset: int = 0):
+        out = (C.c_uint64 * 3)()
+        _check(self._lib.sq_pairs_digest_device(self._h, _tptr(left), _tptr(right), int(n_pairs), int(right_offset),
+                                                out), self._err)
+        return int(out[0]), int(out[1]), int(out[2])
+
+    # ---- instrumentation ------------------------------------------------------------------------
+    def set_profiling(self, enabled: bool = True):
+        _check(self._lib.sq_stream_set_profiling(self._h, int(enabled)), self._err)
+
+    def phase_ms(self):
+        out = (C.c_float * 5)()
+        _check(self._lib.sq_stream_phase_ms(self._h, out), self._err)
+        return {"h2d": out[0], "count": out[1], "write": out[2], "d2h": out[3], "gather": out[4]}
+
+    launches = property(lambda self: int(self._lib.sq_stream_launches(self._h)))
+    bytes = property(lambda self: int(self._lib.sq_stream_bytes(self._h)))

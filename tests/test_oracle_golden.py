@@ -1,0 +1,113 @@
+"""CPU: pin the oracle (coitrees restatement + join driver) to the reference's own golden tables,
+to brute force and to the reference-shipped superintervals C++ library (oracle/_ref)."""
+import numpy as np
+import pytest
+
+from helpers import encode_tables, rows_from_pairs, sort_rows
+
+VARIANTS = [1, 8]  # scalar coitrees (nosimd.rs) and the AVX2 chunk tree (avx.rs)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_equi_and_range_16_rows(oracle, golden, variant):
+    # integration_test.rs:67-118 / interval_join.rs:1748-1812
+    L, R = encode_tables(golden["reads"], golden["targets"], equi=True)
+    l, r, _ = oracle.join(L["key"], L["start"], L["end"], R["key"], R["start"], R["end"], variant)
+    assert rows_from_pairs(L, R, l, r) == sort_rows(golden["equi_rows"])
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_range_only_32_rows(oracle, golden, variant):
+    # integration_test.rs:163-212: on=[(1, 1)] => one key for the whole build side
+    L, R = encode_tables(golden["reads"], golden["targets"], equi=False)
+    l, r, _ = oracle.join(L["key"], L["start"], L["end"], R["key"], R["start"], R["end"], variant)
+    assert rows_from_pairs(L, R, l, r) == sort_rows(golden["range_rows"])
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_closed_boundaries_10_rows(oracle, golden, variant):
+    # integration_test.rs:214-291: a.start <= b.end AND a.end >= b.start
+    L, R = encode_tables(golden["boundary_a"], golden["boundary_b"])
+    l, r, _ = oracle.join(L["key"], L["start"], L["end"], R["key"], R["start"], R["end"], variant)
+    assert rows_from_pairs(L, R, l, r) == sort_rows(golden["closed_rows"])
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_strict_boundaries_6_rows(oracle, golden, variant):
+    # integration_test.rs:293-350: a.start < b.end AND a.end > b.start  => both ends minus one
+    # (intervals.rs:95-137: `ls < re` -> re-1 ; `le > rs` -> le-1)
+    L, R = encode_tables(golden["boundary_a"], golden["boundary_b"])
+    l, r, _ = oracle.join(L["key"], L["start"], L["end"] - 1, R["key"], R["start"], R["end"] - 1, variant)
+    assert rows_from_pairs(L, R, l, r) == sort_rows(golden["strict_rows"])
+
+
+def _random_case(rng, nb, npq, nk, span, wmax, inverted):
+    bk = rng.integers(0, nk, nb).astype(np.uint64) * 7919 + 3
+    pk = rng.integers(0, nk + 1, npq).astype(np.uint64) * 7919 + 3  # one key absent from the build side
+    bs = rng.integers(-50, span, nb).astype(np.int32)
+    be = (bs + rng.integers(0, wmax, nb)).astype(np.int32)
+    ps = rng.integers(-50, span, npq).astype(np.int32)
+    pe = (ps + rng.integers(0, wmax, npq)).astype(np.int32)
+    if inverted:
+        m = rng.random(nb) < 0.1
+        be[m] = bs[m] - rng.integers(1, 20, int(m.sum())).astype(np.int32)
+        m = rng.random(npq) < 0.1
+        pe[m] = ps[m] - rng.integers(1, 20, int(m.sum())).astype(np.int32)
+    return bk, bs, be, pk, ps, pe
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_differential_vs_brute_force(oracle, variant):
+    rng = np.random.default_rng(20261018 + variant)
+    for it in range(120):
+        case = _random_case(rng, int(rng.integers(0, 900)), int(rng.integers(0, 300)), int(rng.integers(1, 4)),
+                            int(rng.integers(10, 5000)), int(rng.integers(1, 400)), inverted=(it % 3 == 0))
+        bl, br = oracle.brute(*case)
+        l, r, c = oracle.join(*case, variant=variant)
+        assert np.all(np.diff(r.astype(np.int64)) >= 0), "right_idx must be non-decreasing"
+        assert np.array_equal(oracle.sorted_pairs(l, r), oracle.sorted_pairs(bl, br))
+        assert np.array_equal(np.bincount(r, minlength=len(case[3])).astype(np.uint32), c)
+
+
+def test_dense_and_large_trees(oracle):
+    # exercises the density cut-off (simple subtrees) and deep vEB recursion
+    rng = np.random.default_rng(5)
+    for nb, span, wmax in ((3000, 1000, 900), (20000, 100000, 3000), (70000, 10 ** 6, 50)):
+        case = _random_case(rng, nb, 1500, 2, span, wmax, False)
+        bl, br = oracle.brute(*case)
+        for v in VARIANTS:
+            l, r, _ = oracle.join(*case, variant=v)
+            assert np.array_equal(oracle.sorted_pairs(l, r), oracle.sorted_pairs(bl, br))
+
+
+def test_against_reference_superintervals(oracle):
+    """oracle/_ref/libsi_ref.so is the reference's own superintervals.hpp compiled from /root/reference:
+    its SuperIntervals arm must agree with Coitrees (interval_join.rs:1752-1758)."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libsi_ref.so not built (reference tree absent)")
+    rng = np.random.default_rng(11)
+    for it in range(60):
+        case = _random_case(rng, int(rng.integers(1, 3000)), int(rng.integers(1, 500)), 3,
+                            int(rng.integers(100, 100000)), int(rng.integers(1, 2000)), False)
+        l, r, _ = oracle.join(*case, variant=8)
+        rl, rr = oracle.ref_superintervals_join(*case)
+        assert np.array_equal(oracle.sorted_pairs(l, r), oracle.sorted_pairs(rl, rr))
+
+
+def test_reference_fixture_through_superintervals_ref(oracle, golden):
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/libsi_ref.so not built")
+    L, R = encode_tables(golden["reads"], golden["targets"], equi=True)
+    l, r = oracle.ref_superintervals_join(L["key"], L["start"], L["end"], R["key"], R["start"], R["end"])
+    assert rows_from_pairs(L, R, l, r) == sort_rows(golden["equi_rows"])
+
+
+def test_synthetic_configs_fanout(oracle):
+    """the generators reproduce the fan-out SURVEY.md §8(d) quotes (scaled sizes, same density)"""
+    import sequila_native_b200 as sn
+    want = {"cfg2": (0.83, 0.1), "cfg3": (22.0, 8.0), "cfg4": (97.0, 6.0), "cfg5": (6.48, 0.5)}
+    scale = {"cfg2": 0.05, "cfg3": 0.02, "cfg4": 0.05, "cfg5": 0.0005}
+    for name, (mean, tol) in want.items():
+        b, p = sn.synth.CONFIGS[name](scale=scale[name])
+        c = oracle.OracleIndex(b["key"], b["start"], b["end"]).counts(p["key"], p["start"], p["end"])
+        assert abs(float(c.mean()) - mean) < tol, (name, float(c.mean()))
