@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py — interval-overlap join probe throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+One "step" = one pass of the probe hot path (count kernel -> emit kernel: interval_join.rs:1582-1618)
+over this rank's probe batch against the resident build index.  Workload (default ``cfg5_shard``) =
+BASELINE.json configs[4], the configuration the metric "at 1/2/4/8 B200" is quoted on: 100M build
+intervals (hg38-weighted contigs, widths U{50..150}) replicated on every GPU, probes of the same
+distribution sharded 12.5M per GPU (weak scaling; N=8 is exactly the 100M x 100M join).  Other
+workloads (cfg2/cfg3/cfg4) are selectable with --workload.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHARD_ROWS = 12_500_000
+BUILD_ROWS = 100_000_000
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="cfg5_shard", choices=["cfg5_shard", "cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--build-rows", type=int, default=BUILD_ROWS)
+    ap.add_argument("--shard-rows", type=int, default=SHARD_ROWS)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-contigs", type=int, default=4)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# data
+# ------------------------------------------------------------------------------------------------
+def torch_uniform_side(n, seed, device, wlo=50, whi=150):
+    """cfg5 distribution generated on the device (same parameters as synth._uniform_side)."""
+    import torch
+    from sequila_native_b200 import synth
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    lengths = torch.tensor(synth.HG38, device=device)
+    cum = torch.cumsum(lengths.double() / float(synth.HG38.sum()), 0)
+    keys = torch.tensor(synth.key_hash(np.arange(24)).view(np.int64), device=device)
+    contig = torch.searchsorted(cum, torch.rand(n, generator=g, device=device, dtype=torch.float64)).clamp_(max=23)
+    L = lengths[contig]
+    w = torch.randint(wlo, whi + 1, (n,), generator=g, device=device)
+    start = (torch.rand(n, generator=g, device=device, dtype=torch.float64) * (L - w + 1).double()).long()
+    end = start + w - 1
+    return {"contig": contig.int(), "key": keys[contig].contiguous(), "start": start.int(), "end": end.int()}
+
+
+def to_device(side, device):
+    import torch
+    return {"contig": torch.from_numpy(side["contig"]).to(device),
+            "key": torch.from_numpy(side["key"].view(np.int64)).to(device),
+            "start": torch.from_numpy(side["start"]).to(device), "end": torch.from_numpy(side["end"]).to(device)}
+
+
+def to_host(side):
+    return {"contig": side["contig"].cpu().numpy(), "key": side["key"].cpu().numpy().view(np.uint64),
+            "start": side["start"].cpu().numpy(), "end": side["end"].cpu().numpy()}
+
+
+def make_workload(args, rank, world, device):
+    from sequila_native_b200 import synth
+    if args.workload == "cfg5_shard":
+        build = torch_uniform_side(args.build_rows, 5001, device)
+        probe = torch_uniform_side(args.shard_rows, 5002 + 7919 * rank + 104729 * world, device)
+        name = (f"cfg5 100Mx100M hg38-weighted U{{50..150}}: {args.build_rows} build rows replicated per GPU, "
+                f"{args.shard_rows}-probe shard per GPU (N=8 == the full config)")
+        return build, probe, name
+    b, p = synth.CONFIGS[args.workload]()
+    names = {"cfg2": "cfg2 1Mx1M 24 contigs x 10Mbp uniform U{50..150}",
+             "cfg3": "cfg3 databio-shaped 1.2M build x 10M probe, skewed lengths",
+             "cfg4": "cfg4 high fan-out 1Mx1M, build widths U{100k..500k}"}
+    if world > 1:  # weak scaling: every rank probes its own re-seeded copy of the probe side
+        rng = np.random.default_rng(rank + 1)
+        perm = rng.permutation(len(p["key"]))
+        p = {k: v[perm] for k, v in p.items()}
+    return to_device(b, device), to_device(p, device), names[args.workload]
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (ts, r) in self.rows if t0 - 0.05 <= ts <= t1 + 0.15] or [r for (_, r) in self.rows]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                for nm, v in zip(names, f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference's coitrees path) on a bounded contig-subset sample
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(args, build_h, probe_h, threads):
+    """Times the reference's CPU path (oracle/: C++ restatement of coitrees 0.4.0 AVX2 tree +
+    interval_join.rs probe loop) on the box's host cores.  Sample = every build AND probe row of the
+    `cpu_sample_contigs` smallest contigs (same density / fan-out as the whole workload, since the
+    join never crosses contigs), capped at 1M probe rows."""
+    from oracle import oracle as O
+    from sequila_native_b200 import synth
+    if args.workload == "cfg5_shard":
+        sel = np.argsort(synth.HG38)[:args.cpu_sample_contigs]
+        bm = np.isin(build_h["contig"], sel)
+        pm = np.isin(probe_h["contig"], sel)
+        what = f"contigs {sorted(int(c) for c in sel)} of the workload"
+    else:
+        bm = np.ones(len(build_h["key"]), bool)
+        pm = np.ones(len(probe_h["key"]), bool)
+        what = "whole build side"
+    pk, ps, pe = probe_h["key"][pm][:1_000_000], probe_h["start"][pm][:1_000_000], probe_h["end"][pm][:1_000_000]
+    idx = O.OracleIndex(build_h["key"][bm], build_h["start"][bm], build_h["end"][bm], variant=8)
+    sec, pairs, _ = idx.time_probe(pk, ps, pe, threads=threads, batch_rows=8192)
+    return {"value": len(pk) / sec, "unit": "probe intervals/s", "cores": threads, "kind": "port",
+            "sample": f"{what}: {int(bm.sum())} build rows, {len(pk)} probe rows, {pairs} pairs, "
+                      f"probe {sec:.3f}s, index build {idx.build_seconds:.2f}s (1 thread); "
+                      f"coitrees 0.4.0 AVX2-layout restatement, 8192-row batches dealt to {threads} thread(s)",
+            "pairs_per_s": pairs / sec, "seconds": sec}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the Rust crate
+    cannot be built here: no cargo/rustc in the image) with all host threads, bounded sample."""
+    if rank != 0:
+        return
+    from sequila_native_b200 import synth
+    threads = os.cpu_count() or 1
+    if args.workload == "cfg5_shard":
+        # generate only the sample's contigs on the host (the GPU is not needed for this arm)
+        sel = np.argsort(synth.HG38)[:args.cpu_sample_contigs]
+        frac = synth.HG38[sel].sum() / synth.HG38.sum()
+        w = synth.HG38[sel] / synth.HG38[sel].sum()
+
+        def side(n, seed):
+            rng = np.random.default_rng(seed)
+            c = sel[rng.choice(len(sel), size=n, p=w)]
+            L = synth.HG38[c]
+            wd = rng.integers(50, 151, n)
+            st = (rng.random(n) * (L - wd + 1)).astype(np.int64)
+            return synth._table(c, st, st + wd - 1)
+        build_h = side(int(args.build_rows * frac), 5001)
+        probe_h = side(min(int(args.shard_rows * frac), 1_000_000), 5002)
+        name = (f"cfg5 100Mx100M hg38-weighted U{{50..150}}: {args.build_rows} build rows replicated per GPU, "
+                f"{args.shard_rows}-probe shard per GPU (N=8 == the full config)")
+    else:
+        build_h, probe_h = synth.CONFIGS[args.workload]()
+        name = args.workload
+    vals = []
+    base = None
+    for it in range(args.warmup + args.steps):
+        base = cpu_baseline(args, build_h, probe_h, threads)
+        if it >= args.warmup:
+            vals.append(base)
+        if it >= 2 and sum(v["seconds"] for v in vals) > 120:
+            break
+    v = float(np.mean([b["value"] for b in vals]))
+    ms = float(np.mean([b["seconds"] for b in vals])) * 1e3
+    base["value"] = v
+    print(json.dumps({
+        "impl": "reference", "metric": "probe_intervals_per_s", "value": v, "unit": "probe intervals/s",
+        "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": name, "note": "CPU reference arm: oracle port of coitrees path, bounded sample"},
+        "cpu_baseline": base,
+        "e2e": {"value": v, "unit": "probe intervals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "pairs_per_s": base["pairs_per_s"], "gpu_launches": 0,
+    }))
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import sequila_native_b200 as sn
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the cuda interval join has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
+
+    ctx = sn.CudaContext(local_rank)
+    build, probe, wname = make_workload(args, rank, world, device)
+    torch.cuda.synchronize()
+    n_build, n_probe = build["key"].numel(), probe["key"].numel()
+
+    # ---- build (once per query: collect_left_input, interval_join.rs:597-689); timed on its own
+    tstream = torch.cuda.current_stream().cuda_stream
+    idx = sn.CudaIndex.build_device(ctx, build["key"], build["start"], build["end"], tstream)
+    build_ms = [idx.build_ms]
+    for _ in range(2):
+        idx = None
+        idx = sn.CudaIndex.build_device(ctx, build["key"], build["start"], build["end"], tstream)
+        build_ms.append(idx.build_ms)
+    build_best = min(build_ms)
+
+    st = sn.CudaStream(ctx, cuda_stream=tstream)
+    n_pairs = st.probe_count_device(idx, probe["key"], probe["start"], probe["end"])
+    left = torch.empty(max(n_pairs, 1), dtype=torch.int32, device=device)
+    right = torch.empty(max(n_pairs, 1), dtype=torch.int32, device=device)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
+
+    def step():
+        n = st.probe_count_device(idx, probe["key"], probe["start"], probe["end"])
+        st.emit_pairs_device(left, right)
+        return n
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    # parity guard inside the bench: digest of the emitted pairs must be reproducible and the pair count
+    # must equal the sum of per-row counts (the oracle comparison itself lives in tests/ and smoke())
+    dg = st.digest_device(left, right, n_pairs)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    st.set_profiling(True)
+    launches0 = st.launches
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t0 = time.time()
+    for a, b in evs:
+        flush.fill_(1)  # L2 flush between timed iterations (outside the event pair)
+        a.record()
+        step()
+        b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t1 = time.time()
+    phases = st.phase_ms()
+    st.set_profiling(False)
+    launches = st.launches - launches0
+    step_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    clocks = sampler.stop(t0, t1) if sampler else None
+
+    tmax = torch.tensor([step_ms], device=device, dtype=torch.float64)
+    tot = torch.tensor([float(n_probe), float(n_pairs)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    step_ms_max = float(tmax.item())
+    probes_total, pairs_total = float(tot[0].item()), float(tot[1].item())
+    value = probes_total / (step_ms_max * 1e-3)
+
+    # ---- end to end through the host C ABI: pinned host inputs -> H2D -> kernels -> D2H pairs
+    host = sn.CudaStream(ctx)
+    hk = ctx.pinned_copy(probe["key"].cpu().numpy().view(np.uint64))
+    hs = ctx.pinned_copy(probe["start"].cpu().numpy())
+    he = ctx.pinned_copy(probe["end"].cpu().numpy())
+    out = (ctx.pinned_empty(max(n_pairs, 1), np.uint32), ctx.pinned_empty(max(n_pairs, 1), np.uint32),
+           ctx.pinned_empty(n_probe, np.uint32))
+
+    def e2e_step():
+        host.probe_count(idx, hk, hs, he)
+        host.emit_pairs(out=out)
+
+    for _ in range(2):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e_ms = (time.perf_counter() - e0) * 1e3 / args.e2e_steps
+    emax = torch.tensor([e_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(emax, op=dist.ReduceOp.MAX)
+    e2e_value = probes_total / (float(emax.item()) * 1e-3)
+    assert np.array_equal(out[0][:1000], left[:1000].cpu().numpy().view(np.uint32)), "host and device paths disagree"
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (algorithmic bytes) -----------------
+        b_count = 16.0 * n_probe          # read key hash 8 + start 4 + end 4 per probe row
+        b_write = 12.0 * n_pairs          # per pair: read build row id 4, write (left,right) 8
+        t_count, t_write = phases["count"], phases["write"]
+        if t_write >= t_count:
+            dom, b_dom, t_dom = "k_probe_write", b_write, t_write
+        else:
+            dom, b_dom, t_dom = "k_probe_count", b_count, t_count
+        achieved = b_dom / (t_dom * 1e-3) / 1e9 if t_dom > 0 else 0.0
+        probe_achieved = (b_count + b_write) / ((t_count + t_write) * 1e-3) / 1e9 if t_count + t_write > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        except Exception:
+            pass
+        result = {
+            "metric": "probe_intervals_per_s", "value": value, "unit": "probe intervals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms_max,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": wname, "build_rows": n_build, "probe_rows_per_gpu": n_probe,
+                       "pairs_per_gpu": n_pairs, "l2": "256 MiB flush write between timed steps; inputs also > L2",
+                       "parallelism": f"probe shards x{world}, build index replicated, no collective on the data path"},
+            "pairs_per_s": pairs_total / (step_ms_max * 1e-3),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": b_dom, "avg_launch_ms": t_dom},
+            "probe_roofline": {"achieved": probe_achieved, "frac": probe_achieved / hbm_peak,
+                               "bytes": b_count + b_write, "count_ms": t_count, "write_ms": t_write,
+                               "note": "count+write kernels together = B_probe of SURVEY §8(d) with u64 key hashes"},
+            "build": {"ms": build_best, "rows_per_s": n_build / (build_best * 1e-3) if build_best else None,
+                      "roofline_frac": (24.0 * n_build / (build_best * 1e-3) / 1e9 / hbm_peak) if build_best else None,
+                      "index_bytes": idx.bytes, "keys": idx.keys},
+            "e2e": {"value": e2e_value, "unit": "probe intervals/s", "h2d_bytes_per_step": 16 * n_probe,
+                    "d2h_bytes_per_step": 8 * n_pairs + 4 * n_probe + 8, "ms_per_step": float(emax.item()),
+                    "steps": args.e2e_steps, "api": "sq_probe_count + sq_probe_emit_pairs, pinned host buffers"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "digest": {"pairs": dg[0], "sum": dg[1], "xor": dg[2]},
+        }
+        if not args.no_cpu_baseline:
+            if args.workload == "cfg5_shard":
+                bh, ph = _sample_to_host(build, args), _sample_to_host(probe, args)
+            else:
+                bh, ph = to_host(build), to_host(probe)
+            result["cpu_baseline"] = cpu_baseline(args, bh, ph, threads=os.cpu_count() or 1)
+        print(json.dumps(result))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _sample_to_host(side, args):
+    """copy only the CPU-baseline sample's contigs back to the host"""
+    import torch
+    from sequila_native_b200 import synth
+    sel = torch.tensor(np.argsort(synth.HG38)[:args.cpu_sample_contigs].astype(np.int32), device=side["contig"].device)
+    m = torch.isin(side["contig"], sel)
+    return to_host({k: v[m] for k, v in side.items()})
+
+
+if __name__ == "__main__":
+    main()

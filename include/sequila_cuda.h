@@ -145,9 +145,10 @@ int32_t sq_cast_i64_to_i32(sq_stream* s, const int64_t* values, uint64_t n, int6
 int32_t sq_pairs_digest_device(sq_stream* s, const uint32_t* d_left, const uint32_t* d_right,
                                uint64_t n_pairs, uint64_t right_offset, uint64_t out3[3]);
 
-/* Per-phase device timings (ms) of the last count+emit on this stream, measured with CUDA
- * events on the stream: [0]=h2d [1]=count kernel [2]=write kernel [3]=d2h [4]=gather.
- * Enabled by sq_stream_set_profiling(s, 1); adds only event records to the stream. */
+/* Per-phase device timings (ms), averaged over the calls since sq_stream_set_profiling(s, 1),
+ * measured with CUDA events recorded on the stream around each phase:
+ * [0]=h2d [1]=count kernel [2]=write kernel [3]=d2h [4]=gather.  Enabling adds only event
+ * records to the stream; sq_stream_phase_ms synchronises the stream to read them. */
 int32_t sq_stream_set_profiling(sq_stream* s, int32_t enabled);
 int32_t sq_stream_phase_ms(sq_stream* s, float out5[5]);
 /* number of kernels this library launched on the stream since creation (bench: gpu_launches) */

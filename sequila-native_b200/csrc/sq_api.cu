@@ -55,6 +55,24 @@ static inline void mark(sq_stream* s, int k) {
   if (s->profiling && s->ev_ready) cudaEventRecord(s->ev[k], s->stream);
 }
 
+// Fold the timings of events that are known complete (the stream was just synchronised) into the
+// running sums.  pending bit k <=> phase k has a recorded, not yet read, event pair.
+static void fold_phases(sq_stream* s) {
+  static const int a[5] = {0, 1, 3, 4, 6}, b[5] = {1, 2, 4, 5, 7};
+  for (int k = 0; k < 5; ++k) {
+    if (!(s->pending & (1u << k))) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s->ev[a[k]], s->ev[b[k]]) == cudaSuccess) {
+      s->phase_ms[k] = ms;
+      s->phase_sum[k] += ms;
+      s->phase_n[k] += 1;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  s->pending = 0;
+}
+
 }  // namespace sq
 
 using namespace sq;
@@ -239,13 +257,20 @@ SQ_API uint64_t sq_stream_bytes(const sq_stream* s) {
 SQ_API int32_t sq_stream_set_profiling(sq_stream* s, int32_t enabled) {
   if (!s) return SQ_EINVAL;
   s->profiling = enabled != 0;
+  s->pending = 0;
+  for (int k = 0; k < 5; ++k) { s->phase_ms[k] = 0.f; s->phase_sum[k] = 0.0; s->phase_n[k] = 0; }
   if (s->profiling) { SQ_CUDA(s->err, cudaSetDevice(s->ctx->device)); return ensure_events(s); }
   return SQ_OK;
 }
 
 SQ_API int32_t sq_stream_phase_ms(sq_stream* s, float out5[5]) {
   if (!s || !out5) return SQ_EINVAL;
-  for (int k = 0; k < 5; ++k) out5[k] = s->phase_ms[k];
+  if (s->profiling) {
+    SQ_CUDA(s->err, cudaSetDevice(s->ctx->device));
+    SQ_CUDA(s->err, cudaStreamSynchronize(s->stream));
+    fold_phases(s);
+  }
+  for (int k = 0; k < 5; ++k) out5[k] = s->phase_n[k] ? float(s->phase_sum[k] / double(s->phase_n[k])) : 0.f;
   return SQ_OK;
 }
 
@@ -265,10 +290,7 @@ static int32_t finish_count(sq_stream* s, uint64_t* n_pairs_out) {
   s->n_pairs = h[0];
   s->counted = true;
   s->emitted = false;
-  if (s->profiling) {
-    cudaEventElapsedTime(&s->phase_ms[0], s->ev[0], s->ev[1]);
-    cudaEventElapsedTime(&s->phase_ms[1], s->ev[1], s->ev[2]);
-  }
+  if (s->profiling) { s->pending |= 3u; fold_phases(s); }
   *n_pairs_out = s->n_pairs;
   return SQ_OK;
 }
@@ -348,10 +370,7 @@ SQ_API int32_t sq_probe_emit_pairs_device(sq_stream* s, uint32_t* d_left_idx_out
   s->d_last_left = d_left_idx_out;
   s->d_last_right = d_right_idx_out;
   s->emitted = true;
-  if (s->profiling) {
-    SQ_CUDA(s->err, cudaStreamSynchronize(s->stream));
-    cudaEventElapsedTime(&s->phase_ms[2], s->ev[3], s->ev[4]);
-  }
+  if (s->profiling) s->pending |= 4u;  // read at the next synchronisation point
   return SQ_OK;
 }
 
@@ -381,10 +400,7 @@ SQ_API int32_t sq_probe_emit_pairs(sq_stream* s, uint32_t* left_idx_out, uint32_
   s->d_last_left = dl;
   s->d_last_right = dr;
   s->emitted = true;
-  if (s->profiling) {
-    cudaEventElapsedTime(&s->phase_ms[2], s->ev[3], s->ev[4]);
-    cudaEventElapsedTime(&s->phase_ms[3], s->ev[4], s->ev[5]);
-  }
+  if (s->profiling) { s->pending |= 12u; fold_phases(s); }
   return SQ_OK;
 }
 
@@ -422,9 +438,10 @@ SQ_API int32_t sq_gather_column_device(sq_stream* s, int32_t side, int32_t build
   mark(s, 6);
   rc = launch_gather(s, src, ix, s->n_pairs, width, d_out);
   mark(s, 7);
-  if (rc == SQ_OK && s->profiling) {
+  if (rc == SQ_OK && s->profiling) {  // one gather per column: fold each (costs a sync; profiling only)
     SQ_CUDA(s->err, cudaStreamSynchronize(s->stream));
-    cudaEventElapsedTime(&s->phase_ms[4], s->ev[6], s->ev[7]);
+    s->pending |= 16u;
+    fold_phases(s);
   }
   return rc;
 }
@@ -458,7 +475,7 @@ SQ_API int32_t sq_gather_column(sq_stream* s, int32_t side, int32_t build_col_id
   mark(s, 7);
   SQ_CUDA(E, cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s->stream));
   SQ_CUDA(E, cudaStreamSynchronize(s->stream));
-  if (s->profiling) cudaEventElapsedTime(&s->phase_ms[4], s->ev[6], s->ev[7]);
+  if (s->profiling) { s->pending |= 16u; fold_phases(s); }
   return SQ_OK;
 }
 

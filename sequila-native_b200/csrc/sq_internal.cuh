@@ -143,7 +143,10 @@ struct sq_stream {
   bool profiling = false;
   cudaEvent_t ev[8] = {};
   bool ev_ready = false;
-  float phase_ms[5] = {0, 0, 0, 0, 0};
+  float phase_ms[5] = {0, 0, 0, 0, 0};   // last value per phase
+  double phase_sum[5] = {0, 0, 0, 0, 0}; // running sums since profiling was enabled
+  uint64_t phase_n[5] = {0, 0, 0, 0, 0};
+  uint32_t pending = 0;                  // phases with a recorded, unread event pair
   uint64_t launches = 0;
 };
 
