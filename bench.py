@@ -271,9 +271,8 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
 
     def step():
-        n = st.probe_count_device(idx, probe["key"], probe["start"], probe["end"])
-        st.emit_pairs_device(left, right)
-        return n
+        # count -> look-back scan -> write as ONE fused kernel pass (sq_probe_join_device)
+        return st.probe_join_device(idx, probe["key"], probe["start"], probe["end"], left, right)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -324,8 +323,7 @@ def main():
            ctx.pinned_empty(n_probe, np.uint32))
 
     def e2e_step():
-        host.probe_count(idx, hk, hs, he)
-        host.emit_pairs(out=out)
+        host.probe_join(idx, hk, hs, he, out)
 
     for _ in range(2):
         e2e_step()
@@ -345,15 +343,13 @@ def main():
 
     if rank == 0:
         # ---- roofline of the dominant kernel (algorithmic bytes) -----------------
-        b_count = 16.0 * n_probe          # read key hash 8 + start 4 + end 4 per probe row
-        b_write = 12.0 * n_pairs          # per pair: read build row id 4, write (left,right) 8
-        t_count, t_write = phases["count"], phases["write"]
-        if t_write >= t_count:
-            dom, b_dom, t_dom = "k_probe_write", b_write, t_write
-        else:
-            dom, b_dom, t_dom = "k_probe_count", b_count, t_count
+        # B_probe of SURVEY.md §8(d) with u64 key hashes consumed on the device:
+        # 16 B per probe row (key hash 8 + start 4 + end 4) + 12 B per emitted pair
+        # (read the hit's build row id 4, write (left,right) 8).  One launch = the whole tile.
+        dom = "k_probe_join"
+        b_dom = 16.0 * n_probe + 12.0 * n_pairs
+        t_dom = phases["join"]
         achieved = b_dom / (t_dom * 1e-3) / 1e9 if t_dom > 0 else 0.0
-        probe_achieved = (b_count + b_write) / ((t_count + t_write) * 1e-3) / 1e9 if t_count + t_write > 0 else 0.0
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
@@ -370,15 +366,12 @@ def main():
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": b_dom, "avg_launch_ms": t_dom},
-            "probe_roofline": {"achieved": probe_achieved, "frac": probe_achieved / hbm_peak,
-                               "bytes": b_count + b_write, "count_ms": t_count, "write_ms": t_write,
-                               "note": "count+write kernels together = B_probe of SURVEY §8(d) with u64 key hashes"},
             "build": {"ms": build_best, "rows_per_s": n_build / (build_best * 1e-3) if build_best else None,
                       "roofline_frac": (24.0 * n_build / (build_best * 1e-3) / 1e9 / hbm_peak) if build_best else None,
                       "index_bytes": idx.bytes, "keys": idx.keys},
             "e2e": {"value": e2e_value, "unit": "probe intervals/s", "h2d_bytes_per_step": 16 * n_probe,
                     "d2h_bytes_per_step": 8 * n_pairs + 4 * n_probe + 8, "ms_per_step": float(emax.item()),
-                    "steps": args.e2e_steps, "api": "sq_probe_count + sq_probe_emit_pairs, pinned host buffers"},
+                    "steps": args.e2e_steps, "api": "sq_probe_join (host C ABI), pinned host buffers"},
             "gpu_launches": int(launches), "clocks": clocks,
             "digest": {"pairs": dg[0], "sum": dg[1], "xor": dg[2]},
         }

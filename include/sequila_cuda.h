@@ -110,8 +110,22 @@ int32_t sq_probe_count(sq_stream* s, const sq_index* idx, const uint64_t* key_ha
 int32_t sq_probe_emit_pairs(sq_stream* s, uint32_t* left_idx_out, uint32_t* right_idx_out,
                             uint32_t* counts_out, uint64_t capacity);
 
-/* Device-pointer variants (kernel-level benchmark; outputs stay in HBM).  The count variant
- * synchronises the stream to return n_pairs. */
+/* Both phases in one call: count -> scan -> write run as ONE fused kernel pass when the pairs fit
+ * `capacity`.  *n_pairs_out is always exact on return.  If n_pairs > capacity the call returns
+ * SQ_ECAPACITY having written nothing usable; allocate n_pairs elements and call
+ * sq_probe_emit_pairs (the tile stays counted). */
+int32_t sq_probe_join(sq_stream* s, const sq_index* idx, const uint64_t* key_hash,
+                      const int32_t* start, const int32_t* end, uint32_t n_rows,
+                      uint32_t* left_idx_out, uint32_t* right_idx_out, uint32_t* counts_out,
+                      uint64_t capacity, uint64_t* n_pairs_out);
+
+/* Device-pointer variants (kernel-level benchmark; outputs stay in HBM).  The count and join
+ * variants synchronise the stream to return n_pairs; probe columns must stay valid until the
+ * tile's emit. */
+int32_t sq_probe_join_device(sq_stream* s, const sq_index* idx, const uint64_t* d_key_hash,
+                             const int32_t* d_start, const int32_t* d_end, uint32_t n_rows,
+                             uint32_t* d_left_idx_out, uint32_t* d_right_idx_out,
+                             uint64_t capacity, uint64_t* n_pairs_out);
 int32_t sq_probe_count_device(sq_stream* s, const sq_index* idx, const uint64_t* d_key_hash,
                               const int32_t* d_start, const int32_t* d_end, uint32_t n_rows,
                               uint64_t* n_pairs_out);
@@ -147,7 +161,8 @@ int32_t sq_pairs_digest_device(sq_stream* s, const uint32_t* d_left, const uint3
 
 /* Per-phase device timings (ms), averaged over the calls since sq_stream_set_profiling(s, 1),
  * measured with CUDA events recorded on the stream around each phase:
- * [0]=h2d [1]=count kernel [2]=write kernel [3]=d2h [4]=gather.  Enabling adds only event
+ * [0]=h2d [1]=fused probe kernel of count/join calls [2]=probe kernel re-run by emit calls
+ * [3]=d2h [4]=gather.  Enabling adds only event
  * records to the stream; sq_stream_phase_ms synchronises the stream to read them. */
 int32_t sq_stream_set_profiling(sq_stream* s, int32_t enabled);
 int32_t sq_stream_phase_ms(sq_stream* s, float out5[5]);

@@ -43,6 +43,8 @@ SIGNATURES = {
     "sq_stream_bytes": (C.c_uint64, [vp]),
     "sq_probe_count": (C.c_int32, [vp, vp, vp, vp, vp, C.c_uint32, u64p]),
     "sq_probe_emit_pairs": (C.c_int32, [vp, vp, vp, vp, C.c_uint64]),
+    "sq_probe_join": (C.c_int32, [vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint64, u64p]),
+    "sq_probe_join_device": (C.c_int32, [vp, vp, vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, u64p]),
     "sq_probe_count_device": (C.c_int32, [vp, vp, vp, vp, vp, C.c_uint32, u64p]),
     "sq_probe_emit_pairs_device": (C.c_int32, [vp, vp, vp, C.c_uint64]),
     "sq_stream_counts_device": (vp, [vp]),

@@ -235,7 +235,7 @@ SQ_API void sq_stream_free(sq_stream* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
   cudaStreamSynchronize(s->stream);
-  for (sq_buf* b : {&s->d_in, &s->d_lo, &s->d_ncand, &s->d_cnt, &s->d_tile, &s->d_scalar, &s->d_left,
+  for (sq_buf* b : {&s->d_in, &s->d_cnt, &s->d_tile, &s->d_scalar, &s->d_left,
                     &s->d_right, &s->d_gather, &s->h_in, &s->h_out, &s->h_scalar})
     release(*b);
   if (s->ev_ready) for (auto& e : s->ev) cudaEventDestroy(e);
@@ -248,7 +248,7 @@ SQ_API const char* sq_stream_last_error(const sq_stream* s) { return s ? s->err.
 SQ_API uint64_t sq_stream_bytes(const sq_stream* s) {
   if (!s) return 0;
   uint64_t t = 0;
-  for (const sq_buf* b : {&s->d_in, &s->d_lo, &s->d_ncand, &s->d_cnt, &s->d_tile, &s->d_scalar, &s->d_left,
+  for (const sq_buf* b : {&s->d_in, &s->d_cnt, &s->d_tile, &s->d_scalar, &s->d_left,
                           &s->d_right, &s->d_gather, &s->h_in, &s->h_out, &s->h_scalar})
     t += b->cap;
   return t;
@@ -280,14 +280,16 @@ SQ_API const uint32_t* sq_stream_counts_device(const sq_stream* s) {
 }
 
 // ---- probe ------------------------------------------------------------------------------------
-static int32_t finish_count(sq_stream* s, uint64_t* n_pairs_out) {
+// Reads {n_pairs, overflow} written by k_probe_join and closes the count phase.
+static int32_t finish_count(sq_stream* s, bool wrote, uint64_t* n_pairs_out) {
   ErrorSlot& E = s->err;
   int rc;
   if ((rc = ensure(E, s->h_scalar, 256, true))) return rc;
   auto* h = static_cast<unsigned long long*>(s->h_scalar.p);
-  SQ_CUDA(E, cudaMemcpyAsync(h, s->d_scalar.p, 8, cudaMemcpyDeviceToHost, s->stream));
+  SQ_CUDA(E, cudaMemcpyAsync(h, s->d_scalar.p, 16, cudaMemcpyDeviceToHost, s->stream));
   SQ_CUDA(E, cudaStreamSynchronize(s->stream));
   s->n_pairs = h[0];
+  s->spec_valid = wrote && h[1] == 0;
   s->counted = true;
   s->emitted = false;
   if (s->profiling) { s->pending |= 3u; fold_phases(s); }
@@ -305,48 +307,103 @@ static int32_t check_probe_args(sq_stream* s, const sq_index* idx, const void* k
   return SQ_OK;
 }
 
+static void begin_tile(sq_stream* s, const sq_index* idx, const uint64_t* dk, const int32_t* ds, const int32_t* de,
+                       uint32_t n) {
+  s->idx = idx;
+  s->n_rows = n;
+  s->d_q_key = dk;
+  s->d_q_start = ds;
+  s->d_q_end = de;
+  s->counted = false;
+  s->emitted = false;
+  s->spec_valid = false;
+  s->d_spec_left = s->d_spec_right = nullptr;
+}
+
+static int32_t empty_tile(sq_stream* s, uint64_t* n_pairs_out) {
+  s->n_pairs = 0;
+  s->counted = true;
+  s->spec_valid = true;
+  *n_pairs_out = 0;
+  return SQ_OK;
+}
+
+// device tile: one fused pass; writes into (d_left, d_right) when the pairs fit `capacity`
+static int32_t join_device(sq_stream* s, const sq_index* idx, const uint64_t* dk, const int32_t* ds,
+                           const int32_t* de, uint32_t n, uint32_t* d_left, uint32_t* d_right, uint64_t capacity,
+                           uint64_t* n_pairs_out) {
+  begin_tile(s, idx, dk, ds, de, n);
+  if (n == 0) return empty_tile(s, n_pairs_out);
+  int rc;
+  mark(s, 1);
+  if ((rc = launch_join(s, idx, dk, ds, de, n, d_left, d_right, capacity))) return rc;
+  mark(s, 2);
+  const bool wrote = d_left != nullptr && capacity > 0;
+  s->d_spec_left = d_left;
+  s->d_spec_right = d_right;
+  return finish_count(s, wrote, n_pairs_out);
+}
+
 SQ_API int32_t sq_probe_count_device(sq_stream* s, const sq_index* idx, const uint64_t* d_key_hash,
                                      const int32_t* d_start, const int32_t* d_end, uint32_t n_rows,
                                      uint64_t* n_pairs_out) {
   int rc = check_probe_args(s, idx, d_key_hash, d_start, d_end, n_rows, n_pairs_out);
   if (rc) return rc;
   SQ_CUDA(s->err, cudaSetDevice(s->ctx->device));
-  s->idx = idx;
-  s->n_rows = n_rows;
-  s->d_q_start = d_start;
-  s->counted = false;
-  if (n_rows == 0) { s->n_pairs = 0; s->counted = true; s->emitted = false; *n_pairs_out = 0; return SQ_OK; }
   mark(s, 0);
-  mark(s, 1);
-  if ((rc = launch_count(s, idx, d_key_hash, d_start, d_end, n_rows))) return rc;
-  mark(s, 2);
-  return finish_count(s, n_pairs_out);
+  return join_device(s, idx, d_key_hash, d_start, d_end, n_rows, nullptr, nullptr, 0, n_pairs_out);
+}
+
+SQ_API int32_t sq_probe_join_device(sq_stream* s, const sq_index* idx, const uint64_t* d_key_hash,
+                                    const int32_t* d_start, const int32_t* d_end, uint32_t n_rows,
+                                    uint32_t* d_left_idx_out, uint32_t* d_right_idx_out, uint64_t capacity,
+                                    uint64_t* n_pairs_out) {
+  int rc = check_probe_args(s, idx, d_key_hash, d_start, d_end, n_rows, n_pairs_out);
+  if (rc) return rc;
+  SQ_CUDA(s->err, cudaSetDevice(s->ctx->device));
+  mark(s, 0);
+  if ((rc = join_device(s, idx, d_key_hash, d_start, d_end, n_rows, d_left_idx_out, d_right_idx_out, capacity,
+                        n_pairs_out)))
+    return rc;
+  if (!s->spec_valid)
+    return fail(s->err, SQ_ECAPACITY, "output capacity %llu < %llu pairs", (unsigned long long)capacity,
+                (unsigned long long)s->n_pairs);
+  s->d_last_left = d_left_idx_out;
+  s->d_last_right = d_right_idx_out;
+  s->emitted = true;
+  return SQ_OK;
+}
+
+// host tile: H2D, then the fused pass writing speculatively into the stream's own pair buffers
+static int32_t count_host(sq_stream* s, const sq_index* idx, const uint64_t* key_hash, const int32_t* start,
+                          const int32_t* end, uint32_t n_rows, uint64_t* n_pairs_out) {
+  ErrorSlot& E = s->err;
+  SQ_CUDA(E, cudaSetDevice(s->ctx->device));
+  int rc;
+  if (n_rows == 0) { begin_tile(s, idx, nullptr, nullptr, nullptr, 0); return empty_tile(s, n_pairs_out); }
+  const size_t n = n_rows;
+  if ((rc = ensure(E, s->d_in, n * 16, false))) return rc;
+  auto* dk = static_cast<uint64_t*>(s->d_in.p);
+  auto* ds = reinterpret_cast<int32_t*>(dk + n);
+  auto* de = ds + n;
+  if (!s->d_left.p) {  // first tile: guess 4 pairs per probe row; later tiles reuse the grown buffers
+    if ((rc = ensure(E, s->d_left, n * 16, false))) return rc;
+    if ((rc = ensure(E, s->d_right, n * 16, false))) return rc;
+  }
+  const uint64_t cap = (s->d_left.cap < s->d_right.cap ? s->d_left.cap : s->d_right.cap) / 4;
+  mark(s, 0);
+  SQ_CUDA(E, cudaMemcpyAsync(dk, key_hash, n * 8, cudaMemcpyHostToDevice, s->stream));
+  SQ_CUDA(E, cudaMemcpyAsync(ds, start, n * 4, cudaMemcpyHostToDevice, s->stream));
+  SQ_CUDA(E, cudaMemcpyAsync(de, end, n * 4, cudaMemcpyHostToDevice, s->stream));
+  return join_device(s, idx, dk, ds, de, n_rows, static_cast<uint32_t*>(s->d_left.p),
+                     static_cast<uint32_t*>(s->d_right.p), cap, n_pairs_out);
 }
 
 SQ_API int32_t sq_probe_count(sq_stream* s, const sq_index* idx, const uint64_t* key_hash, const int32_t* start,
                               const int32_t* end, uint32_t n_rows, uint64_t* n_pairs_out) {
   int rc = check_probe_args(s, idx, key_hash, start, end, n_rows, n_pairs_out);
   if (rc) return rc;
-  ErrorSlot& E = s->err;
-  SQ_CUDA(E, cudaSetDevice(s->ctx->device));
-  s->idx = idx;
-  s->n_rows = n_rows;
-  s->counted = false;
-  if (n_rows == 0) { s->n_pairs = 0; s->counted = true; s->emitted = false; *n_pairs_out = 0; return SQ_OK; }
-  const size_t n = n_rows;
-  if ((rc = ensure(E, s->d_in, n * 16, false))) return rc;
-  auto* dk = static_cast<uint64_t*>(s->d_in.p);
-  auto* ds = reinterpret_cast<int32_t*>(dk + n);
-  auto* de = ds + n;
-  mark(s, 0);
-  SQ_CUDA(E, cudaMemcpyAsync(dk, key_hash, n * 8, cudaMemcpyHostToDevice, s->stream));
-  SQ_CUDA(E, cudaMemcpyAsync(ds, start, n * 4, cudaMemcpyHostToDevice, s->stream));
-  SQ_CUDA(E, cudaMemcpyAsync(de, end, n * 4, cudaMemcpyHostToDevice, s->stream));
-  mark(s, 1);
-  s->d_q_start = ds;
-  if ((rc = launch_count(s, idx, dk, ds, de, n_rows))) return rc;
-  mark(s, 2);
-  return finish_count(s, n_pairs_out);
+  return count_host(s, idx, key_hash, start, end, n_rows, n_pairs_out);
 }
 
 static int32_t check_emit(sq_stream* s, const void* left, uint64_t capacity) {
@@ -365,7 +422,9 @@ SQ_API int32_t sq_probe_emit_pairs_device(sq_stream* s, uint32_t* d_left_idx_out
   if (rc) return rc;
   SQ_CUDA(s->err, cudaSetDevice(s->ctx->device));
   mark(s, 3);
-  if (s->n_pairs && (rc = launch_write(s, d_left_idx_out, d_right_idx_out))) return rc;
+  if (s->n_pairs && (rc = launch_join(s, s->idx, s->d_q_key, s->d_q_start, s->d_q_end, s->n_rows, d_left_idx_out,
+                                      d_right_idx_out, capacity)))
+    return rc;
   mark(s, 4);
   s->d_last_left = d_left_idx_out;
   s->d_last_right = d_right_idx_out;
@@ -381,13 +440,17 @@ SQ_API int32_t sq_probe_emit_pairs(sq_stream* s, uint32_t* left_idx_out, uint32_
   ErrorSlot& E = s->err;
   SQ_CUDA(E, cudaSetDevice(s->ctx->device));
   const size_t np = s->n_pairs;
-  if ((rc = ensure(E, s->d_left, np * 4, false))) return rc;
-  // right_idx is needed on the device whenever a later gather of probe columns may follow
-  if ((rc = ensure(E, s->d_right, np * 4, false))) return rc;
+  mark(s, 3);
+  const bool reuse = s->spec_valid && s->d_spec_left == s->d_left.p && s->d_spec_right == s->d_right.p;
+  if (np && !reuse) {  // the speculative buffers were too small: grow them and run the pass again
+    if ((rc = ensure(E, s->d_left, np * 4, false))) return rc;
+    if ((rc = ensure(E, s->d_right, np * 4, false))) return rc;
+    if ((rc = launch_join(s, s->idx, s->d_q_key, s->d_q_start, s->d_q_end, s->n_rows,
+                          static_cast<uint32_t*>(s->d_left.p), static_cast<uint32_t*>(s->d_right.p), np)))
+      return rc;
+  }
   auto* dl = static_cast<uint32_t*>(s->d_left.p);
   auto* dr = static_cast<uint32_t*>(s->d_right.p);
-  mark(s, 3);
-  if (np && (rc = launch_write(s, dl, dr))) return rc;
   mark(s, 4);
   if (np) {
     SQ_CUDA(E, cudaMemcpyAsync(left_idx_out, dl, np * 4, cudaMemcpyDeviceToHost, s->stream));
@@ -402,6 +465,15 @@ SQ_API int32_t sq_probe_emit_pairs(sq_stream* s, uint32_t* left_idx_out, uint32_
   s->emitted = true;
   if (s->profiling) { s->pending |= 12u; fold_phases(s); }
   return SQ_OK;
+}
+
+SQ_API int32_t sq_probe_join(sq_stream* s, const sq_index* idx, const uint64_t* key_hash, const int32_t* start,
+                             const int32_t* end, uint32_t n_rows, uint32_t* left_idx_out, uint32_t* right_idx_out,
+                             uint32_t* counts_out, uint64_t capacity, uint64_t* n_pairs_out) {
+  int rc = check_probe_args(s, idx, key_hash, start, end, n_rows, n_pairs_out);
+  if (rc) return rc;
+  if ((rc = count_host(s, idx, key_hash, start, end, n_rows, n_pairs_out))) return rc;
+  return sq_probe_emit_pairs(s, left_idx_out, right_idx_out, counts_out, capacity);
 }
 
 // ---- gather -----------------------------------------------------------------------------------

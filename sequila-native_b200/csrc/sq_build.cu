@@ -3,13 +3,16 @@
 //
 //   key hash --(device hash table)--> dense key id
 //   radix sort of (key id, start) carrying the build row
-//   per key segment: start[], end[], row[], runmax[] (running max of end inside the segment)
+//   per key segment: start[], re[] = {runmax, end}, row[]  (runmax = running max of end inside
+//   the segment) and a direct-address bin directory over the starts
 //
 // A probe (qs, qe) against its key segment [sb, se) then has its hits inside the contiguous
 // candidate range [lo, hi):  hi = first j with start[j] >  qe  (all j < hi have start <= qe)
 //                            lo = first j with runmax[j] >= qs (the first row whose end >= qs)
 // and the hits are exactly the rows of [lo, hi) with end[j] >= qs — the same set coitrees'
 // pruned descent visits (nosimd.rs:343-384), for any input including inverted intervals.
+// hi is found through the bin directory (one L2-resident load + a search inside one cache
+// line instead of a ~23-step binary search over HBM); lo by galloping back from hi over runmax.
 //
 // Kernels here are HBM-bound streaming passes; the sort is CUB's radix sort (library code, like
 // cuBLAS for a GEMM) restricted to the significant bits 32 + ceil(log2(#keys)).
@@ -91,13 +94,12 @@ __global__ void __launch_bounds__(256) k_make_sort_keys(const uint64_t* __restri
   }
 }
 
-// After the sort: write start[], row[], end[] (gathered through the permutation) and the segment
-// boundaries seg_off[id] = first sorted position of key id.
+// After the sort: write start[], row[], re[].y = end (gathered through the permutation) and the
+// segment boundaries seg_off[id] = first sorted position of key id.
 __global__ void __launch_bounds__(256) k_finalize(const uint64_t* __restrict__ sorted_key,
                                                   const uint32_t* __restrict__ perm,
                                                   const int32_t* __restrict__ end_in, uint64_t n,
-                                                  int32_t* __restrict__ s_start,
-                                                  int32_t* __restrict__ s_end,
+                                                  int32_t* __restrict__ s_start, int2* __restrict__ s_re,
                                                   uint32_t* __restrict__ s_row,
                                                   uint32_t* __restrict__ seg_off, uint32_t n_keys) {
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
@@ -106,10 +108,54 @@ __global__ void __launch_bounds__(256) k_finalize(const uint64_t* __restrict__ s
     const uint32_t r = perm[j];
     s_start[j] = int32_t(uint32_t(k) ^ 0x80000000u);
     s_row[j] = r;
-    s_end[j] = __ldg(end_in + r);
+    s_re[j] = make_int2(0, __ldg(end_in + r));
     const uint32_t id = uint32_t(k >> 32);
     if (j == 0 || uint32_t(sorted_key[j - 1] >> 32) != id) seg_off[id] = uint32_t(j);
     if (j == n - 1) seg_off[n_keys] = uint32_t(n);
+  }
+}
+
+// One thread per key segment: bin geometry (power-of-two bin width, ~16-32 rows per bin when the
+// starts are spread evenly; skewed data just gets longer in-bin searches).
+__global__ void __launch_bounds__(256) k_seg_meta(const uint32_t* __restrict__ seg_off,
+                                                  const int32_t* __restrict__ s_start, uint32_t n_keys,
+                                                  SegMeta* __restrict__ meta) {
+  const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n_keys) return;
+  SegMeta m;
+  m.sb = seg_off[id];
+  m.se = seg_off[id + 1];
+  m.min_start = s_start[m.sb];
+  const uint32_t range = uint32_t(s_start[m.se - 1]) - uint32_t(m.min_start);
+  const uint32_t rows = m.se - m.sb;
+  const uint32_t max_bins = rows / 16 ? rows / 16 : 1;
+  uint32_t shift = 0;
+  while (shift < 32 && uint64_t(range >> shift) + 1ull > uint64_t(max_bins)) ++shift;
+  m.shift = shift;
+  m.nbins = (shift >= 32 ? 0u : (range >> shift)) + 1u;
+  m.dir_base = 0;  // filled by the host-side exclusive scan over nbins + 1
+  m.pad0 = m.pad1 = 0;
+  meta[id] = m;
+}
+
+// dir[dir_base + b] = first row of the segment whose bin >= b; dir[dir_base + nbins] = se
+__global__ void __launch_bounds__(256) k_fill_dir(const uint64_t* __restrict__ sorted_key,
+                                                  const int32_t* __restrict__ s_start, uint64_t n,
+                                                  const SegMeta* __restrict__ meta,
+                                                  uint32_t* __restrict__ dir) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const uint32_t id = uint32_t(sorted_key[j] >> 32);
+    const SegMeta m = meta[id];
+    const uint32_t sh = m.shift;
+    const uint32_t bin = sh >= 32 ? 0u : ((uint32_t(s_start[j]) - uint32_t(m.min_start)) >> sh);
+    uint32_t from = 0;
+    if (j > m.sb) {
+      const uint32_t prev = sh >= 32 ? 0u : ((uint32_t(s_start[j - 1]) - uint32_t(m.min_start)) >> sh);
+      from = prev + 1;
+    }
+    for (uint32_t b = from; b <= bin; ++b) dir[m.dir_base + b] = uint32_t(j);
+    if (j == uint64_t(m.se) - 1) dir[m.dir_base + m.nbins] = m.se;
   }
 }
 
@@ -124,8 +170,8 @@ constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 __device__ __forceinline__ uint64_t scan_word(const uint64_t* __restrict__ sorted_key,
-                                              const int32_t* __restrict__ s_end, uint64_t j) {
-  return (sorted_key[j] & 0xFFFFFFFF00000000ull) | uint64_t(uint32_t(s_end[j]) ^ 0x80000000u);
+                                              const int2* __restrict__ s_re, uint64_t j) {
+  return (sorted_key[j] & 0xFFFFFFFF00000000ull) | uint64_t(uint32_t(s_re[j].y) ^ 0x80000000u);
 }
 
 __device__ __forceinline__ uint64_t warp_incl_max(uint64_t v) {
@@ -138,7 +184,7 @@ __device__ __forceinline__ uint64_t warp_incl_max(uint64_t v) {
 }
 
 __global__ void __launch_bounds__(kScanThreads) k_runmax_reduce(const uint64_t* __restrict__ sorted_key,
-                                                                const int32_t* __restrict__ s_end,
+                                                                const int2* __restrict__ s_re,
                                                                 uint64_t n, uint64_t* __restrict__ tile_max) {
   __shared__ uint64_t wmax[kScanThreads / 32];
   const uint64_t base = uint64_t(blockIdx.x) * kScanTile;
@@ -146,7 +192,7 @@ __global__ void __launch_bounds__(kScanThreads) k_runmax_reduce(const uint64_t* 
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
     const uint64_t j = base + uint64_t(k) * kScanThreads + threadIdx.x;
-    if (j < n) m = max(m, scan_word(sorted_key, s_end, j));
+    if (j < n) m = max(m, scan_word(sorted_key, s_re, j));
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
@@ -190,10 +236,8 @@ __global__ void __launch_bounds__(1024) k_runmax_mid(uint64_t* __restrict__ tile
 }
 
 __global__ void __launch_bounds__(kScanThreads) k_runmax_final(const uint64_t* __restrict__ sorted_key,
-                                                               const int32_t* __restrict__ s_end,
-                                                               uint64_t n,
-                                                               const uint64_t* __restrict__ tile_excl,
-                                                               int32_t* __restrict__ runmax) {
+                                                               int2* __restrict__ s_re, uint64_t n,
+                                                               const uint64_t* __restrict__ tile_excl) {
   __shared__ uint64_t wtot[kScanThreads / 32];
   const uint64_t base = uint64_t(blockIdx.x) * kScanTile;
   uint64_t carry = tile_excl[blockIdx.x];
@@ -201,14 +245,14 @@ __global__ void __launch_bounds__(kScanThreads) k_runmax_final(const uint64_t* _
 #pragma unroll 1
   for (int k = 0; k < kScanItems; ++k) {
     const uint64_t j = base + uint64_t(k) * kScanThreads + threadIdx.x;
-    const uint64_t v = j < n ? scan_word(sorted_key, s_end, j) : 0;
+    const uint64_t v = j < n ? scan_word(sorted_key, s_re, j) : 0;
     uint64_t inc = warp_incl_max(v);
     if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = inc;
     __syncthreads();
     uint64_t pre = carry;
     for (int w = 0; w < int(threadIdx.x >> 5); ++w) pre = max(pre, wtot[w]);
     inc = max(inc, pre);
-    if (j < n) runmax[j] = int32_t(uint32_t(inc) ^ 0x80000000u);
+    if (j < n) s_re[j].x = int32_t(uint32_t(inc) ^ 0x80000000u);
     uint64_t tot = carry;
     for (int w = 0; w < kScanThreads / 32; ++w) tot = max(tot, wtot[w]);
     carry = tot;
@@ -226,8 +270,8 @@ static inline int grid_for(uint64_t n, int threads, int sm_count, int per_sm = 8
 void free_index(sq_index* idx) {
   if (!idx) return;
   cudaSetDevice(idx->ctx->device);
-  cudaFree(idx->d_start); cudaFree(idx->d_end); cudaFree(idx->d_runmax); cudaFree(idx->d_row);
-  cudaFree(idx->d_seg_off); cudaFree(idx->d_ht_keys); cudaFree(idx->d_ht_ids);
+  cudaFree(idx->d_start); cudaFree(idx->d_re); cudaFree(idx->d_row);
+  cudaFree(idx->d_meta); cudaFree(idx->d_dir); cudaFree(idx->d_ht_keys); cudaFree(idx->d_ht_ids);
   for (auto& c : idx->columns) if (c.owned) cudaFree(c.d_values);
   delete idx;
 }
@@ -296,20 +340,19 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
 
   // 2. sorted arrays
   SQ_CUDA(E, cudaMalloc(&idx->d_start, (n ? n : 1) * 4));
-  SQ_CUDA(E, cudaMalloc(&idx->d_end, (n ? n : 1) * 4));
-  SQ_CUDA(E, cudaMalloc(&idx->d_runmax, (n ? n : 1) * 4));
+  SQ_CUDA(E, cudaMalloc(&idx->d_re, (n ? n : 1) * 8));
   SQ_CUDA(E, cudaMalloc(&idx->d_row, (n ? n : 1) * 4));
-  SQ_CUDA(E, cudaMalloc(&idx->d_seg_off, (size_t(n_keys) + 1) * 4));
-  SQ_CUDA(E, cudaMemsetAsync(idx->d_seg_off, 0, (size_t(n_keys) + 1) * 4, st));
-  idx->bytes = uint64_t(n ? n : 1) * 16 + (uint64_t(n_keys) + 1) * 4 + uint64_t(cap) * 12;
+  SQ_CUDA(E, cudaMalloc(&idx->d_meta, (size_t(n_keys) + 1) * sizeof(SegMeta)));
+  idx->bytes = uint64_t(n ? n : 1) * 16 + (uint64_t(n_keys) + 1) * sizeof(SegMeta) + uint64_t(cap) * 12;
 
   if (n) {
     uint64_t *d_k0 = nullptr, *d_k1 = nullptr;
-    uint32_t *d_v0 = nullptr, *d_v1 = nullptr;
+    uint32_t *d_v0 = nullptr, *d_v1 = nullptr, *d_seg_off = nullptr;
     SQ_CUDA(E, tmp.alloc(&d_k0, n * 8));
     SQ_CUDA(E, tmp.alloc(&d_k1, n * 8));
     SQ_CUDA(E, tmp.alloc(&d_v0, n * 4));
     SQ_CUDA(E, tmp.alloc(&d_v1, n * 4));
+    SQ_CUDA(E, tmp.alloc(&d_seg_off, (size_t(n_keys) + 1) * 4));
     const int g = grid_for(n, 256, ctx->sm_count);
     k_make_sort_keys<<<g, 256, 0, st>>>(d_key, d_start, n, idx->d_ht_keys, idx->d_ht_ids, cap - 1,
                                         idx->sentinel_id, d_k0, d_v0);
@@ -324,20 +367,38 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     SQ_CUDA(E, tmp.alloc(&d_temp, temp_bytes));
     SQ_CUDA(E, ::sq_cub::cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_k0, d_k1, d_v0, d_v1, n, 0, end_bit, st));
 
-    k_finalize<<<g, 256, 0, st>>>(d_k1, d_v1, d_end, n, idx->d_start, idx->d_end, idx->d_row,
-                                  idx->d_seg_off, n_keys);
+    k_finalize<<<g, 256, 0, st>>>(d_k1, d_v1, d_end, n, idx->d_start, idx->d_re, idx->d_row, d_seg_off, n_keys);
     SQ_CUDA(E, cudaGetLastError());
 
-    // 3. running max of end inside each key segment
+    // 3. running max of end inside each key segment -> re[].x
     const uint32_t n_tiles = uint32_t((n + kScanTile - 1) / kScanTile);
     uint64_t* d_tile = nullptr;
     SQ_CUDA(E, tmp.alloc(&d_tile, size_t(n_tiles) * 8));
-    k_runmax_reduce<<<n_tiles, kScanThreads, 0, st>>>(d_k1, idx->d_end, n, d_tile);
+    k_runmax_reduce<<<n_tiles, kScanThreads, 0, st>>>(d_k1, idx->d_re, n, d_tile);
     SQ_CUDA(E, cudaGetLastError());
     k_runmax_mid<<<1, 1024, 0, st>>>(d_tile, n_tiles);
     SQ_CUDA(E, cudaGetLastError());
-    k_runmax_final<<<n_tiles, kScanThreads, 0, st>>>(d_k1, idx->d_end, n, d_tile, idx->d_runmax);
+    k_runmax_final<<<n_tiles, kScanThreads, 0, st>>>(d_k1, idx->d_re, n, d_tile);
     SQ_CUDA(E, cudaGetLastError());
+
+    // 4. per-segment bin directory (geometry on the device, offsets by a host scan: #keys is small)
+    k_seg_meta<<<(n_keys + 255) / 256, 256, 0, st>>>(d_seg_off, idx->d_start, n_keys, idx->d_meta);
+    SQ_CUDA(E, cudaGetLastError());
+    std::vector<SegMeta> h_meta(n_keys);
+    SQ_CUDA(E, cudaMemcpyAsync(h_meta.data(), idx->d_meta, size_t(n_keys) * sizeof(SegMeta), cudaMemcpyDeviceToHost, st));
+    SQ_CUDA(E, cudaStreamSynchronize(st));
+    uint64_t dir_total = 0;
+    for (auto& m : h_meta) {
+      m.dir_base = uint32_t(dir_total);
+      dir_total += uint64_t(m.nbins) + 1;
+    }
+    if (dir_total >= 0xFFFFFFFFull) return fail(E, SQ_EINVAL, "bin directory too large");
+    SQ_CUDA(E, cudaMemcpyAsync(idx->d_meta, h_meta.data(), size_t(n_keys) * sizeof(SegMeta), cudaMemcpyHostToDevice, st));
+    SQ_CUDA(E, cudaMalloc(&idx->d_dir, dir_total * 4));
+    idx->bytes += dir_total * 4;
+    k_fill_dir<<<g, 256, 0, st>>>(d_k1, idx->d_start, n, idx->d_meta, idx->d_dir);
+    SQ_CUDA(E, cudaGetLastError());
+    SQ_CUDA(E, cudaStreamSynchronize(st));  // h_meta must outlive the async copy
   }
   SQ_CUDA(E, cudaEventRecord(e1, st));
   SQ_CUDA(E, cudaStreamSynchronize(st));

@@ -24,13 +24,26 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   x ^= x >> 31; return x;
 }
 
-// Flat, tree-free build index in HBM (SoA, all arrays length n_rows, sorted by (key id, start)).
+// Per key segment: where it lives in the sorted arrays and its direct-address bin directory.
+// bin(x) = (x - min_start) >> shift ; dir[dir_base + b] = first row of the segment whose bin >= b,
+// dir[dir_base + nbins] = se.  Bins hold ~16-32 rows for uniform data, so locating the upper
+// bound of a probe costs one directory load plus a <= 5 step search inside one cache line.
+struct SegMeta {
+  uint32_t sb, se;     // [sb, se) rows of this key in the sorted arrays
+  int32_t min_start;   // start[sb]
+  uint32_t shift;
+  uint32_t dir_base;
+  uint32_t nbins;
+  uint32_t pad0, pad1;
+};
+
+// Flat, tree-free build index in HBM (all arrays length n_rows, sorted by (key id, start)).
 struct IndexView {
-  const int32_t* __restrict__ start;    // sorted starts
-  const int32_t* __restrict__ end;      // end of the same row
-  const int32_t* __restrict__ runmax;   // running max of `end` inside the key segment
+  const int32_t* __restrict__ start;    // sorted starts (searched)
+  const int2* __restrict__ re;          // .x = running max of end inside the key segment, .y = end
   const uint32_t* __restrict__ row;     // original build row (left index)
-  const uint32_t* __restrict__ seg_off; // [n_keys + 1] segment boundaries
+  const SegMeta* __restrict__ meta;     // [n_keys]
+  const uint32_t* __restrict__ dir;     // bin directory, all segments back to back
   const uint64_t* __restrict__ ht_keys; // open-addressing table of key hashes
   const uint32_t* __restrict__ ht_ids;  // slot -> dense key id
   uint32_t ht_mask;                     // capacity - 1
@@ -82,10 +95,10 @@ struct sq_index {
   uint32_t n_keys = 0;
   // device arrays
   int32_t* d_start = nullptr;
-  int32_t* d_end = nullptr;
-  int32_t* d_runmax = nullptr;
+  int2* d_re = nullptr;
   uint32_t* d_row = nullptr;
-  uint32_t* d_seg_off = nullptr;
+  sq::SegMeta* d_meta = nullptr;
+  uint32_t* d_dir = nullptr;
   uint64_t* d_ht_keys = nullptr;
   uint32_t* d_ht_ids = nullptr;
   uint32_t ht_cap = 0;
@@ -97,7 +110,7 @@ struct sq_index {
 
   sq::IndexView view() const {
     sq::IndexView v;
-    v.start = d_start; v.end = d_end; v.runmax = d_runmax; v.row = d_row; v.seg_off = d_seg_off;
+    v.start = d_start; v.re = d_re; v.row = d_row; v.meta = d_meta; v.dir = d_dir;
     v.ht_keys = d_ht_keys; v.ht_ids = d_ht_ids; v.ht_mask = ht_cap - 1; v.sentinel_id = sentinel_id;
     v.n_keys = n_keys; v.n_rows = uint32_t(n_rows);
     return v;
@@ -123,16 +136,19 @@ struct sq_stream {
   uint64_t n_pairs = 0;
   bool counted = false;
   bool emitted = false;
-  const int32_t* d_q_start = nullptr;  // probe starts of the tile (device)
+  const uint64_t* d_q_key = nullptr;   // probe columns of the tile (device), kept for the emit pass
+  const int32_t* d_q_start = nullptr;
+  const int32_t* d_q_end = nullptr;
+  bool spec_valid = false;             // the count pass already wrote the pairs (speculative emit)
+  uint32_t* d_spec_left = nullptr;
+  uint32_t* d_spec_right = nullptr;
   const uint32_t* d_last_left = nullptr;
   const uint32_t* d_last_right = nullptr;
 
   // device scratch
   sq_buf d_in;       // staged probe key/start/end (host entry points)
-  sq_buf d_lo;       // first candidate per probe row
-  sq_buf d_ncand;    // candidate count per probe row
-  sq_buf d_cnt;      // hit count per probe row
-  sq_buf d_tile;     // per-CTA look-back words + bases
+  sq_buf d_cnt;      // hit count per probe row (rle_right)
+  sq_buf d_tile;     // per-CTA look-back words
   sq_buf d_scalar;   // n_pairs, ticket counter, cast-error slot, digest
   sq_buf d_left, d_right;  // emitted pairs (host entry points)
   sq_buf d_gather;   // gather staging
@@ -171,9 +187,10 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
 void free_index(sq_index* idx);
 
 // probe.cu
-int launch_count(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
-                 const int32_t* d_end, uint32_t n);
-int launch_write(sq_stream* s, uint32_t* d_left, uint32_t* d_right);
+// one fused pass: search -> count -> look-back scan -> write (if the pairs fit `capacity`);
+// d_left == nullptr or capacity == 0 => count only
+int launch_join(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
+                const int32_t* d_end, uint32_t n, uint32_t* d_left, uint32_t* d_right, uint64_t capacity);
 
 // gather.cu
 int launch_gather(sq_stream* s, const void* d_values, const uint32_t* d_idx, uint64_t n, uint32_t width,

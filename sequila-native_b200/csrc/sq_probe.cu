@@ -1,19 +1,24 @@
 // Probe + emit of the `Cuda` interval join: replaces the per-row loop of process_probe_batch
 // (reference interval_join.rs:1586-1618: hash_map.get -> coitrees query -> pos_vect / rle_right
-// -> index_right) with two kernels over a tile of probe rows:
+// -> index_right) with ONE fused kernel over a tile of probe rows, k_probe_join:
 //
-//   k_probe_count   one thread per probe row: key hash -> id, two binary searches in the key's
-//                   segment give the contiguous candidate range [lo, hi); each warp then walks
-//                   the 32 rows' candidate ranges as ONE flattened list (coalesced reads of end[],
-//                   no lane idles on a short list) and counts hits per row.  The CTA total goes
-//                   through a decoupled look-back so every CTA learns the output offset of its
-//                   first pair in the same pass (no separate scan kernel, no per-row offsets).
-//   k_probe_write   same flattened walk; because output offsets of consecutive probe rows are
-//                   contiguous, a warp's hits form one contiguous run of the output: position =
-//                   warp base + ballot rank.  Stores of left_idx/right_idx are fully coalesced.
+//   search   one thread per probe row: key hash -> key id -> segment meta; the upper bound hi of
+//            the candidate range comes from the segment's bin directory (one load) plus a short
+//            search inside one cache line of start[]; the lower bound lo by galloping backwards
+//            from hi over the running max end.  Candidates are the contiguous rows [lo, hi).
+//   count    each warp walks the 32 rows' candidate ranges as one flattened list (coalesced
+//            reads of re[], no lane idles on a short list); hits = end >= probe start.
+//   scan     the CTA's pair total goes through a decoupled look-back, so every CTA learns the
+//            output offset of its first pair inside the same pass (count -> exclusive scan ->
+//            write without a second kernel or per-row offsets in HBM).
+//   write    same flattened walk (re[] now in L1/L2); output offsets of consecutive probe rows
+//            are contiguous, so a warp's hits are one contiguous run: position = warp base +
+//            ballot rank.  Stores of left_idx / right_idx are fully coalesced.
 //
-// Both kernels are integer/byte work bounded by HBM (or by L2 latency when the index is small);
-// tensor cores do not apply.
+// The write stage runs only if the tile's pairs fit the caller's capacity; otherwise the kernel
+// has still produced the exact pair count and per-row counts and the caller re-runs it with a
+// large enough buffer (two-phase protocol of the C ABI).  Integer/byte work bounded by HBM (or
+// by L2 when the index fits there); tensor cores do not apply.
 #include "sq_internal.cuh"
 
 namespace sq {
@@ -28,21 +33,46 @@ struct Cand {
   uint32_t nc;  // number of candidates
 };
 
-// hi = first j in [sb,se) with start[j] > qe ; lo = first j in [sb,hi) with runmax[j] >= qs
 __device__ __forceinline__ Cand find_candidates(const IndexView& iv, uint32_t id, int32_t qs, int32_t qe) {
   Cand c{0u, 0u};
-  if (id == kNoKey) return c;
-  const uint32_t sb = __ldg(iv.seg_off + id), se = __ldg(iv.seg_off + id + 1);
-  uint32_t a = sb, len = se - sb;
+  if (id == kNoKey) return c;  // key hash absent from the build side: no rows (interval_join.rs:965)
+  const SegMeta m = iv.meta[id];
+
+  // hi = first j in [sb, se) with start[j] > qe : bin directory, then a search inside the bin
+  uint32_t a, len;
+  if (qe < m.min_start) {
+    a = m.sb; len = 0;
+  } else {
+    const uint32_t off = uint32_t(qe) - uint32_t(m.min_start);
+    const uint32_t b = m.shift >= 32 ? 0u : (off >> m.shift);
+    if (b >= m.nbins) {
+      a = m.se; len = 0;
+    } else {
+      a = __ldg(iv.dir + m.dir_base + b);
+      len = __ldg(iv.dir + m.dir_base + b + 1) - a;
+    }
+  }
   while (len) {
     const uint32_t half = len >> 1;
     if (__ldg(iv.start + a + half) <= qe) { a += half + 1; len -= half + 1; } else len = half;
   }
   const uint32_t hi = a;
-  a = sb; len = hi - sb;
+  if (hi == m.sb || __ldg(&iv.re[hi - 1].x) < qs) return c;  // nothing reaches qs
+
+  // lo = first j in [sb, hi) with runmax[j] >= qs (runmax is non-decreasing): gallop back from hi
+  uint32_t right = hi - 1;  // runmax[right] >= qs
+  uint32_t left = m.sb;
+  uint32_t step = 1;
+  while (right - left >= step) {
+    const uint32_t p = right - step;
+    if (__ldg(&iv.re[p].x) >= qs) { right = p; step <<= 1; } else { left = p + 1; break; }
+  }
+  // first j in [left, right] with runmax[j] >= qs; right qualifies
+  len = right - left;
+  a = left;
   while (len) {
     const uint32_t half = len >> 1;
-    if (__ldg(iv.runmax + a + half) < qs) { a += half + 1; len -= half + 1; } else len = half;
+    if (__ldg(&iv.re[a + half].x) < qs) { a += half + 1; len -= half + 1; } else len = half;
   }
   c.lo = a;
   c.nc = hi - a;
@@ -69,14 +99,20 @@ __device__ __forceinline__ int owner_of(uint32_t incl, uint32_t t) {
   return p;
 }
 
+// bits [x, y) of a 32-bit mask, 0 <= x < y <= 32
+__device__ __forceinline__ uint32_t bit_range(uint32_t x, uint32_t y) {
+  const uint32_t hi = y >= 32 ? 0xffffffffu : ((1u << y) - 1u);
+  return hi & ~((1u << x) - 1u);
+}
+
+template <bool WRITE_RIGHT>
 __global__ void __launch_bounds__(kProbeBlock)
-k_probe_count(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __restrict__ q_start,
-              const int32_t* __restrict__ q_end, uint32_t n, uint32_t* __restrict__ lo_out,
-              uint32_t* __restrict__ nc_out, uint32_t* __restrict__ cnt_out,
-              unsigned long long* tile_state, uint64_t* __restrict__ tile_base,
-              unsigned int* ticket, unsigned long long* n_pairs_out) {
-  __shared__ uint32_t s_cnt[kProbeBlock];
+k_probe_join(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __restrict__ q_start,
+             const int32_t* __restrict__ q_end, uint32_t n, uint32_t* __restrict__ cnt_out,
+             unsigned long long* tile_state, unsigned int* ticket, unsigned long long* result,
+             uint32_t* __restrict__ left_out, uint32_t* __restrict__ right_out, uint64_t capacity) {
   __shared__ uint64_t s_wtot[kWarpsPerBlock];
+  __shared__ uint64_t s_base;
   __shared__ uint32_t s_bid;
 
   if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);  // CTAs take tiles in start order
@@ -84,7 +120,9 @@ k_probe_count(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* _
   const uint32_t bid = s_bid;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t i = bid * kProbeBlock + threadIdx.x;
+  const uint32_t tile_first = bid * kProbeBlock + warp * 32;
 
+  // ---- search -------------------------------------------------------------------------------
   Cand c{0u, 0u};
   int32_t qs = 0;
   if (i < n) {
@@ -93,40 +131,32 @@ k_probe_count(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* _
     c = find_candidates(iv, id, qs, q_end[i]);
   }
 
-  // flattened walk over the warp's candidates, counting hits per owner row
-  uint32_t* wcnt = s_cnt + warp * 32;
-  wcnt[lane] = 0;
+  // ---- count: flattened walk over the warp's candidates ----------------------------------------
   const uint32_t incl = warp_incl_sum(c.nc);
   const uint32_t excl = incl - c.nc;
   const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-  __syncwarp();
+  uint32_t cnt = 0, wcount = 0;
   for (uint32_t t0 = 0; t0 < total; t0 += 32) {
     const uint32_t t = t0 + lane;
     const int p = owner_of(incl, t);
     const uint32_t j = __shfl_sync(0xffffffffu, c.lo, p) + (t - __shfl_sync(0xffffffffu, excl, p));
     const int32_t pqs = __shfl_sync(0xffffffffu, qs, p);
-    const bool hit = (t < total) && (__ldg(iv.end + j) >= pqs);
-    const unsigned peers = __match_any_sync(0xffffffffu, hit ? p : 32 + lane);
-    if (hit && (__ffs(peers) - 1) == lane) wcnt[p] += __popc(peers);
-    __syncwarp();
+    const bool hit = (t < total) && (__ldg(&iv.re[j].y) >= pqs);
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    // my own row's share of this chunk: flattened positions [excl, incl) clipped to the chunk
+    const uint32_t a = max(excl, t0), b = min(incl, t0 + 32);
+    if (a < b) cnt += __popc(m & bit_range(a - t0, b - t0));
+    wcount += __popc(m);
   }
-  const uint32_t cnt = wcnt[lane];
-  if (i < n) {
-    lo_out[i] = c.lo;
-    nc_out[i] = c.nc;
-    cnt_out[i] = cnt;
-  }
+  if (cnt_out && i < n) cnt_out[i] = cnt;
 
-  // CTA total -> decoupled look-back -> exclusive base of this CTA
-  uint64_t wsum = cnt;
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, d);
-  if (lane == 0) s_wtot[warp] = wsum;
+  // ---- scan: CTA total -> decoupled look-back -> exclusive base of this CTA ---------------------
+  if (lane == 0) s_wtot[warp] = wcount;
   __syncthreads();
-  if (warp == 0) {
-    uint64_t agg = 0;
+  uint64_t agg = 0;
 #pragma unroll
-    for (int w = 0; w < kWarpsPerBlock; ++w) agg += s_wtot[w];
+  for (int w = 0; w < kWarpsPerBlock; ++w) agg += s_wtot[w];
+  if (warp == 0) {
     if (lane == 0)
       atomicExch(tile_state + bid, (unsigned long long)((bid == 0 ? kFlagInc : kFlagAgg) | agg));
     uint64_t excl_base = 0;
@@ -152,49 +182,28 @@ k_probe_count(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* _
       if (lane == 0) atomicExch(tile_state + bid, (unsigned long long)(kFlagInc | (excl_base + agg)));
     }
     if (lane == 0) {
-      tile_base[bid] = excl_base;
-      if (bid == gridDim.x - 1) *n_pairs_out = excl_base + agg;
+      s_base = excl_base;
+      if (bid == gridDim.x - 1) result[0] = excl_base + agg;
     }
   }
-}
-
-template <bool WRITE_RIGHT>
-__global__ void __launch_bounds__(kProbeBlock)
-k_probe_write(IndexView iv, const int32_t* __restrict__ q_start, uint32_t n,
-              const uint32_t* __restrict__ lo_in, const uint32_t* __restrict__ nc_in,
-              const uint32_t* __restrict__ cnt_in, const uint64_t* __restrict__ tile_base,
-              uint32_t* __restrict__ left_out, uint32_t* __restrict__ right_out) {
-  __shared__ uint64_t s_wtot[kWarpsPerBlock];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t i = blockIdx.x * kProbeBlock + threadIdx.x;
-  const uint32_t tile_first = blockIdx.x * kProbeBlock + warp * 32;
-
-  uint32_t lo = 0, nc = 0, cnt = 0;
-  int32_t qs = 0;
-  if (i < n) {
-    lo = lo_in[i];
-    nc = nc_in[i];
-    cnt = cnt_in[i];
-    qs = q_start[i];
-  }
-  uint64_t wsum = cnt;
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, d);
-  if (lane == 0) s_wtot[warp] = wsum;
+  if (left_out == nullptr) return;  // count-only pass
   __syncthreads();
-  if (wsum == 0) return;  // warp-uniform
-  uint64_t base = tile_base[blockIdx.x];
-  for (int w = 0; w < warp; ++w) base += s_wtot[w];
 
-  const uint32_t incl = warp_incl_sum(nc);
-  const uint32_t excl = incl - nc;
-  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  // ---- write -----------------------------------------------------------------------------------
+  const uint64_t cta_base = s_base;
+  if (cta_base + agg > capacity) {  // CTA-uniform: the caller's buffer is too small, report it
+    if (threadIdx.x == 0) result[1] = 1;
+    return;
+  }
+  if (wcount == 0) return;  // warp-uniform
+  uint64_t base = cta_base;
+  for (int w = 0; w < warp; ++w) base += s_wtot[w];
   for (uint32_t t0 = 0; t0 < total; t0 += 32) {
     const uint32_t t = t0 + lane;
     const int p = owner_of(incl, t);
-    const uint32_t j = __shfl_sync(0xffffffffu, lo, p) + (t - __shfl_sync(0xffffffffu, excl, p));
+    const uint32_t j = __shfl_sync(0xffffffffu, c.lo, p) + (t - __shfl_sync(0xffffffffu, excl, p));
     const int32_t pqs = __shfl_sync(0xffffffffu, qs, p);
-    const bool hit = (t < total) && (__ldg(iv.end + j) >= pqs);
+    const bool hit = (t < total) && (__ldg(&iv.re[j].y) >= pqs);
     const unsigned m = __ballot_sync(0xffffffffu, hit);
     if (hit) {
       const uint64_t pos = base + __popc(m & ((1u << lane) - 1u));
@@ -206,46 +215,27 @@ k_probe_write(IndexView iv, const int32_t* __restrict__ q_start, uint32_t n,
 }
 
 // ---------------------------------------------------------------------------------------------
-int launch_count(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
-                 const int32_t* d_end, uint32_t n) {
+int launch_join(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
+                const int32_t* d_end, uint32_t n, uint32_t* d_left, uint32_t* d_right, uint64_t capacity) {
   ErrorSlot& E = s->err;
   const uint32_t n_tiles = (n + kProbeBlock - 1) / kProbeBlock;
   int rc;
-  if ((rc = ensure(E, s->d_lo, size_t(n) * 4, false))) return rc;
-  if ((rc = ensure(E, s->d_ncand, size_t(n) * 4, false))) return rc;
   if ((rc = ensure(E, s->d_cnt, size_t(n) * 4, false))) return rc;
-  if ((rc = ensure(E, s->d_tile, size_t(n_tiles) * 16, false))) return rc;
+  if ((rc = ensure(E, s->d_tile, size_t(n_tiles) * 8, false))) return rc;
   if ((rc = ensure(E, s->d_scalar, 256, false))) return rc;
   auto* tile_state = static_cast<unsigned long long*>(s->d_tile.p);
-  auto* tile_base = reinterpret_cast<uint64_t*>(tile_state + n_tiles);
-  auto* n_pairs = static_cast<unsigned long long*>(s->d_scalar.p);
-  auto* ticket = reinterpret_cast<unsigned int*>(n_pairs + 1);
+  auto* result = static_cast<unsigned long long*>(s->d_scalar.p);  // [0] n_pairs [1] overflow [2] ticket
+  auto* ticket = reinterpret_cast<unsigned int*>(result + 2);
   SQ_CUDA(E, cudaMemsetAsync(tile_state, 0, size_t(n_tiles) * 8, s->stream));
-  SQ_CUDA(E, cudaMemsetAsync(s->d_scalar.p, 0, 16, s->stream));
-  k_probe_count<<<n_tiles, kProbeBlock, 0, s->stream>>>(
-      idx->view(), d_key, d_start, d_end, n, static_cast<uint32_t*>(s->d_lo.p),
-      static_cast<uint32_t*>(s->d_ncand.p), static_cast<uint32_t*>(s->d_cnt.p), tile_state, tile_base,
-      ticket, n_pairs);
-  SQ_CUDA(E, cudaGetLastError());
-  s->launches += 1;
-  return SQ_OK;
-}
-
-int launch_write(sq_stream* s, uint32_t* d_left, uint32_t* d_right) {
-  ErrorSlot& E = s->err;
-  const uint32_t n = s->n_rows;
-  const uint32_t n_tiles = (n + kProbeBlock - 1) / kProbeBlock;
-  auto* tile_state = static_cast<unsigned long long*>(s->d_tile.p);
-  auto* tile_base = reinterpret_cast<const uint64_t*>(tile_state + n_tiles);
-  const auto* lo = static_cast<const uint32_t*>(s->d_lo.p);
-  const auto* nc = static_cast<const uint32_t*>(s->d_ncand.p);
-  const auto* cnt = static_cast<const uint32_t*>(s->d_cnt.p);
-  if (d_right)
-    k_probe_write<true><<<n_tiles, kProbeBlock, 0, s->stream>>>(s->idx->view(), s->d_q_start, n, lo, nc, cnt,
-                                                               tile_base, d_left, d_right);
+  SQ_CUDA(E, cudaMemsetAsync(result, 0, 32, s->stream));
+  if (capacity == 0) d_left = nullptr;
+  auto* cnt = static_cast<uint32_t*>(s->d_cnt.p);
+  if (d_left && d_right)
+    k_probe_join<true><<<n_tiles, kProbeBlock, 0, s->stream>>>(idx->view(), d_key, d_start, d_end, n, cnt, tile_state,
+                                                              ticket, result, d_left, d_right, capacity);
   else
-    k_probe_write<false><<<n_tiles, kProbeBlock, 0, s->stream>>>(s->idx->view(), s->d_q_start, n, lo, nc, cnt,
-                                                                tile_base, d_left, nullptr);
+    k_probe_join<false><<<n_tiles, kProbeBlock, 0, s->stream>>>(idx->view(), d_key, d_start, d_end, n, cnt, tile_state,
+                                                               ticket, result, d_left, nullptr, capacity);
   SQ_CUDA(E, cudaGetLastError());
   s->launches += 1;
   return SQ_OK;

@@ -176,6 +176,20 @@ class CudaStream:
         self.probe_count(index, key_hash, start, end)
         return self.emit_pairs()
 
+    def probe_join(self, index: CudaIndex, key_hash, start, end, out):
+        """sq_probe_join: one fused call into caller buffers out=(left, right|None, counts|None).
+        Raises SequilaCudaError(code 5) with .n_pairs set when `left` is too small."""
+        k, s, e = _np(key_hash, np.uint64), _np(start, np.int32), _np(end, np.int32)
+        left, r, c = out
+        n = C.c_uint64(0)
+        rc = self._lib.sq_probe_join(self._h, index._h, _ptr(k), _ptr(s), _ptr(e), k.shape[0], _ptr(left),
+                                     _ptr(r) if r is not None else None, _ptr(c) if c is not None else None,
+                                     left.shape[0], C.byref(n))
+        self._keep = index
+        self.n_rows, self.n_pairs = int(k.shape[0]), int(n.value)
+        _check(rc, self._err)
+        return self.n_pairs
+
     def gather_build(self, col_id: int, dtype, width: int | None = None) -> np.ndarray:
         dtype = np.dtype(dtype)
         out = np.empty(self.n_pairs, dtype=dtype)
@@ -207,6 +221,17 @@ class CudaStream:
         self.n_rows, self.n_pairs = int(key_hash.numel()), int(n.value)
         return self.n_pairs
 
+    def probe_join_device(self, index: CudaIndex, key_hash, start, end, left, right=None) -> int:
+        """sq_probe_join_device: fused count->scan->write pass into caller tensors."""
+        n = C.c_uint64(0)
+        rc = self._lib.sq_probe_join_device(self._h, index._h, _tptr(key_hash), _tptr(start), _tptr(end),
+                                            key_hash.numel(), _tptr(left), _tptr(right) if right is not None else None,
+                                            left.numel(), C.byref(n))
+        self._keep = (index, key_hash, start, end)
+        self.n_rows, self.n_pairs = int(key_hash.numel()), int(n.value)
+        _check(rc, self._err)
+        return self.n_pairs
+
     def emit_pairs_device(self, left, right=None):
         _check(self._lib.sq_probe_emit_pairs_device(self._h, _tptr(left), _tptr(right) if right is not None else None,
                                                     left.numel()), self._err)
@@ -235,7 +260,7 @@ class CudaStream:
     def phase_ms(self):
         out = (C.c_float * 5)()
         _check(self._lib.sq_stream_phase_ms(self._h, out), self._err)
-        return {"h2d": out[0], "count": out[1], "write": out[2], "d2h": out[3], "gather": out[4]}
+        return {"h2d": out[0], "join": out[1], "emit": out[2], "d2h": out[3], "gather": out[4]}
 
     launches = property(lambda self: int(self._lib.sq_stream_launches(self._h)))
     bytes = property(lambda self: int(self._lib.sq_stream_bytes(self._h)))

@@ -125,6 +125,53 @@ def test_probe_tiles_reuse_one_index_and_stream(cuda_ctx, oracle):
         assert np.array_equal(c, oc) and np.array_equal(canon(l, r), canon(ol, orr))
 
 
+def test_fused_join_call_and_capacity_protocol(cuda_ctx, oracle):
+    """sq_probe_join: one fused pass when the pairs fit; SQ_ECAPACITY + exact n_pairs otherwise,
+    after which sq_probe_emit_pairs completes the same tile."""
+    b, p = sn.synth.cfg4(scale=0.02)
+    ol, orr, oc = oracle.join(b["key"], b["start"], b["end"], p["key"], p["start"], p["end"])
+    idx = sn.CudaIndex.build(cuda_ctx, b["key"], b["start"], b["end"])
+    st = sn.CudaStream(cuda_ctx)
+    big = (np.empty(len(ol) + 7, np.uint32), np.empty(len(ol) + 7, np.uint32), np.empty(len(p["key"]), np.uint32))
+    for _ in range(2):  # second call reuses the grown speculative buffers: single pass
+        n = st.probe_join(idx, p["key"], p["start"], p["end"], big)
+        assert n == len(ol) and np.array_equal(big[2], oc)
+        assert np.array_equal(canon(big[0][:n], big[1][:n]), canon(ol, orr))
+    small = (np.empty(10, np.uint32), np.empty(10, np.uint32), None)
+    with pytest.raises(sn.SequilaCudaError) as e:
+        st.probe_join(idx, p["key"], p["start"], p["end"], small)
+    assert e.value.code == 5 and st.n_pairs == len(ol)
+    l, r, c = st.emit_pairs()
+    assert np.array_equal(canon(l, r), canon(ol, orr)) and np.array_equal(c, oc)
+
+
+def test_device_entry_points(cuda_ctx, oracle):
+    import torch
+    b, p = sn.synth.cfg3(scale=0.01)
+    ol, orr, oc = oracle.join(b["key"], b["start"], b["end"], p["key"], p["start"], p["end"])
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a).to(dev)
+    idx = sn.CudaIndex.build_device(cuda_ctx, t(b["key"]), t(b["start"]), t(b["end"]),
+                                    torch.cuda.current_stream().cuda_stream)
+    st = sn.CudaStream(cuda_ctx, cuda_stream=torch.cuda.current_stream().cuda_stream)
+    pk, ps, pe = t(p["key"]), t(p["start"]), t(p["end"])
+    n = st.probe_count_device(idx, pk, ps, pe)
+    assert n == len(ol)
+    left = torch.empty(n, dtype=torch.int32, device=dev)
+    right = torch.empty(n, dtype=torch.int32, device=dev)
+    st.emit_pairs_device(left, right)
+    torch.cuda.synchronize()
+    assert np.array_equal(canon(left.cpu().numpy().view(np.uint32), right.cpu().numpy().view(np.uint32)), canon(ol, orr))
+    left.zero_(); right.zero_()
+    assert st.probe_join_device(idx, pk, ps, pe, left, right) == n
+    torch.cuda.synchronize()
+    assert np.array_equal(canon(left.cpu().numpy().view(np.uint32), right.cpu().numpy().view(np.uint32)), canon(ol, orr))
+    assert st.digest_device(left, right, n) == oracle.pair_digest(ol, orr)
+    with pytest.raises(sn.SequilaCudaError) as e:
+        st.probe_join_device(idx, pk, ps, pe, left[: n // 2], right[: n // 2])
+    assert e.value.code == 5 and st.n_pairs == n
+
+
 def test_gather_columns_match_take(cuda_ctx, oracle):
     """materialise = arrow take of every column (interval_join.rs:1620-1632)"""
     b, p = sn.synth.cfg3(scale=0.01)
