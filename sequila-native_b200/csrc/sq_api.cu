@@ -2,6 +2,7 @@
 // objects, host<->device staging and the call protocol around the kernels in sq_build.cu,
 // sq_probe.cu and sq_gather.cu.  No CPU fallback exists anywhere in this library.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "sq_internal.cuh"
@@ -106,6 +107,10 @@ SQ_API int32_t sq_ctx_create(int32_t device, sq_ctx** out) {
     return fail(g_create_err, SQ_ECUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
   }
   c->sm_count = prop.multiProcessorCount;
+  // The probe reads scattered 32-byte sectors of a multi-GB index: ask L2 to fetch exactly the
+  // sector that missed instead of the default wider granule (a hint; ignored where unsupported).
+  if (const char* g = getenv("SQ_L2_FETCH_GRANULARITY"))
+    if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(atoi(g))) != cudaSuccess) cudaGetLastError();
   *out = c;
   return SQ_OK;
 }

@@ -11,14 +11,18 @@
 //   scan     the CTA's pair total goes through a decoupled look-back, so every CTA learns the
 //            output offset of its first pair inside the same pass (count -> exclusive scan ->
 //            write without a second kernel or per-row offsets in HBM).
-//   write    same flattened walk (re[] now in L1/L2); output offsets of consecutive probe rows
-//            are contiguous, so a warp's hits are one contiguous run: position = warp base +
-//            ballot rank.  Stores of left_idx / right_idx are fully coalesced.
+//   write    output offsets of consecutive probe rows are contiguous, so a warp's hits are one
+//            contiguous run of the output.  Hits found by the count stage were staged in shared
+//            memory (build row id + owner lane), so the write stage is a coalesced smem -> HBM
+//            copy and the index is read exactly once; a warp with more hits than the stage holds
+//            (high fan-out => small, cache-resident index) re-walks its candidates instead.
 //
 // The write stage runs only if the tile's pairs fit the caller's capacity; otherwise the kernel
 // has still produced the exact pair count and per-row counts and the caller re-runs it with a
 // large enough buffer (two-phase protocol of the C ABI).  Integer/byte work bounded by HBM (or
 // by L2 when the index fits there); tensor cores do not apply.
+#include <cstdlib>
+
 #include "sq_internal.cuh"
 
 namespace sq {
@@ -105,15 +109,19 @@ __device__ __forceinline__ uint32_t bit_range(uint32_t x, uint32_t y) {
   return hi & ~((1u << x) - 1u);
 }
 
+constexpr int kStage = 384;  // hits staged per warp between the count and the write stage
+
 template <bool WRITE_RIGHT>
 __global__ void __launch_bounds__(kProbeBlock)
 k_probe_join(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __restrict__ q_start,
              const int32_t* __restrict__ q_end, uint32_t n, uint32_t* __restrict__ cnt_out,
              unsigned long long* tile_state, unsigned int* ticket, unsigned long long* result,
-             uint32_t* __restrict__ left_out, uint32_t* __restrict__ right_out, uint64_t capacity) {
+             uint32_t* __restrict__ left_out, uint32_t* __restrict__ right_out, uint64_t capacity, int stage) {
   __shared__ uint64_t s_wtot[kWarpsPerBlock];
   __shared__ uint64_t s_base;
   __shared__ uint32_t s_bid;
+  __shared__ uint32_t s_rows[kWarpsPerBlock][kStage];
+  __shared__ uint8_t s_own[kWarpsPerBlock][WRITE_RIGHT ? kStage : 4];
 
   if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);  // CTAs take tiles in start order
   __syncthreads();
@@ -146,6 +154,13 @@ k_probe_join(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __
     // my own row's share of this chunk: flattened positions [excl, incl) clipped to the chunk
     const uint32_t a = max(excl, t0), b = min(incl, t0 + 32);
     if (a < b) cnt += __popc(m & bit_range(a - t0, b - t0));
+    if (hit && stage) {  // stage the hit so the write stage never re-reads the index
+      const uint32_t k = wcount + __popc(m & ((1u << lane) - 1u));
+      if (k < kStage) {
+        s_rows[warp][k] = __ldg(iv.row + j);
+        if (WRITE_RIGHT) s_own[warp][k] = uint8_t(p);
+      }
+    }
     wcount += __popc(m);
   }
   if (cnt_out && i < n) cnt_out[i] = cnt;
@@ -198,6 +213,14 @@ k_probe_join(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __
   if (wcount == 0) return;  // warp-uniform
   uint64_t base = cta_base;
   for (int w = 0; w < warp; ++w) base += s_wtot[w];
+  if (stage && wcount <= kStage) {  // warp-uniform: coalesced copy of the staged hits
+    __syncwarp();
+    for (uint32_t k = lane; k < wcount; k += 32) {
+      left_out[base + k] = s_rows[warp][k];
+      if (WRITE_RIGHT) right_out[base + k] = tile_first + s_own[warp][k];
+    }
+    return;
+  }
   for (uint32_t t0 = 0; t0 < total; t0 += 32) {
     const uint32_t t = t0 + lane;
     const int p = owner_of(incl, t);
@@ -229,13 +252,15 @@ int launch_join(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const 
   SQ_CUDA(E, cudaMemsetAsync(tile_state, 0, size_t(n_tiles) * 8, s->stream));
   SQ_CUDA(E, cudaMemsetAsync(result, 0, 32, s->stream));
   if (capacity == 0) d_left = nullptr;
+  static const int stage_env = getenv("SQ_STAGE") ? atoi(getenv("SQ_STAGE")) : 1;
+  const int stage = (d_left != nullptr) ? stage_env : 0;
   auto* cnt = static_cast<uint32_t*>(s->d_cnt.p);
   if (d_left && d_right)
     k_probe_join<true><<<n_tiles, kProbeBlock, 0, s->stream>>>(idx->view(), d_key, d_start, d_end, n, cnt, tile_state,
-                                                              ticket, result, d_left, d_right, capacity);
+                                                              ticket, result, d_left, d_right, capacity, stage);
   else
     k_probe_join<false><<<n_tiles, kProbeBlock, 0, s->stream>>>(idx->view(), d_key, d_start, d_end, n, cnt, tile_state,
-                                                               ticket, result, d_left, nullptr, capacity);
+                                                               ticket, result, d_left, nullptr, capacity, stage);
   SQ_CUDA(E, cudaGetLastError());
   s->launches += 1;
   return SQ_OK;
