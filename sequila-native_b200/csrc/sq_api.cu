@@ -109,8 +109,16 @@ SQ_API int32_t sq_ctx_create(int32_t device, sq_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   // The probe reads scattered 32-byte sectors of a multi-GB index: ask L2 to fetch exactly the
   // sector that missed instead of the default wider granule (a hint; ignored where unsupported).
-  if (const char* g = getenv("SQ_L2_FETCH_GRANULARITY"))
-    if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(atoi(g))) != cudaSuccess) cudaGetLastError();
+  // L2 set-aside for the probe's hot read-only structure (the bin directory): see launch_join.
+  c->l2_persist_bytes = 0;
+  {
+    const char* e = getenv("SQ_L2_PERSIST_MB");
+    size_t want = size_t(e ? atoi(e) : 0) << 20;  // measured on B200: no gain for the directory, off by default
+    if (want > size_t(prop.persistingL2CacheMaxSize)) want = size_t(prop.persistingL2CacheMaxSize);
+    if (want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) c->l2_persist_bytes = want;
+    else cudaGetLastError();
+    c->l2_window_max = size_t(prop.accessPolicyMaxWindowSize);
+  }
   *out = c;
   return SQ_OK;
 }

@@ -396,6 +396,7 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     SQ_CUDA(E, cudaMemcpyAsync(idx->d_meta, h_meta.data(), size_t(n_keys) * sizeof(SegMeta), cudaMemcpyHostToDevice, st));
     SQ_CUDA(E, cudaMalloc(&idx->d_dir, dir_total * 4));
     idx->bytes += dir_total * 4;
+    idx->dir_bytes = dir_total * 4;
     k_fill_dir<<<g, 256, 0, st>>>(d_k1, idx->d_start, n, idx->d_meta, idx->d_dir);
     SQ_CUDA(E, cudaGetLastError());
     SQ_CUDA(E, cudaStreamSynchronize(st));  // h_meta must outlive the async copy

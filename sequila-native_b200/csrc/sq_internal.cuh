@@ -80,6 +80,8 @@ struct ErrorSlot {
 struct sq_ctx {
   int device = 0;
   int sm_count = 148;
+  size_t l2_persist_bytes = 0;  // L2 set-aside granted for persisting accesses
+  size_t l2_window_max = 0;
   sq::ErrorSlot err;
 };
 
@@ -99,6 +101,7 @@ struct sq_index {
   uint32_t* d_row = nullptr;
   sq::SegMeta* d_meta = nullptr;
   uint32_t* d_dir = nullptr;
+  uint64_t dir_bytes = 0;
   uint64_t* d_ht_keys = nullptr;
   uint32_t* d_ht_ids = nullptr;
   uint32_t ht_cap = 0;
@@ -132,6 +135,7 @@ struct sq_stream {
 
   // state of the tile currently between count and emit
   const sq_index* idx = nullptr;
+  const sq_index* l2_window_idx = nullptr;  // index whose directory this stream's L2 window covers
   uint32_t n_rows = 0;
   uint64_t n_pairs = 0;
   bool counted = false;

@@ -11,11 +11,9 @@
 //   scan     the CTA's pair total goes through a decoupled look-back, so every CTA learns the
 //            output offset of its first pair inside the same pass (count -> exclusive scan ->
 //            write without a second kernel or per-row offsets in HBM).
-//   write    output offsets of consecutive probe rows are contiguous, so a warp's hits are one
-//            contiguous run of the output.  Hits found by the count stage were staged in shared
-//            memory (build row id + owner lane), so the write stage is a coalesced smem -> HBM
-//            copy and the index is read exactly once; a warp with more hits than the stage holds
-//            (high fan-out => small, cache-resident index) re-walks its candidates instead.
+//   write    same flattened walk (re[] now in L1/L2); output offsets of consecutive probe rows
+//            are contiguous, so a warp's hits are one contiguous run: position = warp base +
+//            ballot rank.  Stores of left_idx / right_idx are fully coalesced.
 //
 // The write stage runs only if the tile's pairs fit the caller's capacity; otherwise the kernel
 // has still produced the exact pair count and per-row counts and the caller re-runs it with a
@@ -37,12 +35,16 @@ struct Cand {
   uint32_t nc;  // number of candidates
 };
 
+// Both searches are written as a few rounds of INDEPENDENT loads (memory-level parallelism per
+// thread) instead of dependent binary-search steps: every HBM/L2 round trip a probe row waits for
+// is one of (1) the directory entry, (2) the four sampled starts that cover its bin, (3) the five
+// speculative gallop points over runmax; the refinements that follow hit lines already in L1.
 __device__ __forceinline__ Cand find_candidates(const IndexView& iv, uint32_t id, int32_t qs, int32_t qe) {
   Cand c{0u, 0u};
   if (id == kNoKey) return c;  // key hash absent from the build side: no rows (interval_join.rs:965)
   const SegMeta m = iv.meta[id];
 
-  // hi = first j in [sb, se) with start[j] > qe : bin directory, then a search inside the bin
+  // ---- hi = first j in [sb, se) with start[j] > qe : bin directory, then a search inside the bin
   uint32_t a, len;
   if (qe < m.min_start) {
     a = m.sb; len = 0;
@@ -56,21 +58,61 @@ __device__ __forceinline__ Cand find_candidates(const IndexView& iv, uint32_t id
       len = __ldg(iv.dir + m.dir_base + b + 1) - a;
     }
   }
-  while (len) {
+  while (len > 32) {  // crowded bin (skewed data): narrow it the classic way first
     const uint32_t half = len >> 1;
     if (__ldg(iv.start + a + half) <= qe) { a += half + 1; len -= half + 1; } else len = half;
   }
-  const uint32_t hi = a;
-  if (hi == m.sb || __ldg(&iv.re[hi - 1].x) < qs) return c;  // nothing reaches qs
-
-  // lo = first j in [sb, hi) with runmax[j] >= qs (runmax is non-decreasing): gallop back from hi
-  uint32_t right = hi - 1;  // runmax[right] >= qs
-  uint32_t left = m.sb;
-  uint32_t step = 1;
-  while (right - left >= step) {
-    const uint32_t p = right - step;
-    if (__ldg(&iv.re[p].x) >= qs) { right = p; step <<= 1; } else { left = p + 1; break; }
+  if (len) {
+    // last element of each group of 8 (clamped): 4 independent loads that touch every sector of the bin
+    const int32_t* sp = iv.start + a;
+    int32_t s0 = __ldg(sp + min(7u, len - 1)), s1 = __ldg(sp + min(15u, len - 1));
+    int32_t s2 = __ldg(sp + min(23u, len - 1)), s3 = __ldg(sp + min(31u, len - 1));
+    uint32_t g = 0;  // number of whole groups that are <= qe
+    g += (7u < len && s0 <= qe);
+    g += (15u < len && s1 <= qe);
+    g += (23u < len && s2 <= qe);
+    g += (31u < len && s3 <= qe);
+    // starts are sorted, so whole groups <= qe form a prefix: the answer is inside group g
+    const uint32_t gb = 8u * g;
+    uint32_t cnt = 0;
+    if (gb < len) {
+      const uint32_t gl = min(8u, len - gb);
+      int32_t v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldg(sp + gb + min(uint32_t(k), gl - 1));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cnt += (uint32_t(k) < gl && v[k] <= qe);
+    }
+    a += gb + cnt;
   }
+  const uint32_t hi = a;
+  if (hi == m.sb) return c;
+
+  // ---- lo = first j in [sb, hi) with runmax[j] >= qs (runmax non-decreasing): speculative gallop
+  const uint32_t span = hi - m.sb;  // rows available below hi
+  const int2* rp = iv.re + hi;      // rp[-d] = row hi-d
+  const int32_t r1 = __ldg(&rp[-int(min(1u, span))].x);
+  const int32_t r2 = __ldg(&rp[-int(min(2u, span))].x);
+  const int32_t r4 = __ldg(&rp[-int(min(4u, span))].x);
+  const int32_t r8 = __ldg(&rp[-int(min(8u, span))].x);
+  const int32_t r16 = __ldg(&rp[-int(min(16u, span))].x);
+  if (r1 < qs) return c;  // nothing reaches qs
+  // [left, right]: right qualifies, everything below left does not
+  uint32_t right, left;
+  if (r2 < qs) { right = hi - 1; left = hi - 1; }
+  else if (r4 < qs) { right = hi - min(2u, span); left = hi - min(4u, span) + 1; }
+  else if (r8 < qs) { right = hi - min(4u, span); left = hi - min(8u, span) + 1; }
+  else if (r16 < qs) { right = hi - min(8u, span); left = hi - min(16u, span) + 1; }
+  else {
+    right = hi - min(16u, span);
+    left = m.sb;
+    uint32_t step = 16;
+    while (right - left >= step) {
+      const uint32_t p = right - step;
+      if (__ldg(&iv.re[p].x) >= qs) { right = p; step <<= 1; } else { left = p + 1; break; }
+    }
+  }
+  if (left > right) left = right;  // clamped gallop points may coincide
   // first j in [left, right] with runmax[j] >= qs; right qualifies
   len = right - left;
   a = left;
@@ -109,19 +151,15 @@ __device__ __forceinline__ uint32_t bit_range(uint32_t x, uint32_t y) {
   return hi & ~((1u << x) - 1u);
 }
 
-constexpr int kStage = 384;  // hits staged per warp between the count and the write stage
-
 template <bool WRITE_RIGHT>
 __global__ void __launch_bounds__(kProbeBlock)
 k_probe_join(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __restrict__ q_start,
              const int32_t* __restrict__ q_end, uint32_t n, uint32_t* __restrict__ cnt_out,
              unsigned long long* tile_state, unsigned int* ticket, unsigned long long* result,
-             uint32_t* __restrict__ left_out, uint32_t* __restrict__ right_out, uint64_t capacity, int stage) {
+             uint32_t* __restrict__ left_out, uint32_t* __restrict__ right_out, uint64_t capacity) {
   __shared__ uint64_t s_wtot[kWarpsPerBlock];
   __shared__ uint64_t s_base;
   __shared__ uint32_t s_bid;
-  __shared__ uint32_t s_rows[kWarpsPerBlock][kStage];
-  __shared__ uint8_t s_own[kWarpsPerBlock][WRITE_RIGHT ? kStage : 4];
 
   if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);  // CTAs take tiles in start order
   __syncthreads();
@@ -154,13 +192,6 @@ k_probe_join(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __
     // my own row's share of this chunk: flattened positions [excl, incl) clipped to the chunk
     const uint32_t a = max(excl, t0), b = min(incl, t0 + 32);
     if (a < b) cnt += __popc(m & bit_range(a - t0, b - t0));
-    if (hit && stage) {  // stage the hit so the write stage never re-reads the index
-      const uint32_t k = wcount + __popc(m & ((1u << lane) - 1u));
-      if (k < kStage) {
-        s_rows[warp][k] = __ldg(iv.row + j);
-        if (WRITE_RIGHT) s_own[warp][k] = uint8_t(p);
-      }
-    }
     wcount += __popc(m);
   }
   if (cnt_out && i < n) cnt_out[i] = cnt;
@@ -213,14 +244,6 @@ k_probe_join(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __
   if (wcount == 0) return;  // warp-uniform
   uint64_t base = cta_base;
   for (int w = 0; w < warp; ++w) base += s_wtot[w];
-  if (stage && wcount <= kStage) {  // warp-uniform: coalesced copy of the staged hits
-    __syncwarp();
-    for (uint32_t k = lane; k < wcount; k += 32) {
-      left_out[base + k] = s_rows[warp][k];
-      if (WRITE_RIGHT) right_out[base + k] = tile_first + s_own[warp][k];
-    }
-    return;
-  }
   for (uint32_t t0 = 0; t0 < total; t0 += 32) {
     const uint32_t t = t0 + lane;
     const int p = owner_of(incl, t);
@@ -252,15 +275,27 @@ int launch_join(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const 
   SQ_CUDA(E, cudaMemsetAsync(tile_state, 0, size_t(n_tiles) * 8, s->stream));
   SQ_CUDA(E, cudaMemsetAsync(result, 0, 32, s->stream));
   if (capacity == 0) d_left = nullptr;
-  static const int stage_env = getenv("SQ_STAGE") ? atoi(getenv("SQ_STAGE")) : 1;
-  const int stage = (d_left != nullptr) ? stage_env : 0;
+  // Keep the bin directory (one random 4-byte read per probe row, ~n_rows/4 bytes) resident in the
+  // L2 set-aside: the streaming index/probe/output traffic would otherwise evict it.
+  if (s->l2_window_idx != idx && s->ctx->l2_persist_bytes && idx->dir_bytes) {
+    cudaStreamAttrValue av{};
+    size_t bytes = idx->dir_bytes;
+    if (bytes > s->ctx->l2_window_max) bytes = s->ctx->l2_window_max;
+    av.accessPolicyWindow.base_ptr = idx->d_dir;
+    av.accessPolicyWindow.num_bytes = bytes;
+    av.accessPolicyWindow.hitRatio = bytes <= s->ctx->l2_persist_bytes ? 1.0f : float(s->ctx->l2_persist_bytes) / float(bytes);
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+    s->l2_window_idx = idx;
+  }
   auto* cnt = static_cast<uint32_t*>(s->d_cnt.p);
   if (d_left && d_right)
     k_probe_join<true><<<n_tiles, kProbeBlock, 0, s->stream>>>(idx->view(), d_key, d_start, d_end, n, cnt, tile_state,
-                                                              ticket, result, d_left, d_right, capacity, stage);
+                                                              ticket, result, d_left, d_right, capacity);
   else
     k_probe_join<false><<<n_tiles, kProbeBlock, 0, s->stream>>>(idx->view(), d_key, d_start, d_end, n, cnt, tile_state,
-                                                               ticket, result, d_left, nullptr, capacity, stage);
+                                                               ticket, result, d_left, nullptr, capacity);
   SQ_CUDA(E, cudaGetLastError());
   s->launches += 1;
   return SQ_OK;
