@@ -248,7 +248,7 @@ SQ_API void sq_stream_free(sq_stream* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
   cudaStreamSynchronize(s->stream);
-  for (sq_buf* b : {&s->d_in, &s->d_cnt, &s->d_tile, &s->d_scalar, &s->d_left,
+  for (sq_buf* b : {&s->d_in, &s->d_cnt, &s->d_state, &s->d_tile, &s->d_scalar, &s->d_left,
                     &s->d_right, &s->d_gather, &s->h_in, &s->h_out, &s->h_scalar})
     release(*b);
   if (s->ev_ready) for (auto& e : s->ev) cudaEventDestroy(e);
@@ -261,7 +261,7 @@ SQ_API const char* sq_stream_last_error(const sq_stream* s) { return s ? s->err.
 SQ_API uint64_t sq_stream_bytes(const sq_stream* s) {
   if (!s) return 0;
   uint64_t t = 0;
-  for (const sq_buf* b : {&s->d_in, &s->d_cnt, &s->d_tile, &s->d_scalar, &s->d_left,
+  for (const sq_buf* b : {&s->d_in, &s->d_cnt, &s->d_state, &s->d_tile, &s->d_scalar, &s->d_left,
                           &s->d_right, &s->d_gather, &s->h_in, &s->h_out, &s->h_scalar})
     t += b->cap;
   return t;
@@ -349,9 +349,12 @@ static int32_t join_device(sq_stream* s, const sq_index* idx, const uint64_t* dk
   if (n == 0) return empty_tile(s, n_pairs_out);
   int rc;
   mark(s, 1);
-  if ((rc = launch_join(s, idx, dk, ds, de, n, d_left, d_right, capacity))) return rc;
-  mark(s, 2);
+  if ((rc = launch_count(s, idx, dk, ds, de, n))) return rc;
   const bool wrote = d_left != nullptr && capacity > 0;
+  // speculative emit: the write kernel checks n_pairs <= capacity on the device, so the whole
+  // count -> scan -> write chain is enqueued without a host round trip
+  if (wrote && (rc = launch_write(s, idx, ds, n, d_left, d_right, capacity))) return rc;
+  mark(s, 2);
   s->d_spec_left = d_left;
   s->d_spec_right = d_right;
   return finish_count(s, wrote, n_pairs_out);
@@ -435,8 +438,7 @@ SQ_API int32_t sq_probe_emit_pairs_device(sq_stream* s, uint32_t* d_left_idx_out
   if (rc) return rc;
   SQ_CUDA(s->err, cudaSetDevice(s->ctx->device));
   mark(s, 3);
-  if (s->n_pairs && (rc = launch_join(s, s->idx, s->d_q_key, s->d_q_start, s->d_q_end, s->n_rows, d_left_idx_out,
-                                      d_right_idx_out, capacity)))
+  if (s->n_pairs && (rc = launch_write(s, s->idx, s->d_q_start, s->n_rows, d_left_idx_out, d_right_idx_out, capacity)))
     return rc;
   mark(s, 4);
   s->d_last_left = d_left_idx_out;
@@ -455,11 +457,11 @@ SQ_API int32_t sq_probe_emit_pairs(sq_stream* s, uint32_t* left_idx_out, uint32_
   const size_t np = s->n_pairs;
   mark(s, 3);
   const bool reuse = s->spec_valid && s->d_spec_left == s->d_left.p && s->d_spec_right == s->d_right.p;
-  if (np && !reuse) {  // the speculative buffers were too small: grow them and run the pass again
+  if (np && !reuse) {  // the speculative buffers were too small: grow them, re-run only the write kernel
     if ((rc = ensure(E, s->d_left, np * 4, false))) return rc;
     if ((rc = ensure(E, s->d_right, np * 4, false))) return rc;
-    if ((rc = launch_join(s, s->idx, s->d_q_key, s->d_q_start, s->d_q_end, s->n_rows,
-                          static_cast<uint32_t*>(s->d_left.p), static_cast<uint32_t*>(s->d_right.p), np)))
+    if ((rc = launch_write(s, s->idx, s->d_q_start, s->n_rows, static_cast<uint32_t*>(s->d_left.p),
+                           static_cast<uint32_t*>(s->d_right.p), np)))
       return rc;
   }
   auto* dl = static_cast<uint32_t*>(s->d_left.p);

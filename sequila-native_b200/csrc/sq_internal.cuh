@@ -152,7 +152,8 @@ struct sq_stream {
   // device scratch
   sq_buf d_in;       // staged probe key/start/end (host entry points)
   sq_buf d_cnt;      // hit count per probe row (rle_right)
-  sq_buf d_tile;     // per-CTA look-back words
+  sq_buf d_state;    // per probe row: lo, nc, hit mask (3 x u32 arrays)
+  sq_buf d_tile;     // per-CTA pair totals -> offsets, + chained-scan words
   sq_buf d_scalar;   // n_pairs, ticket counter, cast-error slot, digest
   sq_buf d_left, d_right;  // emitted pairs (host entry points)
   sq_buf d_gather;   // gather staging
@@ -191,10 +192,12 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
 void free_index(sq_index* idx);
 
 // probe.cu
-// one fused pass: search -> count -> look-back scan -> write (if the pairs fit `capacity`);
-// d_left == nullptr or capacity == 0 => count only
-int launch_join(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
-                const int32_t* d_end, uint32_t n, uint32_t* d_left, uint32_t* d_right, uint64_t capacity);
+// K1 + K2: per-row state (lo, nc, hit mask, count), tile offsets, result[0] = n_pairs
+int launch_count(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
+                 const int32_t* d_end, uint32_t n);
+// K3: pairs from the saved state; sets result[1] instead of writing when n_pairs > capacity
+int launch_write(sq_stream* s, const sq_index* idx, const int32_t* d_start, uint32_t n, uint32_t* d_left,
+                 uint32_t* d_right, uint64_t capacity);
 
 // gather.cu
 int launch_gather(sq_stream* s, const void* d_values, const uint32_t* d_idx, uint64_t n, uint32_t width,

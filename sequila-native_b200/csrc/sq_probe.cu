@@ -1,24 +1,24 @@
 // Probe + emit of the `Cuda` interval join: replaces the per-row loop of process_probe_batch
 // (reference interval_join.rs:1586-1618: hash_map.get -> coitrees query -> pos_vect / rle_right
-// -> index_right) with ONE fused kernel over a tile of probe rows, k_probe_join:
+// -> index_right) with three kernels over a tile of probe rows (count -> exclusive scan -> write):
 //
-//   search   one thread per probe row: key hash -> key id -> segment meta; the upper bound hi of
-//            the candidate range comes from the segment's bin directory (one load) plus a short
-//            search inside one cache line of start[]; the lower bound lo by galloping backwards
-//            from hi over the running max end.  Candidates are the contiguous rows [lo, hi).
-//   count    each warp walks the 32 rows' candidate ranges as one flattened list (coalesced
-//            reads of re[], no lane idles on a short list); hits = end >= probe start.
-//   scan     the CTA's pair total goes through a decoupled look-back, so every CTA learns the
-//            output offset of its first pair inside the same pass (count -> exclusive scan ->
-//            write without a second kernel or per-row offsets in HBM).
-//   write    same flattened walk (re[] now in L1/L2); output offsets of consecutive probe rows
-//            are contiguous, so a warp's hits are one contiguous run: position = warp base +
-//            ballot rank.  Stores of left_idx / right_idx are fully coalesced.
+//   k_probe_count  one thread per probe row: key hash -> key id -> segment meta; the upper bound
+//                  hi of the candidate range comes from the segment's bin directory plus one round
+//                  of sampled loads inside the bin; the lower bound lo from a speculative gallop
+//                  backwards over the running max end.  Candidates are the contiguous rows [lo,hi).
+//                  Each warp then walks its 32 rows' candidate ranges as ONE flattened list
+//                  (coalesced reads, no lane idles on a short list); hits = end >= probe start.
+//                  Saved per row: lo, nc, hit bitmask (nc <= 32), hit count; per CTA: pair total.
+//   k_tile_scan    chained scan (decoupled look-back) of the CTA totals -> output offset per tile.
+//   k_probe_write  the same flattened walk driven by the saved state: hits come from the bitmask,
+//                  only row[] is read; a warp's hits are one contiguous run of the output
+//                  (position = warp base + ballot rank) so left_idx / right_idx stores coalesce.
 //
-// The write stage runs only if the tile's pairs fit the caller's capacity; otherwise the kernel
-// has still produced the exact pair count and per-row counts and the caller re-runs it with a
-// large enough buffer (two-phase protocol of the C ABI).  Integer/byte work bounded by HBM (or
-// by L2 when the index fits there); tensor cores do not apply.
+// count and write are separate kernels on purpose: a single fused kernel had every CTA wait at a
+// barrier for its look-back (21-24 % of warp stalls in ncu, profiles/r01_v2_*) while holding its
+// registers, and its write stage re-read index sectors that had left L2 in the meantime.
+// Integer/byte work bounded by HBM (or by L1/L2 when the index is cache-resident); tensor cores
+// do not apply.
 #include <cstdlib>
 
 #include "sq_internal.cuh"
@@ -151,24 +151,24 @@ __device__ __forceinline__ uint32_t bit_range(uint32_t x, uint32_t y) {
   return hi & ~((1u << x) - 1u);
 }
 
-template <bool WRITE_RIGHT>
+__device__ __forceinline__ uint32_t low_bits(uint32_t nbits) {  // nbits in [0, 32]
+  return nbits >= 32 ? 0xffffffffu : ((1u << nbits) - 1u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: search + count.  Per probe row it leaves in HBM everything the write kernel needs so that
+// nothing is searched twice: lo, nc, the hit bitmask of its candidates when nc <= 32 (bit k <=>
+// row lo+k is a hit) and the hit count (= rle_right, interval_join.rs:1604).  Per CTA: pair total.
+// ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kProbeBlock)
-k_probe_join(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __restrict__ q_start,
-             const int32_t* __restrict__ q_end, uint32_t n, uint32_t* __restrict__ cnt_out,
-             unsigned long long* tile_state, unsigned int* ticket, unsigned long long* result,
-             uint32_t* __restrict__ left_out, uint32_t* __restrict__ right_out, uint64_t capacity) {
-  __shared__ uint64_t s_wtot[kWarpsPerBlock];
-  __shared__ uint64_t s_base;
-  __shared__ uint32_t s_bid;
-
-  if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);  // CTAs take tiles in start order
-  __syncthreads();
-  const uint32_t bid = s_bid;
+k_probe_count(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __restrict__ q_start,
+              const int32_t* __restrict__ q_end, uint32_t n, uint32_t* __restrict__ lo_out,
+              uint32_t* __restrict__ nc_out, uint32_t* __restrict__ mask_out, uint32_t* __restrict__ cnt_out,
+              unsigned long long* __restrict__ tile_total) {
+  __shared__ uint32_t s_wtot[kWarpsPerBlock];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t i = bid * kProbeBlock + threadIdx.x;
-  const uint32_t tile_first = bid * kProbeBlock + warp * 32;
+  const uint32_t i = blockIdx.x * kProbeBlock + threadIdx.x;
 
-  // ---- search -------------------------------------------------------------------------------
   Cand c{0u, 0u};
   int32_t qs = 0;
   if (i < n) {
@@ -177,79 +177,166 @@ k_probe_join(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __
     c = find_candidates(iv, id, qs, q_end[i]);
   }
 
-  // ---- count: flattened walk over the warp's candidates ----------------------------------------
+  // flattened walk over the warp's candidates: lane t looks at candidate t of the concatenation
   const uint32_t incl = warp_incl_sum(c.nc);
   const uint32_t excl = incl - c.nc;
   const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-  uint32_t cnt = 0, wcount = 0;
+  const uint32_t jbase = c.lo - excl;  // row of candidate t (owned by this lane) = jbase + t
+  uint32_t cnt = 0, mask = 0;
   for (uint32_t t0 = 0; t0 < total; t0 += 32) {
     const uint32_t t = t0 + lane;
     const int p = owner_of(incl, t);
-    const uint32_t j = __shfl_sync(0xffffffffu, c.lo, p) + (t - __shfl_sync(0xffffffffu, excl, p));
+    const uint32_t j = __shfl_sync(0xffffffffu, jbase, p) + t;
     const int32_t pqs = __shfl_sync(0xffffffffu, qs, p);
     const bool hit = (t < total) && (__ldg(&iv.re[j].y) >= pqs);
     const unsigned m = __ballot_sync(0xffffffffu, hit);
     // my own row's share of this chunk: flattened positions [excl, incl) clipped to the chunk
     const uint32_t a = max(excl, t0), b = min(incl, t0 + 32);
-    if (a < b) cnt += __popc(m & bit_range(a - t0, b - t0));
-    wcount += __popc(m);
+    if (a < b) {
+      const uint32_t bits = (m >> (a - t0)) & low_bits(b - a);
+      cnt += __popc(bits);
+      if (c.nc <= 32) mask |= bits << (a - excl);
+    }
   }
-  if (cnt_out && i < n) cnt_out[i] = cnt;
-
-  // ---- scan: CTA total -> decoupled look-back -> exclusive base of this CTA ---------------------
-  if (lane == 0) s_wtot[warp] = wcount;
-  __syncthreads();
-  uint64_t agg = 0;
+  if (i < n) {
+    lo_out[i] = c.lo;
+    nc_out[i] = c.nc;
+    mask_out[i] = mask;
+    cnt_out[i] = cnt;
+  }
+  uint32_t wsum = cnt;  // <= 32 * n_rows_build fits u32 only per lane; sum per CTA in u64 below
 #pragma unroll
-  for (int w = 0; w < kWarpsPerBlock; ++w) agg += s_wtot[w];
+  for (int d = 16; d > 0; d >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, d);
+  // a warp's total can exceed 2^32 only if 32 rows each hit > 2^27 build rows; keep u64 across warps
+  if (lane == 0) s_wtot[warp] = wsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long tot = 0;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerBlock; ++w) tot += s_wtot[w];
+    tile_total[blockIdx.x] = tot;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: exclusive scan of the per-CTA pair totals (in place) -> output offset of every probe tile,
+// and the grand total.  Chained scan with decoupled look-back across CTAs of 1024 tiles each.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_tile_scan(unsigned long long* __restrict__ tile_total, uint32_t n_tiles, unsigned long long* chain_state,
+            unsigned int* ticket, unsigned long long* result) {
+  __shared__ unsigned long long s_w[32];
+  __shared__ unsigned long long s_excl;
+  __shared__ uint32_t s_bid;
+  if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t bid = s_bid;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t i = bid * 1024 + threadIdx.x;
+  const unsigned long long v = i < n_tiles ? tile_total[i] : 0ull;
+  unsigned long long inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
   if (warp == 0) {
-    if (lane == 0)
-      atomicExch(tile_state + bid, (unsigned long long)((bid == 0 ? kFlagInc : kFlagAgg) | agg));
-    uint64_t excl_base = 0;
+    unsigned long long w = s_w[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long o = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += o;
+    }
+    s_w[lane] = w;  // inclusive over warps
+    const unsigned long long agg = __shfl_sync(0xffffffffu, w, 31);
+    if (lane == 0) atomicExch(chain_state + bid, (bid == 0 ? kFlagInc : kFlagAgg) | agg);
+    unsigned long long excl_base = 0;
     if (bid > 0) {
       int64_t look = int64_t(bid) - 1;
       for (;;) {
         const int64_t k = look - lane;
-        uint64_t w = kFlagInc;  // tiles before 0 behave as a finished prefix of 0
+        unsigned long long x = kFlagInc;
         if (k >= 0) {
-          do {
-            w = *reinterpret_cast<volatile unsigned long long*>(tile_state + k);
-          } while ((w >> 62) == 0);
+          do { x = *reinterpret_cast<volatile unsigned long long*>(chain_state + k); } while ((x >> 62) == 0);
         }
-        const unsigned inc_mask = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+        const unsigned inc_mask = __ballot_sync(0xffffffffu, (x >> 62) == 2);
         const int first_inc = inc_mask ? (__ffs(inc_mask) - 1) : 32;
-        uint64_t v = (lane <= first_inc) ? (w & kValMask) : 0;
+        unsigned long long y = (lane <= first_inc) ? (x & kValMask) : 0;
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        excl_base += v;
+        for (int d = 16; d > 0; d >>= 1) y += __shfl_xor_sync(0xffffffffu, y, d);
+        excl_base += y;
         if (inc_mask) break;
         look -= 32;
       }
-      if (lane == 0) atomicExch(tile_state + bid, (unsigned long long)(kFlagInc | (excl_base + agg)));
+      if (lane == 0) atomicExch(chain_state + bid, kFlagInc | (excl_base + agg));
     }
     if (lane == 0) {
-      s_base = excl_base;
+      s_excl = excl_base;
       if (bid == gridDim.x - 1) result[0] = excl_base + agg;
     }
   }
-  if (left_out == nullptr) return;  // count-only pass
   __syncthreads();
+  if (i < n_tiles) tile_total[i] = s_excl + (warp ? s_w[warp - 1] : 0ull) + (inc - v);
+}
 
-  // ---- write -----------------------------------------------------------------------------------
-  const uint64_t cta_base = s_base;
-  if (cta_base + agg > capacity) {  // CTA-uniform: the caller's buffer is too small, report it
-    if (threadIdx.x == 0) result[1] = 1;
+// ---------------------------------------------------------------------------------------------
+// K3: write.  Same flattened walk, driven by the saved candidate ranges; a probe row with <= 32
+// candidates takes its hits from the saved bitmask (the index arrays end/runmax are not touched
+// again), wider rows re-test end[] against the probe start.  Output offsets of consecutive probe
+// rows are contiguous, so a warp's hits are one contiguous run: position = warp base + ballot
+// rank, and the stores of left_idx / right_idx are fully coalesced.
+// ---------------------------------------------------------------------------------------------
+template <bool WRITE_RIGHT>
+__global__ void __launch_bounds__(kProbeBlock)
+k_probe_write(IndexView iv, const int32_t* __restrict__ q_start, uint32_t n, const uint32_t* __restrict__ lo_in,
+              const uint32_t* __restrict__ nc_in, const uint32_t* __restrict__ mask_in,
+              const uint32_t* __restrict__ cnt_in, const unsigned long long* __restrict__ tile_base,
+              unsigned long long* result, uint32_t* __restrict__ left_out, uint32_t* __restrict__ right_out,
+              uint64_t capacity) {
+  __shared__ uint32_t s_wtot[kWarpsPerBlock];
+  if (result[0] > capacity) {  // grid-uniform: the caller's buffer is too small, report it
+    if (blockIdx.x == 0 && threadIdx.x == 0) result[1] = 1;
     return;
   }
-  if (wcount == 0) return;  // warp-uniform
-  uint64_t base = cta_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t i = blockIdx.x * kProbeBlock + threadIdx.x;
+  const uint32_t tile_first = blockIdx.x * kProbeBlock + warp * 32;
+
+  uint32_t lo = 0, nc = 0, mask = 0, cnt = 0;
+  if (i < n) {
+    lo = lo_in[i];
+    nc = nc_in[i];
+    mask = mask_in[i];
+    cnt = cnt_in[i];
+  }
+  uint32_t wsum = cnt;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, d);
+  if (lane == 0) s_wtot[warp] = wsum;
+  __syncthreads();
+  if (wsum == 0) return;  // warp-uniform
+  uint64_t base = tile_base[blockIdx.x];
   for (int w = 0; w < warp; ++w) base += s_wtot[w];
+
+  const unsigned wide = __ballot_sync(0xffffffffu, nc > 32);
+  int32_t qs = 0;
+  if (wide && i < n) qs = q_start[i];
+  const uint32_t incl = warp_incl_sum(nc);
+  const uint32_t excl = incl - nc;
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
   for (uint32_t t0 = 0; t0 < total; t0 += 32) {
     const uint32_t t = t0 + lane;
     const int p = owner_of(incl, t);
-    const uint32_t j = __shfl_sync(0xffffffffu, c.lo, p) + (t - __shfl_sync(0xffffffffu, excl, p));
-    const int32_t pqs = __shfl_sync(0xffffffffu, qs, p);
-    const bool hit = (t < total) && (__ldg(&iv.re[j].y) >= pqs);
+    const uint32_t k = t - __shfl_sync(0xffffffffu, excl, p);  // candidate k of row p
+    const uint32_t j = __shfl_sync(0xffffffffu, lo, p) + k;
+    const uint32_t bits = __shfl_sync(0xffffffffu, mask, p);
+    bool hit = (t < total) && ((bits >> (k & 31)) & 1u);
+    if (wide) {  // warp-uniform
+      const int32_t pqs = __shfl_sync(0xffffffffu, qs, p);
+      if ((wide >> p) & 1u) hit = (t < total) && (__ldg(&iv.re[j].y) >= pqs);
+    }
     const unsigned m = __ballot_sync(0xffffffffu, hit);
     if (hit) {
       const uint64_t pos = base + __popc(m & ((1u << lane) - 1u));
@@ -261,41 +348,56 @@ k_probe_join(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __
 }
 
 // ---------------------------------------------------------------------------------------------
-int launch_join(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
-                const int32_t* d_end, uint32_t n, uint32_t* d_left, uint32_t* d_right, uint64_t capacity) {
+static int ensure_probe_state(sq_stream* s, uint32_t n, uint32_t n_tiles) {
   ErrorSlot& E = s->err;
-  const uint32_t n_tiles = (n + kProbeBlock - 1) / kProbeBlock;
   int rc;
   if ((rc = ensure(E, s->d_cnt, size_t(n) * 4, false))) return rc;
-  if ((rc = ensure(E, s->d_tile, size_t(n_tiles) * 8, false))) return rc;
+  if ((rc = ensure(E, s->d_state, size_t(n) * 12, false))) return rc;
+  const size_t chain = (size_t(n_tiles) + 1023) / 1024;
+  if ((rc = ensure(E, s->d_tile, (size_t(n_tiles) + chain) * 8, false))) return rc;
   if ((rc = ensure(E, s->d_scalar, 256, false))) return rc;
-  auto* tile_state = static_cast<unsigned long long*>(s->d_tile.p);
+  return SQ_OK;
+}
+
+// K1 + K2 on the stream: per-row state, tile offsets and result[0] = n_pairs
+int launch_count(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
+                 const int32_t* d_end, uint32_t n) {
+  ErrorSlot& E = s->err;
+  const uint32_t n_tiles = (n + kProbeBlock - 1) / kProbeBlock;
+  const uint32_t n_chain = (n_tiles + 1023) / 1024;
+  int rc;
+  if ((rc = ensure_probe_state(s, n, n_tiles))) return rc;
+  auto* tile = static_cast<unsigned long long*>(s->d_tile.p);
+  auto* chain = tile + n_tiles;
   auto* result = static_cast<unsigned long long*>(s->d_scalar.p);  // [0] n_pairs [1] overflow [2] ticket
   auto* ticket = reinterpret_cast<unsigned int*>(result + 2);
-  SQ_CUDA(E, cudaMemsetAsync(tile_state, 0, size_t(n_tiles) * 8, s->stream));
+  auto* st = static_cast<uint32_t*>(s->d_state.p);
+  SQ_CUDA(E, cudaMemsetAsync(chain, 0, size_t(n_chain) * 8, s->stream));
   SQ_CUDA(E, cudaMemsetAsync(result, 0, 32, s->stream));
-  if (capacity == 0) d_left = nullptr;
-  // Keep the bin directory (one random 4-byte read per probe row, ~n_rows/4 bytes) resident in the
-  // L2 set-aside: the streaming index/probe/output traffic would otherwise evict it.
-  if (s->l2_window_idx != idx && s->ctx->l2_persist_bytes && idx->dir_bytes) {
-    cudaStreamAttrValue av{};
-    size_t bytes = idx->dir_bytes;
-    if (bytes > s->ctx->l2_window_max) bytes = s->ctx->l2_window_max;
-    av.accessPolicyWindow.base_ptr = idx->d_dir;
-    av.accessPolicyWindow.num_bytes = bytes;
-    av.accessPolicyWindow.hitRatio = bytes <= s->ctx->l2_persist_bytes ? 1.0f : float(s->ctx->l2_persist_bytes) / float(bytes);
-    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    if (cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
-    s->l2_window_idx = idx;
-  }
-  auto* cnt = static_cast<uint32_t*>(s->d_cnt.p);
-  if (d_left && d_right)
-    k_probe_join<true><<<n_tiles, kProbeBlock, 0, s->stream>>>(idx->view(), d_key, d_start, d_end, n, cnt, tile_state,
-                                                              ticket, result, d_left, d_right, capacity);
+  k_probe_count<<<n_tiles, kProbeBlock, 0, s->stream>>>(idx->view(), d_key, d_start, d_end, n, st, st + n,
+                                                        st + 2 * size_t(n), static_cast<uint32_t*>(s->d_cnt.p), tile);
+  SQ_CUDA(E, cudaGetLastError());
+  k_tile_scan<<<n_chain, 1024, 0, s->stream>>>(tile, n_tiles, chain, ticket, result);
+  SQ_CUDA(E, cudaGetLastError());
+  s->launches += 2;
+  return SQ_OK;
+}
+
+// K3 on the stream; writes nothing and sets result[1] when n_pairs > capacity
+int launch_write(sq_stream* s, const sq_index* idx, const int32_t* d_start, uint32_t n, uint32_t* d_left,
+                 uint32_t* d_right, uint64_t capacity) {
+  ErrorSlot& E = s->err;
+  const uint32_t n_tiles = (n + kProbeBlock - 1) / kProbeBlock;
+  auto* tile = static_cast<unsigned long long*>(s->d_tile.p);
+  auto* result = static_cast<unsigned long long*>(s->d_scalar.p);
+  auto* st = static_cast<uint32_t*>(s->d_state.p);
+  const auto* cnt = static_cast<const uint32_t*>(s->d_cnt.p);
+  if (d_right)
+    k_probe_write<true><<<n_tiles, kProbeBlock, 0, s->stream>>>(idx->view(), d_start, n, st, st + n, st + 2 * size_t(n),
+                                                               cnt, tile, result, d_left, d_right, capacity);
   else
-    k_probe_join<false><<<n_tiles, kProbeBlock, 0, s->stream>>>(idx->view(), d_key, d_start, d_end, n, cnt, tile_state,
-                                                               ticket, result, d_left, nullptr, capacity);
+    k_probe_write<false><<<n_tiles, kProbeBlock, 0, s->stream>>>(idx->view(), d_start, n, st, st + n, st + 2 * size_t(n),
+                                                                cnt, tile, result, d_left, nullptr, capacity);
   SQ_CUDA(E, cudaGetLastError());
   s->launches += 1;
   return SQ_OK;
