@@ -3,8 +3,8 @@
 //
 //   key hash --(device hash table)--> dense key id
 //   radix sort of (key id, start) carrying the build row
-//   per key segment: start[], re[] = {runmax, end}, row[]  (runmax = running max of end inside
-//   the segment) and a direct-address bin directory over the starts
+//   per key segment: start[], end[], runmax[], row[]  (runmax = running max of end inside the
+//   segment) and a direct-address bin directory over the starts
 //
 // A probe (qs, qe) against its key segment [sb, se) then has its hits inside the contiguous
 // candidate range [lo, hi):  hi = first j with start[j] >  qe  (all j < hi have start <= qe)
@@ -94,12 +94,12 @@ __global__ void __launch_bounds__(256) k_make_sort_keys(const uint64_t* __restri
   }
 }
 
-// After the sort: write start[], row[], re[].y = end (gathered through the permutation) and the
+// After the sort: write start[], row[], end[] (gathered through the permutation) and the
 // segment boundaries seg_off[id] = first sorted position of key id.
 __global__ void __launch_bounds__(256) k_finalize(const uint64_t* __restrict__ sorted_key,
                                                   const uint32_t* __restrict__ perm,
                                                   const int32_t* __restrict__ end_in, uint64_t n,
-                                                  int32_t* __restrict__ s_start, int2* __restrict__ s_re,
+                                                  int32_t* __restrict__ s_start, int32_t* __restrict__ s_end,
                                                   uint32_t* __restrict__ s_row,
                                                   uint32_t* __restrict__ seg_off, uint32_t n_keys) {
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) k_finalize(const uint64_t* __restrict__ s
     const uint32_t r = perm[j];
     s_start[j] = int32_t(uint32_t(k) ^ 0x80000000u);
     s_row[j] = r;
-    s_re[j] = make_int2(0, __ldg(end_in + r));
+    s_end[j] = __ldg(end_in + r);
     const uint32_t id = uint32_t(k >> 32);
     if (j == 0 || uint32_t(sorted_key[j - 1] >> 32) != id) seg_off[id] = uint32_t(j);
     if (j == n - 1) seg_off[n_keys] = uint32_t(n);
@@ -170,8 +170,8 @@ constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 __device__ __forceinline__ uint64_t scan_word(const uint64_t* __restrict__ sorted_key,
-                                              const int2* __restrict__ s_re, uint64_t j) {
-  return (sorted_key[j] & 0xFFFFFFFF00000000ull) | uint64_t(uint32_t(s_re[j].y) ^ 0x80000000u);
+                                              const int32_t* __restrict__ s_end, uint64_t j) {
+  return (sorted_key[j] & 0xFFFFFFFF00000000ull) | uint64_t(uint32_t(s_end[j]) ^ 0x80000000u);
 }
 
 __device__ __forceinline__ uint64_t warp_incl_max(uint64_t v) {
@@ -184,7 +184,7 @@ __device__ __forceinline__ uint64_t warp_incl_max(uint64_t v) {
 }
 
 __global__ void __launch_bounds__(kScanThreads) k_runmax_reduce(const uint64_t* __restrict__ sorted_key,
-                                                                const int2* __restrict__ s_re,
+                                                                const int32_t* __restrict__ s_end,
                                                                 uint64_t n, uint64_t* __restrict__ tile_max) {
   __shared__ uint64_t wmax[kScanThreads / 32];
   const uint64_t base = uint64_t(blockIdx.x) * kScanTile;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kScanThreads) k_runmax_reduce(const uint64_t* 
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
     const uint64_t j = base + uint64_t(k) * kScanThreads + threadIdx.x;
-    if (j < n) m = max(m, scan_word(sorted_key, s_re, j));
+    if (j < n) m = max(m, scan_word(sorted_key, s_end, j));
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
@@ -236,8 +236,9 @@ __global__ void __launch_bounds__(1024) k_runmax_mid(uint64_t* __restrict__ tile
 }
 
 __global__ void __launch_bounds__(kScanThreads) k_runmax_final(const uint64_t* __restrict__ sorted_key,
-                                                               int2* __restrict__ s_re, uint64_t n,
-                                                               const uint64_t* __restrict__ tile_excl) {
+                                                               const int32_t* __restrict__ s_end, uint64_t n,
+                                                               const uint64_t* __restrict__ tile_excl,
+                                                               int32_t* __restrict__ runmax) {
   __shared__ uint64_t wtot[kScanThreads / 32];
   const uint64_t base = uint64_t(blockIdx.x) * kScanTile;
   uint64_t carry = tile_excl[blockIdx.x];
@@ -245,14 +246,14 @@ __global__ void __launch_bounds__(kScanThreads) k_runmax_final(const uint64_t* _
 #pragma unroll 1
   for (int k = 0; k < kScanItems; ++k) {
     const uint64_t j = base + uint64_t(k) * kScanThreads + threadIdx.x;
-    const uint64_t v = j < n ? scan_word(sorted_key, s_re, j) : 0;
+    const uint64_t v = j < n ? scan_word(sorted_key, s_end, j) : 0;
     uint64_t inc = warp_incl_max(v);
     if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = inc;
     __syncthreads();
     uint64_t pre = carry;
     for (int w = 0; w < int(threadIdx.x >> 5); ++w) pre = max(pre, wtot[w]);
     inc = max(inc, pre);
-    if (j < n) s_re[j].x = int32_t(uint32_t(inc) ^ 0x80000000u);
+    if (j < n) runmax[j] = int32_t(uint32_t(inc) ^ 0x80000000u);
     uint64_t tot = carry;
     for (int w = 0; w < kScanThreads / 32; ++w) tot = max(tot, wtot[w]);
     carry = tot;
@@ -270,7 +271,7 @@ static inline int grid_for(uint64_t n, int threads, int sm_count, int per_sm = 8
 void free_index(sq_index* idx) {
   if (!idx) return;
   cudaSetDevice(idx->ctx->device);
-  cudaFree(idx->d_start); cudaFree(idx->d_re); cudaFree(idx->d_row);
+  cudaFree(idx->d_start); cudaFree(idx->d_runmax); cudaFree(idx->d_end); cudaFree(idx->d_row);
   cudaFree(idx->d_meta); cudaFree(idx->d_dir); cudaFree(idx->d_ht_keys); cudaFree(idx->d_ht_ids);
   for (auto& c : idx->columns) if (c.owned) cudaFree(c.d_values);
   delete idx;
@@ -340,7 +341,8 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
 
   // 2. sorted arrays
   SQ_CUDA(E, cudaMalloc(&idx->d_start, (n ? n : 1) * 4));
-  SQ_CUDA(E, cudaMalloc(&idx->d_re, (n ? n : 1) * 8));
+  SQ_CUDA(E, cudaMalloc(&idx->d_runmax, (n ? n : 1) * 4));
+  SQ_CUDA(E, cudaMalloc(&idx->d_end, (n ? n : 1) * 4));
   SQ_CUDA(E, cudaMalloc(&idx->d_row, (n ? n : 1) * 4));
   SQ_CUDA(E, cudaMalloc(&idx->d_meta, (size_t(n_keys) + 1) * sizeof(SegMeta)));
   idx->bytes = uint64_t(n ? n : 1) * 16 + (uint64_t(n_keys) + 1) * sizeof(SegMeta) + uint64_t(cap) * 12;
@@ -367,18 +369,18 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     SQ_CUDA(E, tmp.alloc(&d_temp, temp_bytes));
     SQ_CUDA(E, ::sq_cub::cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_k0, d_k1, d_v0, d_v1, n, 0, end_bit, st));
 
-    k_finalize<<<g, 256, 0, st>>>(d_k1, d_v1, d_end, n, idx->d_start, idx->d_re, idx->d_row, d_seg_off, n_keys);
+    k_finalize<<<g, 256, 0, st>>>(d_k1, d_v1, d_end, n, idx->d_start, idx->d_end, idx->d_row, d_seg_off, n_keys);
     SQ_CUDA(E, cudaGetLastError());
 
-    // 3. running max of end inside each key segment -> re[].x
+    // 3. running max of end inside each key segment
     const uint32_t n_tiles = uint32_t((n + kScanTile - 1) / kScanTile);
     uint64_t* d_tile = nullptr;
     SQ_CUDA(E, tmp.alloc(&d_tile, size_t(n_tiles) * 8));
-    k_runmax_reduce<<<n_tiles, kScanThreads, 0, st>>>(d_k1, idx->d_re, n, d_tile);
+    k_runmax_reduce<<<n_tiles, kScanThreads, 0, st>>>(d_k1, idx->d_end, n, d_tile);
     SQ_CUDA(E, cudaGetLastError());
     k_runmax_mid<<<1, 1024, 0, st>>>(d_tile, n_tiles);
     SQ_CUDA(E, cudaGetLastError());
-    k_runmax_final<<<n_tiles, kScanThreads, 0, st>>>(d_k1, idx->d_re, n, d_tile);
+    k_runmax_final<<<n_tiles, kScanThreads, 0, st>>>(d_k1, idx->d_end, n, d_tile, idx->d_runmax);
     SQ_CUDA(E, cudaGetLastError());
 
     // 4. per-segment bin directory (geometry on the device, offsets by a host scan: #keys is small)

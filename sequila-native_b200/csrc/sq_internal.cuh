@@ -40,7 +40,8 @@ struct SegMeta {
 // Flat, tree-free build index in HBM (all arrays length n_rows, sorted by (key id, start)).
 struct IndexView {
   const int32_t* __restrict__ start;    // sorted starts (searched)
-  const int2* __restrict__ re;          // .x = running max of end inside the key segment, .y = end
+  const int32_t* __restrict__ runmax;   // running max of end inside the key segment (non-decreasing)
+  const int32_t* __restrict__ end;      // end of the same row
   const uint32_t* __restrict__ row;     // original build row (left index)
   const SegMeta* __restrict__ meta;     // [n_keys]
   const uint32_t* __restrict__ dir;     // bin directory, all segments back to back
@@ -97,7 +98,8 @@ struct sq_index {
   uint32_t n_keys = 0;
   // device arrays
   int32_t* d_start = nullptr;
-  int2* d_re = nullptr;
+  int32_t* d_runmax = nullptr;
+  int32_t* d_end = nullptr;
   uint32_t* d_row = nullptr;
   sq::SegMeta* d_meta = nullptr;
   uint32_t* d_dir = nullptr;
@@ -113,7 +115,7 @@ struct sq_index {
 
   sq::IndexView view() const {
     sq::IndexView v;
-    v.start = d_start; v.re = d_re; v.row = d_row; v.meta = d_meta; v.dir = d_dir;
+    v.start = d_start; v.runmax = d_runmax; v.end = d_end; v.row = d_row; v.meta = d_meta; v.dir = d_dir;
     v.ht_keys = d_ht_keys; v.ht_ids = d_ht_ids; v.ht_mask = ht_cap - 1; v.sentinel_id = sentinel_id;
     v.n_keys = n_keys; v.n_rows = uint32_t(n_rows);
     return v;

@@ -90,12 +90,12 @@ __device__ __forceinline__ Cand find_candidates(const IndexView& iv, uint32_t id
 
   // ---- lo = first j in [sb, hi) with runmax[j] >= qs (runmax non-decreasing): speculative gallop
   const uint32_t span = hi - m.sb;  // rows available below hi
-  const int2* rp = iv.re + hi;      // rp[-d] = row hi-d
-  const int32_t r1 = __ldg(&rp[-int(min(1u, span))].x);
-  const int32_t r2 = __ldg(&rp[-int(min(2u, span))].x);
-  const int32_t r4 = __ldg(&rp[-int(min(4u, span))].x);
-  const int32_t r8 = __ldg(&rp[-int(min(8u, span))].x);
-  const int32_t r16 = __ldg(&rp[-int(min(16u, span))].x);
+  const int32_t* rp = iv.runmax + hi;  // rp[-d] = row hi-d
+  const int32_t r1 = __ldg(rp - int(min(1u, span)));
+  const int32_t r2 = __ldg(rp - int(min(2u, span)));
+  const int32_t r4 = __ldg(rp - int(min(4u, span)));
+  const int32_t r8 = __ldg(rp - int(min(8u, span)));
+  const int32_t r16 = __ldg(rp - int(min(16u, span)));
   if (r1 < qs) return c;  // nothing reaches qs
   // [left, right]: right qualifies, everything below left does not
   uint32_t right, left;
@@ -109,7 +109,7 @@ __device__ __forceinline__ Cand find_candidates(const IndexView& iv, uint32_t id
     uint32_t step = 16;
     while (right - left >= step) {
       const uint32_t p = right - step;
-      if (__ldg(&iv.re[p].x) >= qs) { right = p; step <<= 1; } else { left = p + 1; break; }
+      if (__ldg(iv.runmax + p) >= qs) { right = p; step <<= 1; } else { left = p + 1; break; }
     }
   }
   if (left > right) left = right;  // clamped gallop points may coincide
@@ -118,7 +118,7 @@ __device__ __forceinline__ Cand find_candidates(const IndexView& iv, uint32_t id
   a = left;
   while (len) {
     const uint32_t half = len >> 1;
-    if (__ldg(&iv.re[a + half].x) < qs) { a += half + 1; len -= half + 1; } else len = half;
+    if (__ldg(iv.runmax + a + half) < qs) { a += half + 1; len -= half + 1; } else len = half;
   }
   c.lo = a;
   c.nc = hi - a;
@@ -134,25 +134,53 @@ __device__ __forceinline__ uint32_t warp_incl_sum(uint32_t v) {
   return v;
 }
 
-// Owner row (lane) of flattened candidate t: number of lanes whose inclusive prefix <= t.
-__device__ __forceinline__ int owner_of(uint32_t incl, uint32_t t) {
-  int p = 0;
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const uint32_t v = __shfl_sync(0xffffffffu, incl, p + s - 1);
-    if (v <= t) p += s;
-  }
-  return p;
-}
-
-// bits [x, y) of a 32-bit mask, 0 <= x < y <= 32
-__device__ __forceinline__ uint32_t bit_range(uint32_t x, uint32_t y) {
-  const uint32_t hi = y >= 32 ? 0xffffffffu : ((1u << y) - 1u);
-  return hi & ~((1u << x) - 1u);
-}
-
 __device__ __forceinline__ uint32_t low_bits(uint32_t nbits) {  // nbits in [0, 32]
   return nbits >= 32 ? 0xffffffffu : ((1u << nbits) - 1u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Candidate walks.  A warp owns 32 probe rows, each with a contiguous candidate range [lo, lo+nc).
+//   small rows (nc <= 32) are walked FLATTENED: their ranges are concatenated and lane t takes
+//     candidate t, so no lane idles on a short list.  The owner of candidate t is found without a
+//     search: the non-empty rows are compacted to ranks 0..R-1 once per warp; per 32-candidate
+//     chunk one warp-wide OR marks where a new rank starts inside the chunk and one ballot counts
+//     the ranks already finished, so rank(t) = finished + popc(starts at or below t).
+//   big rows (nc > 32) are walked WIDE: the whole warp takes one row, 32 candidates per step.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kSmallMax = 32;  // rows with <= 32 candidates carry a hit bitmask
+
+struct Flat {
+  uint32_t r_incl;   // (rank lane) inclusive candidate prefix of the row with my rank; UINT_MAX past R
+  uint32_t r_excl;   // (rank lane) exclusive prefix
+  int r_src;         // (rank lane) lane that owns the row with my rank
+  uint32_t total;    // candidates of all small rows
+};
+
+// snc = this lane's candidate count if its row is small, else 0; inv = 32 bytes of this warp's smem
+__device__ __forceinline__ Flat flat_setup(uint32_t snc, int lane, volatile uint8_t* inv) {
+  Flat f;
+  const uint32_t incl = warp_incl_sum(snc);
+  f.total = __shfl_sync(0xffffffffu, incl, 31);
+  const unsigned nz = __ballot_sync(0xffffffffu, snc != 0);
+  const int R = __popc(nz);
+  // invert lane -> rank through shared memory: rank r is owned by the r-th non-empty lane
+  __syncwarp();
+  if (snc != 0) inv[__popc(nz & ((1u << lane) - 1u))] = uint8_t(lane);
+  __syncwarp();
+  f.r_src = lane < R ? int(inv[lane]) : 31;
+  const uint32_t i_s = __shfl_sync(0xffffffffu, incl, f.r_src);
+  const uint32_t n_s = __shfl_sync(0xffffffffu, snc, f.r_src);
+  f.r_incl = lane < R ? i_s : 0xffffffffu;
+  f.r_excl = lane < R ? i_s - n_s : 0xffffffffu;
+  return f;
+}
+
+// rank owning flattened candidate t0 + lane (valid when t0 + lane < total)
+__device__ __forceinline__ int flat_rank(const Flat& f, uint32_t t0, int lane) {
+  const uint32_t d = f.r_excl - t0;  // my rank's first candidate, relative to the chunk
+  const unsigned starts = __reduce_or_sync(0xffffffffu, (d - 1u) < 31u ? (1u << d) : 0u);  // 1 <= d <= 31
+  const int done = __popc(__ballot_sync(0xffffffffu, f.r_incl <= t0));
+  return done + __popc(starts & ((2u << lane) - 2u));  // starts at positions 1..lane
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -165,7 +193,8 @@ k_probe_count(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* _
               const int32_t* __restrict__ q_end, uint32_t n, uint32_t* __restrict__ lo_out,
               uint32_t* __restrict__ nc_out, uint32_t* __restrict__ mask_out, uint32_t* __restrict__ cnt_out,
               unsigned long long* __restrict__ tile_total) {
-  __shared__ uint32_t s_wtot[kWarpsPerBlock];
+  __shared__ unsigned long long s_tot[kWarpsPerBlock];
+  __shared__ uint8_t s_inv[kWarpsPerBlock][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t i = blockIdx.x * kProbeBlock + threadIdx.x;
 
@@ -176,44 +205,62 @@ k_probe_count(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* _
     const uint32_t id = ht_lookup(iv.ht_keys, iv.ht_ids, iv.ht_mask, iv.sentinel_id, q_key[i]);
     c = find_candidates(iv, id, qs, q_end[i]);
   }
-
-  // flattened walk over the warp's candidates: lane t looks at candidate t of the concatenation
-  const uint32_t incl = warp_incl_sum(c.nc);
-  const uint32_t excl = incl - c.nc;
-  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-  const uint32_t jbase = c.lo - excl;  // row of candidate t (owned by this lane) = jbase + t
   uint32_t cnt = 0, mask = 0;
-  for (uint32_t t0 = 0; t0 < total; t0 += 32) {
-    const uint32_t t = t0 + lane;
-    const int p = owner_of(incl, t);
-    const uint32_t j = __shfl_sync(0xffffffffu, jbase, p) + t;
-    const int32_t pqs = __shfl_sync(0xffffffffu, qs, p);
-    const bool hit = (t < total) && (__ldg(&iv.re[j].y) >= pqs);
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    // my own row's share of this chunk: flattened positions [excl, incl) clipped to the chunk
-    const uint32_t a = max(excl, t0), b = min(incl, t0 + 32);
-    if (a < b) {
-      const uint32_t bits = (m >> (a - t0)) & low_bits(b - a);
-      cnt += __popc(bits);
-      if (c.nc <= 32) mask |= bits << (a - excl);
+
+  // ---- small rows, flattened ----------------------------------------------------------------------
+  {
+    const Flat f = flat_setup(c.nc <= kSmallMax ? c.nc : 0u, lane, s_inv[warp]);
+    const uint32_t r_jbase = __shfl_sync(0xffffffffu, c.lo, f.r_src) - f.r_excl;  // candidate t -> row r_jbase + t
+    const int32_t r_qs = __shfl_sync(0xffffffffu, qs, f.r_src);
+    uint32_t r_mask = 0;  // hit mask of the row with my rank
+    for (uint32_t t0 = 0; t0 < f.total; t0 += 32) {
+      const uint32_t t = t0 + lane;
+      const int r = flat_rank(f, t0, lane);
+      const uint32_t j = __shfl_sync(0xffffffffu, r_jbase, r) + t;
+      const int32_t pqs = __shfl_sync(0xffffffffu, r_qs, r);
+      const bool hit = (t < f.total) && (__ldg(iv.end + j) >= pqs);
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      // the share of my rank's row in this chunk: positions [r_excl, r_incl) clipped to the chunk
+      const uint32_t a = max(f.r_excl, t0), b = min(f.r_incl, t0 + 32);
+      if (f.r_incl != 0xffffffffu && a < b) r_mask |= ((m >> (a - t0)) & low_bits(b - a)) << (a - f.r_excl);
     }
+    // hand the masks back from rank lanes to owner lanes
+    const unsigned nz = __ballot_sync(0xffffffffu, c.nc != 0 && c.nc <= kSmallMax);
+    const uint32_t got = __shfl_sync(0xffffffffu, r_mask, __popc(nz & ((1u << lane) - 1u)));
+    if ((nz >> lane) & 1u) { mask = got; cnt = __popc(got); }
   }
+  // ---- big rows, wide --------------------------------------------------------------------------------
+  unsigned big = __ballot_sync(0xffffffffu, c.nc > kSmallMax);
+  while (big) {
+    const int p = __ffs(big) - 1;
+    big &= big - 1;
+    const uint32_t nc_p = __shfl_sync(0xffffffffu, c.nc, p);
+    const uint32_t lo_p = __shfl_sync(0xffffffffu, c.lo, p);
+    const int32_t qs_p = __shfl_sync(0xffffffffu, qs, p);
+    uint32_t tot = 0;
+    for (uint32_t k0 = 0; k0 < nc_p; k0 += 32) {
+      const uint32_t k = k0 + lane;
+      const bool hit = k < nc_p && (__ldg(iv.end + lo_p + k) >= qs_p);
+      tot += __popc(__ballot_sync(0xffffffffu, hit));
+    }
+    if (lane == p) cnt = tot;
+  }
+
   if (i < n) {
     lo_out[i] = c.lo;
     nc_out[i] = c.nc;
     mask_out[i] = mask;
     cnt_out[i] = cnt;
   }
-  uint32_t wsum = cnt;  // <= 32 * n_rows_build fits u32 only per lane; sum per CTA in u64 below
+  unsigned long long wsum = cnt;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, d);
-  // a warp's total can exceed 2^32 only if 32 rows each hit > 2^27 build rows; keep u64 across warps
-  if (lane == 0) s_wtot[warp] = wsum;
+  if (lane == 0) s_tot[warp] = wsum;
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long tot = 0;
 #pragma unroll
-    for (int w = 0; w < kWarpsPerBlock; ++w) tot += s_wtot[w];
+    for (int w = 0; w < kWarpsPerBlock; ++w) tot += s_tot[w];
     tile_total[blockIdx.x] = tot;
   }
 }
@@ -282,11 +329,11 @@ k_tile_scan(unsigned long long* __restrict__ tile_total, uint32_t n_tiles, unsig
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3: write.  Same flattened walk, driven by the saved candidate ranges; a probe row with <= 32
-// candidates takes its hits from the saved bitmask (the index arrays end/runmax are not touched
-// again), wider rows re-test end[] against the probe start.  Output offsets of consecutive probe
-// rows are contiguous, so a warp's hits are one contiguous run: position = warp base + ballot
-// rank, and the stores of left_idx / right_idx are fully coalesced.
+// K3: write.  The same walks, driven by the saved state; a small row takes its hits from the saved
+// bitmask (end/runmax are not touched again), big rows re-test end[] against the probe start.
+// Output offsets of consecutive probe rows are contiguous: row p's pairs start at warp base +
+// exclusive prefix of the hit counts, and hit k of a row lands at that offset + popc(mask below
+// k), so the stores of left_idx / right_idx fill dense runs of the output.
 // ---------------------------------------------------------------------------------------------
 template <bool WRITE_RIGHT>
 __global__ void __launch_bounds__(kProbeBlock)
@@ -295,7 +342,8 @@ k_probe_write(IndexView iv, const int32_t* __restrict__ q_start, uint32_t n, con
               const uint32_t* __restrict__ cnt_in, const unsigned long long* __restrict__ tile_base,
               unsigned long long* result, uint32_t* __restrict__ left_out, uint32_t* __restrict__ right_out,
               uint64_t capacity) {
-  __shared__ uint32_t s_wtot[kWarpsPerBlock];
+  __shared__ unsigned long long s_wtot[kWarpsPerBlock];
+  __shared__ uint8_t s_inv[kWarpsPerBlock][32];
   if (result[0] > capacity) {  // grid-uniform: the caller's buffer is too small, report it
     if (blockIdx.x == 0 && threadIdx.x == 0) result[1] = 1;
     return;
@@ -311,39 +359,61 @@ k_probe_write(IndexView iv, const int32_t* __restrict__ q_start, uint32_t n, con
     mask = mask_in[i];
     cnt = cnt_in[i];
   }
-  uint32_t wsum = cnt;
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, d);
-  if (lane == 0) s_wtot[warp] = wsum;
+  const uint32_t cincl = warp_incl_sum(cnt);  // a warp emits < 2^32 pairs unless rows hit > 2^27 builds each
+  const uint32_t wtot = __shfl_sync(0xffffffffu, cincl, 31);
+  if (lane == 0) s_wtot[warp] = wtot;
   __syncthreads();
-  if (wsum == 0) return;  // warp-uniform
+  if (wtot == 0) return;  // warp-uniform
   uint64_t base = tile_base[blockIdx.x];
   for (int w = 0; w < warp; ++w) base += s_wtot[w];
+  uint32_t* __restrict__ lout = left_out + base;
+  uint32_t* __restrict__ rout = WRITE_RIGHT ? right_out + base : nullptr;
+  const uint32_t coff = cincl - cnt;  // offset of my row's first pair inside the warp's run
 
-  const unsigned wide = __ballot_sync(0xffffffffu, nc > 32);
+  // ---- small rows, flattened over the candidates up to each row's last hit --------------------------
+  {
+    const Flat f = flat_setup(mask ? 32u - uint32_t(__clz(mask)) : 0u, lane, s_inv[warp]);
+    const uint32_t r_jbase = __shfl_sync(0xffffffffu, lo, f.r_src) - f.r_excl;
+    const uint32_t r_mask = __shfl_sync(0xffffffffu, mask, f.r_src);
+    const uint32_t r_coff = __shfl_sync(0xffffffffu, coff, f.r_src);
+    for (uint32_t t0 = 0; t0 < f.total; t0 += 32) {
+      const uint32_t t = t0 + lane;
+      const int r = flat_rank(f, t0, lane);
+      const uint32_t k = t - __shfl_sync(0xffffffffu, f.r_excl, r);  // candidate k of that row
+      const uint32_t bits = __shfl_sync(0xffffffffu, r_mask, r);
+      const uint32_t off = __shfl_sync(0xffffffffu, r_coff, r);
+      const uint32_t j = __shfl_sync(0xffffffffu, r_jbase, r) + t;  // 32-bit wrap-around is intended
+      const int src = __shfl_sync(0xffffffffu, f.r_src, r);
+      if (t < f.total && ((bits >> (k & 31)) & 1u)) {
+        const uint32_t pos = off + __popc(bits & low_bits(k & 31));
+        lout[pos] = __ldg(iv.row + j);
+        if (WRITE_RIGHT) rout[pos] = tile_first + src;
+      }
+    }
+  }
+  // ---- big rows, wide: re-test end[] ---------------------------------------------------------------------
+  unsigned big = __ballot_sync(0xffffffffu, nc > kSmallMax);
+  if (big == 0) return;
   int32_t qs = 0;
-  if (wide && i < n) qs = q_start[i];
-  const uint32_t incl = warp_incl_sum(nc);
-  const uint32_t excl = incl - nc;
-  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-  for (uint32_t t0 = 0; t0 < total; t0 += 32) {
-    const uint32_t t = t0 + lane;
-    const int p = owner_of(incl, t);
-    const uint32_t k = t - __shfl_sync(0xffffffffu, excl, p);  // candidate k of row p
-    const uint32_t j = __shfl_sync(0xffffffffu, lo, p) + k;
-    const uint32_t bits = __shfl_sync(0xffffffffu, mask, p);
-    bool hit = (t < total) && ((bits >> (k & 31)) & 1u);
-    if (wide) {  // warp-uniform
-      const int32_t pqs = __shfl_sync(0xffffffffu, qs, p);
-      if ((wide >> p) & 1u) hit = (t < total) && (__ldg(&iv.re[j].y) >= pqs);
+  if (i < n) qs = q_start[i];
+  while (big) {
+    const int p = __ffs(big) - 1;
+    big &= big - 1;
+    const uint32_t nc_p = __shfl_sync(0xffffffffu, nc, p);
+    const uint32_t lo_p = __shfl_sync(0xffffffffu, lo, p);
+    const int32_t qs_p = __shfl_sync(0xffffffffu, qs, p);
+    uint32_t run = __shfl_sync(0xffffffffu, coff, p);
+    for (uint32_t k0 = 0; k0 < nc_p; k0 += 32) {
+      const uint32_t k = k0 + lane;
+      const bool hit = k < nc_p && (__ldg(iv.end + lo_p + k) >= qs_p);
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const uint32_t pos = run + __popc(m & ((1u << lane) - 1u));
+        lout[pos] = __ldg(iv.row + lo_p + k);
+        if (WRITE_RIGHT) rout[pos] = tile_first + p;
+      }
+      run += __popc(m);
     }
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (hit) {
-      const uint64_t pos = base + __popc(m & ((1u << lane) - 1u));
-      left_out[pos] = __ldg(iv.row + j);
-      if (WRITE_RIGHT) right_out[pos] = tile_first + p;
-    }
-    base += __popc(m);
   }
 }
 
