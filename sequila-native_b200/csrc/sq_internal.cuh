@@ -26,8 +26,8 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 
 // Per key segment: where it lives in the sorted arrays and its direct-address bin directory.
 // bin(x) = (x - min_start) >> shift ; dir[dir_base + b] = first row of the segment whose bin >= b,
-// dir[dir_base + nbins] = se.  Bins hold ~16-32 rows for uniform data, so locating the upper
-// bound of a probe costs one directory load plus a <= 5 step search inside one cache line.
+// dir[dir_base + nbins] = se.  Bins hold 8-16 rows for uniform data, so locating the upper
+// bound of a probe costs one directory load plus one round of loads inside one cache line.
 struct SegMeta {
   uint32_t sb, se;     // [sb, se) rows of this key in the sorted arrays
   int32_t min_start;   // start[sb]
