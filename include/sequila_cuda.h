@@ -101,7 +101,8 @@ int32_t sq_probe_count(sq_stream* s, const sq_index* idx, const uint64_t* key_ha
                        const int32_t* start, const int32_t* end, uint32_t n_rows,
                        uint64_t* n_pairs_out);
 /* Phase 2 (IJ:1604-1618): writes the pairs of the tile just counted.
- *   left_idx_out[k]  = build row (== `pos as u32`, IJ:1590)
+ *   left_idx_out[k]  = build row (== `pos as u32`, IJ:1590); NULL = keep the pairs on the device
+ *                      only (capacity is then ignored past n_pairs; sq_gather_* calls follow)
  *   right_idx_out[k] = probe row within this tile, non-decreasing (IJ:1611-1618); may be NULL
  *   counts_out[i]    = hits of probe row i (`rle_right`, IJ:1604); may be NULL
  * The order of left hits inside one probe row is unspecified (as in the reference, where it
@@ -144,6 +145,22 @@ int32_t sq_gather_column(sq_stream* s, int32_t side, int32_t build_col_id,
 int32_t sq_gather_column_device(sq_stream* s, int32_t side, int32_t build_col_id,
                                 const void* d_probe_values, uint32_t width, void* d_out,
                                 uint64_t capacity);
+
+/* Utf8 columns (Arrow `take` of a string column, IJ:1624-1627).  Build side: offsets are n_rows+1
+ * int64 (the host concatenates the build batches, IJ:685).  Gathering is two-phase so the caller
+ * can allocate: sq_gather_utf8 computes the n_pairs+1 output offsets (32-bit, Arrow Utf8) and the
+ * byte total; sq_gather_utf8_data then copies the bytes.  Probe side (side 1): this tile's column
+ * is passed with int64 offsets. */
+int32_t sq_index_add_utf8_column(sq_index* idx, const int64_t* offsets, const uint8_t* data,
+                                 uint64_t data_bytes, int32_t* col_id_out);
+int32_t sq_gather_utf8(sq_stream* s, int32_t side, int32_t build_col_id, const int64_t* probe_offsets,
+                       const uint8_t* probe_data, uint64_t probe_data_bytes, int32_t* out_offsets,
+                       uint64_t* total_bytes_out);
+int32_t sq_gather_utf8_data(sq_stream* s, uint8_t* out_data, uint64_t capacity);
+/* Arrow validity bitmaps of payload columns: out bit k = in bit idx[k]; *null_count_out = zeros. */
+int32_t sq_index_set_validity(sq_index* idx, int32_t col_id, const uint8_t* bitmap);
+int32_t sq_gather_validity(sq_stream* s, int32_t side, int32_t build_col_id, const uint8_t* probe_bitmap,
+                           uint8_t* out_bitmap, uint64_t* null_count_out);
 
 /* ---- helpers on the boundary -------------------------------------------------------------
  * `evaluate_as_i32` for BIGINT columns (IJ:1661-1672): checked cast Int64 -> Int32 on the

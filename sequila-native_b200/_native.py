@@ -50,6 +50,11 @@ SIGNATURES = {
     "sq_stream_counts_device": (vp, [vp]),
     "sq_gather_column": (C.c_int32, [vp, C.c_int32, C.c_int32, vp, C.c_uint32, vp, C.c_uint64]),
     "sq_gather_column_device": (C.c_int32, [vp, C.c_int32, C.c_int32, vp, C.c_uint32, vp, C.c_uint64]),
+    "sq_index_add_utf8_column": (C.c_int32, [vp, vp, vp, C.c_uint64, C.POINTER(C.c_int32)]),
+    "sq_gather_utf8": (C.c_int32, [vp, C.c_int32, C.c_int32, vp, vp, C.c_uint64, vp, u64p]),
+    "sq_gather_utf8_data": (C.c_int32, [vp, vp, C.c_uint64]),
+    "sq_index_set_validity": (C.c_int32, [vp, C.c_int32, vp]),
+    "sq_gather_validity": (C.c_int32, [vp, C.c_int32, C.c_int32, vp, vp, u64p]),
     "sq_cast_i64_to_i32": (C.c_int32, [vp, vp, C.c_uint64, C.c_int64, vp]),
     "sq_pairs_digest_device": (C.c_int32, [vp, vp, vp, C.c_uint64, C.c_uint64, u64p]),
     "sq_stream_set_profiling": (C.c_int32, [vp, C.c_int32]),

@@ -249,7 +249,7 @@ SQ_API void sq_stream_free(sq_stream* s) {
   cudaSetDevice(s->ctx->device);
   cudaStreamSynchronize(s->stream);
   for (sq_buf* b : {&s->d_in, &s->d_cnt, &s->d_state, &s->d_tile, &s->d_scalar, &s->d_left,
-                    &s->d_right, &s->d_gather, &s->h_in, &s->h_out, &s->h_scalar})
+                    &s->d_right, &s->d_gather, &s->d_gather2, &s->d_chain, &s->d_strblk, &s->d_strdata, &s->h_in, &s->h_out, &s->h_scalar})
     release(*b);
   if (s->ev_ready) for (auto& e : s->ev) cudaEventDestroy(e);
   if (s->own_stream) cudaStreamDestroy(s->stream);
@@ -262,7 +262,7 @@ SQ_API uint64_t sq_stream_bytes(const sq_stream* s) {
   if (!s) return 0;
   uint64_t t = 0;
   for (const sq_buf* b : {&s->d_in, &s->d_cnt, &s->d_state, &s->d_tile, &s->d_scalar, &s->d_left,
-                          &s->d_right, &s->d_gather, &s->h_in, &s->h_out, &s->h_scalar})
+                          &s->d_right, &s->d_gather, &s->d_gather2, &s->d_chain, &s->d_strblk, &s->d_strdata, &s->h_in, &s->h_out, &s->h_scalar})
     t += b->cap;
   return t;
 }
@@ -428,7 +428,7 @@ static int32_t check_emit(sq_stream* s, const void* left, uint64_t capacity) {
   if (capacity < s->n_pairs)
     return fail(s->err, SQ_ECAPACITY, "output capacity %llu < %llu pairs", (unsigned long long)capacity,
                 (unsigned long long)s->n_pairs);
-  if (s->n_pairs && !left) return fail(s->err, SQ_EINVAL, "null left_idx_out");
+  (void)left;  // NULL left_idx_out = keep the pairs on the device only (a gather follows)
   return SQ_OK;
 }
 
@@ -436,6 +436,7 @@ SQ_API int32_t sq_probe_emit_pairs_device(sq_stream* s, uint32_t* d_left_idx_out
                                           uint64_t capacity) {
   int rc = check_emit(s, d_left_idx_out, capacity);
   if (rc) return rc;
+  if (s->n_pairs && !d_left_idx_out) return fail(s->err, SQ_EINVAL, "null d_left_idx_out");
   SQ_CUDA(s->err, cudaSetDevice(s->ctx->device));
   mark(s, 3);
   if (s->n_pairs && (rc = launch_write(s, s->idx, s->d_q_start, s->n_rows, d_left_idx_out, d_right_idx_out, capacity)))
@@ -468,7 +469,7 @@ SQ_API int32_t sq_probe_emit_pairs(sq_stream* s, uint32_t* left_idx_out, uint32_
   auto* dr = static_cast<uint32_t*>(s->d_right.p);
   mark(s, 4);
   if (np) {
-    SQ_CUDA(E, cudaMemcpyAsync(left_idx_out, dl, np * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (left_idx_out) SQ_CUDA(E, cudaMemcpyAsync(left_idx_out, dl, np * 4, cudaMemcpyDeviceToHost, s->stream));
     if (right_idx_out) SQ_CUDA(E, cudaMemcpyAsync(right_idx_out, dr, np * 4, cudaMemcpyDeviceToHost, s->stream));
   }
   if (counts_out && s->n_rows)
@@ -563,6 +564,167 @@ SQ_API int32_t sq_gather_column(sq_stream* s, int32_t side, int32_t build_col_id
   SQ_CUDA(E, cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s->stream));
   SQ_CUDA(E, cudaStreamSynchronize(s->stream));
   if (s->profiling) { s->pending |= 16u; fold_phases(s); }
+  return SQ_OK;
+}
+
+// ---- Utf8 / validity take ---------------------------------------------------------------------------
+SQ_API int32_t sq_index_add_utf8_column(sq_index* idx, const int64_t* offsets, const uint8_t* data, uint64_t data_bytes,
+                                        int32_t* col_id_out) {
+  if (!idx || !col_id_out) return SQ_EINVAL;
+  ErrorSlot& E = idx->ctx->err;
+  if (!offsets) return fail(E, SQ_EINVAL, "null utf8 offsets");
+  SQ_CUDA(E, cudaSetDevice(idx->ctx->device));
+  sq_column c;
+  c.width = 0;
+  c.owned = true;
+  c.data_bytes = data_bytes;
+  const size_t n = size_t(idx->n_rows);
+  SQ_CUDA(E, cudaMalloc(&c.d_offsets, (n + 1) * 8));
+  SQ_CUDA(E, cudaMalloc(&c.d_values, data_bytes ? data_bytes : 16));
+  cudaError_t e = cudaMemcpy(c.d_offsets, offsets, (n + 1) * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && data_bytes) e = cudaMemcpy(c.d_values, data, data_bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(c.d_offsets); cudaFree(c.d_values);
+    return fail(E, SQ_ECUDA, "H2D copy of utf8 build column: %s", cudaGetErrorString(e));
+  }
+  std::lock_guard<std::mutex> g(idx->col_mu);
+  idx->bytes += (n + 1) * 8 + data_bytes;
+  idx->columns.push_back(c);
+  *col_id_out = int32_t(idx->columns.size() - 1);
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_index_set_validity(sq_index* idx, int32_t col_id, const uint8_t* bitmap) {
+  if (!idx) return SQ_EINVAL;
+  ErrorSlot& E = idx->ctx->err;
+  std::lock_guard<std::mutex> g(idx->col_mu);
+  if (col_id < 0 || size_t(col_id) >= idx->columns.size()) return fail(E, SQ_EINVAL, "unknown build column id %d", col_id);
+  if (!bitmap) return fail(E, SQ_EINVAL, "null validity bitmap");
+  SQ_CUDA(E, cudaSetDevice(idx->ctx->device));
+  const size_t bytes = (size_t(idx->n_rows) + 7) / 8;
+  uint8_t* d = nullptr;
+  SQ_CUDA(E, cudaMalloc(&d, bytes ? bytes : 16));
+  cudaError_t e = cudaMemcpy(d, bitmap, bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(d); return fail(E, SQ_ECUDA, "H2D copy of validity: %s", cudaGetErrorString(e)); }
+  if (idx->columns[col_id].d_validity) cudaFree(idx->columns[col_id].d_validity);
+  idx->columns[col_id].d_validity = d;
+  idx->bytes += bytes;
+  return SQ_OK;
+}
+
+static int32_t pick_indices(sq_stream* s, int32_t side, const uint32_t** ix) {
+  if (!s->emitted) return fail(s->err, SQ_ESTATE, "gather called without a preceding emit");
+  if (side == 0) *ix = s->d_last_left;
+  else if (side == 1) {
+    if (!s->d_last_right && s->n_pairs) return fail(s->err, SQ_ESTATE, "right indices were not emitted on the device");
+    *ix = s->d_last_right;
+  } else return fail(s->err, SQ_EINVAL, "side must be 0 (build) or 1 (probe)");
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_gather_utf8(sq_stream* s, int32_t side, int32_t build_col_id, const int64_t* probe_offsets,
+                              const uint8_t* probe_data, uint64_t probe_data_bytes, int32_t* out_offsets,
+                              uint64_t* total_bytes_out) {
+  if (!s || !total_bytes_out) return SQ_EINVAL;
+  ErrorSlot& E = s->err;
+  const uint32_t* ix = nullptr;
+  int rc = pick_indices(s, side, &ix);
+  if (rc) return rc;
+  SQ_CUDA(E, cudaSetDevice(s->ctx->device));
+  const int64_t* d_off = nullptr;
+  const uint8_t* d_data = nullptr;
+  if (side == 0) {
+    sq_index* idx = const_cast<sq_index*>(s->idx);
+    std::lock_guard<std::mutex> g(idx->col_mu);
+    if (build_col_id < 0 || size_t(build_col_id) >= idx->columns.size() || !idx->columns[build_col_id].d_offsets)
+      return fail(E, SQ_EINVAL, "build column %d is not a utf8 column", build_col_id);
+    d_off = idx->columns[build_col_id].d_offsets;
+    d_data = static_cast<const uint8_t*>(idx->columns[build_col_id].d_values);
+  } else {
+    if (s->n_rows && !probe_offsets) return fail(E, SQ_EINVAL, "null probe utf8 offsets");
+    const size_t off_bytes = (size_t(s->n_rows) + 1) * 8;
+    if ((rc = ensure(E, s->d_gather2, off_bytes + probe_data_bytes + 32, false))) return rc;
+    auto* p = static_cast<char*>(s->d_gather2.p);
+    SQ_CUDA(E, cudaMemcpyAsync(p, probe_offsets, off_bytes, cudaMemcpyHostToDevice, s->stream));
+    if (probe_data_bytes)
+      SQ_CUDA(E, cudaMemcpyAsync(p + off_bytes, probe_data, probe_data_bytes, cudaMemcpyHostToDevice, s->stream));
+    d_off = reinterpret_cast<const int64_t*>(p);
+    d_data = reinterpret_cast<const uint8_t*>(p + off_bytes);
+  }
+  const uint64_t np = s->n_pairs;
+  if ((rc = ensure(E, s->d_gather, (np + 1) * 12 + 32, false))) return rc;
+  auto* d_out_off = static_cast<int64_t*>(s->d_gather.p);
+  uint64_t total = 0;
+  if ((rc = launch_str_offsets(s, d_off, ix, np, d_out_off, &total))) return rc;
+  if (total > 0x7FFFFFFFull)
+    return fail(E, SQ_ECAPACITY, "gathered utf8 column needs %llu bytes; Utf8 offsets are 32-bit", (unsigned long long)total);
+  if (out_offsets) {  // narrow the 64-bit device offsets on the way out
+    std::vector<int64_t> tmp(np + 1);
+    SQ_CUDA(E, cudaMemcpyAsync(tmp.data(), d_out_off, (np + 1) * 8, cudaMemcpyDeviceToHost, s->stream));
+    SQ_CUDA(E, cudaStreamSynchronize(s->stream));
+    for (uint64_t k = 0; k <= np; ++k) out_offsets[k] = int32_t(tmp[k]);
+  }
+  s->str_src_off = d_off;
+  s->str_src_data = d_data;
+  s->str_idx = ix;
+  s->str_out_off = d_out_off;
+  s->str_total = total;
+  s->str_pending = true;
+  *total_bytes_out = total;
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_gather_utf8_data(sq_stream* s, uint8_t* out_data, uint64_t capacity) {
+  if (!s) return SQ_EINVAL;
+  ErrorSlot& E = s->err;
+  if (!s->str_pending) return fail(E, SQ_ESTATE, "sq_gather_utf8_data without sq_gather_utf8");
+  if (capacity < s->str_total) return fail(E, SQ_ECAPACITY, "utf8 data capacity %llu < %llu", (unsigned long long)capacity,
+                                           (unsigned long long)s->str_total);
+  s->str_pending = false;
+  if (s->str_total == 0) return SQ_OK;
+  if (!out_data) return fail(E, SQ_EINVAL, "null utf8 output");
+  SQ_CUDA(E, cudaSetDevice(s->ctx->device));
+  int rc;
+  if ((rc = ensure(E, s->d_strdata, s->str_total, false))) return rc;
+  auto* d_out = static_cast<uint8_t*>(s->d_strdata.p);
+  if ((rc = launch_str_copy(s, s->str_src_off, s->str_src_data, s->str_idx, s->n_pairs, s->str_out_off, d_out))) return rc;
+  SQ_CUDA(E, cudaMemcpyAsync(out_data, d_out, s->str_total, cudaMemcpyDeviceToHost, s->stream));
+  SQ_CUDA(E, cudaStreamSynchronize(s->stream));
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_gather_validity(sq_stream* s, int32_t side, int32_t build_col_id, const uint8_t* probe_bitmap,
+                                  uint8_t* out_bitmap, uint64_t* null_count_out) {
+  if (!s || !null_count_out) return SQ_EINVAL;
+  ErrorSlot& E = s->err;
+  const uint32_t* ix = nullptr;
+  int rc = pick_indices(s, side, &ix);
+  if (rc) return rc;
+  SQ_CUDA(E, cudaSetDevice(s->ctx->device));
+  const uint64_t np = s->n_pairs;
+  const size_t out_bytes = (np + 7) / 8;
+  const size_t in_bytes = side == 1 ? (size_t(s->n_rows) + 7) / 8 : 0;
+  if ((rc = ensure(E, s->d_gather, out_bytes + in_bytes + 64, false))) return rc;
+  auto* d_out = static_cast<uint8_t*>(s->d_gather.p);
+  const uint8_t* d_in = nullptr;
+  if (side == 0) {
+    sq_index* idx = const_cast<sq_index*>(s->idx);
+    std::lock_guard<std::mutex> g(idx->col_mu);
+    if (build_col_id < 0 || size_t(build_col_id) >= idx->columns.size() || !idx->columns[build_col_id].d_validity)
+      return fail(E, SQ_EINVAL, "build column %d has no validity bitmap", build_col_id);
+    d_in = idx->columns[build_col_id].d_validity;
+  } else {
+    if (!probe_bitmap) return fail(E, SQ_EINVAL, "null probe validity bitmap");
+    uint8_t* d = d_out + ((out_bytes + 31) & ~size_t(31));
+    SQ_CUDA(E, cudaMemcpyAsync(d, probe_bitmap, in_bytes, cudaMemcpyHostToDevice, s->stream));
+    d_in = d;
+  }
+  if ((rc = launch_gather_bits(s, d_in, ix, np, d_out, null_count_out))) return rc;
+  if (np) {
+    if (!out_bitmap) return fail(E, SQ_EINVAL, "null validity output");
+    SQ_CUDA(E, cudaMemcpyAsync(out_bitmap, d_out, out_bytes, cudaMemcpyDeviceToHost, s->stream));
+    SQ_CUDA(E, cudaStreamSynchronize(s->stream));
+  }
   return SQ_OK;
 }
 

@@ -279,7 +279,10 @@ void free_index(sq_index* idx) {
   cudaSetDevice(idx->ctx->device);
   cudaFree(idx->d_start); cudaFree(idx->d_runmax); cudaFree(idx->d_end); cudaFree(idx->d_row);
   cudaFree(idx->d_meta); cudaFree(idx->d_dir); cudaFree(idx->d_ht_keys); cudaFree(idx->d_ht_ids);
-  for (auto& c : idx->columns) if (c.owned) cudaFree(c.d_values);
+  for (auto& c : idx->columns) {
+    if (c.owned) { cudaFree(c.d_values); cudaFree(c.d_offsets); }
+    cudaFree(c.d_validity);
+  }
   delete idx;
 }
 

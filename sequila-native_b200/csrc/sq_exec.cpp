@@ -1,0 +1,614 @@
+// Host-side exec node of the `Cuda` interval join (declared in include/sequila_exec.h): the C++
+// counterpart of IntervalJoinExec / IntervalJoinStream (reference interval_join.rs) above the C ABI
+// of include/sequila_cuda.h.  It only marshals Arrow buffers: hashing of the `on` keys, the i32
+// view of the interval columns, and one sq_* call per step; searching, emitting and `take` run on
+// the GPU.
+#include "sequila_exec.h"
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "sequila_cuda.h"
+
+#define SQ_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+using Clock = std::chrono::steady_clock;
+
+inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  x ^= x >> 31; return x;
+}
+
+enum class Kind { Fixed, Utf8, LargeUtf8 };
+
+struct ColType {
+  std::string format, name;
+  int64_t flags = 0;
+  Kind kind = Kind::Fixed;
+  uint32_t width = 0;  // bytes per value for Kind::Fixed
+};
+
+// fixed-width Arrow primitive formats -> byte width (Columnar format spec, "Data type description")
+bool parse_format(const char* f, ColType* t) {
+  t->format = f;
+  if (!strcmp(f, "u")) { t->kind = Kind::Utf8; return true; }
+  if (!strcmp(f, "U")) { t->kind = Kind::LargeUtf8; return true; }
+  t->kind = Kind::Fixed;
+  if (!strcmp(f, "c") || !strcmp(f, "C")) t->width = 1;
+  else if (!strcmp(f, "s") || !strcmp(f, "S") || !strcmp(f, "e")) t->width = 2;
+  else if (!strcmp(f, "i") || !strcmp(f, "I") || !strcmp(f, "f") || !strncmp(f, "tdD", 3) || !strncmp(f, "tts", 3) ||
+           !strncmp(f, "ttm", 3))
+    t->width = 4;
+  else if (!strcmp(f, "l") || !strcmp(f, "L") || !strcmp(f, "g") || !strncmp(f, "tdm", 3) || !strncmp(f, "ttu", 3) ||
+           !strncmp(f, "ttn", 3) || !strncmp(f, "ts", 2) || !strncmp(f, "tD", 2))
+    t->width = 8;
+  else return false;
+  return true;
+}
+
+struct Side {
+  std::vector<ColType> cols;
+};
+
+struct Owned {  // release bookkeeping of an exported array / schema
+  std::vector<void*> pinned;
+  std::vector<void*> heap;
+  std::vector<ArrowArray*> children;
+  std::vector<ArrowSchema*> schema_children;
+  std::vector<const void*> buffers;
+  std::vector<ArrowArray*> child_ptrs;
+  std::vector<ArrowSchema*> schema_child_ptrs;
+  std::string s1, s2;
+  sq_ctx* ctx = nullptr;
+};
+
+void release_array(ArrowArray* a) {
+  if (!a || !a->release) return;
+  auto* o = static_cast<Owned*>(a->private_data);
+  for (ArrowArray* c : o->children) {
+    if (c->release) c->release(c);
+    delete c;
+  }
+  for (void* p : o->pinned) sq_host_free(o->ctx, p);
+  for (void* p : o->heap) free(p);
+  delete o;
+  a->release = nullptr;
+}
+
+void release_schema(ArrowSchema* s) {
+  if (!s || !s->release) return;
+  auto* o = static_cast<Owned*>(s->private_data);
+  for (ArrowSchema* c : o->schema_children) {
+    if (c->release) c->release(c);
+    delete c;
+  }
+  delete o;
+  s->release = nullptr;
+}
+
+}  // namespace
+
+struct sq_exec {
+  sq_exec_config cfg{};
+  std::vector<int32_t> on_left, on_right, projection;
+  Side left, right;
+  sq_ctx* ctx = nullptr;
+  sq_index* index = nullptr;
+  std::vector<ArrowArray> build_batches;  // owned (moved in)
+  std::vector<int32_t> build_col_id;      // left column -> sq_index column id (or -1 when not projected)
+  std::mutex mu;
+  std::map<int32_t, sq_stream*> streams;
+  std::string err;
+  uint64_t m[16] = {};
+  bool built = false;
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    std::lock_guard<std::mutex> g(mu);
+    err = buf;
+    return code;
+  }
+};
+
+namespace {
+
+int read_side(sq_exec* e, const ArrowSchema* s, Side* out, const char* which) {
+  if (!s || !s->format || strcmp(s->format, "+s")) return e->fail(SQ_EINVAL, "%s schema is not a struct (+s)", which);
+  out->cols.resize(size_t(s->n_children));
+  for (int64_t i = 0; i < s->n_children; ++i) {
+    const ArrowSchema* c = s->children[i];
+    ColType t;
+    if (!parse_format(c->format, &t)) {
+      t.format = c->format;
+      t.width = 0;  // unsupported types are only an error if the column is actually used
+      t.kind = Kind::Fixed;
+    }
+    t.name = c->name ? c->name : "";
+    t.flags = c->flags;
+    out->cols[size_t(i)] = t;
+  }
+  return SQ_OK;
+}
+
+// value buffers of child `col` of a struct batch, honouring offsets
+struct ColView {
+  const uint8_t* validity = nullptr;
+  const uint8_t* values = nullptr;   // fixed: values ; utf8: offsets
+  const uint8_t* data = nullptr;     // utf8 bytes
+  int64_t offset = 0, length = 0, null_count = 0;
+};
+
+ColView view_of(const ArrowArray* batch, int32_t col) {
+  const ArrowArray* a = batch->children[col];
+  ColView v;
+  v.offset = a->offset + 0;
+  v.length = a->length;
+  v.null_count = a->null_count;
+  v.validity = static_cast<const uint8_t*>(a->buffers[0]);
+  v.values = static_cast<const uint8_t*>(a->n_buffers > 1 ? a->buffers[1] : nullptr);
+  v.data = static_cast<const uint8_t*>(a->n_buffers > 2 ? a->buffers[2] : nullptr);
+  return v;
+}
+
+inline bool bit_at(const uint8_t* bm, int64_t i) { return (bm[i >> 3] >> (i & 7)) & 1; }
+
+// 64-bit hash of the `on` columns of every row (IJ:1037 / IJ:1211 call create_hashes here)
+int hash_keys(sq_exec* e, const Side& side, const std::vector<int32_t>& on, const ArrowArray* batch,
+              std::vector<uint64_t>* out) {
+  const int64_t n = batch->length;
+  out->assign(size_t(n), mix64(1));  // on=[(1,1)]: every row carries the constant's hash
+  for (int32_t col : on) {
+    const ColType& t = side.cols[size_t(col)];
+    const ColView v = view_of(batch, col);
+    if (t.kind == Kind::Fixed) {
+      if (t.width != 1 && t.width != 2 && t.width != 4 && t.width != 8)
+        return e->fail(SQ_EINVAL, "key column '%s' has unsupported type '%s'", t.name.c_str(), t.format.c_str());
+      for (int64_t i = 0; i < n; ++i) {
+        uint64_t raw = 0;
+        memcpy(&raw, v.values + (v.offset + i) * t.width, t.width);
+        (*out)[size_t(i)] = mix64((*out)[size_t(i)] ^ (mix64(raw) + 0x9e3779b97f4a7c15ull));
+      }
+    } else {
+      for (int64_t i = 0; i < n; ++i) {
+        int64_t a, b;
+        if (t.kind == Kind::Utf8) {
+          const int32_t* off = reinterpret_cast<const int32_t*>(v.values) + v.offset;
+          a = off[i]; b = off[i + 1];
+        } else {
+          const int64_t* off = reinterpret_cast<const int64_t*>(v.values) + v.offset;
+          a = off[i]; b = off[i + 1];
+        }
+        uint64_t h = 0xcbf29ce484222325ull;  // FNV-1a over the bytes
+        for (int64_t k = a; k < b; ++k) { h ^= v.data[k]; h *= 0x100000001b3ull; }
+        (*out)[size_t(i)] = mix64((*out)[size_t(i)] ^ (mix64(h) + 0x9e3779b97f4a7c15ull));
+      }
+    }
+  }
+  return SQ_OK;
+}
+
+// evaluate_as_i32 (IJ:1661-1672): the interval column (or `column - 1`) as Int32, overflow is an error
+int eval_i32(sq_exec* e, sq_stream* st, const Side& side, int32_t col, bool minus_one, const ArrowArray* batch,
+             std::vector<int32_t>* out) {
+  const ColType& t = side.cols[size_t(col)];
+  const ColView v = view_of(batch, col);
+  const int64_t n = batch->length;
+  out->resize(size_t(n));
+  if (t.format == "i") {
+    const int32_t* p = reinterpret_cast<const int32_t*>(v.values) + v.offset;
+    for (int64_t i = 0; i < n; ++i) {
+      if (minus_one && p[i] == INT32_MIN) return e->fail(SQ_ECAST, "Arrow error: Arithmetic overflow: Overflow happened on: %d - 1", p[i]);
+      (*out)[size_t(i)] = p[i] - (minus_one ? 1 : 0);
+    }
+    return SQ_OK;
+  }
+  if (t.format == "l") {  // BIGINT columns (queries/q1-coitrees.sql:6,11): checked cast on the device
+    const int64_t* p = reinterpret_cast<const int64_t*>(v.values) + v.offset;
+    int rc = sq_cast_i64_to_i32(st, p, uint64_t(n), minus_one ? 1 : 0, out->data());
+    if (rc != SQ_OK) return e->fail(rc, "%s", sq_stream_last_error(st));
+    return SQ_OK;
+  }
+  return e->fail(SQ_EINVAL, "interval column '%s' must be Int32 or Int64, got '%s'", t.name.c_str(), t.format.c_str());
+}
+
+int stream_for(sq_exec* e, int32_t partition, sq_stream** out) {
+  std::lock_guard<std::mutex> g(e->mu);
+  auto it = e->streams.find(partition);
+  if (it != e->streams.end()) { *out = it->second; return SQ_OK; }
+  sq_stream* s = nullptr;
+  int rc = sq_stream_create(e->ctx, &s);
+  if (rc != SQ_OK) { e->err = sq_last_error(e->ctx); return rc; }
+  e->streams[partition] = s;
+  *out = s;
+  return SQ_OK;
+}
+
+// [left columns..., right columns...] index -> (side, column)
+inline void split_col(const sq_exec* e, int32_t pc, int* side, int32_t* col) {
+  const int32_t nl = int32_t(e->left.cols.size());
+  *side = pc < nl ? 0 : 1;
+  *col = pc < nl ? pc : pc - nl;
+}
+
+ArrowSchema* make_field(const ColType& t) {
+  auto* f = new ArrowSchema();
+  auto* o = new Owned();
+  o->s1 = t.format;
+  o->s2 = t.name;
+  f->format = o->s1.c_str();
+  f->name = o->s2.c_str();
+  f->metadata = nullptr;
+  f->flags = t.flags;
+  f->n_children = 0;
+  f->children = nullptr;
+  f->dictionary = nullptr;
+  f->release = release_schema;
+  f->private_data = o;
+  return f;
+}
+
+}  // namespace
+
+SQ_API int32_t sq_exec_create(const sq_exec_config* cfg, const ArrowSchema* left_schema, const ArrowSchema* right_schema,
+                              sq_exec** out) {
+  if (!cfg || !out) return SQ_EINVAL;
+  *out = nullptr;
+  auto e = std::make_unique<sq_exec>();
+  e->cfg = *cfg;
+  int rc;
+  if ((rc = read_side(e.get(), left_schema, &e->left, "left")) || (rc = read_side(e.get(), right_schema, &e->right, "right"))) {
+    *out = e.release();  // caller reads the message, then frees
+    return rc;
+  }
+  e->on_left.assign(cfg->on_left, cfg->on_left + (cfg->n_on > 0 ? cfg->n_on : 0));
+  e->on_right.assign(cfg->on_right, cfg->on_right + (cfg->n_on > 0 ? cfg->n_on : 0));
+  const int32_t nl = int32_t(e->left.cols.size()), nr = int32_t(e->right.cols.size());
+  if (cfg->n_projection < 0) {
+    for (int32_t i = 0; i < nl + nr; ++i) e->projection.push_back(i);
+  } else {
+    e->projection.assign(cfg->projection, cfg->projection + cfg->n_projection);
+  }
+  *out = e.get();
+  auto bad = [&](const char* what, int32_t v, int32_t lim) {
+    return v < 0 || v >= lim ? e->fail(SQ_EINVAL, "%s index %d out of range [0,%d)", what, v, lim) : SQ_OK;
+  };
+  for (int32_t c : e->on_left) if ((rc = bad("on_left", c, nl))) { e.release(); return rc; }
+  for (int32_t c : e->on_right) if ((rc = bad("on_right", c, nr))) { e.release(); return rc; }
+  for (int32_t c : e->projection) if ((rc = bad("projection", c, nl + nr))) { e.release(); return rc; }
+  if ((rc = bad("left_start", cfg->left_start, nl)) || (rc = bad("left_end", cfg->left_end, nl)) ||
+      (rc = bad("right_start", cfg->right_start, nr)) || (rc = bad("right_end", cfg->right_end, nr))) {
+    e.release();
+    return rc;
+  }
+  for (int32_t pc : e->projection) {
+    int side; int32_t col;
+    split_col(e.get(), pc, &side, &col);
+    const ColType& t = (side ? e->right : e->left).cols[size_t(col)];
+    if (t.kind == Kind::Fixed && t.width != 4 && t.width != 8 && t.width != 16 && t.width != 1 && t.width != 2) {
+      rc = e->fail(SQ_EINVAL, "output column '%s' has unsupported type '%s'", t.name.c_str(), t.format.c_str());
+      e.release();
+      return rc;
+    }
+  }
+  rc = sq_ctx_create(cfg->device, &e->ctx);
+  if (rc != SQ_OK) {  // no usable GPU: an error at execute, never a CPU fallback
+    e->err = sq_last_error(nullptr);
+    e.release();
+    return rc;
+  }
+  e.release();
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_exec_push_build(sq_exec* e, ArrowArray* batch) {
+  if (!e || !batch || !batch->release) return SQ_EINVAL;
+  if (e->built) return e->fail(SQ_ESTATE, "build side already finished");
+  if (batch->n_children != int64_t(e->left.cols.size())) return e->fail(SQ_EINVAL, "build batch has %lld columns, schema has %zu",
+                                                                         (long long)batch->n_children, e->left.cols.size());
+  e->build_batches.push_back(*batch);  // move (Arrow C data interface: shallow copy + mark source released)
+  batch->release = nullptr;
+  e->m[0] += 1;
+  e->m[1] += uint64_t(batch->length);
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_exec_finish_build(sq_exec* e) {
+  if (!e) return SQ_EINVAL;
+  if (e->built) return e->fail(SQ_ESTATE, "build side already finished");
+  const auto t0 = Clock::now();
+  uint64_t n = 0;
+  for (auto& b : e->build_batches) n += uint64_t(b.length);
+  std::vector<uint64_t> keys;
+  std::vector<int32_t> start, end;
+  keys.reserve(n); start.reserve(n); end.reserve(n);
+  sq_stream* st = nullptr;
+  int rc = stream_for(e, -1, &st);
+  if (rc) return rc;
+  std::vector<uint64_t> hk;
+  std::vector<int32_t> s32, e32;
+  for (auto& b : e->build_batches) {  // update_hashmap per batch, rows numbered across batches (IJ:667-681)
+    if ((rc = hash_keys(e, e->left, e->on_left, &b, &hk))) return rc;
+    if ((rc = eval_i32(e, st, e->left, e->cfg.left_start, false, &b, &s32))) return rc;
+    if ((rc = eval_i32(e, st, e->left, e->cfg.left_end, e->cfg.left_end_minus_one != 0, &b, &e32))) return rc;
+    keys.insert(keys.end(), hk.begin(), hk.end());
+    start.insert(start.end(), s32.begin(), s32.end());
+    end.insert(end.end(), e32.begin(), e32.end());
+  }
+  rc = sq_index_build(e->ctx, keys.data(), start.data(), end.data(), n, &e->index);
+  if (rc != SQ_OK) return e->fail(rc, "%s", sq_last_error(e->ctx));
+
+  // build-side payload columns that the projection needs become device-resident (concat_batches, IJ:685)
+  e->build_col_id.assign(e->left.cols.size(), -1);
+  for (int32_t pc : e->projection) {
+    int side; int32_t col;
+    split_col(e, pc, &side, &col);
+    if (side != 0 || e->build_col_id[size_t(col)] >= 0) continue;
+    const ColType& t = e->left.cols[size_t(col)];
+    int32_t id = -1;
+    bool any_null = false;
+    std::vector<uint8_t> validity((n + 7) / 8, 0xFF);
+    if (t.kind == Kind::Fixed) {
+      // sub-4-byte values are widened into 4-byte slots for the gather and narrowed again on output
+      const uint32_t w = t.width < 4 ? 4 : t.width;
+      std::vector<uint8_t> buf(size_t(n) * w, 0);
+      uint64_t r = 0;
+      for (auto& b : e->build_batches) {
+        const ColView v = view_of(&b, col);
+        for (int64_t i = 0; i < v.length; ++i, ++r) {
+          memcpy(buf.data() + r * w, v.values + (v.offset + i) * t.width, t.width);
+          if (v.null_count != 0 && v.validity && !bit_at(v.validity, v.offset + i)) { validity[r >> 3] &= uint8_t(~(1u << (r & 7))); any_null = true; }
+        }
+      }
+      rc = sq_index_add_column(e->index, buf.data(), w, &id);
+    } else {
+      std::vector<int64_t> off(size_t(n) + 1, 0);
+      std::vector<uint8_t> data;
+      uint64_t r = 0;
+      for (auto& b : e->build_batches) {
+        const ColView v = view_of(&b, col);
+        for (int64_t i = 0; i < v.length; ++i, ++r) {
+          int64_t a, z;
+          if (t.kind == Kind::Utf8) { const int32_t* o = reinterpret_cast<const int32_t*>(v.values) + v.offset; a = o[i]; z = o[i + 1]; }
+          else { const int64_t* o = reinterpret_cast<const int64_t*>(v.values) + v.offset; a = o[i]; z = o[i + 1]; }
+          data.insert(data.end(), v.data + a, v.data + z);
+          off[r + 1] = int64_t(data.size());
+          if (v.null_count != 0 && v.validity && !bit_at(v.validity, v.offset + i)) { validity[r >> 3] &= uint8_t(~(1u << (r & 7))); any_null = true; }
+        }
+      }
+      rc = sq_index_add_utf8_column(e->index, off.data(), data.data(), data.size(), &id);
+    }
+    if (rc != SQ_OK) return e->fail(rc, "%s", sq_last_error(e->ctx));
+    if (any_null && (rc = sq_index_set_validity(e->index, id, validity.data())) != SQ_OK) return e->fail(rc, "%s", sq_last_error(e->ctx));
+    e->build_col_id[size_t(col)] = id | (any_null ? 0x40000000 : 0);
+  }
+  for (auto& b : e->build_batches) if (b.release) b.release(&b);  // everything needed now lives on the device
+  e->build_batches.clear();
+  e->built = true;
+  e->m[2] = sq_index_bytes(e->index);
+  e->m[9] = sq_index_bytes(e->index);
+  e->m[10] = sq_index_keys(e->index);
+  e->m[7] = uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - t0).count());
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_exec_output_schema(const sq_exec* e, ArrowSchema* out) {
+  if (!e || !out) return SQ_EINVAL;
+  auto* o = new Owned();
+  o->s1 = "+s";
+  o->s2 = "";
+  for (int32_t pc : e->projection) {
+    int side; int32_t col;
+    split_col(e, pc, &side, &col);
+    ColType t = (side ? e->right : e->left).cols[size_t(col)];
+    if (t.kind == Kind::LargeUtf8) { t.kind = Kind::Utf8; }  // format is kept; LargeUtf8 output uses int64 offsets
+    o->schema_children.push_back(make_field(t));
+  }
+  o->schema_child_ptrs = o->schema_children;
+  out->format = o->s1.c_str();
+  out->name = o->s2.c_str();
+  out->metadata = nullptr;
+  out->flags = 0;
+  out->n_children = int64_t(o->schema_children.size());
+  out->children = o->schema_child_ptrs.data();
+  out->dictionary = nullptr;
+  out->release = release_schema;
+  out->private_data = o;
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_exec_probe(sq_exec* e, int32_t partition, const ArrowArray* batch, ArrowArray* out) {
+  if (!e || !batch || !out) return SQ_EINVAL;
+  if (!e->built) return e->fail(SQ_ESTATE, "Expected build side in ready state");  // IJ:1425
+  if (batch->n_children != int64_t(e->right.cols.size())) return e->fail(SQ_EINVAL, "probe batch has %lld columns, schema has %zu",
+                                                                          (long long)batch->n_children, e->right.cols.size());
+  const auto t0 = Clock::now();
+  sq_stream* st = nullptr;
+  int rc = stream_for(e, partition, &st);
+  if (rc) return rc;
+  const uint64_t n = uint64_t(batch->length);
+  if (n > 0xFFFFFFFFull) return e->fail(SQ_EINVAL, "probe batch too large");
+  std::vector<uint64_t> keys;
+  std::vector<int32_t> start, end;
+  if ((rc = hash_keys(e, e->right, e->on_right, batch, &keys))) return rc;
+  if ((rc = eval_i32(e, st, e->right, e->cfg.right_start, false, batch, &start))) return rc;
+  if ((rc = eval_i32(e, st, e->right, e->cfg.right_end, e->cfg.right_end_minus_one != 0, batch, &end))) return rc;
+
+  uint64_t n_pairs = 0;
+  rc = sq_probe_count(st, e->index, keys.data(), start.data(), end.data(), uint32_t(n), &n_pairs);
+  if (rc != SQ_OK) return e->fail(rc, "%s", sq_stream_last_error(st));
+  // the index pairs stay on the device: only the gathered columns travel back (IJ:1620-1632)
+  rc = sq_probe_emit_pairs(st, nullptr, nullptr, nullptr, n_pairs);
+  if (rc != SQ_OK) return e->fail(rc, "%s", sq_stream_last_error(st));
+
+  // `out` is assembled in place; on any failure below everything attached so far is released
+  auto* own = new Owned();
+  own->ctx = e->ctx;
+  out->release = release_array;
+  out->private_data = own;
+  struct Unwind {
+    ArrowArray* a; bool armed;
+    ~Unwind() { if (armed) release_array(a); }
+  } unwind{out, true};
+  auto pinned = [&](size_t bytes) -> void* {
+    void* p = nullptr;
+    if (sq_host_alloc(e->ctx, bytes ? bytes : 8, &p) != SQ_OK) return nullptr;
+    return p;
+  };
+  for (int32_t pc : e->projection) {
+    int side; int32_t col;
+    split_col(e, pc, &side, &col);
+    const ColType& t = (side ? e->right : e->left).cols[size_t(col)];
+    auto* child = new ArrowArray();
+    auto* co = new Owned();
+    co->ctx = e->ctx;
+    child->length = int64_t(n_pairs);
+    child->offset = 0;
+    child->n_children = 0;
+    child->children = nullptr;
+    child->dictionary = nullptr;
+    child->release = release_array;
+    child->private_data = co;
+    child->null_count = 0;
+    own->children.push_back(child);
+    const void* validity_out = nullptr;
+
+    // validity of the source column, if it has nulls
+    const int32_t bid = side == 0 ? (e->build_col_id[size_t(col)] & 0x3FFFFFFF) : -1;
+    const bool build_nulls = side == 0 && (e->build_col_id[size_t(col)] & 0x40000000);
+    ColView pv;
+    std::vector<uint8_t> probe_bm;
+    bool probe_nulls = false;
+    if (side == 1) {
+      pv = view_of(batch, col);
+      if (pv.null_count != 0 && pv.validity) {
+        probe_nulls = true;
+        probe_bm.assign((n + 7) / 8, 0);
+        for (uint64_t i = 0; i < n; ++i) if (bit_at(pv.validity, pv.offset + int64_t(i))) probe_bm[i >> 3] |= uint8_t(1u << (i & 7));
+      }
+    }
+    if ((build_nulls || probe_nulls) && n_pairs) {
+      void* bm = pinned((n_pairs + 7) / 8);
+      if (!bm) return e->fail(SQ_ENOMEM, "pinned allocation failed");
+      co->pinned.push_back(bm);
+      uint64_t nulls = 0;
+      rc = sq_gather_validity(st, side, bid, probe_nulls ? probe_bm.data() : nullptr, static_cast<uint8_t*>(bm), &nulls);
+      if (rc != SQ_OK) return e->fail(rc, "%s", sq_stream_last_error(st));
+      child->null_count = int64_t(nulls);
+      validity_out = bm;
+    }
+
+    if (t.kind == Kind::Fixed) {
+      const uint32_t w = t.width < 4 ? 4 : t.width;
+      void* vals = pinned(size_t(n_pairs) * w);
+      if (!vals) return e->fail(SQ_ENOMEM, "pinned allocation failed");
+      co->pinned.push_back(vals);
+      if (n_pairs) {
+        if (side == 0) {
+          rc = sq_gather_column(st, 0, bid, nullptr, w, vals, n_pairs);
+        } else {
+          std::vector<uint8_t> wide;
+          const uint8_t* src = pv.values + pv.offset * t.width;
+          if (t.width < 4) {
+            wide.assign(size_t(n) * 4, 0);
+            for (uint64_t i = 0; i < n; ++i) memcpy(wide.data() + i * 4, src + i * t.width, t.width);
+            src = wide.data();
+          }
+          rc = sq_gather_column(st, 1, -1, src, w, vals, n_pairs);
+        }
+        if (rc != SQ_OK) return e->fail(rc, "%s", sq_stream_last_error(st));
+        if (t.width < 4) {  // narrow back in place
+          auto* p = static_cast<uint8_t*>(vals);
+          for (uint64_t k = 0; k < n_pairs; ++k) memmove(p + k * t.width, p + k * 4, t.width);
+        }
+      }
+      co->buffers = {validity_out, vals};
+    } else {
+      // Utf8 / LargeUtf8: offsets first (gives the byte total), then the bytes
+      std::vector<int64_t> poff;
+      const uint8_t* pdata = nullptr;
+      uint64_t pbytes = 0;
+      if (side == 1) {
+        poff.resize(size_t(n) + 1);
+        if (t.kind == Kind::Utf8) { const int32_t* o = reinterpret_cast<const int32_t*>(pv.values) + pv.offset; for (uint64_t i = 0; i <= n; ++i) poff[i] = o[i] - o[0]; pdata = pv.data + o[0]; pbytes = uint64_t(o[n] - o[0]); }
+        else { const int64_t* o = reinterpret_cast<const int64_t*>(pv.values) + pv.offset; for (uint64_t i = 0; i <= n; ++i) poff[i] = o[i] - o[0]; pdata = pv.data + o[0]; pbytes = uint64_t(o[n] - o[0]); }
+      }
+      void* off32 = pinned((size_t(n_pairs) + 1) * 4);
+      if (!off32) return e->fail(SQ_ENOMEM, "pinned allocation failed");
+      co->pinned.push_back(off32);
+      static_cast<int32_t*>(off32)[0] = 0;
+      uint64_t total = 0;
+      if (n_pairs) {
+        rc = sq_gather_utf8(st, side, bid, side ? poff.data() : nullptr, pdata, pbytes, static_cast<int32_t*>(off32), &total);
+        if (rc != SQ_OK) return e->fail(rc, "%s", sq_stream_last_error(st));
+      }
+      void* bytes = pinned(total);
+      if (!bytes) return e->fail(SQ_ENOMEM, "pinned allocation failed");
+      co->pinned.push_back(bytes);
+      if (n_pairs && (rc = sq_gather_utf8_data(st, static_cast<uint8_t*>(bytes), total)) != SQ_OK)
+        return e->fail(rc, "%s", sq_stream_last_error(st));
+      if (t.kind == Kind::LargeUtf8) {  // widen the offsets for a LargeUtf8 output column
+        void* off64 = pinned((size_t(n_pairs) + 1) * 8);
+        if (!off64) return e->fail(SQ_ENOMEM, "pinned allocation failed");
+        co->pinned.push_back(off64);
+        for (uint64_t k = 0; k <= n_pairs; ++k) static_cast<int64_t*>(off64)[k] = static_cast<int32_t*>(off32)[k];
+        co->buffers = {validity_out, off64, bytes};
+      } else {
+        co->buffers = {validity_out, off32, bytes};
+      }
+    }
+    child->n_buffers = int64_t(co->buffers.size());
+    child->buffers = co->buffers.data();
+  }
+  own->child_ptrs = own->children;
+  own->buffers = {nullptr};
+  out->length = int64_t(n_pairs);
+  out->null_count = 0;
+  out->offset = 0;
+  out->n_buffers = 1;
+  out->buffers = own->buffers.data();
+  out->n_children = int64_t(own->children.size());
+  out->children = own->child_ptrs.data();
+  out->dictionary = nullptr;
+  unwind.armed = false;
+  {
+    std::lock_guard<std::mutex> g(e->mu);
+    e->m[3] += 1;
+    e->m[4] += n;
+    e->m[5] += 1;
+    e->m[6] += n_pairs;
+    e->m[8] += uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - t0).count());
+  }
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_exec_metrics(const sq_exec* e, uint64_t out[16]) {
+  if (!e || !out) return SQ_EINVAL;
+  memcpy(out, e->m, sizeof e->m);
+  return SQ_OK;
+}
+
+SQ_API const char* sq_exec_last_error(const sq_exec* e) { return e ? e->err.c_str() : ""; }
+
+SQ_API void sq_exec_free(sq_exec* e) {
+  if (!e) return;
+  for (auto& kv : e->streams) sq_stream_free(kv.second);
+  for (auto& b : e->build_batches) if (b.release) b.release(&b);
+  if (e->index) sq_index_free(e->index);
+  if (e->ctx) sq_ctx_destroy(e->ctx);
+  delete e;
+}

@@ -150,4 +150,162 @@ int launch_digest(sq_stream* s, const uint32_t* d_left, const uint32_t* d_right,
   return SQ_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Utf8 take (arrow::compute::take of a string column, interval_join.rs:1624-1627):
+//   k_str_blocksum  per 1024 output rows: sum of the gathered string lengths
+//   (launch_scan_u64 over the block sums)
+//   k_str_offsets   output offsets = block base + in-block exclusive scan
+//   k_str_copy      bytes of every output string
+// Contig names are a few bytes long, so one thread copies one string.
+// ---------------------------------------------------------------------------------------------
+constexpr int kStrBlock = 1024;
+
+__device__ __forceinline__ unsigned long long str_len(const int64_t* __restrict__ off, const uint32_t* __restrict__ idx,
+                                                      uint64_t k, uint64_t n) {
+  if (k >= n) return 0ull;
+  const uint32_t r = __ldg(idx + k);
+  return (unsigned long long)(__ldg(off + r + 1) - __ldg(off + r));
+}
+
+__device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long v, unsigned long long* s_w,
+                                                              unsigned long long* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long w = s_w[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long o = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += o;
+    }
+    s_w[lane] = w;
+  }
+  __syncthreads();
+  *total = s_w[31];
+  return (warp ? s_w[warp - 1] : 0ull) + inc - v;
+}
+
+__global__ void __launch_bounds__(kStrBlock) k_str_blocksum(const int64_t* __restrict__ off,
+                                                            const uint32_t* __restrict__ idx, uint64_t n,
+                                                            unsigned long long* __restrict__ blk) {
+  __shared__ unsigned long long s_w[32];
+  unsigned long long tot;
+  block_excl_scan(str_len(off, idx, uint64_t(blockIdx.x) * kStrBlock + threadIdx.x, n), s_w, &tot);
+  if (threadIdx.x == 0) blk[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kStrBlock) k_str_offsets(const int64_t* __restrict__ off,
+                                                           const uint32_t* __restrict__ idx, uint64_t n,
+                                                           const unsigned long long* __restrict__ blk_base,
+                                                           const unsigned long long* __restrict__ total,
+                                                           int64_t* __restrict__ out_off) {
+  __shared__ unsigned long long s_w[32];
+  const uint64_t k = uint64_t(blockIdx.x) * kStrBlock + threadIdx.x;
+  unsigned long long tot;
+  const unsigned long long e = block_excl_scan(str_len(off, idx, k, n), s_w, &tot);
+  if (k < n) out_off[k] = int64_t(blk_base[blockIdx.x] + e);
+  if (k == n) out_off[n] = int64_t(total[0]);
+}
+
+__global__ void __launch_bounds__(256) k_str_copy(const int64_t* __restrict__ off, const uint8_t* __restrict__ data,
+                                                  const uint32_t* __restrict__ idx, uint64_t n,
+                                                  const int64_t* __restrict__ out_off, uint8_t* __restrict__ out) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t k = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < n; k += stride) {
+    const uint32_t r = __ldg(idx + k);
+    const int64_t a = __ldg(off + r), b = __ldg(off + r + 1);
+    uint8_t* dst = out + out_off[k];
+    for (int64_t c = a; c < b; ++c) *dst++ = __ldg(data + c);
+  }
+}
+
+int launch_str_offsets(sq_stream* s, const int64_t* d_src_off, const uint32_t* d_idx, uint64_t n,
+                       int64_t* d_out_off, uint64_t* total) {
+  ErrorSlot& E = s->err;
+  const uint64_t n_blk64 = (n + 1 + kStrBlock - 1) / kStrBlock;  // +1: the thread k == n writes the last offset
+  if (n_blk64 > 0xFFFFFFFFull) return fail(E, SQ_EINVAL, "string gather of %llu rows is too large", (unsigned long long)n);
+  const uint32_t n_blk = uint32_t(n_blk64);
+  int rc;
+  if ((rc = ensure(E, s->d_strblk, size_t(n_blk) * 8 + 16, false))) return rc;
+  if ((rc = ensure(E, s->h_scalar, 256, true))) return rc;
+  auto* blk = static_cast<unsigned long long*>(s->d_strblk.p);
+  auto* tot = blk + n_blk;
+  k_str_blocksum<<<n_blk, kStrBlock, 0, s->stream>>>(d_src_off, d_idx, n, blk);
+  SQ_CUDA(E, cudaGetLastError());
+  s->launches += 1;
+  if ((rc = launch_scan_u64(s, blk, n_blk, tot))) return rc;
+  k_str_offsets<<<n_blk, kStrBlock, 0, s->stream>>>(d_src_off, d_idx, n, blk, tot, d_out_off);
+  SQ_CUDA(E, cudaGetLastError());
+  s->launches += 1;
+  auto* h = static_cast<unsigned long long*>(s->h_scalar.p) + 16;
+  SQ_CUDA(E, cudaMemcpyAsync(h, tot, 8, cudaMemcpyDeviceToHost, s->stream));
+  SQ_CUDA(E, cudaStreamSynchronize(s->stream));
+  *total = h[0];
+  return SQ_OK;
+}
+
+int launch_str_copy(sq_stream* s, const int64_t* d_src_off, const uint8_t* d_src_data, const uint32_t* d_idx,
+                    uint64_t n, const int64_t* d_out_off, uint8_t* d_out_data) {
+  if (n == 0) return SQ_OK;
+  k_str_copy<<<grid_for(n, 256, s->ctx->sm_count), 256, 0, s->stream>>>(d_src_off, d_src_data, d_idx, n, d_out_off,
+                                                                         d_out_data);
+  SQ_CUDA(s->err, cudaGetLastError());
+  s->launches += 1;
+  return SQ_OK;
+}
+
+// Arrow validity take: out bit k = in bit idx[k]; one thread per output byte; counts the nulls
+__global__ void __launch_bounds__(256) k_gather_bits(const uint8_t* __restrict__ bitmap,
+                                                     const uint32_t* __restrict__ idx, uint64_t n,
+                                                     uint8_t* __restrict__ out, unsigned long long* nulls) {
+  const uint64_t n_bytes = (n + 7) / 8;
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  unsigned int my_nulls = 0;
+  for (uint64_t b = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; b < n_bytes; b += stride) {
+    unsigned int v = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint64_t e = b * 8 + k;
+      if (e < n) {
+        const uint32_t r = __ldg(idx + e);
+        const unsigned int bit = (__ldg(bitmap + (r >> 3)) >> (r & 7)) & 1u;
+        v |= bit << k;
+        my_nulls += 1u - bit;
+      }
+    }
+    out[b] = uint8_t(v);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) my_nulls += __shfl_xor_sync(0xffffffffu, my_nulls, d);
+  if ((threadIdx.x & 31) == 0 && my_nulls) atomicAdd(nulls, (unsigned long long)my_nulls);
+}
+
+int launch_gather_bits(sq_stream* s, const uint8_t* d_bitmap, const uint32_t* d_idx, uint64_t n, uint8_t* d_out,
+                       uint64_t* null_count) {
+  ErrorSlot& E = s->err;
+  *null_count = 0;
+  if (n == 0) return SQ_OK;
+  int rc;
+  if ((rc = ensure(E, s->d_scalar, 256, false))) return rc;
+  if ((rc = ensure(E, s->h_scalar, 256, true))) return rc;
+  auto* slot = reinterpret_cast<unsigned long long*>(static_cast<char*>(s->d_scalar.p) + 192);
+  SQ_CUDA(E, cudaMemsetAsync(slot, 0, 8, s->stream));
+  k_gather_bits<<<grid_for((n + 7) / 8, 256, s->ctx->sm_count), 256, 0, s->stream>>>(d_bitmap, d_idx, n, d_out, slot);
+  SQ_CUDA(E, cudaGetLastError());
+  s->launches += 1;
+  auto* h = static_cast<unsigned long long*>(s->h_scalar.p) + 24;
+  SQ_CUDA(E, cudaMemcpyAsync(h, slot, 8, cudaMemcpyDeviceToHost, s->stream));
+  SQ_CUDA(E, cudaStreamSynchronize(s->stream));
+  *null_count = h[0];
+  return SQ_OK;
+}
+
 }  // namespace sq

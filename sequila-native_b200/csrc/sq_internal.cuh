@@ -87,9 +87,12 @@ struct sq_ctx {
 };
 
 struct sq_column {
-  void* d_values = nullptr;
-  uint32_t width = 0;
+  void* d_values = nullptr;          // fixed-width values, or the bytes of a Utf8 column
+  uint32_t width = 0;                // 4/8/16, or 0 for Utf8
   bool owned = false;
+  int64_t* d_offsets = nullptr;      // Utf8: n_rows + 1 offsets into d_values
+  uint64_t data_bytes = 0;
+  uint8_t* d_validity = nullptr;     // optional Arrow validity bitmap (bit i = row i is valid)
 };
 
 struct sq_index {
@@ -159,6 +162,17 @@ struct sq_stream {
   sq_buf d_scalar;   // n_pairs, ticket counter, cast-error slot, digest
   sq_buf d_left, d_right;  // emitted pairs (host entry points)
   sq_buf d_gather;   // gather staging
+  sq_buf d_gather2;  // Utf8 gather: staged probe column / output offsets
+  sq_buf d_chain;    // chained-scan words of launch_scan_u64
+  sq_buf d_strblk;   // Utf8 gather: per-block length sums
+  sq_buf d_strdata;  // Utf8 gather: output bytes
+  // Utf8 gather in flight between sq_gather_utf8 (offsets) and sq_gather_utf8_data (bytes)
+  const int64_t* str_src_off = nullptr;
+  const uint8_t* str_src_data = nullptr;
+  const uint32_t* str_idx = nullptr;
+  int64_t* str_out_off = nullptr;
+  uint64_t str_total = 0;
+  bool str_pending = false;
   // pinned staging
   sq_buf h_in, h_out, h_scalar;
 
@@ -208,5 +222,14 @@ int launch_cast_i64(sq_stream* s, const int64_t* d_in, uint64_t n, int64_t minus
                     int64_t* bad_value, bool* bad);
 int launch_digest(sq_stream* s, const uint32_t* d_left, const uint32_t* d_right, uint64_t n,
                   uint64_t right_offset, uint64_t out3[3]);
+// Utf8 take: d_out_off[n+1] = exclusive scan of the gathered string lengths; *total = bytes (stream synced)
+int launch_str_offsets(sq_stream* s, const int64_t* d_src_off, const uint32_t* d_idx, uint64_t n,
+                       int64_t* d_out_off, uint64_t* total);
+int launch_str_copy(sq_stream* s, const int64_t* d_src_off, const uint8_t* d_src_data, const uint32_t* d_idx,
+                    uint64_t n, const int64_t* d_out_off, uint8_t* d_out_data);
+int launch_gather_bits(sq_stream* s, const uint8_t* d_bitmap, const uint32_t* d_idx, uint64_t n, uint8_t* d_out,
+                       uint64_t* null_count);
+// exclusive scan, in place, of n u64 values (chained scan with decoupled look-back); total -> d_total[0]
+int launch_scan_u64(sq_stream* s, unsigned long long* d_vals, uint32_t n, unsigned long long* d_total);
 
 }  // namespace sq

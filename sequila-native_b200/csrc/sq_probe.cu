@@ -429,6 +429,20 @@ static int ensure_probe_state(sq_stream* s, uint32_t n, uint32_t n_tiles) {
   return SQ_OK;
 }
 
+int launch_scan_u64(sq_stream* s, unsigned long long* d_vals, uint32_t n, unsigned long long* d_total) {
+  ErrorSlot& E = s->err;
+  const uint32_t n_chain = (n + 1023) / 1024;
+  int rc;
+  if ((rc = ensure(E, s->d_chain, size_t(n_chain) * 8 + 16, false))) return rc;
+  auto* chain = static_cast<unsigned long long*>(s->d_chain.p);
+  auto* ticket = reinterpret_cast<unsigned int*>(chain + n_chain);
+  SQ_CUDA(E, cudaMemsetAsync(chain, 0, size_t(n_chain) * 8 + 16, s->stream));
+  k_tile_scan<<<n_chain ? n_chain : 1, 1024, 0, s->stream>>>(d_vals, n, chain, ticket, d_total);
+  SQ_CUDA(E, cudaGetLastError());
+  s->launches += 1;
+  return SQ_OK;
+}
+
 // K1 + K2 on the stream: per-row state, tile offsets and result[0] = n_pairs
 int launch_count(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
                  const int32_t* d_end, uint32_t n) {
