@@ -349,11 +349,16 @@ static int32_t join_device(sq_stream* s, const sq_index* idx, const uint64_t* dk
   if (n == 0) return empty_tile(s, n_pairs_out);
   int rc;
   mark(s, 1);
-  if ((rc = launch_count(s, idx, dk, ds, de, n))) return rc;
   const bool wrote = d_left != nullptr && capacity > 0;
-  // speculative emit: the write kernel checks n_pairs <= capacity on the device, so the whole
-  // count -> scan -> write chain is enqueued without a host round trip
-  if (wrote && (rc = launch_write(s, idx, ds, n, d_left, d_right, capacity))) return rc;
+  if (use_packed(idx)) {
+    // narrow index: ONE kernel searches, counts, scans and (when there is room) writes
+    if ((rc = launch_packed(s, idx, dk, ds, de, n, wrote ? d_left : nullptr, d_right, capacity))) return rc;
+  } else {
+    if ((rc = launch_count(s, idx, dk, ds, de, n))) return rc;
+    // speculative emit: the write kernel checks n_pairs <= capacity on the device, so the whole
+    // count -> scan -> write chain is enqueued without a host round trip
+    if (wrote && (rc = launch_write(s, idx, ds, n, d_left, d_right, capacity))) return rc;
+  }
   mark(s, 2);
   s->d_spec_left = d_left;
   s->d_spec_right = d_right;
@@ -422,6 +427,13 @@ SQ_API int32_t sq_probe_count(sq_stream* s, const sq_index* idx, const uint64_t*
   return count_host(s, idx, key_hash, start, end, n_rows, n_pairs_out);
 }
 
+// the write pass of a tile that was only counted (or whose speculative buffers were too small)
+static int32_t launch_emit(sq_stream* s, uint32_t* d_left, uint32_t* d_right, uint64_t capacity) {
+  if (use_packed(s->idx))
+    return launch_packed(s, s->idx, s->d_q_key, s->d_q_start, s->d_q_end, s->n_rows, d_left, d_right, capacity);
+  return launch_write(s, s->idx, s->d_q_start, s->n_rows, d_left, d_right, capacity);
+}
+
 static int32_t check_emit(sq_stream* s, const void* left, uint64_t capacity) {
   if (!s) return SQ_EINVAL;
   if (!s->counted) return fail(s->err, SQ_ESTATE, "sq_probe_emit_pairs called without a preceding sq_probe_count");
@@ -439,8 +451,7 @@ SQ_API int32_t sq_probe_emit_pairs_device(sq_stream* s, uint32_t* d_left_idx_out
   if (s->n_pairs && !d_left_idx_out) return fail(s->err, SQ_EINVAL, "null d_left_idx_out");
   SQ_CUDA(s->err, cudaSetDevice(s->ctx->device));
   mark(s, 3);
-  if (s->n_pairs && (rc = launch_write(s, s->idx, s->d_q_start, s->n_rows, d_left_idx_out, d_right_idx_out, capacity)))
-    return rc;
+  if (s->n_pairs && (rc = launch_emit(s, d_left_idx_out, d_right_idx_out, capacity))) return rc;
   mark(s, 4);
   s->d_last_left = d_left_idx_out;
   s->d_last_right = d_right_idx_out;
@@ -461,9 +472,7 @@ SQ_API int32_t sq_probe_emit_pairs(sq_stream* s, uint32_t* left_idx_out, uint32_
   if (np && !reuse) {  // the speculative buffers were too small: grow them, re-run only the write kernel
     if ((rc = ensure(E, s->d_left, np * 4, false))) return rc;
     if ((rc = ensure(E, s->d_right, np * 4, false))) return rc;
-    if ((rc = launch_write(s, s->idx, s->d_q_start, s->n_rows, static_cast<uint32_t*>(s->d_left.p),
-                           static_cast<uint32_t*>(s->d_right.p), np)))
-      return rc;
+    if ((rc = launch_emit(s, static_cast<uint32_t*>(s->d_left.p), static_cast<uint32_t*>(s->d_right.p), np))) return rc;
   }
   auto* dl = static_cast<uint32_t*>(s->d_left.p);
   auto* dr = static_cast<uint32_t*>(s->d_right.p);

@@ -136,7 +136,8 @@ __global__ void __launch_bounds__(256) k_seg_meta(const uint32_t* __restrict__ s
   m.shift = shift;
   m.nbins = (shift >= 32 ? 0u : (range >> shift)) + 1u;
   m.dir_base = 0;  // filled by the host-side exclusive scan over nbins + 1
-  m.pad0 = m.pad1 = 0;
+  m.line_base = 0;  // filled by the host-side scan too
+  m.pad1 = 0;
   meta[id] = m;
 }
 
@@ -267,6 +268,62 @@ __global__ void __launch_bounds__(kScanThreads) k_runmax_final(const uint64_t* _
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Packed lines (see PackedLine in sq_internal.cuh): 8 threads per line, each writes its 16 bytes.
+// status[0] |= 1 when some row does not fit the narrow encoding (the index then keeps only the
+// SoA arrays); status[1] += lines a probe ending at this line's last start would walk back.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack_lines(const int32_t* __restrict__ s_start, const int32_t* __restrict__ s_end,
+                                                    const int32_t* __restrict__ s_runmax, const uint32_t* __restrict__ s_row,
+                                                    const SegMeta* __restrict__ meta, uint32_t n_keys, uint64_t n_lines,
+                                                    uint4* __restrict__ lines, unsigned long long* status) {
+  const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint64_t line = t >> 3;
+  const uint32_t sub = uint32_t(t & 7);
+  if (line >= n_lines) return;
+  // key segment of this line: last id with line_base <= line (meta[n_keys].line_base = n_lines)
+  uint32_t lo = 0, hi = n_keys;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (uint64_t(meta[mid].line_base) <= line) lo = mid; else hi = mid;
+  }
+  const SegMeta m = meta[lo];
+  const uint32_t j0 = m.sb + uint32_t(line - m.line_base) * kLineRows;
+  const int32_t base = s_start[j0];
+  bool bad = false;
+  auto enc = [&](uint32_t r, uint32_t* lo_word, uint32_t* id_word) {
+    const uint32_t j = j0 + r;
+    if (j >= m.se) { *lo_word = 0; *id_word = kEmptyRow; return; }
+    const int64_t ds = int64_t(s_start[j]) - int64_t(base);
+    const int64_t w = int64_t(s_end[j]) - int64_t(s_start[j]);
+    if (ds < 0 || ds > 65535 || w < 0 || w > 65535) bad = true;
+    *lo_word = uint32_t(ds & 0xFFFF) | (uint32_t(w & 0xFFFF) << 16);
+    *id_word = s_row[j];
+  };
+  uint4 v;
+  if (sub == 0) {
+    v.x = uint32_t(base);
+    v.y = uint32_t(j0 > m.sb ? s_runmax[j0 - 1] : INT32_MIN);
+    enc(0, &v.z, &v.w);
+    // statistic: how many earlier lines does a probe starting at this line's last start visit?
+    const uint32_t jl = min(j0 + kLineRows, m.se) - 1;
+    const int32_t qs = s_start[jl];
+    uint32_t a = m.sb, len = j0 - m.sb;  // first row in [sb, j0) with runmax >= qs
+    while (len) {
+      const uint32_t half = len >> 1;
+      if (s_runmax[a + half] < qs) { a += half + 1; len -= half + 1; } else len = half;
+    }
+    const uint32_t back = a < j0 ? (j0 - a + kLineRows - 1) / kLineRows : 0u;
+    if (back) atomicAdd(status + 1, (unsigned long long)back);
+  } else {
+    enc(2 * sub - 1, &v.x, &v.y);
+    enc(2 * sub, &v.z, &v.w);
+  }
+  lines[t] = v;
+  if (bad) atomicOr(status, 1ull);
+}
+
 // ---------------------------------------------------------------------------------------------
 static inline int grid_for(uint64_t n, int threads, int sm_count, int per_sm = 8) {
   const uint64_t want = (n + threads - 1) / threads;
@@ -279,6 +336,7 @@ void free_index(sq_index* idx) {
   cudaSetDevice(idx->ctx->device);
   cudaFree(idx->d_start); cudaFree(idx->d_runmax); cudaFree(idx->d_end); cudaFree(idx->d_row);
   cudaFree(idx->d_meta); cudaFree(idx->d_dir); cudaFree(idx->d_ht_keys); cudaFree(idx->d_ht_ids);
+  cudaFree(idx->d_lines);
   for (auto& c : idx->columns) {
     if (c.owned) { cudaFree(c.d_values); cudaFree(c.d_offsets); }
     cudaFree(c.d_validity);
@@ -399,19 +457,45 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     std::vector<SegMeta> h_meta(n_keys);
     SQ_CUDA(E, cudaMemcpyAsync(h_meta.data(), idx->d_meta, size_t(n_keys) * sizeof(SegMeta), cudaMemcpyDeviceToHost, st));
     SQ_CUDA(E, cudaStreamSynchronize(st));
-    uint64_t dir_total = 0;
-    for (auto& m : h_meta) {
+    uint64_t dir_total = 0, line_total = 0;
+    h_meta.resize(size_t(n_keys) + 1);  // + sentinel entry carrying the line total
+    for (uint32_t k = 0; k < n_keys; ++k) {
+      SegMeta& m = h_meta[k];
       m.dir_base = uint32_t(dir_total);
       dir_total += uint64_t(m.nbins) + 1;
+      m.line_base = uint32_t(line_total);
+      line_total += (uint64_t(m.se - m.sb) + kLineRows - 1) / kLineRows;
     }
     if (dir_total >= 0xFFFFFFFFull) return fail(E, SQ_EINVAL, "bin directory too large");
-    SQ_CUDA(E, cudaMemcpyAsync(idx->d_meta, h_meta.data(), size_t(n_keys) * sizeof(SegMeta), cudaMemcpyHostToDevice, st));
+    h_meta[n_keys] = SegMeta{};
+    h_meta[n_keys].sb = h_meta[n_keys].se = uint32_t(n);
+    h_meta[n_keys].line_base = uint32_t(line_total);
+    SQ_CUDA(E, cudaMemcpyAsync(idx->d_meta, h_meta.data(), (size_t(n_keys) + 1) * sizeof(SegMeta), cudaMemcpyHostToDevice, st));
     SQ_CUDA(E, cudaMalloc(&idx->d_dir, dir_total * 4));
     idx->bytes += dir_total * 4;
     idx->dir_bytes = dir_total * 4;
     k_fill_dir<<<g, 256, 0, st>>>(d_k1, idx->d_start, n, idx->d_meta, idx->d_dir);
     SQ_CUDA(E, cudaGetLastError());
-    SQ_CUDA(E, cudaStreamSynchronize(st));  // h_meta must outlive the async copy
+
+    // 5. packed lines for narrow indexes (every width and every in-line start offset < 65536)
+    unsigned long long* d_pstat = nullptr;
+    SQ_CUDA(E, tmp.alloc(&d_pstat, 16));
+    SQ_CUDA(E, cudaMemsetAsync(d_pstat, 0, 16, st));
+    SQ_CUDA(E, cudaMalloc(&idx->d_lines, line_total * 128));
+    k_pack_lines<<<unsigned((line_total * 8 + 255) / 256), 256, 0, st>>>(idx->d_start, idx->d_end, idx->d_runmax, idx->d_row,
+                                                                          idx->d_meta, n_keys, line_total, idx->d_lines, d_pstat);
+    SQ_CUDA(E, cudaGetLastError());
+    unsigned long long h_pstat[2] = {0, 0};
+    SQ_CUDA(E, cudaMemcpyAsync(h_pstat, d_pstat, 16, cudaMemcpyDeviceToHost, st));
+    SQ_CUDA(E, cudaStreamSynchronize(st));  // h_meta / h_pstat must outlive the async copies
+    if (h_pstat[0]) {  // wide or inverted intervals: the SoA arrays serve this index
+      cudaFree(idx->d_lines);
+      idx->d_lines = nullptr;
+    } else {
+      idx->n_lines = line_total;
+      idx->mean_back_lines = float(double(h_pstat[1]) / double(line_total));
+      idx->bytes += line_total * 128;
+    }
   }
   SQ_CUDA(E, cudaEventRecord(e1, st));
   SQ_CUDA(E, cudaStreamSynchronize(st));

@@ -34,8 +34,21 @@ struct SegMeta {
   uint32_t shift;
   uint32_t dir_base;
   uint32_t nbins;
-  uint32_t pad0, pad1;
+  uint32_t line_base;  // first packed line of this key (packed layout, see PackedLine)
+  uint32_t pad1;
 };
+
+// Packed layout of the same sorted rows ("narrow" indexes: 0 <= end - start < 65536 for every row
+// and < 65536 between the first and last start of a line): 128-byte lines of 15 rows, key segments
+// padded to whole lines.  One cooperative 8-lane load (8 x 16 bytes = one L2 request) brings
+//   lane 0      : { base_start, exmax, row0.lo, row0.id }
+//   lanes 1..7  : { row(2k-1).lo, row(2k-1).id, row(2k).lo, row(2k).id }
+// with row.lo = (start - base_start) | (end - start) << 16, row.id = build row (0xFFFFFFFF = empty
+// slot) and exmax = max end over all earlier rows of the key segment (INT32_MIN on its first line):
+// a probe (qs, qe) walks lines backwards from the one holding the last start <= qe while
+// exmax >= qs, testing the exact predicate per row.
+constexpr uint32_t kLineRows = 15;
+constexpr uint32_t kEmptyRow = 0xFFFFFFFFu;
 
 // Flat, tree-free build index in HBM (all arrays length n_rows, sorted by (key id, start)).
 struct IndexView {
@@ -51,6 +64,7 @@ struct IndexView {
   uint32_t sentinel_id;                 // id of the key hash equal to kEmptyKey, or kNoKey
   uint32_t n_keys;
   uint32_t n_rows;
+  const uint4* __restrict__ lines;      // packed lines (nullptr when the index is not "narrow")
 };
 
 #ifdef __CUDACC__
@@ -107,6 +121,9 @@ struct sq_index {
   sq::SegMeta* d_meta = nullptr;
   uint32_t* d_dir = nullptr;
   uint64_t dir_bytes = 0;
+  uint4* d_lines = nullptr;    // packed lines, or nullptr (wide / inverted intervals: SoA path only)
+  uint64_t n_lines = 0;
+  float mean_back_lines = 0.f; // mean number of extra lines a probe landing on a line's last row walks back
   uint64_t* d_ht_keys = nullptr;
   uint32_t* d_ht_ids = nullptr;
   uint32_t ht_cap = 0;
@@ -121,6 +138,7 @@ struct sq_index {
     v.start = d_start; v.runmax = d_runmax; v.end = d_end; v.row = d_row; v.meta = d_meta; v.dir = d_dir;
     v.ht_keys = d_ht_keys; v.ht_ids = d_ht_ids; v.ht_mask = ht_cap - 1; v.sentinel_id = sentinel_id;
     v.n_keys = n_keys; v.n_rows = uint32_t(n_rows);
+    v.lines = d_lines;
     return v;
   }
 };
@@ -214,6 +232,13 @@ int launch_count(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const
 // K3: pairs from the saved state; sets result[1] instead of writing when n_pairs > capacity
 int launch_write(sq_stream* s, const sq_index* idx, const int32_t* d_start, uint32_t n, uint32_t* d_left,
                  uint32_t* d_right, uint64_t capacity);
+
+// probe_packed.cu: one fused pass over the packed lines (count + chained scan + write when
+// d_left != nullptr; count only otherwise).  Leaves cnt per row in s->d_cnt, result[0] = n_pairs and
+// result[1] = 1 when the pairs did not fit `capacity` (nothing useful was written then).
+int launch_packed(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
+                  const int32_t* d_end, uint32_t n, uint32_t* d_left, uint32_t* d_right, uint64_t capacity);
+bool use_packed(const sq_index* idx);
 
 // gather.cu
 int launch_gather(sq_stream* s, const void* d_values, const uint32_t* d_idx, uint64_t n, uint32_t width,

@@ -9,6 +9,15 @@ from helpers import canon, encode_tables, rows_from_pairs, sort_rows
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["packed", "soa"])
+def probe_layout(request, monkeypatch):
+    """Every parity test runs against both probe implementations: the fused kernel over packed
+    lines (narrow indexes) and the count/scan/write kernels over the SoA arrays (SQ_PACKED knob,
+    sq_probe_packed.cu::use_packed)."""
+    monkeypatch.setenv("SQ_PACKED", "1" if request.param == "packed" else "0")
+    return request.param
+
+
 def cuda_join(ctx, L, R):
     idx = sn.CudaIndex.build(ctx, L["key"], L["start"], L["end"])
     st = sn.CudaStream(ctx)
