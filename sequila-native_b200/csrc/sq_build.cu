@@ -451,8 +451,13 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     SQ_CUDA(E, cudaGetLastError());
 
     // 4. per-segment bin directory (geometry on the device, offsets by a host scan: #keys is small)
+    uint32_t rows_per_bin = kRowsPerBin;
+    if (const char* e = getenv("SQ_ROWS_PER_BIN")) {  // experiment knob
+      const int v = atoi(e);
+      if (v >= 1 && v <= 1024) rows_per_bin = uint32_t(v);
+    }
     k_seg_meta<<<(n_keys + 255) / 256, 256, 0, st>>>(d_seg_off, idx->d_start, n_keys, idx->d_meta,
-                                                     kRowsPerBin);
+                                                     rows_per_bin);
     SQ_CUDA(E, cudaGetLastError());
     std::vector<SegMeta> h_meta(n_keys);
     SQ_CUDA(E, cudaMemcpyAsync(h_meta.data(), idx->d_meta, size_t(n_keys) * sizeof(SegMeta), cudaMemcpyDeviceToHost, st));

@@ -84,7 +84,7 @@ k_probe_packed(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* 
   __shared__ unsigned long long s_wtot[kPWarps];
   __shared__ unsigned long long s_base;
   __shared__ uint32_t s_bid;
-  __shared__ uint8_t s_inv[kPWarps][32];
+  __shared__ __align__(8) uint8_t s_inv[kPWarps][32];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 3, sub = lane & 7;  // lane group (one probe row at a time) and lane in group
@@ -109,57 +109,65 @@ k_probe_packed(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* 
     sl = find_start_line(iv, id, my_qe);
   }
 
-  // ---- phase 2: 4 probe rows per step, 8 lanes each; rounds of 8 independent line requests ------------
-  // Round r fetches line (start line - r) of every row that is still walking back, all 8 steps of the
-  // warp at once, so a warp waits for ceil(longest walk) memory round trips, not for their sum.
+  // ---- phase 2: 4 probe rows per step, 8 lanes each; rounds of up to 8 independent line requests -----
+  // Every round, the rows that still walk back are compacted (rank among walking rows -> step, group),
+  // each fetches ONE more line, all steps of the warp at once: a warp waits for as many memory round
+  // trips as its longest walk and executes only as many steps as it has (row, line) pairs.
   uint32_t* stash = s_stash + (EMIT ? warp * 32 * kStride : 0);
-  uint32_t c[8];       // hits so far of the row this group serves in step `it` (group-uniform)
-  unsigned walking = 0;  // bit it: that row still walks back (group-uniform)
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    c[it] = 0;
-    walking |= (__shfl_sync(0xffffffffu, int(sl.act), it * 4 + g) != 0 ? 1u : 0u) << it;
-  }
-  for (uint32_t round = 0; __any_sync(0xffffffffu, walking != 0); ++round) {
+  bool walking = sl.act;
+  uint32_t ln = sl.line;  // next line of my row
+  uint32_t cnt = 0;       // hits of my row so far
+  for (;;) {
+    const unsigned A = __ballot_sync(0xffffffffu, walking);
+    if (A == 0) break;
+    const int n_walk = __popc(A);
+    const int r = __popc(A & ((1u << lane) - 1u));  // my rank: served in step r >> 2 by group r & 3
+    __syncwarp();
+    if (walking) s_inv[warp][(r & 3) * 8 + (r >> 2)] = uint8_t(lane);
+    __syncwarp();
+    const unsigned long long srcs = *reinterpret_cast<const unsigned long long*>(&s_inv[warp][g0]);  // my group's 8 rows
+    const int n_steps = (n_walk + 3) >> 2;
     uint4 v[8];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const uint32_t ln = __shfl_sync(0xffffffffu, sl.line, it * 4 + g) - round;
-      v[it] = ((walking >> it) & 1u) ? __ldg(iv.lines + size_t(ln) * 8 + sub) : make_uint4(0u, 0u, 0u, kEmptyRow);
+    for (int st = 0; st < 8; ++st) {
+      const int p = int(srcs >> (8 * st)) & 31;
+      const uint32_t lnp = __shfl_sync(0xffffffffu, ln, p);
+      v[st] = (4 * st + g < n_walk) ? __ldg(iv.lines + size_t(lnp) * 8 + sub) : make_uint4(0u, 0u, 0u, kEmptyRow);
     }
+    bool cont = false;
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int p = it * 4 + g;
+    for (int st = 0; st < 8; ++st) {
+      if (st >= n_steps) break;  // warp-uniform
+      const int p = int(srcs >> (8 * st)) & 31;
+      const bool valid = 4 * st + g < n_walk;
       const int32_t qs = __shfl_sync(0xffffffffu, my_qs, p);
       const int32_t qe = __shfl_sync(0xffffffffu, my_qe, p);
-      const uint32_t ln = __shfl_sync(0xffffffffu, sl.line, p) - round;
-      const uint32_t first = __shfl_sync(0xffffffffu, sl.first, p);
-      const bool act = (walking >> it) & 1u;
-      const uint4 d = v[it];
+      const uint32_t c0 = __shfl_sync(0xffffffffu, cnt, p);
+      const uint4 d = v[st];
       const int32_t base = int32_t(__shfl_sync(0xffffffffu, d.x, g0));
       const int32_t exmax = int32_t(__shfl_sync(0xffffffffu, d.y, g0));
       const Slots s = slots_of(d, sub);
-      const bool ha = act && row_hits(s.a_lo, s.a_id, base, qs, qe);
-      const bool hb = act && row_hits(s.b_lo, s.b_id, base, qs, qe);
+      const bool ha = valid && row_hits(s.a_lo, s.a_id, base, qs, qe);
+      const bool hb = valid && row_hits(s.b_lo, s.b_id, base, qs, qe);
       const uint32_t ma = (__ballot_sync(0xffffffffu, ha) >> g0) & 0xFFu;
       const uint32_t mb = (__ballot_sync(0xffffffffu, hb) >> g0) & 0xFFu;
       if (EMIT) {
         const uint32_t below = (1u << sub) - 1u;
-        const uint32_t pa = c[it] + __popc(ma & below);
-        const uint32_t pb = c[it] + __popc(ma) + __popc(mb & below);
+        const uint32_t pa = c0 + __popc(ma & below);
+        const uint32_t pb = c0 + __popc(ma) + __popc(mb & below);
         if (ha && pa < kSlots) stash[p * kStride + pa] = s.a_id;
         if (hb && pb < kSlots) stash[p * kStride + pb] = s.b_id;
       }
-      c[it] += __popc(ma) + __popc(mb);
-      const bool more = act && exmax >= qs && ln > first;  // an earlier row still reaches qs
-      if (!more) walking &= ~(1u << it);
+      // hand the new count and "an earlier row still reaches qs" back to the owner lane
+      const uint32_t c1 = __shfl_sync(0xffffffffu, c0 + __popc(ma) + __popc(mb), (r & 3) * 8);
+      const unsigned reach = __ballot_sync(0xffffffffu, valid && exmax >= qs);
+      if (walking && (r >> 2) == st) {
+        cnt = c1;
+        cont = (reach >> ((r & 3) * 8)) & 1u;
+      }
     }
-  }
-  uint32_t cnt = 0;
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {  // row L was served in step L >> 2 by group L & 3
-    const uint32_t got = __shfl_sync(0xffffffffu, c[it], (lane & 3) * 8);
-    if ((lane >> 2) == it) cnt = got;
+    walking = walking && cont && ln > sl.first;
+    ln -= 1;
   }
   if (i < n) cnt_out[i] = cnt;  // rle_right (interval_join.rs:1604)
 
@@ -284,9 +292,10 @@ bool use_packed(const sq_index* idx) {
   const int forced = e ? atoi(e) : -1;
   if (forced == 0) return false;
   if (forced == 1) return true;
-  const char* b = getenv("SQ_PACKED_MAX_BACK");
-  const float max_back = b ? float(atof(b)) : 1e9f;
-  return idx->mean_back_lines <= max_back;
+  // Measured on B200: the fused kernel wins when the index is far larger than L2 (cfg5, 100M rows:
+  // 1.15 ms vs 1.83 ms per 12.5M probe rows) and loses on an L2-resident one (cfg2, 1M rows: 0.085
+  // vs 0.067 ms), where the SoA kernels' loads are cache hits and the chained scan is pure overhead.
+  return idx->n_lines * 128ull > (64ull << 20);
 }
 
 int launch_packed(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
@@ -303,6 +312,21 @@ int launch_packed(sq_stream* s, const sq_index* idx, const uint64_t* d_key, cons
   auto* cnt = static_cast<uint32_t*>(s->d_cnt.p);
   SQ_CUDA(E, cudaMemsetAsync(result, 0, 32, s->stream));
   const IndexView iv = idx->view();
+  if (s->ctx->l2_persist_bytes && s->l2_window_idx != idx && idx->dir_bytes) {
+    // optional (SQ_L2_PERSIST_MB): keep the bin directory, the one structure every probe row reads at a
+    // random place, in the persisting part of L2; everything else streams through the rest
+    cudaStreamAttrValue av{};
+    size_t win = size_t(idx->dir_bytes);
+    if (win > s->ctx->l2_window_max) win = s->ctx->l2_window_max;
+    av.accessPolicyWindow.base_ptr = idx->d_dir;
+    av.accessPolicyWindow.num_bytes = win;
+    const double ratio = double(s->ctx->l2_persist_bytes) / double(win);
+    av.accessPolicyWindow.hitRatio = float(ratio > 1.0 ? 1.0 : ratio);
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+    s->l2_window_idx = idx;
+  }
   if (!d_left) {
     k_probe_packed<false, false><<<n_tiles, kPBlock, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket,
                                                                      result, nullptr, nullptr, 0);
