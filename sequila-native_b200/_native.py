@@ -62,6 +62,28 @@ SIGNATURES = {
     "sq_stream_launches": (C.c_uint64, [vp]),
 }
 
+
+
+class SqExecConfig(C.Structure):
+    """struct sq_exec_config (include/sequila_exec.h)"""
+    _fields_ = [("device", C.c_int32), ("n_on", C.c_int32), ("on_left", i32p), ("on_right", i32p),
+                ("left_start", C.c_int32), ("left_end", C.c_int32), ("right_start", C.c_int32),
+                ("right_end", C.c_int32), ("left_end_minus_one", C.c_int32), ("right_end_minus_one", C.c_int32),
+                ("n_projection", C.c_int32), ("projection", i32p)]
+
+
+# every symbol include/sequila_exec.h declares (Arrow C Data Interface structs travel as addresses)
+EXEC_SIGNATURES = {
+    "sq_exec_create": (C.c_int32, [C.POINTER(SqExecConfig), vp, vp, C.POINTER(vp)]),
+    "sq_exec_push_build": (C.c_int32, [vp, vp]),
+    "sq_exec_finish_build": (C.c_int32, [vp]),
+    "sq_exec_output_schema": (C.c_int32, [vp, vp]),
+    "sq_exec_probe": (C.c_int32, [vp, C.c_int32, vp, vp]),
+    "sq_exec_metrics": (C.c_int32, [vp, u64p]),
+    "sq_exec_last_error": (C.c_char_p, [vp]),
+    "sq_exec_free": (None, [vp]),
+}
+
 _lib = None
 
 
@@ -80,7 +102,7 @@ def lib():
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
                 " (make -C sequila-native_b200/csrc). The cuda interval join has no CPU fallback.")
         L = C.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
+        for name, (res, args) in list(SIGNATURES.items()) + list(EXEC_SIGNATURES.items()):
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args

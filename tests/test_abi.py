@@ -9,8 +9,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def header_symbols():
-    text = open(os.path.join(ROOT, "include", "sequila_cuda.h")).read()
+def header_symbols(name="sequila_cuda.h"):
+    text = open(os.path.join(ROOT, "include", name)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(sq_[a-z0-9_]+)\s*\(", text)))
 
@@ -32,6 +32,11 @@ def test_library_exports_every_declared_symbol():
     assert not missing, missing
     # the Python binding covers the same surface, so tests call exactly what a Rust -sys crate would
     assert sorted(_native.SIGNATURES) == declared
+    # same for the exec-node layer (Arrow C Data Interface), include/sequila_exec.h
+    declared_exec = [x for x in header_symbols("sequila_exec.h") if x.startswith("sq_exec_")]
+    missing = [x for x in declared_exec if not hasattr(lib, x)]
+    assert not missing, missing
+    assert sorted(_native.EXEC_SIGNATURES) == declared_exec
 
 
 def test_abi_version_and_no_fallback_without_gpu():
