@@ -43,7 +43,8 @@ def parse_args():
     ap.add_argument("--e2e-partitions", type=int, default=4, help="host threads, one sq_stream each")
     ap.add_argument("--e2e-tiles", type=int, default=16, help="probe sub-tiles per step (all partitions)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-contigs", type=int, default=4)
+    ap.add_argument("--cpu-sample-contigs", type=int, default=8)
+    ap.add_argument("--cpu-sample-probes", type=int, default=2_000_000)
     return ap.parse_args()
 
 
@@ -147,12 +148,10 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU baseline (oracle port of the reference's coitrees path) on a bounded contig-subset sample
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline(args, build_h, probe_h, threads):
-    """Times the reference's CPU path (oracle/: C++ restatement of coitrees 0.4.0 AVX2 tree +
-    interval_join.rs probe loop) on the box's host cores.  Sample = every build AND probe row of the
-    `cpu_sample_contigs` smallest contigs (same density / fan-out as the whole workload, since the
-    join never crosses contigs), capped at 1M probe rows."""
-    from oracle import oracle as O
+def cpu_sample(args, build_h, probe_h):
+    """Bounded sample of the workload for the CPU arm: every build AND probe row of the
+    `cpu_sample_contigs` smallest contigs (same density / fan-out as the whole workload, since the join
+    never crosses contigs), probe rows capped at --cpu-sample-probes."""
     from sequila_native_b200 import synth
     if args.workload == "cfg5_shard":
         sel = np.argsort(synth.HG38)[:args.cpu_sample_contigs]
@@ -163,14 +162,31 @@ def cpu_baseline(args, build_h, probe_h, threads):
         bm = np.ones(len(build_h["key"]), bool)
         pm = np.ones(len(probe_h["key"]), bool)
         what = "whole build side"
-    pk, ps, pe = probe_h["key"][pm][:1_000_000], probe_h["start"][pm][:1_000_000], probe_h["end"][pm][:1_000_000]
-    idx = O.OracleIndex(build_h["key"][bm], build_h["start"][bm], build_h["end"][bm], variant=8)
-    sec, pairs, _ = idx.time_probe(pk, ps, pe, threads=threads, batch_rows=8192)
-    return {"value": len(pk) / sec, "unit": "probe intervals/s", "cores": threads, "kind": "port",
-            "sample": f"{what}: {int(bm.sum())} build rows, {len(pk)} probe rows, {pairs} pairs, "
-                      f"probe {sec:.3f}s, index build {idx.build_seconds:.2f}s (1 thread); "
+    cap = args.cpu_sample_probes
+    return ({k: build_h[k][bm] for k in ("key", "start", "end")},
+            {k: probe_h[k][pm][:cap] for k in ("key", "start", "end")}, what)
+
+
+def cpu_baseline(args, build_h, probe_h, threads, min_seconds=1.0, index=None):
+    """Times the reference's CPU path (oracle/: C++ restatement of coitrees 0.4.0 AVX2 tree +
+    interval_join.rs probe loop) on the box's host cores: 8192-row probe batches dealt round-robin to
+    `threads` threads over one shared index (= DataFusion CollectLeft with target_partitions = threads).
+    Passes over the sample are repeated until `min_seconds` of wall time (x threads = CPU work)."""
+    from oracle import oracle as O
+    b, p, what = cpu_sample(args, build_h, probe_h)
+    idx = index or O.OracleIndex(b["key"], b["start"], b["end"], variant=8)
+    secs, pairs = [], 0
+    idx.time_probe(p["key"], p["start"], p["end"], threads=threads, batch_rows=8192)  # warm-up pass
+    while sum(secs) < min_seconds and len(secs) < 64:
+        sec, pairs, _ = idx.time_probe(p["key"], p["start"], p["end"], threads=threads, batch_rows=8192)
+        secs.append(sec)
+    sec = float(np.mean(secs))
+    n = len(p["key"])
+    return {"value": n / sec, "unit": "probe intervals/s", "cores": threads, "target_partitions": threads, "kind": "port",
+            "sample": f"{what}: {len(b['key'])} build rows, {n} probe rows, {pairs} pairs per pass, {len(secs)} passes of "
+                      f"{sec:.3f}s ({sum(secs) * threads:.0f} core-seconds), index build {idx.build_seconds:.2f}s (1 thread); "
                       f"coitrees 0.4.0 AVX2-layout restatement, 8192-row batches dealt to {threads} thread(s)",
-            "pairs_per_s": pairs / sec, "seconds": sec}
+            "pairs_per_s": pairs / sec, "seconds": sec, "_index": idx}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -195,7 +211,7 @@ def run_reference(args, rank, world):
             st = (rng.random(n) * (L - wd + 1)).astype(np.int64)
             return synth._table(c, st, st + wd - 1)
         build_h = side(int(args.build_rows * frac), 5001)
-        probe_h = side(min(int(args.shard_rows * frac), 1_000_000), 5002)
+        probe_h = side(min(int(args.shard_rows * frac), args.cpu_sample_probes), 5002)
         name = (f"cfg5 100Mx100M hg38-weighted U{{50..150}}: {args.build_rows} build rows replicated per GPU, "
                 f"{args.shard_rows}-probe shard per GPU (N=8 == the full config)")
     else:
@@ -203,11 +219,14 @@ def run_reference(args, rank, world):
         name = args.workload
     vals = []
     base = None
-    for it in range(args.warmup + args.steps):
-        base = cpu_baseline(args, build_h, probe_h, threads)
+    index = None
+    t_all = time.time()
+    for it in range(args.warmup + args.steps):  # one step = one timed pass set over the bounded sample
+        base = cpu_baseline(args, build_h, probe_h, threads, min_seconds=0.5, index=index)
+        index = base.pop("_index")
         if it >= args.warmup:
             vals.append(base)
-        if it >= 2 and sum(v["seconds"] for v in vals) > 120:
+        if len(vals) >= 3 and time.time() - t_all > 150:
             break
     v = float(np.mean([b["value"] for b in vals]))
     ms = float(np.mean([b["seconds"] for b in vals])) * 1e3
@@ -307,13 +326,8 @@ def main():
     step_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
     clocks = sampler.stop(t0, t1) if sampler else None
 
-    tmax = torch.tensor([step_ms], device=device, dtype=torch.float64)
-    tot = torch.tensor([float(n_probe), float(n_pairs)], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    step_ms_max = float(tmax.item())
-    probes_total, pairs_total = float(tot[0].item()), float(tot[1].item())
+    from sequila_native_b200.sharding import reduce_step
+    step_ms_max, probes_total, pairs_total = reduce_step(step_ms, n_probe, n_pairs, device)
     value = probes_total / (step_ms_max * 1e-3)
 
     # ---- end to end through the host C ABI: pinned host inputs -> H2D -> kernels -> D2H pairs.
@@ -369,10 +383,8 @@ def main():
         e2e_step()
     torch.cuda.synchronize()
     e_ms = (time.perf_counter() - e0) * 1e3 / args.e2e_steps
-    emax = torch.tensor([e_ms], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(emax, op=dist.ReduceOp.MAX)
-    e2e_value = probes_total / (float(emax.item()) * 1e-3)
+    e_ms_max, _, _ = reduce_step(e_ms, 0, 0, device)
+    e2e_value = probes_total / (e_ms_max * 1e-3)
     pool.shutdown()
 
     if rank == 0:
@@ -380,7 +392,7 @@ def main():
         # B_probe of SURVEY.md §8(d) with u64 key hashes consumed on the device:
         # 16 B per probe row (key hash 8 + start 4 + end 4) + 12 B per emitted pair
         # (read the hit's build row id 4, write (left,right) 8).  One launch = the whole tile.
-        dom = "k_probe_join"
+        dom = "k_probe_packed" if launches <= args.steps else "k_probe_count+k_tile_scan+k_probe_write"
         b_dom = 16.0 * n_probe + 12.0 * n_pairs
         t_dom = phases["join"]
         achieved = b_dom / (t_dom * 1e-3) / 1e9 if t_dom > 0 else 0.0
@@ -404,7 +416,7 @@ def main():
                       "roofline_frac": (24.0 * n_build / (build_best * 1e-3) / 1e9 / hbm_peak) if build_best else None,
                       "index_bytes": idx.bytes, "keys": idx.keys},
             "e2e": {"value": e2e_value, "unit": "probe intervals/s", "h2d_bytes_per_step": 16 * n_probe,
-                    "d2h_bytes_per_step": 8 * n_pairs + 4 * n_probe + 8, "ms_per_step": float(emax.item()),
+                    "d2h_bytes_per_step": 8 * n_pairs + 4 * n_probe + 8, "ms_per_step": e_ms_max,
                     "steps": args.e2e_steps, "api": "sq_probe_join (host C ABI), pinned host buffers", "partitions": T, "tiles": n_tiles},
             "gpu_launches": int(launches), "clocks": clocks,
             "digest": {"pairs": dg[0], "sum": dg[1], "xor": dg[2]},
@@ -414,7 +426,8 @@ def main():
                 bh, ph = _sample_to_host(build, args), _sample_to_host(probe, args)
             else:
                 bh, ph = to_host(build), to_host(probe)
-            result["cpu_baseline"] = cpu_baseline(args, bh, ph, threads=os.cpu_count() or 1)
+            result["cpu_baseline"] = cpu_baseline(args, bh, ph, threads=os.cpu_count() or 1, min_seconds=1.5)
+            result["cpu_baseline"].pop("_index", None)
         print(json.dumps(result))
     if world > 1:
         dist.barrier()
