@@ -30,8 +30,7 @@
 
 namespace sq {
 
-constexpr int kPBlock = 128;             // threads per CTA = probe rows per CTA
-constexpr int kPWarps = kPBlock / 32;
+constexpr int kPBlockDefault = 128;      // threads per CTA = probe rows per CTA
 constexpr uint32_t kSlots = 32;          // stash slots per probe row
 constexpr uint32_t kStride = kSlots + 1; // padded row stride of the stash (bank spread)
 
@@ -74,12 +73,13 @@ __device__ __forceinline__ bool row_hits(uint32_t lo_word, uint32_t id, int32_t 
   return id != kEmptyRow && st <= qe && en >= qs;
 }
 
-template <bool EMIT, bool WRITE_RIGHT>
-__global__ void __launch_bounds__(kPBlock, 8)
+template <bool EMIT, bool WRITE_RIGHT, int kPBlock>
+__global__ void __launch_bounds__(kPBlock, 1024 / kPBlock)
 k_probe_packed(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __restrict__ q_start,
                const int32_t* __restrict__ q_end, uint32_t n, uint32_t* __restrict__ cnt_out,
                unsigned long long* chain_state, unsigned int* ticket, unsigned long long* result,
                uint32_t* __restrict__ left_out, uint32_t* __restrict__ right_out, uint64_t capacity) {
+  constexpr int kPWarps = kPBlock / 32;
   __shared__ uint32_t s_stash[EMIT ? kPWarps * 32 * kStride : 1];
   __shared__ unsigned long long s_wtot[kPWarps];
   __shared__ unsigned long long s_base;
@@ -173,8 +173,14 @@ k_probe_packed(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* 
 
   const uint32_t cincl = warp_incl_sum(cnt);  // a warp emits < 2^32 pairs unless rows hit > 2^27 builds each
   const uint32_t wtot = __shfl_sync(0xffffffffu, cincl, 31);
-  if (!EMIT) {  // count only: the grand total is order-free
-    if (lane == 0 && wtot) atomicAdd(result, (unsigned long long)wtot);
+  if (!EMIT) {  // count only: the grand total is order-free; one atomic per CTA (same-address atomics
+                // serialise at ~2.5 ns each: one per warp would cost 1 ms per 12.5M rows by itself)
+    __shared__ unsigned long long s_ctot;
+    if (threadIdx.x == 0) s_ctot = 0;
+    __syncthreads();
+    if (lane == 0 && wtot) atomicAdd(&s_ctot, (unsigned long long)wtot);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_ctot) atomicAdd(result, s_ctot);
     return;
   }
 
@@ -298,10 +304,31 @@ bool use_packed(const sq_index* idx) {
   return idx->n_lines * 128ull > (64ull << 20);
 }
 
+template <int B>
+static void launch_packed_b(sq_stream* s, const IndexView& iv, const uint64_t* d_key, const int32_t* d_start,
+                            const int32_t* d_end, uint32_t n, uint32_t* cnt, unsigned long long* chain, unsigned int* ticket,
+                            unsigned long long* result, uint32_t* d_left, uint32_t* d_right, uint64_t capacity) {
+  const uint32_t n_tiles = (n + B - 1) / B;
+  if (!d_left)
+    k_probe_packed<false, false, B><<<n_tiles, B, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket, result,
+                                                                   nullptr, nullptr, 0);
+  else if (d_right)
+    k_probe_packed<true, true, B><<<n_tiles, B, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket, result,
+                                                                 d_left, d_right, capacity);
+  else
+    k_probe_packed<true, false, B><<<n_tiles, B, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket, result,
+                                                                  d_left, nullptr, capacity);
+}
+
 int launch_packed(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
                   const int32_t* d_end, uint32_t n, uint32_t* d_left, uint32_t* d_right, uint64_t capacity) {
   ErrorSlot& E = s->err;
-  const uint32_t n_tiles = (n + kPBlock - 1) / kPBlock;
+  int block = kPBlockDefault;
+  if (const char* e = getenv("SQ_PBLOCK")) {  // experiment knob
+    const int v = atoi(e);
+    if (v == 64 || v == 128 || v == 256) block = v;
+  }
+  const uint32_t n_tiles = (n + block - 1) / block;
   int rc;
   if ((rc = ensure(E, s->d_cnt, size_t(n) * 4, false))) return rc;
   if ((rc = ensure(E, s->d_tile, size_t(n_tiles) * 8 + 16, false))) return rc;
@@ -327,18 +354,10 @@ int launch_packed(sq_stream* s, const sq_index* idx, const uint64_t* d_key, cons
     if (cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
     s->l2_window_idx = idx;
   }
-  if (!d_left) {
-    k_probe_packed<false, false><<<n_tiles, kPBlock, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket,
-                                                                     result, nullptr, nullptr, 0);
-  } else {
-    SQ_CUDA(E, cudaMemsetAsync(chain, 0, size_t(n_tiles) * 8 + 16, s->stream));
-    if (d_right)
-      k_probe_packed<true, true><<<n_tiles, kPBlock, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket,
-                                                                     result, d_left, d_right, capacity);
-    else
-      k_probe_packed<true, false><<<n_tiles, kPBlock, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket,
-                                                                      result, d_left, nullptr, capacity);
-  }
+  if (d_left) SQ_CUDA(E, cudaMemsetAsync(chain, 0, size_t(n_tiles) * 8 + 16, s->stream));
+  if (block == 64) launch_packed_b<64>(s, iv, d_key, d_start, d_end, n, cnt, chain, ticket, result, d_left, d_right, capacity);
+  else if (block == 256) launch_packed_b<256>(s, iv, d_key, d_start, d_end, n, cnt, chain, ticket, result, d_left, d_right, capacity);
+  else launch_packed_b<128>(s, iv, d_key, d_start, d_end, n, cnt, chain, ticket, result, d_left, d_right, capacity);
   SQ_CUDA(E, cudaGetLastError());
   s->launches += 1;
   return SQ_OK;
