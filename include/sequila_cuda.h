@@ -120,6 +120,24 @@ int32_t sq_probe_join(sq_stream* s, const sq_index* idx, const uint64_t* key_has
                       uint32_t* left_idx_out, uint32_t* right_idx_out, uint32_t* counts_out,
                       uint64_t capacity, uint64_t* n_pairs_out);
 
+/* Algorithm::CoitreesNearest on the same index (IJ:794-812 build, IJ:909-956 `nearest`, IJ:972-990
+ * `get`, IJ:1593-1602 emit): ONE output row per probe row.
+ *   left_idx_out[i] = a build row overlapping probe row i when one exists (the reference reports the
+ *                     first one its tree traversal visits, "an arbitrary one", IJ:976; here: the
+ *                     overlapping row that is last in (start) order), else the row `nearest()` picks
+ *                     (two candidates around `end`, earlier one wins ties), else SQ_NULL_INDEX when the
+ *                     key hash never occurred on the build side (NULL left side, IJ:1597-1598).
+ *   right index of output row i is i.  May be NULL: the result then stays on the device for sq_gather_*
+ *   (fixed-width gathers write zero, Utf8 gathers an empty string, sq_gather_validity a cleared bit for
+ *   SQ_NULL_INDEX). */
+#define SQ_NULL_INDEX 0xFFFFFFFFu
+int32_t sq_probe_nearest(sq_stream* s, const sq_index* idx, const uint64_t* key_hash,
+                         const int32_t* start, const int32_t* end, uint32_t n_rows,
+                         uint32_t* left_idx_out);
+int32_t sq_probe_nearest_device(sq_stream* s, const sq_index* idx, const uint64_t* d_key_hash,
+                                const int32_t* d_start, const int32_t* d_end, uint32_t n_rows,
+                                uint32_t* d_left_idx_out);
+
 /* Device-pointer variants (kernel-level benchmark; outputs stay in HBM).  The count and join
  * variants synchronise the stream to return n_pairs; probe columns must stay valid until the
  * tile's emit. */
@@ -157,7 +175,8 @@ int32_t sq_gather_utf8(sq_stream* s, int32_t side, int32_t build_col_id, const i
                        const uint8_t* probe_data, uint64_t probe_data_bytes, int32_t* out_offsets,
                        uint64_t* total_bytes_out);
 int32_t sq_gather_utf8_data(sq_stream* s, uint8_t* out_data, uint64_t capacity);
-/* Arrow validity bitmaps of payload columns: out bit k = in bit idx[k]; *null_count_out = zeros. */
+/* Arrow validity bitmaps of payload columns: out bit k = in bit idx[k] (a build column without a bitmap
+ * counts as all-valid), 0 where idx[k] == SQ_NULL_INDEX; *null_count_out = zeros. */
 int32_t sq_index_set_validity(sq_index* idx, int32_t col_id, const uint8_t* bitmap);
 int32_t sq_gather_validity(sq_stream* s, int32_t side, int32_t build_col_id, const uint8_t* probe_bitmap,
                            uint8_t* out_bitmap, uint64_t* null_count_out);

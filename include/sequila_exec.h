@@ -66,7 +66,12 @@ typedef struct sq_exec_config {
   int32_t right_end_minus_one;
   int32_t n_projection;       /* -1 = all columns: left then right (build_join_schema, IJ:133) */
   const int32_t* projection;  /* indices into [left columns..., right columns...] (IJ:520-526) */
+  int32_t algorithm;          /* SQ_EXEC_OVERLAPS: every overlapping pair (alg=Cuda, the Coitrees semantics);
+                                 SQ_EXEC_NEAREST: one row per probe row, left side = an overlapping build row,
+                                 else the nearest one, else NULL (alg=CudaNearest = CoitreesNearest, IJ:972-990) */
 } sq_exec_config;
+#define SQ_EXEC_OVERLAPS 0
+#define SQ_EXEC_NEAREST 1
 
 /* schemas are struct ("+s") schemas of the two inputs; they are only read during the call */
 int32_t sq_exec_create(const sq_exec_config* cfg, const struct ArrowSchema* left_schema,

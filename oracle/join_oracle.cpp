@@ -13,14 +13,19 @@
 //   orc_probe_counts  IJ:1604      the rle_right vector itself
 //   orc_gather_i32    IJ:1620-1632 arrow::compute::take of one 4-byte column
 //   orc_brute         independent O(Nb*Np) check of the predicate IV:95-137 / CT/nosimd.rs:647-649
+//   orc_nearest       IJ:794-812 (build: tree + intervals sorted by (first, last)), IJ:909-956
+//                     (`nearest`), IJ:972-990 (`get`: first overlap the tree reports, else nearest),
+//                     IJ:1593-1602 (one output row per probe row, NULL left side on a key miss)
 //   orc_time_probe    the same probe loop dealt to T threads in 8192-row
 //                     batches over one shared index (= PartitionMode::CollectLeft
 //                     with target_partitions = T, IJ:473-487), for the CPU baseline
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // --impl reference legs may load this library.
+#include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <climits>
 #include <cstdlib>
 #include <thread>
 #include <unordered_map>
@@ -128,6 +133,57 @@ int64_t orc_probe_counts(const void* h, const uint64_t* key, const int32_t* star
     total += int64_t(hits.size());
   }
   return total;
+}
+
+
+// Algorithm::CoitreesNearest.  left_out[i] = build row chosen for probe row i, 0xFFFFFFFF = NULL.
+// overlap_out[i] (nullable) = 1 when the row was an overlap (then WHICH overlapping row is reported
+// is the tree's traversal order, unspecified by the reference: "return an arbitrary one", IJ:976).
+void orc_nearest(const uint64_t* bkey, const int32_t* bstart, const int32_t* bend, uint64_t nb,
+                 const uint64_t* pkey, const int32_t* pstart, const int32_t* pend, uint64_t np,
+                 uint32_t* left_out, uint8_t* overlap_out) {
+  struct PerKey {
+    orc::Tree<8> tree;
+    std::vector<orc::Interval> sorted;
+  };
+  std::unordered_map<uint64_t, std::vector<orc::Interval>> buckets;
+  for (uint64_t i = 0; i < nb; ++i) buckets[bkey[i]].push_back(orc::Interval{bstart[i], bend[i], i});
+  std::unordered_map<uint64_t, PerKey> map;
+  for (auto& kv : buckets) {
+    std::vector<orc::Interval> sorted = kv.second;  // IJ:803-806: stable sort by (first, last)
+    std::stable_sort(sorted.begin(), sorted.end(), [](const orc::Interval& a, const orc::Interval& b) {
+      return a.first != b.first ? a.first < b.first : a.last < b.last;
+    });
+    map.emplace(kv.first, PerKey{orc::Tree<8>(std::vector<orc::Interval>(kv.second)), std::move(sorted)});
+  }
+  for (uint64_t i = 0; i < np; ++i) {
+    left_out[i] = 0xFFFFFFFFu;
+    if (overlap_out) overlap_out[i] = 0;
+    auto it = map.find(pkey[i]);
+    if (it == map.end()) continue;  // IJ:974: no tree for the key => f never called => NULL (IJ:1597-1598)
+    const int32_t start = pstart[i], end = pend[i];
+    int seen = 0;
+    it->second.tree.query(start, end, [&](uint64_t pos) {  // IJ:977-983: the first overlap reported
+      if (seen == 0) { left_out[i] = uint32_t(pos); ++seen; }
+    });
+    if (seen) { if (overlap_out) overlap_out[i] = 1; continue; }
+    const auto& r = it->second.sorted;  // IJ:909-956
+    size_t left = 0, right = r.size();
+    while (left < right) {
+      const size_t mid = (left + right) / 2;
+      if (r[mid].first < end) left = mid + 1; else right = mid;
+    }
+    int64_t min_distance = INT32_MAX;
+    const size_t cand[2] = {left == 0 ? 0 : left - 1, left};
+    for (size_t c : cand) {
+      if (c >= r.size()) continue;
+      int64_t d;
+      if (end < r[c].first) d = int64_t(r[c].first) - end;
+      else if (r[c].last < start) d = int64_t(start) - r[c].last;
+      else d = 0;
+      if (d < min_distance) { min_distance = d; left_out[i] = uint32_t(r[c].meta); }
+    }
+  }
 }
 
 void orc_free(void* p) { std::free(p); }

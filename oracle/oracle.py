@@ -57,6 +57,9 @@ def _lib():
         L.orc_brute.restype = C.c_int64
         L.orc_brute.argtypes = [_u64p, _i32p, _i32p, C.c_uint64, _u64p, _i32p, _i32p, C.c_uint64,
                                 C.POINTER(_u32p), C.POINTER(_u32p)]
+        L.orc_nearest.restype = None
+        L.orc_nearest.argtypes = [_u64p, _i32p, _i32p, C.c_uint64, _u64p, _i32p, _i32p, C.c_uint64, _u32p,
+                                  C.POINTER(C.c_uint8)]
         L.orc_time_probe.restype = C.c_double
         L.orc_time_probe.argtypes = [C.c_void_p, _u64p, _i32p, _i32p, C.c_uint64, C.c_int32,
                                      C.c_uint32, C.c_int32, C.POINTER(_i32p), C.POINTER(_i32p),
@@ -193,6 +196,22 @@ def ref_superintervals_join(bkey, bstart, bend, pkey, pstart, pend):
                           _p(pk, _u64p), _p(ps, _i32p), _p(pe, _i32p), pk.shape[0],
                           C.byref(lp), C.byref(rp))
     return _take_pairs(_ref().siref_free, int(m), lp, rp)
+
+
+NULL_INDEX = 0xFFFFFFFF
+
+
+def nearest(bkey, bstart, bend, pkey, pstart, pend):
+    """Algorithm::CoitreesNearest (IJ:794-812, 909-956, 972-990, 1593-1602) -> (left_idx with
+    NULL_INDEX for a NULL left side, is_overlap flags)."""
+    bk, bs, be = _c(bkey, np.uint64), _c(bstart, np.int32), _c(bend, np.int32)
+    pk, ps, pe = _c(pkey, np.uint64), _c(pstart, np.int32), _c(pend, np.int32)
+    left = np.empty(pk.shape[0], dtype=np.uint32)
+    ov = np.zeros(pk.shape[0], dtype=np.uint8)
+    _lib().orc_nearest(_p(bk, _u64p), _p(bs, _i32p), _p(be, _i32p), bk.shape[0],
+                       _p(pk, _u64p), _p(ps, _i32p), _p(pe, _i32p), pk.shape[0], _p(left, _u32p),
+                       ov.ctypes.data_as(C.POINTER(C.c_uint8)))
+    return left, ov.astype(bool)
 
 
 def gather_i32(col, idx):

@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsequila_cuda.so")
 
 SQ_OK, SQ_EINVAL, SQ_ECUDA, SQ_ENOMEM, SQ_ESTATE, SQ_ECAPACITY, SQ_ECAST = range(7)
+NULL_INDEX = 0xFFFFFFFF  # SQ_NULL_INDEX
 
 u64p = C.POINTER(C.c_uint64)
 i64p = C.POINTER(C.c_int64)
@@ -44,6 +45,8 @@ SIGNATURES = {
     "sq_probe_count": (C.c_int32, [vp, vp, vp, vp, vp, C.c_uint32, u64p]),
     "sq_probe_emit_pairs": (C.c_int32, [vp, vp, vp, vp, C.c_uint64]),
     "sq_probe_join": (C.c_int32, [vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint64, u64p]),
+    "sq_probe_nearest": (C.c_int32, [vp, vp, vp, vp, vp, C.c_uint32, vp]),
+    "sq_probe_nearest_device": (C.c_int32, [vp, vp, vp, vp, vp, C.c_uint32, vp]),
     "sq_probe_join_device": (C.c_int32, [vp, vp, vp, vp, vp, C.c_uint32, vp, vp, C.c_uint64, u64p]),
     "sq_probe_count_device": (C.c_int32, [vp, vp, vp, vp, vp, C.c_uint32, u64p]),
     "sq_probe_emit_pairs_device": (C.c_int32, [vp, vp, vp, C.c_uint64]),
@@ -69,7 +72,7 @@ class SqExecConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("n_on", C.c_int32), ("on_left", i32p), ("on_right", i32p),
                 ("left_start", C.c_int32), ("left_end", C.c_int32), ("right_start", C.c_int32),
                 ("right_end", C.c_int32), ("left_end_minus_one", C.c_int32), ("right_end_minus_one", C.c_int32),
-                ("n_projection", C.c_int32), ("projection", i32p)]
+                ("n_projection", C.c_int32), ("projection", i32p), ("algorithm", C.c_int32)]
 
 
 # every symbol include/sequila_exec.h declares (Arrow C Data Interface structs travel as addresses)

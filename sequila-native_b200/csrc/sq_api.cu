@@ -576,6 +576,59 @@ SQ_API int32_t sq_gather_column(sq_stream* s, int32_t side, int32_t build_col_id
   return SQ_OK;
 }
 
+
+// ---- nearest (Algorithm::CoitreesNearest on the flat index) ------------------------------------
+static int32_t nearest_device(sq_stream* s, const sq_index* idx, const uint64_t* dk, const int32_t* ds,
+                              const int32_t* de, uint32_t n, uint32_t* d_left) {
+  ErrorSlot& E = s->err;
+  begin_tile(s, idx, dk, ds, de, n);
+  int rc;
+  if ((rc = ensure(E, s->d_right, size_t(n) * 4, false))) return rc;
+  if ((rc = launch_nearest(s, idx, dk, ds, de, n, d_left))) return rc;
+  if ((rc = launch_iota(s, static_cast<uint32_t*>(s->d_right.p), n))) return rc;
+  s->n_pairs = n;  // one output row per probe row (interval_join.rs:1593-1602)
+  s->counted = true;
+  s->emitted = true;
+  s->d_last_left = d_left;
+  s->d_last_right = static_cast<const uint32_t*>(s->d_right.p);
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_probe_nearest_device(sq_stream* s, const sq_index* idx, const uint64_t* d_key_hash,
+                                       const int32_t* d_start, const int32_t* d_end, uint32_t n_rows,
+                                       uint32_t* d_left_idx_out) {
+  uint64_t dummy = 0;
+  int rc = check_probe_args(s, idx, d_key_hash, d_start, d_end, n_rows, &dummy);
+  if (rc) return rc;
+  if (n_rows && !d_left_idx_out) return fail(s->err, SQ_EINVAL, "null d_left_idx_out");
+  SQ_CUDA(s->err, cudaSetDevice(s->ctx->device));
+  return nearest_device(s, idx, d_key_hash, d_start, d_end, n_rows, d_left_idx_out);
+}
+
+SQ_API int32_t sq_probe_nearest(sq_stream* s, const sq_index* idx, const uint64_t* key_hash, const int32_t* start,
+                                const int32_t* end, uint32_t n_rows, uint32_t* left_idx_out) {
+  uint64_t dummy = 0;
+  int rc = check_probe_args(s, idx, key_hash, start, end, n_rows, &dummy);
+  if (rc) return rc;
+  ErrorSlot& E = s->err;
+  SQ_CUDA(E, cudaSetDevice(s->ctx->device));
+  const size_t n = n_rows;
+  if (n == 0) { begin_tile(s, idx, nullptr, nullptr, nullptr, 0); s->n_pairs = 0; s->counted = s->emitted = true; return SQ_OK; }
+  if ((rc = ensure(E, s->d_in, n * 16, false))) return rc;
+  if ((rc = ensure(E, s->d_left, n * 4, false))) return rc;
+  auto* dk = static_cast<uint64_t*>(s->d_in.p);
+  auto* ds = reinterpret_cast<int32_t*>(dk + n);
+  auto* de = ds + n;
+  SQ_CUDA(E, cudaMemcpyAsync(dk, key_hash, n * 8, cudaMemcpyHostToDevice, s->stream));
+  SQ_CUDA(E, cudaMemcpyAsync(ds, start, n * 4, cudaMemcpyHostToDevice, s->stream));
+  SQ_CUDA(E, cudaMemcpyAsync(de, end, n * 4, cudaMemcpyHostToDevice, s->stream));
+  auto* dl = static_cast<uint32_t*>(s->d_left.p);
+  if ((rc = nearest_device(s, idx, dk, ds, de, n_rows, dl))) return rc;
+  if (left_idx_out) SQ_CUDA(E, cudaMemcpyAsync(left_idx_out, dl, n * 4, cudaMemcpyDeviceToHost, s->stream));
+  SQ_CUDA(E, cudaStreamSynchronize(s->stream));
+  return SQ_OK;
+}
+
 // ---- Utf8 / validity take ---------------------------------------------------------------------------
 SQ_API int32_t sq_index_add_utf8_column(sq_index* idx, const int64_t* offsets, const uint8_t* data, uint64_t data_bytes,
                                         int32_t* col_id_out) {
@@ -719,9 +772,9 @@ SQ_API int32_t sq_gather_validity(sq_stream* s, int32_t side, int32_t build_col_
   if (side == 0) {
     sq_index* idx = const_cast<sq_index*>(s->idx);
     std::lock_guard<std::mutex> g(idx->col_mu);
-    if (build_col_id < 0 || size_t(build_col_id) >= idx->columns.size() || !idx->columns[build_col_id].d_validity)
-      return fail(E, SQ_EINVAL, "build column %d has no validity bitmap", build_col_id);
-    d_in = idx->columns[build_col_id].d_validity;
+    if (build_col_id < 0 || size_t(build_col_id) >= idx->columns.size())
+      return fail(E, SQ_EINVAL, "unknown build column id %d", build_col_id);
+    d_in = idx->columns[build_col_id].d_validity;  // nullptr = every row valid; NULL indices still clear bits
   } else {
     if (!probe_bitmap) return fail(E, SQ_EINVAL, "null probe validity bitmap");
     uint8_t* d = d_out + ((out_bytes + 31) & ~size_t(31));

@@ -449,11 +449,18 @@ SQ_API int32_t sq_exec_probe(sq_exec* e, int32_t partition, const ArrowArray* ba
   if ((rc = eval_i32(e, st, e->right, e->cfg.right_end, e->cfg.right_end_minus_one != 0, batch, &end))) return rc;
 
   uint64_t n_pairs = 0;
-  rc = sq_probe_count(st, e->index, keys.data(), start.data(), end.data(), uint32_t(n), &n_pairs);
-  if (rc != SQ_OK) return e->fail(rc, "%s", sq_stream_last_error(st));
-  // the index pairs stay on the device: only the gathered columns travel back (IJ:1620-1632)
-  rc = sq_probe_emit_pairs(st, nullptr, nullptr, nullptr, n_pairs);
-  if (rc != SQ_OK) return e->fail(rc, "%s", sq_stream_last_error(st));
+  const bool nearest = e->cfg.algorithm == SQ_EXEC_NEAREST;
+  if (nearest) {  // one output row per probe row; the left side may be NULL (IJ:1593-1602)
+    rc = sq_probe_nearest(st, e->index, keys.data(), start.data(), end.data(), uint32_t(n), nullptr);
+    if (rc != SQ_OK) return e->fail(rc, "%s", sq_stream_last_error(st));
+    n_pairs = n;
+  } else {
+    rc = sq_probe_count(st, e->index, keys.data(), start.data(), end.data(), uint32_t(n), &n_pairs);
+    if (rc != SQ_OK) return e->fail(rc, "%s", sq_stream_last_error(st));
+    // the index pairs stay on the device: only the gathered columns travel back (IJ:1620-1632)
+    rc = sq_probe_emit_pairs(st, nullptr, nullptr, nullptr, n_pairs);
+    if (rc != SQ_OK) return e->fail(rc, "%s", sq_stream_last_error(st));
+  }
 
   // `out` is assembled in place; on any failure below everything attached so far is released
   auto* own = new Owned();
@@ -501,7 +508,7 @@ SQ_API int32_t sq_exec_probe(sq_exec* e, int32_t partition, const ArrowArray* ba
         for (uint64_t i = 0; i < n; ++i) if (bit_at(pv.validity, pv.offset + int64_t(i))) probe_bm[i >> 3] |= uint8_t(1u << (i & 7));
       }
     }
-    if ((build_nulls || probe_nulls) && n_pairs) {
+    if ((build_nulls || probe_nulls || (nearest && side == 0)) && n_pairs) {
       void* bm = pinned((n_pairs + 7) / 8);
       if (!bm) return e->fail(SQ_ENOMEM, "pinned allocation failed");
       co->pinned.push_back(bm);
@@ -509,7 +516,7 @@ SQ_API int32_t sq_exec_probe(sq_exec* e, int32_t partition, const ArrowArray* ba
       rc = sq_gather_validity(st, side, bid, probe_nulls ? probe_bm.data() : nullptr, static_cast<uint8_t*>(bm), &nulls);
       if (rc != SQ_OK) return e->fail(rc, "%s", sq_stream_last_error(st));
       child->null_count = int64_t(nulls);
-      validity_out = bm;
+      validity_out = nulls ? bm : nullptr;  // Arrow: no bitmap needed when nothing is null
     }
 
     if (t.kind == Kind::Fixed) {

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256) k_gather(const T* __restrict__ values, co
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
       const uint64_t i = base + uint64_t(k) * blockDim.x;
-      if (i < n) v[k] = __ldg(values + ix[k]);
+      if (i < n) v[k] = ix[k] == kEmptyRow ? T{} : __ldg(values + ix[k]);  // NULL left side (nearest): zero value
     }
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
@@ -165,6 +165,7 @@ __device__ __forceinline__ unsigned long long str_len(const int64_t* __restrict_
                                                       uint64_t k, uint64_t n) {
   if (k >= n) return 0ull;
   const uint32_t r = __ldg(idx + k);
+  if (r == kEmptyRow) return 0ull;  // NULL left side: empty string under a cleared validity bit
   return (unsigned long long)(__ldg(off + r + 1) - __ldg(off + r));
 }
 
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(256) k_str_copy(const int64_t* __restrict__ of
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
   for (uint64_t k = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < n; k += stride) {
     const uint32_t r = __ldg(idx + k);
+    if (r == kEmptyRow) continue;
     const int64_t a = __ldg(off + r), b = __ldg(off + r + 1);
     uint8_t* dst = out + out_off[k];
     for (int64_t c = a; c < b; ++c) *dst++ = __ldg(data + c);
@@ -262,7 +264,8 @@ int launch_str_copy(sq_stream* s, const int64_t* d_src_off, const uint8_t* d_src
   return SQ_OK;
 }
 
-// Arrow validity take: out bit k = in bit idx[k]; one thread per output byte; counts the nulls
+// Arrow validity take: out bit k = in bit idx[k] (all set when bitmap == nullptr), 0 for a NULL index;
+// one thread per output byte; counts the nulls
 __global__ void __launch_bounds__(256) k_gather_bits(const uint8_t* __restrict__ bitmap,
                                                      const uint32_t* __restrict__ idx, uint64_t n,
                                                      uint8_t* __restrict__ out, unsigned long long* nulls) {
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(256) k_gather_bits(const uint8_t* __restrict__
       const uint64_t e = b * 8 + k;
       if (e < n) {
         const uint32_t r = __ldg(idx + e);
-        const unsigned int bit = (__ldg(bitmap + (r >> 3)) >> (r & 7)) & 1u;
+        const unsigned int bit = r == kEmptyRow ? 0u : (bitmap ? ((__ldg(bitmap + (r >> 3)) >> (r & 7)) & 1u) : 1u);
         v |= bit << k;
         my_nulls += 1u - bit;
       }
@@ -305,6 +308,19 @@ int launch_gather_bits(sq_stream* s, const uint8_t* d_bitmap, const uint32_t* d_
   SQ_CUDA(E, cudaMemcpyAsync(h, slot, 8, cudaMemcpyDeviceToHost, s->stream));
   SQ_CUDA(E, cudaStreamSynchronize(s->stream));
   *null_count = h[0];
+  return SQ_OK;
+}
+
+__global__ void __launch_bounds__(256) k_iota(uint32_t* __restrict__ out, uint64_t n) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = uint32_t(i);
+}
+
+int launch_iota(sq_stream* s, uint32_t* d_out, uint64_t n) {
+  if (n == 0) return SQ_OK;
+  k_iota<<<grid_for(n, 256, s->ctx->sm_count), 256, 0, s->stream>>>(d_out, n);
+  SQ_CUDA(s->err, cudaGetLastError());
+  s->launches += 1;
   return SQ_OK;
 }
 

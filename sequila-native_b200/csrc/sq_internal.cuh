@@ -233,6 +233,12 @@ int launch_count(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const
 int launch_write(sq_stream* s, const sq_index* idx, const int32_t* d_start, uint32_t n, uint32_t* d_left,
                  uint32_t* d_right, uint64_t capacity);
 
+// one output row per probe row: an overlapping build row, else the nearest one, else kEmptyRow (NULL)
+int launch_nearest(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
+                   const int32_t* d_end, uint32_t n, uint32_t* d_left);
+// right_idx of a one-row-per-probe-row result: 0, 1, ..., n-1
+int launch_iota(sq_stream* s, uint32_t* d_out, uint64_t n);
+
 // probe_packed.cu: one fused pass over the packed lines (count + chained scan + write when
 // d_left != nullptr; count only otherwise).  Leaves cnt per row in s->d_cnt, result[0] = n_pairs and
 // result[1] = 1 when the pairs did not fit `capacity` (nothing useful was written then).

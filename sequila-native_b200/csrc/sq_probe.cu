@@ -355,6 +355,97 @@ k_probe_write(IndexView iv, const int32_t* __restrict__ q_start, uint32_t n, con
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Algorithm::CoitreesNearest on the flat index (reference interval_join.rs:794-812, 909-956, 972-990,
+// 1593-1602): ONE output row per probe row.  left = a build row overlapping the probe row if one
+// exists (the reference reports the first its tree traversal visits, "an arbitrary one"; here: the
+// overlapping row with the greatest sorted position), else the row `nearest()` picks, else NULL when
+// the key hash never occurred on the build side.  `nearest()` looks at exactly two candidates of the
+// segment ordered by (start, end, row): the last one with start < qe and the first one with
+// start >= qe; the earlier candidate wins ties.  Rows with equal start are adjacent here (the segment
+// is sorted by start), so each candidate is a min / max over one short run.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t first_start_greater(const IndexView& iv, const SegMeta& m, int32_t q) {
+  if (q < m.min_start) return m.sb;
+  const uint32_t off = uint32_t(q) - uint32_t(m.min_start);
+  const uint32_t b = m.shift >= 32 ? 0u : (off >> m.shift);
+  if (b >= m.nbins) return m.se;
+  uint32_t a = __ldg(iv.dir + m.dir_base + b);
+  uint32_t len = __ldg(iv.dir + m.dir_base + b + 1) - a;
+  while (len) {
+    const uint32_t half = len >> 1;
+    if (__ldg(iv.start + a + half) <= q) { a += half + 1; len -= half + 1; } else len = half;
+  }
+  return a;
+}
+
+__global__ void __launch_bounds__(256)
+k_probe_nearest(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __restrict__ q_start,
+                const int32_t* __restrict__ q_end, uint32_t n, uint32_t* __restrict__ left_out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t qs = q_start[i], qe = q_end[i];
+  const uint32_t id = ht_lookup(iv.ht_keys, iv.ht_ids, iv.ht_mask, iv.sentinel_id, q_key[i]);
+  if (id == kNoKey) { left_out[i] = kEmptyRow; return; }  // NULL left side (interval_join.rs:1597-1598)
+  const SegMeta m = iv.meta[id];
+  // an overlap, if any: walk back from the last start <= qe while some earlier end still reaches qs
+  const uint32_t hi = first_start_greater(iv, m, qe);
+  for (uint32_t j = hi; j > m.sb;) {
+    --j;
+    if (__ldg(iv.runmax + j) < qs) break;
+    if (__ldg(iv.end + j) >= qs) { left_out[i] = __ldg(iv.row + j); return; }
+  }
+  // nearest(): `left` = first position with start >= qe in (start, end, row) order
+  const uint32_t lb = qe == INT32_MIN ? m.sb : first_start_greater(iv, m, qe - 1);
+  long long best_d = INT32_MAX;
+  uint32_t best = kEmptyRow;
+  auto consider = [&](int32_t st, int32_t en, uint32_t row) {
+    long long d;
+    if (qe < st) d = (long long)st - qe;
+    else if (en < qs) d = (long long)qs - en;
+    else d = 0;
+    if (d < best_d) { best_d = d; best = row; }
+  };
+  auto first_of_run = [&](uint32_t j0) {  // min (end, row) over the run of rows with start == start[j0], j0 = its first row
+    const int32_t st = __ldg(iv.start + j0);
+    int32_t en = __ldg(iv.end + j0);
+    uint32_t row = __ldg(iv.row + j0);
+    for (uint32_t j = j0 + 1; j < m.se && __ldg(iv.start + j) == st; ++j) {
+      const int32_t e2 = __ldg(iv.end + j);
+      const uint32_t r2 = __ldg(iv.row + j);
+      if (e2 < en || (e2 == en && r2 < row)) { en = e2; row = r2; }
+    }
+    consider(st, en, row);
+  };
+  if (lb > m.sb) {  // sorted[left - 1]: max (end, row) over the run ending at lb - 1
+    const uint32_t j1 = lb - 1;
+    const int32_t st = __ldg(iv.start + j1);
+    int32_t en = __ldg(iv.end + j1);
+    uint32_t row = __ldg(iv.row + j1);
+    for (uint32_t j = j1; j > m.sb && __ldg(iv.start + j - 1) == st;) {
+      --j;
+      const int32_t e2 = __ldg(iv.end + j);
+      const uint32_t r2 = __ldg(iv.row + j);
+      if (e2 > en || (e2 == en && r2 > row)) { en = e2; row = r2; }
+    }
+    consider(st, en, row);
+  } else {
+    first_of_run(m.sb);  // left == 0: left.saturating_sub(1) is sorted[0] as well
+  }
+  if (lb < m.se) first_of_run(lb);  // sorted[left]
+  left_out[i] = best;
+}
+
+int launch_nearest(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
+                   const int32_t* d_end, uint32_t n, uint32_t* d_left) {
+  if (n == 0) return SQ_OK;
+  k_probe_nearest<<<(n + 255) / 256, 256, 0, s->stream>>>(idx->view(), d_key, d_start, d_end, n, d_left);
+  SQ_CUDA(s->err, cudaGetLastError());
+  s->launches += 1;
+  return SQ_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 static int ensure_probe_state(sq_stream* s, uint32_t n, uint32_t n_tiles) {
   ErrorSlot& E = s->err;

@@ -190,6 +190,15 @@ class CudaStream:
         _check(rc, self._err)
         return self.n_pairs
 
+    def probe_nearest(self, index: CudaIndex, key_hash, start, end) -> np.ndarray:
+        """sq_probe_nearest: one build row (or N.NULL_INDEX) per probe row."""
+        k, s, e = _np(key_hash, np.uint64), _np(start, np.int32), _np(end, np.int32)
+        out = np.empty(k.shape[0], dtype=np.uint32)
+        _check(self._lib.sq_probe_nearest(self._h, index._h, _ptr(k), _ptr(s), _ptr(e), k.shape[0], _ptr(out)), self._err)
+        self._keep = index
+        self.n_rows = self.n_pairs = int(k.shape[0])
+        return out
+
     def gather_build(self, col_id: int, dtype, width: int | None = None) -> np.ndarray:
         dtype = np.dtype(dtype)
         out = np.empty(self.n_pairs, dtype=dtype)

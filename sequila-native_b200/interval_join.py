@@ -192,8 +192,8 @@ class IntervalJoinExec:
         return (self._lib.sq_exec_last_error(self._exec) or b"").decode()
 
     def _open(self):
-        if self.algorithm != Algorithm.Cuda:
-            raise ExecutionError(f"algorithm {self.algorithm} is the reference's CPU code; this build executes alg=Cuda only")
+        if self.algorithm not in (Algorithm.Cuda, Algorithm.CudaNearest):
+            raise ExecutionError(f"algorithm {self.algorithm} is the reference's CPU code; this build executes alg=Cuda / CudaNearest only")
         if self.mode == AUTO:
             # IJ:504-509
             raise PlanError("Invalid IntervalJoinExec, unsupported PartitionMode Auto in execute()")
@@ -205,7 +205,7 @@ class IntervalJoinExec:
         proj = self.projection
         parr = (C.c_int32 * max(len(proj) if proj is not None else 1, 1))(*(proj or []))
         cfg = N.SqExecConfig(self.device, n_on, onl, onr, ls, le, rs, re_, int(lem), int(rem),
-                             -1 if proj is None else len(proj), parr)
+                             -1 if proj is None else len(proj), parr, 1 if self.algorithm == Algorithm.CudaNearest else 0)
         lsch, rsch = _ArrowSchema(), _ArrowSchema()
         self.left_schema._export_to_c(C.addressof(lsch))
         self.right_schema._export_to_c(C.addressof(rsch))

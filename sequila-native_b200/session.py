@@ -31,6 +31,7 @@ class Algorithm(enum.Enum):
     CoitreesNearest = "CoitreesNearest"
     CoitreesCountOverlaps = "CoitreesCountOverlaps"
     Cuda = "Cuda"  # the arm this repository adds next to coitrees and lapper
+    CudaNearest = "CudaNearest"  # CoitreesNearest's semantics (one row per probe row) on the same GPU index
 
     @classmethod
     def default(cls) -> "Algorithm":

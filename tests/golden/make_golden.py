@@ -10,6 +10,7 @@ Sources (reference file:line):
   sequila/sequila-core/tests/integration_test.rs:216-291       closed boundaries: 12 b-rows -> 10 rows
   sequila/sequila-core/tests/integration_test.rs:295-350       strict boundaries -> 6 rows
   sequila/sequila-core/src/physical_planner/joins/interval_join.rs:1959-1965  cast-overflow text
+  sequila/sequila-core/tests/integration_test.rs:352-399       CoitreesNearest: 1 a-row, 4 b-rows -> 4 rows
 """
 import csv
 import json
@@ -57,6 +58,15 @@ def main():
     a_sql = gteq[gteq.index("let a ="):gteq.index("let b =")]
     b_sql = gteq[gteq.index("let b ="):gteq.index("let q0")]
     m = re.search(r'"(Arrow error: Cast error: Can\'t cast value \{\} to type Int32)"', ij)
+    near = fn_body(it, "async fn test_nearest")
+    near_a = near[near.index("let a ="):near.index("let b =")]
+    near_b = near[near.index("let b ="):near.index("ctx.sql(\"SET")]
+    quad = lambda block: [[m[0], m[1], int(m[2]), int(m[3])]
+                          for m in re.findall(r"\('(\w+)',\s*'(\w+)',\s*(-?\d+),\s*(-?\d+)\)", block)]
+    near_rows = []
+    for line in re.findall(r'"\|([^"]*)\|"', near[near.index("let expected"):])[1:]:
+        cells = [c.strip() for c in line.split("|")]
+        near_rows.append([None if c == "" else (int(c) if re.fullmatch(r"-?\d+", c) else c) for c in cells])
     golden = {
         "_generated_by": "tests/golden/make_golden.py from /root/reference (see docstring for file:line)",
         "reads": read_csv("reads.csv"),
@@ -69,7 +79,11 @@ def main():
         "strict_rows": table_rows(gtlt[gtlt.index("let expected"):]),
         "cast_error_format": m.group(1),
         "cast_error_value": 2 ** 31,
+        "nearest_a": quad(near_a),
+        "nearest_b": quad(near_b),
+        "nearest_rows": near_rows,
     }
+    assert len(golden["nearest_a"]) == 1 and len(golden["nearest_b"]) == 4 and len(golden["nearest_rows"]) == 4
     assert len(golden["reads"]) == 12 and len(golden["targets"]) == 10
     assert len(golden["equi_rows"]) == 16 and len(golden["range_rows"]) == 32
     assert len(golden["boundary_a"]) == 1 and len(golden["boundary_b"]) == 12

@@ -111,3 +111,52 @@ def test_synthetic_configs_fanout(oracle):
         b, p = sn.synth.CONFIGS[name](scale=scale[name])
         c = oracle.OracleIndex(b["key"], b["start"], b["end"]).counts(p["key"], p["start"], p["end"])
         assert abs(float(c.mean()) - mean) < tol, (name, float(c.mean()))
+
+
+def test_nearest_matches_the_reference_table(oracle, golden):
+    """integration_test.rs:352-399 (CoitreesNearest, strict operators => end - 1 on both sides)"""
+    A, B = golden["nearest_a"], golden["nearest_b"]
+    ids = {}
+
+    def key(r):
+        return ids.setdefault((r[0], r[1]), len(ids) + 1)
+    bk = np.array([key(r) for r in A], np.uint64)
+    pk = np.array([key(r) for r in B], np.uint64)
+    left, ov = oracle.nearest(bk, [r[2] for r in A], [r[3] - 1 for r in A], pk, [r[2] for r in B], [r[3] - 1 for r in B])
+    rows = [(A[int(x)] if x != oracle.NULL_INDEX else [None] * 4) + B[i] for i, x in enumerate(left)]
+    assert sorted(rows, key=str) == sorted(golden["nearest_rows"], key=str)
+    assert not ov.any()
+
+
+def test_nearest_differential_vs_python_restatement(oracle):
+    """the C++ nearest() against a line-by-line Python restatement of interval_join.rs:909-956"""
+    rng = np.random.default_rng(5)
+    for _ in range(30):
+        nb, npq = int(rng.integers(1, 60)), int(rng.integers(1, 80))
+        bs = rng.integers(0, 300, nb).astype(np.int32)
+        be = (bs + rng.integers(0, 12, nb)).astype(np.int32)
+        ps = rng.integers(0, 300, npq).astype(np.int32)
+        pe = (ps + rng.integers(0, 12, npq)).astype(np.int32)
+        bk = np.zeros(nb, np.uint64)
+        pk = (rng.random(npq) < 0.1).astype(np.uint64)  # key 1 is absent from the build side
+        left, ov = oracle.nearest(bk, bs, be, pk, ps, pe)
+        order = sorted(range(nb), key=lambda j: (bs[j], be[j], j))  # stable sort by (first, last)
+        for i in range(npq):
+            if pk[i] == 1:
+                assert left[i] == oracle.NULL_INDEX
+                continue
+            hits = [j for j in range(nb) if bs[j] <= pe[i] and be[j] >= ps[i]]
+            if hits:
+                assert ov[i] and int(left[i]) in hits
+                continue
+            lo = 0
+            while lo < nb and bs[order[lo]] < pe[i]:
+                lo += 1
+            best, best_d = None, 2 ** 31 - 1
+            for c in (max(lo - 1, 0), lo):
+                if c < nb:
+                    j = order[c]
+                    d = bs[j] - pe[i] if pe[i] < bs[j] else (ps[i] - be[j] if be[j] < ps[i] else 0)
+                    if d < best_d:
+                        best, best_d = j, d
+            assert int(left[i]) == best
