@@ -181,6 +181,17 @@ int32_t sq_index_set_validity(sq_index* idx, int32_t col_id, const uint8_t* bitm
 int32_t sq_gather_validity(sq_stream* s, int32_t side, int32_t build_col_id, const uint8_t* probe_bitmap,
                            uint8_t* out_bitmap, uint64_t* null_count_out);
 
+/* ---- bounded output --------------------------------------------------------------------------
+ * The GPU analogue of `sequila.interval_join_low_memory` (IJ:1433-1530: the reference caps an output batch
+ * at 1M rows and continues with the remaining probe rows): the whole tile is emitted ONCE into device
+ * memory (sq_probe_emit_pairs with NULL outputs), the host then walks it in windows of the pair sequence —
+ * cut at probe-row boundaries with the counts of sq_stream_counts — and only one window at a time is
+ * gathered / copied to the host.  right_idx stays relative to the tile. */
+int32_t sq_stream_counts(sq_stream* s, uint32_t* counts_out /* n_rows of the counted tile: rle_right */);
+int32_t sq_stream_set_window(sq_stream* s, uint64_t pair_offset, uint64_t n_pairs);
+/* D2H copy of the current window (the whole tile if none was set); either output may be NULL */
+int32_t sq_fetch_pairs(sq_stream* s, uint32_t* left_idx_out, uint32_t* right_idx_out, uint64_t capacity);
+
 /* ---- helpers on the boundary -------------------------------------------------------------
  * `evaluate_as_i32` for BIGINT columns (IJ:1661-1672): checked cast Int64 -> Int32 on the
  * device, optionally subtracting `minus` first (the `end - 1` of strict comparisons,

@@ -10,6 +10,7 @@
  *   sq_exec_probe         fetch_probe_batch + process_probe_batch (full mode)  IJ:1192-1233, 1580-1640:
  *                         key hashes, evaluate_as_i32, probe on the GPU, `take` of every projected
  *                         column on the GPU, one output RecordBatch per probe batch
+ *   sq_exec_probe_begin / _next   the same in low-memory mode (IJ:1433-1530): bounded output batches
  *   sq_exec_metrics       BuildProbeJoinMetrics      utils.rs:441-495
  *
  * Batches cross the boundary as Arrow C Data Interface struct arrays (a RecordBatch).  Key hashing
@@ -69,6 +70,9 @@ typedef struct sq_exec_config {
   int32_t algorithm;          /* SQ_EXEC_OVERLAPS: every overlapping pair (alg=Cuda, the Coitrees semantics);
                                  SQ_EXEC_NEAREST: one row per probe row, left side = an overlapping build row,
                                  else the nearest one, else NULL (alg=CudaNearest = CoitreesNearest, IJ:972-990) */
+  int32_t low_memory;         /* sequila.interval_join_low_memory (SC:54): informational here, the caller picks
+                                 sq_exec_probe (one output batch per probe batch) or the begin/next protocol */
+  int64_t max_output_rows;    /* cap of one output batch in the begin/next protocol; <= 0: 1,000,000 (IJ:1439) */
 } sq_exec_config;
 #define SQ_EXEC_OVERLAPS 0
 #define SQ_EXEC_NEAREST 1
@@ -84,6 +88,11 @@ int32_t sq_exec_output_schema(const sq_exec* e, struct ArrowSchema* out);
 /* probes one batch (borrowed for the duration of the call) for `partition`; fills *out with one
  * struct array = the output RecordBatch of this probe batch (caller releases it) */
 int32_t sq_exec_probe(sq_exec* e, int32_t partition, const struct ArrowArray* batch, struct ArrowArray* out);
+/* Low-memory mode (IJ:1433-1530): the probe batch is joined once on the GPU, then handed back in output
+ * batches of at most max_output_rows rows cut at probe-row boundaries (a single probe row with more matches
+ * forms a batch of its own).  `batch` must stay valid until sq_exec_probe_next reported *has_more_out = 0. */
+int32_t sq_exec_probe_begin(sq_exec* e, int32_t partition, const struct ArrowArray* batch);
+int32_t sq_exec_probe_next(sq_exec* e, int32_t partition, struct ArrowArray* out, int32_t* has_more_out);
 /* [0] build_input_batches [1] build_input_rows [2] build_mem_used [3] input_batches [4] input_rows
  * [5] output_batches [6] output_rows [7] build_time_ns [8] join_time_ns [9] index_bytes [10] keys */
 int32_t sq_exec_metrics(const sq_exec* e, uint64_t out[16]);

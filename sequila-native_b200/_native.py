@@ -58,6 +58,9 @@ SIGNATURES = {
     "sq_gather_utf8_data": (C.c_int32, [vp, vp, C.c_uint64]),
     "sq_index_set_validity": (C.c_int32, [vp, C.c_int32, vp]),
     "sq_gather_validity": (C.c_int32, [vp, C.c_int32, C.c_int32, vp, vp, u64p]),
+    "sq_stream_counts": (C.c_int32, [vp, vp]),
+    "sq_stream_set_window": (C.c_int32, [vp, C.c_uint64, C.c_uint64]),
+    "sq_fetch_pairs": (C.c_int32, [vp, vp, vp, C.c_uint64]),
     "sq_cast_i64_to_i32": (C.c_int32, [vp, vp, C.c_uint64, C.c_int64, vp]),
     "sq_pairs_digest_device": (C.c_int32, [vp, vp, vp, C.c_uint64, C.c_uint64, u64p]),
     "sq_stream_set_profiling": (C.c_int32, [vp, C.c_int32]),
@@ -72,7 +75,8 @@ class SqExecConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("n_on", C.c_int32), ("on_left", i32p), ("on_right", i32p),
                 ("left_start", C.c_int32), ("left_end", C.c_int32), ("right_start", C.c_int32),
                 ("right_end", C.c_int32), ("left_end_minus_one", C.c_int32), ("right_end_minus_one", C.c_int32),
-                ("n_projection", C.c_int32), ("projection", i32p), ("algorithm", C.c_int32)]
+                ("n_projection", C.c_int32), ("projection", i32p), ("algorithm", C.c_int32),
+                ("low_memory", C.c_int32), ("max_output_rows", C.c_int64)]
 
 
 # every symbol include/sequila_exec.h declares (Arrow C Data Interface structs travel as addresses)
@@ -82,6 +86,8 @@ EXEC_SIGNATURES = {
     "sq_exec_finish_build": (C.c_int32, [vp]),
     "sq_exec_output_schema": (C.c_int32, [vp, vp]),
     "sq_exec_probe": (C.c_int32, [vp, C.c_int32, vp, vp]),
+    "sq_exec_probe_begin": (C.c_int32, [vp, C.c_int32, vp]),
+    "sq_exec_probe_next": (C.c_int32, [vp, C.c_int32, vp, i32p]),
     "sq_exec_metrics": (C.c_int32, [vp, u64p]),
     "sq_exec_last_error": (C.c_char_p, [vp]),
     "sq_exec_free": (None, [vp]),

@@ -331,6 +331,8 @@ static void begin_tile(sq_stream* s, const sq_index* idx, const uint64_t* dk, co
   s->emitted = false;
   s->spec_valid = false;
   s->d_spec_left = s->d_spec_right = nullptr;
+  s->win_set = false;
+  s->win_off = s->win_n = 0;
 }
 
 static int32_t empty_tile(sq_stream* s, uint64_t* n_pairs_out) {
@@ -502,6 +504,10 @@ SQ_API int32_t sq_probe_join(sq_stream* s, const sq_index* idx, const uint64_t* 
 }
 
 // ---- gather -----------------------------------------------------------------------------------
+// Bounded output: gathers and fetches see the window [win_off, win_off + win_n) of the emitted pairs
+// (the whole tile unless sq_stream_set_window narrowed it).
+static inline uint64_t win_pairs(const sq_stream* s) { return s->win_set ? s->win_n : s->n_pairs; }
+
 static int32_t gather_source(sq_stream* s, int32_t side, int32_t build_col_id, uint32_t* width,
                              const void** d_values, const uint32_t** d_idx) {
   if (!s->emitted) return fail(s->err, SQ_ESTATE, "sq_gather_column called without a preceding emit");
@@ -512,10 +518,10 @@ static int32_t gather_source(sq_stream* s, int32_t side, int32_t build_col_id, u
       return fail(s->err, SQ_EINVAL, "unknown build column id %d", build_col_id);
     *width = idx->columns[build_col_id].width;
     *d_values = idx->columns[build_col_id].d_values;
-    *d_idx = s->d_last_left;
+    *d_idx = s->d_last_left ? s->d_last_left + s->win_off : nullptr;
   } else if (side == 1) {
-    if (!s->d_last_right && s->n_pairs) return fail(s->err, SQ_ESTATE, "right indices were not emitted on the device");
-    *d_idx = s->d_last_right;
+    if (!s->d_last_right && win_pairs(s)) return fail(s->err, SQ_ESTATE, "right indices were not emitted on the device");
+    *d_idx = s->d_last_right ? s->d_last_right + s->win_off : nullptr;
   } else {
     return fail(s->err, SQ_EINVAL, "side must be 0 (build) or 1 (probe)");
   }
@@ -529,11 +535,11 @@ SQ_API int32_t sq_gather_column_device(sq_stream* s, int32_t side, int32_t build
   const uint32_t* ix = nullptr;
   int rc = gather_source(s, side, build_col_id, &width, &src, &ix);
   if (rc) return rc;
-  if (capacity < s->n_pairs) return fail(s->err, SQ_ECAPACITY, "gather capacity %llu < %llu", (unsigned long long)capacity,
-                                         (unsigned long long)s->n_pairs);
+  if (capacity < win_pairs(s)) return fail(s->err, SQ_ECAPACITY, "gather capacity %llu < %llu", (unsigned long long)capacity,
+                                         (unsigned long long)win_pairs(s));
   SQ_CUDA(s->err, cudaSetDevice(s->ctx->device));
   mark(s, 6);
-  rc = launch_gather(s, src, ix, s->n_pairs, width, d_out);
+  rc = launch_gather(s, src, ix, win_pairs(s), width, d_out);
   mark(s, 7);
   if (rc == SQ_OK && s->profiling) {  // one gather per column: fold each (costs a sync; profiling only)
     SQ_CUDA(s->err, cudaStreamSynchronize(s->stream));
@@ -552,12 +558,12 @@ SQ_API int32_t sq_gather_column(sq_stream* s, int32_t side, int32_t build_col_id
   int rc = gather_source(s, side, build_col_id, &width, &src, &ix);
   if (rc) return rc;
   if (width != 4 && width != 8 && width != 16) return fail(E, SQ_EINVAL, "gather: unsupported value width %u", width);
-  if (capacity < s->n_pairs) return fail(E, SQ_ECAPACITY, "gather capacity %llu < %llu", (unsigned long long)capacity,
-                                         (unsigned long long)s->n_pairs);
-  if (s->n_pairs == 0) return SQ_OK;
+  if (capacity < win_pairs(s)) return fail(E, SQ_ECAPACITY, "gather capacity %llu < %llu", (unsigned long long)capacity,
+                                         (unsigned long long)win_pairs(s));
+  if (win_pairs(s) == 0) return SQ_OK;
   if (!out) return fail(E, SQ_EINVAL, "null gather output");
   SQ_CUDA(E, cudaSetDevice(s->ctx->device));
-  const size_t out_bytes = size_t(s->n_pairs) * width;
+  const size_t out_bytes = size_t(win_pairs(s)) * width;
   const size_t in_bytes = side == 1 ? size_t(s->n_rows) * width : 0;
   if ((rc = ensure(E, s->d_gather, out_bytes + in_bytes + 32, false))) return rc;
   char* d_out = static_cast<char*>(s->d_gather.p);
@@ -568,7 +574,7 @@ SQ_API int32_t sq_gather_column(sq_stream* s, int32_t side, int32_t build_col_id
     src = d_src;
   }
   mark(s, 6);
-  if ((rc = launch_gather(s, src, ix, s->n_pairs, width, d_out))) return rc;
+  if ((rc = launch_gather(s, src, ix, win_pairs(s), width, d_out))) return rc;
   mark(s, 7);
   SQ_CUDA(E, cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s->stream));
   SQ_CUDA(E, cudaStreamSynchronize(s->stream));
@@ -676,10 +682,10 @@ SQ_API int32_t sq_index_set_validity(sq_index* idx, int32_t col_id, const uint8_
 
 static int32_t pick_indices(sq_stream* s, int32_t side, const uint32_t** ix) {
   if (!s->emitted) return fail(s->err, SQ_ESTATE, "gather called without a preceding emit");
-  if (side == 0) *ix = s->d_last_left;
+  if (side == 0) *ix = s->d_last_left ? s->d_last_left + s->win_off : nullptr;
   else if (side == 1) {
-    if (!s->d_last_right && s->n_pairs) return fail(s->err, SQ_ESTATE, "right indices were not emitted on the device");
-    *ix = s->d_last_right;
+    if (!s->d_last_right && win_pairs(s)) return fail(s->err, SQ_ESTATE, "right indices were not emitted on the device");
+    *ix = s->d_last_right ? s->d_last_right + s->win_off : nullptr;
   } else return fail(s->err, SQ_EINVAL, "side must be 0 (build) or 1 (probe)");
   return SQ_OK;
 }
@@ -713,7 +719,7 @@ SQ_API int32_t sq_gather_utf8(sq_stream* s, int32_t side, int32_t build_col_id, 
     d_off = reinterpret_cast<const int64_t*>(p);
     d_data = reinterpret_cast<const uint8_t*>(p + off_bytes);
   }
-  const uint64_t np = s->n_pairs;
+  const uint64_t np = win_pairs(s);
   if ((rc = ensure(E, s->d_gather, (np + 1) * 12 + 32, false))) return rc;
   auto* d_out_off = static_cast<int64_t*>(s->d_gather.p);
   uint64_t total = 0;
@@ -749,7 +755,7 @@ SQ_API int32_t sq_gather_utf8_data(sq_stream* s, uint8_t* out_data, uint64_t cap
   int rc;
   if ((rc = ensure(E, s->d_strdata, s->str_total, false))) return rc;
   auto* d_out = static_cast<uint8_t*>(s->d_strdata.p);
-  if ((rc = launch_str_copy(s, s->str_src_off, s->str_src_data, s->str_idx, s->n_pairs, s->str_out_off, d_out))) return rc;
+  if ((rc = launch_str_copy(s, s->str_src_off, s->str_src_data, s->str_idx, win_pairs(s), s->str_out_off, d_out))) return rc;
   SQ_CUDA(E, cudaMemcpyAsync(out_data, d_out, s->str_total, cudaMemcpyDeviceToHost, s->stream));
   SQ_CUDA(E, cudaStreamSynchronize(s->stream));
   return SQ_OK;
@@ -763,7 +769,7 @@ SQ_API int32_t sq_gather_validity(sq_stream* s, int32_t side, int32_t build_col_
   int rc = pick_indices(s, side, &ix);
   if (rc) return rc;
   SQ_CUDA(E, cudaSetDevice(s->ctx->device));
-  const uint64_t np = s->n_pairs;
+  const uint64_t np = win_pairs(s);
   const size_t out_bytes = (np + 7) / 8;
   const size_t in_bytes = side == 1 ? (size_t(s->n_rows) + 7) / 8 : 0;
   if ((rc = ensure(E, s->d_gather, out_bytes + in_bytes + 64, false))) return rc;
@@ -787,6 +793,53 @@ SQ_API int32_t sq_gather_validity(sq_stream* s, int32_t side, int32_t build_col_
     SQ_CUDA(E, cudaMemcpyAsync(out_bitmap, d_out, out_bytes, cudaMemcpyDeviceToHost, s->stream));
     SQ_CUDA(E, cudaStreamSynchronize(s->stream));
   }
+  return SQ_OK;
+}
+
+
+// ---- bounded output (GPU analogue of interval_join_low_memory, IJ:1433-1530) -----------------------
+SQ_API int32_t sq_stream_set_window(sq_stream* s, uint64_t pair_offset, uint64_t n_pairs) {
+  if (!s) return SQ_EINVAL;
+  if (!s->emitted) return fail(s->err, SQ_ESTATE, "sq_stream_set_window called without a preceding emit");
+  if (pair_offset > s->n_pairs || n_pairs > s->n_pairs - pair_offset)
+    return fail(s->err, SQ_EINVAL, "window [%llu, +%llu) exceeds the tile's %llu pairs", (unsigned long long)pair_offset,
+                (unsigned long long)n_pairs, (unsigned long long)s->n_pairs);
+  s->win_set = true;
+  s->win_off = pair_offset;
+  s->win_n = n_pairs;
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_fetch_pairs(sq_stream* s, uint32_t* left_idx_out, uint32_t* right_idx_out, uint64_t capacity) {
+  if (!s) return SQ_EINVAL;
+  ErrorSlot& E = s->err;
+  if (!s->emitted) return fail(E, SQ_ESTATE, "sq_fetch_pairs called without a preceding emit");
+  const uint64_t n = win_pairs(s);
+  if (capacity < n) return fail(E, SQ_ECAPACITY, "output capacity %llu < %llu pairs", (unsigned long long)capacity,
+                                (unsigned long long)n);
+  if (n == 0) return SQ_OK;
+  SQ_CUDA(E, cudaSetDevice(s->ctx->device));
+  if (left_idx_out) {
+    if (!s->d_last_left) return fail(E, SQ_ESTATE, "left indices are not on the device");
+    SQ_CUDA(E, cudaMemcpyAsync(left_idx_out, s->d_last_left + s->win_off, n * 4, cudaMemcpyDeviceToHost, s->stream));
+  }
+  if (right_idx_out) {
+    if (!s->d_last_right) return fail(E, SQ_ESTATE, "right indices are not on the device");
+    SQ_CUDA(E, cudaMemcpyAsync(right_idx_out, s->d_last_right + s->win_off, n * 4, cudaMemcpyDeviceToHost, s->stream));
+  }
+  SQ_CUDA(E, cudaStreamSynchronize(s->stream));
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_stream_counts(sq_stream* s, uint32_t* counts_out) {
+  if (!s) return SQ_EINVAL;
+  ErrorSlot& E = s->err;
+  if (!s->counted) return fail(E, SQ_ESTATE, "sq_stream_counts called without a counted tile");
+  if (s->n_rows == 0) return SQ_OK;
+  if (!counts_out) return fail(E, SQ_EINVAL, "null counts_out");
+  SQ_CUDA(E, cudaSetDevice(s->ctx->device));
+  SQ_CUDA(E, cudaMemcpyAsync(counts_out, s->d_cnt.p, size_t(s->n_rows) * 4, cudaMemcpyDeviceToHost, s->stream));
+  SQ_CUDA(E, cudaStreamSynchronize(s->stream));
   return SQ_OK;
 }
 

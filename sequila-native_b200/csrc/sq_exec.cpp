@@ -5,6 +5,7 @@
 // the GPU.
 #include "sequila_exec.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -99,6 +100,14 @@ void release_schema(ArrowSchema* s) {
 
 }  // namespace
 
+// per-partition state of a probe batch that is being emitted in windows (low-memory mode)
+struct PartState {
+  const ArrowArray* batch = nullptr;
+  uint64_t n = 0;
+  std::vector<std::pair<uint64_t, uint64_t>> windows;  // (pair offset, pair count), cut at probe-row boundaries
+  size_t next = 0;
+};
+
 struct sq_exec {
   sq_exec_config cfg{};
   std::vector<int32_t> on_left, on_right, projection;
@@ -109,6 +118,7 @@ struct sq_exec {
   std::vector<int32_t> build_col_id;      // left column -> sq_index column id (or -1 when not projected)
   std::mutex mu;
   std::map<int32_t, sq_stream*> streams;
+  std::map<int32_t, PartState> parts;
   std::string err;
   uint64_t m[16] = {};
   bool built = false;
@@ -431,26 +441,21 @@ SQ_API int32_t sq_exec_output_schema(const sq_exec* e, ArrowSchema* out) {
   return SQ_OK;
 }
 
-SQ_API int32_t sq_exec_probe(sq_exec* e, int32_t partition, const ArrowArray* batch, ArrowArray* out) {
-  if (!e || !batch || !out) return SQ_EINVAL;
-  if (!e->built) return e->fail(SQ_ESTATE, "Expected build side in ready state");  // IJ:1425
-  if (batch->n_children != int64_t(e->right.cols.size())) return e->fail(SQ_EINVAL, "probe batch has %lld columns, schema has %zu",
-                                                                          (long long)batch->n_children, e->right.cols.size());
-  const auto t0 = Clock::now();
-  sq_stream* st = nullptr;
-  int rc = stream_for(e, partition, &st);
-  if (rc) return rc;
+namespace {
+
+// hashes the keys, casts the interval columns and runs the probe of one batch on the GPU; the result stays
+// on the device.  *n_out = output rows of the whole batch.
+int probe_on_device(sq_exec* e, sq_stream* st, const ArrowArray* batch, uint64_t* n_out) {
   const uint64_t n = uint64_t(batch->length);
   if (n > 0xFFFFFFFFull) return e->fail(SQ_EINVAL, "probe batch too large");
   std::vector<uint64_t> keys;
   std::vector<int32_t> start, end;
+  int rc;
   if ((rc = hash_keys(e, e->right, e->on_right, batch, &keys))) return rc;
   if ((rc = eval_i32(e, st, e->right, e->cfg.right_start, false, batch, &start))) return rc;
   if ((rc = eval_i32(e, st, e->right, e->cfg.right_end, e->cfg.right_end_minus_one != 0, batch, &end))) return rc;
-
   uint64_t n_pairs = 0;
-  const bool nearest = e->cfg.algorithm == SQ_EXEC_NEAREST;
-  if (nearest) {  // one output row per probe row; the left side may be NULL (IJ:1593-1602)
+  if (e->cfg.algorithm == SQ_EXEC_NEAREST) {  // one output row per probe row; the left side may be NULL (IJ:1593-1602)
     rc = sq_probe_nearest(st, e->index, keys.data(), start.data(), end.data(), uint32_t(n), nullptr);
     if (rc != SQ_OK) return e->fail(rc, "%s", sq_stream_last_error(st));
     n_pairs = n;
@@ -461,7 +466,15 @@ SQ_API int32_t sq_exec_probe(sq_exec* e, int32_t partition, const ArrowArray* ba
     rc = sq_probe_emit_pairs(st, nullptr, nullptr, nullptr, n_pairs);
     if (rc != SQ_OK) return e->fail(rc, "%s", sq_stream_last_error(st));
   }
+  *n_out = n_pairs;
+  return SQ_OK;
+}
 
+// one output RecordBatch = `take` of every projected column over the stream's current pair window
+int assemble_output(sq_exec* e, sq_stream* st, const ArrowArray* batch, uint64_t n_pairs, ArrowArray* out) {
+  const uint64_t n = uint64_t(batch->length);
+  const bool nearest = e->cfg.algorithm == SQ_EXEC_NEAREST;
+  int rc;
   // `out` is assembled in place; on any failure below everything attached so far is released
   auto* own = new Owned();
   own->ctx = e->ctx;
@@ -592,14 +605,96 @@ SQ_API int32_t sq_exec_probe(sq_exec* e, int32_t partition, const ArrowArray* ba
   out->children = own->child_ptrs.data();
   out->dictionary = nullptr;
   unwind.armed = false;
+  return SQ_OK;
+}
+
+}  // namespace
+
+SQ_API int32_t sq_exec_probe(sq_exec* e, int32_t partition, const ArrowArray* batch, ArrowArray* out) {
+  if (!e || !batch || !out) return SQ_EINVAL;
+  if (!e->built) return e->fail(SQ_ESTATE, "Expected build side in ready state");  // IJ:1425
+  if (batch->n_children != int64_t(e->right.cols.size())) return e->fail(SQ_EINVAL, "probe batch has %lld columns, schema has %zu",
+                                                                          (long long)batch->n_children, e->right.cols.size());
+  const auto t0 = Clock::now();
+  sq_stream* st = nullptr;
+  int rc = stream_for(e, partition, &st);
+  if (rc) return rc;
+  uint64_t n_pairs = 0;
+  if ((rc = probe_on_device(e, st, batch, &n_pairs))) return rc;
+  if ((rc = assemble_output(e, st, batch, n_pairs, out))) return rc;
+  std::lock_guard<std::mutex> g(e->mu);
+  e->m[3] += 1;
+  e->m[4] += uint64_t(batch->length);
+  e->m[5] += 1;
+  e->m[6] += n_pairs;
+  e->m[8] += uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - t0).count());
+  return SQ_OK;
+}
+
+// Low-memory mode (IJ:1433-1530): the probe batch is processed once on the GPU, then handed back as output
+// batches of at most cfg.max_output_rows rows, cut at probe-row boundaries; a single probe row with more
+// matches than the cap forms a batch of its own (IJ:1467-1471: `&& total_output_rows > 0`).
+SQ_API int32_t sq_exec_probe_begin(sq_exec* e, int32_t partition, const ArrowArray* batch) {
+  if (!e || !batch) return SQ_EINVAL;
+  if (!e->built) return e->fail(SQ_ESTATE, "Expected build side in ready state");
+  if (batch->n_children != int64_t(e->right.cols.size())) return e->fail(SQ_EINVAL, "probe batch has %lld columns, schema has %zu",
+                                                                          (long long)batch->n_children, e->right.cols.size());
+  const auto t0 = Clock::now();
+  sq_stream* st = nullptr;
+  int rc = stream_for(e, partition, &st);
+  if (rc) return rc;
+  uint64_t n_pairs = 0;
+  if ((rc = probe_on_device(e, st, batch, &n_pairs))) return rc;
+  PartState ps;
+  ps.batch = batch;
+  ps.n = uint64_t(batch->length);
+  const uint64_t cap = e->cfg.max_output_rows > 0 ? uint64_t(e->cfg.max_output_rows) : 1000000ull;  // IJ:1439
+  if (e->cfg.algorithm == SQ_EXEC_NEAREST) {
+    for (uint64_t o = 0; o < n_pairs; o += cap) ps.windows.emplace_back(o, std::min(cap, n_pairs - o));
+  } else {
+    std::vector<uint32_t> counts(ps.n);
+    if (ps.n && (rc = sq_stream_counts(st, counts.data())) != SQ_OK) return e->fail(rc, "%s", sq_stream_last_error(st));
+    uint64_t off = 0, cur = 0;
+    for (uint64_t i = 0; i < ps.n; ++i) {
+      if (cur + counts[i] > cap && cur > 0) { ps.windows.emplace_back(off, cur); off += cur; cur = 0; }
+      cur += counts[i];
+    }
+    ps.windows.emplace_back(off, cur);  // the last (possibly empty) batch, as in the reference
+  }
+  if (ps.windows.empty()) ps.windows.emplace_back(0, 0);
+  std::lock_guard<std::mutex> g(e->mu);
+  e->parts[partition] = std::move(ps);
+  e->m[3] += 1;
+  e->m[4] += uint64_t(batch->length);
+  e->m[8] += uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - t0).count());
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_exec_probe_next(sq_exec* e, int32_t partition, ArrowArray* out, int32_t* has_more_out) {
+  if (!e || !out || !has_more_out) return SQ_EINVAL;
+  const auto t0 = Clock::now();
+  PartState* ps = nullptr;
   {
     std::lock_guard<std::mutex> g(e->mu);
-    e->m[3] += 1;
-    e->m[4] += n;
-    e->m[5] += 1;
-    e->m[6] += n_pairs;
-    e->m[8] += uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - t0).count());
+    auto it = e->parts.find(partition);
+    if (it == e->parts.end() || it->second.next >= it->second.windows.size()) {
+      e->err = "sq_exec_probe_next without a pending sq_exec_probe_begin";
+      return SQ_ESTATE;
+    }
+    ps = &it->second;
   }
+  sq_stream* st = nullptr;
+  int rc = stream_for(e, partition, &st);
+  if (rc) return rc;
+  const auto w = ps->windows[ps->next];
+  if ((rc = sq_stream_set_window(st, w.first, w.second)) != SQ_OK) return e->fail(rc, "%s", sq_stream_last_error(st));
+  if ((rc = assemble_output(e, st, ps->batch, w.second, out))) return rc;
+  ps->next += 1;
+  *has_more_out = ps->next < ps->windows.size() ? 1 : 0;
+  std::lock_guard<std::mutex> g(e->mu);
+  e->m[5] += 1;
+  e->m[6] += w.second;
+  e->m[8] += uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - t0).count());
   return SQ_OK;
 }
 

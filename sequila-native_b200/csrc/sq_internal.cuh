@@ -171,6 +171,8 @@ struct sq_stream {
   uint32_t* d_spec_right = nullptr;
   const uint32_t* d_last_left = nullptr;
   const uint32_t* d_last_right = nullptr;
+  bool win_set = false;                // sq_stream_set_window: gathers / fetches see pairs [win_off, win_off + win_n)
+  uint64_t win_off = 0, win_n = 0;
 
   // device scratch
   sq_buf d_in;       // staged probe key/start/end (host entry points)

@@ -190,6 +190,21 @@ class CudaStream:
         _check(rc, self._err)
         return self.n_pairs
 
+    # ---- bounded output (low-memory protocol) -------------------------------------------------
+    def counts(self) -> np.ndarray:
+        out = np.empty(self.n_rows, dtype=np.uint32)
+        _check(self._lib.sq_stream_counts(self._h, _ptr(out)), self._err)
+        return out
+
+    def set_window(self, pair_offset: int, n_pairs: int):
+        _check(self._lib.sq_stream_set_window(self._h, int(pair_offset), int(n_pairs)), self._err)
+        self._win = int(n_pairs)
+
+    def fetch_pairs(self, n: int):
+        left, right = np.empty(n, dtype=np.uint32), np.empty(n, dtype=np.uint32)
+        _check(self._lib.sq_fetch_pairs(self._h, _ptr(left), _ptr(right), n), self._err)
+        return left, right
+
     def probe_nearest(self, index: CudaIndex, key_hash, start, end) -> np.ndarray:
         """sq_probe_nearest: one build row (or N.NULL_INDEX) per probe row."""
         k, s, e = _np(key_hash, np.uint64), _np(start, np.int32), _np(end, np.int32)

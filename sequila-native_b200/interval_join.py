@@ -145,6 +145,9 @@ class IntervalJoinExec:
         self.null_equals_null = null_equals_null
         self.algorithm = algorithm
         self.low_memory = low_memory
+        # the reference caps a low-memory output batch at 1M rows (interval_join.rs:1439)
+        import os
+        self.max_output_rows = int(os.environ.get("SEQUILA_MAX_OUTPUT_ROWS", "1000000"))
         self.device = device
         self._exec = None
         self._lib = None
@@ -205,7 +208,8 @@ class IntervalJoinExec:
         proj = self.projection
         parr = (C.c_int32 * max(len(proj) if proj is not None else 1, 1))(*(proj or []))
         cfg = N.SqExecConfig(self.device, n_on, onl, onr, ls, le, rs, re_, int(lem), int(rem),
-                             -1 if proj is None else len(proj), parr, 1 if self.algorithm == Algorithm.CudaNearest else 0)
+                             -1 if proj is None else len(proj), parr, 1 if self.algorithm == Algorithm.CudaNearest else 0,
+                             int(self.low_memory), int(self.max_output_rows))
         lsch, rsch = _ArrowSchema(), _ArrowSchema()
         self.left_schema._export_to_c(C.addressof(lsch))
         self.right_schema._export_to_c(C.addressof(rsch))
@@ -263,11 +267,34 @@ class IntervalJoinExec:
             raise ExecutionError(self._err())
         return pa.RecordBatch._import_from_c(C.addressof(out), self.schema())
 
+    def probe_batch_low_memory(self, batch, partition: int = 0) -> Iterator:
+        """process_probe_batch, low-memory mode (IJ:1433-1530): output batches of at most
+        `max_output_rows` rows, cut at probe-row boundaries."""
+        import pyarrow as pa
+        lib = self._lib
+        arr = _ArrowArray()
+        batch._export_to_c(C.addressof(arr))
+        try:
+            if lib.sq_exec_probe_begin(self._exec, partition, C.addressof(arr)) != N.SQ_OK:
+                raise ExecutionError(self._err())
+            more = C.c_int32(1)
+            while more.value:
+                out = _ArrowArray()
+                if lib.sq_exec_probe_next(self._exec, partition, C.addressof(out), C.byref(more)) != N.SQ_OK:
+                    raise ExecutionError(self._err())
+                yield pa.RecordBatch._import_from_c(C.addressof(out), self.schema())
+        finally:
+            if arr.release:
+                _RELEASE_ARRAY(arr.release)(C.addressof(arr))
+
     def execute(self, build_batches: Iterable, probe_batches: Iterable, partition: int = 0) -> Iterator:
         """IJ:449-557: await the build side, then stream the probe side."""
         self.collect_build(build_batches)
         for b in probe_batches:
-            yield self.probe_batch(b, partition)
+            if self.low_memory:
+                yield from self.probe_batch_low_memory(b, partition)
+            else:
+                yield self.probe_batch(b, partition)
 
     def metrics(self) -> JoinMetrics:
         out = (C.c_uint64 * 16)()

@@ -137,3 +137,29 @@ def test_empty_sides():
     assert out[0].num_rows == 0 and out[0].schema.names == COLS + COLS
     _, out = run_join(one, empty, Q1)
     assert out[0].num_rows == 0
+
+
+def test_partitioned_mode_one_exec_per_partition(oracle):
+    """PartitionMode::Partitioned (interval_join.rs:488-503): both sides hash-partitioned on the key, every
+    partition builds its own index and probes only its rows; the union is the whole join."""
+    from sequila_native_b200 import sharding
+    from sequila_native_b200.interval_join import PARTITIONED
+    rng = np.random.default_rng(21)
+    nb, npq, nk = 4000, 3000, 6
+    names = np.array([f"chr{i}" for i in range(nk)])
+    bc, pc = rng.integers(0, nk, nb), rng.integers(0, nk, npq)
+    bs = rng.integers(0, 30000, nb).astype(np.int32); be = (bs + rng.integers(0, 200, nb)).astype(np.int32)
+    ps = rng.integers(0, 30000, npq).astype(np.int32); pe = (ps + rng.integers(0, 200, npq)).astype(np.int32)
+    plan_keys = sharding.assign_keys_lpt(np.bincount(bc, minlength=nk), 2)
+    got = []
+    for part, (brows, prows) in enumerate(zip(sharding.route_rows(bc, plan_keys), sharding.route_rows(pc, plan_keys))):
+        left = pa.record_batch([pa.array(names[bc[brows]]), pa.array(bs[brows]), pa.array(be[brows])], names=COLS)
+        right = pa.record_batch([pa.array(names[pc[prows]]), pa.array(ps[prows]), pa.array(pe[prows])], names=COLS)
+        f = IV.parse_condition_sql(Q1, "a", COLS, "b", COLS)
+        plan = optimize(HashJoinDesc(left.schema, right.schema, [("contig", "contig")], f, partition_mode=PARTITIONED), cuda_config())
+        assert "mode=Partitioned" in plan.display()
+        for b in plan.execute([left], [right], partition=part):
+            got += [tuple(r) for r in zip(*[c.to_pylist() for c in b.columns])]
+    ol, orr, _ = oracle.join(bc.astype(np.uint64), bs, be, pc.astype(np.uint64), ps, pe)
+    want = sorted(zip(names[bc][ol].tolist(), bs[ol].tolist(), be[ol].tolist(), names[pc][orr].tolist(), ps[orr].tolist(), pe[orr].tolist()))
+    assert sorted(got) == want

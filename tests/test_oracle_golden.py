@@ -160,3 +160,17 @@ def test_nearest_differential_vs_python_restatement(oracle):
                     if d < best_d:
                         best, best_d = j, d
             assert int(left[i]) == best
+
+
+def test_lapper_conversion_gives_the_same_multiset_for_non_negative_coordinates(oracle):
+    """The reference's Lapper arm stores `start as u32 .. end as u32 + 1` and queries
+    `find(start as u32, end as u32 + 1)` (interval_join.rs:711-717, 1005-1011; rust-lapper's find is
+    half-open: iv.start < stop && iv.stop > start).  For coordinates >= 0 that is the closed predicate."""
+    rng = np.random.default_rng(9)
+    nb, npq = 700, 500
+    bs = rng.integers(0, 5000, nb).astype(np.int64); be = bs + rng.integers(0, 60, nb)
+    ps = rng.integers(0, 5000, npq).astype(np.int64); pe = ps + rng.integers(0, 60, npq)
+    k = np.zeros(nb, np.uint64); kq = np.zeros(npq, np.uint64)
+    lap = [(b, q) for q in range(npq) for b in range(nb) if bs[b] < pe[q] + 1 and be[b] + 1 > ps[q]]
+    ol, orr, _ = oracle.join(k, bs, be, kq, ps, pe)
+    assert sorted(lap) == sorted(zip(ol.tolist(), orr.tolist()))
