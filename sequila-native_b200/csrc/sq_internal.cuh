@@ -248,6 +248,7 @@ int launch_packed(sq_stream* s, const sq_index* idx, const uint64_t* d_key, cons
                   const int32_t* d_end, uint32_t n, uint32_t* d_left, uint32_t* d_right, uint64_t capacity);
 bool use_packed(const sq_index* idx);
 
+
 // gather.cu
 int launch_gather(sq_stream* s, const void* d_values, const uint32_t* d_idx, uint64_t n, uint32_t width,
                   void* d_out);

@@ -1,0 +1,200 @@
+// Device pieces shared by the probe kernels over the packed lines (sq_probe_packed.cu: one tile per CTA;
+// sq_probe_pipe.cu: persistent CTAs with software-pipelined loads): decoding a line, the register-path
+// walk in compacted rounds, the chained scan across tiles and the ordered emit of a warp's rows.
+#pragma once
+#include "sq_internal.cuh"
+#include "sq_probe_common.cuh"
+
+namespace sq {
+
+constexpr uint32_t kSlots = 32;          // stash slots per probe row
+constexpr uint32_t kStride = kSlots + 1; // padded row stride of the stash (bank spread)
+
+// the two row slots this lane holds of a line: lane 0 = {header, row 0}, lanes 1..7 = {row 2k-1, row 2k}
+struct Slots {
+  uint32_t a_lo, a_id, b_lo, b_id;
+};
+__device__ __forceinline__ Slots slots_of(const uint4& d, int sub) {
+  Slots s;
+  s.a_lo = sub ? d.x : d.z;
+  s.a_id = sub ? d.y : d.w;
+  s.b_lo = d.z;
+  s.b_id = sub ? d.w : kEmptyRow;
+  return s;
+}
+__device__ __forceinline__ bool row_hits(uint32_t lo_word, uint32_t id, int32_t base, int32_t qs, int32_t qe) {
+  const int32_t st = base + int32_t(lo_word & 0xFFFFu);
+  const int32_t en = st + int32_t(lo_word >> 16);
+  return id != kEmptyRow && st <= qe && en >= qs;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Walk in rounds (register path).  Lane L owns probe row L of the warp: `walking` = the row still has a
+// line to visit, `ln` = that line, `cnt` = its hits so far.  Every round the walking rows are compacted
+// (rank among walking rows -> step, group), each fetches ONE line with a cooperative 8-lane load, all
+// steps of the warp at once (8 independent requests per lane in flight): a warp waits for as many memory
+// round trips as its longest walk and executes only as many steps as it has (row, line) pairs.
+// inv8: 32 bytes of shared memory of this warp, 8-byte aligned.  stash: kStride words per row.
+// ---------------------------------------------------------------------------------------------
+template <bool EMIT>
+__device__ __forceinline__ void walk_rounds(const IndexView& iv, uint32_t* stash, uint8_t* inv8, int32_t my_qs,
+                                            int32_t my_qe, uint32_t first, bool& walking, uint32_t& ln, uint32_t& cnt) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 3, sub = lane & 7, g0 = g * 8;
+  for (;;) {
+    const unsigned A = __ballot_sync(0xffffffffu, walking);
+    if (A == 0) break;
+    const int n_walk = __popc(A);
+    const int r = __popc(A & ((1u << lane) - 1u));  // my rank: served in step r >> 2 by group r & 3
+    __syncwarp();
+    if (walking) inv8[(r & 3) * 8 + (r >> 2)] = uint8_t(lane);
+    __syncwarp();
+    const unsigned long long srcs = *reinterpret_cast<const unsigned long long*>(inv8 + g0);  // my group's 8 rows
+    const int n_steps = (n_walk + 3) >> 2;
+    uint4 v[8];
+#pragma unroll
+    for (int st = 0; st < 8; ++st) {
+      const int p = int(srcs >> (8 * st)) & 31;
+      const uint32_t lnp = __shfl_sync(0xffffffffu, ln, p);
+      v[st] = (4 * st + g < n_walk) ? __ldg(iv.lines + size_t(lnp) * 8 + sub) : make_uint4(0u, 0u, 0u, kEmptyRow);
+    }
+    bool cont = false;
+#pragma unroll
+    for (int st = 0; st < 8; ++st) {
+      if (st >= n_steps) break;  // warp-uniform
+      const int p = int(srcs >> (8 * st)) & 31;
+      const bool valid = 4 * st + g < n_walk;
+      const int32_t qs = __shfl_sync(0xffffffffu, my_qs, p);
+      const int32_t qe = __shfl_sync(0xffffffffu, my_qe, p);
+      const uint32_t c0 = __shfl_sync(0xffffffffu, cnt, p);
+      const uint4 d = v[st];
+      const int32_t base = int32_t(__shfl_sync(0xffffffffu, d.x, g0));
+      const int32_t exmax = int32_t(__shfl_sync(0xffffffffu, d.y, g0));
+      const Slots s = slots_of(d, sub);
+      const bool ha = valid && row_hits(s.a_lo, s.a_id, base, qs, qe);
+      const bool hb = valid && row_hits(s.b_lo, s.b_id, base, qs, qe);
+      const uint32_t ma = (__ballot_sync(0xffffffffu, ha) >> g0) & 0xFFu;
+      const uint32_t mb = (__ballot_sync(0xffffffffu, hb) >> g0) & 0xFFu;
+      if (EMIT) {
+        const uint32_t below = (1u << sub) - 1u;
+        const uint32_t pa = c0 + __popc(ma & below);
+        const uint32_t pb = c0 + __popc(ma) + __popc(mb & below);
+        if (ha && pa < kSlots) stash[p * kStride + pa] = s.a_id;
+        if (hb && pb < kSlots) stash[p * kStride + pb] = s.b_id;
+      }
+      // hand the new count and "an earlier row still reaches qs" back to the owner lane
+      const uint32_t c1 = __shfl_sync(0xffffffffu, c0 + __popc(ma) + __popc(mb), (r & 3) * 8);
+      const unsigned reach = __ballot_sync(0xffffffffu, valid && exmax >= qs);
+      if (walking && (r >> 2) == st) {
+        cnt = c1;
+        cont = (reach >> ((r & 3) * 8)) & 1u;
+      }
+    }
+    walking = walking && cont && ln > first;
+    ln -= 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chained scan with decoupled look-back over tiles (one 64-bit word per tile: [63:62] status).  Called
+// by ONE full warp of the tile's CTA: publishes the tile's aggregate, sums its predecessors' (32 words
+// per step, stopping at the first inclusive prefix), publishes the inclusive prefix and returns the
+// exclusive one.  Predecessor tiles must already be running (ticket order / resident persistent grid).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long chain_lookback(unsigned long long* chain_state, uint32_t tile,
+                                                              unsigned long long agg) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) atomicExch(chain_state + tile, (tile == 0 ? kFlagInc : kFlagAgg) | agg);
+  unsigned long long excl = 0;
+  if (tile > 0) {
+    int64_t look = int64_t(tile) - 1;
+    for (;;) {
+      const int64_t k = look - lane;
+      unsigned long long x = kFlagInc;
+      if (k >= 0) {
+        do { x = *reinterpret_cast<volatile unsigned long long*>(chain_state + k); } while ((x >> 62) == 0);
+      }
+      const unsigned inc_mask = __ballot_sync(0xffffffffu, (x >> 62) == 2);
+      const int first_inc = inc_mask ? (__ffs(inc_mask) - 1) : 32;
+      unsigned long long y = (lane <= first_inc) ? (x & kValMask) : 0;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) y += __shfl_xor_sync(0xffffffffu, y, d);
+      excl += y;
+      if (inc_mask) break;
+      look -= 32;
+    }
+    if (lane == 0) atomicExch(chain_state + tile, kFlagInc | (excl + agg));
+  }
+  return excl;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ordered emit of one warp's 32 rows.  Row L's pairs go to lout/rout[coff_L ...] (coff = exclusive prefix
+// of the hit counts inside the warp).  Rows with <= kSlots hits are copied from the stash as ONE flattened
+// list (coalesced stores); rows with more hits are re-walked by the whole warp, four lines per step, from
+// their start line `line0`.
+// ---------------------------------------------------------------------------------------------
+template <bool WRITE_RIGHT>
+__device__ __forceinline__ void emit_rows(const IndexView& iv, const uint32_t* stash, uint8_t* inv, uint32_t cnt,
+                                          uint32_t coff, int32_t my_qs, int32_t my_qe, uint32_t line0, uint32_t first,
+                                          uint32_t* __restrict__ lout, uint32_t* __restrict__ rout, uint32_t tile_first) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 3, sub = lane & 7, g0 = g * 8;
+  {
+    const Flat f = flat_setup(cnt <= kSlots ? cnt : 0u, lane, inv);  // also orders the stash writes
+    const uint32_t r_coff = __shfl_sync(0xffffffffu, coff, f.r_src);
+    for (uint32_t t0 = 0; t0 < f.total; t0 += 32) {
+      const uint32_t t = t0 + lane;
+      const int r = flat_rank(f, t0, lane);
+      const uint32_t k = t - __shfl_sync(0xffffffffu, f.r_excl, r);
+      const uint32_t off = __shfl_sync(0xffffffffu, r_coff, r);
+      const int src = __shfl_sync(0xffffffffu, f.r_src, r);
+      if (t < f.total) {
+        const uint32_t pos = off + k;
+        lout[pos] = stash[src * kStride + k];
+        if (WRITE_RIGHT) rout[pos] = tile_first + src;
+      }
+    }
+  }
+  unsigned big = __ballot_sync(0xffffffffu, cnt > kSlots);
+  while (big) {
+    const int p = __ffs(big) - 1;
+    big &= big - 1;
+    const int32_t qs = __shfl_sync(0xffffffffu, my_qs, p);
+    const int32_t qe = __shfl_sync(0xffffffffu, my_qe, p);
+    uint32_t ln = __shfl_sync(0xffffffffu, line0, p);
+    const uint32_t fst = __shfl_sync(0xffffffffu, first, p);
+    uint32_t run = __shfl_sync(0xffffffffu, coff, p);
+    for (;;) {
+      const bool has = ln - fst >= uint32_t(g);  // group g takes line ln - g
+      const uint4 d = has ? __ldg(iv.lines + size_t(ln - g) * 8 + sub) : make_uint4(0u, uint32_t(INT32_MIN), 0u, kEmptyRow);
+      const int32_t lbase = int32_t(__shfl_sync(0xffffffffu, d.x, g0));
+      const int32_t exmax = int32_t(__shfl_sync(0xffffffffu, d.y, g0));
+      const bool more = has && exmax >= qs && (ln - g) > fst;  // this line sends the walk one line further
+      const unsigned mm = __ballot_sync(0xffffffffu, more);
+      const unsigned m4 = (mm & 1u) | ((mm >> 7) & 2u) | ((mm >> 14) & 4u) | ((mm >> 21) & 8u);
+      const bool live = has && ((m4 & ((1u << g) - 1u)) == ((1u << g) - 1u));  // every later line continued
+      const Slots s = slots_of(d, sub);
+      const bool ha = live && row_hits(s.a_lo, s.a_id, lbase, qs, qe);
+      const bool hb = live && row_hits(s.b_lo, s.b_id, lbase, qs, qe);
+      const unsigned ma = __ballot_sync(0xffffffffu, ha), mb = __ballot_sync(0xffffffffu, hb);
+      const unsigned below = (1u << lane) - 1u;
+      if (ha) {
+        const uint32_t pos = run + __popc(ma & below);
+        lout[pos] = s.a_id;
+        if (WRITE_RIGHT) rout[pos] = tile_first + p;
+      }
+      if (hb) {
+        const uint32_t pos = run + __popc(ma) + __popc(mb & below);
+        lout[pos] = s.b_id;
+        if (WRITE_RIGHT) rout[pos] = tile_first + p;
+      }
+      run += __popc(ma) + __popc(mb);
+      if (m4 != 0xFu) break;
+      ln -= 4;
+    }
+  }
+}
+
+}  // namespace sq

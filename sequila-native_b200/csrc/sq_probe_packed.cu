@@ -26,13 +26,11 @@
 #include <cstdlib>
 
 #include "sq_internal.cuh"
-#include "sq_probe_common.cuh"
+#include "sq_packed_common.cuh"
 
 namespace sq {
 
 constexpr int kPBlockDefault = 128;      // threads per CTA = probe rows per CTA
-constexpr uint32_t kSlots = 32;          // stash slots per probe row
-constexpr uint32_t kStride = kSlots + 1; // padded row stride of the stash (bank spread)
 
 struct StartLine {
   uint32_t line;   // line holding the last row whose start can be <= qe
@@ -53,24 +51,6 @@ __device__ __forceinline__ StartLine find_start_line(const IndexView& iv, uint32
   r.first = m.line_base;
   r.act = true;
   return r;
-}
-
-// the two row slots this lane holds of a line: lane 0 = {header, row 0}, lanes 1..7 = {row 2k-1, row 2k}
-struct Slots {
-  uint32_t a_lo, a_id, b_lo, b_id;
-};
-__device__ __forceinline__ Slots slots_of(const uint4& d, int sub) {
-  Slots s;
-  s.a_lo = sub ? d.x : d.z;
-  s.a_id = sub ? d.y : d.w;
-  s.b_lo = d.z;
-  s.b_id = sub ? d.w : kEmptyRow;
-  return s;
-}
-__device__ __forceinline__ bool row_hits(uint32_t lo_word, uint32_t id, int32_t base, int32_t qs, int32_t qe) {
-  const int32_t st = base + int32_t(lo_word & 0xFFFFu);
-  const int32_t en = st + int32_t(lo_word >> 16);
-  return id != kEmptyRow && st <= qe && en >= qs;
 }
 
 template <bool EMIT, bool WRITE_RIGHT, int kPBlock>
@@ -109,66 +89,12 @@ k_probe_packed(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* 
     sl = find_start_line(iv, id, my_qe);
   }
 
-  // ---- phase 2: 4 probe rows per step, 8 lanes each; rounds of up to 8 independent line requests -----
-  // Every round, the rows that still walk back are compacted (rank among walking rows -> step, group),
-  // each fetches ONE more line, all steps of the warp at once: a warp waits for as many memory round
-  // trips as its longest walk and executes only as many steps as it has (row, line) pairs.
+  // ---- phase 2: walk in compacted rounds (sq_packed_common.cuh) -----------------------------------
   uint32_t* stash = s_stash + (EMIT ? warp * 32 * kStride : 0);
   bool walking = sl.act;
   uint32_t ln = sl.line;  // next line of my row
   uint32_t cnt = 0;       // hits of my row so far
-  for (;;) {
-    const unsigned A = __ballot_sync(0xffffffffu, walking);
-    if (A == 0) break;
-    const int n_walk = __popc(A);
-    const int r = __popc(A & ((1u << lane) - 1u));  // my rank: served in step r >> 2 by group r & 3
-    __syncwarp();
-    if (walking) s_inv[warp][(r & 3) * 8 + (r >> 2)] = uint8_t(lane);
-    __syncwarp();
-    const unsigned long long srcs = *reinterpret_cast<const unsigned long long*>(&s_inv[warp][g0]);  // my group's 8 rows
-    const int n_steps = (n_walk + 3) >> 2;
-    uint4 v[8];
-#pragma unroll
-    for (int st = 0; st < 8; ++st) {
-      const int p = int(srcs >> (8 * st)) & 31;
-      const uint32_t lnp = __shfl_sync(0xffffffffu, ln, p);
-      v[st] = (4 * st + g < n_walk) ? __ldg(iv.lines + size_t(lnp) * 8 + sub) : make_uint4(0u, 0u, 0u, kEmptyRow);
-    }
-    bool cont = false;
-#pragma unroll
-    for (int st = 0; st < 8; ++st) {
-      if (st >= n_steps) break;  // warp-uniform
-      const int p = int(srcs >> (8 * st)) & 31;
-      const bool valid = 4 * st + g < n_walk;
-      const int32_t qs = __shfl_sync(0xffffffffu, my_qs, p);
-      const int32_t qe = __shfl_sync(0xffffffffu, my_qe, p);
-      const uint32_t c0 = __shfl_sync(0xffffffffu, cnt, p);
-      const uint4 d = v[st];
-      const int32_t base = int32_t(__shfl_sync(0xffffffffu, d.x, g0));
-      const int32_t exmax = int32_t(__shfl_sync(0xffffffffu, d.y, g0));
-      const Slots s = slots_of(d, sub);
-      const bool ha = valid && row_hits(s.a_lo, s.a_id, base, qs, qe);
-      const bool hb = valid && row_hits(s.b_lo, s.b_id, base, qs, qe);
-      const uint32_t ma = (__ballot_sync(0xffffffffu, ha) >> g0) & 0xFFu;
-      const uint32_t mb = (__ballot_sync(0xffffffffu, hb) >> g0) & 0xFFu;
-      if (EMIT) {
-        const uint32_t below = (1u << sub) - 1u;
-        const uint32_t pa = c0 + __popc(ma & below);
-        const uint32_t pb = c0 + __popc(ma) + __popc(mb & below);
-        if (ha && pa < kSlots) stash[p * kStride + pa] = s.a_id;
-        if (hb && pb < kSlots) stash[p * kStride + pb] = s.b_id;
-      }
-      // hand the new count and "an earlier row still reaches qs" back to the owner lane
-      const uint32_t c1 = __shfl_sync(0xffffffffu, c0 + __popc(ma) + __popc(mb), (r & 3) * 8);
-      const unsigned reach = __ballot_sync(0xffffffffu, valid && exmax >= qs);
-      if (walking && (r >> 2) == st) {
-        cnt = c1;
-        cont = (reach >> ((r & 3) * 8)) & 1u;
-      }
-    }
-    walking = walking && cont && ln > sl.first;
-    ln -= 1;
-  }
+  walk_rounds<EMIT>(iv, stash, s_inv[warp], my_qs, my_qe, sl.first, walking, ln, cnt);
   if (i < n) cnt_out[i] = cnt;  // rle_right (interval_join.rs:1604)
 
   const uint32_t cincl = warp_incl_sum(cnt);  // a warp emits < 2^32 pairs unless rows hit > 2^27 builds each
@@ -191,27 +117,7 @@ k_probe_packed(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* 
     unsigned long long agg = 0;
 #pragma unroll
     for (int w = 0; w < kPWarps; ++w) agg += s_wtot[w];
-    if (lane == 0) atomicExch(chain_state + bid, (bid == 0 ? kFlagInc : kFlagAgg) | agg);
-    unsigned long long excl = 0;
-    if (bid > 0) {
-      int64_t look = int64_t(bid) - 1;
-      for (;;) {
-        const int64_t k = look - lane;
-        unsigned long long x = kFlagInc;
-        if (k >= 0) {
-          do { x = *reinterpret_cast<volatile unsigned long long*>(chain_state + k); } while ((x >> 62) == 0);
-        }
-        const unsigned inc_mask = __ballot_sync(0xffffffffu, (x >> 62) == 2);
-        const int first_inc = inc_mask ? (__ffs(inc_mask) - 1) : 32;
-        unsigned long long y = (lane <= first_inc) ? (x & kValMask) : 0;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) y += __shfl_xor_sync(0xffffffffu, y, d);
-        excl += y;
-        if (inc_mask) break;
-        look -= 32;
-      }
-      if (lane == 0) atomicExch(chain_state + bid, kFlagInc | (excl + agg));
-    }
+    const unsigned long long excl = chain_lookback(chain_state, bid, agg);
     if (lane == 0) {
       s_base = excl;
       if (bid == gridDim.x - 1) result[0] = excl + agg;
@@ -232,62 +138,8 @@ k_probe_packed(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* 
   uint32_t* __restrict__ rout = WRITE_RIGHT ? right_out + base : nullptr;
   const uint32_t coff = cincl - cnt;  // offset of my row's first pair inside the warp's run
 
-  // ---- phase 4a: rows with <= 32 hits, one flattened list per warp out of the stash ------------------
-  {
-    const Flat f = flat_setup(cnt <= kSlots ? cnt : 0u, lane, s_inv[warp]);  // also orders the stash writes
-    const uint32_t r_coff = __shfl_sync(0xffffffffu, coff, f.r_src);
-    for (uint32_t t0 = 0; t0 < f.total; t0 += 32) {
-      const uint32_t t = t0 + lane;
-      const int r = flat_rank(f, t0, lane);
-      const uint32_t k = t - __shfl_sync(0xffffffffu, f.r_excl, r);
-      const uint32_t off = __shfl_sync(0xffffffffu, r_coff, r);
-      const int src = __shfl_sync(0xffffffffu, f.r_src, r);
-      if (t < f.total) {
-        const uint32_t pos = off + k;
-        lout[pos] = stash[src * kStride + k];
-        if (WRITE_RIGHT) rout[pos] = tile_first + src;
-      }
-    }
-  }
-  // ---- phase 4b: rows with > 32 hits, the whole warp re-walks the row, four lines per step -----------
-  unsigned big = __ballot_sync(0xffffffffu, cnt > kSlots);
-  while (big) {
-    const int p = __ffs(big) - 1;
-    big &= big - 1;
-    const int32_t qs = __shfl_sync(0xffffffffu, my_qs, p);
-    const int32_t qe = __shfl_sync(0xffffffffu, my_qe, p);
-    uint32_t ln = __shfl_sync(0xffffffffu, sl.line, p);
-    const uint32_t first = __shfl_sync(0xffffffffu, sl.first, p);
-    uint32_t run = __shfl_sync(0xffffffffu, coff, p);
-    for (;;) {
-      const bool has = ln - first >= uint32_t(g);  // group g takes line ln - g
-      const uint4 d = has ? __ldg(iv.lines + size_t(ln - g) * 8 + sub) : make_uint4(0u, uint32_t(INT32_MIN), 0u, kEmptyRow);
-      const int32_t lbase = int32_t(__shfl_sync(0xffffffffu, d.x, g0));
-      const int32_t exmax = int32_t(__shfl_sync(0xffffffffu, d.y, g0));
-      const bool more = has && exmax >= qs && (ln - g) > first;  // this line sends the walk one line further
-      const unsigned mm = __ballot_sync(0xffffffffu, more);
-      const unsigned m4 = (mm & 1u) | ((mm >> 7) & 2u) | ((mm >> 14) & 4u) | ((mm >> 21) & 8u);
-      const bool live = has && ((m4 & ((1u << g) - 1u)) == ((1u << g) - 1u));  // every later line continued
-      const Slots s = slots_of(d, sub);
-      const bool ha = live && row_hits(s.a_lo, s.a_id, lbase, qs, qe);
-      const bool hb = live && row_hits(s.b_lo, s.b_id, lbase, qs, qe);
-      const unsigned ma = __ballot_sync(0xffffffffu, ha), mb = __ballot_sync(0xffffffffu, hb);
-      const unsigned below = (1u << lane) - 1u;
-      if (ha) {
-        const uint32_t pos = run + __popc(ma & below);
-        lout[pos] = s.a_id;
-        if (WRITE_RIGHT) rout[pos] = tile_first + p;
-      }
-      if (hb) {
-        const uint32_t pos = run + __popc(ma) + __popc(mb & below);
-        lout[pos] = s.b_id;
-        if (WRITE_RIGHT) rout[pos] = tile_first + p;
-      }
-      run += __popc(ma) + __popc(mb);
-      if (m4 != 0xFu) break;
-      ln -= 4;
-    }
-  }
+  // ---- phase 4: ordered emit (stash -> flattened coalesced stores; rows with > 32 hits re-walked) ----
+  emit_rows<WRITE_RIGHT>(iv, stash, s_inv[warp], cnt, coff, my_qs, my_qe, sl.line, sl.first, lout, rout, tile_first);
 }
 
 // ---------------------------------------------------------------------------------------------
