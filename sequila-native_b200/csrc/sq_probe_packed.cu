@@ -67,8 +67,6 @@ k_probe_packed(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* 
   __shared__ __align__(8) uint8_t s_inv[kPWarps][32];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 3, sub = lane & 7;  // lane group (one probe row at a time) and lane in group
-  const int g0 = g * 8;
 
   uint32_t bid = blockIdx.x;
   if (EMIT) {  // tiles in ticket order: every predecessor in the chained scan is already running
