@@ -259,6 +259,20 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the cuda interval join has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # NUMA locality of the pinned staging buffers: run this rank on the CPUs next to its GPU (what a
+    # launcher with --bind-to would do); the CPU baseline below widens the mask again
+    all_cpus = os.sched_getaffinity(0)
+    if world > 1 and not os.environ.get("SQ_NO_AFFINITY"):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (max(all_cpus) // 64) + 1)
+            near = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1} & all_cpus
+            if near:
+                os.sched_setaffinity(0, near)
+        except Exception:
+            pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version banner on stdout when NCCL_DEBUG is set on the box; stdout carries the
@@ -367,16 +381,14 @@ def main():
     for w in range(T):
         mine = list(range(w, n_tiles, T))
         cap = max(max(tile_pairs[t] for t in mine), 1)
-        rows = max(int(bounds[t + 1] - bounds[t]) for t in mine)
         workers.append({"st": sn.CudaStream(ctx), "tiles": mine,
-                        "out": (ctx.pinned_empty(cap, np.uint32), ctx.pinned_empty(cap, np.uint32),
-                                ctx.pinned_empty(rows, np.uint32))})
+                        "out": (ctx.pinned_empty(cap, np.uint32), ctx.pinned_empty(cap, np.uint32))})
 
     def run_partition(wk):
         got = 0
         for t in wk["tiles"]:
             lo, hi = int(bounds[t]), int(bounds[t + 1])
-            out = (wk["out"][0], wk["out"][1], wk["out"][2][:hi - lo])
+            out = (wk["out"][0], wk["out"][1], None)  # index pairs; the optional per-row counts stay on the device
             got += wk["st"].probe_join(idx, hk[lo:hi], hs[lo:hi], he[lo:hi], out)
         return got
 
@@ -428,12 +440,13 @@ def main():
                       "roofline_frac": (24.0 * n_build / (build_best * 1e-3) / 1e9 / hbm_peak) if build_best else None,
                       "index_bytes": idx.bytes, "keys": idx.keys},
             "e2e": {"value": e2e_value, "unit": "probe intervals/s", "h2d_bytes_per_step": 16 * n_probe,
-                    "d2h_bytes_per_step": 8 * n_pairs + 4 * n_probe + 8, "ms_per_step": e_ms_max,
+                    "d2h_bytes_per_step": 8 * n_pairs + 16, "ms_per_step": e_ms_max,
                     "steps": args.e2e_steps, "api": "sq_probe_join (host C ABI), pinned host buffers", "partitions": T, "tiles": n_tiles},
             "gpu_launches": int(launches), "clocks": clocks,
             "digest": {"pairs": dg[0], "sum": dg[1], "xor": dg[2]},
         }
         if not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)
             if args.workload == "cfg5_shard":
                 bh, ph = _sample_to_host(build, args), _sample_to_host(probe, args)
             else:
