@@ -440,7 +440,8 @@ def main():
                       "roofline_frac": (24.0 * n_build / (build_best * 1e-3) / 1e9 / hbm_peak) if build_best else None,
                       "index_bytes": idx.bytes, "keys": idx.keys},
             "e2e": {"value": e2e_value, "unit": "probe intervals/s", "h2d_bytes_per_step": 16 * n_probe,
-                    "d2h_bytes_per_step": 8 * n_pairs + 16, "ms_per_step": e_ms_max,
+                    "d2h_bytes_per_step": (4 * n_pairs + 4 * n_probe + 16 * n_tiles) if os.environ.get("SQ_RLE_WIRE", "0") != "0"
+                    else 8 * n_pairs + 16 * n_tiles, "ms_per_step": e_ms_max,
                     "steps": args.e2e_steps, "api": "sq_probe_join (host C ABI), pinned host buffers", "partitions": T, "tiles": n_tiles},
             "gpu_launches": int(launches), "clocks": clocks,
             "digest": {"pairs": dg[0], "sum": dg[1], "xor": dg[2]},

@@ -252,6 +252,7 @@ SQ_API void sq_stream_free(sq_stream* s) {
                     &s->d_right, &s->d_gather, &s->d_gather2, &s->d_chain, &s->d_strblk, &s->d_strdata, &s->h_in, &s->h_out, &s->h_scalar})
     release(*b);
   if (s->ev_ready) for (auto& e : s->ev) cudaEventDestroy(e);
+  if (s->ev_rle) cudaEventDestroy(s->ev_rle);
   if (s->own_stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -436,6 +437,41 @@ static int32_t launch_emit(sq_stream* s, uint32_t* d_left, uint32_t* d_right, ui
   return launch_write(s, s->idx, s->d_q_start, s->n_rows, d_left, d_right, capacity);
 }
 
+
+// right_idx[k] = the probe row of pair k: row i repeated counts[i] times (the reference's own expansion
+// loop, IJ:1611-1618).  Rows with few hits dominate, so a row is written as one 32-byte block of eight
+// copies and the cursor advances by its count; longer runs loop over blocks; the tail is filled exactly.
+static void expand_counts(const uint32_t* counts, uint32_t n_rows, uint32_t* right, uint64_t n_pairs) {
+  struct V8 { uint32_t v[8]; };
+  uint64_t o = 0;
+  uint32_t i = 0;
+  for (; i < n_rows && o + 8 <= n_pairs; ++i) {
+    const uint32_t c = counts[i];
+    if (c == 0) continue;
+    V8 b;
+    for (int k = 0; k < 8; ++k) b.v[k] = i;
+    if (c <= 8) {
+      memcpy(right + o, &b, sizeof b);  // may overshoot by up to 7 entries that later rows overwrite
+      o += c;
+    } else {
+      const uint64_t end = o + c;
+      for (; o + 8 <= end && o + 8 <= n_pairs; o += 8) memcpy(right + o, &b, sizeof b);
+      for (; o < end; ++o) right[o] = i;
+    }
+  }
+  for (; i < n_rows; ++i)  // the last few pairs: never write past n_pairs
+    for (uint32_t k = 0; k < counts[i] && o < n_pairs; ++k) right[o++] = i;
+}
+
+// Opt-in (SQ_RLE_WIRE=1).  Measured on the B200 box: one host thread expands ~1 G pairs/s, so with four
+// partition threads per GPU the decode (20 ms per 80M pairs) is slower than copying right_idx itself over a
+// dedicated PCIe 5 x16 link (13.4 ms per step end to end vs 17.9 ms); it pays only where several GPUs share
+// the host link (8 GPUs on that box: 60 ms per step with plain copies).
+static bool rle_on_the_wire() {
+  const char* e = getenv("SQ_RLE_WIRE");
+  return e && atoi(e) != 0;
+}
+
 static int32_t check_emit(sq_stream* s, const void* left, uint64_t capacity) {
   if (!s) return SQ_EINVAL;
   if (!s->counted) return fail(s->err, SQ_ESTATE, "sq_probe_emit_pairs called without a preceding sq_probe_count");
@@ -479,12 +515,31 @@ SQ_API int32_t sq_probe_emit_pairs(sq_stream* s, uint32_t* left_idx_out, uint32_
   auto* dl = static_cast<uint32_t*>(s->d_left.p);
   auto* dr = static_cast<uint32_t*>(s->d_right.p);
   mark(s, 4);
+  // right_idx is a run-length expansion of the per-row counts (IJ:1611-1618); optionally it travels as the
+  // counts (4 B per probe row instead of 4 B per pair) and is decoded into the caller's buffer here while
+  // left_idx is still arriving (see rle_on_the_wire).
+  const bool rle_wire = right_idx_out && np && rle_on_the_wire();
+  const uint32_t* h_counts = counts_out;
+  if ((counts_out || rle_wire) && s->n_rows) {
+    if (!counts_out) {
+      if ((rc = ensure(E, s->h_out, size_t(s->n_rows) * 4, true))) return rc;
+      h_counts = static_cast<const uint32_t*>(s->h_out.p);
+    }
+    SQ_CUDA(E, cudaMemcpyAsync(const_cast<uint32_t*>(h_counts), s->d_cnt.p, size_t(s->n_rows) * 4, cudaMemcpyDeviceToHost,
+                               s->stream));
+    if (rle_wire) {
+      if (!s->ev_rle) SQ_CUDA(E, cudaEventCreateWithFlags(&s->ev_rle, cudaEventDisableTiming));
+      SQ_CUDA(E, cudaEventRecord(s->ev_rle, s->stream));
+    }
+  }
   if (np) {
     if (left_idx_out) SQ_CUDA(E, cudaMemcpyAsync(left_idx_out, dl, np * 4, cudaMemcpyDeviceToHost, s->stream));
-    if (right_idx_out) SQ_CUDA(E, cudaMemcpyAsync(right_idx_out, dr, np * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (right_idx_out && !rle_wire) SQ_CUDA(E, cudaMemcpyAsync(right_idx_out, dr, np * 4, cudaMemcpyDeviceToHost, s->stream));
   }
-  if (counts_out && s->n_rows)
-    SQ_CUDA(E, cudaMemcpyAsync(counts_out, s->d_cnt.p, size_t(s->n_rows) * 4, cudaMemcpyDeviceToHost, s->stream));
+  if (rle_wire) {
+    SQ_CUDA(E, cudaEventSynchronize(s->ev_rle));
+    expand_counts(h_counts, s->n_rows, right_idx_out, np);
+  }
   mark(s, 5);
   SQ_CUDA(E, cudaStreamSynchronize(s->stream));
   s->d_last_left = dl;

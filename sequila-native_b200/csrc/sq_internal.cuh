@@ -200,6 +200,7 @@ struct sq_stream {
   bool profiling = false;
   cudaEvent_t ev[8] = {};
   bool ev_ready = false;
+  cudaEvent_t ev_rle = nullptr;          // "the counts have arrived" (right_idx is decoded from them on the host)
   float phase_ms[5] = {0, 0, 0, 0, 0};   // last value per phase
   double phase_sum[5] = {0, 0, 0, 0, 0}; // running sums since profiling was enabled
   uint64_t phase_n[5] = {0, 0, 0, 0, 0};

@@ -224,3 +224,13 @@ def test_error_paths(cuda_ctx):
     with pytest.raises(sn.SequilaCudaError) as e:
         st.emit_pairs(out=small)
     assert e.value.code == 5  # SQ_ECAPACITY
+
+
+def test_right_idx_run_length_encoded_on_the_wire(cuda_ctx, oracle, monkeypatch):
+    """SQ_RLE_WIRE=1: right_idx crosses PCIe as per-row counts and is expanded on the host."""
+    monkeypatch.setenv("SQ_RLE_WIRE", "1")
+    for name, scale in (("cfg2", 0.05), ("cfg3", 0.01), ("cfg4", 0.02)):
+        b, p = sn.synth.CONFIGS[name](scale=scale)
+        assert_same(oracle, cuda_ctx, b, p)
+    one = {"key": np.array([7], dtype=np.uint64), "start": np.array([5], dtype=np.int32), "end": np.array([10], dtype=np.int32)}
+    assert_same(oracle, cuda_ctx, one, one)
