@@ -130,15 +130,54 @@ SQ_API const char* sq_last_error(const sq_ctx* ctx) {
   return ctx ? ctx->err.msg.c_str() : g_create_err.msg.c_str();
 }
 
+// Process-wide: buffers handed to Arrow consumers are released whenever the consumer drops them, possibly
+// after the context (and the exec node) that allocated them is gone.  Pinned memory is not tied to a device.
+static HostPool& host_pool() {
+  static HostPool* p = new HostPool();  // never destroyed: finalizers may release buffers during process exit
+  return *p;
+}
+
 SQ_API int32_t sq_host_alloc(sq_ctx* ctx, size_t bytes, void** out) {
   if (!ctx || !out) return SQ_EINVAL;
+  size_t cap = 4096;
+  while (cap < bytes) cap <<= 1;
+  HostPool& hp = host_pool();
+  {
+    std::lock_guard<std::mutex> g(hp.mu);
+    auto it = hp.idle.find(cap);
+    if (it != hp.idle.end()) {
+      *out = it->second;
+      hp.idle.erase(it);
+      hp.idle_bytes -= cap;
+      return SQ_OK;
+    }
+  }
   SQ_CUDA(ctx->err, cudaSetDevice(ctx->device));
-  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
-  if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx->err, SQ_ENOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+  cudaError_t e = cudaHostAlloc(out, cap, cudaHostAllocDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx->err, SQ_ENOMEM, "cudaHostAlloc(%zu): %s", cap, cudaGetErrorString(e)); }
+  std::lock_guard<std::mutex> g(hp.mu);
+  hp.capacity[*out] = cap;
   return SQ_OK;
 }
 
-SQ_API void sq_host_free(sq_ctx*, void* p) { if (p) cudaFreeHost(p); }
+SQ_API void sq_host_free(sq_ctx*, void* p) {
+  if (!p) return;
+  {  // the context may be gone already (Arrow arrays outlive the exec node that produced them)
+    HostPool& hp = host_pool();
+    std::lock_guard<std::mutex> g(hp.mu);
+    auto it = hp.capacity.find(p);
+    if (it != hp.capacity.end()) {
+      constexpr size_t kKeep = size_t(8) << 30;  // pooled pinned memory is capped; beyond it buffers go back to the OS
+      if (hp.idle_bytes + it->second <= kKeep) {
+        hp.idle.emplace(it->second, p);
+        hp.idle_bytes += it->second;
+        return;
+      }
+      hp.capacity.erase(it);
+    }
+  }
+  cudaFreeHost(p);
+}
 
 // ---- build ------------------------------------------------------------------------------------
 SQ_API int32_t sq_index_build_device(sq_ctx* ctx, const uint64_t* d_key_hash, const int32_t* d_start,
@@ -781,11 +820,11 @@ SQ_API int32_t sq_gather_utf8(sq_stream* s, int32_t side, int32_t build_col_id, 
   if ((rc = launch_str_offsets(s, d_off, ix, np, d_out_off, &total))) return rc;
   if (total > 0x7FFFFFFFull)
     return fail(E, SQ_ECAPACITY, "gathered utf8 column needs %llu bytes; Utf8 offsets are 32-bit", (unsigned long long)total);
-  if (out_offsets) {  // narrow the 64-bit device offsets on the way out
-    std::vector<int64_t> tmp(np + 1);
-    SQ_CUDA(E, cudaMemcpyAsync(tmp.data(), d_out_off, (np + 1) * 8, cudaMemcpyDeviceToHost, s->stream));
+  if (out_offsets) {  // Arrow Utf8 offsets are 32-bit: narrow on the device, copy straight into the caller's buffer
+    auto* d_off32 = reinterpret_cast<int32_t*>(d_out_off + np + 1);
+    if ((rc = launch_narrow_offsets(s, d_out_off, np + 1, d_off32))) return rc;
+    SQ_CUDA(E, cudaMemcpyAsync(out_offsets, d_off32, (np + 1) * 4, cudaMemcpyDeviceToHost, s->stream));
     SQ_CUDA(E, cudaStreamSynchronize(s->stream));
-    for (uint64_t k = 0; k <= np; ++k) out_offsets[k] = int32_t(tmp[k]);
   }
   s->str_src_off = d_off;
   s->str_src_data = d_data;

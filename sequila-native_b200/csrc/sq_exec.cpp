@@ -25,6 +25,19 @@ namespace {
 
 using Clock = std::chrono::steady_clock;
 
+// SQ_EXEC_TRACE=1: per-phase wall times of every probe batch on stderr (development aid)
+struct Trace {
+  bool on;
+  Clock::time_point t;
+  Trace() : on(getenv("SQ_EXEC_TRACE") != nullptr), t(Clock::now()) {}
+  void lap(const char* what) {
+    if (!on) return;
+    const auto n = Clock::now();
+    fprintf(stderr, "[sq_exec] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+
 inline uint64_t mix64(uint64_t x) {
   x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
   x ^= x >> 27; x *= 0x94d049bb133111ebull;
@@ -194,6 +207,10 @@ int hash_keys(sq_exec* e, const Side& side, const std::vector<int32_t>& on, cons
         (*out)[size_t(i)] = mix64((*out)[size_t(i)] ^ (mix64(raw) + 0x9e3779b97f4a7c15ull));
       }
     } else {
+      // strings of up to 8 bytes (contig names) hash from one masked 8-byte load; longer ones byte by byte
+      const int64_t data_end = n == 0 ? 0
+                               : (t.kind == Kind::Utf8 ? int64_t((reinterpret_cast<const int32_t*>(v.values) + v.offset)[n])
+                                                       : (reinterpret_cast<const int64_t*>(v.values) + v.offset)[n]);
       for (int64_t i = 0; i < n; ++i) {
         int64_t a, b;
         if (t.kind == Kind::Utf8) {
@@ -203,8 +220,21 @@ int hash_keys(sq_exec* e, const Side& side, const std::vector<int32_t>& on, cons
           const int64_t* off = reinterpret_cast<const int64_t*>(v.values) + v.offset;
           a = off[i]; b = off[i + 1];
         }
-        uint64_t h = 0xcbf29ce484222325ull;  // FNV-1a over the bytes
-        for (int64_t k = a; k < b; ++k) { h ^= v.data[k]; h *= 0x100000001b3ull; }
+        const int64_t len = b - a;
+        uint64_t h;
+        if (len <= 8) {
+          uint64_t raw = 0;
+          if (a + 8 <= data_end) {
+            memcpy(&raw, v.data + a, 8);
+            raw &= len == 8 ? ~0ull : ((1ull << (8 * len)) - 1ull);
+          } else {
+            memcpy(&raw, v.data + a, size_t(len));
+          }
+          h = mix64(raw ^ (0x9e3779b97f4a7c15ull * uint64_t(len + 1)));
+        } else {
+          h = 0xcbf29ce484222325ull;  // FNV-1a over the bytes
+          for (int64_t k = a; k < b; ++k) { h ^= v.data[k]; h *= 0x100000001b3ull; }
+        }
         (*out)[size_t(i)] = mix64((*out)[size_t(i)] ^ (mix64(h) + 0x9e3779b97f4a7c15ull));
       }
     }
@@ -221,6 +251,7 @@ int eval_i32(sq_exec* e, sq_stream* st, const Side& side, int32_t col, bool minu
   out->resize(size_t(n));
   if (t.format == "i") {
     const int32_t* p = reinterpret_cast<const int32_t*>(v.values) + v.offset;
+    if (!minus_one) { out->assign(p, p + n); return SQ_OK; }
     for (int64_t i = 0; i < n; ++i) {
       if (minus_one && p[i] == INT32_MIN) return e->fail(SQ_ECAST, "Arrow error: Arithmetic overflow: Overflow happened on: %d - 1", p[i]);
       (*out)[size_t(i)] = p[i] - (minus_one ? 1 : 0);
@@ -451,9 +482,12 @@ int probe_on_device(sq_exec* e, sq_stream* st, const ArrowArray* batch, uint64_t
   std::vector<uint64_t> keys;
   std::vector<int32_t> start, end;
   int rc;
+  Trace tr;
   if ((rc = hash_keys(e, e->right, e->on_right, batch, &keys))) return rc;
+  tr.lap("hash_keys");
   if ((rc = eval_i32(e, st, e->right, e->cfg.right_start, false, batch, &start))) return rc;
   if ((rc = eval_i32(e, st, e->right, e->cfg.right_end, e->cfg.right_end_minus_one != 0, batch, &end))) return rc;
+  tr.lap("eval_i32 x2");
   uint64_t n_pairs = 0;
   if (e->cfg.algorithm == SQ_EXEC_NEAREST) {  // one output row per probe row; the left side may be NULL (IJ:1593-1602)
     rc = sq_probe_nearest(st, e->index, keys.data(), start.data(), end.data(), uint32_t(n), nullptr);
@@ -466,6 +500,7 @@ int probe_on_device(sq_exec* e, sq_stream* st, const ArrowArray* batch, uint64_t
     rc = sq_probe_emit_pairs(st, nullptr, nullptr, nullptr, n_pairs);
     if (rc != SQ_OK) return e->fail(rc, "%s", sq_stream_last_error(st));
   }
+  tr.lap("probe on device");
   *n_out = n_pairs;
   return SQ_OK;
 }
@@ -475,6 +510,7 @@ int assemble_output(sq_exec* e, sq_stream* st, const ArrowArray* batch, uint64_t
   const uint64_t n = uint64_t(batch->length);
   const bool nearest = e->cfg.algorithm == SQ_EXEC_NEAREST;
   int rc;
+  Trace tr;
   // `out` is assembled in place; on any failure below everything attached so far is released
   auto* own = new Owned();
   own->ctx = e->ctx;
@@ -593,6 +629,7 @@ int assemble_output(sq_exec* e, sq_stream* st, const ArrowArray* batch, uint64_t
     }
     child->n_buffers = int64_t(co->buffers.size());
     child->buffers = co->buffers.data();
+    tr.lap(t.kind == Kind::Fixed ? "column (fixed)" : "column (utf8)");
   }
   own->child_ptrs = own->children;
   own->buffers = {nullptr};

@@ -311,6 +311,19 @@ int launch_gather_bits(sq_stream* s, const uint8_t* d_bitmap, const uint32_t* d_
   return SQ_OK;
 }
 
+__global__ void __launch_bounds__(256) k_narrow_offsets(const int64_t* __restrict__ in, uint64_t n, int32_t* __restrict__ out) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = int32_t(in[i]);
+}
+
+int launch_narrow_offsets(sq_stream* s, const int64_t* d_in, uint64_t n, int32_t* d_out) {
+  if (n == 0) return SQ_OK;
+  k_narrow_offsets<<<grid_for(n, 256, s->ctx->sm_count), 256, 0, s->stream>>>(d_in, n, d_out);
+  SQ_CUDA(s->err, cudaGetLastError());
+  s->launches += 1;
+  return SQ_OK;
+}
+
 __global__ void __launch_bounds__(256) k_iota(uint32_t* __restrict__ out, uint64_t n) {
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = uint32_t(i);

@@ -4,8 +4,10 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "sequila_cuda.h"
@@ -91,6 +93,16 @@ struct ErrorSlot {
 };
 
 }  // namespace sq
+
+// Pool behind sq_host_alloc / sq_host_free: cudaHostAlloc costs milliseconds per call, and the exec node
+// hands one pinned buffer per output column per batch to Arrow, so released buffers are kept (size classes
+// of powers of two) and reused.
+struct HostPool {
+  std::mutex mu;
+  std::multimap<size_t, void*> idle;          // capacity -> buffer
+  std::unordered_map<void*, size_t> capacity; // every buffer this pool handed out
+  size_t idle_bytes = 0;
+};
 
 struct sq_ctx {
   int device = 0;
@@ -241,6 +253,7 @@ int launch_nearest(sq_stream* s, const sq_index* idx, const uint64_t* d_key, con
                    const int32_t* d_end, uint32_t n, uint32_t* d_left);
 // right_idx of a one-row-per-probe-row result: 0, 1, ..., n-1
 int launch_iota(sq_stream* s, uint32_t* d_out, uint64_t n);
+int launch_narrow_offsets(sq_stream* s, const int64_t* d_in, uint64_t n, int32_t* d_out);
 
 // probe_packed.cu: one fused pass over the packed lines (count + chained scan + write when
 // d_left != nullptr; count only otherwise).  Leaves cnt per row in s->d_cnt, result[0] = n_pairs and
