@@ -53,16 +53,20 @@ __device__ __forceinline__ StartLine find_start_line(const IndexView& iv, uint32
   return r;
 }
 
-template <bool EMIT, bool WRITE_RIGHT, int kPBlock>
+// kTiles consecutive tiles per CTA: the probe columns and directory words of ALL of them are requested up
+// front, so only the first tile of a CTA waits for those two round trips (count-only launches use 2; see
+// launch_packed_b for why emitting launches use 1).
+template <bool EMIT, bool WRITE_RIGHT, int kPBlock, int kTiles>
 __global__ void __launch_bounds__(kPBlock, 1024 / kPBlock)
 k_probe_packed(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __restrict__ q_start,
                const int32_t* __restrict__ q_end, uint32_t n, uint32_t* __restrict__ cnt_out,
                unsigned long long* chain_state, unsigned int* ticket, unsigned long long* result,
-               uint32_t* __restrict__ left_out, uint32_t* __restrict__ right_out, uint64_t capacity) {
+               uint32_t* __restrict__ left_out, uint32_t* __restrict__ right_out, uint64_t capacity,
+               uint32_t n_tiles) {
   constexpr int kPWarps = kPBlock / 32;
   __shared__ uint32_t s_stash[EMIT ? kPWarps * 32 * kStride : 1];
-  __shared__ unsigned long long s_wtot[kPWarps];
-  __shared__ unsigned long long s_base;
+  __shared__ unsigned long long s_wtot[2][kPWarps];
+  __shared__ unsigned long long s_base[2];
   __shared__ uint32_t s_bid;
   __shared__ __align__(8) uint8_t s_inv[kPWarps][32];
 
@@ -74,70 +78,91 @@ k_probe_packed(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* 
     __syncthreads();
     bid = s_bid;
   }
-  const uint32_t i = bid * kPBlock + threadIdx.x;
-  const uint32_t tile_first = bid * kPBlock + warp * 32;
 
-  // ---- phase 1: my probe row -> start line ----------------------------------------------------------
-  int32_t my_qs = 0, my_qe = 0;
-  StartLine sl{0u, 0u, false};
-  if (i < n) {
-    my_qs = q_start[i];
-    my_qe = q_end[i];
-    const uint32_t id = ht_lookup(iv.ht_keys, iv.ht_ids, iv.ht_mask, iv.sentinel_id, q_key[i]);
-    sl = find_start_line(iv, id, my_qe);
-  }
-
-  // ---- phase 2: walk in compacted rounds (sq_packed_common.cuh) -----------------------------------
-  uint32_t* stash = s_stash + (EMIT ? warp * 32 * kStride : 0);
-  bool walking = sl.act;
-  uint32_t ln = sl.line;  // next line of my row
-  uint32_t cnt = 0;       // hits of my row so far
-  walk_rounds<EMIT>(iv, stash, s_inv[warp], my_qs, my_qe, sl.first, walking, ln, cnt);
-  if (i < n) cnt_out[i] = cnt;  // rle_right (interval_join.rs:1604)
-
-  const uint32_t cincl = warp_incl_sum(cnt);  // a warp emits < 2^32 pairs unless rows hit > 2^27 builds each
-  const uint32_t wtot = __shfl_sync(0xffffffffu, cincl, 31);
-  if (!EMIT) {  // count only: the grand total is order-free; one atomic per CTA (same-address atomics
-                // serialise at ~2.5 ns each: one per warp would cost 1 ms per 12.5M rows by itself)
-    __shared__ unsigned long long s_ctot;
-    if (threadIdx.x == 0) s_ctot = 0;
-    __syncthreads();
-    if (lane == 0 && wtot) atomicAdd(&s_ctot, (unsigned long long)wtot);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_ctot) atomicAdd(result, s_ctot);
-    return;
-  }
-
-  // ---- phase 3: CTA total -> chained scan -------------------------------------------------------------
-  if (lane == 0) s_wtot[warp] = wtot;
-  __syncthreads();
-  if (warp == 0) {
-    unsigned long long agg = 0;
+  // ---- phase 1 of every tile of this CTA: my probe rows -> their start lines ---------------------------
+  int32_t t_qs[kTiles], t_qe[kTiles];
+  uint64_t t_key[kTiles];
+  StartLine t_sl[kTiles];
 #pragma unroll
-    for (int w = 0; w < kPWarps; ++w) agg += s_wtot[w];
-    const unsigned long long excl = chain_lookback(chain_state, bid, agg);
-    if (lane == 0) {
-      s_base = excl;
-      if (bid == gridDim.x - 1) result[0] = excl + agg;
-      if (excl + agg > capacity) result[1] = 1;  // the caller's buffers are too small: report, write nothing here
+  for (int t = 0; t < kTiles; ++t) {
+    const uint64_t i = (uint64_t(bid) * kTiles + t) * kPBlock + threadIdx.x;
+    t_qs[t] = t_qe[t] = 0;
+    t_key[t] = 0;
+    if (i < n) {
+      t_qs[t] = q_start[i];
+      t_qe[t] = q_end[i];
+      t_key[t] = q_key[i];
     }
   }
-  __syncthreads();
-  if (wtot == 0) return;  // warp-uniform
-  uint64_t base = s_base;
-  unsigned long long cta_tot = 0;
 #pragma unroll
-  for (int w = 0; w < kPWarps; ++w) {
-    if (w < warp) base += s_wtot[w];
-    cta_tot += s_wtot[w];
+  for (int t = 0; t < kTiles; ++t) {
+    const uint64_t i = (uint64_t(bid) * kTiles + t) * kPBlock + threadIdx.x;
+    t_sl[t] = StartLine{0u, 0u, false};
+    if (i < n) {
+      const uint32_t id = ht_lookup(iv.ht_keys, iv.ht_ids, iv.ht_mask, iv.sentinel_id, t_key[t]);
+      t_sl[t] = find_start_line(iv, id, t_qe[t]);
+    }
   }
-  if (s_base + cta_tot > capacity) return;  // CTA-uniform
-  uint32_t* __restrict__ lout = left_out + base;
-  uint32_t* __restrict__ rout = WRITE_RIGHT ? right_out + base : nullptr;
-  const uint32_t coff = cincl - cnt;  // offset of my row's first pair inside the warp's run
 
-  // ---- phase 4: ordered emit (stash -> flattened coalesced stores; rows with > 32 hits re-walked) ----
-  emit_rows<WRITE_RIGHT>(iv, stash, s_inv[warp], cnt, coff, my_qs, my_qe, sl.line, sl.first, lout, rout, tile_first);
+#pragma unroll
+  for (int t = 0; t < kTiles; ++t) {
+    const uint32_t tile = bid * kTiles + t;
+    if (tile >= n_tiles) break;  // CTA-uniform
+    const uint64_t i = uint64_t(tile) * kPBlock + threadIdx.x;
+    const uint32_t tile_first = tile * kPBlock + warp * 32;
+    const int32_t my_qs = t_qs[t], my_qe = t_qe[t];
+    const StartLine sl = t_sl[t];
+
+    // ---- phase 2: walk in compacted rounds (sq_packed_common.cuh) ---------------------------------
+    uint32_t* stash = s_stash + (EMIT ? warp * 32 * kStride : 0);
+    bool walking = sl.act;
+    uint32_t ln = sl.line;  // next line of my row
+    uint32_t cnt = 0;       // hits of my row so far
+    walk_rounds<EMIT>(iv, stash, s_inv[warp], my_qs, my_qe, sl.first, walking, ln, cnt);
+    if (i < n) cnt_out[i] = cnt;  // rle_right (interval_join.rs:1604)
+
+    const uint32_t cincl = warp_incl_sum(cnt);  // a warp emits < 2^32 pairs unless rows hit > 2^27 builds each
+    const uint32_t wtot = __shfl_sync(0xffffffffu, cincl, 31);
+    const int buf = t & 1;  // totals of consecutive tiles alternate buffers: one barrier separates reuse
+    if (lane == 0) s_wtot[buf][warp] = wtot;
+    __syncthreads();
+    if (!EMIT) {  // count only: the grand total is order-free; one atomic per CTA and tile (same-address
+                  // atomics serialise at ~2.5 ns each: one per warp would cost 1 ms per 12.5M rows by itself)
+      if (threadIdx.x == 0) {
+        unsigned long long tot = 0;
+#pragma unroll
+        for (int w = 0; w < kPWarps; ++w) tot += s_wtot[buf][w];
+        if (tot) atomicAdd(result, tot);
+      }
+      continue;
+    }
+
+    // ---- phase 3: CTA total -> chained scan ---------------------------------------------------------
+    if (warp == 0) {
+      unsigned long long agg = 0;
+#pragma unroll
+      for (int w = 0; w < kPWarps; ++w) agg += s_wtot[buf][w];
+      const unsigned long long excl = chain_lookback(chain_state, tile, agg);
+      if (lane == 0) {
+        s_base[buf] = excl;
+        if (tile == n_tiles - 1) result[0] = excl + agg;
+        if (excl + agg > capacity) result[1] = 1;  // the caller's buffers are too small: report, write nothing here
+      }
+    }
+    __syncthreads();
+    uint64_t base = s_base[buf];
+    unsigned long long cta_tot = 0;
+#pragma unroll
+    for (int w = 0; w < kPWarps; ++w) {
+      if (w < warp) base += s_wtot[buf][w];
+      cta_tot += s_wtot[buf][w];
+    }
+    // ---- phase 4: ordered emit (stash -> flattened coalesced stores; rows with > 32 hits re-walked) ----
+    if (wtot != 0 && s_base[buf] + cta_tot <= capacity)
+      emit_rows<WRITE_RIGHT>(iv, stash, s_inv[warp], cnt, cincl - cnt, my_qs, my_qe, sl.line, sl.first, left_out + base,
+                             WRITE_RIGHT ? right_out + base : nullptr, tile_first);
+    __syncwarp();  // the stash is reused by the next tile
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -154,20 +179,24 @@ bool use_packed(const sq_index* idx) {
   return idx->n_lines * 128ull > (64ull << 20);
 }
 
+// Count-only launches give every CTA two consecutive tiles (measured: 0.69 vs 0.77 ms per 12.5M rows, the
+// second tile's probe columns and directory word are already there).  Emitting launches must not: tile
+// 2b+2 could only finish its look-back after CTA b has published its SECOND tile, i.e. after CTA b has
+// waited for and written its first one — the chained scan would serialise the whole grid (measured: 400 ms).
 template <int B>
 static void launch_packed_b(sq_stream* s, const IndexView& iv, const uint64_t* d_key, const int32_t* d_start,
                             const int32_t* d_end, uint32_t n, uint32_t* cnt, unsigned long long* chain, unsigned int* ticket,
                             unsigned long long* result, uint32_t* d_left, uint32_t* d_right, uint64_t capacity) {
   const uint32_t n_tiles = (n + B - 1) / B;
   if (!d_left)
-    k_probe_packed<false, false, B><<<n_tiles, B, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket, result,
-                                                                   nullptr, nullptr, 0);
+    k_probe_packed<false, false, B, 2><<<(n_tiles + 1) / 2, B, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket,
+                                                                                result, nullptr, nullptr, 0, n_tiles);
   else if (d_right)
-    k_probe_packed<true, true, B><<<n_tiles, B, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket, result,
-                                                                 d_left, d_right, capacity);
+    k_probe_packed<true, true, B, 1><<<n_tiles, B, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket, result,
+                                                                    d_left, d_right, capacity, n_tiles);
   else
-    k_probe_packed<true, false, B><<<n_tiles, B, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket, result,
-                                                                  d_left, nullptr, capacity);
+    k_probe_packed<true, false, B, 1><<<n_tiles, B, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket, result,
+                                                                     d_left, nullptr, capacity, n_tiles);
 }
 
 int launch_packed(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
