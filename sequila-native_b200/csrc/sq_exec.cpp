@@ -573,6 +573,7 @@ int assemble_output(sq_exec* e, sq_stream* st, const ArrowArray* batch, uint64_t
       void* vals = pinned(size_t(n_pairs) * w);
       if (!vals) return e->fail(SQ_ENOMEM, "pinned allocation failed");
       co->pinned.push_back(vals);
+      tr.lap("  alloc");
       if (n_pairs) {
         if (side == 0) {
           rc = sq_gather_column(st, 0, bid, nullptr, w, vals, n_pairs);
