@@ -163,3 +163,18 @@ def test_partitioned_mode_one_exec_per_partition(oracle):
     ol, orr, _ = oracle.join(bc.astype(np.uint64), bs, be, pc.astype(np.uint64), ps, pe)
     want = sorted(zip(names[bc][ol].tolist(), bs[ol].tolist(), be[ol].tolist(), names[pc][orr].tolist(), ps[orr].tolist(), pe[orr].tolist()))
     assert sorted(got) == want
+
+
+def test_empty_projection_is_a_count_only_probe(oracle):
+    """`SELECT count(*) FROM a JOIN b ON ...`: the join node projects no column, the output batches carry
+    only their row counts and the pairs are never written (what the reference's benchmarks run)."""
+    rng = np.random.default_rng(8)
+    nb, npq = 5000, 4000
+    bs = rng.integers(0, 40000, nb).astype(np.int32); be = (bs + rng.integers(0, 300, nb)).astype(np.int32)
+    ps = rng.integers(0, 40000, npq).astype(np.int32); pe = (ps + rng.integers(0, 300, npq)).astype(np.int32)
+    left = pa.record_batch([pa.array(["c"] * nb), pa.array(bs), pa.array(be)], names=COLS)
+    right = pa.record_batch([pa.array(["c"] * npq), pa.array(ps), pa.array(pe)], names=COLS)
+    plan, out = run_join(left, right, Q1, batch_rows=1500, projection=[])
+    ol, _, _ = oracle.join(np.zeros(nb, np.uint64), bs, be, np.zeros(npq, np.uint64), ps, pe)
+    assert all(b.num_columns == 0 for b in out) and sum(b.num_rows for b in out) == len(ol)
+    assert plan.metrics().output_rows == len(ol)
