@@ -39,8 +39,8 @@ def parse_args():
     ap.add_argument("--build-rows", type=int, default=BUILD_ROWS)
     ap.add_argument("--shard-rows", type=int, default=SHARD_ROWS)
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--e2e-partitions", type=int, default=4, help="host threads, one sq_stream each")
-    ap.add_argument("--e2e-tiles", type=int, default=16, help="probe sub-tiles per step (all partitions)")
+    ap.add_argument("--e2e-partitions", type=int, default=8, help="host threads, one sq_stream each")
+    ap.add_argument("--e2e-tiles", type=int, default=32, help="probe sub-tiles per step (all partitions)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-contigs", type=int, default=8)
     ap.add_argument("--cpu-sample-probes", type=int, default=2_000_000)
@@ -452,8 +452,10 @@ def main():
                       "roofline_frac": (24.0 * n_build / (build_best * 1e-3) / 1e9 / hbm_peak) if build_best else None,
                       "index_bytes": idx.bytes, "keys": idx.keys},
             "e2e": {"value": e2e_value, "unit": "probe intervals/s", "h2d_bytes_per_step": 16 * n_probe,
-                    "d2h_bytes_per_step": (4 * n_pairs + 4 * n_probe + 16 * n_tiles) if os.environ.get("SQ_RLE_WIRE", "0") != "0"
-                    else 8 * n_pairs + 16 * n_tiles, "ms_per_step": e_ms_max,
+                    "d2h_bytes_per_step": (4 * n_pairs + 4 * n_probe + 16 * n_tiles) if os.environ.get("SQ_RLE_WIRE", "1") != "0"
+                    else 8 * n_pairs + 16 * n_tiles,
+                    "wire": "left_idx u32 per pair + per-row counts u32; right_idx is expanded from the counts into the caller's "
+                            "host buffer by the calling thread (interval_join.rs:1611-1618)", "ms_per_step": e_ms_max,
                     "steps": args.e2e_steps, "api": "sq_probe_join (host C ABI), pinned host buffers", "partitions": T, "tiles": n_tiles},
             "gpu_launches": int(launches), "clocks": clocks,
             "digest": {"pairs": dg[0], "sum": dg[1], "xor": dg[2]},

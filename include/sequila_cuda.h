@@ -108,9 +108,9 @@ int32_t sq_probe_count(sq_stream* s, const sq_index* idx, const uint64_t* key_ha
  * The order of left hits inside one probe row is unspecified (as in the reference, where it
  * is coitrees' traversal order and every test sorts, IJ:1808).
  * capacity = number of elements left_idx_out/right_idx_out can hold (>= n_pairs).
- * With SQ_RLE_WIRE=1 in the environment right_idx crosses PCIe run-length encoded (the per-row counts, 4 B
- * per probe row instead of 4 B per pair) and is expanded into right_idx_out by the calling thread — the
- * expansion loop the reference runs at IJ:1611-1618; worthwhile only where GPUs share the host link. */
+ * right_idx crosses PCIe run-length encoded (the per-row counts, 4 B per probe row instead of 4 B per pair)
+ * and is expanded into right_idx_out by the calling thread while left_idx is still arriving — the expansion
+ * loop the reference runs at IJ:1611-1618.  SQ_RLE_WIRE=0 in the environment copies right_idx itself. */
 int32_t sq_probe_emit_pairs(sq_stream* s, uint32_t* left_idx_out, uint32_t* right_idx_out,
                             uint32_t* counts_out, uint64_t capacity);
 

@@ -4,6 +4,9 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "sq_internal.cuh"
 
@@ -478,37 +481,44 @@ static int32_t launch_emit(sq_stream* s, uint32_t* d_left, uint32_t* d_right, ui
 
 
 // right_idx[k] = the probe row of pair k: row i repeated counts[i] times (the reference's own expansion
-// loop, IJ:1611-1618).  Rows with few hits dominate, so a row is written as one 32-byte block of eight
-// copies and the cursor advances by its count; longer runs loop over blocks; the tail is filled exactly.
+// loop, IJ:1611-1618).  Rows with few hits dominate, so every row is written as one 64-byte block of sixteen
+// copies (branch-free for counts <= 16) and the cursor advances by its count, later rows overwrite the
+// excess; longer runs loop over 16-byte stores; the last sixteen pairs are filled exactly.
 static void expand_counts(const uint32_t* counts, uint32_t n_rows, uint32_t* right, uint64_t n_pairs) {
-  struct V8 { uint32_t v[8]; };
   uint64_t o = 0;
   uint32_t i = 0;
-  for (; i < n_rows && o + 8 <= n_pairs; ++i) {
-    const uint32_t c = counts[i];
-    if (c == 0) continue;
-    V8 b;
-    for (int k = 0; k < 8; ++k) b.v[k] = i;
-    if (c <= 8) {
-      memcpy(right + o, &b, sizeof b);  // may overshoot by up to 7 entries that later rows overwrite
+#if defined(__SSE2__)
+  if (n_pairs >= 16) {
+    const uint64_t safe = n_pairs - 16;
+    for (; i < n_rows && o <= safe; ++i) {
+      const uint32_t c = counts[i];
+      const __m128i v = _mm_set1_epi32(int(i));
+      __m128i* p = reinterpret_cast<__m128i*>(right + o);
+      _mm_storeu_si128(p, v);
+      _mm_storeu_si128(p + 1, v);
+      _mm_storeu_si128(p + 2, v);
+      _mm_storeu_si128(p + 3, v);
+      if (__builtin_expect(c > 16, 0)) {
+        uint64_t q = o + 16;
+        const uint64_t end = o + c;
+        for (; q + 4 <= end && q + 4 <= n_pairs; q += 4) _mm_storeu_si128(reinterpret_cast<__m128i*>(right + q), v);
+        for (; q < end; ++q) right[q] = i;
+      }
       o += c;
-    } else {
-      const uint64_t end = o + c;
-      for (; o + 8 <= end && o + 8 <= n_pairs; o += 8) memcpy(right + o, &b, sizeof b);
-      for (; o < end; ++o) right[o] = i;
     }
   }
-  for (; i < n_rows; ++i)  // the last few pairs: never write past n_pairs
+#endif
+  for (; i < n_rows; ++i)  // the tail (and the portable path): never write past n_pairs
     for (uint32_t k = 0; k < counts[i] && o < n_pairs; ++k) right[o++] = i;
 }
 
-// Opt-in (SQ_RLE_WIRE=1).  Measured on the B200 box: one host thread expands ~1 G pairs/s, so with four
-// partition threads per GPU the decode (20 ms per 80M pairs) is slower than copying right_idx itself over a
-// dedicated PCIe 5 x16 link (13.4 ms per step end to end vs 17.9 ms); it pays only where several GPUs share
-// the host link (8 GPUs on that box: 60 ms per step with plain copies).
+// On by default (SQ_RLE_WIRE=0 copies right_idx itself).  Measured on a B200 box with 16 host cores, 12.5M
+// probe rows / 80.6M pairs per step: one host thread decodes ~1 G pairs/s, so with 4 partition threads the
+// decode is the bottleneck (18.4 ms per step vs 13.7 ms with plain copies), with 8 it is not (11.4 ms vs
+// 13.7 ms); it pays most where several GPUs share the host link (8 GPUs: 60 ms per step with plain copies).
 static bool rle_on_the_wire() {
   const char* e = getenv("SQ_RLE_WIRE");
-  return e && atoi(e) != 0;
+  return !e || atoi(e) != 0;
 }
 
 static int32_t check_emit(sq_stream* s, const void* left, uint64_t capacity) {

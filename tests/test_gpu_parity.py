@@ -226,9 +226,10 @@ def test_error_paths(cuda_ctx):
     assert e.value.code == 5  # SQ_ECAPACITY
 
 
-def test_right_idx_run_length_encoded_on_the_wire(cuda_ctx, oracle, monkeypatch):
-    """SQ_RLE_WIRE=1: right_idx crosses PCIe as per-row counts and is expanded on the host."""
-    monkeypatch.setenv("SQ_RLE_WIRE", "1")
+@pytest.mark.parametrize("rle", ["1", "0"])
+def test_right_idx_wire_encodings(cuda_ctx, oracle, monkeypatch, rle):
+    """right_idx crosses PCIe as per-row counts and is expanded on the host (default), or as itself."""
+    monkeypatch.setenv("SQ_RLE_WIRE", rle)
     for name, scale in (("cfg2", 0.05), ("cfg3", 0.01), ("cfg4", 0.02)):
         b, p = sn.synth.CONFIGS[name](scale=scale)
         assert_same(oracle, cuda_ctx, b, p)
