@@ -30,50 +30,66 @@ __device__ __forceinline__ bool row_hits(uint32_t lo_word, uint32_t id, int32_t 
 
 
 // ---------------------------------------------------------------------------------------------
-// Walk in rounds (register path).  Lane L owns probe row L of the warp: `walking` = the row still has a
-// line to visit, `ln` = that line, `cnt` = its hits so far.  Every round the walking rows are compacted
-// (rank among walking rows -> step, group), each fetches ONE line with a cooperative 8-lane load, all
-// steps of the warp at once (8 independent requests per lane in flight): a warp waits for as many memory
-// round trips as its longest walk and executes only as many steps as it has (row, line) pairs.
-// inv8: 32 bytes of shared memory of this warp, 8-byte aligned.  stash: kStride words per row.
+// Walk in rounds.  Lane L owns probe row L of the warp: `walking` = the row still has a line to visit,
+// `ln` = that line, `cnt` = its hits so far.  Every round the walking rows are compacted (rank among
+// walking rows -> step, group), each fetches ONE line with a cooperative 8-lane load, all steps of the warp
+// at once (8 independent requests per lane in flight): a warp waits for as many memory round trips as its
+// longest walk and executes only as many steps as it has (row, line) pairs.
+// The kernel is bound by the LSU/MIO pipe as much as by memory latency (ncu: lsu data pipe 53 % busy, the
+// highest unit), so what a step needs of its row travels through ONE 16-byte shared-memory record instead
+// of a shuffle per field, and the line numbers of a round through two vector loads per group.
 // ---------------------------------------------------------------------------------------------
+struct __align__(16) RowState {
+  int32_t qs, qe;
+  uint32_t cnt_reach;  // [30:0] hits so far, [31] the last line said "an earlier row still reaches qs"
+  uint32_t pad;
+};
+struct __align__(16) WalkShared {
+  RowState row[32];   // indexed by owner lane
+  uint32_t line[32];  // line to fetch, indexed by slot = group * 8 + step
+  uint8_t inv[32];    // owner lane, indexed by slot
+};
+
 template <bool EMIT>
-__device__ __forceinline__ void walk_rounds(const IndexView& iv, uint32_t* stash, uint8_t* inv8, int32_t my_qs,
+__device__ __forceinline__ void walk_rounds(const IndexView& iv, uint32_t* stash, WalkShared& ws, int32_t my_qs,
                                             int32_t my_qe, uint32_t first, bool& walking, uint32_t& ln, uint32_t& cnt) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 3, sub = lane & 7, g0 = g * 8;
+  const uint4* __restrict__ my_lines = iv.lines + sub;
+  ws.row[lane] = RowState{my_qs, my_qe, 0u, 0u};
   for (;;) {
     const unsigned A = __ballot_sync(0xffffffffu, walking);
     if (A == 0) break;
     const int n_walk = __popc(A);
     const int r = __popc(A & ((1u << lane) - 1u));  // my rank: served in step r >> 2 by group r & 3
     __syncwarp();
-    if (walking) inv8[(r & 3) * 8 + (r >> 2)] = uint8_t(lane);
+    if (walking) {
+      const int slot = (r & 3) * 8 + (r >> 2);
+      ws.inv[slot] = uint8_t(lane);
+      ws.line[slot] = ln;
+    }
     __syncwarp();
-    const unsigned long long srcs = *reinterpret_cast<const unsigned long long*>(inv8 + g0);  // my group's 8 rows
+    const unsigned long long srcs = *reinterpret_cast<const unsigned long long*>(ws.inv + g0);  // my group's 8 rows
+    const uint4 la = *reinterpret_cast<const uint4*>(ws.line + g0), lb = *reinterpret_cast<const uint4*>(ws.line + g0 + 4);
+    const uint32_t lines8[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
     const int n_steps = (n_walk + 3) >> 2;
     uint4 v[8];
 #pragma unroll
-    for (int st = 0; st < 8; ++st) {
-      const int p = int(srcs >> (8 * st)) & 31;
-      const uint32_t lnp = __shfl_sync(0xffffffffu, ln, p);
-      v[st] = (4 * st + g < n_walk) ? __ldg(iv.lines + size_t(lnp) * 8 + sub) : make_uint4(0u, 0u, 0u, kEmptyRow);
-    }
-    bool cont = false;
+    for (int st = 0; st < 8; ++st)
+      if (st < n_steps)  // warp-uniform: later rounds have few steps
+        v[st] = (4 * st + g < n_walk) ? __ldg(my_lines + size_t(lines8[st]) * 8) : make_uint4(0u, 0u, 0u, kEmptyRow);
 #pragma unroll
     for (int st = 0; st < 8; ++st) {
       if (st >= n_steps) break;  // warp-uniform
       const int p = int(srcs >> (8 * st)) & 31;
       const bool valid = 4 * st + g < n_walk;
-      const int32_t qs = __shfl_sync(0xffffffffu, my_qs, p);
-      const int32_t qe = __shfl_sync(0xffffffffu, my_qe, p);
-      const uint32_t c0 = __shfl_sync(0xffffffffu, cnt, p);
+      const RowState rs = ws.row[p];
+      const uint32_t c0 = rs.cnt_reach & 0x7FFFFFFFu;
       const uint4 d = v[st];
       const int32_t base = int32_t(__shfl_sync(0xffffffffu, d.x, g0));
-      const int32_t exmax = int32_t(__shfl_sync(0xffffffffu, d.y, g0));
       const Slots s = slots_of(d, sub);
-      const bool ha = valid && row_hits(s.a_lo, s.a_id, base, qs, qe);
-      const bool hb = valid && row_hits(s.b_lo, s.b_id, base, qs, qe);
+      const bool ha = valid && row_hits(s.a_lo, s.a_id, base, rs.qs, rs.qe);
+      const bool hb = valid && row_hits(s.b_lo, s.b_id, base, rs.qs, rs.qe);
       const uint32_t ma = (__ballot_sync(0xffffffffu, ha) >> g0) & 0xFFu;
       const uint32_t mb = (__ballot_sync(0xffffffffu, hb) >> g0) & 0xFFu;
       if (EMIT) {
@@ -83,16 +99,17 @@ __device__ __forceinline__ void walk_rounds(const IndexView& iv, uint32_t* stash
         if (ha && pa < kSlots) stash[p * kStride + pa] = s.a_id;
         if (hb && pb < kSlots) stash[p * kStride + pb] = s.b_id;
       }
-      // hand the new count and "an earlier row still reaches qs" back to the owner lane
-      const uint32_t c1 = __shfl_sync(0xffffffffu, c0 + __popc(ma) + __popc(mb), (r & 3) * 8);
-      const unsigned reach = __ballot_sync(0xffffffffu, valid && exmax >= qs);
-      if (walking && (r >> 2) == st) {
-        cnt = c1;
-        cont = (reach >> ((r & 3) * 8)) & 1u;
-      }
+      // the group's first lane holds the line header: new count and "an earlier row still reaches qs"
+      if (sub == 0 && valid)
+        ws.row[p].cnt_reach = (c0 + __popc(ma) + __popc(mb)) | (int32_t(d.y) >= rs.qs ? 0x80000000u : 0u);
     }
-    walking = walking && cont && ln > first;
-    ln -= 1;
+    __syncwarp();
+    if (walking) {
+      const uint32_t cr = ws.row[lane].cnt_reach;
+      cnt = cr & 0x7FFFFFFFu;
+      walking = (cr >> 31) != 0u && ln > first;
+      ln -= 1;
+    }
   }
 }
 
@@ -103,7 +120,7 @@ __device__ __forceinline__ void walk_rounds(const IndexView& iv, uint32_t* stash
 // exclusive one.  Predecessor tiles must already be running (ticket order / resident persistent grid).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long chain_lookback(unsigned long long* chain_state, uint32_t tile,
-                                                              unsigned long long agg) {
+                                                              unsigned long long agg, uint32_t backoff_ns = 64) {
   const int lane = threadIdx.x & 31;
   if (lane == 0) atomicExch(chain_state + tile, (tile == 0 ? kFlagInc : kFlagAgg) | agg);
   unsigned long long excl = 0;
@@ -113,7 +130,9 @@ __device__ __forceinline__ unsigned long long chain_lookback(unsigned long long*
       const int64_t k = look - lane;
       unsigned long long x = kFlagInc;
       if (k >= 0) {
-        do { x = *reinterpret_cast<volatile unsigned long long*>(chain_state + k); } while ((x >> 62) == 0);
+        // back off while a predecessor has not published yet: a spinning warp takes issue slots away from
+        // the warps of the other CTAs on this SM that are doing the predecessors' work
+        while (((x = *reinterpret_cast<volatile unsigned long long*>(chain_state + k)) >> 62) == 0) __nanosleep(backoff_ns);
       }
       const unsigned inc_mask = __ballot_sync(0xffffffffu, (x >> 62) == 2);
       const int first_inc = inc_mask ? (__ffs(inc_mask) - 1) : 32;

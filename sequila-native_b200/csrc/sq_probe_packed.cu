@@ -62,13 +62,14 @@ k_probe_packed(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* 
                const int32_t* __restrict__ q_end, uint32_t n, uint32_t* __restrict__ cnt_out,
                unsigned long long* chain_state, unsigned int* ticket, unsigned long long* result,
                uint32_t* __restrict__ left_out, uint32_t* __restrict__ right_out, uint64_t capacity,
-               uint32_t n_tiles) {
+               uint32_t n_tiles, uint32_t backoff_ns) {
   constexpr int kPWarps = kPBlock / 32;
   __shared__ uint32_t s_stash[EMIT ? kPWarps * 32 * kStride : 1];
   __shared__ unsigned long long s_wtot[2][kPWarps];
   __shared__ unsigned long long s_base[2];
   __shared__ uint32_t s_bid;
   __shared__ __align__(8) uint8_t s_inv[kPWarps][32];
+  __shared__ WalkShared s_walk[kPWarps];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -118,7 +119,7 @@ k_probe_packed(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* 
     bool walking = sl.act;
     uint32_t ln = sl.line;  // next line of my row
     uint32_t cnt = 0;       // hits of my row so far
-    walk_rounds<EMIT>(iv, stash, s_inv[warp], my_qs, my_qe, sl.first, walking, ln, cnt);
+    walk_rounds<EMIT>(iv, stash, s_walk[warp], my_qs, my_qe, sl.first, walking, ln, cnt);
     if (i < n) cnt_out[i] = cnt;  // rle_right (interval_join.rs:1604)
 
     const uint32_t cincl = warp_incl_sum(cnt);  // a warp emits < 2^32 pairs unless rows hit > 2^27 builds each
@@ -142,7 +143,7 @@ k_probe_packed(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* 
       unsigned long long agg = 0;
 #pragma unroll
       for (int w = 0; w < kPWarps; ++w) agg += s_wtot[buf][w];
-      const unsigned long long excl = chain_lookback(chain_state, tile, agg);
+      const unsigned long long excl = chain_lookback(chain_state, tile, agg, backoff_ns);
       if (lane == 0) {
         s_base[buf] = excl;
         if (tile == n_tiles - 1) result[0] = excl + agg;
@@ -188,15 +189,17 @@ static void launch_packed_b(sq_stream* s, const IndexView& iv, const uint64_t* d
                             const int32_t* d_end, uint32_t n, uint32_t* cnt, unsigned long long* chain, unsigned int* ticket,
                             unsigned long long* result, uint32_t* d_left, uint32_t* d_right, uint64_t capacity) {
   const uint32_t n_tiles = (n + B - 1) / B;
+  uint32_t backoff = 64;
+  if (const char* e = getenv("SQ_BACKOFF_NS")) backoff = uint32_t(atoi(e));  // experiment knob
   if (!d_left)
     k_probe_packed<false, false, B, 2><<<(n_tiles + 1) / 2, B, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket,
-                                                                                result, nullptr, nullptr, 0, n_tiles);
+                                                                                result, nullptr, nullptr, 0, n_tiles, 0u);
   else if (d_right)
     k_probe_packed<true, true, B, 1><<<n_tiles, B, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket, result,
-                                                                    d_left, d_right, capacity, n_tiles);
+                                                                    d_left, d_right, capacity, n_tiles, backoff);
   else
     k_probe_packed<true, false, B, 1><<<n_tiles, B, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket, result,
-                                                                     d_left, nullptr, capacity, n_tiles);
+                                                                     d_left, nullptr, capacity, n_tiles, backoff);
 }
 
 int launch_packed(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
