@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsequila_cuda.so")
+LIB_PATH = os.environ.get("SQ_LIB_PATH") or os.path.join(_HERE, "libsequila_cuda.so")  # SQ_LIB_PATH: A/B experiments only
 
 SQ_OK, SQ_EINVAL, SQ_ECUDA, SQ_ENOMEM, SQ_ESTATE, SQ_ECAPACITY, SQ_ECAST = range(7)
 NULL_INDEX = 0xFFFFFFFF  # SQ_NULL_INDEX
