@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--shard-rows", type=int, default=SHARD_ROWS)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-partitions", type=int, default=8, help="host threads, one sq_stream each")
-    ap.add_argument("--e2e-tiles", type=int, default=32, help="probe sub-tiles per step (all partitions)")
+    ap.add_argument("--e2e-tiles", type=int, default=64, help="probe sub-tiles per step (all partitions)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-contigs", type=int, default=8)
     ap.add_argument("--cpu-sample-probes", type=int, default=2_000_000)
