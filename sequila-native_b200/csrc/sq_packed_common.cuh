@@ -63,6 +63,8 @@ __device__ __forceinline__ void walk_rounds(const IndexView& iv, uint32_t* stash
     const int n_walk = __popc(A);
     const int r = __popc(A & ((1u << lane) - 1u));  // my rank: served in step r >> 2 by group r & 3
     __syncwarp();
+    ws.line[lane] = 0u;  // slots past the last walking row fetch line 0 (always there) and are ignored
+    __syncwarp();
     if (walking) {
       const int slot = (r & 3) * 8 + (r >> 2);
       ws.inv[slot] = uint8_t(lane);
@@ -77,7 +79,7 @@ __device__ __forceinline__ void walk_rounds(const IndexView& iv, uint32_t* stash
 #pragma unroll
     for (int st = 0; st < 8; ++st)
       if (st < n_steps)  // warp-uniform: later rounds have few steps
-        v[st] = (4 * st + g < n_walk) ? __ldg(my_lines + size_t(lines8[st]) * 8) : make_uint4(0u, 0u, 0u, kEmptyRow);
+        v[st] = __ldg(my_lines + size_t(lines8[st]) * 8);
 #pragma unroll
     for (int st = 0; st < 8; ++st) {
       if (st >= n_steps) break;  // warp-uniform
