@@ -235,3 +235,33 @@ def test_right_idx_wire_encodings(cuda_ctx, oracle, monkeypatch, rle):
         assert_same(oracle, cuda_ctx, b, p)
     one = {"key": np.array([7], dtype=np.uint64), "start": np.array([5], dtype=np.int32), "end": np.array([10], dtype=np.int32)}
     assert_same(oracle, cuda_ctx, one, one)
+
+
+def test_concurrent_partitions_share_one_index(cuda_ctx, oracle):
+    """Many OS threads, one sq_stream each, probe ONE index at the same time (DataFusion partitions over a
+    CollectLeft build side, interval_join.rs:473-487, 528-556): every partition's pairs equal the oracle's."""
+    import concurrent.futures as cf
+    b, p = sn.synth.cfg5(scale=0.004)
+    idx = sn.CudaIndex.build(cuda_ctx, b["key"], b["start"], b["end"])
+    oidx = oracle.OracleIndex(b["key"], b["start"], b["end"])
+    n_parts, n_tiles = 8, 6
+    bounds = np.linspace(0, len(p["key"]), n_parts * n_tiles + 1).astype(int)
+
+    def partition(w):
+        st = sn.CudaStream(cuda_ctx)
+        out = []
+        for t in range(w, n_parts * n_tiles, n_parts):
+            lo, hi = bounds[t], bounds[t + 1]
+            k, s, e = p["key"][lo:hi], p["start"][lo:hi], p["end"][lo:hi]
+            n = st.probe_count(idx, k, s, e)
+            l, r, c = st.emit_pairs()
+            out.append((t, n, l.copy(), r.copy(), c.copy()))
+        return out
+
+    with cf.ThreadPoolExecutor(n_parts) as pool:
+        results = [x for part in pool.map(partition, range(n_parts)) for x in part]
+    assert len(results) == n_parts * n_tiles
+    for t, n, l, r, c in results:
+        lo, hi = bounds[t], bounds[t + 1]
+        ol, orr, oc = oidx.probe(p["key"][lo:hi], p["start"][lo:hi], p["end"][lo:hi])
+        assert n == len(ol) and np.array_equal(c, oc) and np.array_equal(canon(l, r), canon(ol, orr))
