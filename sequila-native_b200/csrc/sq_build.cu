@@ -39,20 +39,27 @@ struct HtStatus {
 __global__ void __launch_bounds__(256) k_ht_insert(const uint64_t* __restrict__ keys, uint64_t n,
                                                    uint64_t* __restrict__ ht_keys, uint32_t mask,
                                                    HtStatus* st) {
+  // per-CTA filter of keys this CTA has already seen in the table: a genomic join has a few dozen keys, so
+  // after its first iterations a CTA answers every row from shared memory (hash, one load, one compare)
+  __shared__ uint64_t s_seen[256];
+  s_seen[threadIdx.x] = kEmptyKey;
+  __syncthreads();
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
   // warp-uniform trip count so that the whole warp reaches the ballot together
   const uint64_t first = uint64_t(blockIdx.x) * blockDim.x + (threadIdx.x & ~31u);
   for (uint64_t i0 = first; i0 < n; i0 += stride) {
     const uint64_t i = i0 + (threadIdx.x & 31);
     const bool valid = i < n;
-    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-    if (!valid) continue;
-    const uint64_t key = keys[i];
-    // one lane per distinct key in the warp does the table work
-    const unsigned peers = __match_any_sync(vmask, key);
+    const uint64_t key = valid ? keys[i] : kEmptyKey;
+    if (valid && key == kEmptyKey) st->has_sentinel = 1;
+    const uint32_t h = uint32_t(mix64(key));
+    const bool miss = key != kEmptyKey && *reinterpret_cast<volatile uint64_t*>(&s_seen[h & 255u]) != key;
+    const unsigned mm = __ballot_sync(0xffffffffu, miss);
+    if (!miss) continue;
+    // one lane per distinct missing key in the warp does the table work
+    const unsigned peers = __match_any_sync(mm, key);
     if ((__ffs(peers) - 1) != int(threadIdx.x & 31)) continue;
-    if (key == kEmptyKey) { st->has_sentinel = 1; continue; }
-    uint32_t slot = uint32_t(mix64(key)) & mask;
+    uint32_t slot = h & mask;
     for (uint32_t step = 0; step <= mask; ++step) {
       uint64_t cur = *reinterpret_cast<volatile uint64_t*>(ht_keys + slot);
       if (cur == key) break;
@@ -69,6 +76,7 @@ __global__ void __launch_bounds__(256) k_ht_insert(const uint64_t* __restrict__ 
       slot = (slot + 1) & mask;
       if (step == mask) st->overflow = 1;
     }
+    *reinterpret_cast<volatile uint64_t*>(&s_seen[h & 255u]) = key;  // in the table now (or the table overflowed)
   }
 }
 
@@ -80,37 +88,39 @@ __global__ void __launch_bounds__(256) k_ht_assign(const uint64_t* __restrict__ 
   ht_ids[slot] = (ht_keys[slot] != kEmptyKey) ? atomicAdd(counter, 1u) : kNoKey;
 }
 
-// sort key = (key id << 32) | (start with the sign bit flipped), value = build row
+// sort key = (key id << 32) | (start with the sign bit flipped), value = (end << 32) | build row: the end
+// travels with the row through the sort (a gather of end[] through the permutation afterwards would be
+// 100M random 4-byte reads, 2 ms; 4 more bytes per row and pass in the sort cost a third of that)
 __global__ void __launch_bounds__(256) k_make_sort_keys(const uint64_t* __restrict__ keys,
-                                                        const int32_t* __restrict__ start, uint64_t n,
+                                                        const int32_t* __restrict__ start,
+                                                        const int32_t* __restrict__ end, uint64_t n,
                                                         const uint64_t* __restrict__ ht_keys,
                                                         const uint32_t* __restrict__ ht_ids,
                                                         uint32_t mask, uint32_t sentinel_id,
                                                         uint64_t* __restrict__ sort_key,
-                                                        uint32_t* __restrict__ sort_val) {
+                                                        uint64_t* __restrict__ sort_val) {
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const uint32_t id = ht_lookup(ht_keys, ht_ids, mask, sentinel_id, keys[i]);
     sort_key[i] = (uint64_t(id) << 32) | uint64_t(uint32_t(start[i]) ^ 0x80000000u);
-    sort_val[i] = uint32_t(i);
+    sort_val[i] = (uint64_t(uint32_t(end[i])) << 32) | uint64_t(uint32_t(i));
   }
 }
 
-// After the sort: write start[], row[], end[] (gathered through the permutation) and the
+// After the sort: write start[], row[], end[] (unpacked from the sorted key / value words) and the
 // segment boundaries seg_off[id] = first sorted position of key id.
 __global__ void __launch_bounds__(256) k_finalize(const uint64_t* __restrict__ sorted_key,
-                                                  const uint32_t* __restrict__ perm,
-                                                  const int32_t* __restrict__ end_in, uint64_t n,
+                                                  const uint64_t* __restrict__ sorted_val, uint64_t n,
                                                   int32_t* __restrict__ s_start, int32_t* __restrict__ s_end,
                                                   uint32_t* __restrict__ s_row,
                                                   uint32_t* __restrict__ seg_off, uint32_t n_keys) {
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
   for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride) {
     const uint64_t k = sorted_key[j];
-    const uint32_t r = perm[j];
+    const uint64_t v = sorted_val[j];
     s_start[j] = int32_t(uint32_t(k) ^ 0x80000000u);
-    s_row[j] = r;
-    s_end[j] = __ldg(end_in + r);
+    s_row[j] = uint32_t(v);
+    s_end[j] = int32_t(uint32_t(v >> 32));
     const uint32_t id = uint32_t(k >> 32);
     if (j == 0 || uint32_t(sorted_key[j - 1] >> 32) != id) seg_off[id] = uint32_t(j);
     if (j == n - 1) seg_off[n_keys] = uint32_t(n);
@@ -344,15 +354,34 @@ void free_index(sq_index* idx) {
   delete idx;
 }
 
+// Temporaries of a build (sort double buffers, scan tiles: several GB for 100M rows) come from the
+// stream-ordered allocator: the device's default pool keeps them between builds instead of returning them
+// to the driver (cudaMalloc / cudaFree of GB-sized blocks cost tens of milliseconds and synchronise).
 struct TmpFree {
+  cudaStream_t st;
   std::vector<void*> ptrs;
-  ~TmpFree() { for (void* p : ptrs) cudaFree(p); }
+  explicit TmpFree(cudaStream_t s) : st(s) {}
+  ~TmpFree() { for (void* p : ptrs) cudaFreeAsync(p, st); }
   template <class T> cudaError_t alloc(T** p, size_t bytes) {
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), bytes ? bytes : 16);
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(p), bytes ? bytes : 16, st);
     if (e == cudaSuccess) ptrs.push_back(*p);
     return e;
   }
 };
+
+static void keep_pool_memory(int device) {
+  static std::mutex mu;
+  static std::vector<int> done;
+  std::lock_guard<std::mutex> g(mu);
+  for (int d : done) if (d == device) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  cudaGetLastError();
+  done.push_back(device);
+}
 
 int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_start, const int32_t* d_end,
                        uint64_t n, cudaStream_t st, sq_index** out) {
@@ -365,7 +394,8 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
   idx->ctx = ctx;
   idx->n_rows = n;
   struct Guard { sq_index* p; ~Guard() { if (p) free_index(p); } } guard{idx};
-  TmpFree tmp;
+  keep_pool_memory(ctx->device);
+  TmpFree tmp(st);
 
   cudaEvent_t e0, e1;
   SQ_CUDA(E, cudaEventCreate(&e0));
@@ -416,14 +446,15 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
 
   if (n) {
     uint64_t *d_k0 = nullptr, *d_k1 = nullptr;
-    uint32_t *d_v0 = nullptr, *d_v1 = nullptr, *d_seg_off = nullptr;
+    uint64_t *d_v0 = nullptr, *d_v1 = nullptr;
+    uint32_t* d_seg_off = nullptr;
     SQ_CUDA(E, tmp.alloc(&d_k0, n * 8));
     SQ_CUDA(E, tmp.alloc(&d_k1, n * 8));
-    SQ_CUDA(E, tmp.alloc(&d_v0, n * 4));
-    SQ_CUDA(E, tmp.alloc(&d_v1, n * 4));
+    SQ_CUDA(E, tmp.alloc(&d_v0, n * 8));
+    SQ_CUDA(E, tmp.alloc(&d_v1, n * 8));
     SQ_CUDA(E, tmp.alloc(&d_seg_off, (size_t(n_keys) + 1) * 4));
     const int g = grid_for(n, 256, ctx->sm_count);
-    k_make_sort_keys<<<g, 256, 0, st>>>(d_key, d_start, n, idx->d_ht_keys, idx->d_ht_ids, cap - 1,
+    k_make_sort_keys<<<g, 256, 0, st>>>(d_key, d_start, d_end, n, idx->d_ht_keys, idx->d_ht_ids, cap - 1,
                                         idx->sentinel_id, d_k0, d_v0);
     SQ_CUDA(E, cudaGetLastError());
 
@@ -436,7 +467,7 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     SQ_CUDA(E, tmp.alloc(&d_temp, temp_bytes));
     SQ_CUDA(E, ::sq_cub::cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_k0, d_k1, d_v0, d_v1, n, 0, end_bit, st));
 
-    k_finalize<<<g, 256, 0, st>>>(d_k1, d_v1, d_end, n, idx->d_start, idx->d_end, idx->d_row, d_seg_off, n_keys);
+    k_finalize<<<g, 256, 0, st>>>(d_k1, d_v1, n, idx->d_start, idx->d_end, idx->d_row, d_seg_off, n_keys);
     SQ_CUDA(E, cudaGetLastError());
 
     // 3. running max of end inside each key segment
