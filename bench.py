@@ -428,7 +428,7 @@ def main():
         # B_probe of SURVEY.md §8(d) with u64 key hashes consumed on the device:
         # 16 B per probe row (key hash 8 + start 4 + end 4) + 12 B per emitted pair
         # (read the hit's build row id 4, write (left,right) 8).  One launch = the whole tile.
-        dom = "k_probe_packed" if launches <= args.steps else "k_probe_count+k_tile_scan+k_probe_write"
+        dom = "k_probe_packed" if idx.uses_packed else "k_probe_count+k_tile_scan+k_probe_write"
         b_dom = 16.0 * n_probe + 12.0 * n_pairs
         t_dom = phases["join"]
         achieved = b_dom / (t_dom * 1e-3) / 1e9 if t_dom > 0 else 0.0

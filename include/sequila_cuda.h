@@ -69,6 +69,9 @@ int32_t sq_index_build_device(sq_ctx* ctx, const uint64_t* d_key_hash, const int
 uint64_t sq_index_bytes(const sq_index* idx); /* device bytes held (build_mem_used gauge, IJ:631) */
 uint64_t sq_index_rows(const sq_index* idx);
 uint64_t sq_index_keys(const sq_index* idx);  /* distinct key hashes = number of per-key trees    */
+/* which probe kernels serve this index: 1 = the fused kernel over packed lines (every width < 65536, index
+ * far larger than L2 and shallow), 0 = count / scan / write over the SoA arrays */
+int32_t sq_index_uses_packed(const sq_index* idx);
 /* device time of the last build's kernels in ms (sort, scan, ...); 0 if unknown */
 float sq_index_build_ms(const sq_index* idx);
 void sq_index_free(sq_index* idx);

@@ -224,6 +224,7 @@ SQ_API int32_t sq_index_build(sq_ctx* ctx, const uint64_t* key_hash, const int32
 SQ_API uint64_t sq_index_bytes(const sq_index* idx) { return idx ? idx->bytes : 0; }
 SQ_API uint64_t sq_index_rows(const sq_index* idx) { return idx ? idx->n_rows : 0; }
 SQ_API uint64_t sq_index_keys(const sq_index* idx) { return idx ? idx->n_keys : 0; }
+SQ_API int32_t sq_index_uses_packed(const sq_index* idx) { return idx && use_packed(idx) ? 1 : 0; }
 SQ_API float sq_index_build_ms(const sq_index* idx) { return idx ? idx->build_ms : 0.f; }
 SQ_API void sq_index_free(sq_index* idx) { free_index(idx); }
 

@@ -17,6 +17,7 @@
 // Kernels here are HBM-bound streaming passes; the sort is CUB's radix sort (library code, like
 // cuBLAS for a GEMM) restricted to the significant bits 32 + ceil(log2(#keys)).
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <cstdlib>
 
@@ -280,13 +281,56 @@ __global__ void __launch_bounds__(kScanThreads) k_runmax_final(const uint64_t* _
 
 
 // ---------------------------------------------------------------------------------------------
-// Packed lines (see PackedLine in sq_internal.cuh): 8 threads per line, each writes its 16 bytes.
-// status[0] |= 1 when some row does not fit the narrow encoding (the index then keeps only the
-// SoA arrays); status[1] += lines a probe ending at this line's last start would walk back.
+// Packed lines (see sq_internal.cuh).  A line starts at the first row of a key segment, wherever the
+// start crosses a 65536-wide window (so every in-line start offset fits 16 bits whatever the gaps in the
+// data) and every 15 rows after the segment start: lines hold 1..15 rows, the lines of a segment are
+// contiguous.  k_line_flags marks line starts, an inclusive sum numbers the lines, k_line_first inverts
+// that, k_seg_lines / k_fill_dir_line translate segment starts and directory entries from rows to lines,
+// k_pack_lines writes the lines (8 threads per line, each its 16 bytes).
+// status[0] |= 1 when some width does not fit 16 bits (the index then keeps only the SoA arrays);
+// status[1] += lines a probe ending at this line's last start would walk back.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t start_window(int32_t x) { return (uint32_t(x) ^ 0x80000000u) >> 16; }
+
+__global__ void __launch_bounds__(256) k_line_flags(const uint64_t* __restrict__ sorted_key, const int32_t* __restrict__ s_start,
+                                                    uint64_t n, const SegMeta* __restrict__ meta, uint32_t* __restrict__ flag) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const uint32_t sb = meta[uint32_t(sorted_key[j] >> 32)].sb;
+    flag[j] = (j == sb || (j - sb) % kLineRows == 0 || start_window(s_start[j]) != start_window(s_start[j - 1])) ? 1u : 0u;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_line_first(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ line_incl,
+                                                    uint64_t n, uint32_t* __restrict__ line_first) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride) {
+    if (flag[j]) line_first[line_incl[j] - 1u] = uint32_t(j);
+    if (j == n - 1) line_first[line_incl[j]] = uint32_t(n);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_seg_lines(const uint32_t* __restrict__ line_incl, uint32_t n_keys, uint64_t n,
+                                                   SegMeta* __restrict__ meta) {
+  const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id > n_keys) return;
+  meta[id].line_base = id < n_keys ? line_incl[meta[id].sb] - 1u : line_incl[n - 1];  // sentinel entry: the line total
+}
+
+// dir_line[e] = line of the last row below directory entry e (= line holding the last start <= any qe of bin e - 1)
+__global__ void __launch_bounds__(256) k_fill_dir_line(const uint32_t* __restrict__ dir, uint64_t n_entries,
+                                                       const uint32_t* __restrict__ line_incl, uint32_t* __restrict__ dir_line) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t e = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n_entries; e += stride) {
+    const uint32_t r = dir[e];
+    dir_line[e] = r ? line_incl[r - 1u] - 1u : 0u;
+  }
+}
+
 __global__ void __launch_bounds__(256) k_pack_lines(const int32_t* __restrict__ s_start, const int32_t* __restrict__ s_end,
                                                     const int32_t* __restrict__ s_runmax, const uint32_t* __restrict__ s_row,
                                                     const SegMeta* __restrict__ meta, uint32_t n_keys, uint64_t n_lines,
+                                                    const uint32_t* __restrict__ line_first, const uint32_t* __restrict__ line_incl,
                                                     uint4* __restrict__ lines, unsigned long long* status) {
   const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const uint64_t line = t >> 3;
@@ -299,13 +343,14 @@ __global__ void __launch_bounds__(256) k_pack_lines(const int32_t* __restrict__ 
     if (uint64_t(meta[mid].line_base) <= line) lo = mid; else hi = mid;
   }
   const SegMeta m = meta[lo];
-  const uint32_t j0 = m.sb + uint32_t(line - m.line_base) * kLineRows;
+  const uint32_t j0 = line_first[line];
+  const uint32_t rows = line_first[line + 1] - j0;  // 1..15
   const int32_t base = s_start[j0];
   bool bad = false;
   auto enc = [&](uint32_t r, uint32_t* lo_word, uint32_t* id_word) {
+    if (r >= rows) { *lo_word = 0; *id_word = kEmptyRow; return; }
     const uint32_t j = j0 + r;
-    if (j >= m.se) { *lo_word = 0; *id_word = kEmptyRow; return; }
-    const int64_t ds = int64_t(s_start[j]) - int64_t(base);
+    const int64_t ds = int64_t(s_start[j]) - int64_t(base);  // < 65536: one window per line
     const int64_t w = int64_t(s_end[j]) - int64_t(s_start[j]);
     if (ds < 0 || ds > 65535 || w < 0 || w > 65535) bad = true;
     *lo_word = uint32_t(ds & 0xFFFF) | (uint32_t(w & 0xFFFF) << 16);
@@ -317,15 +362,13 @@ __global__ void __launch_bounds__(256) k_pack_lines(const int32_t* __restrict__ 
     v.y = uint32_t(j0 > m.sb ? s_runmax[j0 - 1] : INT32_MIN);
     enc(0, &v.z, &v.w);
     // statistic: how many earlier lines does a probe starting at this line's last start visit?
-    const uint32_t jl = min(j0 + kLineRows, m.se) - 1;
-    const int32_t qs = s_start[jl];
+    const int32_t qs = s_start[j0 + rows - 1];
     uint32_t a = m.sb, len = j0 - m.sb;  // first row in [sb, j0) with runmax >= qs
     while (len) {
       const uint32_t half = len >> 1;
       if (s_runmax[a + half] < qs) { a += half + 1; len -= half + 1; } else len = half;
     }
-    const uint32_t back = a < j0 ? (j0 - a + kLineRows - 1) / kLineRows : 0u;
-    if (back) atomicAdd(status + 1, (unsigned long long)back);
+    if (a < j0) atomicAdd(status + 1, (unsigned long long)(uint32_t(line) - (line_incl[a] - 1u)));
   } else {
     enc(2 * sub - 1, &v.x, &v.y);
     enc(2 * sub, &v.z, &v.w);
@@ -347,6 +390,7 @@ void free_index(sq_index* idx) {
   cudaFree(idx->d_start); cudaFree(idx->d_runmax); cudaFree(idx->d_end); cudaFree(idx->d_row);
   cudaFree(idx->d_meta); cudaFree(idx->d_dir); cudaFree(idx->d_ht_keys); cudaFree(idx->d_ht_ids);
   cudaFree(idx->d_lines);
+  cudaFree(idx->d_dir_line);
   for (auto& c : idx->columns) {
     if (c.owned) { cudaFree(c.d_values); cudaFree(c.d_offsets); }
     cudaFree(c.d_validity);
@@ -493,19 +537,16 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     std::vector<SegMeta> h_meta(n_keys);
     SQ_CUDA(E, cudaMemcpyAsync(h_meta.data(), idx->d_meta, size_t(n_keys) * sizeof(SegMeta), cudaMemcpyDeviceToHost, st));
     SQ_CUDA(E, cudaStreamSynchronize(st));
-    uint64_t dir_total = 0, line_total = 0;
-    h_meta.resize(size_t(n_keys) + 1);  // + sentinel entry carrying the line total
+    uint64_t dir_total = 0;
+    h_meta.resize(size_t(n_keys) + 1);  // + sentinel entry that will carry the line total
     for (uint32_t k = 0; k < n_keys; ++k) {
       SegMeta& m = h_meta[k];
       m.dir_base = uint32_t(dir_total);
       dir_total += uint64_t(m.nbins) + 1;
-      m.line_base = uint32_t(line_total);
-      line_total += (uint64_t(m.se - m.sb) + kLineRows - 1) / kLineRows;
     }
     if (dir_total >= 0xFFFFFFFFull) return fail(E, SQ_EINVAL, "bin directory too large");
     h_meta[n_keys] = SegMeta{};
     h_meta[n_keys].sb = h_meta[n_keys].se = uint32_t(n);
-    h_meta[n_keys].line_base = uint32_t(line_total);
     SQ_CUDA(E, cudaMemcpyAsync(idx->d_meta, h_meta.data(), (size_t(n_keys) + 1) * sizeof(SegMeta), cudaMemcpyHostToDevice, st));
     SQ_CUDA(E, cudaMalloc(&idx->d_dir, dir_total * 4));
     idx->bytes += dir_total * 4;
@@ -513,24 +554,49 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     k_fill_dir<<<g, 256, 0, st>>>(d_k1, idx->d_start, n, idx->d_meta, idx->d_dir);
     SQ_CUDA(E, cudaGetLastError());
 
-    // 5. packed lines for narrow indexes (every width and every in-line start offset < 65536)
+    // 5. packed lines for narrow indexes (every width < 65536)
+    uint32_t *d_flag = nullptr, *d_line_incl = nullptr, *d_line_first = nullptr;
+    SQ_CUDA(E, tmp.alloc(&d_flag, n * 4));
+    SQ_CUDA(E, tmp.alloc(&d_line_incl, n * 4));
+    k_line_flags<<<g, 256, 0, st>>>(d_k1, idx->d_start, n, idx->d_meta, d_flag);
+    SQ_CUDA(E, cudaGetLastError());
+    size_t scan_bytes = 0;
+    SQ_CUDA(E, ::sq_cub::cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, d_flag, d_line_incl, n, st));
+    void* d_scan_tmp = nullptr;
+    SQ_CUDA(E, tmp.alloc(&d_scan_tmp, scan_bytes));
+    SQ_CUDA(E, ::sq_cub::cub::DeviceScan::InclusiveSum(d_scan_tmp, scan_bytes, d_flag, d_line_incl, n, st));
+    uint32_t h_lines = 0;
+    SQ_CUDA(E, cudaMemcpyAsync(&h_lines, d_line_incl + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    SQ_CUDA(E, cudaStreamSynchronize(st));  // also: h_meta must outlive its async copy
+    const uint64_t line_total = h_lines;
+    SQ_CUDA(E, tmp.alloc(&d_line_first, (line_total + 1) * 4));
+    k_line_first<<<g, 256, 0, st>>>(d_flag, d_line_incl, n, d_line_first);
+    SQ_CUDA(E, cudaGetLastError());
+    k_seg_lines<<<(n_keys + 256) / 256, 256, 0, st>>>(d_line_incl, n_keys, n, idx->d_meta);
+    SQ_CUDA(E, cudaGetLastError());
+    SQ_CUDA(E, cudaMalloc(&idx->d_dir_line, dir_total * 4));
+    k_fill_dir_line<<<grid_for(dir_total, 256, ctx->sm_count), 256, 0, st>>>(idx->d_dir, dir_total, d_line_incl, idx->d_dir_line);
+    SQ_CUDA(E, cudaGetLastError());
     unsigned long long* d_pstat = nullptr;
     SQ_CUDA(E, tmp.alloc(&d_pstat, 16));
     SQ_CUDA(E, cudaMemsetAsync(d_pstat, 0, 16, st));
     SQ_CUDA(E, cudaMalloc(&idx->d_lines, line_total * 128));
     k_pack_lines<<<unsigned((line_total * 8 + 255) / 256), 256, 0, st>>>(idx->d_start, idx->d_end, idx->d_runmax, idx->d_row,
-                                                                          idx->d_meta, n_keys, line_total, idx->d_lines, d_pstat);
+                                                                          idx->d_meta, n_keys, line_total, d_line_first,
+                                                                          d_line_incl, idx->d_lines, d_pstat);
     SQ_CUDA(E, cudaGetLastError());
     unsigned long long h_pstat[2] = {0, 0};
     SQ_CUDA(E, cudaMemcpyAsync(h_pstat, d_pstat, 16, cudaMemcpyDeviceToHost, st));
-    SQ_CUDA(E, cudaStreamSynchronize(st));  // h_meta / h_pstat must outlive the async copies
+    SQ_CUDA(E, cudaStreamSynchronize(st));
     if (h_pstat[0]) {  // wide or inverted intervals: the SoA arrays serve this index
       cudaFree(idx->d_lines);
+      cudaFree(idx->d_dir_line);
       idx->d_lines = nullptr;
+      idx->d_dir_line = nullptr;
     } else {
       idx->n_lines = line_total;
       idx->mean_back_lines = float(double(h_pstat[1]) / double(line_total));
-      idx->bytes += line_total * 128;
+      idx->bytes += line_total * 128 + dir_total * 4;
     }
   }
   SQ_CUDA(E, cudaEventRecord(e1, st));

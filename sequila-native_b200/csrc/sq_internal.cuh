@@ -40,9 +40,9 @@ struct SegMeta {
   uint32_t pad1;
 };
 
-// Packed layout of the same sorted rows ("narrow" indexes: 0 <= end - start < 65536 for every row
-// and < 65536 between the first and last start of a line): 128-byte lines of 15 rows, key segments
-// padded to whole lines.  One cooperative 8-lane load (8 x 16 bytes = one L2 request) brings
+// Packed layout of the same sorted rows ("narrow" indexes: 0 <= end - start < 65536 for every row):
+// 128-byte lines of up to 15 rows; a line never crosses a key segment or a 65536-wide window of starts,
+// so in-line start offsets fit 16 bits whatever the gaps in the data.  One cooperative 8-lane load (8 x 16 bytes = one L2 request) brings
 //   lane 0      : { base_start, exmax, row0.lo, row0.id }
 //   lanes 1..7  : { row(2k-1).lo, row(2k-1).id, row(2k).lo, row(2k).id }
 // with row.lo = (start - base_start) | (end - start) << 16, row.id = build row (0xFFFFFFFF = empty
@@ -67,6 +67,7 @@ struct IndexView {
   uint32_t n_keys;
   uint32_t n_rows;
   const uint4* __restrict__ lines;      // packed lines (nullptr when the index is not "narrow")
+  const uint32_t* __restrict__ dir_line; // directory entry -> line holding the last row below it
 };
 
 #ifdef __CUDACC__
@@ -134,6 +135,7 @@ struct sq_index {
   uint32_t* d_dir = nullptr;
   uint64_t dir_bytes = 0;
   uint4* d_lines = nullptr;    // packed lines, or nullptr (wide / inverted intervals: SoA path only)
+  uint32_t* d_dir_line = nullptr;
   uint64_t n_lines = 0;
   float mean_back_lines = 0.f; // mean number of extra lines a probe landing on a line's last row walks back
   uint64_t* d_ht_keys = nullptr;
@@ -151,6 +153,7 @@ struct sq_index {
     v.ht_keys = d_ht_keys; v.ht_ids = d_ht_ids; v.ht_mask = ht_cap - 1; v.sentinel_id = sentinel_id;
     v.n_keys = n_keys; v.n_rows = uint32_t(n_rows);
     v.lines = d_lines;
+    v.dir_line = d_dir_line;
     return v;
   }
 };

@@ -45,9 +45,9 @@ __device__ __forceinline__ StartLine find_start_line(const IndexView& iv, uint32
   if (qe < m.min_start) return r;
   const uint32_t off = uint32_t(qe) - uint32_t(m.min_start);
   const uint32_t b = m.shift >= 32 ? 0u : (off >> m.shift);
-  // first row whose bin is > b: every row with start <= qe lies below it
-  const uint32_t r_end = b >= m.nbins ? m.se : __ldg(iv.dir + m.dir_base + b + 1);
-  r.line = m.line_base + (r_end - 1u - m.sb) / kLineRows;
+  // directory entry b + 1 = first row whose bin is > b: every row with start <= qe lies below it, and
+  // dir_line gives the line of the last such row directly
+  r.line = __ldg(iv.dir_line + m.dir_base + (b >= m.nbins ? m.nbins : b + 1u));
   r.first = m.line_base;
   r.act = true;
   return r;
@@ -175,9 +175,12 @@ bool use_packed(const sq_index* idx) {
   if (forced == 0) return false;
   if (forced == 1) return true;
   // Measured on B200: the fused kernel wins when the index is far larger than L2 (cfg5, 100M rows:
-  // 1.15 ms vs 1.83 ms per 12.5M probe rows) and loses on an L2-resident one (cfg2, 1M rows: 0.085
+  // 1.05 ms vs 1.83 ms per 12.5M probe rows) and loses on an L2-resident one (cfg2, 1M rows: 0.085
   // vs 0.067 ms), where the SoA kernels' loads are cache hits and the chained scan is pure overhead.
-  return idx->n_lines * 128ull > (64ull << 20);
+  // It also loses on deep overlap (cfg3 forced through it: 2.4 ms vs 1.3 ms): a row walks one line per
+  // round and rows with more than 32 hits are re-walked one at a time, so the index must be shallow —
+  // mean_back_lines is the build-time estimate of how many extra lines a probe walks.
+  return idx->n_lines * 128ull > (64ull << 20) && idx->mean_back_lines <= 1.5f;
 }
 
 // Count-only launches give every CTA two consecutive tiles (measured: 0.69 vs 0.77 ms per 12.5M rows, the

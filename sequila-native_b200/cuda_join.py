@@ -126,6 +126,7 @@ class CudaIndex:
     rows = property(lambda self: int(self._lib.sq_index_rows(self._h)))
     keys = property(lambda self: int(self._lib.sq_index_keys(self._h)))
     build_ms = property(lambda self: float(self._lib.sq_index_build_ms(self._h)))
+    uses_packed = property(lambda self: bool(self._lib.sq_index_uses_packed(self._h)))
 
 
 class CudaStream:
