@@ -33,6 +33,7 @@ extern "C" {
 #define SQ_ESTATE 4    /* call order violated (emit without count, ...) */
 #define SQ_ECAPACITY 5 /* caller buffer smaller than the result         */
 #define SQ_ECAST 6     /* value does not fit Int32 (IJ:1661-1672)       */
+#define SQ_EPARSE 7    /* malformed delimited text (sequila_scan.h)     */
 
 #define SQ_ABI_VERSION 1
 

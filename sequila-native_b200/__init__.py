@@ -7,11 +7,12 @@ There is no CPU fallback: importing :mod:`cuda_join` objects without the built l
 """
 from ._native import SequilaCudaError, LIB_PATH  # noqa: F401
 from .cuda_join import CudaContext, CudaIndex, CudaStream  # noqa: F401
+from .scan import CudaScan  # noqa: F401
 from . import synth  # noqa: F401
 from .session import Algorithm, SequilaConfig, apply_set, ParseAlgorithmError  # noqa: F401
 from . import intervals  # noqa: F401
 from .interval_join import IntervalJoinExec, HashJoinDesc, optimize  # noqa: F401
 
-__all__ = ["CudaContext", "CudaIndex", "CudaStream", "SequilaCudaError", "synth", "LIB_PATH", "Algorithm",
+__all__ = ["CudaContext", "CudaIndex", "CudaStream", "CudaScan", "SequilaCudaError", "synth", "LIB_PATH", "Algorithm",
            "SequilaConfig", "apply_set", "ParseAlgorithmError", "intervals", "IntervalJoinExec", "HashJoinDesc",
            "optimize"]

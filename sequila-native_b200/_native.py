@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SQ_LIB_PATH") or os.path.join(_HERE, "libsequila_cuda.so")  # SQ_LIB_PATH: A/B experiments only
 
-SQ_OK, SQ_EINVAL, SQ_ECUDA, SQ_ENOMEM, SQ_ESTATE, SQ_ECAPACITY, SQ_ECAST = range(7)
+SQ_OK, SQ_EINVAL, SQ_ECUDA, SQ_ENOMEM, SQ_ESTATE, SQ_ECAPACITY, SQ_ECAST, SQ_EPARSE = range(8)
 NULL_INDEX = 0xFFFFFFFF  # SQ_NULL_INDEX
 
 u64p = C.POINTER(C.c_uint64)
@@ -71,6 +71,31 @@ SIGNATURES = {
 
 
 
+class SqScanOptions(C.Structure):
+    """struct sq_scan_options (include/sequila_scan.h)"""
+    _fields_ = [("delimiter", C.c_uint8), ("has_header", C.c_uint8), ("comment", C.c_uint8), ("reserved", C.c_uint8),
+                ("col_key", C.c_int32), ("col_start", C.c_int32), ("col_end", C.c_int32), ("reserved2", C.c_int32),
+                ("start_minus", C.c_int64), ("end_minus", C.c_int64)]
+
+
+# every symbol include/sequila_scan.h declares
+SCAN_SIGNATURES = {
+    "sq_scan_text": (C.c_int32, [vp, vp, C.c_uint64, C.POINTER(SqScanOptions), C.POINTER(vp)]),
+    "sq_scan_text_device": (C.c_int32, [vp, vp, C.c_uint64, C.POINTER(SqScanOptions), C.POINTER(vp)]),
+    "sq_scan_rows": (C.c_uint64, [vp]),
+    "sq_scan_bytes": (C.c_uint64, [vp]),
+    "sq_scan_key_hash_device": (vp, [vp]),
+    "sq_scan_start_device": (vp, [vp]),
+    "sq_scan_end_device": (vp, [vp]),
+    "sq_scan_key_ids_device": (vp, [vp]),
+    "sq_scan_dict_size": (C.c_uint32, [vp]),
+    "sq_scan_dict_entry": (C.c_int32, [vp, C.c_uint32, C.POINTER(vp), u32p, u64p]),
+    "sq_scan_fetch": (C.c_int32, [vp, vp, vp, vp, vp, vp]),
+    "sq_scan_timing": (C.c_int32, [vp, f32p]),
+    "sq_scan_free": (None, [vp]),
+}
+
+
 class SqExecConfig(C.Structure):
     """struct sq_exec_config (include/sequila_exec.h)"""
     _fields_ = [("device", C.c_int32), ("n_on", C.c_int32), ("on_left", i32p), ("on_right", i32p),
@@ -112,7 +137,7 @@ def lib():
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
                 " (make -C sequila-native_b200/csrc). The cuda interval join has no CPU fallback.")
         L = C.CDLL(LIB_PATH)
-        for name, (res, args) in list(SIGNATURES.items()) + list(EXEC_SIGNATURES.items()):
+        for name, (res, args) in list(SIGNATURES.items()) + list(EXEC_SIGNATURES.items()) + list(SCAN_SIGNATURES.items()):
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args

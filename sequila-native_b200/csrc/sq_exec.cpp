@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "sequila_cuda.h"
+#include "sq_keyhash.h"
 
 #define SQ_API extern "C" __attribute__((visibility("default")))
 
@@ -38,11 +39,7 @@ struct Trace {
   }
 };
 
-inline uint64_t mix64(uint64_t x) {
-  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
-  x ^= x >> 27; x *= 0x94d049bb133111ebull;
-  x ^= x >> 31; return x;
-}
+using sqkey::mix64;  // the key hash is defined once, in sq_keyhash.h (shared with the device-side scanner)
 
 enum class Kind { Fixed, Utf8, LargeUtf8 };
 
@@ -194,7 +191,7 @@ inline bool bit_at(const uint8_t* bm, int64_t i) { return (bm[i >> 3] >> (i & 7)
 int hash_keys(sq_exec* e, const Side& side, const std::vector<int32_t>& on, const ArrowArray* batch,
               std::vector<uint64_t>* out) {
   const int64_t n = batch->length;
-  out->assign(size_t(n), mix64(1));  // on=[(1,1)]: every row carries the constant's hash
+  out->assign(size_t(n), sqkey::seed());  // on=[(1,1)]: every row carries the constant's hash
   for (int32_t col : on) {
     const ColType& t = side.cols[size_t(col)];
     const ColView v = view_of(batch, col);
@@ -204,7 +201,7 @@ int hash_keys(sq_exec* e, const Side& side, const std::vector<int32_t>& on, cons
       for (int64_t i = 0; i < n; ++i) {
         uint64_t raw = 0;
         memcpy(&raw, v.values + (v.offset + i) * t.width, t.width);
-        (*out)[size_t(i)] = mix64((*out)[size_t(i)] ^ (mix64(raw) + 0x9e3779b97f4a7c15ull));
+        (*out)[size_t(i)] = sqkey::fold((*out)[size_t(i)], sqkey::of_fixed(raw));
       }
     } else {
       // strings of up to 8 bytes (contig names) hash from one masked 8-byte load; longer ones byte by byte
@@ -230,12 +227,12 @@ int hash_keys(sq_exec* e, const Side& side, const std::vector<int32_t>& on, cons
           } else {
             memcpy(&raw, v.data + a, size_t(len));
           }
-          h = mix64(raw ^ (0x9e3779b97f4a7c15ull * uint64_t(len + 1)));
+          h = sqkey::of_string(raw, 0, uint64_t(len));
         } else {
-          h = 0xcbf29ce484222325ull;  // FNV-1a over the bytes
-          for (int64_t k = a; k < b; ++k) { h ^= v.data[k]; h *= 0x100000001b3ull; }
+          h = sqkey::kFnvOffset;  // FNV-1a over the bytes
+          for (int64_t k = a; k < b; ++k) { h ^= v.data[k]; h *= sqkey::kFnvPrime; }
         }
-        (*out)[size_t(i)] = mix64((*out)[size_t(i)] ^ (mix64(h) + 0x9e3779b97f4a7c15ull));
+        (*out)[size_t(i)] = sqkey::fold((*out)[size_t(i)], h);
       }
     }
   }

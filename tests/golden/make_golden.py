@@ -70,6 +70,9 @@ def main():
     golden = {
         "_generated_by": "tests/golden/make_golden.py from /root/reference (see docstring for file:line)",
         "reads": read_csv("reads.csv"),
+        # the fixture files byte for byte (scan-side parity: the device scanner and its oracle parse THESE bytes)
+        "reads_csv_text": open(os.path.join(REF, "testing/data/interval/reads.csv"), "rb").read().decode("ascii"),
+        "targets_csv_text": open(os.path.join(REF, "testing/data/interval/targets.csv"), "rb").read().decode("ascii"),
         "targets": read_csv("targets.csv"),
         "equi_rows": table_rows(fn_body(it, "fn expected_equi()")),
         "range_rows": table_rows(fn_body(it, "fn expected_range()")),

@@ -37,6 +37,12 @@ def test_library_exports_every_declared_symbol():
     missing = [x for x in declared_exec if not hasattr(lib, x)]
     assert not missing, missing
     assert sorted(_native.EXEC_SIGNATURES) == declared_exec
+    # and the scan side (delimited text -> device columns), include/sequila_scan.h
+    declared_scan = [x for x in header_symbols("sequila_scan.h") if x.startswith("sq_scan_")]
+    assert "sq_scan_text" in declared_scan and "sq_scan_key_ids_device" in declared_scan
+    missing = [x for x in declared_scan if not hasattr(lib, x)]
+    assert not missing, missing
+    assert sorted(_native.SCAN_SIGNATURES) == declared_scan
 
 
 def test_abi_version_and_no_fallback_without_gpu():

@@ -1,0 +1,125 @@
+"""Measurement of the scan side (include/sequila_scan.h): BED text -> device columns.
+
+    python tools/time_scan.py [--rows 20000000] [--out gpurun_out/scan.json]
+
+Workload: the cfg5 build-side generator's rows (hg38-weighted contigs, widths U{50..150}) written as a BED file
+(`contig \\t start \\t end \\n`, what queries/q1-coitrees.sql reads), larger than L2.
+Reports, in one JSON line:
+  * device: CUDA-event time of the locate + parse kernels and of the id assignment on text resident in HBM,
+    as text GB/s, rows/s and the fraction of the measured HBM peak on the ALGORITHMIC bytes
+    (text read once + 20 B/row written: key hash 8, start 4, end 4, dictionary id 4);
+  * host: wall time of sq_scan_text on a host buffer (H2D of the text included);
+  * cpu: pyarrow.csv.read_csv of the same bytes (Arrow C++ reader, the sibling of the arrow-rs reader
+    DataFusion uses; NOT the reference itself) with all cores and with one thread, plus hashing nothing —
+    the reference additionally hashes the contig strings per row and casts the BIGINT columns;
+  * q1: scan both sides + build + `count(1)` of the overlap join, file bytes to count.
+Checked: the scanned columns equal the generator's arrays."""
+import argparse
+import io
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import sequila_native_b200 as sn  # noqa: E402
+
+
+def bed_bytes(table) -> bytes:
+    import pyarrow as pa
+    import pyarrow.csv as pacsv
+    names = pa.array(sn.synth.CONTIG_NAMES)
+    contig = pa.DictionaryArray.from_arrays(pa.array(table["contig"].astype(np.int32)), names).cast(pa.string())
+    t = pa.table({"contig": contig, "start": pa.array(table["start"]), "end": pa.array(table["end"])})
+    buf = io.BytesIO()
+    pacsv.write_csv(t, buf, pacsv.WriteOptions(include_header=False, delimiter="\t", quoting_style="none"))
+    return buf.getvalue()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=20_000_000)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    b, p = sn.synth.cfg5(nb=a.rows, np_=a.rows // 4)
+    tb, tp = bed_bytes(b), bed_bytes(p)
+    ctx = sn.CudaContext(0)
+    st = sn.CudaStream(ctx)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    # device-resident text: kernels only
+    d_text = torch.frombuffer(bytearray(tb), dtype=torch.uint8).cuda()
+    kern, ids = [], []
+    for i in range(a.reps + 2):
+        flush.zero_()
+        torch.cuda.synchronize()
+        sc = sn.CudaScan.from_text(st, d_text)
+        if i >= 2:
+            _, k_ms, i_ms = sc.timing_ms
+            kern.append(k_ms)
+            ids.append(i_ms)
+        if i == 0:
+            k, s, e, di = sc.fetch()
+            assert np.array_equal(s, b["start"]) and np.array_equal(e, b["end"])
+            assert [sc.dictionary[j].decode() for j in di[:100000]] == [sn.synth.CONTIG_NAMES[c] for c in b["contig"][:100000]]
+            assert len(set(zip(k[:100000].tolist(), b["contig"][:100000].tolist()))) == len(set(b["contig"][:100000].tolist()))
+        del sc
+    dev_ms = float(np.mean(kern) + np.mean(ids))
+    alg_bytes = len(tb) + 20 * a.rows
+    # host text: what a caller with a file in memory pays
+    host = []
+    for i in range(3):
+        t0 = time.perf_counter()
+        sc = sn.CudaScan.from_text(st, tb)
+        host.append((time.perf_counter() - t0) * 1e3)
+        h2d_ms = sc.timing_ms[0]
+        del sc
+    # q1 shape: file bytes -> count(1)
+    t0 = time.perf_counter()
+    sa = sn.CudaScan.from_text(st, tb)
+    sp = sn.CudaScan.from_text(st, tp)
+    idx = sa.build_index(ctx)
+    n_pairs = sp.probe_count(st, idx)
+    q1_ms = (time.perf_counter() - t0) * 1e3
+    # CPU reader beside it
+    import pyarrow.csv as pacsv
+    cpu = {}
+    for threads in (True, False):
+        best = 1e30
+        for _ in range(2):
+            t0 = time.perf_counter()
+            t = pacsv.read_csv(io.BytesIO(tb), read_options=pacsv.ReadOptions(use_threads=threads, column_names=["c", "s", "e"]),
+                               parse_options=pacsv.ParseOptions(delimiter="\t"))
+            best = min(best, time.perf_counter() - t0)
+        assert t.num_rows == a.rows
+        cpu["all_cores" if threads else "one_thread"] = best * 1e3
+    out = {
+        "what": "scan side: BED text -> device columns (key hash, start, end, dictionary id)",
+        "rows": a.rows, "text_bytes": len(tb), "bytes_per_row": len(tb) / a.rows,
+        "device": {"parse_ms": float(np.mean(kern)), "ids_ms": float(np.mean(ids)), "ms": dev_ms,
+                   "text_GBps": len(tb) / dev_ms / 1e6, "rows_per_s": a.rows / dev_ms * 1e3,
+                   "roofline": {"bound": "hbm", "algorithmic_bytes": alg_bytes, "achieved": alg_bytes / dev_ms / 1e6,
+                                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg_bytes / dev_ms / 1e6 / peaks["hbm_gbs"]}},
+        "host": {"ms": float(min(host)), "h2d_ms": float(h2d_ms), "rows_per_s": a.rows / min(host) * 1e3,
+                 "text_GBps": len(tb) / min(host) / 1e6, "note": "pageable host buffer; H2D of the text inside"},
+        "cpu_reader": {"kind": "pyarrow.csv.read_csv (Arrow C++), not the reference", "cores": os.cpu_count(),
+                       "all_cores_ms": cpu["all_cores"], "one_thread_ms": cpu["one_thread"],
+                       "all_cores_rows_per_s": a.rows / cpu["all_cores"] * 1e3},
+        "q1_shape": {"build_rows": a.rows, "probe_rows": a.rows // 4, "pairs": int(n_pairs), "ms_file_bytes_to_count": q1_ms},
+    }
+    line = json.dumps(out)
+    print(line)
+    if a.out:
+        with open(a.out, "w") as f:
+            f.write(line + "\n")
+
+
+if __name__ == "__main__":
+    main()
