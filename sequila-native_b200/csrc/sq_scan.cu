@@ -3,15 +3,16 @@
 // evaluate_as_i32 do on the host in the reference (queries/q1-coitrees.sql:6-14, interval_join.rs:1037,
 // 1211, 1661-1672).
 //
-//   k_scan_count   every thread owns 32 bytes of text: newline mask (4 bytes per instruction), row
-//                  starts = bytes behind a newline that do not open an empty / comment row; per 8 KB
+//   k_scan_count   every thread owns 64 bytes of text: newline mask (4 bytes per instruction), row
+//                  starts = bytes behind a newline that do not open an empty / comment row; per 16 KB
 //                  tile the number of row starts
 //   (exclusive scan of the tile counts: launch_scan_u64)
-//   k_scan_parse   same row starts, block scan -> row number; the thread that owns a row's first byte
-//                  parses the row forward (fields, integers, key bytes -> key hash) and writes
-//                  key_hash / start / end of that row; the key's (hash -> first text offset) goes into
-//                  a small L2-resident open-addressing table (read before the atomic: after the first
-//                  few rows of a contig no atomic is issued)
+//   k_scan_parse   the tile's text is staged in shared memory on the way to the same row starts, which a
+//                  block scan compacts into a row list; the CTA's threads take the rows round-robin
+//                  (neighbouring lanes = neighbouring rows: shared-memory bytes in, coalesced column
+//                  stores out), parse field by field (key bytes -> key hash, BIGINT fields -> checked
+//                  Int32) and note (hash -> first text offset) of the key in a per-CTA shared-memory
+//                  table that is flushed to a small global table once per CTA
 //   k_scan_ids     dictionary id per row (ids = order of first occurrence, assigned on the host from
 //                  the table, a few thousand entries at most for genomes)
 // Byte work bounded by HBM: the text is read twice (count, parse), 16-20 bytes per row are written.
@@ -44,9 +45,10 @@ struct sq_scan {
 namespace sq {
 
 constexpr int kScanBlock = 256;
-constexpr int kScanChunk = 32;  // bytes of text per thread
-constexpr uint64_t kScanTile = uint64_t(kScanBlock) * kScanChunk;
+constexpr int kScanChunk = 64;  // bytes of text per thread
+constexpr uint32_t kScanTile = uint32_t(kScanBlock) * kScanChunk;  // 16 KB of text per CTA
 constexpr unsigned long long kNoError = ~0ull;
+constexpr int kLocalDict = 64;  // slots of the per-CTA key table
 
 #ifdef __CUDACC__
 
@@ -74,13 +76,51 @@ __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* s_
   return (warp ? s_w[warp - 1] : 0u) + inc - v;
 }
 
+__device__ __forceinline__ uint32_t newline_bits(const uint4& a, const uint4& b) {
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t m = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t eq = __vcmpeq4(w[k], 0x0a0a0a0au) & 0x01010101u;  // one flag bit per matching byte
+    m |= ((eq * 0x01020408u) >> 24) << (4 * k);                      // the four flags side by side
+  }
+  return m;
+}
+
+// The thread's 64 bytes of text (bytes behind the end of the text read as '\n'): the two row-start masks of its
+// halves; `keep`, when given, receives the bytes (the tile staged in shared memory).
+__device__ __forceinline__ void chunk_row_starts(const uint8_t* __restrict__ text, uint64_t n, uint64_t q0, uint8_t comment,
+                                                 uint4* keep, uint32_t* m_lo, uint32_t* m_hi) {
+  uint4 v[4];
+  if (q0 + kScanChunk <= n) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = __ldg(reinterpret_cast<const uint4*>(text + q0) + k);
+  } else {
+    uint8_t* bytes = reinterpret_cast<uint8_t*>(v);
+    for (int k = 0; k < kScanChunk; ++k) bytes[k] = q0 + k < n ? __ldg(text + q0 + k) : uint8_t('\n');
+  }
+  if (keep) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) keep[k] = v[k];
+  }
+  *m_lo = *m_hi = 0u;
+  if (q0 >= n) return;
+  const TextSrc src{text, n};
+  const uint32_t nl_lo = newline_bits(v[0], v[1]), nl_hi = newline_bits(v[2], v[3]);
+  const uint64_t left = n - q0;
+  const bool prev_nl = q0 == 0 || __ldg(text + q0 - 1) == '\n';
+  *m_lo = row_starts_from_newlines(src, q0, nl_lo, prev_nl, left >= 32 ? 32u : uint32_t(left), comment);
+  if (left > 32) *m_hi = row_starts_from_newlines(src, q0 + 32, nl_hi, (nl_lo >> 31) != 0u, left >= 64 ? 32u : uint32_t(left - 32), comment);
+}
+
 __global__ void __launch_bounds__(kScanBlock) k_scan_count(const uint8_t* __restrict__ text, uint64_t n, uint8_t comment,
                                                            unsigned long long* __restrict__ tile_rows) {
   __shared__ uint32_t s_w[32];
   const uint64_t q0 = uint64_t(blockIdx.x) * kScanTile + uint64_t(threadIdx.x) * kScanChunk;
-  const uint32_t c = __popc(row_start_mask32(text, n, q0, comment));
+  uint32_t m_lo, m_hi;
+  chunk_row_starts(text, n, q0, comment, nullptr, &m_lo, &m_hi);
   uint32_t total;
-  block_excl_scan_u32(c, s_w, &total);
+  block_excl_scan_u32(__popc(m_lo) + __popc(m_hi), s_w, &total);
   if (threadIdx.x == 0) tile_rows[blockIdx.x] = total;
 }
 
@@ -130,35 +170,85 @@ __device__ __forceinline__ uint32_t dict_find(const DictTable& t, uint64_t key) 
   return 0xFFFFFFFFu;
 }
 
+// per-CTA key table in shared memory: the rows of one tile carry a handful of distinct keys (one, in a sorted
+// BED file), so the global table sees a few operations per CTA instead of one per row — every row of the text
+// reading the same 24 table words made those L2 lines the hot spot of the kernel
+__device__ __forceinline__ bool local_note(unsigned long long* s_keys, unsigned long long* s_vals, uint64_t key,
+                                           unsigned long long v) {
+  if (key == kEmptyKey) return false;
+  uint32_t slot = uint32_t(key >> 17) & (kLocalDict - 1);
+  for (int step = 0; step < kLocalDict; ++step) {
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(s_keys + slot);
+    if (cur == kEmptyKey) cur = atomicCAS(s_keys + slot, (unsigned long long)kEmptyKey, (unsigned long long)key);
+    if (cur == kEmptyKey || cur == key) {
+      if (*reinterpret_cast<volatile unsigned long long*>(s_vals + slot) > v) atomicMin(s_vals + slot, v);
+      return true;
+    }
+    slot = (slot + 1u) & (kLocalDict - 1);
+  }
+  return false;  // more distinct keys in this tile than slots: the caller goes to the global table
+}
+
+// Locate + parse: the tile's text goes to shared memory on the way to the newline masks, the row starts of the
+// tile are compacted into a list (block scan), and the CTA's threads take the rows of that list round-robin:
+// neighbouring lanes parse neighbouring rows (shared-memory bytes, coalesced column stores), whatever the
+// row lengths.
 __global__ void __launch_bounds__(kScanBlock)
 k_scan_parse(const uint8_t* __restrict__ text, uint64_t n, ScanOpts o, const unsigned long long* __restrict__ tile_base,
              uint64_t n_rows, uint64_t* __restrict__ key_out, int32_t* __restrict__ start_out,
              int32_t* __restrict__ end_out, DictTable dict, unsigned long long* err_off) {
+  __shared__ uint4 s_text[kScanTile / 16];
+  __shared__ uint16_t s_row[kScanTile / 2];  // a row is at least one byte and its newline
   __shared__ uint32_t s_w[32];
-  const uint64_t q0 = uint64_t(blockIdx.x) * kScanTile + uint64_t(threadIdx.x) * kScanChunk;
-  uint32_t m = row_start_mask32(text, n, q0, o.comment);
+  __shared__ unsigned long long s_dkeys[kLocalDict], s_dvals[kLocalDict];
+  const uint64_t tile0 = uint64_t(blockIdx.x) * kScanTile;
+  const uint64_t q0 = tile0 + uint64_t(threadIdx.x) * kScanChunk;
+  if (threadIdx.x < kLocalDict) {
+    s_dkeys[threadIdx.x] = kEmptyKey;
+    s_dvals[threadIdx.x] = ~0ull;
+  }
+  uint32_t m_lo, m_hi;
+  chunk_row_starts(text, n, q0, o.comment, s_text + threadIdx.x * (kScanChunk / 16), &m_lo, &m_hi);
   uint32_t total;
-  const uint32_t excl = block_excl_scan_u32(__popc(m), s_w, &total);
-  uint64_t row = tile_base[blockIdx.x] + excl;
-  while (m) {
-    const int j = __ffs(m) - 1;
-    m &= m - 1;
-    uint64_t r = row++;
+  uint32_t at = block_excl_scan_u32(__popc(m_lo) + __popc(m_hi), s_w, &total);
+  while (m_lo) {
+    s_row[at++] = uint16_t(threadIdx.x * kScanChunk + (__ffs(m_lo) - 1));
+    m_lo &= m_lo - 1;
+  }
+  while (m_hi) {
+    s_row[at++] = uint16_t(threadIdx.x * kScanChunk + 32 + (__ffs(m_hi) - 1));
+    m_hi &= m_hi - 1;
+  }
+  __syncthreads();
+  const TileSrc src{reinterpret_cast<const uint8_t*>(s_text), uint32_t(__cvta_generic_to_shared(s_text)), tile0, kScanTile,
+                    TextSrc{text, n}};
+  const uint64_t first = tile_base[blockIdx.x];
+  for (uint32_t k = threadIdx.x; k < total; k += kScanBlock) {
+    uint64_t r = first + k;
     if (o.has_header) {
       if (r == 0) continue;  // the header row
       r -= 1;
     }
     if (r >= n_rows) continue;
-    const RowResult res = parse_row(text, n, q0 + j, o);
+    const uint64_t q = tile0 + s_row[k];
+    // every row but the tile's last ends (newline included) in front of the next row start, i.e. inside the tile
+    const RowResult res = k + 1 < total ? parse_row(SmemSrc{src.tile_saddr, tile0}, uint32_t(s_row[k]), o)
+                                        : parse_row(src, uint32_t(s_row[k]), o);
     if (res.err != kRowOk) {
-      atomicMin(err_off, (unsigned long long)(q0 + j));  // offsets grow with the row number: min = first bad row
+      atomicMin(err_off, (unsigned long long)q);  // offsets grow with the row number: min = first bad row
       continue;
     }
     key_out[r] = res.key;
     start_out[r] = res.start;
     end_out[r] = res.end;
-    if (o.col_key >= 0) dict_note(dict, res.key, ((unsigned long long)res.key_off << 16) | res.key_len);
+    if (o.col_key >= 0) {
+      const unsigned long long v = ((unsigned long long)res.key_off << 16) | res.key_len;
+      if (!local_note(s_dkeys, s_dvals, res.key, v)) dict_note(dict, res.key, v);
+    }
   }
+  if (o.col_key < 0) return;
+  __syncthreads();
+  if (threadIdx.x < kLocalDict && s_dkeys[threadIdx.x] != kEmptyKey) dict_note(dict, s_dkeys[threadIdx.x], s_dvals[threadIdx.x]);
 }
 
 __global__ void __launch_bounds__(256) k_scan_ids(const uint64_t* __restrict__ key, uint64_t n_rows, DictTable dict,
@@ -205,7 +295,7 @@ int diagnose(sq_stream* s, const uint8_t* d_text, uint64_t n, uint64_t off, cons
   std::vector<uint8_t> win(len);
   SQ_CUDA(E, cudaMemcpyAsync(win.data(), d_text + off, len, cudaMemcpyDeviceToHost, s->stream));
   SQ_CUDA(E, cudaStreamSynchronize(s->stream));
-  const RowResult r = parse_row(win.data(), len, 0, o);
+  const RowResult r = parse_row(TextSrc{win.data(), len}, 0, o);
   const std::string row = printable(win.data(), len);
   switch (r.err) {
     case kRowCastStart:
@@ -245,9 +335,10 @@ int scan_device(sq_stream* s, const uint8_t* d_text, const uint8_t* h_text, uint
     return fail(E, SQ_EINVAL, "the key column cannot also be an interval column");
   if (reinterpret_cast<uintptr_t>(d_text) & 15u) return fail(E, SQ_EINVAL, "device text must be 16-byte aligned");
 
-  cudaEvent_t ev[4];
+  // [0,1] locate (count + tile scan)  [2,3] parse  [4,5] id kernel: kernels only, allocations stay outside
+  cudaEvent_t ev[6];
   for (auto& e : ev) SQ_CUDA(E, cudaEventCreate(&e));
-  struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 4; ++i) cudaEventDestroy(e[i]); } } evg{ev};
+  struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 6; ++i) cudaEventDestroy(e[i]); } } evg{ev};
 
   auto* sc = new sq_scan();
   sc->ctx = s->ctx;
@@ -256,7 +347,7 @@ int scan_device(sq_stream* s, const uint8_t* d_text, const uint8_t* h_text, uint
   const uint64_t n_tiles64 = (n + kScanTile - 1) / kScanTile;
   if (n_tiles64 > 0x7FFFFFFFull) return fail(E, SQ_EINVAL, "text too large for one scan (%llu bytes)", (unsigned long long)n);
   const uint32_t n_tiles = uint32_t(n_tiles64);
-  SQ_CUDA(E, cudaEventRecord(ev[0], s->stream));
+  if (ev_begin) SQ_CUDA(E, cudaEventRecord(ev[0], s->stream));
   uint64_t total_rows = 0;
   DeviceTemp tiles, tot;
   if (n_tiles) {
@@ -264,11 +355,19 @@ int scan_device(sq_stream* s, const uint8_t* d_text, const uint8_t* h_text, uint
     SQ_CUDA(E, cudaMalloc(&tot.p, 64));
     auto* d_tiles = static_cast<unsigned long long*>(tiles.p);
     auto* d_tot = static_cast<unsigned long long*>(tot.p);
+    float h2d = 0.f;
+    if (ev_begin) {  // the text's host-to-device copy is over here
+      SQ_CUDA(E, cudaEventSynchronize(ev[0]));
+      cudaEventElapsedTime(&h2d, ev_begin, ev[0]);
+    }
+    sc->ms[0] = h2d;
+    SQ_CUDA(E, cudaEventRecord(ev[0], s->stream));
     k_scan_count<<<n_tiles, kScanBlock, 0, s->stream>>>(d_text, n, o.comment, d_tiles);
     SQ_CUDA(E, cudaGetLastError());
     s->launches += 1;
     int rc;
     if ((rc = launch_scan_u64(s, d_tiles, n_tiles, d_tot))) return rc;
+    SQ_CUDA(E, cudaEventRecord(ev[1], s->stream));
     SQ_CUDA(E, cudaMemcpyAsync(&total_rows, d_tot, 8, cudaMemcpyDeviceToHost, s->stream));
     SQ_CUDA(E, cudaStreamSynchronize(s->stream));
   }
@@ -307,9 +406,11 @@ int scan_device(sq_stream* s, const uint8_t* d_text, const uint8_t* h_text, uint
     dict.mask = cap - 1;
     dict.n_distinct = reinterpret_cast<unsigned int*>(d_flags + 1);
     dict.overflow = reinterpret_cast<unsigned int*>(d_flags + 2);
+    SQ_CUDA(E, cudaEventRecord(ev[2], s->stream));
     k_scan_parse<<<n_tiles, kScanBlock, 0, s->stream>>>(d_text, n, o, static_cast<unsigned long long*>(tiles.p), n_rows,
                                                          sc->d_key, sc->d_start, sc->d_end, dict, d_flags);
     SQ_CUDA(E, cudaGetLastError());
+    SQ_CUDA(E, cudaEventRecord(ev[3], s->stream));
     s->launches += 1;
     unsigned long long h_flags[3];
     SQ_CUDA(E, cudaMemcpyAsync(h_flags, d_flags, 24, cudaMemcpyDeviceToHost, s->stream));
@@ -319,8 +420,7 @@ int scan_device(sq_stream* s, const uint8_t* d_text, const uint8_t* h_text, uint
     if (cap >= (1u << 28)) return fail(E, SQ_EINVAL, "more than 2^27 distinct keys");
     cap <<= 4;  // the key column has more distinct values than the table holds: again with a larger one
   }
-  SQ_CUDA(E, cudaEventRecord(ev[1], s->stream));
-
+  bool ids_timed = false;
   if (n_rows && o.col_key >= 0) {
     h_keys.resize(cap + 1);
     h_vals.resize(cap + 1);
@@ -348,15 +448,21 @@ int scan_device(sq_stream* s, const uint8_t* d_text, const uint8_t* h_text, uint
     SQ_CUDA(E, cudaMemcpyAsync(dict.vals, h_vals.data(), size_t(cap + 1) * 8, cudaMemcpyHostToDevice, s->stream));
     const uint64_t want = (n_rows + 255) / 256;
     const uint64_t gcap = uint64_t(s->ctx->sm_count) * 16;
+    SQ_CUDA(E, cudaEventRecord(ev[4], s->stream));
     k_scan_ids<<<int(std::min(want, gcap)), 256, 0, s->stream>>>(sc->d_key, n_rows, dict, sc->d_ids);
     SQ_CUDA(E, cudaGetLastError());
+    SQ_CUDA(E, cudaEventRecord(ev[5], s->stream));
     s->launches += 1;
+    ids_timed = true;
   }
-  SQ_CUDA(E, cudaEventRecord(ev[2], s->stream));
   SQ_CUDA(E, cudaStreamSynchronize(s->stream));
-  if (ev_begin) cudaEventElapsedTime(&sc->ms[0], ev_begin, ev[0]);
-  cudaEventElapsedTime(&sc->ms[1], ev[0], ev[1]);
-  cudaEventElapsedTime(&sc->ms[2], ev[1], ev[2]);
+  if (n_rows) {
+    float locate = 0.f, parse = 0.f;
+    cudaEventElapsedTime(&locate, ev[0], ev[1]);
+    cudaEventElapsedTime(&parse, ev[2], ev[3]);
+    sc->ms[1] = locate + parse;
+    if (ids_timed) cudaEventElapsedTime(&sc->ms[2], ev[4], ev[5]);
+  }
   guard.p = nullptr;
   *out = sc;
   return SQ_OK;

@@ -37,55 +37,213 @@ struct RowResult {
   int fields;
 };
 
+// BIGINT field, [+-]?[0-9]+.  Genomic coordinates have at most 9 digits: those accumulate in 32 bits, longer
+// numbers continue in 64 bits, and only numbers of 19 digits pay for the Int64 range check.
 struct IntField {
+  uint32_t lo = 0;
   uint64_t mag = 0;
   int digits = 0;
   bool neg = false, sign = false, bad = false;
   SQ_HD void push(uint8_t c) {
-    if ((c == '-' || c == '+') && digits == 0 && !sign) {
+    const uint32_t d = uint32_t(c) - uint32_t('0');
+    if (d < 10u) {
+      if (digits < 9) {
+        lo = lo * 10u + d;
+      } else {
+        if (digits == 9) mag = lo;
+        if (digits >= 18 && mag > (0x7FFFFFFFFFFFFFFFull - d) / 10ull) bad = true;  // beyond Int64: not a BIGINT
+        else mag = mag * 10ull + d;
+      }
+      ++digits;
+    } else if ((c == '-' || c == '+') && digits == 0 && !sign) {
       sign = true;
       neg = c == '-';
-    } else if (c >= '0' && c <= '9') {
-      const uint64_t d = uint64_t(c - '0');
-      if (mag > (0x7FFFFFFFFFFFFFFFull - d) / 10ull) bad = true;  // beyond Int64: not a BIGINT
-      else mag = mag * 10ull + d;
-      ++digits;
     } else {
       bad = true;
     }
   }
   SQ_HD bool ok() const { return digits > 0 && !bad; }
-  SQ_HD int64_t value() const { return neg ? -int64_t(mag) : int64_t(mag); }
+  SQ_HD int64_t value() const {
+    const int64_t v = digits <= 9 ? int64_t(lo) : int64_t(mag);
+    return neg ? -v : v;
+  }
 };
 
-// One row, from its first byte `q` to its newline (or the end of the text).  Shared by the kernel and by
-// the host-side diagnosis of the first failing row.
-SQ_HD RowResult parse_row(const uint8_t* text, uint64_t n, uint64_t q, const ScanOpts& o) {
+// Key field: the first 8 bytes packed little-endian (two 32-bit halves) and the length — all the hash of a
+// contig name of up to 8 bytes needs (sq_keyhash.h); longer keys are hashed by a second read of the field.
+struct KeyField {
+  uint32_t lo = 0, hi = 0, len = 0;
+  SQ_HD void push(uint8_t c) {
+    if (len < 4u) lo |= uint32_t(c) << (8u * len);
+    else if (len < 8u) hi |= uint32_t(c) << (8u * (len - 4u));
+    ++len;
+  }
+};
+
+// Byte sources of parse_row: src(p) = the byte at position p, '\n' for every position at or behind the end of
+// the text; positions are absolute offsets (TextSrc) or offsets from the start of a tile (TileSrc, 32 bits:
+// the per-byte address arithmetic of the kernel stays in one register).
+struct TextSrc {  // plain memory (host diagnosis / CPU harness)
+  typedef uint64_t pos_t;
+  const uint8_t* text;
+  uint64_t n;
+  SQ_HD uint8_t operator()(uint64_t p) const { return p < n ? text[p] : uint8_t('\n'); }
+  SQ_HD uint64_t absolute(uint64_t p) const { return p; }
+};
+struct TileSrc {  // the kernel: a tile of the text staged in shared memory, global memory behind it
+  typedef uint32_t pos_t;
+  const uint8_t* tile;  // bytes [base, base + len) of the text
+  uint32_t tile_saddr;  // the same as a 32-bit shared-memory address (device code loads through it: a generic
+                        // pointer made the compiler rebuild the shared window address for every byte)
+  uint64_t base;
+  uint32_t len;
+  TextSrc rest;
+  SQ_HD uint8_t operator()(uint32_t p) const {
+    if (p < len) {
+#ifdef __CUDA_ARCH__
+      uint32_t v;
+      asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(tile_saddr + p));
+      return uint8_t(v);
+#else
+      return tile[p];
+#endif
+    }
+    return rest(base + p);
+  }
+  SQ_HD uint64_t absolute(uint32_t p) const { return base + p; }
+};
+
+#ifdef __CUDACC__
+struct SmemSrc {  // the kernel, for a row known to end inside the staged tile: no bounds check per byte
+  typedef uint32_t pos_t;
+  uint32_t tile_saddr;
+  uint64_t base;
+  __device__ __forceinline__ uint8_t operator()(uint32_t p) const {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(tile_saddr + p));
+    return uint8_t(v);
+  }
+  __device__ __forceinline__ uint64_t absolute(uint32_t p) const { return base + p; }
+};
+#endif
+
+// One row, from its first byte `q` to its newline (or the end of the text), field by field: the key field is
+// hashed while it is read, the two interval fields are parsed as BIGINT, every other field is skipped, and
+// nothing behind the last field the table names is read.  Shared by the kernel, by the host-side diagnosis of
+// the first failing row and by the CPU harness of the tests.
+template <class Src>
+SQ_HD RowResult parse_row(const Src& src, typename Src::pos_t q, const ScanOpts& o) {
+  typedef typename Src::pos_t pos_t;
   RowResult r;
   r.key = sqkey::seed();
-  r.key_off = q;
+  r.key_off = src.absolute(q);
   r.key_len = 0;
   r.start = r.end = 0;
   r.err = kRowOk;
   r.bad_value = 0;
-  int field = 0;
   int cast_err = kRowOk;  // reported only when the row parses: the reader fails before the cast is evaluated
-  sqkey::StringHasher kh;
-  IntField iv;
   bool have_key = o.col_key < 0, have_start = false, have_end = false;
-  uint64_t field_off = q;
-  for (uint64_t p = q;; ++p) {
-    const uint8_t c = p < n ? text[p] : uint8_t('\n');
-    if (c == '\r' && (p + 1 >= n || text[p + 1] == '\n')) continue;  // the CR of a CRLF row end
-    const bool eol = c == '\n';
-    if (eol || c == o.delim) {
-      if (field == o.col_key) {
-        r.key = sqkey::fold(sqkey::seed(), kh.finish());
-        r.key_off = field_off;
-        r.key_len = uint32_t(kh.len);
-        have_key = true;
-        if (kh.len >= 0xFFFFull && r.err == kRowOk) r.err = kRowKeyTooLong;
+  const int last_needed = o.col_key > o.col_start ? (o.col_key > o.col_end ? o.col_key : o.col_end)
+                                                  : (o.col_start > o.col_end ? o.col_start : o.col_end);
+  const uint8_t delim = o.delim;
+  // a field ends at the delimiter, at '\n' (src gives '\n' behind the text) or at the CR of a CRLF row end;
+  // '\t', '\n' and '\r' are all below 14, so ordinary bytes take one or two compares
+#define SQ_FIELD_ENDS(c, p) ((c) == delim || ((c) < 14 && ((c) == '\n' || ((c) == '\r' && src(pos_t((p) + 1)) == '\n'))))
+  // what stopped a fast loop at p: 1 = the delimiter, 2 = the row's end, 0 = some other byte
+#define SQ_END_KIND(c, p) ((c) == delim ? 1 : ((c) == '\n' || ((c) == '\r' && src(pos_t((p) + 1)) == '\n')) ? 2 : 0)
+  pos_t p = q;
+  int field = 0;
+  for (;;) {
+    uint8_t c;
+    const pos_t f0 = p;
+    // Fast paths for what BED / CSV rows are made of — a key of up to 8 bytes, an unsigned number of up to 9
+    // digits, a field to skip — as short loops of straight-line iterations; anything else (a sign, a longer
+    // number or name, a stray CR, a malformed field) starts the field again in the general code below.
+    int kind = 0;
+    if (field == o.col_key) {
+      uint64_t raw = 0;
+      uint32_t len = 0;
+      c = src(p);
+      while (len < 8u && !((c == delim) | (c == '\n') | (c == '\r'))) {
+        raw |= uint64_t(c) << (8u * len);
+        ++len;
+        c = src(++p);
       }
+      kind = SQ_END_KIND(c, p);
+      if (kind != 0 && (raw & 0xFFull) != '"') {
+        r.key = sqkey::fold(sqkey::seed(), sqkey::of_string(raw, 0, len));
+        r.key_off = src.absolute(f0);
+        r.key_len = len;
+        have_key = true;
+      } else {
+        kind = 0;
+      }
+    } else if (field == o.col_start || field == o.col_end) {
+      uint32_t lo = 0;
+      int digits = 0;
+      c = src(p);
+      while (digits < 9) {
+        const uint32_t d = uint32_t(c) - uint32_t('0');
+        if (d > 9u) break;
+        lo = lo * 10u + d;
+        ++digits;
+        c = src(++p);
+      }
+      kind = digits > 0 ? SQ_END_KIND(c, p) : 0;
+      if (kind != 0) {  // 0 .. 999999999: inside Int64; the cast below still checks Int32 after `minus`
+        if (field == o.col_start) {
+          have_start = true;
+          const int64_t v = int64_t(lo) - o.start_minus;
+          if (v < int64_t(INT32_MIN) || v > int64_t(INT32_MAX)) { cast_err = kRowCastStart; r.bad_value = v; }
+          else r.start = int32_t(v);
+        }
+        if (field == o.col_end) {
+          have_end = true;
+          const int64_t v = int64_t(lo) - o.end_minus;
+          if (v < int64_t(INT32_MIN) || v > int64_t(INT32_MAX)) { if (cast_err == kRowOk) { cast_err = kRowCastEnd; r.bad_value = v; } }
+          else r.end = int32_t(v);
+        }
+      }
+    } else {
+      c = src(p);
+      while (!((c == delim) | (c == '\n') | (c == '\r'))) c = src(++p);
+      kind = SQ_END_KIND(c, p);
+    }
+    if (kind != 0) {
+      ++field;
+      if (kind == 2) break;            // the row is over
+      if (field > last_needed) break;  // everything the table names has been read
+      ++p;
+      continue;
+    }
+    p = f0;  // the general code, from the field's first byte
+    if (field == o.col_key) {
+      KeyField kf;
+      for (;; ++p) {
+        c = src(p);
+        if (SQ_FIELD_ENDS(c, p)) break;
+        kf.push(c);
+      }
+      uint64_t fnv = 0;
+      if (kf.len > 8u) {  // a long name: FNV-1a over the whole field
+        fnv = sqkey::kFnvOffset;
+        for (pos_t k = f0; k != p; ++k) fnv = (fnv ^ src(k)) * sqkey::kFnvPrime;
+      }
+      r.key = sqkey::fold(sqkey::seed(), sqkey::of_string(uint64_t(kf.lo) | (uint64_t(kf.hi) << 32), fnv, kf.len));
+      r.key_off = src.absolute(f0);
+      r.key_len = kf.len;
+      have_key = true;
+      if (kf.len != 0u && (kf.lo & 0xFFu) == '"' && r.err == kRowOk) r.err = kRowQuoted;
+      if (kf.len >= 0xFFFFu && r.err == kRowOk) r.err = kRowKeyTooLong;
+    } else if (field == o.col_start || field == o.col_end) {
+      IntField iv;
+      const uint8_t c0 = src(p);
+      for (;; ++p) {
+        c = src(p);
+        if (SQ_FIELD_ENDS(c, p)) break;
+        iv.push(c);
+      }
+      if (c0 == '"' && r.err == kRowOk) r.err = kRowQuoted;
       // a table may name one field twice (start == end column: point intervals), hence no `else`
       if (field == o.col_start) {
         have_start = true;
@@ -105,22 +263,19 @@ SQ_HD RowResult parse_row(const uint8_t* text, uint64_t n, uint64_t q, const Sca
           else r.end = int32_t(v);
         }
       }
-      ++field;
-      kh = sqkey::StringHasher();
-      iv = IntField();
-      field_off = p + 1;
-      if (eol) break;
-      continue;
+    } else {
+      for (;; ++p) {
+        c = src(p);
+        if (SQ_FIELD_ENDS(c, p)) break;
+      }
     }
-    if (field == o.col_key) {
-      if (kh.len == 0 && c == '"' && r.err == kRowOk) r.err = kRowQuoted;
-      kh.push(c);
-    }
-    if (field == o.col_start || field == o.col_end) {
-      if (iv.digits == 0 && !iv.sign && c == '"' && r.err == kRowOk) r.err = kRowQuoted;
-      iv.push(c);
-    }
+    ++field;
+    if (c != delim) break;           // '\n', or the CR in front of it: the row is over
+    if (field > last_needed) break;  // everything the table names has been read
+    ++p;
   }
+#undef SQ_FIELD_ENDS
+#undef SQ_END_KIND
   r.fields = field;
   if (!(have_key && have_start && have_end)) r.err = kRowFewFields;  // reported before any field error: the row is short
   // a cast failure of `start` is reported before one of `end` (evaluation order, interval_join.rs:1039-1040):
@@ -157,24 +312,32 @@ SQ_HD int lowest_bit(uint32_t m) {
 #endif
 }
 
-// bit j = a row starts at q0 + j: first byte of the text or the byte behind a newline, unless the row is
-// empty ("\n", "\r\n", a lone "\r" at the end) or opens with the comment byte
-SQ_HD uint32_t row_start_mask32(const uint8_t* text, uint64_t n, uint64_t q0, uint8_t comment) {
-  if (q0 >= n) return 0u;
-  const uint32_t nl = newline_mask32(text, n, q0);
-  const bool prev_nl = q0 == 0 || text[q0 - 1] == '\n';
+// bit j = a row starts at q0 + j, given the newline mask `nl` of the 32 bytes at q0 (`valid` of them lie inside
+// the text) and whether the byte in front of q0 is a newline (or q0 == 0): first byte of the text or the byte
+// behind a newline, unless the row is empty ("\n", "\r\n", a lone "\r" at the end) or opens with the
+// comment byte
+template <class Src>
+SQ_HD uint32_t row_starts_from_newlines(const Src& src, uint64_t q0, uint32_t nl, bool prev_nl, uint32_t valid,
+                                        uint8_t comment) {
   uint32_t cand = ((nl << 1) | (prev_nl ? 1u : 0u)) & ~nl;
-  if (q0 + 32 > n) cand &= (1u << uint32_t(n - q0)) - 1u;
+  if (valid < 32u) cand &= (1u << valid) - 1u;
   uint32_t m = cand;
   while (m) {
     const int j = lowest_bit(m);
     m &= m - 1;
     const uint64_t p = q0 + j;
-    const uint8_t c = text[p];
-    const bool skip = (comment != 0 && c == comment) || (c == '\r' && (p + 1 >= n || text[p + 1] == '\n'));
+    const uint8_t c = src(p);
+    const bool skip = (comment != 0 && c == comment) || (c == '\r' && src(p + 1) == '\n');
     if (skip) cand &= ~(1u << j);
   }
   return cand;
+}
+
+SQ_HD uint32_t row_start_mask32(const uint8_t* text, uint64_t n, uint64_t q0, uint8_t comment) {
+  if (q0 >= n) return 0u;
+  const uint32_t nl = newline_mask32(text, n, q0);
+  const bool prev_nl = q0 == 0 || text[q0 - 1] == '\n';
+  return row_starts_from_newlines(TextSrc{text, n}, q0, nl, prev_nl, n - q0 >= 32 ? 32u : uint32_t(n - q0), comment);
 }
 
 }  // namespace sq

@@ -26,7 +26,7 @@ extern "C" int64_t scan_host(const uint8_t* text, uint64_t n, uint8_t delim, int
       m &= m - 1;
       const uint64_t r = row++;
       if (o.has_header && r == 0) continue;
-      const sq::RowResult res = sq::parse_row(text, n, q0 + j, o);
+      const sq::RowResult res = sq::parse_row(sq::TextSrc{text, n}, q0 + j, o);
       if (res.err != sq::kRowOk) {
         *err_kind = res.err;
         *bad_value = res.bad_value;

@@ -82,12 +82,23 @@ def main():
         h2d_ms = sc.timing_ms[0]
         del sc
     # q1 shape: file bytes -> count(1)
-    t0 = time.perf_counter()
-    sa = sn.CudaScan.from_text(st, tb)
-    sp = sn.CudaScan.from_text(st, tp)
-    idx = sa.build_index(ctx)
-    n_pairs = sp.probe_count(st, idx)
-    q1_ms = (time.perf_counter() - t0) * 1e3
+    q1_ms, q1_steps = 1e30, None
+    for _ in range(3):  # first pass pays the stream's scratch allocations
+        t0 = time.perf_counter()
+        sa = sn.CudaScan.from_text(st, tb)
+        t1 = time.perf_counter()
+        sp = sn.CudaScan.from_text(st, tp)
+        t2 = time.perf_counter()
+        idx = sa.build_index(ctx)
+        t3 = time.perf_counter()
+        n_pairs = sp.probe_count(st, idx)
+        t4 = time.perf_counter()
+        if t4 - t0 < q1_ms:
+            q1_ms = t4 - t0
+            q1_steps = {"scan_build_side_ms": (t1 - t0) * 1e3, "scan_probe_side_ms": (t2 - t1) * 1e3,
+                        "index_build_ms": (t3 - t2) * 1e3, "probe_count_ms": (t4 - t3) * 1e3}
+        del idx, sa, sp
+    q1_ms *= 1e3
     # CPU reader beside it
     import pyarrow.csv as pacsv
     cpu = {}
@@ -112,7 +123,7 @@ def main():
         "cpu_reader": {"kind": "pyarrow.csv.read_csv (Arrow C++), not the reference", "cores": os.cpu_count(),
                        "all_cores_ms": cpu["all_cores"], "one_thread_ms": cpu["one_thread"],
                        "all_cores_rows_per_s": a.rows / cpu["all_cores"] * 1e3},
-        "q1_shape": {"build_rows": a.rows, "probe_rows": a.rows // 4, "pairs": int(n_pairs), "ms_file_bytes_to_count": q1_ms},
+        "q1_shape": {"build_rows": a.rows, "probe_rows": a.rows // 4, "pairs": int(n_pairs), "ms_file_bytes_to_count": q1_ms, "steps": q1_steps},
     }
     line = json.dumps(out)
     print(line)
