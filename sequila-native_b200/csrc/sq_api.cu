@@ -292,7 +292,7 @@ SQ_API void sq_stream_free(sq_stream* s) {
   cudaSetDevice(s->ctx->device);
   cudaStreamSynchronize(s->stream);
   for (sq_buf* b : {&s->d_in, &s->d_cnt, &s->d_state, &s->d_tile, &s->d_scalar, &s->d_left,
-                    &s->d_right, &s->d_gather, &s->d_gather2, &s->d_chain, &s->d_strblk, &s->d_strdata, &s->h_in, &s->h_out, &s->h_scalar})
+                    &s->d_right, &s->d_gather, &s->d_gather2, &s->d_chain, &s->d_strblk, &s->d_strdata, &s->h_in, &s->h_out, &s->h_scalar, &s->h_scan})
     release(*b);
   if (s->ev_ready) for (auto& e : s->ev) cudaEventDestroy(e);
   if (s->ev_rle) cudaEventDestroy(s->ev_rle);
@@ -306,7 +306,7 @@ SQ_API uint64_t sq_stream_bytes(const sq_stream* s) {
   if (!s) return 0;
   uint64_t t = 0;
   for (const sq_buf* b : {&s->d_in, &s->d_cnt, &s->d_state, &s->d_tile, &s->d_scalar, &s->d_left,
-                          &s->d_right, &s->d_gather, &s->d_gather2, &s->d_chain, &s->d_strblk, &s->d_strdata, &s->h_in, &s->h_out, &s->h_scalar})
+                          &s->d_right, &s->d_gather, &s->d_gather2, &s->d_chain, &s->d_strblk, &s->d_strdata, &s->h_in, &s->h_out, &s->h_scalar, &s->h_scan})
     t += b->cap;
   return t;
 }

@@ -210,6 +210,7 @@ struct sq_stream {
   bool str_pending = false;
   // pinned staging
   sq_buf h_in, h_out, h_scalar;
+  sq_buf h_scan;     // ring of pinned chunks the text scanner copies pageable host text through
 
   // profiling
   bool profiling = false;

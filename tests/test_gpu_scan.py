@@ -160,3 +160,24 @@ def test_scanned_join_equals_the_oracle_join_at_cfg2_scale(cuda_ctx, stream, ora
     got_ids = stream.gather_build(col, np.uint32)
     bk, bs, be, bids = sb.fetch()
     assert np.array_equal(got_ids, bids[left])
+
+
+def test_large_host_text_goes_through_the_pinned_ring(stream):
+    """texts of 16 MB and more are copied by four host threads through a ring of pinned chunks (sq_scan.cu,
+    copy_text_to_device): every chunk must land at its offset — the columns equal the generator's."""
+    import io
+    import pyarrow as pa
+    import pyarrow.csv as pacsv
+    b, _ = sn.synth.cfg5(nb=1_500_000, np_=1000)
+    names = pa.array(sn.synth.CONTIG_NAMES)
+    contig = pa.DictionaryArray.from_arrays(pa.array(b["contig"].astype(np.int32)), names).cast(pa.string())
+    buf = io.BytesIO()
+    pacsv.write_csv(pa.table({"c": contig, "s": pa.array(b["start"]), "e": pa.array(b["end"])}), buf,
+                    pacsv.WriteOptions(include_header=False, delimiter="\t", quoting_style="none"))
+    text = buf.getvalue()
+    assert len(text) > (33 << 20)  # several rounds of the ring, last chunk partial
+    for _ in range(2):  # the second call reuses the ring
+        sc = sn.CudaScan.from_text(stream, text)
+        k, s, e, ids = sc.fetch()
+        assert np.array_equal(s, b["start"]) and np.array_equal(e, b["end"])
+        assert np.array_equal(np.array([sn.synth.CONTIG_NAMES.index(d.decode()) for d in sc.dictionary])[ids], b["contig"])
