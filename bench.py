@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--e2e-partitions", type=int, default=8, help="host threads, one sq_stream each")
     ap.add_argument("--e2e-tiles", type=int, default=64, help="probe sub-tiles per step (all partitions)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-locality", action="store_true", help="skip the position-sorted side measurement")
     ap.add_argument("--cpu-sample-contigs", type=int, default=8)
     ap.add_argument("--cpu-sample-probes", type=int, default=2_000_000)
     return ap.parse_args()
@@ -423,6 +424,34 @@ def main():
     e2e_value = probes_total / (e_ms_max * 1e-3)
     pool.shutdown()
 
+    # ---- same rows in position order (what BAM / BED inputs look like): an explanatory side line, N=1 only.
+    # The headline workload probes in random order on purpose; with locality the walk's line reads hit L2
+    # instead of costing one DRAM request each, and this shows how much of the gap to the
+    # streaming roofline is the access pattern rather than the kernel.
+    locality = None
+    if world == 1 and not args.no_locality:
+        order = torch.argsort(probe["contig"].to(torch.int64) * (1 << 32) + probe["start"].to(torch.int64))
+        sp = {k: v[order].contiguous() for k, v in probe.items()}
+        del order
+
+        def sorted_step():
+            return st.probe_join_device(idx, sp["key"], sp["start"], sp["end"], left, right)
+
+        for _ in range(3):
+            assert sorted_step() == n_pairs
+        torch.cuda.synchronize()
+        st.set_profiling(True)
+        for _ in range(min(args.steps, 10)):
+            flush.fill_(1)
+            sorted_step()
+        torch.cuda.synchronize()
+        s_ms = st.phase_ms()["join"]
+        st.set_profiling(False)
+        locality = {"probe_order": "position-sorted (contig, start)", "avg_launch_ms": s_ms,
+                    "value": n_probe / (s_ms * 1e-3), "unit": "probe intervals/s",
+                    "roofline_frac": (16.0 * n_probe + 12.0 * n_pairs) / (s_ms * 1e-3) / 1e9 / hbm_peak}
+        del sp
+
     if rank == 0:
         # ---- roofline of the dominant kernel (algorithmic bytes) -----------------
         # B_probe of SURVEY.md §8(d) with u64 key hashes consumed on the device:
@@ -447,7 +476,10 @@ def main():
             "pairs_per_s": pairs_total / (step_ms_max * 1e-3),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": b_dom, "avg_launch_ms": t_dom},
+                         "algorithmic_bytes_per_launch": b_dom, "avg_launch_ms": t_dom,
+                         # DRAM bytes the launch really moves (ncu) over its duration: how busy HBM is
+                         "traffic_rate": (traffic / (t_dom * 1e-3) / 1e9) if traffic and t_dom > 0 else None,
+                         "traffic_frac": (traffic / (t_dom * 1e-3) / 1e9 / hbm_peak) if traffic and t_dom > 0 else None},
             "build": {"ms": build_best, "rows_per_s": n_build / (build_best * 1e-3) if build_best else None,
                       "roofline_frac": (24.0 * n_build / (build_best * 1e-3) / 1e9 / hbm_peak) if build_best else None,
                       "index_bytes": idx.bytes, "keys": idx.keys},
@@ -460,6 +492,8 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks,
             "digest": {"pairs": dg[0], "sum": dg[1], "xor": dg[2]},
         }
+        if locality:
+            result["locality"] = locality
         if not args.no_cpu_baseline:
             os.sched_setaffinity(0, all_cpus)
             if args.workload == "cfg5_shard":

@@ -48,6 +48,10 @@ struct ColType {
   int64_t flags = 0;
   Kind kind = Kind::Fixed;
   uint32_t width = 0;  // bytes per value for Kind::Fixed
+  // dictionary-encoded strings (DictionaryArray<intN, Utf8 | LargeUtf8>): kind = Fixed over the index type (the
+  // indices are gathered like any fixed-width column), the values travel once per batch as the dictionary
+  bool dict = false;
+  bool dict_large = false;  // dictionary values are LargeUtf8
 };
 
 // fixed-width Arrow primitive formats -> byte width (Columnar format spec, "Data type description")
@@ -91,6 +95,11 @@ void release_array(ArrowArray* a) {
     if (c->release) c->release(c);
     delete c;
   }
+  if (a->dictionary) {  // dictionary values of a dictionary-encoded output column (created by make_dictionary)
+    if (a->dictionary->release) a->dictionary->release(a->dictionary);
+    delete a->dictionary;
+    a->dictionary = nullptr;
+  }
   for (void* p : o->pinned) sq_host_free(o->ctx, p);
   for (void* p : o->heap) free(p);
   delete o;
@@ -103,6 +112,11 @@ void release_schema(ArrowSchema* s) {
   for (ArrowSchema* c : o->schema_children) {
     if (c->release) c->release(c);
     delete c;
+  }
+  if (s->dictionary) {
+    if (s->dictionary->release) s->dictionary->release(s->dictionary);
+    delete s->dictionary;
+    s->dictionary = nullptr;
   }
   delete o;
   s->release = nullptr;
@@ -126,6 +140,7 @@ struct sq_exec {
   sq_index* index = nullptr;
   std::vector<ArrowArray> build_batches;  // owned (moved in)
   std::vector<int32_t> build_col_id;      // left column -> sq_index column id (or -1 when not projected)
+  std::map<int32_t, std::vector<std::string>> build_dicts;  // left dictionary column -> values unified over the build batches
   std::mutex mu;
   std::map<int32_t, sq_stream*> streams;
   std::map<int32_t, PartState> parts;
@@ -158,6 +173,17 @@ int read_side(sq_exec* e, const ArrowSchema* s, Side* out, const char* which) {
       t.width = 0;  // unsupported types are only an error if the column is actually used
       t.kind = Kind::Fixed;
     }
+    if (c->dictionary) {
+      const char* vf = c->dictionary->format ? c->dictionary->format : "";
+      const bool idx_ok = t.kind == Kind::Fixed && strlen(c->format) == 1 && strchr("cCsSiI", c->format[0]) != nullptr;
+      if (idx_ok && (!strcmp(vf, "u") || !strcmp(vf, "U"))) {
+        t.dict = true;
+        t.dict_large = !strcmp(vf, "U");
+      } else {
+        t.width = 0;  // unsupported dictionary type: only an error if the column is used
+        t.kind = Kind::Fixed;
+      }
+    }
     t.name = c->name ? c->name : "";
     t.flags = c->flags;
     out->cols[size_t(i)] = t;
@@ -187,6 +213,53 @@ ColView view_of(const ArrowArray* batch, int32_t col) {
 
 inline bool bit_at(const uint8_t* bm, int64_t i) { return (bm[i >> 3] >> (i & 7)) & 1; }
 
+// ---- dictionary-encoded string columns ----------------------------------------------------------------
+typedef std::pair<const uint8_t*, int64_t> StrRef;
+
+// index of row i (indices are non-negative; 1, 2 or 4 bytes wide)
+inline uint32_t dict_index(const uint8_t* values, int64_t i, uint32_t width) {
+  uint32_t v = 0;
+  memcpy(&v, values + i * width, width);
+  return v;
+}
+
+// the values of a dictionary (Utf8 or LargeUtf8 array), honouring its offset
+void dict_strings(const ArrowArray* d, bool large, std::vector<StrRef>* out) {
+  out->clear();
+  if (!d || d->n_buffers < 3) return;
+  const uint8_t* data = static_cast<const uint8_t*>(d->buffers[2]);
+  for (int64_t k = 0; k < d->length; ++k) {
+    int64_t a, z;
+    if (large) { const int64_t* o = static_cast<const int64_t*>(d->buffers[1]) + d->offset; a = o[k]; z = o[k + 1]; }
+    else { const int32_t* o = static_cast<const int32_t*>(d->buffers[1]) + d->offset; a = o[k]; z = o[k + 1]; }
+    out->emplace_back(data + a, z - a);
+  }
+}
+
+// per-column hash of one string value (sq_keyhash.h `of_string`)
+inline uint64_t string_hash(const uint8_t* p, int64_t len) {
+  if (len <= 8) {
+    uint64_t raw = 0;
+    memcpy(&raw, p, size_t(len));
+    return sqkey::of_string(raw, 0, uint64_t(len));
+  }
+  uint64_t h = sqkey::kFnvOffset;  // FNV-1a over the bytes
+  for (int64_t k = 0; k < len; ++k) { h ^= p[k]; h *= sqkey::kFnvPrime; }
+  return h;
+}
+
+// largest index the dictionary's index type can hold
+inline uint64_t dict_index_limit(const std::string& format) {
+  switch (format[0]) {
+    case 'c': return 127ull;
+    case 'C': return 255ull;
+    case 's': return 32767ull;
+    case 'S': return 65535ull;
+    case 'i': return 2147483647ull;
+    default: return 4294967295ull;
+  }
+}
+
 // 64-bit hash of the `on` columns of every row (IJ:1037 / IJ:1211 call create_hashes here)
 int hash_keys(sq_exec* e, const Side& side, const std::vector<int32_t>& on, const ArrowArray* batch,
               std::vector<uint64_t>* out) {
@@ -195,7 +268,18 @@ int hash_keys(sq_exec* e, const Side& side, const std::vector<int32_t>& on, cons
   for (int32_t col : on) {
     const ColType& t = side.cols[size_t(col)];
     const ColView v = view_of(batch, col);
-    if (t.kind == Kind::Fixed) {
+    if (t.dict) {
+      // dictionary-encoded key: hash every dictionary value once, rows look their value's hash up — the same
+      // hash a plain Utf8 column of the same strings gets, so a dictionary side and a Utf8 side of one join agree
+      std::vector<StrRef> strs;
+      dict_strings(batch->children[col]->dictionary, t.dict_large, &strs);
+      std::vector<uint64_t> eh(strs.size());
+      for (size_t k = 0; k < strs.size(); ++k) eh[k] = string_hash(strs[k].first, strs[k].second);
+      for (int64_t i = 0; i < n; ++i) {
+        const uint32_t ix = dict_index(v.values, v.offset + i, t.width);
+        (*out)[size_t(i)] = sqkey::fold((*out)[size_t(i)], ix < eh.size() ? eh[ix] : 0);
+      }
+    } else if (t.kind == Kind::Fixed) {
       if (t.width != 1 && t.width != 2 && t.width != 4 && t.width != 8)
         return e->fail(SQ_EINVAL, "key column '%s' has unsupported type '%s'", t.name.c_str(), t.format.c_str());
       for (int64_t i = 0; i < n; ++i) {
@@ -297,7 +381,56 @@ ArrowSchema* make_field(const ColType& t) {
   f->dictionary = nullptr;
   f->release = release_schema;
   f->private_data = o;
+  if (t.dict) {  // the field of the dictionary values
+    auto* d = new ArrowSchema();
+    auto* od = new Owned();
+    od->s1 = t.dict_large ? "U" : "u";
+    od->s2 = "";
+    d->format = od->s1.c_str();
+    d->name = od->s2.c_str();
+    d->metadata = nullptr;
+    d->flags = 0;
+    d->n_children = 0;
+    d->children = nullptr;
+    d->dictionary = nullptr;
+    d->release = release_schema;
+    d->private_data = od;
+    f->dictionary = d;
+  }
   return f;
+}
+
+// a Utf8 / LargeUtf8 array owning copies of `strs`: the dictionary of a dictionary-encoded output column
+ArrowArray* make_dictionary(const std::vector<StrRef>& strs, bool large) {
+  auto* a = new ArrowArray();
+  auto* o = new Owned();
+  uint64_t total = 0;
+  for (const StrRef& s : strs) total += uint64_t(s.second);
+  const size_t ow = large ? 8 : 4;
+  void* off = malloc((strs.size() + 1) * ow);
+  auto* data = static_cast<uint8_t*>(malloc(total ? total : 1));
+  o->heap = {off, data};
+  uint64_t at = 0;
+  for (size_t k = 0; k <= strs.size(); ++k) {
+    if (large) static_cast<int64_t*>(off)[k] = int64_t(at);
+    else static_cast<int32_t*>(off)[k] = int32_t(at);
+    if (k < strs.size()) {
+      if (strs[k].second) memcpy(data + at, strs[k].first, size_t(strs[k].second));
+      at += uint64_t(strs[k].second);
+    }
+  }
+  o->buffers = {nullptr, off, data};
+  a->length = int64_t(strs.size());
+  a->null_count = 0;
+  a->offset = 0;
+  a->n_buffers = 3;
+  a->buffers = o->buffers.data();
+  a->n_children = 0;
+  a->children = nullptr;
+  a->dictionary = nullptr;
+  a->release = release_array;
+  a->private_data = o;
+  return a;
 }
 
 }  // namespace
@@ -400,7 +533,36 @@ SQ_API int32_t sq_exec_finish_build(sq_exec* e) {
     int32_t id = -1;
     bool any_null = false;
     std::vector<uint8_t> validity((n + 7) / 8, 0xFF);
-    if (t.kind == Kind::Fixed) {
+    if (t.dict) {
+      // the build batches may each bring their own dictionary: unify the values (order of first occurrence over
+      // the batches) and renumber the indices, which then live on the device as a 4-byte payload column
+      std::vector<std::string>& gdict = e->build_dicts[col];
+      std::map<std::string, uint32_t> gmap;
+      std::vector<uint32_t> buf(size_t(n), 0);
+      uint64_t r = 0;
+      for (auto& b : e->build_batches) {
+        const ColView v = view_of(&b, col);
+        std::vector<StrRef> strs;
+        dict_strings(b.children[col]->dictionary, t.dict_large, &strs);
+        std::vector<uint32_t> remap(strs.size());
+        for (size_t k = 0; k < strs.size(); ++k) {
+          std::string sv(reinterpret_cast<const char*>(strs[k].first), size_t(strs[k].second));
+          auto it = gmap.find(sv);
+          if (it == gmap.end()) { it = gmap.emplace(sv, uint32_t(gdict.size())).first; gdict.push_back(sv); }
+          remap[k] = it->second;
+        }
+        for (int64_t i = 0; i < v.length; ++i, ++r) {
+          const bool null = v.null_count != 0 && v.validity && !bit_at(v.validity, v.offset + i);
+          const uint32_t ix = dict_index(v.values, v.offset + i, t.width);
+          buf[r] = (!null && ix < remap.size()) ? remap[ix] : 0u;
+          if (null) { validity[r >> 3] &= uint8_t(~(1u << (r & 7))); any_null = true; }
+        }
+      }
+      if (!gdict.empty() && gdict.size() - 1 > dict_index_limit(t.format))
+        return e->fail(SQ_EINVAL, "column '%s': %zu distinct values over the build batches do not fit index type '%s'",
+                       t.name.c_str(), gdict.size(), t.format.c_str());
+      rc = sq_index_add_column(e->index, buf.data(), 4, &id);
+    } else if (t.kind == Kind::Fixed) {
       // sub-4-byte values are widened into 4-byte slots for the gather and narrowed again on output
       const uint32_t w = t.width < 4 ? 4 : t.width;
       std::vector<uint8_t> buf(size_t(n) * w, 0);
@@ -595,6 +757,17 @@ int assemble_output(sq_exec* e, sq_stream* st, const ArrowArray* batch, uint64_t
         }
       }
       co->buffers = {validity_out, vals};
+      if (t.dict) {  // the values travel once per batch: the build side's unified dictionary, or this batch's own
+        std::vector<StrRef> strs;
+        if (side == 0) {
+          auto it = e->build_dicts.find(col);
+          if (it != e->build_dicts.end())
+            for (const std::string& sv : it->second) strs.emplace_back(reinterpret_cast<const uint8_t*>(sv.data()), int64_t(sv.size()));
+        } else {
+          dict_strings(batch->children[col]->dictionary, t.dict_large, &strs);
+        }
+        child->dictionary = make_dictionary(strs, t.dict_large);
+      }
     } else {
       // Utf8 / LargeUtf8: offsets first (gives the byte total), then the bytes
       std::vector<int64_t> poff;

@@ -178,3 +178,77 @@ def test_empty_projection_is_a_count_only_probe(oracle):
     ol, _, _ = oracle.join(np.zeros(nb, np.uint64), bs, be, np.zeros(npq, np.uint64), ps, pe)
     assert all(b.num_columns == 0 for b in out) and sum(b.num_rows for b in out) == len(ol)
     assert plan.metrics().output_rows == len(ol)
+
+
+# ---- dictionary-encoded contig columns ("dictionary-encode contig once") -------------
+def dict_table(rows, index_type=pa.int32(), value_type=pa.string(), dictionary=None):
+    """contig as DictionaryArray<index_type, value_type>; `dictionary` fixes the value order (may hold unused values)"""
+    values = list(dictionary) if dictionary is not None else sorted({r[0] for r in rows}, reverse=True)
+    idx = pa.array([values.index(r[0]) for r in rows], index_type)
+    contig = pa.DictionaryArray.from_arrays(idx, pa.array(values, value_type))
+    return pa.record_batch([contig, pa.array([r[1] for r in rows], pa.int32()), pa.array([r[2] for r in rows], pa.int32())],
+                           names=COLS)
+
+
+@pytest.mark.parametrize("index_type", [pa.int8(), pa.uint16(), pa.int32(), pa.uint32()])
+@pytest.mark.parametrize("value_type", [pa.string(), pa.large_string()])
+def test_dictionary_contig_fixture_equi_join_16_rows(golden, index_type, value_type):
+    left, right = dict_table(golden["reads"], index_type, value_type), dict_table(golden["targets"], index_type, value_type)
+    plan, out = run_join(left, right, Q1)
+    assert sort_rows(rows_of(out)) == sort_rows(golden["equi_rows"])
+    want = pa.dictionary(index_type, value_type)
+    assert out[0].schema == plan.schema()
+    assert out[0].schema.field(0).type == want and out[0].schema.field(3).type == want  # types unchanged (Appendix A4)
+    out[0].validate(full=True)
+
+
+def test_dictionary_batches_with_their_own_dictionaries_and_a_utf8_side(oracle):
+    """every build batch brings its own dictionary (different order, unused values); the probe side is plain Utf8 in
+    one run and dictionary-encoded in the other: same rows as the all-Utf8 join (the key hash of a dictionary
+    value is the hash of the string)."""
+    rng = np.random.default_rng(21)
+    names = ["chr1", "chr2", "chrX", "chrUn_gl000220", "chr10"]
+    def rows(n):
+        c = rng.integers(0, len(names), n)
+        s = rng.integers(0, 5000, n)
+        return [[names[c[i]], int(s[i]), int(s[i] + rng.integers(0, 200))] for i in range(n)]
+    lrows, rrows = rows(3000), rows(2500)
+    f = IV.parse_condition_sql(Q1, "a", COLS, "b", COLS)
+
+    def run(lbatches, rbatches):
+        plan = optimize(HashJoinDesc(lbatches[0].schema, rbatches[0].schema, [("contig", "contig")], f), cuda_config())
+        return rows_of(list(plan.execute(lbatches, rbatches)))
+
+    want = run([table(lrows)], [table(rrows)])
+    assert len(want) > 1000
+    orders = [names, names[::-1] + ["unused"], ["zz"] + names[2:] + names[:2]]
+    lb = [dict_table(lrows[i * 1000:(i + 1) * 1000], dictionary=orders[i]) for i in range(3)]
+    rb_utf8 = [table(rrows[i:i + 700]) for i in range(0, len(rrows), 700)]
+    rb_dict = [dict_table(rrows[i:i + 700], pa.int8(), dictionary=orders[(i // 700) % 3]) for i in range(0, len(rrows), 700)]
+    assert sort_rows(run(lb, rb_utf8)) == sort_rows(want)
+    assert sort_rows(run(lb, rb_dict)) == sort_rows(want)
+
+
+def test_dictionary_payload_column_with_nulls_and_projection():
+    name_vals = pa.array(["geneA", "geneB"])
+    name = pa.DictionaryArray.from_arrays(pa.array([0, None, 1, 0], pa.int16()), name_vals)
+    left = pa.record_batch([pa.array(["c", "c", "c", "d"]), pa.array([10, 20, 30, 10], pa.int32()),
+                            pa.array([15, 25, 35, 15], pa.int32()), name], names=COLS + ["name"])
+    right = pa.record_batch([pa.array(["c", "d"]), pa.array([0, 0], pa.int32()), pa.array([100, 100], pa.int32())], names=COLS)
+    f = IV.parse_condition_sql(Q1, "a", COLS + ["name"], "b", COLS)
+    plan = optimize(HashJoinDesc(left.schema, right.schema, [("contig", "contig")], f, projection=[3, 1, 4]), cuda_config())
+    out = list(plan.execute([left], [right]))
+    got = sorted(rows_of(out), key=lambda r: (r[2], r[1]))
+    assert got == [["geneA", 10, "c"], [None, 20, "c"], ["geneB", 30, "c"], ["geneA", 10, "d"]]
+    assert out[0].schema.field(0).type == pa.dictionary(pa.int16(), pa.string())
+    out[0].validate(full=True)
+
+
+def test_dictionary_index_type_too_small_for_the_unified_build_dictionary():
+    lb = [dict_table([[f"k{i}_{j}", 1, 2] for j in range(100)], pa.int8()) for i in range(2)]  # 200 distinct values, int8 holds 128
+    right = table([["k0_0", 0, 5]])
+    f = IV.parse_condition_sql(Q1, "a", COLS, "b", COLS)
+    plan = optimize(HashJoinDesc(lb[0].schema, right.schema, [("contig", "contig")], f), cuda_config())
+    with pytest.raises(ExecutionError) as e:
+        list(plan.execute(lb, [right]))
+    assert "do not fit index type" in str(e.value)
