@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--e2e-tiles", type=int, default=64, help="probe sub-tiles per step (all partitions)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-locality", action="store_true", help="skip the position-sorted side measurement")
+    ap.add_argument("--no-materialise", action="store_true", help="skip the six-column gather measurement")
     ap.add_argument("--cpu-sample-contigs", type=int, default=8)
     ap.add_argument("--cpu-sample-probes", type=int, default=2_000_000)
     return ap.parse_args()
@@ -424,6 +425,55 @@ def main():
     e2e_value = probes_total / (e_ms_max * 1e-3)
     pool.shutdown()
 
+    # ---- materialise (process_probe_batch's `take` per output column, interval_join.rs:1620-1632): the six output
+    # columns of SURVEY §8(d) — contig (dictionary id, int32), pos_start, pos_end of both sides — gathered on the
+    # device from the pairs of the last step; B_gather = 8 B pair read + 2 x 4 B per column = 56 B per pair.
+    materialise = None
+    if not args.no_materialise:
+        assert step() == n_pairs
+        cols = [idx.add_column_device(build[k]) for k in ("contig", "start", "end")]
+        outs = [torch.empty(max(n_pairs, 1), dtype=torch.int32, device=device) for _ in range(6)]
+
+        pack = idx.pack_columns(cols)  # the three build columns row-wise: one random read per pair serves all
+        pvals = [probe[k] for k in ("contig", "start", "end")]
+
+        def gather_step():  # two launches: build pack, probe columns
+            st.gather_pack_device(pack, outs[:3])
+            st.gather_probe_columns_device(pvals, outs[3:])
+
+        def take_step():  # `take` column by column, what the reference's loop does (six launches)
+            for c, o in zip(cols, outs[:3]):
+                st.gather_build_device(c, o)
+            for v, o in zip(pvals, outs[3:]):
+                st.gather_probe_device(v, o)
+
+        def timed(fn):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            evs_ = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 10))]
+            for a, b in evs_:
+                flush.fill_(1)
+                a.record()
+                fn()
+                b.record()
+            torch.cuda.synchronize()
+            return float(np.mean([a.elapsed_time(b) for a, b in evs_]))
+
+        take_ms = timed(take_step)
+        g_ms = timed(gather_step)
+        # spot check against torch indexing (same device data)
+        li = left[:n_pairs].long()[:: max(n_pairs // 100000, 1)]
+        assert torch.equal(outs[1][:n_pairs][:: max(n_pairs // 100000, 1)], build["start"][li])
+        ri = right[:n_pairs].long()[:: max(n_pairs // 100000, 1)]
+        assert torch.equal(outs[5][:n_pairs][:: max(n_pairs // 100000, 1)], probe["end"][ri])
+        g_bytes = 56.0 * n_pairs
+        materialise = {"columns": 6, "ms": g_ms, "pairs_per_s": n_pairs / (g_ms * 1e-3) if g_ms else None,
+                       "algorithmic_bytes": g_bytes, "roofline_frac": g_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak if g_ms else None,
+                       "launches": 2, "how": "build columns packed row-wise (16 B per build row): one random read per pair; "
+                       "probe columns in one pass over right_idx", "take_per_column_ms": take_ms}
+        del outs
+
     # ---- same rows in position order (what BAM / BED inputs look like): an explanatory side line, N=1 only.
     # The headline workload probes in random order on purpose; with locality the walk's line reads hit L2
     # instead of costing one DRAM request each, and this shows how much of the gap to the
@@ -494,6 +544,8 @@ def main():
         }
         if locality:
             result["locality"] = locality
+        if materialise:
+            result["materialise"] = materialise
         if not args.no_cpu_baseline:
             os.sched_setaffinity(0, all_cpus)
             if args.workload == "cfg5_shard":

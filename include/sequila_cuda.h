@@ -171,6 +171,20 @@ int32_t sq_gather_column_device(sq_stream* s, int32_t side, int32_t build_col_id
                                 const void* d_probe_values, uint32_t width, void* d_out,
                                 uint64_t capacity);
 
+/* Several columns per pass.  `take` column by column (what IJ:1620-1632 does on the CPU) costs the GPU one
+ * random 32-byte sector per pair AND per build column, plus one more read of the index array; measured on
+ * the cfg5 shard the six-column output took 5.6 ms that way against 1.0 ms for the join itself.
+ * sq_index_pack_columns interleaves up to four 4-byte build columns row-wise (16 bytes per build row, built
+ * once per query on the device) so that ONE random read per pair serves all of them;
+ * sq_gather_pack_device writes the pack's columns for the pairs of the last emit into d_outs[0..n_cols).
+ * sq_gather_probe_columns_device does the same for up to four 4-byte probe columns of this tile (right_idx
+ * is non-decreasing: sequential reads, one pass instead of one per column). */
+int32_t sq_index_pack_columns(sq_index* idx, const int32_t* col_ids, int32_t n_cols, int32_t* pack_id_out);
+int32_t sq_gather_pack_device(sq_stream* s, int32_t pack_id, void* const* d_outs, int32_t n_outs,
+                              uint64_t capacity);
+int32_t sq_gather_probe_columns_device(sq_stream* s, const void* const* d_probe_values, void* const* d_outs,
+                                       int32_t n_cols, uint64_t capacity);
+
 /* Utf8 columns (Arrow `take` of a string column, IJ:1624-1627).  Build side: offsets are n_rows+1
  * int64 (the host concatenates the build batches, IJ:685).  Gathering is two-phase so the caller
  * can allocate: sq_gather_utf8 computes the n_pairs+1 output offsets (32-bit, Arrow Utf8) and the

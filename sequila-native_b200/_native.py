@@ -54,6 +54,9 @@ SIGNATURES = {
     "sq_stream_counts_device": (vp, [vp]),
     "sq_gather_column": (C.c_int32, [vp, C.c_int32, C.c_int32, vp, C.c_uint32, vp, C.c_uint64]),
     "sq_gather_column_device": (C.c_int32, [vp, C.c_int32, C.c_int32, vp, C.c_uint32, vp, C.c_uint64]),
+    "sq_index_pack_columns": (C.c_int32, [vp, i32p, C.c_int32, C.POINTER(C.c_int32)]),
+    "sq_gather_pack_device": (C.c_int32, [vp, C.c_int32, C.POINTER(vp), C.c_int32, C.c_uint64]),
+    "sq_gather_probe_columns_device": (C.c_int32, [vp, C.POINTER(vp), C.POINTER(vp), C.c_int32, C.c_uint64]),
     "sq_index_add_utf8_column": (C.c_int32, [vp, vp, vp, C.c_uint64, C.POINTER(C.c_int32)]),
     "sq_gather_utf8": (C.c_int32, [vp, C.c_int32, C.c_int32, vp, vp, C.c_uint64, vp, u64p]),
     "sq_gather_utf8_data": (C.c_int32, [vp, vp, C.c_uint64]),

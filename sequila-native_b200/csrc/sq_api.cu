@@ -654,6 +654,81 @@ SQ_API int32_t sq_gather_column_device(sq_stream* s, int32_t side, int32_t build
   return rc;
 }
 
+SQ_API int32_t sq_index_pack_columns(sq_index* idx, const int32_t* col_ids, int32_t n_cols, int32_t* pack_id_out) {
+  if (!idx || !pack_id_out) return SQ_EINVAL;
+  ErrorSlot& E = idx->ctx->err;
+  if (!col_ids || n_cols < 1 || n_cols > 4) return fail(E, SQ_EINVAL, "a pack holds 1 to 4 columns, got %d", n_cols);
+  const uint32_t* cols[4] = {nullptr, nullptr, nullptr, nullptr};
+  {
+    std::lock_guard<std::mutex> g(idx->col_mu);
+    for (int c = 0; c < n_cols; ++c) {
+      if (col_ids[c] < 0 || size_t(col_ids[c]) >= idx->columns.size())
+        return fail(E, SQ_EINVAL, "unknown build column id %d", col_ids[c]);
+      const sq_column& col = idx->columns[size_t(col_ids[c])];
+      if (col.width != 4) return fail(E, SQ_EINVAL, "column %d is %u bytes wide: a pack holds 4-byte columns", col_ids[c], col.width);
+      cols[c] = static_cast<const uint32_t*>(col.d_values);
+    }
+  }
+  SQ_CUDA(E, cudaSetDevice(idx->ctx->device));
+  sq_pack pk;
+  pk.n_cols = n_cols;
+  const size_t bytes = size_t(idx->n_rows ? idx->n_rows : 1) * 16;
+  SQ_CUDA(E, cudaMalloc(&pk.d_rows, bytes));
+  int rc = launch_pack_columns(idx->ctx, cols, n_cols, idx->n_rows, pk.d_rows);
+  if (rc) { cudaFree(pk.d_rows); return rc; }
+  std::lock_guard<std::mutex> g(idx->col_mu);
+  idx->bytes += bytes;
+  idx->packs.push_back(pk);
+  *pack_id_out = int32_t(idx->packs.size() - 1);
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_gather_pack_device(sq_stream* s, int32_t pack_id, void* const* d_outs, int32_t n_outs, uint64_t capacity) {
+  if (!s) return SQ_EINVAL;
+  ErrorSlot& E = s->err;
+  if (!s->emitted) return fail(E, SQ_ESTATE, "sq_gather_pack_device called without a preceding emit");
+  sq_index* idx = const_cast<sq_index*>(s->idx);
+  sq_pack pk;
+  {
+    std::lock_guard<std::mutex> g(idx->col_mu);
+    if (pack_id < 0 || size_t(pack_id) >= idx->packs.size()) return fail(E, SQ_EINVAL, "unknown pack id %d", pack_id);
+    pk = idx->packs[size_t(pack_id)];
+  }
+  if (!d_outs || n_outs < 1 || n_outs > pk.n_cols) return fail(E, SQ_EINVAL, "the pack holds %d columns, %d outputs given", pk.n_cols, n_outs);
+  const uint64_t n = win_pairs(s);
+  if (capacity < n) return fail(E, SQ_ECAPACITY, "gather capacity %llu < %llu", (unsigned long long)capacity, (unsigned long long)n);
+  if (n == 0) return SQ_OK;
+  if (!s->d_last_left) return fail(E, SQ_ESTATE, "left indices were not emitted on the device");
+  uint32_t* outs[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int c = 0; c < n_outs; ++c) {
+    if (!d_outs[c]) return fail(E, SQ_EINVAL, "null gather output %d", c);
+    outs[c] = static_cast<uint32_t*>(d_outs[c]);
+  }
+  SQ_CUDA(E, cudaSetDevice(s->ctx->device));
+  return launch_gather_pack(s, pk.d_rows, s->d_last_left + s->win_off, n, outs, n_outs);
+}
+
+SQ_API int32_t sq_gather_probe_columns_device(sq_stream* s, const void* const* d_probe_values, void* const* d_outs,
+                                              int32_t n_cols, uint64_t capacity) {
+  if (!s) return SQ_EINVAL;
+  ErrorSlot& E = s->err;
+  if (!s->emitted) return fail(E, SQ_ESTATE, "sq_gather_probe_columns_device called without a preceding emit");
+  if (!d_probe_values || !d_outs || n_cols < 1 || n_cols > 4) return fail(E, SQ_EINVAL, "1 to 4 probe columns per pass, got %d", n_cols);
+  const uint64_t n = win_pairs(s);
+  if (capacity < n) return fail(E, SQ_ECAPACITY, "gather capacity %llu < %llu", (unsigned long long)capacity, (unsigned long long)n);
+  if (n == 0) return SQ_OK;
+  if (!s->d_last_right) return fail(E, SQ_ESTATE, "right indices were not emitted on the device");
+  const uint32_t* cols[4] = {nullptr, nullptr, nullptr, nullptr};
+  uint32_t* outs[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int c = 0; c < n_cols; ++c) {
+    if (!d_probe_values[c] || !d_outs[c]) return fail(E, SQ_EINVAL, "null probe column / output %d", c);
+    cols[c] = static_cast<const uint32_t*>(d_probe_values[c]);
+    outs[c] = static_cast<uint32_t*>(d_outs[c]);
+  }
+  SQ_CUDA(E, cudaSetDevice(s->ctx->device));
+  return launch_gather_probe_columns(s, cols, s->d_last_right + s->win_off, n, outs, n_cols);
+}
+
 SQ_API int32_t sq_gather_column(sq_stream* s, int32_t side, int32_t build_col_id, const void* probe_values,
                                 uint32_t width, void* out, uint64_t capacity) {
   if (!s) return SQ_EINVAL;

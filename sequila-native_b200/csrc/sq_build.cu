@@ -395,6 +395,7 @@ void free_index(sq_index* idx) {
     if (c.owned) { cudaFree(c.d_values); cudaFree(c.d_offsets); }
     cudaFree(c.d_validity);
   }
+  for (auto& pk : idx->packs) cudaFree(pk.d_rows);
   delete idx;
 }
 

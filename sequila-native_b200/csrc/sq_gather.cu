@@ -80,6 +80,127 @@ __global__ void __launch_bounds__(256) k_cast_i64(const int64_t* __restrict__ in
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Several columns per pass (include/sequila_cuda.h, "Several columns per pass").
+//   k_pack_columns       rows[i] = {c0[i], c1[i], c2[i], c3[i]} (missing columns = 0): streaming, once per query
+//   k_gather_pack        per pair ONE 16-byte read of the build row serves every packed column; 4 pairs per
+//                        thread in flight; the column stores are coalesced
+//   k_gather_probe_cols  per pair one read of right_idx, then the (sequential, cached) values of every column
+// ---------------------------------------------------------------------------------------------
+struct Ptr4 {
+  const uint32_t* in[4];
+  uint32_t* out[4];
+};
+
+__global__ void __launch_bounds__(256) k_pack_columns(Ptr4 p, int n_cols, uint64_t n, uint4* __restrict__ rows) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint4 v;
+    v.x = __ldg(p.in[0] + i);
+    v.y = n_cols > 1 ? __ldg(p.in[1] + i) : 0u;
+    v.z = n_cols > 2 ? __ldg(p.in[2] + i) : 0u;
+    v.w = n_cols > 3 ? __ldg(p.in[3] + i) : 0u;
+    rows[i] = v;
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(256) k_gather_pack(const uint4* __restrict__ rows, const uint32_t* __restrict__ idx,
+                                                     uint64_t n, Ptr4 p) {
+  constexpr int kPer = 4;
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x * kPer;
+  for (uint64_t base = (uint64_t(blockIdx.x) * blockDim.x) * kPer + threadIdx.x; base < n; base += stride) {
+    uint32_t ix[kPer];
+    uint4 v[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const uint64_t i = base + uint64_t(k) * blockDim.x;
+      ix[k] = i < n ? __ldg(idx + i) : kEmptyRow;
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k)
+      v[k] = ix[k] == kEmptyRow ? make_uint4(0u, 0u, 0u, 0u) : __ldg(rows + ix[k]);  // NULL left side (nearest): zero values
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const uint64_t i = base + uint64_t(k) * blockDim.x;
+      if (i < n) {
+        p.out[0][i] = v[k].x;
+        if (N > 1) p.out[1][i] = v[k].y;
+        if (N > 2) p.out[2][i] = v[k].z;
+        if (N > 3) p.out[3][i] = v[k].w;
+      }
+    }
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(256) k_gather_probe_cols(const uint32_t* __restrict__ idx, uint64_t n, Ptr4 p) {
+  constexpr int kPer = 4;
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x * kPer;
+  for (uint64_t base = (uint64_t(blockIdx.x) * blockDim.x) * kPer + threadIdx.x; base < n; base += stride) {
+    uint32_t ix[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const uint64_t i = base + uint64_t(k) * blockDim.x;
+      ix[k] = i < n ? __ldg(idx + i) : 0u;
+    }
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+      uint32_t v[kPer];
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) v[k] = __ldg(p.in[c] + ix[k]);
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) {
+        const uint64_t i = base + uint64_t(k) * blockDim.x;
+        if (i < n) p.out[c][i] = v[k];
+      }
+    }
+  }
+}
+
+int launch_pack_columns(sq_ctx* ctx, const uint32_t* const* d_cols, int n_cols, uint64_t n_rows, uint4* d_rows) {
+  if (n_rows == 0) return SQ_OK;
+  Ptr4 p{};
+  for (int c = 0; c < n_cols; ++c) p.in[c] = d_cols[c];
+  k_pack_columns<<<grid_for(n_rows, 256, ctx->sm_count), 256>>>(p, n_cols, n_rows, d_rows);
+  SQ_CUDA(ctx->err, cudaGetLastError());
+  SQ_CUDA(ctx->err, cudaDeviceSynchronize());
+  return SQ_OK;
+}
+
+int launch_gather_pack(sq_stream* s, const uint4* d_rows, const uint32_t* d_idx, uint64_t n, uint32_t* const* d_outs, int n_outs) {
+  if (n == 0) return SQ_OK;
+  Ptr4 p{};
+  for (int c = 0; c < n_outs; ++c) p.out[c] = d_outs[c];
+  const int g = grid_for(n, 256 * 4, s->ctx->sm_count);
+  switch (n_outs) {
+    case 1: k_gather_pack<1><<<g, 256, 0, s->stream>>>(d_rows, d_idx, n, p); break;
+    case 2: k_gather_pack<2><<<g, 256, 0, s->stream>>>(d_rows, d_idx, n, p); break;
+    case 3: k_gather_pack<3><<<g, 256, 0, s->stream>>>(d_rows, d_idx, n, p); break;
+    default: k_gather_pack<4><<<g, 256, 0, s->stream>>>(d_rows, d_idx, n, p); break;
+  }
+  SQ_CUDA(s->err, cudaGetLastError());
+  s->launches += 1;
+  return SQ_OK;
+}
+
+int launch_gather_probe_columns(sq_stream* s, const uint32_t* const* d_cols, const uint32_t* d_idx, uint64_t n,
+                                uint32_t* const* d_outs, int n_cols) {
+  if (n == 0) return SQ_OK;
+  Ptr4 p{};
+  for (int c = 0; c < n_cols; ++c) { p.in[c] = d_cols[c]; p.out[c] = d_outs[c]; }
+  const int g = grid_for(n, 256 * 4, s->ctx->sm_count);
+  switch (n_cols) {
+    case 1: k_gather_probe_cols<1><<<g, 256, 0, s->stream>>>(d_idx, n, p); break;
+    case 2: k_gather_probe_cols<2><<<g, 256, 0, s->stream>>>(d_idx, n, p); break;
+    case 3: k_gather_probe_cols<3><<<g, 256, 0, s->stream>>>(d_idx, n, p); break;
+    default: k_gather_probe_cols<4><<<g, 256, 0, s->stream>>>(d_idx, n, p); break;
+  }
+  SQ_CUDA(s->err, cudaGetLastError());
+  s->launches += 1;
+  return SQ_OK;
+}
+
 int launch_cast_i64(sq_stream* s, const int64_t* d_in, uint64_t n, int64_t minus, int32_t* d_out,
                     int64_t* bad_value, bool* bad) {
   ErrorSlot& E = s->err;

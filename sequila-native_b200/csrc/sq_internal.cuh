@@ -122,6 +122,11 @@ struct sq_column {
   uint8_t* d_validity = nullptr;     // optional Arrow validity bitmap (bit i = row i is valid)
 };
 
+struct sq_pack {  // up to four 4-byte build columns interleaved row-wise (sq_index_pack_columns)
+  uint4* d_rows = nullptr;
+  int n_cols = 0;
+};
+
 struct sq_index {
   sq_ctx* ctx = nullptr;
   uint64_t n_rows = 0;
@@ -146,6 +151,7 @@ struct sq_index {
   float build_ms = 0.f;
   std::mutex col_mu;
   std::vector<sq_column> columns;
+  std::vector<sq_pack> packs;
 
   sq::IndexView view() const {
     sq::IndexView v;
@@ -270,6 +276,11 @@ bool use_packed(const sq_index* idx);
 // gather.cu
 int launch_gather(sq_stream* s, const void* d_values, const uint32_t* d_idx, uint64_t n, uint32_t width,
                   void* d_out);
+// row-wise pack of up to four 4-byte columns, and the multi-column gathers over it / over probe columns
+int launch_pack_columns(sq_ctx* ctx, const uint32_t* const* d_cols, int n_cols, uint64_t n_rows, uint4* d_rows);
+int launch_gather_pack(sq_stream* s, const uint4* d_rows, const uint32_t* d_idx, uint64_t n, uint32_t* const* d_outs, int n_outs);
+int launch_gather_probe_columns(sq_stream* s, const uint32_t* const* d_cols, const uint32_t* d_idx, uint64_t n,
+                                uint32_t* const* d_outs, int n_cols);
 int launch_cast_i64(sq_stream* s, const int64_t* d_in, uint64_t n, int64_t minus, int32_t* d_out,
                     int64_t* bad_value, bool* bad);
 int launch_digest(sq_stream* s, const uint32_t* d_left, const uint32_t* d_right, uint64_t n,

@@ -56,8 +56,11 @@ __device__ __forceinline__ StartLine find_start_line(const IndexView& iv, uint32
 // kTiles consecutive tiles per CTA: the probe columns and directory words of ALL of them are requested up
 // front, so only the first tile of a CTA waits for those two round trips (count-only launches use 2; see
 // launch_packed_b for why emitting launches use 1).
+#ifndef SQ_PACKED_THREADS_PER_SM
+#define SQ_PACKED_THREADS_PER_SM 1024  // resident threads per SM the kernel is compiled for (register budget)
+#endif
 template <bool EMIT, bool WRITE_RIGHT, int kPBlock, int kTiles>
-__global__ void __launch_bounds__(kPBlock, 1024 / kPBlock)
+__global__ void __launch_bounds__(kPBlock, SQ_PACKED_THREADS_PER_SM / kPBlock)
 k_probe_packed(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __restrict__ q_start,
                const int32_t* __restrict__ q_end, uint32_t n, uint32_t* __restrict__ cnt_out,
                unsigned long long* chain_state, unsigned int* ticket, unsigned long long* result,

@@ -122,6 +122,13 @@ class CudaIndex:
         self._keep = (self._keep or []) + [tensor]
         return int(cid.value)
 
+    def pack_columns(self, col_ids) -> int:
+        """sq_index_pack_columns: up to four 4-byte build columns interleaved row-wise for one-read-per-pair gathers"""
+        ids = (C.c_int32 * len(col_ids))(*[int(c) for c in col_ids])
+        pid = C.c_int32(-1)
+        _check(self._lib.sq_index_pack_columns(self._h, ids, len(col_ids), C.byref(pid)), self.ctx._err)
+        return int(pid.value)
+
     bytes = property(lambda self: int(self._lib.sq_index_bytes(self._h)))
     rows = property(lambda self: int(self._lib.sq_index_rows(self._h)))
     keys = property(lambda self: int(self._lib.sq_index_keys(self._h)))
@@ -268,6 +275,17 @@ class CudaStream:
     def gather_probe_device(self, values, out):
         _check(self._lib.sq_gather_column_device(self._h, 1, -1, _tptr(values), values.element_size(), _tptr(out),
                                                  out.numel()), self._err)
+
+    def gather_pack_device(self, pack_id: int, outs):
+        """every column of a pack for the pairs of the last emit, one pass (outs: torch CUDA tensors of 4-byte elements)"""
+        ptrs = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+        _check(self._lib.sq_gather_pack_device(self._h, int(pack_id), ptrs, len(outs), min(o.numel() for o in outs)), self._err)
+
+    def gather_probe_columns_device(self, values, outs):
+        """up to four 4-byte probe columns of this tile for the pairs of the last emit, one pass"""
+        vin = (C.c_void_p * len(values))(*[v.data_ptr() for v in values])
+        ptrs = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+        _check(self._lib.sq_gather_probe_columns_device(self._h, vin, ptrs, len(outs), min(o.numel() for o in outs)), self._err)
 
     def counts_device_ptr(self) -> int:
         return int(self._lib.sq_stream_counts_device(self._h) or 0)
