@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-locality", action="store_true", help="skip the position-sorted side measurement")
     ap.add_argument("--no-materialise", action="store_true", help="skip the six-column gather measurement")
+    ap.add_argument("--no-count-only", action="store_true", help="skip the count(1) measurement")
     ap.add_argument("--cpu-sample-contigs", type=int, default=8)
     ap.add_argument("--cpu-sample-probes", type=int, default=2_000_000)
     return ap.parse_args()
@@ -425,6 +426,24 @@ def main():
     e2e_value = probes_total / (e_ms_max * 1e-3)
     pool.shutdown()
 
+    # ---- count only: `select count(1) from a join b on ...` is what the reference's own benchmark queries run
+    # (queries/q1-coitrees.sql:16-19, benches/databio_benchmark.rs); no pair is written
+    count_only = None
+    if not args.no_count_only:
+        for _ in range(3):
+            assert st.probe_count_device(idx, probe["key"], probe["start"], probe["end"]) == n_pairs
+        torch.cuda.synchronize()
+        st.set_profiling(True)
+        for _ in range(min(args.steps, 10)):
+            flush.fill_(1)
+            st.probe_count_device(idx, probe["key"], probe["start"], probe["end"])
+        torch.cuda.synchronize()
+        c_ms = st.phase_ms()["join"]
+        st.set_profiling(False)
+        count_only = {"query": "count(1) of the join", "avg_launch_ms": c_ms, "value": n_probe / (c_ms * 1e-3),
+                      "unit": "probe intervals/s", "algorithmic_bytes": 16.0 * n_probe + 4.0 * n_pairs,
+                      "roofline_frac": (16.0 * n_probe + 4.0 * n_pairs) / (c_ms * 1e-3) / 1e9 / hbm_peak}
+
     # ---- materialise (process_probe_batch's `take` per output column, interval_join.rs:1620-1632): the six output
     # columns of SURVEY §8(d) — contig (dictionary id, int32), pos_start, pos_end of both sides — gathered on the
     # device from the pairs of the last step; B_gather = 8 B pair read + 2 x 4 B per column = 56 B per pair.
@@ -546,6 +565,8 @@ def main():
             result["locality"] = locality
         if materialise:
             result["materialise"] = materialise
+        if count_only:
+            result["count_only"] = count_only
         if not args.no_cpu_baseline:
             os.sched_setaffinity(0, all_cpus)
             if args.workload == "cfg5_shard":
