@@ -399,8 +399,11 @@ void free_index(sq_index* idx) {
   delete idx;
 }
 
-// Temporaries of a build (sort double buffers, scan tiles: several GB for 100M rows) come from the
-// stream-ordered allocator: the device's default pool keeps them between builds instead of returning them
+// The index arrays themselves and the temporaries of a build (sort double buffers, scan tiles: several GB for
+// 100M rows) come from the stream-ordered allocator (cudaFree in free_index hands pool memory back to the
+// pool): a build in a long-running process reuses what earlier queries released — nine cudaMalloc calls of
+// hundreds of MB inside the build cost 12-24 ms per 100M rows, more than all its kernels together (10 ms).
+// Temporaries: the device's default pool keeps them between builds instead of returning them
 // to the driver (cudaMalloc / cudaFree of GB-sized blocks cost tens of milliseconds and synchronise).
 struct TmpFree {
   cudaStream_t st;
@@ -455,7 +458,7 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
   uint32_t cap = 4096;
   HtStatus hs{};
   for (;;) {
-    SQ_CUDA(E, cudaMalloc(&idx->d_ht_keys, size_t(cap) * 8));
+    SQ_CUDA(E, cudaMallocAsync(&idx->d_ht_keys, size_t(cap) * 8, st));
     SQ_CUDA(E, cudaMemsetAsync(idx->d_ht_keys, 0xFF, size_t(cap) * 8, st));
     SQ_CUDA(E, cudaMemsetAsync(d_status, 0, sizeof(HtStatus) + 16, st));
     if (n) {
@@ -474,7 +477,7 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     cap = uint32_t(uint64_t(cap) * 16 > max_cap ? max_cap : uint64_t(cap) * 16);
   }
   idx->ht_cap = cap;
-  SQ_CUDA(E, cudaMalloc(&idx->d_ht_ids, size_t(cap) * 4));
+  SQ_CUDA(E, cudaMallocAsync(&idx->d_ht_ids, size_t(cap) * 4, st));
   k_ht_assign<<<(cap + 255) / 256, 256, 0, st>>>(idx->d_ht_keys, idx->d_ht_ids, cap, d_counter);
   SQ_CUDA(E, cudaGetLastError());
   uint32_t n_keys = hs.distinct;
@@ -482,11 +485,11 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
   idx->n_keys = n_keys;
 
   // 2. sorted arrays
-  SQ_CUDA(E, cudaMalloc(&idx->d_start, (n ? n : 1) * 4));
-  SQ_CUDA(E, cudaMalloc(&idx->d_runmax, (n ? n : 1) * 4));
-  SQ_CUDA(E, cudaMalloc(&idx->d_end, (n ? n : 1) * 4));
-  SQ_CUDA(E, cudaMalloc(&idx->d_row, (n ? n : 1) * 4));
-  SQ_CUDA(E, cudaMalloc(&idx->d_meta, (size_t(n_keys) + 1) * sizeof(SegMeta)));
+  SQ_CUDA(E, cudaMallocAsync(&idx->d_start, (n ? n : 1) * 4, st));
+  SQ_CUDA(E, cudaMallocAsync(&idx->d_runmax, (n ? n : 1) * 4, st));
+  SQ_CUDA(E, cudaMallocAsync(&idx->d_end, (n ? n : 1) * 4, st));
+  SQ_CUDA(E, cudaMallocAsync(&idx->d_row, (n ? n : 1) * 4, st));
+  SQ_CUDA(E, cudaMallocAsync(&idx->d_meta, (size_t(n_keys) + 1) * sizeof(SegMeta), st));
   idx->bytes = uint64_t(n ? n : 1) * 16 + (uint64_t(n_keys) + 1) * sizeof(SegMeta) + uint64_t(cap) * 12;
 
   if (n) {
@@ -549,7 +552,7 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     h_meta[n_keys] = SegMeta{};
     h_meta[n_keys].sb = h_meta[n_keys].se = uint32_t(n);
     SQ_CUDA(E, cudaMemcpyAsync(idx->d_meta, h_meta.data(), (size_t(n_keys) + 1) * sizeof(SegMeta), cudaMemcpyHostToDevice, st));
-    SQ_CUDA(E, cudaMalloc(&idx->d_dir, dir_total * 4));
+    SQ_CUDA(E, cudaMallocAsync(&idx->d_dir, dir_total * 4, st));
     idx->bytes += dir_total * 4;
     idx->dir_bytes = dir_total * 4;
     k_fill_dir<<<g, 256, 0, st>>>(d_k1, idx->d_start, n, idx->d_meta, idx->d_dir);
@@ -575,13 +578,13 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     SQ_CUDA(E, cudaGetLastError());
     k_seg_lines<<<(n_keys + 256) / 256, 256, 0, st>>>(d_line_incl, n_keys, n, idx->d_meta);
     SQ_CUDA(E, cudaGetLastError());
-    SQ_CUDA(E, cudaMalloc(&idx->d_dir_line, dir_total * 4));
+    SQ_CUDA(E, cudaMallocAsync(&idx->d_dir_line, dir_total * 4, st));
     k_fill_dir_line<<<grid_for(dir_total, 256, ctx->sm_count), 256, 0, st>>>(idx->d_dir, dir_total, d_line_incl, idx->d_dir_line);
     SQ_CUDA(E, cudaGetLastError());
     unsigned long long* d_pstat = nullptr;
     SQ_CUDA(E, tmp.alloc(&d_pstat, 16));
     SQ_CUDA(E, cudaMemsetAsync(d_pstat, 0, 16, st));
-    SQ_CUDA(E, cudaMalloc(&idx->d_lines, line_total * 128));
+    SQ_CUDA(E, cudaMallocAsync(&idx->d_lines, line_total * 128, st));
     k_pack_lines<<<unsigned((line_total * 8 + 255) / 256), 256, 0, st>>>(idx->d_start, idx->d_end, idx->d_runmax, idx->d_row,
                                                                           idx->d_meta, n_keys, line_total, d_line_first,
                                                                           d_line_incl, idx->d_lines, d_pstat);
