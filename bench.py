@@ -197,7 +197,14 @@ def cpu_baseline(args, build_h, probe_h, threads, min_seconds=1.0, index=None):
         secs.append(sec)
     sec = float(np.mean(secs))
     n = len(p["key"])
-    return {"value": n / sec, "unit": "probe intervals/s", "cores": threads, "target_partitions": threads, "kind": "port",
+    # T = 1, the setting of the reference's own benchmarks (benches/databio_benchmark.rs:125,141, README.md:39-41:
+    # target_partitions = 1), on a slice of the same sample so that it stays around a second
+    one = None
+    if threads > 1 and not index:
+        m = max(min(n // max(threads // 2, 1), n), 1)
+        s1, _, _ = idx.time_probe(p["key"][:m], p["start"][:m], p["end"][:m], threads=1, batch_rows=8192)
+        one = {"value": m / s1, "cores": 1, "target_partitions": 1, "probe_rows": int(m), "seconds": s1}
+    return {"one_thread": one, "value": n / sec, "unit": "probe intervals/s", "cores": threads, "target_partitions": threads, "kind": "port",
             "sample": f"{what}: {len(b['key'])} build rows, {n} probe rows, {pairs} pairs per pass, {len(secs)} passes of "
                       f"{sec:.3f}s ({sum(secs) * threads:.0f} core-seconds), index build {idx.build_seconds:.2f}s (1 thread); "
                       f"coitrees 0.4.0 AVX2-layout restatement, 8192-row batches dealt to {threads} thread(s)",
@@ -235,10 +242,12 @@ def run_reference(args, rank, world):
     vals = []
     base = None
     index = None
+    one_thread = None
     t_all = time.time()
     for it in range(args.warmup + args.steps):  # one step = one timed pass set over the bounded sample
         base = cpu_baseline(args, build_h, probe_h, threads, min_seconds=0.5, index=index)
         index = base.pop("_index")
+        one_thread = base.get("one_thread") or (one_thread if it else None)  # measured with the first pass set
         if it >= args.warmup:
             vals.append(base)
         if len(vals) >= 3 and time.time() - t_all > 150:
@@ -246,6 +255,7 @@ def run_reference(args, rank, world):
     v = float(np.mean([b["value"] for b in vals]))
     ms = float(np.mean([b["seconds"] for b in vals])) * 1e3
     base["value"] = v
+    base["one_thread"] = one_thread
     print(json.dumps({
         "impl": "reference", "metric": "probe_intervals_per_s", "value": v, "unit": "probe intervals/s",
         "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup, "ms_per_step": ms,
