@@ -44,19 +44,98 @@ struct __align__(16) RowState {
   uint32_t cnt_reach;  // [30:0] hits so far, [31] the last line said "an earlier row still reaches qs"
   uint32_t pad;
 };
+#ifndef SQ_WALK_DUMMY
+#define SQ_WALK_DUMMY 1
+#endif
 struct __align__(16) WalkShared {
-  RowState row[32];   // indexed by owner lane
+  RowState row[33];   // indexed by owner lane; [32] = a record no build row can hit (slots no row uses point at it)
   uint32_t line[32];  // line to fetch, indexed by slot = group * 8 + step
   uint8_t inv[32];    // owner lane, indexed by slot
 };
 
+// Variant for count-only launches.  Row records live in SLOT order (slot = group * 8 + step) for the duration of a round: a step reads its record at
+// a fixed offset from the lane's group base (no owner decode, no address arithmetic) and the record names its
+// owner lane; slots past the last walking row hold a record no build row can hit (qs = INT32_MAX, qe = INT32_MIN)
+// and fetch line 0, so a step needs no "is this slot in use" predicate either.  Measured against the owner-order
+// walk below (same box, ms per 12.5M probe rows): count only 0.642 vs 0.662; emitting 1.067 vs 1.028 (the stash
+// address now depends on the record just loaded), position-sorted emitting 0.893 vs 0.890 — hence count only.
 template <bool EMIT>
-__device__ __forceinline__ void walk_rounds(const IndexView& iv, uint32_t* stash, WalkShared& ws, int32_t my_qs,
+__device__ __forceinline__ void walk_rounds_slot_order(const IndexView& iv, uint32_t* stash, WalkShared& ws, int32_t my_qs,
                                             int32_t my_qe, uint32_t first, bool& walking, uint32_t& ln, uint32_t& cnt) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 3, sub = lane & 7, g0 = g * 8;
   const uint4* __restrict__ my_lines = iv.lines + sub;
+  RowState* grp = ws.row + g0;  // the eight records of my group, one per step
+  for (;;) {
+    const unsigned A = __ballot_sync(0xffffffffu, walking);
+    if (A == 0) break;
+    const int n_walk = __popc(A);
+    const int r = __popc(A & ((1u << lane) - 1u));  // my rank: served in step r >> 2 by group r & 3
+    const int slot = (r & 3) * 8 + (r >> 2);
+    __syncwarp();
+    ws.row[lane] = RowState{INT32_MAX, INT32_MIN, 0u, uint32_t(lane)};
+    ws.line[lane] = 0u;
+    __syncwarp();
+    if (walking) {
+      ws.row[slot] = RowState{my_qs, my_qe, cnt, uint32_t(lane)};
+      ws.line[slot] = ln;
+    }
+    __syncwarp();
+    const uint4 la = *reinterpret_cast<const uint4*>(ws.line + g0), lb = *reinterpret_cast<const uint4*>(ws.line + g0 + 4);
+    const uint32_t lines8[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+    const int n_steps = (n_walk + 3) >> 2;
+    uint4 v[8];
+#pragma unroll
+    for (int st = 0; st < 8; ++st)
+      if (st < n_steps)  // warp-uniform: later rounds have few steps
+        v[st] = __ldg(my_lines + size_t(lines8[st]) * 8);
+#pragma unroll
+    for (int st = 0; st < 8; ++st) {
+      if (st >= n_steps) break;  // warp-uniform
+      const RowState rs = grp[st];
+      const uint32_t c0 = rs.cnt_reach;
+      const uint4 d = v[st];
+      const int32_t base = int32_t(__shfl_sync(0xffffffffu, d.x, g0));
+      const Slots s = slots_of(d, sub);
+      const bool ha = row_hits(s.a_lo, s.a_id, base, rs.qs, rs.qe);
+      const bool hb = row_hits(s.b_lo, s.b_id, base, rs.qs, rs.qe);
+      const uint32_t ma = (__ballot_sync(0xffffffffu, ha) >> g0) & 0xFFu;
+      const uint32_t mb = (__ballot_sync(0xffffffffu, hb) >> g0) & 0xFFu;
+      if (EMIT) {
+        const uint32_t below = (1u << sub) - 1u;
+        const uint32_t pa = c0 + __popc(ma & below);
+        const uint32_t pb = c0 + __popc(ma) + __popc(mb & below);
+        uint32_t* mine = stash + rs.pad * kStride;
+        if (ha && pa < kSlots) mine[pa] = s.a_id;
+        if (hb && pb < kSlots) mine[pb] = s.b_id;
+      }
+      // the group's first lane holds the line header: new count and "an earlier row still reaches qs"
+      if (sub == 0) grp[st].cnt_reach = (c0 + __popc(ma) + __popc(mb)) | (int32_t(d.y) >= rs.qs ? 0x80000000u : 0u);
+    }
+    __syncwarp();
+    if (walking) {
+      const uint32_t cr = ws.row[slot].cnt_reach;
+      cnt = cr & 0x7FFFFFFFu;
+      walking = (cr >> 31) != 0u && ln > first;
+      ln -= 1;
+    }
+  }
+}
+
+template <bool EMIT>
+__device__ __forceinline__ void walk_rounds(const IndexView& iv, uint32_t* stash, WalkShared& ws, int32_t my_qs,
+                                            int32_t my_qe, uint32_t first, bool& walking, uint32_t& ln, uint32_t& cnt) {
+  if (!EMIT) {
+    walk_rounds_slot_order<false>(iv, stash, ws, my_qs, my_qe, first, walking, ln, cnt);
+    return;
+  }
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 3, sub = lane & 7, g0 = g * 8;
+  const uint4* __restrict__ my_lines = iv.lines + sub;
   ws.row[lane] = RowState{my_qs, my_qe, 0u, 0u};
+#if SQ_WALK_DUMMY
+  if (lane == 0) ws.row[32] = RowState{INT32_MAX, INT32_MIN, 0u, 0u};
+#endif
   for (;;) {
     const unsigned A = __ballot_sync(0xffffffffu, walking);
     if (A == 0) break;
@@ -64,6 +143,9 @@ __device__ __forceinline__ void walk_rounds(const IndexView& iv, uint32_t* stash
     const int r = __popc(A & ((1u << lane) - 1u));  // my rank: served in step r >> 2 by group r & 3
     __syncwarp();
     ws.line[lane] = 0u;  // slots past the last walking row fetch line 0 (always there) and are ignored
+#if SQ_WALK_DUMMY
+    ws.inv[lane] = 32;   // ... and test it against the record nothing hits: a step needs no "slot in use" predicate
+#endif
     __syncwarp();
     if (walking) {
       const int slot = (r & 3) * 8 + (r >> 2);
@@ -83,8 +165,13 @@ __device__ __forceinline__ void walk_rounds(const IndexView& iv, uint32_t* stash
 #pragma unroll
     for (int st = 0; st < 8; ++st) {
       if (st >= n_steps) break;  // warp-uniform
+#if SQ_WALK_DUMMY
+      const int p = int(srcs >> (8 * st)) & 63;
+      const bool valid = true;
+#else
       const int p = int(srcs >> (8 * st)) & 31;
       const bool valid = 4 * st + g < n_walk;
+#endif
       const RowState rs = ws.row[p];
       const uint32_t c0 = rs.cnt_reach & 0x7FFFFFFFu;
       const uint4 d = v[st];
@@ -114,6 +201,8 @@ __device__ __forceinline__ void walk_rounds(const IndexView& iv, uint32_t* stash
     }
   }
 }
+
+
 
 // ---------------------------------------------------------------------------------------------
 // Chained scan with decoupled look-back over tiles (one 64-bit word per tile: [63:62] status).  Called
