@@ -317,13 +317,23 @@ __global__ void __launch_bounds__(256) k_seg_lines(const uint32_t* __restrict__ 
   meta[id].line_base = id < n_keys ? line_incl[meta[id].sb] - 1u : line_incl[n - 1];  // sentinel entry: the line total
 }
 
-// dir_line[e] = line of the last row below directory entry e (= line holding the last start <= any qe of bin e - 1)
+// dir_line[e] = {L, T}: L = line of the last row below directory entry e (= the last line that can hold a start <=
+// any qe of bin e - 1), T = the start of L's first row.  A probe with qe < T starts one line earlier: L begins past
+// qe, so it holds no candidate (a bin's 8-16 rows straddle a line boundary about half of the time), and the same
+// 8-byte load that names the line says so — no read of the line, no second lookup.
 __global__ void __launch_bounds__(256) k_fill_dir_line(const uint32_t* __restrict__ dir, uint64_t n_entries,
-                                                       const uint32_t* __restrict__ line_incl, uint32_t* __restrict__ dir_line) {
+                                                       const uint32_t* __restrict__ line_incl,
+                                                       const uint32_t* __restrict__ line_first,
+                                                       const int32_t* __restrict__ s_start, uint2* __restrict__ dir_line) {
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
   for (uint64_t e = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; e < n_entries; e += stride) {
     const uint32_t r = dir[e];
-    dir_line[e] = r ? line_incl[r - 1u] - 1u : 0u;
+    uint2 v = make_uint2(0u, uint32_t(INT32_MIN));
+    if (r) {
+      v.x = line_incl[r - 1u] - 1u;
+      v.y = uint32_t(s_start[line_first[v.x]]);
+    }
+    dir_line[e] = v;
   }
 }
 
@@ -578,8 +588,9 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     SQ_CUDA(E, cudaGetLastError());
     k_seg_lines<<<(n_keys + 256) / 256, 256, 0, st>>>(d_line_incl, n_keys, n, idx->d_meta);
     SQ_CUDA(E, cudaGetLastError());
-    SQ_CUDA(E, cudaMallocAsync(&idx->d_dir_line, dir_total * 4, st));
-    k_fill_dir_line<<<grid_for(dir_total, 256, ctx->sm_count), 256, 0, st>>>(idx->d_dir, dir_total, d_line_incl, idx->d_dir_line);
+    SQ_CUDA(E, cudaMallocAsync(&idx->d_dir_line, dir_total * 8, st));
+    k_fill_dir_line<<<grid_for(dir_total, 256, ctx->sm_count), 256, 0, st>>>(idx->d_dir, dir_total, d_line_incl, d_line_first,
+                                                                             idx->d_start, idx->d_dir_line);
     SQ_CUDA(E, cudaGetLastError());
     unsigned long long* d_pstat = nullptr;
     SQ_CUDA(E, tmp.alloc(&d_pstat, 16));
@@ -600,7 +611,7 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     } else {
       idx->n_lines = line_total;
       idx->mean_back_lines = float(double(h_pstat[1]) / double(line_total));
-      idx->bytes += line_total * 128 + dir_total * 4;
+      idx->bytes += line_total * 128 + dir_total * 8;
     }
   }
   SQ_CUDA(E, cudaEventRecord(e1, st));

@@ -67,7 +67,7 @@ struct IndexView {
   uint32_t n_keys;
   uint32_t n_rows;
   const uint4* __restrict__ lines;      // packed lines (nullptr when the index is not "narrow")
-  const uint32_t* __restrict__ dir_line; // directory entry -> line holding the last row below it
+  const uint2* __restrict__ dir_line;   // directory entry -> {line holding the last row below it, that line's first start}
 };
 
 #ifdef __CUDACC__
@@ -140,7 +140,7 @@ struct sq_index {
   uint32_t* d_dir = nullptr;
   uint64_t dir_bytes = 0;
   uint4* d_lines = nullptr;    // packed lines, or nullptr (wide / inverted intervals: SoA path only)
-  uint32_t* d_dir_line = nullptr;
+  uint2* d_dir_line = nullptr;
   uint64_t n_lines = 0;
   float mean_back_lines = 0.f; // mean number of extra lines a probe landing on a line's last row walks back
   uint64_t* d_ht_keys = nullptr;

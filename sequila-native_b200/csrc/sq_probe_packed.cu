@@ -47,8 +47,14 @@ __device__ __forceinline__ StartLine find_start_line(const IndexView& iv, uint32
   const uint32_t b = m.shift >= 32 ? 0u : (off >> m.shift);
   // directory entry b + 1 = first row whose bin is > b: every row with start <= qe lies below it, and
   // dir_line gives the line of the last such row directly
-  r.line = __ldg(iv.dir_line + m.dir_base + (b >= m.nbins ? m.nbins : b + 1u));
+  const uint2 e = __ldg(iv.dir_line + m.dir_base + (b >= m.nbins ? m.nbins : b + 1u));
   r.first = m.line_base;
+  // e.y = first start of line e.x: when it lies past qe the line holds no candidate and the walk starts a line earlier
+#ifdef SQ_NO_LINE_SKIP  // A/B builds only
+  r.line = e.x;
+#else
+  r.line = e.x - ((qe < int32_t(e.y) && e.x > r.first) ? 1u : 0u);
+#endif
   r.act = true;
   return r;
 }
