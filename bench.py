@@ -435,6 +435,24 @@ def main():
     e_ms = (time.perf_counter() - e0) * 1e3 / args.e2e_steps
     e_ms_max, _, _ = reduce_step(e_ms, 0, 0, device)
     e2e_value = probes_total / (e_ms_max * 1e-3)
+
+    # the same through sq_probe_count: `select count(1)` end to end (host columns in, one number out) — the query
+    # shape of the reference's own benchmarks (queries/q1-coitrees.sql:16-19); only the H2D copy is left on the wire
+    def count_partition(wk):
+        got = 0
+        for t in wk["tiles"]:
+            lo, hi = int(bounds[t]), int(bounds[t + 1])
+            got += wk["st"].probe_count(idx, hk[lo:hi], hs[lo:hi], he[lo:hi])
+        return got
+
+    assert sum(pool.map(count_partition, workers)) == n_pairs
+    torch.cuda.synchronize()
+    c0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        sum(pool.map(count_partition, workers))
+    torch.cuda.synchronize()
+    ec_ms = (time.perf_counter() - c0) * 1e3 / args.e2e_steps
+    ec_ms_max, _, _ = reduce_step(ec_ms, 0, 0, device)
     pool.shutdown()
 
     # ---- count only: `select count(1) from a join b on ...` is what the reference's own benchmark queries run
@@ -568,7 +586,10 @@ def main():
                     else 8 * n_pairs + 16 * n_tiles,
                     "wire": "left_idx u32 per pair + per-row counts u32; right_idx is expanded from the counts into the caller's "
                             "host buffer by the calling thread (interval_join.rs:1611-1618)", "ms_per_step": e_ms_max,
-                    "steps": args.e2e_steps, "api": "sq_probe_join (host C ABI), pinned host buffers", "partitions": T, "tiles": n_tiles},
+                    "steps": args.e2e_steps, "api": "sq_probe_join (host C ABI), pinned host buffers", "partitions": T, "tiles": n_tiles,
+                    "count_only": {"value": probes_total / (ec_ms_max * 1e-3), "unit": "probe intervals/s", "ms_per_step": ec_ms_max,
+                                   "api": "sq_probe_count (host C ABI): count(1) of the join, host columns in, one number out",
+                                   "h2d_bytes_per_step": 16 * n_probe, "d2h_bytes_per_step": 8 * n_tiles}},
             "gpu_launches": int(launches), "clocks": clocks,
             "digest": {"pairs": dg[0], "sum": dg[1], "xor": dg[2]},
         }
