@@ -234,12 +234,13 @@ int launch_packed(sq_stream* s, const sq_index* idx, const uint64_t* d_key, cons
   SQ_CUDA(E, cudaMemsetAsync(result, 0, 32, s->stream));
   const IndexView iv = idx->view();
   if (s->ctx->l2_persist_bytes && s->l2_window_idx != idx && idx->dir_bytes) {
-    // optional (SQ_L2_PERSIST_MB): keep the bin directory, the one structure every probe row reads at a
-    // random place, in the persisting part of L2; everything else streams through the rest
+    // optional (SQ_L2_PERSIST_MB): keep the line directory (8-byte entries, same entry count as the 4-byte row
+    // directory), the one structure every probe row reads at a random place, in the persisting part of L2;
+    // everything else streams through the rest
     cudaStreamAttrValue av{};
-    size_t win = size_t(idx->dir_bytes);
+    size_t win = size_t(idx->dir_bytes) * 2;
     if (win > s->ctx->l2_window_max) win = s->ctx->l2_window_max;
-    av.accessPolicyWindow.base_ptr = idx->d_dir;
+    av.accessPolicyWindow.base_ptr = idx->d_dir_line;
     av.accessPolicyWindow.num_bytes = win;
     const double ratio = double(s->ctx->l2_persist_bytes) / double(win);
     av.accessPolicyWindow.hitRatio = float(ratio > 1.0 ? 1.0 : ratio);

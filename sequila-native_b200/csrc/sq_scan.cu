@@ -485,7 +485,11 @@ int copy_text_to_device(sq_stream* s, uint8_t* d_text, const uint8_t* text, uint
   int rc;
   if ((rc = ensure(E, s->h_scan, kChunk * kThreads * kSlots, true))) return rc;
   auto* ring = static_cast<uint8_t*>(s->h_scan.p);
-  cudaEvent_t done[kThreads][kSlots];
+  cudaEvent_t done[kThreads][kSlots] = {};
+  struct Events {  // destroyed on every way out
+    cudaEvent_t (&ev)[kThreads][kSlots];
+    ~Events() { for (auto& t : ev) for (auto& e : t) if (e) cudaEventDestroy(e); }
+  } events{done};
   for (auto& t : done)
     for (auto& e : t) SQ_CUDA(E, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   const uint64_t n_chunks = (n + kChunk - 1) / kChunk;
@@ -510,8 +514,6 @@ int copy_text_to_device(sq_stream* s, uint8_t* d_text, const uint8_t* text, uint
   for (auto& x : th) x.join();
   // the ring is reused by the next call: every DMA out of it must be over before this one returns
   cudaError_t e = cudaStreamSynchronize(s->stream);
-  for (auto& t : done)
-    for (auto& ev : t) cudaEventDestroy(ev);
   if (failed || e != cudaSuccess) {
     cudaGetLastError();
     return fail(E, SQ_ECUDA, "host-to-device copy of the text failed: %s", cudaGetErrorString(e));
