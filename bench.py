@@ -204,7 +204,23 @@ def cpu_baseline(args, build_h, probe_h, threads, min_seconds=1.0, index=None):
         m = max(min(n // max(threads // 2, 1), n), 1)
         s1, _, _ = idx.time_probe(p["key"][:m], p["start"][:m], p["end"][:m], threads=1, batch_rows=8192)
         one = {"value": m / s1, "cores": 1, "target_partitions": 1, "probe_rows": int(m), "seconds": s1}
-    return {"one_thread": one, "value": n / sec, "unit": "probe intervals/s", "cores": threads, "target_partitions": threads, "kind": "port",
+    # the reference's OWN superintervals.hpp (its `SuperIntervals` arm, which its tests require to return the same rows
+    # as `Coitrees`, IJ:1752-1758), compiled from /root/reference into oracle/_ref: a reference-authored anchor next to
+    # the coitrees restatement, same sample, same threads, same batch dealing
+    ref_si = None
+    if not index and O.ref_timing_available():
+        try:
+            si = O.RefSuperIntervalsIndex(b["key"], b["start"], b["end"])
+            si.time_probe(p["key"], p["start"], p["end"], threads=threads, batch_rows=8192)  # warm-up
+            s_sec, s_pairs = si.time_probe(p["key"], p["start"], p["end"], threads=threads, batch_rows=8192)
+            assert s_pairs == pairs, (s_pairs, pairs)  # the two reference algorithms agree on the sample
+            ref_si = {"value": n / s_sec, "unit": "probe intervals/s", "kind": "reference", "cores": threads,
+                      "what": "superintervals.hpp from the reference tree (Algorithm::SuperIntervals arm), oracle/_ref/libsi_ref.so",
+                      "seconds": s_sec, "index_build_seconds": si.build_seconds}
+            del si
+        except Exception as ex:  # the anchor is optional; the coitrees restatement above is the baseline
+            ref_si = {"unavailable": repr(ex)}
+    return {"reference_superintervals": ref_si, "one_thread": one, "value": n / sec, "unit": "probe intervals/s", "cores": threads, "target_partitions": threads, "kind": "port",
             "sample": f"{what}: {len(b['key'])} build rows, {n} probe rows, {pairs} pairs per pass, {len(secs)} passes of "
                       f"{sec:.3f}s ({sum(secs) * threads:.0f} core-seconds), index build {idx.build_seconds:.2f}s (1 thread); "
                       f"coitrees 0.4.0 AVX2-layout restatement, 8192-row batches dealt to {threads} thread(s)",
@@ -243,11 +259,13 @@ def run_reference(args, rank, world):
     base = None
     index = None
     one_thread = None
+    ref_si = None
     t_all = time.time()
     for it in range(args.warmup + args.steps):  # one step = one timed pass set over the bounded sample
         base = cpu_baseline(args, build_h, probe_h, threads, min_seconds=0.5, index=index)
         index = base.pop("_index")
         one_thread = base.get("one_thread") or (one_thread if it else None)  # measured with the first pass set
+        ref_si = base.get("reference_superintervals") or (ref_si if it else None)
         if it >= args.warmup:
             vals.append(base)
         if len(vals) >= 3 and time.time() - t_all > 150:
@@ -256,6 +274,7 @@ def run_reference(args, rank, world):
     ms = float(np.mean([b["seconds"] for b in vals])) * 1e3
     base["value"] = v
     base["one_thread"] = one_thread
+    base["reference_superintervals"] = ref_si
     print(json.dumps({
         "impl": "reference", "metric": "probe_intervals_per_s", "value": v, "unit": "probe intervals/s",
         "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup, "ms_per_step": ms,

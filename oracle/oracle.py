@@ -80,6 +80,14 @@ def _ref():
         L.siref_join.argtypes = [_u64p, _i32p, _i32p, C.c_uint64, _u64p, _i32p, _i32p, C.c_uint64,
                                  C.POINTER(_u32p), C.POINTER(_u32p)]
         L.siref_free.argtypes = [C.c_void_p]
+        if hasattr(L, "siref_build"):  # timing entry points (bench.py cpu_baseline)
+            L.siref_build.restype = C.c_void_p
+            L.siref_build.argtypes = [_u64p, _i32p, _i32p, C.c_uint64]
+            L.siref_build_seconds.restype = C.c_double
+            L.siref_build_seconds.argtypes = [C.c_void_p]
+            L.siref_time_probe.restype = C.c_double
+            L.siref_time_probe.argtypes = [C.c_void_p, _u64p, _i32p, _i32p, C.c_uint64, C.c_int32, C.c_uint32, _u64p]
+            L.siref_destroy.argtypes = [C.c_void_p]
         _REF = L
     return _REF
 
@@ -196,6 +204,33 @@ def ref_superintervals_join(bkey, bstart, bend, pkey, pstart, pend):
                           _p(pk, _u64p), _p(ps, _i32p), _p(pe, _i32p), pk.shape[0],
                           C.byref(lp), C.byref(rp))
     return _take_pairs(_ref().siref_free, int(m), lp, rp)
+
+
+class RefSuperIntervalsIndex:
+    """The reference's own superintervals library (its `SuperIntervals` algorithm arm, IJ:858-870, 1012-1017),
+    compiled from /root/reference into oracle/_ref/libsi_ref.so: build once, time the probe loop."""
+
+    def __init__(self, bkey, bstart, bend):
+        bk, bs, be = _c(bkey, np.uint64), _c(bstart, np.int32), _c(bend, np.int32)
+        self._h = _ref().siref_build(_p(bk, _u64p), _p(bs, _i32p), _p(be, _i32p), bk.shape[0])
+        self.build_seconds = float(_ref().siref_build_seconds(self._h))
+
+    def time_probe(self, pkey, pstart, pend, threads=1, batch_rows=8192):
+        pk, ps, pe = _c(pkey, np.uint64), _c(pstart, np.int32), _c(pend, np.int32)
+        pairs = C.c_uint64(0)
+        sec = _ref().siref_time_probe(self._h, _p(pk, _u64p), _p(ps, _i32p), _p(pe, _i32p), pk.shape[0], int(threads),
+                                      int(batch_rows), C.byref(pairs))
+        return float(sec), int(pairs.value)
+
+    def __del__(self):
+        try:
+            _ref().siref_destroy(self._h)
+        except Exception:
+            pass
+
+
+def ref_timing_available() -> bool:
+    return ref_available() and hasattr(_ref(), "siref_build")
 
 
 NULL_INDEX = 0xFFFFFFFF

@@ -94,6 +94,20 @@ def test_against_reference_superintervals(oracle):
         assert np.array_equal(oracle.sorted_pairs(l, r), oracle.sorted_pairs(rl, rr))
 
 
+def test_reference_superintervals_timing_entry_points_count_the_same_pairs(oracle):
+    """the probe-loop timer over the reference's library (bench.py's `reference_superintervals` anchor) visits the same
+    pairs as the coitrees restatement, single- and multi-threaded"""
+    if not oracle.ref_timing_available():
+        pytest.skip("oracle/_ref/libsi_ref.so without the timing entry points")
+    rng = np.random.default_rng(5)
+    case = _random_case(rng, 20000, 30000, 5, 200000, 300, False)
+    l, _, _ = oracle.join(*case, variant=8)
+    si = oracle.RefSuperIntervalsIndex(*case[:3])
+    for threads in (1, 3):
+        sec, pairs = si.time_probe(*case[3:], threads=threads, batch_rows=1000)
+        assert pairs == len(l) and sec > 0
+
+
 def test_reference_fixture_through_superintervals_ref(oracle, golden):
     if not oracle.ref_available():
         pytest.skip("oracle/_ref/libsi_ref.so not built")
