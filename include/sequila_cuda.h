@@ -227,6 +227,12 @@ int32_t sq_cast_i64_to_i32(sq_stream* s, const int64_t* values, uint64_t n, int6
 int32_t sq_pairs_digest_device(sq_stream* s, const uint32_t* d_left, const uint32_t* d_right,
                                uint64_t n_pairs, uint64_t right_offset, uint64_t out3[3]);
 
+/* Test / tuning hook of the host-side expansion of right_idx from the per-row counts (the wire format of the
+ * host entry points, IJ:1611-1618): runs ONE named variant (-1 = the widest the CPU supports = what the library
+ * uses, 0 scalar, 1 SSE2, 2 AVX2, 3 AVX-512); returns 0 when the CPU lacks it, else 1.  No device involved. */
+int32_t sq_rle_expand_variant(int32_t variant, const uint32_t* counts, uint32_t n_rows, uint32_t* right_idx_out,
+                              uint64_t n_pairs);
+
 /* Per-phase device timings (ms), averaged over the calls since sq_stream_set_profiling(s, 1),
  * measured with CUDA events recorded on the stream around each phase:
  * [0]=h2d [1]=fused probe kernel of count/join calls [2]=probe kernel re-run by emit calls

@@ -66,6 +66,7 @@ SIGNATURES = {
     "sq_stream_set_window": (C.c_int32, [vp, C.c_uint64, C.c_uint64]),
     "sq_fetch_pairs": (C.c_int32, [vp, vp, vp, C.c_uint64]),
     "sq_cast_i64_to_i32": (C.c_int32, [vp, vp, C.c_uint64, C.c_int64, vp]),
+    "sq_rle_expand_variant": (C.c_int32, [C.c_int32, vp, C.c_uint32, vp, C.c_uint64]),
     "sq_pairs_digest_device": (C.c_int32, [vp, vp, vp, C.c_uint64, C.c_uint64, u64p]),
     "sq_stream_set_profiling": (C.c_int32, [vp, C.c_int32]),
     "sq_stream_phase_ms": (C.c_int32, [vp, f32p]),

@@ -481,37 +481,8 @@ static int32_t launch_emit(sq_stream* s, uint32_t* d_left, uint32_t* d_right, ui
 }
 
 
-// right_idx[k] = the probe row of pair k: row i repeated counts[i] times (the reference's own expansion
-// loop, IJ:1611-1618).  Rows with few hits dominate, so every row is written as one 64-byte block of sixteen
-// copies (branch-free for counts <= 16) and the cursor advances by its count, later rows overwrite the
-// excess; longer runs loop over 16-byte stores; the last sixteen pairs are filled exactly.
-static void expand_counts(const uint32_t* counts, uint32_t n_rows, uint32_t* right, uint64_t n_pairs) {
-  uint64_t o = 0;
-  uint32_t i = 0;
-#if defined(__SSE2__)
-  if (n_pairs >= 16) {
-    const uint64_t safe = n_pairs - 16;
-    for (; i < n_rows && o <= safe; ++i) {
-      const uint32_t c = counts[i];
-      const __m128i v = _mm_set1_epi32(int(i));
-      __m128i* p = reinterpret_cast<__m128i*>(right + o);
-      _mm_storeu_si128(p, v);
-      _mm_storeu_si128(p + 1, v);
-      _mm_storeu_si128(p + 2, v);
-      _mm_storeu_si128(p + 3, v);
-      if (__builtin_expect(c > 16, 0)) {
-        uint64_t q = o + 16;
-        const uint64_t end = o + c;
-        for (; q + 4 <= end && q + 4 <= n_pairs; q += 4) _mm_storeu_si128(reinterpret_cast<__m128i*>(right + q), v);
-        for (; q < end; ++q) right[q] = i;
-      }
-      o += c;
-    }
-  }
-#endif
-  for (; i < n_rows; ++i)  // the tail (and the portable path): never write past n_pairs
-    for (uint32_t k = 0; k < counts[i] && o < n_pairs; ++k) right[o++] = i;
-}
+// right_idx[k] = the probe row of pair k: row i repeated counts[i] times — sq::expand_counts (sq_rle.cpp, host
+// compiler: SSE2 / AVX2 / AVX-512 variants picked at run time)
 
 // On by default (SQ_RLE_WIRE=0 copies right_idx itself).  Measured on a B200 box with 16 host cores, 12.5M
 // probe rows / 80.6M pairs per step: one host thread decodes ~1 G pairs/s, so with 4 partition threads the

@@ -273,6 +273,9 @@ int launch_packed(sq_stream* s, const sq_index* idx, const uint64_t* d_key, cons
 bool use_packed(const sq_index* idx);
 
 
+// rle.cpp (plain C++): right_idx from the per-row counts, on the host (interval_join.rs:1611-1618)
+void expand_counts(const uint32_t* counts, uint32_t n_rows, uint32_t* right, uint64_t n_pairs);
+
 // gather.cu
 int launch_gather(sq_stream* s, const void* d_values, const uint32_t* d_idx, uint64_t n, uint32_t width,
                   void* d_out);
