@@ -45,6 +45,19 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_native.SCAN_SIGNATURES) == declared_scan
 
 
+@pytest.mark.parametrize("header", ["sequila_cuda.h", "sequila_exec.h", "sequila_scan.h"])
+def test_headers_are_plain_c(header):
+    """the boundary is a C ABI: every header must compile as C11 on its own (what cgo / bindgen / a C host would see)"""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    p = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I",
+                        os.path.join(ROOT, "include"), "-x", "c", "-"], input=f'#include "{header}"\n', text=True,
+                       capture_output=True)
+    assert p.returncode == 0, p.stderr
+
+
 def test_abi_version_and_no_fallback_without_gpu():
     import sequila_native_b200 as sn
     from sequila_native_b200 import _native
