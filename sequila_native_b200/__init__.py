@@ -1,9 +1,18 @@
-"""Import alias: the package directory is named ``sequila-native_b200`` (not a valid Python
-identifier), so ``import sequila_native_b200`` is routed to it here."""
-import os as _os
+"""sequila-native_b200 — B200-native interval-overlap join (`SET sequila.interval_join_algorithm TO cuda`).
 
-_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "sequila-native_b200")
-__path__ = [_real]
-with open(_os.path.join(_real, "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
-del _f
+Only the hot path of sequila-native is here: build-side index, probe, emit and
+column gather as hand-written sm_100a CUDA kernels behind the C ABI in ``include/sequila_cuda.h``
+(``libsequila_cuda.so``), plus the host-side mirror of the reference's operator surface.
+There is no CPU fallback: importing :mod:`cuda_join` objects without the built library raises.
+"""
+from ._native import SequilaCudaError, LIB_PATH  # noqa: F401
+from .cuda_join import CudaContext, CudaIndex, CudaStream  # noqa: F401
+from .scan import CudaScan  # noqa: F401
+from . import synth  # noqa: F401
+from .session import Algorithm, SequilaConfig, apply_set, ParseAlgorithmError  # noqa: F401
+from . import intervals  # noqa: F401
+from .interval_join import IntervalJoinExec, HashJoinDesc, optimize  # noqa: F401
+
+__all__ = ["CudaContext", "CudaIndex", "CudaStream", "CudaScan", "SequilaCudaError", "synth", "LIB_PATH", "Algorithm",
+           "SequilaConfig", "apply_set", "ParseAlgorithmError", "intervals", "IntervalJoinExec", "HashJoinDesc",
+           "optimize"]

@@ -139,7 +139,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise ImportError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
-                " (make -C sequila-native_b200/csrc). The cuda interval join has no CPU fallback.")
+                " (make -C sequila_native_b200/csrc). The cuda interval join has no CPU fallback.")
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in list(SIGNATURES.items()) + list(EXEC_SIGNATURES.items()) + list(SCAN_SIGNATURES.items()):
             fn = getattr(L, name)

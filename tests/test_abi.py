@@ -71,7 +71,7 @@ def test_abi_version_and_no_fallback_without_gpu():
 
 
 def test_product_package_never_imports_the_oracle():
-    pkg = os.path.join(ROOT, "sequila-native_b200")
+    pkg = os.path.join(ROOT, "sequila_native_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):

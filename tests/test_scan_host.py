@@ -2,7 +2,7 @@
  1. the scan oracle (oracle/scan_oracle.py) is pinned to the reference's own fixtures: the bytes of
     testing/data/interval/reads.csv / targets.csv parse to the rows the reference's tests list, and to what
     Python's csv module reads;
- 2. the row-location and row-parse code the CUDA kernels run (sequila-native_b200/csrc/sq_scan_row.h, host +
+ 2. the row-location and row-parse code the CUDA kernels run (sequila_native_b200/csrc/sq_scan_row.h, host +
     device) is compiled with g++ into a harness and compared with the oracle on the fixtures, hand-written
     edge cases and random tables — so only the CUDA-specific parts (block scan, dictionary table, SIMD
     newline mask) are left to the GPU tests (tests/test_gpu_scan.py)."""
@@ -24,7 +24,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def shim(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("scan_shim") / "scan_host_shim.so")
     subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC",
-                    "-I" + os.path.join(ROOT, "sequila-native_b200", "csrc"), "-o", out,
+                    "-I" + os.path.join(ROOT, "sequila_native_b200", "csrc"), "-o", out,
                     os.path.join(ROOT, "tests", "scan_host_shim.cpp")], check=True)
     lib = C.CDLL(out)
     lib.scan_host.restype = C.c_int64
