@@ -34,6 +34,7 @@ extern "C" {
 #define SQ_ECAPACITY 5 /* caller buffer smaller than the result         */
 #define SQ_ECAST 6     /* value does not fit Int32 (IJ:1661-1672)       */
 #define SQ_EPARSE 7    /* malformed delimited text (sequila_scan.h)     */
+#define SQ_EBUSY 8     /* every tile slot of the stream is in flight    */
 
 #define SQ_ABI_VERSION 1
 
@@ -48,6 +49,23 @@ int32_t sq_ctx_create(int32_t device, sq_ctx** out);
 void sq_ctx_destroy(sq_ctx* ctx);
 const char* sq_last_error(const sq_ctx* ctx);
 int32_t sq_device_count(void);
+
+/* Tuning options = the `sequila.cuda_*` session keys, set the way the reference sets its own knobs
+ * (`SET sequila.<key> TO <value>` -> ConfigExtension::set, SC:106-132); the "sequila." prefix is optional.
+ * Nothing in the library reads the process environment.
+ *   cuda_probe_layout         auto | packed | soa   which probe kernels serve an index that has both layouts
+ *   cuda_staged_probe         auto | on | off       shared-memory (TMA) staged kernel for position-local probe tiles
+ *   cuda_probe_block          64 | 128 | 256        probe rows per CTA of the packed-line kernels
+ *   cuda_lookback_backoff_ns  integer               sleep between polls of the chained scan's look-back
+ *   cuda_rows_per_bin         1..1024               build: target rows per directory bin
+ *   cuda_right_idx_wire       rle | copy            host entry points: right_idx crosses PCIe as per-row counts (default)
+ *                                                   or as itself
+ *   cuda_l2_persist_mb        integer               L2 set-aside for the probe directory (device-wide limit; default 0)
+ *   cuda_scan_dict_capacity   power of two          text scan: initial key-dictionary capacity
+ *   cuda_exec_trace           0 | 1                 exec node: per-phase wall times on stderr
+ * Unknown keys and invalid values return SQ_EINVAL with a message; values may be changed between calls. */
+int32_t sq_ctx_set_option(sq_ctx* ctx, const char* key, const char* value);
+int32_t sq_ctx_get_option(sq_ctx* ctx, const char* key, char* value_out, size_t capacity);
 
 /* Pinned host memory for Arrow buffers the host wants copied without a staging hop. */
 int32_t sq_host_alloc(sq_ctx* ctx, size_t bytes, void** out);
@@ -114,7 +132,7 @@ int32_t sq_probe_count(sq_stream* s, const sq_index* idx, const uint64_t* key_ha
  * capacity = number of elements left_idx_out/right_idx_out can hold (>= n_pairs).
  * right_idx crosses PCIe run-length encoded (the per-row counts, 4 B per probe row instead of 4 B per pair)
  * and is expanded into right_idx_out by the calling thread while left_idx is still arriving — the expansion
- * loop the reference runs at IJ:1611-1618.  SQ_RLE_WIRE=0 in the environment copies right_idx itself. */
+ * loop the reference runs at IJ:1611-1618.  Option cuda_right_idx_wire=copy copies right_idx itself. */
 int32_t sq_probe_emit_pairs(sq_stream* s, uint32_t* left_idx_out, uint32_t* right_idx_out,
                             uint32_t* counts_out, uint64_t capacity);
 
@@ -126,6 +144,45 @@ int32_t sq_probe_join(sq_stream* s, const sq_index* idx, const uint64_t* key_has
                       const int32_t* start, const int32_t* end, uint32_t n_rows,
                       uint32_t* left_idx_out, uint32_t* right_idx_out, uint32_t* counts_out,
                       uint64_t capacity, uint64_t* n_pairs_out);
+
+/* ---- asynchronous tile pipeline ------------------------------------------------------------
+ * The reference's stream state machine handles one probe batch at a time inside poll_next (IJ:1054-1167,
+ * 1192-1233); behind PCIe the three legs of a tile (H2D of the probe columns, kernels, D2H of the result) have
+ * to overlap ACROSS tiles.  sq_stream_submit enqueues all three legs of one tile on the stream's copy-in,
+ * compute and copy-out CUDA streams and returns at once; up to `cuda_pipeline_depth` (default 3) tiles may be
+ * in flight per sq_stream (SQ_EBUSY beyond that).  sq_stream_collect waits for the OLDEST ticket and hands over
+ * its result in pinned host buffers taken from the library's pool, fresh for every tile (sized from the fan-out
+ * of the previous tile; a tile that outgrows them is re-emitted, so the call never fails for lack of room):
+ *   left_idx[n_pairs]   build rows (`pos as u32`, IJ:1590)
+ *   counts[n_rows]      hits per probe row (`rle_right`, IJ:1604); right_idx is its run-length expansion
+ *                       (IJ:1611-1618) and by default does not cross PCIe at all
+ *   right_idx           NULL unless SQ_TILE_RIGHT_IDX (copied from the device) or SQ_TILE_EXPAND_RIGHT
+ *                       (expanded from the counts by the collecting thread) was requested
+ * The caller owns the buffers and returns each with sq_host_free (e.g. from an Arrow buffer's release
+ * callback).  The probe columns passed to submit must stay valid until the ticket has been collected; they
+ * should be pinned (sq_host_alloc) for the copy-in to be asynchronous.  Tiles of one stream are collected in
+ * submission order (probe order is preserved, IJ:210-218). */
+#define SQ_TILE_COUNT_ONLY 1u   /* count(*) of the join: no pairs are written or moved                         */
+#define SQ_TILE_RIGHT_IDX 2u    /* also copy right_idx from the device (8 B per pair on the wire instead of 4)  */
+#define SQ_TILE_EXPAND_RIGHT 4u /* expand right_idx from the counts on the collecting thread                    */
+#define SQ_TILE_NO_COUNTS 8u    /* do not move the per-row counts (count-only callers that want the total only) */
+typedef struct sq_tile_out {
+  uint64_t n_pairs;
+  uint32_t n_rows;
+  uint32_t reserved;
+  uint32_t* left_idx;
+  uint32_t* right_idx;
+  uint32_t* counts;
+} sq_tile_out;
+int32_t sq_stream_submit(sq_stream* s, const sq_index* idx, const uint64_t* key_hash, const int32_t* start,
+                         const int32_t* end, uint32_t n_rows, uint32_t flags, uint64_t* ticket_out);
+int32_t sq_stream_collect(sq_stream* s, uint64_t ticket, sq_tile_out* out);
+int32_t sq_stream_in_flight(const sq_stream* s);
+/* gauges of the pipeline since the stream was created (the reference's BuildProbeJoinMetrics, utils.rs:441-495,
+ * has join_time only): [0..2] device ms summed over tiles of copy-in / kernels / copy-out, [3] bytes copied in,
+ * [4] bytes copied out, [5] tiles collected, [6] tiles re-emitted into larger buffers, [7] pairs per probe row
+ * of the last tile */
+int32_t sq_stream_pipeline_stats(const sq_stream* s, double out8[8]);
 
 /* Algorithm::CoitreesNearest on the same index (IJ:794-812 build, IJ:909-956 `nearest`, IJ:972-990
  * `get`, IJ:1593-1602 emit): ONE output row per probe row.

@@ -97,6 +97,9 @@ int32_t sq_exec_probe_next(sq_exec* e, int32_t partition, struct ArrowArray* out
  * [5] output_batches [6] output_rows [7] build_time_ns [8] join_time_ns [9] index_bytes [10] keys */
 int32_t sq_exec_metrics(const sq_exec* e, uint64_t out[16]);
 const char* sq_exec_last_error(const sq_exec* e);
+/* `SET sequila.cuda_<name> TO <value>` for this node's context (keys of sq_ctx_set_option, sequila_cuda.h);
+ * the reference carries its knobs the same way, as SequilaConfig fields set through SET (SC:50-60, 106-132) */
+int32_t sq_exec_set_option(sq_exec* e, const char* key, const char* value);
 void sq_exec_free(sq_exec* e);
 
 #ifdef __cplusplus

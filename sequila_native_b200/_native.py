@@ -9,7 +9,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SQ_LIB_PATH") or os.path.join(_HERE, "libsequila_cuda.so")  # SQ_LIB_PATH: A/B experiments only
 
-SQ_OK, SQ_EINVAL, SQ_ECUDA, SQ_ENOMEM, SQ_ESTATE, SQ_ECAPACITY, SQ_ECAST, SQ_EPARSE = range(8)
+SQ_OK, SQ_EINVAL, SQ_ECUDA, SQ_ENOMEM, SQ_ESTATE, SQ_ECAPACITY, SQ_ECAST, SQ_EPARSE, SQ_EBUSY = range(9)
+TILE_COUNT_ONLY, TILE_RIGHT_IDX, TILE_EXPAND_RIGHT, TILE_NO_COUNTS = 1, 2, 4, 8  # SQ_TILE_* flags
 NULL_INDEX = 0xFFFFFFFF  # SQ_NULL_INDEX
 
 u64p = C.POINTER(C.c_uint64)
@@ -19,6 +20,12 @@ u32p = C.POINTER(C.c_uint32)
 f32p = C.POINTER(C.c_float)
 vp = C.c_void_p
 
+class SqTileOut(C.Structure):
+    """struct sq_tile_out (include/sequila_cuda.h)"""
+    _fields_ = [("n_pairs", C.c_uint64), ("n_rows", C.c_uint32), ("reserved", C.c_uint32),
+                ("left_idx", C.c_void_p), ("right_idx", C.c_void_p), ("counts", C.c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol include/sequila_cuda.h declares
 SIGNATURES = {
     "sq_abi_version": (C.c_int32, []),
@@ -26,6 +33,8 @@ SIGNATURES = {
     "sq_ctx_destroy": (None, [vp]),
     "sq_last_error": (C.c_char_p, [vp]),
     "sq_device_count": (C.c_int32, []),
+    "sq_ctx_set_option": (C.c_int32, [vp, C.c_char_p, C.c_char_p]),
+    "sq_ctx_get_option": (C.c_int32, [vp, C.c_char_p, C.c_char_p, C.c_size_t]),
     "sq_host_alloc": (C.c_int32, [vp, C.c_size_t, C.POINTER(vp)]),
     "sq_host_free": (None, [vp, vp]),
     "sq_index_build": (C.c_int32, [vp, vp, vp, vp, C.c_uint64, C.POINTER(vp)]),
@@ -71,6 +80,10 @@ SIGNATURES = {
     "sq_stream_set_profiling": (C.c_int32, [vp, C.c_int32]),
     "sq_stream_phase_ms": (C.c_int32, [vp, f32p]),
     "sq_stream_launches": (C.c_uint64, [vp]),
+    "sq_stream_submit": (C.c_int32, [vp, vp, vp, vp, vp, C.c_uint32, C.c_uint32, u64p]),
+    "sq_stream_collect": (C.c_int32, [vp, C.c_uint64, C.POINTER(SqTileOut)]),
+    "sq_stream_in_flight": (C.c_int32, [vp]),
+    "sq_stream_pipeline_stats": (C.c_int32, [vp, C.POINTER(C.c_double)]),
 }
 
 
@@ -120,6 +133,7 @@ EXEC_SIGNATURES = {
     "sq_exec_probe_next": (C.c_int32, [vp, C.c_int32, vp, i32p]),
     "sq_exec_metrics": (C.c_int32, [vp, u64p]),
     "sq_exec_last_error": (C.c_char_p, [vp]),
+    "sq_exec_set_option": (C.c_int32, [vp, C.c_char_p, C.c_char_p]),
     "sq_exec_free": (None, [vp]),
 }
 

@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <strings.h>
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
@@ -110,23 +111,95 @@ SQ_API int32_t sq_ctx_create(int32_t device, sq_ctx** out) {
     return fail(g_create_err, SQ_ECUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
   }
   c->sm_count = prop.multiProcessorCount;
-  // The probe reads scattered 32-byte sectors of a multi-GB index: ask L2 to fetch exactly the
-  // sector that missed instead of the default wider granule (a hint; ignored where unsupported).
-  // L2 set-aside for the probe's hot read-only structure (the bin directory): see launch_join.
-  c->l2_persist_bytes = 0;
-  {
-    const char* e = getenv("SQ_L2_PERSIST_MB");
-    size_t want = size_t(e ? atoi(e) : 0) << 20;  // measured on B200: no gain for the directory, off by default
-    if (want > size_t(prop.persistingL2CacheMaxSize)) want = size_t(prop.persistingL2CacheMaxSize);
-    if (want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) c->l2_persist_bytes = want;
-    else cudaGetLastError();
-    c->l2_window_max = size_t(prop.accessPolicyMaxWindowSize);
-  }
+  c->l2_persist_max = size_t(prop.persistingL2CacheMaxSize);
+  c->l2_window_max = size_t(prop.accessPolicyMaxWindowSize);
   *out = c;
   return SQ_OK;
 }
 
 SQ_API void sq_ctx_destroy(sq_ctx* ctx) { delete ctx; }
+
+// ---- options: the `sequila.cuda_*` keys ---------------------------------------------------------
+namespace {
+struct OptDesc {
+  const char* name;
+  std::atomic<int> sq_options::*field;
+  int lo, hi;
+  const char* const* words;  // optional symbolic values, index = value
+};
+const char* const kLayoutWords[] = {"auto", "packed", "soa", nullptr};
+const char* const kWireWords[] = {"rle", "copy", nullptr};
+const char* const kStagedWords[] = {"auto", "on", "off", nullptr};
+const OptDesc kOpts[] = {
+    {"cuda_probe_layout", &sq_options::probe_layout, 0, 2, kLayoutWords},
+    {"cuda_probe_block", &sq_options::probe_block, 64, 256, nullptr},
+    {"cuda_lookback_backoff_ns", &sq_options::lookback_backoff_ns, 0, 1 << 20, nullptr},
+    {"cuda_rows_per_bin", &sq_options::rows_per_bin, 1, 1024, nullptr},
+    {"cuda_right_idx_wire", &sq_options::right_idx_wire, 0, 1, kWireWords},
+    {"cuda_staged_probe", &sq_options::staged_probe, 0, 2, kStagedWords},
+    {"cuda_scan_dict_capacity", &sq_options::scan_dict_capacity, 4, 1 << 30, nullptr},
+    {"cuda_exec_trace", &sq_options::exec_trace, 0, 1, nullptr},
+    {"cuda_pipeline_depth", &sq_options::pipeline_depth, 2, 8, nullptr},
+};
+const char* strip_prefix(const char* key) { return strncmp(key, "sequila.", 8) == 0 ? key + 8 : key; }
+}  // namespace
+
+SQ_API int32_t sq_ctx_set_option(sq_ctx* ctx, const char* key, const char* value) {
+  if (!ctx) return SQ_EINVAL;
+  if (!key || !value) return fail(ctx->err, SQ_EINVAL, "null option key or value");
+  const char* k = strip_prefix(key);
+  if (strcmp(k, "cuda_l2_persist_mb") == 0) {
+    // L2 set-aside for the probe's directory (device-wide limit; measured on B200: no gain for the join, up to
+    // 10 % for count-only launches) -- applied here, once, not per probe call
+    char* endp = nullptr;
+    const long mb = strtol(value, &endp, 10);
+    if (endp == value || *endp || mb < 0) return fail(ctx->err, SQ_EINVAL, "option %s: '%s' is not a size in MiB", k, value);
+    size_t want = size_t(mb) << 20;
+    if (want > ctx->l2_persist_max) want = ctx->l2_persist_max;
+    SQ_CUDA(ctx->err, cudaSetDevice(ctx->device));
+    SQ_CUDA(ctx->err, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+    ctx->l2_persist_bytes = want;
+    return SQ_OK;
+  }
+  for (const OptDesc& d : kOpts) {
+    if (strcmp(k, d.name) != 0) continue;
+    int v = -1;
+    bool ok = false;
+    if (d.words)
+      for (int i = 0; d.words[i]; ++i)
+        if (strcasecmp(value, d.words[i]) == 0) { v = i; ok = true; }
+    if (!ok) {
+      char* endp = nullptr;
+      const long x = strtol(value, &endp, 10);
+      ok = endp != value && !*endp && x >= d.lo && x <= d.hi;
+      v = int(x);
+    }
+    if (ok && d.field == &sq_options::probe_block) ok = v == 64 || v == 128 || v == 256;
+    if (ok && d.field == &sq_options::scan_dict_capacity) ok = (v & (v - 1)) == 0;
+    if (!ok) return fail(ctx->err, SQ_EINVAL, "option %s: invalid value '%s'", k, value);
+    (ctx->opt.*(d.field)).store(v, std::memory_order_relaxed);
+    return SQ_OK;
+  }
+  return fail(ctx->err, SQ_EINVAL, "unknown option '%s'", key);
+}
+
+SQ_API int32_t sq_ctx_get_option(sq_ctx* ctx, const char* key, char* value_out, size_t capacity) {
+  if (!ctx) return SQ_EINVAL;
+  if (!key || !value_out || capacity == 0) return fail(ctx->err, SQ_EINVAL, "null option key or output");
+  const char* k = strip_prefix(key);
+  if (strcmp(k, "cuda_l2_persist_mb") == 0) {
+    snprintf(value_out, capacity, "%zu", ctx->l2_persist_bytes >> 20);
+    return SQ_OK;
+  }
+  for (const OptDesc& d : kOpts) {
+    if (strcmp(k, d.name) != 0) continue;
+    const int v = (ctx->opt.*(d.field)).load(std::memory_order_relaxed);
+    if (d.words) snprintf(value_out, capacity, "%s", d.words[v]);
+    else snprintf(value_out, capacity, "%d", v);
+    return SQ_OK;
+  }
+  return fail(ctx->err, SQ_EINVAL, "unknown option '%s'", key);
+}
 
 SQ_API const char* sq_last_error(const sq_ctx* ctx) {
   // the returned pointer stays valid until the next failing call on the same object
@@ -291,6 +364,7 @@ SQ_API void sq_stream_free(sq_stream* s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
   cudaStreamSynchronize(s->stream);
+  pipeline_destroy(s);
   for (sq_buf* b : {&s->d_in, &s->d_cnt, &s->d_state, &s->d_tile, &s->d_scalar, &s->d_left,
                     &s->d_right, &s->d_gather, &s->d_gather2, &s->d_chain, &s->d_strblk, &s->d_strdata, &s->h_in, &s->h_out, &s->h_scalar, &s->h_scan})
     release(*b);
@@ -308,7 +382,7 @@ SQ_API uint64_t sq_stream_bytes(const sq_stream* s) {
   for (const sq_buf* b : {&s->d_in, &s->d_cnt, &s->d_state, &s->d_tile, &s->d_scalar, &s->d_left,
                           &s->d_right, &s->d_gather, &s->d_gather2, &s->d_chain, &s->d_strblk, &s->d_strdata, &s->h_in, &s->h_out, &s->h_scalar, &s->h_scan})
     t += b->cap;
-  return t;
+  return t + pipeline_bytes(s);
 }
 
 SQ_API int32_t sq_stream_set_profiling(sq_stream* s, int32_t enabled) {
@@ -364,8 +438,9 @@ static int32_t check_probe_args(sq_stream* s, const sq_index* idx, const void* k
   return SQ_OK;
 }
 
-static void begin_tile(sq_stream* s, const sq_index* idx, const uint64_t* dk, const int32_t* ds, const int32_t* de,
-                       uint32_t n) {
+namespace sq {
+void tile_begin(sq_stream* s, const sq_index* idx, const uint64_t* dk, const int32_t* ds, const int32_t* de,
+                uint32_t n) {
   s->idx = idx;
   s->n_rows = n;
   s->d_q_key = dk;
@@ -378,6 +453,8 @@ static void begin_tile(sq_stream* s, const sq_index* idx, const uint64_t* dk, co
   s->win_set = false;
   s->win_off = s->win_n = 0;
 }
+}  // namespace sq
+#define begin_tile sq::tile_begin
 
 static int32_t empty_tile(sq_stream* s, uint64_t* n_pairs_out) {
   s->n_pairs = 0;
@@ -474,23 +551,25 @@ SQ_API int32_t sq_probe_count(sq_stream* s, const sq_index* idx, const uint64_t*
 }
 
 // the write pass of a tile that was only counted (or whose speculative buffers were too small)
-static int32_t launch_emit(sq_stream* s, uint32_t* d_left, uint32_t* d_right, uint64_t capacity) {
+namespace sq {
+int tile_emit(sq_stream* s, uint32_t* d_left, uint32_t* d_right, uint64_t capacity) {
   if (use_packed(s->idx))
     return launch_packed(s, s->idx, s->d_q_key, s->d_q_start, s->d_q_end, s->n_rows, d_left, d_right, capacity);
   return launch_write(s, s->idx, s->d_q_start, s->n_rows, d_left, d_right, capacity);
 }
+}  // namespace sq
+#define launch_emit sq::tile_emit
 
 
 // right_idx[k] = the probe row of pair k: row i repeated counts[i] times — sq::expand_counts (sq_rle.cpp, host
 // compiler: SSE2 / AVX2 / AVX-512 variants picked at run time)
 
-// On by default (SQ_RLE_WIRE=0 copies right_idx itself).  Measured on a B200 box with 16 host cores, 12.5M
+// On by default (option cuda_right_idx_wire=copy copies right_idx itself).  Measured on a B200 box with 16 host cores, 12.5M
 // probe rows / 80.6M pairs per step: one host thread decodes ~1 G pairs/s, so with 4 partition threads the
 // decode is the bottleneck (18.4 ms per step vs 13.7 ms with plain copies), with 8 it is not (11.4 ms vs
 // 13.7 ms); it pays most where several GPUs share the host link (8 GPUs: 60 ms per step with plain copies).
-static bool rle_on_the_wire() {
-  const char* e = getenv("SQ_RLE_WIRE");
-  return !e || atoi(e) != 0;
+static bool rle_on_the_wire(const sq_stream* s) {
+  return s->ctx->opt.right_idx_wire.load(std::memory_order_relaxed) == 0;
 }
 
 static int32_t check_emit(sq_stream* s, const void* left, uint64_t capacity) {
@@ -539,7 +618,7 @@ SQ_API int32_t sq_probe_emit_pairs(sq_stream* s, uint32_t* left_idx_out, uint32_
   // right_idx is a run-length expansion of the per-row counts (IJ:1611-1618); optionally it travels as the
   // counts (4 B per probe row instead of 4 B per pair) and is decoded into the caller's buffer here while
   // left_idx is still arriving (see rle_on_the_wire).
-  const bool rle_wire = right_idx_out && np && rle_on_the_wire();
+  const bool rle_wire = right_idx_out && np && rle_on_the_wire(s);
   const uint32_t* h_counts = counts_out;
   if ((counts_out || rle_wire) && s->n_rows) {
     if (!counts_out) {

@@ -181,7 +181,6 @@ __global__ void __launch_bounds__(256) k_fill_dir(const uint64_t* __restrict__ s
 // ---------------------------------------------------------------------------------------------
 // Directory bins hold 8-16 rows for evenly spread starts: measured on B200 (100M-row index, random
 // probes) 8 beats 16 and 32 (1.87 / 1.98 / 2.15 ms per 12.5M probes) and costs n/2 bytes of directory.
-constexpr uint32_t kRowsPerBin = 8;
 
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
@@ -540,11 +539,7 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     SQ_CUDA(E, cudaGetLastError());
 
     // 4. per-segment bin directory (geometry on the device, offsets by a host scan: #keys is small)
-    uint32_t rows_per_bin = kRowsPerBin;
-    if (const char* e = getenv("SQ_ROWS_PER_BIN")) {  // experiment knob
-      const int v = atoi(e);
-      if (v >= 1 && v <= 1024) rows_per_bin = uint32_t(v);
-    }
+    const uint32_t rows_per_bin = uint32_t(ctx->opt.rows_per_bin.load(std::memory_order_relaxed));
     k_seg_meta<<<(n_keys + 255) / 256, 256, 0, st>>>(d_seg_off, idx->d_start, n_keys, idx->d_meta,
                                                      rows_per_bin);
     SQ_CUDA(E, cudaGetLastError());

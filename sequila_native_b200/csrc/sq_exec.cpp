@@ -26,11 +26,14 @@ namespace {
 
 using Clock = std::chrono::steady_clock;
 
-// SQ_EXEC_TRACE=1: per-phase wall times of every probe batch on stderr (development aid)
+// option cuda_exec_trace=1: per-phase wall times of every probe batch on stderr (development aid)
 struct Trace {
   bool on;
   Clock::time_point t;
-  Trace() : on(getenv("SQ_EXEC_TRACE") != nullptr), t(Clock::now()) {}
+  explicit Trace(sq_ctx* ctx) : on(false), t(Clock::now()) {
+    char v[8] = {0};
+    on = sq_ctx_get_option(ctx, "cuda_exec_trace", v, sizeof v) == SQ_OK && v[0] == '1';
+  }
   void lap(const char* what) {
     if (!on) return;
     const auto n = Clock::now();
@@ -641,7 +644,7 @@ int probe_on_device(sq_exec* e, sq_stream* st, const ArrowArray* batch, uint64_t
   std::vector<uint64_t> keys;
   std::vector<int32_t> start, end;
   int rc;
-  Trace tr;
+  Trace tr(e->ctx);
   if ((rc = hash_keys(e, e->right, e->on_right, batch, &keys))) return rc;
   tr.lap("hash_keys");
   if ((rc = eval_i32(e, st, e->right, e->cfg.right_start, false, batch, &start))) return rc;
@@ -673,7 +676,7 @@ int assemble_output(sq_exec* e, sq_stream* st, const ArrowArray* batch, uint64_t
   const uint64_t n = uint64_t(batch->length);
   const bool nearest = e->cfg.algorithm == SQ_EXEC_NEAREST;
   int rc;
-  Trace tr;
+  Trace tr(e->ctx);
   // `out` is assembled in place; on any failure below everything attached so far is released
   auto* own = new Owned();
   own->ctx = e->ctx;
@@ -918,6 +921,14 @@ SQ_API int32_t sq_exec_metrics(const sq_exec* e, uint64_t out[16]) {
 }
 
 SQ_API const char* sq_exec_last_error(const sq_exec* e) { return e ? e->err.c_str() : ""; }
+
+// `SET sequila.cuda_* TO value` reaches the exec node's context here (sq_ctx_set_option)
+SQ_API int32_t sq_exec_set_option(sq_exec* e, const char* key, const char* value) {
+  if (!e) return SQ_EINVAL;
+  const int rc = sq_ctx_set_option(e->ctx, key, value);
+  if (rc != SQ_OK) return e->fail(rc, "%s", sq_last_error(e->ctx));
+  return SQ_OK;
+}
 
 SQ_API void sq_exec_free(sq_exec* e) {
   if (!e) return;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <map>
@@ -105,11 +106,29 @@ struct HostPool {
   size_t idle_bytes = 0;
 };
 
+// Tuning options of a context = the `sequila.cuda_*` session keys (sq_ctx_set_option; the reference keeps its
+// knobs in SequilaConfig, session_context.rs:50-60).  Plain relaxed atomics: a host may SET from one thread
+// while partitions probe on others; every reader takes one consistent value per call.
+struct sq_options {
+  std::atomic<int> probe_layout{0};         // 0 auto, 1 packed lines (when the index has them), 2 SoA arrays
+  std::atomic<int> probe_block{128};        // rows per CTA of the packed-line kernels: 64 / 128 / 256
+  std::atomic<int> lookback_backoff_ns{64}; // sleep between polls of a predecessor's chained-scan word
+  std::atomic<int> rows_per_bin{8};         // build: target rows per directory bin
+  std::atomic<int> right_idx_wire{0};       // host entry points: 0 = per-row counts cross PCIe and right_idx is expanded on
+                                            // the host (IJ:1611-1618), 1 = right_idx itself is copied
+  std::atomic<int> staged_probe{0};         // 0 auto (adaptive per stream), 1 always try the staged kernel, 2 never
+  std::atomic<int> scan_dict_capacity{1 << 16};  // text scan: initial capacity of the per-call key dictionary
+  std::atomic<int> exec_trace{0};           // exec node: per-phase wall-clock trace on stderr
+  std::atomic<int> pipeline_depth{3};       // sq_stream_submit: tiles in flight per stream (2..8)
+};
+
 struct sq_ctx {
   int device = 0;
   int sm_count = 148;
   size_t l2_persist_bytes = 0;  // L2 set-aside granted for persisting accesses
   size_t l2_window_max = 0;
+  size_t l2_persist_max = 0;
+  sq_options opt;
   sq::ErrorSlot err;
 };
 
@@ -171,11 +190,22 @@ struct sq_buf {
   bool pinned = false;
 };
 
+struct sq_tile_slot;  // sq_pipeline.cu
+
 struct sq_stream {
   sq_ctx* ctx = nullptr;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   sq::ErrorSlot err;
+
+  // asynchronous tile pipeline (sq_stream_submit / sq_stream_collect, sq_pipeline.cu)
+  std::vector<sq_tile_slot*> slots;
+  cudaStream_t stream_in = nullptr, stream_out = nullptr;  // H2D and D2H run beside the kernels of other tiles
+  uint64_t next_ticket = 1, oldest_ticket = 1;
+  double pairs_per_row = -1.0;         // of the last collected tile: sizes the next tiles' buffers and speculative copies
+  double pipe_ms[3] = {0, 0, 0};       // summed device time of h2d / kernels / d2h over collected tiles
+  uint64_t pipe_bytes[2] = {0, 0};     // bytes moved h2d / d2h
+  uint64_t pipe_tiles = 0, pipe_regrow = 0;
 
   // state of the tile currently between count and emit
   const sq_index* idx = nullptr;
@@ -272,6 +302,13 @@ int launch_packed(sq_stream* s, const sq_index* idx, const uint64_t* d_key, cons
                   const int32_t* d_end, uint32_t n, uint32_t* d_left, uint32_t* d_right, uint64_t capacity);
 bool use_packed(const sq_index* idx);
 
+
+// api.cu: per-tile state of a stream (count -> emit protocol) and the write pass of a counted tile
+void tile_begin(sq_stream* s, const sq_index* idx, const uint64_t* dk, const int32_t* ds, const int32_t* de, uint32_t n);
+int tile_emit(sq_stream* s, uint32_t* d_left, uint32_t* d_right, uint64_t capacity);
+// pipeline.cu
+void pipeline_destroy(sq_stream* s);
+uint64_t pipeline_bytes(const sq_stream* s);
 
 // rle.cpp (plain C++): right_idx from the per-row counts, on the host (interval_join.rs:1611-1618)
 void expand_counts(const uint32_t* counts, uint32_t n_rows, uint32_t* right, uint64_t n_pairs);

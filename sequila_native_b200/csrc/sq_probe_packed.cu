@@ -30,7 +30,6 @@
 
 namespace sq {
 
-constexpr int kPBlockDefault = 128;      // threads per CTA = probe rows per CTA
 
 struct StartLine {
   uint32_t line;   // line holding the last row whose start can be <= qe
@@ -178,10 +177,9 @@ k_probe_packed(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* 
 // ---------------------------------------------------------------------------------------------
 bool use_packed(const sq_index* idx) {
   if (!idx->d_lines) return false;
-  // experiment / test knobs, read per call: SQ_PACKED=0 forces the SoA kernels, =1 the packed kernel
-  const char* e = getenv("SQ_PACKED");
-  const int forced = e ? atoi(e) : -1;
-  if (forced == 0) return false;
+  // option cuda_probe_layout: soa forces the SoA kernels, packed the packed-line kernel (tests, A/B runs)
+  const int forced = idx->ctx->opt.probe_layout.load(std::memory_order_relaxed);
+  if (forced == 2) return false;
   if (forced == 1) return true;
   // Measured on B200: the fused kernel wins when the index is far larger than L2 (cfg5, 100M rows:
   // 1.05 ms vs 1.83 ms per 12.5M probe rows) and loses on an L2-resident one (cfg2, 1M rows: 0.085
@@ -201,8 +199,7 @@ static void launch_packed_b(sq_stream* s, const IndexView& iv, const uint64_t* d
                             const int32_t* d_end, uint32_t n, uint32_t* cnt, unsigned long long* chain, unsigned int* ticket,
                             unsigned long long* result, uint32_t* d_left, uint32_t* d_right, uint64_t capacity) {
   const uint32_t n_tiles = (n + B - 1) / B;
-  uint32_t backoff = 64;
-  if (const char* e = getenv("SQ_BACKOFF_NS")) backoff = uint32_t(atoi(e));  // experiment knob
+  const uint32_t backoff = uint32_t(s->ctx->opt.lookback_backoff_ns.load(std::memory_order_relaxed));
   if (!d_left)
     k_probe_packed<false, false, B, 2><<<(n_tiles + 1) / 2, B, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket,
                                                                                 result, nullptr, nullptr, 0, n_tiles, 0u);
@@ -217,11 +214,7 @@ static void launch_packed_b(sq_stream* s, const IndexView& iv, const uint64_t* d
 int launch_packed(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
                   const int32_t* d_end, uint32_t n, uint32_t* d_left, uint32_t* d_right, uint64_t capacity) {
   ErrorSlot& E = s->err;
-  int block = kPBlockDefault;
-  if (const char* e = getenv("SQ_PBLOCK")) {  // experiment knob
-    const int v = atoi(e);
-    if (v == 64 || v == 128 || v == 256) block = v;
-  }
+  const int block = s->ctx->opt.probe_block.load(std::memory_order_relaxed);
   const uint32_t n_tiles = (n + block - 1) / block;
   int rc;
   if ((rc = ensure(E, s->d_cnt, size_t(n) * 4, false))) return rc;
@@ -234,7 +227,7 @@ int launch_packed(sq_stream* s, const sq_index* idx, const uint64_t* d_key, cons
   SQ_CUDA(E, cudaMemsetAsync(result, 0, 32, s->stream));
   const IndexView iv = idx->view();
   if (s->ctx->l2_persist_bytes && s->l2_window_idx != idx && idx->dir_bytes) {
-    // optional (SQ_L2_PERSIST_MB): keep the line directory (8-byte entries, same entry count as the 4-byte row
+    // optional (option cuda_l2_persist_mb): keep the line directory (8-byte entries, same entry count as the 4-byte row
     // directory), the one structure every probe row reads at a random place, in the persisting part of L2;
     // everything else streams through the rest
     cudaStreamAttrValue av{};

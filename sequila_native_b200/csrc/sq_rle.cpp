@@ -38,11 +38,12 @@ static void expand_sse2(const uint32_t* counts, uint32_t n_rows, uint32_t* right
       _mm_storeu_si128(p + 3, v);
       if (__builtin_expect(c > 16, 0)) {
         uint64_t q = o + 16;
-        const uint64_t end = o + c;
+        const uint64_t end = o + c < n_pairs ? o + c : n_pairs;  // counts that sum past n_pairs never write past it
         for (; q + 4 <= end && q + 4 <= n_pairs; q += 4) _mm_storeu_si128(reinterpret_cast<__m128i*>(right + q), v);
         for (; q < end; ++q) right[q] = i;
       }
       o += c;
+      if (o > n_pairs) o = n_pairs;
     }
   }
   expand_tail(counts, n_rows, right, n_pairs, i, o);
@@ -62,11 +63,12 @@ __attribute__((target("avx2"))) static void expand_avx2(const uint32_t* counts, 
       _mm256_storeu_si256(p + 1, v);
       if (__builtin_expect(c > 16, 0)) {
         uint64_t q = o + 16;
-        const uint64_t end = o + c;
+        const uint64_t end = o + c < n_pairs ? o + c : n_pairs;  // counts that sum past n_pairs never write past it
         for (; q + 8 <= end && q + 8 <= n_pairs; q += 8) _mm256_storeu_si256(reinterpret_cast<__m256i*>(right + q), v);
         for (; q < end; ++q) right[q] = i;
       }
       o += c;
+      if (o > n_pairs) o = n_pairs;
     }
   }
   expand_tail(counts, n_rows, right, n_pairs, i, o);
@@ -84,11 +86,12 @@ __attribute__((target("avx512f"))) static void expand_avx512(const uint32_t* cou
       _mm512_storeu_si512(right + o, v);
       if (__builtin_expect(c > 16, 0)) {
         uint64_t q = o + 16;
-        const uint64_t end = o + c;
+        const uint64_t end = o + c < n_pairs ? o + c : n_pairs;  // counts that sum past n_pairs never write past it
         for (; q + 16 <= end && q + 16 <= n_pairs; q += 16) _mm512_storeu_si512(right + q, v);
         for (; q < end; ++q) right[q] = i;
       }
       o += c;
+      if (o > n_pairs) o = n_pairs;
     }
   }
   expand_tail(counts, n_rows, right, n_pairs, i, o);

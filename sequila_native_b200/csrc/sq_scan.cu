@@ -392,11 +392,8 @@ int scan_device(sq_stream* s, const uint8_t* d_text, const uint8_t* h_text, uint
   DictTable dict{};
   SQ_CUDA(E, cudaMalloc(&flags.p, 64));
   auto* d_flags = static_cast<unsigned long long*>(flags.p);  // [0] first bad offset, [1] n_distinct (u32), [2] overflow (u32)
-  uint32_t cap = 1u << 16;
-  if (const char* e = getenv("SQ_SCAN_DICT_CAP")) {  // test knob: start small to exercise the growth path
-    uint32_t v = uint32_t(atoi(e));
-    if (v >= 4 && (v & (v - 1)) == 0) cap = v;
-  }
+  // option cuda_scan_dict_capacity: tests start small to exercise the growth path
+  uint32_t cap = uint32_t(s->ctx->opt.scan_dict_capacity.load(std::memory_order_relaxed));
   for (; n_rows;) {
     if (tab.p) { cudaFree(tab.p); tab.p = nullptr; }
     SQ_CUDA(E, cudaMalloc(&tab.p, size_t(cap + 1) * 16));

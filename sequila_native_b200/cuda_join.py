@@ -58,6 +58,15 @@ class CudaContext:
     def _err(self):
         return self._lib.sq_last_error(self._h)
 
+    def set_option(self, key: str, value) -> None:
+        """sq_ctx_set_option: one `sequila.cuda_*` key (SET sequila.cuda_probe_layout TO soa, ...)."""
+        _check(self._lib.sq_ctx_set_option(self._h, str(key).encode(), str(value).encode()), self._err)
+
+    def get_option(self, key: str) -> str:
+        buf = C.create_string_buffer(64)
+        _check(self._lib.sq_ctx_get_option(self._h, str(key).encode(), buf, 64), self._err)
+        return buf.value.decode()
+
     def pinned_empty(self, n: int, dtype) -> np.ndarray:
         """numpy array in pinned host memory (sq_host_alloc); full-speed async copies."""
         dtype = np.dtype(dtype)
@@ -197,6 +206,48 @@ class CudaStream:
         self.n_rows, self.n_pairs = int(k.shape[0]), int(n.value)
         _check(rc, self._err)
         return self.n_pairs
+
+    # ---- asynchronous tile pipeline (sq_stream_submit / sq_stream_collect) ------------------------------
+    def submit(self, index: CudaIndex, key_hash, start, end, flags: int = 0) -> int:
+        """Enqueue H2D + kernels + D2H of one tile; returns its ticket at once.  The three arrays must stay alive
+        (and should be pinned, CudaContext.pinned_*) until the ticket is collected."""
+        k, s, e = _np(key_hash, np.uint64), _np(start, np.int32), _np(end, np.int32)
+        t = C.c_uint64(0)
+        _check(self._lib.sq_stream_submit(self._h, index._h, _ptr(k), _ptr(s), _ptr(e), k.shape[0], int(flags), C.byref(t)),
+               self._err)
+        self._keep = index
+        self._tiles = getattr(self, "_tiles", {})
+        self._tiles[int(t.value)] = (k, s, e)
+        return int(t.value)
+
+    def collect(self, ticket: int):
+        """Wait for the oldest ticket -> (n_pairs, left_idx, right_idx | None, counts | None): numpy views of pinned
+        buffers from the library's pool; each goes back to the pool when its array is garbage collected."""
+        out = N.SqTileOut()
+        rc = self._lib.sq_stream_collect(self._h, int(ticket), C.byref(out))
+        getattr(self, "_tiles", {}).pop(int(ticket), None)
+        _check(rc, self._err)
+
+        def view(addr, n):
+            if not addr:
+                return None
+            buf = (C.c_uint32 * max(int(n), 1)).from_address(addr)
+            arr = np.frombuffer(buf, dtype=np.uint32, count=int(n))
+            weakref.finalize(buf, self._lib.sq_host_free, self.ctx._h, C.c_void_p(addr))
+            return arr
+        self.n_rows, self.n_pairs = int(out.n_rows), int(out.n_pairs)
+        return (int(out.n_pairs), view(out.left_idx, out.n_pairs), view(out.right_idx, out.n_pairs),
+                view(out.counts, out.n_rows))
+
+    @property
+    def in_flight(self) -> int:
+        return int(self._lib.sq_stream_in_flight(self._h))
+
+    def pipeline_stats(self) -> dict:
+        o = (C.c_double * 8)()
+        _check(self._lib.sq_stream_pipeline_stats(self._h, o), self._err)
+        return {"h2d_ms": o[0], "kernel_ms": o[1], "d2h_ms": o[2], "h2d_bytes": int(o[3]), "d2h_bytes": int(o[4]),
+                "tiles": int(o[5]), "regrown": int(o[6]), "pairs_per_row": o[7]}
 
     # ---- bounded output (low-memory protocol) -------------------------------------------------
     def counts(self) -> np.ndarray:

@@ -267,6 +267,11 @@ class IntervalJoinExec:
             raise ExecutionError(self._err())
         return pa.RecordBatch._import_from_c(C.addressof(out), self.schema())
 
+    def probe_batches(self, batches: Iterable, partition: int = 0) -> Iterator:
+        """The probe side of a partition as a stream of batches -> a stream of output batches (full mode)."""
+        for b in batches:
+            yield self.probe_batch(b, partition)
+
     def probe_batch_low_memory(self, batch, partition: int = 0) -> Iterator:
         """process_probe_batch, low-memory mode (IJ:1433-1530): output batches of at most
         `max_output_rows` rows, cut at probe-row boundaries."""

@@ -52,6 +52,16 @@ def route_rows(key_ids: np.ndarray, assignment: Sequence[Sequence[int]]) -> List
     return [np.flatnonzero(dest == g) for g in range(len(assignment))]
 
 
+def gather_ranks(obj, device="cpu") -> list:
+    """every rank's `obj` (a small picklable record: rows, pairs, timings, parity verdict) as a list in rank order"""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        out = [None] * dist.get_world_size()
+        dist.all_gather_object(out, obj)
+        return out
+    return [obj]
+
+
 def reduce_step(step_ms: float, probes: float, pairs: float, device="cpu"):
     """(max over ranks of the step time, sum of probe rows, sum of pairs) — the bench contract: whole-job
     throughput = units all ranks processed / the slowest rank's device time."""

@@ -83,6 +83,105 @@ def cfg5(scale: float = 1.0, nb: int = 100_000_000, np_: int = 100_000_000):
     return build, probe
 
 
+# ---- counter-based generator: row i of a side depends on (seed, i) only --------------
+# so any slice of a side can be produced anywhere — on the device with torch for the CUDA arm of bench.py, on
+# the host with numpy for the reference arm and the tests — and the two are bit-identical.  Integer arithmetic
+# only: three splitmix64 outputs per row give the contig (32-bit value against cumulative hg38 thresholds), the
+# width and the start (32 x 32 -> 64-bit multiply-shift).
+_GAMMA = 0x9E3779B97F4A7C15
+_MASK64 = (1 << 64) - 1
+
+
+def _contig_thresholds(lengths):
+    cum = np.cumsum(lengths.astype(np.float64)) / float(lengths.sum())
+    t = np.minimum(np.floor(cum * 4294967296.0), 4294967295.0).astype(np.int64)
+    t[-1] = 1 << 32  # every 32-bit value falls below the last threshold
+    return t
+
+
+def _mix64_np(x):
+    with np.errstate(over="ignore"):
+        x = x ^ (x >> np.uint64(30))
+        x = x * _M1
+        x = x ^ (x >> np.uint64(27))
+        x = x * _M2
+        x = x ^ (x >> np.uint64(31))
+    return x
+
+
+def counter_side(n: int, seed: int, first_row: int = 0, wlo: int = 50, whi: int = 150, lengths=HG38, chunk: int = 1 << 24,
+                 keep_contigs=None):
+    """Rows [first_row, first_row + n) of the side `seed` (numpy, host).  keep_contigs: only rows of those
+    contigs are kept (the bounded CPU-baseline sample of bench.py), generated chunk by chunk."""
+    thr = _contig_thresholds(lengths)
+    out = []
+    keep = None if keep_contigs is None else np.asarray(sorted(int(c) for c in keep_contigs), dtype=np.int64)
+    for lo in range(0, n, chunk):
+        m = min(chunk, n - lo)
+        i = np.arange(first_row + lo, first_row + lo + m, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            base = np.uint64((seed * _GAMMA) & _MASK64) + (i * np.uint64(3) + np.uint64(1)) * np.uint64(_GAMMA)
+            u1 = _mix64_np(base) >> np.uint64(32)
+            u2 = _mix64_np(base + np.uint64(_GAMMA)) >> np.uint64(32)
+            u3 = _mix64_np(base + np.uint64((2 * _GAMMA) & _MASK64)) >> np.uint64(32)
+        contig = np.searchsorted(thr, u1.astype(np.int64), side="right").astype(np.int64)
+        L = lengths[contig]
+        w = np.minimum(wlo + (u2.astype(np.int64) % (whi - wlo + 1)), L)
+        start = (u3.astype(np.int64) * (L - w + 1)) >> 32
+        if keep is not None:
+            sel = np.isin(contig, keep)
+            contig, start, w = contig[sel], start[sel], w[sel]
+        out.append((contig.astype(np.int32), start.astype(np.int32), (start + w - 1).astype(np.int32)))
+    contig = np.concatenate([o[0] for o in out]) if out else np.zeros(0, np.int32)
+    start = np.concatenate([o[1] for o in out]) if out else np.zeros(0, np.int32)
+    end = np.concatenate([o[2] for o in out]) if out else np.zeros(0, np.int32)
+    return {"contig": contig, "key": key_hash(contig), "start": start, "end": end}
+
+
+def counter_side_torch(n: int, seed: int, device, first_row: int = 0, wlo: int = 50, whi: int = 150, lengths=HG38,
+                       chunk: int = 1 << 25):
+    """The same rows as counter_side, generated on `device` (torch int64 arithmetic wraps like uint64; logical
+    right shifts are arithmetic shifts with the sign bits masked off).  'key' is int64 (the bits of the u64 hash)."""
+    import torch
+
+    def s64(v):
+        v &= _MASK64
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    def mix(x):
+        x = x ^ ((x >> 30) & ((1 << 34) - 1))
+        x = x * s64(int(_M1))
+        x = x ^ ((x >> 27) & ((1 << 37) - 1))
+        x = x * s64(int(_M2))
+        x = x ^ ((x >> 31) & ((1 << 33) - 1))
+        return x
+
+    thr = torch.from_numpy(_contig_thresholds(lengths)).to(device)
+    Lt = torch.from_numpy(np.asarray(lengths, dtype=np.int64)).to(device)
+    keys = torch.from_numpy(key_hash(np.arange(len(lengths))).view(np.int64)).to(device)
+    contig_o = torch.empty(n, dtype=torch.int32, device=device)
+    key_o = torch.empty(n, dtype=torch.int64, device=device)
+    start_o = torch.empty(n, dtype=torch.int32, device=device)
+    end_o = torch.empty(n, dtype=torch.int32, device=device)
+    g = s64(_GAMMA)
+    for lo in range(0, n, chunk):
+        m = min(chunk, n - lo)
+        i = torch.arange(first_row + lo, first_row + lo + m, dtype=torch.int64, device=device)
+        base = (i * 3 + 1) * g + s64(seed * _GAMMA)
+        u1 = (mix(base) >> 32) & 0xFFFFFFFF
+        u2 = (mix(base + g) >> 32) & 0xFFFFFFFF
+        u3 = (mix(base + s64(2 * _GAMMA)) >> 32) & 0xFFFFFFFF
+        contig = torch.searchsorted(thr, u1, right=True)
+        L = Lt[contig]
+        w = torch.minimum(wlo + (u2 % (whi - wlo + 1)), L)
+        start = (u3 * (L - w + 1)) >> 32
+        contig_o[lo:lo + m] = contig.int()
+        key_o[lo:lo + m] = keys[contig]
+        start_o[lo:lo + m] = start.int()
+        end_o[lo:lo + m] = (start + w - 1).int()
+    return {"contig": contig_o, "key": key_o, "start": start_o, "end": end_o}
+
+
 def cfg5_probe_shard(rank: int, world: int, rows_per_rank: int = 12_500_000, seed: int = 5002):
     """Probe shard of config 5 for one GPU (weak scaling: rows_per_rank fixed, world grows)."""
     L = HG38

@@ -13,9 +13,10 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(autouse=True, params=["packed", "soa"])
-def probe_layout(request, monkeypatch):
-    monkeypatch.setenv("SQ_PACKED", "1" if request.param == "packed" else "0")
-    return request.param
+def probe_layout(request, cuda_ctx):
+    cuda_ctx.set_option("sequila.cuda_probe_layout", request.param)
+    yield request.param
+    cuda_ctx.set_option("sequila.cuda_probe_layout", "auto")
 
 
 def check(oracle, ctx, b, p):

@@ -10,12 +10,13 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(autouse=True, params=["packed", "soa"])
-def probe_layout(request, monkeypatch):
+def probe_layout(request, cuda_ctx):
     """Every parity test runs against both probe implementations: the fused kernel over packed
-    lines (narrow indexes) and the count/scan/write kernels over the SoA arrays (SQ_PACKED knob,
-    sq_probe_packed.cu::use_packed)."""
-    monkeypatch.setenv("SQ_PACKED", "1" if request.param == "packed" else "0")
-    return request.param
+    lines (narrow indexes) and the count/scan/write kernels over the SoA arrays (option
+    sequila.cuda_probe_layout, sq_probe_packed.cu::use_packed)."""
+    cuda_ctx.set_option("sequila.cuda_probe_layout", request.param)
+    yield request.param
+    cuda_ctx.set_option("sequila.cuda_probe_layout", "auto")
 
 
 def cuda_join(ctx, L, R):
@@ -226,10 +227,17 @@ def test_error_paths(cuda_ctx):
     assert e.value.code == 5  # SQ_ECAPACITY
 
 
-@pytest.mark.parametrize("rle", ["1", "0"])
-def test_right_idx_wire_encodings(cuda_ctx, oracle, monkeypatch, rle):
+@pytest.mark.parametrize("wire", ["rle", "copy"])
+def test_right_idx_wire_encodings(cuda_ctx, oracle, wire):
     """right_idx crosses PCIe as per-row counts and is expanded on the host (default), or as itself."""
-    monkeypatch.setenv("SQ_RLE_WIRE", rle)
+    cuda_ctx.set_option("cuda_right_idx_wire", wire)
+    try:
+        _wire_cases(cuda_ctx, oracle)
+    finally:
+        cuda_ctx.set_option("cuda_right_idx_wire", "rle")
+
+
+def _wire_cases(cuda_ctx, oracle):
     for name, scale in (("cfg2", 0.05), ("cfg3", 0.01), ("cfg4", 0.02)):
         b, p = sn.synth.CONFIGS[name](scale=scale)
         assert_same(oracle, cuda_ctx, b, p)

@@ -1,0 +1,169 @@
+"""GPU: the asynchronous tile pipeline (sq_stream_submit / sq_stream_collect) against the oracle — several tiles in
+flight per stream, buffers sized from the previous tile's fan-out (first tile and fan-out jumps go through the
+re-emit path), every wire flag, both probe layouts, and the `sequila.cuda_*` option surface it is configured by."""
+import numpy as np
+import pytest
+
+import sequila_native_b200 as sn
+from sequila_native_b200 import _native as N
+from helpers import canon
+
+pytestmark = pytest.mark.gpu
+
+
+def tiles_of(p, n_tiles):
+    b = np.linspace(0, len(p["key"]), n_tiles + 1).astype(np.int64)
+    return [(int(b[i]), int(b[i + 1])) for i in range(n_tiles)]
+
+
+def run_pipeline(ctx, idx, p, n_tiles, flags=0, depth=None, pinned=True):
+    """-> per tile (n_pairs, left, right, counts) in probe order, submitting ahead as far as the stream allows"""
+    if depth:
+        ctx.set_option("cuda_pipeline_depth", depth)
+    st = sn.CudaStream(ctx)
+    cols = {k: (ctx.pinned_copy(p[k]) if pinned else np.ascontiguousarray(p[k])) for k in ("key", "start", "end")}
+    out, pending = [], []
+    depth = int(ctx.get_option("cuda_pipeline_depth"))
+    for lo, hi in tiles_of(p, n_tiles):
+        if len(pending) == depth:
+            out.append(st.collect(pending.pop(0)))
+        pending.append(st.submit(idx, cols["key"][lo:hi], cols["start"][lo:hi], cols["end"][lo:hi], flags))
+        assert st.in_flight == len(pending)
+    while pending:
+        out.append(st.collect(pending.pop(0)))
+    assert st.in_flight == 0
+    return st, out
+
+
+def check_tiles(oracle, b, p, n_tiles, out, flags):
+    oidx = oracle.OracleIndex(b["key"], b["start"], b["end"])
+    for (lo, hi), (n, left, right, counts) in zip(tiles_of(p, n_tiles), out):
+        ol, orr, oc = oidx.probe(p["key"][lo:hi], p["start"][lo:hi], p["end"][lo:hi])
+        assert n == len(ol)
+        if flags & N.TILE_COUNT_ONLY:
+            assert left is None and right is None
+        else:
+            assert len(left) == n
+            r = right if right is not None else np.repeat(np.arange(hi - lo, dtype=np.uint32), counts)
+            assert np.all(np.diff(r.astype(np.int64)) >= 0)
+            assert np.array_equal(canon(left, r), canon(ol, orr))
+        if not flags & N.TILE_NO_COUNTS:
+            assert np.array_equal(counts, oc)
+        else:
+            assert counts is None
+        if flags & (N.TILE_RIGHT_IDX | N.TILE_EXPAND_RIGHT) and not flags & N.TILE_COUNT_ONLY and n:
+            assert right is not None and np.array_equal(right, np.repeat(np.arange(hi - lo, dtype=np.uint32), oc))
+
+
+@pytest.mark.parametrize("layout", ["packed", "soa"])
+@pytest.mark.parametrize("flags", [0, N.TILE_RIGHT_IDX, N.TILE_EXPAND_RIGHT, N.TILE_COUNT_ONLY,
+                                   N.TILE_COUNT_ONLY | N.TILE_NO_COUNTS])
+def test_pipeline_matches_oracle(cuda_ctx, oracle, layout, flags):
+    cuda_ctx.set_option("cuda_probe_layout", layout)
+    try:
+        b, p = sn.synth.cfg5(scale=0.004)
+        idx = sn.CudaIndex.build(cuda_ctx, b["key"], b["start"], b["end"])
+        st, out = run_pipeline(cuda_ctx, idx, p, 9, flags)
+        check_tiles(oracle, b, p, 9, out, flags)
+        stats = st.pipeline_stats()
+        assert stats["tiles"] == 9 and stats["h2d_bytes"] == 16 * len(p["key"])
+        if not flags & N.TILE_COUNT_ONLY:
+            assert stats["regrown"] <= 1  # only the first tile may have been sized blind
+    finally:
+        cuda_ctx.set_option("cuda_probe_layout", "auto")
+
+
+def test_pipeline_survives_fanout_jumps_and_empty_tiles(cuda_ctx, oracle):
+    """tiles alternate between ~1 and ~100 hits per row, with empty tiles and absent keys in between: every estimate
+    is wrong, so both the device re-emit and the pinned re-allocation paths run"""
+    rng = np.random.default_rng(3)
+    b4, p4 = sn.synth.cfg4(scale=0.02)
+    b2, p2 = sn.synth.cfg2(scale=0.02)
+    b2 = dict(b2)
+    b2["key"] = b2["key"] ^ np.uint64(0x5555)  # distinct key space: one index holds both shapes
+    p2 = dict(p2)
+    p2["key"] = p2["key"] ^ np.uint64(0x5555)
+    b = {k: np.concatenate([b4[k], b2[k]]) for k in ("key", "start", "end")}
+    idx = sn.CudaIndex.build(cuda_ctx, b["key"], b["start"], b["end"])
+    oidx = oracle.OracleIndex(b["key"], b["start"], b["end"])
+    st = sn.CudaStream(cuda_ctx)
+    pieces = []
+    for i in range(8):
+        src = p4 if i % 2 else p2
+        lo = int(rng.integers(0, len(src["key"]) - 3000))
+        n = 0 if i == 4 else int(rng.integers(500, 3000))
+        t = {k: cuda_ctx.pinned_copy(src[k][lo:lo + n]) for k in ("key", "start", "end")}
+        if i == 6:
+            t["key"][:] = np.uint64(12345)  # key hash absent from the build side: zero pairs (interval_join.rs:965)
+        pieces.append(t)
+    tickets = []
+    got = []
+    for t in pieces:
+        if len(tickets) == 3:
+            got.append(st.collect(tickets.pop(0)))
+        tickets.append(st.submit(idx, t["key"], t["start"], t["end"]))
+    with pytest.raises(sn.SequilaCudaError) as e:  # a fourth tile does not fit the default depth of 3
+        st.submit(idx, pieces[0]["key"], pieces[0]["start"], pieces[0]["end"])
+    assert e.value.code == N.SQ_EBUSY
+    with pytest.raises(sn.SequilaCudaError) as e:  # tiles are collected in submission order
+        st.collect(tickets[1])
+    assert e.value.code == N.SQ_ESTATE
+    while tickets:
+        got.append(st.collect(tickets.pop(0)))
+    for t, (n, left, right, counts) in zip(pieces, got):
+        ol, orr, oc = oidx.probe(t["key"], t["start"], t["end"])
+        assert n == len(ol) and np.array_equal(counts if counts is not None else np.zeros(0, np.uint32), oc)
+        if n:
+            assert np.array_equal(canon(left, np.repeat(np.arange(len(oc), dtype=np.uint32), counts)), canon(ol, orr))
+    assert got[6][0] == 0 and got[4][0] == 0
+    assert st.pipeline_stats()["regrown"] >= 2
+
+
+def test_pipeline_many_streams_concurrently(cuda_ctx, oracle):
+    """partitions = OS threads, one sq_stream each, each with tiles in flight over ONE shared index"""
+    import concurrent.futures as cf
+    b, p = sn.synth.cfg5(scale=0.004)
+    idx = sn.CudaIndex.build(cuda_ctx, b["key"], b["start"], b["end"])
+    T = 6
+    parts = tiles_of(p, T)
+
+    def work(lohi):
+        lo, hi = lohi
+        sub = {k: p[k][lo:hi] for k in ("key", "start", "end")}
+        _, out = run_pipeline(cuda_ctx, idx, sub, 5)
+        return sub, out
+    with cf.ThreadPoolExecutor(T) as pool:
+        res = list(pool.map(work, parts))
+    for sub, out in res:
+        check_tiles(oracle, b, sub, 5, out, 0)
+
+
+def test_pageable_inputs_and_depth_option(cuda_ctx, oracle):
+    b, p = sn.synth.cfg3(scale=0.005)
+    idx = sn.CudaIndex.build(cuda_ctx, b["key"], b["start"], b["end"])
+    try:
+        _, out = run_pipeline(cuda_ctx, idx, p, 7, 0, depth=2, pinned=False)
+        check_tiles(oracle, b, p, 7, out, 0)
+        _, out = run_pipeline(cuda_ctx, idx, p, 7, 0, depth=8)
+        check_tiles(oracle, b, p, 7, out, 0)
+    finally:
+        cuda_ctx.set_option("cuda_pipeline_depth", 3)
+
+
+def test_options_surface(cuda_ctx):
+    """the `sequila.cuda_*` keys: symbolic and numeric values, the optional prefix, rejections with a message"""
+    c = cuda_ctx
+    assert c.get_option("sequila.cuda_probe_layout") == "auto"
+    c.set_option("sequila.cuda_probe_layout", "SOA")
+    assert c.get_option("cuda_probe_layout") == "soa"
+    c.set_option("cuda_probe_layout", "auto")
+    c.set_option("cuda_probe_block", 256)
+    assert c.get_option("cuda_probe_block") == "256"
+    c.set_option("cuda_probe_block", 128)
+    for key, bad in (("cuda_probe_block", "100"), ("cuda_probe_layout", "tree"), ("cuda_pipeline_depth", "1"),
+                     ("cuda_scan_dict_capacity", "6"), ("cuda_nonsense", "1"), ("cuda_rows_per_bin", "x")):
+        with pytest.raises(sn.SequilaCudaError) as e:
+            c.set_option(key, bad)
+        assert e.value.code == N.SQ_EINVAL and key.split(".")[-1] in str(e.value)
+    c.set_option("cuda_l2_persist_mb", 0)
+    assert c.get_option("cuda_l2_persist_mb") == "0"

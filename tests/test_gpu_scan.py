@@ -111,12 +111,15 @@ def test_random_tables(stream, seed):
     check(stream, text, comment="#")
 
 
-def test_dictionary_table_growth(stream, monkeypatch):
-    monkeypatch.setenv("SQ_SCAN_DICT_CAP", "4")  # the table starts with 4 slots: 70 distinct names force two regrowths
-    rng = np.random.default_rng(9)
-    text, *_ = random_table(rng, 20_000, long_names=True)
-    sc, o = check(stream, text)
-    assert len(sc.dictionary) == 70
+def test_dictionary_table_growth(cuda_ctx, stream):
+    cuda_ctx.set_option("cuda_scan_dict_capacity", 4)  # the table starts with 4 slots: 70 distinct names force two regrowths
+    try:
+        rng = np.random.default_rng(9)
+        text, *_ = random_table(rng, 20_000, long_names=True)
+        sc, o = check(stream, text)
+        assert len(sc.dictionary) == 70
+    finally:
+        cuda_ctx.set_option("cuda_scan_dict_capacity", 1 << 16)
 
 
 def test_device_text_entry_point(cuda_ctx, stream):

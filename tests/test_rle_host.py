@@ -42,3 +42,25 @@ def test_expand_counts_variants(variant):
         assert np.array_equal(out[:len(want)], want), (trial, variant)
         assert (out[len(want):] == 0xDEADBEEF).all(), "wrote behind the last pair"
     assert ran or variant in (2, 3)
+
+
+@pytest.mark.parametrize("variant", [-1, 0, 1, 2, 3])
+def test_counts_that_sum_past_n_pairs_never_write_past_it(variant):
+    """counts and n_pairs that disagree (a caller bug, or counts of another tile): the expansion stops at n_pairs"""
+    from sequila_native_b200 import _native
+    lib = _native.lib()
+    rng = np.random.default_rng(70 + variant)
+    for trial in range(100):
+        n = int(rng.integers(1, 400))
+        counts = rng.integers(0, 90 if trial % 2 else 12, n).astype(np.uint32)
+        full = np.repeat(np.arange(n, dtype=np.uint32), counts)
+        if len(full) < 2:
+            continue
+        cut = int(rng.integers(1, len(full)))  # n_pairs < sum(counts)
+        out = np.full(cut + 64, 0xDEADBEEF, np.uint32)
+        ok = lib.sq_rle_expand_variant(variant, C.c_void_p(counts.ctypes.data), n, C.c_void_p(out.ctypes.data), cut)
+        if not ok:
+            assert variant in (2, 3)
+            continue
+        assert np.array_equal(out[:cut], full[:cut]), (trial, variant)
+        assert (out[cut:] == 0xDEADBEEF).all(), "wrote past n_pairs"
