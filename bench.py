@@ -388,62 +388,49 @@ def e2e_pipeline(sn, ctx, idx, probe_h, n_pairs_expect, args, T, flags, steps, b
     """End to end through the host C ABI, asynchronous tile pipeline (sq_stream_submit / sq_stream_collect): pinned
     host probe columns in, pinned host (left_idx, counts) out, fresh output buffers from the library's pool for every
     tile, no pre-pass, `cuda_pipeline_depth` tiles in flight per partition.  T host threads = DataFusion partitions
-    over one shared index (PartitionMode::CollectLeft, interval_join.rs:473-487)."""
-    import concurrent.futures as cf
+    over one shared index (PartitionMode::CollectLeft, interval_join.rs:473-487), run by the library's native partition
+    loop (sq_drive_partitions, include/sequila_driver.h: what a compiled host does; a Python loop holds the GIL for
+    ~100 us per tile, which at 64 tiles per step is most of the step).  The wire format is verified once, untimed, through
+    the Python binding of the same two calls: the host-side pairs digest must equal the device-side one."""
+    from sequila_native_b200.cuda_join import drive_partitions
     n_probe = len(probe_h["key"])
-    tiles_per = max(1, args.e2e_tiles // T)
-    n_tiles = T * tiles_per
-    bounds = np.linspace(0, n_probe, n_tiles + 1).astype(np.int64)
-    depth = int(ctx.get_option("cuda_pipeline_depth"))
-    workers = [{"st": sn.CudaStream(ctx), "tiles": list(range(w, n_tiles, T))} for w in range(T)]
+    n_tiles = max(T, (args.e2e_tiles // T) * T)
     hk, hs, he = probe_h["key"], probe_h["start"], probe_h["end"]
-    keep_last = {}
-
-    def run_partition(wk):
-        st, pend, got = wk["st"], [], 0
-        for t in wk["tiles"]:
-            if len(pend) == depth:
-                tk, tt = pend.pop(0)
-                res = st.collect(tk)
-                got += res[0]
-                keep_last[tt] = res
-            lo, hi = int(bounds[t]), int(bounds[t + 1])
-            pend.append((st.submit(idx, hk[lo:hi], hs[lo:hi], he[lo:hi], flags), t))
-        for tk, tt in pend:
-            res = st.collect(tk)
-            got += res[0]
-            keep_last[tt] = res
-        return got
-
-    pool = cf.ThreadPoolExecutor(T)
-
-    def step():
-        return sum(pool.map(run_partition, workers))
-
-    for _ in range(2):
-        got = step()
-        assert got == n_pairs_expect, (got, n_pairs_expect)
-    # parity of the wire format, once, untimed: the host-side pairs of the last warm-up step
     digest = None
     if not flags & 1:
-        cnt = tot = 0
-        for t in range(n_tiles):
-            n, left, right, counts = keep_last[t]
+        bounds = np.linspace(0, n_probe, 9).astype(np.int64)
+        st = sn.CudaStream(ctx)
+        depth = int(ctx.get_option("cuda_pipeline_depth"))
+        pend, cnt, tot = [], 0, 0
+
+        def fold(tk, t):
+            nonlocal cnt, tot
+            n, left, right, counts = st.collect(tk)
             r = np.repeat(np.arange(int(bounds[t]), int(bounds[t + 1]), dtype=np.uint64), counts)
-            c, s = host_digest(left, r)
+            c, s_ = host_digest(left, r)
             cnt += c
-            tot = (tot + s) & ((1 << 64) - 1)
+            tot = (tot + s_) & ((1 << 64) - 1)
+        for t in range(8):
+            if len(pend) == depth:
+                fold(*pend.pop(0))
+            lo, hi = int(bounds[t]), int(bounds[t + 1])
+            pend.append((st.submit(idx, hk[lo:hi], hs[lo:hi], he[lo:hi], flags), t))
+        for tk, t in pend:
+            fold(tk, t)
         digest = (cnt, tot)
-    keep_last.clear()
+        del st
+    for _ in range(2):
+        got = drive_partitions(ctx, idx, hk, hs, he, T, n_tiles, flags)
+        assert got["n_pairs"] == n_pairs_expect, (got, n_pairs_expect)
     barrier()
     e0 = time.perf_counter()
+    agg = {"h2d_ms": 0.0, "kernel_ms": 0.0, "d2h_ms": 0.0, "tiles": 0, "regrown": 0, "native_seconds": 0.0}
     for _ in range(steps):
-        step()
-        keep_last.clear()  # the consumer drops the tile results: their pinned buffers go back to the pool
+        r = drive_partitions(ctx, idx, hk, hs, he, T, n_tiles, flags)
+        for k, f in (("h2d_ms", "h2d_ms"), ("kernel_ms", "kernel_ms"), ("d2h_ms", "d2h_ms"), ("tiles", "n_tiles"),
+                     ("regrown", "regrown_tiles"), ("native_seconds", "seconds")):
+            agg[k] += r[f]
     ms = (time.perf_counter() - e0) * 1e3 / steps
-    stats = [w["st"].pipeline_stats() for w in workers]
-    pool.shutdown()
-    agg = {k: sum(s[k] for s in stats) for k in ("h2d_ms", "kernel_ms", "d2h_ms", "h2d_bytes", "d2h_bytes", "tiles", "regrown")}
     return ms, n_tiles, digest, agg
 
 
@@ -853,8 +840,9 @@ def main():
                     "wire": "in: key hash u64 + start/end i32 per probe row; out: left_idx u32 per pair + per-row counts u32 "
                             "(= rle_right, interval_join.rs:1604; right_idx is their run-length expansion and does not cross PCIe)",
                     "ms_per_step": e_ms_max, "rows_per_step_per_gpu": e2e_rows, "steps": args.e2e_steps,
-                    "api": "sq_stream_submit / sq_stream_collect (host C ABI): pinned host inputs, fresh pinned outputs from the "
-                           "library's pool per tile, no pre-pass", "partitions": T, "tiles": n_tiles,
+                    "api": "sq_stream_submit / sq_stream_collect (host C ABI) driven by sq_drive_partitions (native partition threads): "
+                           "pinned host inputs, fresh pinned outputs from the library's pool per tile, no pre-pass",
+                    "partitions": T, "tiles": n_tiles,
                     "pipeline_depth": int(ctx.get_option("cuda_pipeline_depth")),
                     "phase_ms": {"h2d_sum": e_stats["h2d_ms"], "kernels_sum": e_stats["kernel_ms"], "d2h_sum": e_stats["d2h_ms"],
                                  "tiles": e_stats["tiles"], "regrown": e_stats["regrown"]},

@@ -113,6 +113,20 @@ SCAN_SIGNATURES = {
 }
 
 
+class SqDriveStats(C.Structure):
+    """struct sq_drive_stats (include/sequila_driver.h)"""
+    _fields_ = [("n_pairs", C.c_uint64), ("n_tiles", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("left_xor", C.c_uint64), ("regrown_tiles", C.c_uint64), ("seconds", C.c_double), ("h2d_ms", C.c_double),
+                ("kernel_ms", C.c_double), ("d2h_ms", C.c_double)]
+
+
+# every symbol include/sequila_driver.h declares
+DRIVER_SIGNATURES = {
+    "sq_drive_partitions": (C.c_int32, [vp, vp, vp, vp, vp, C.c_uint64, C.c_int32, C.c_int32, C.c_uint32, C.c_int32, vp, vp,
+                                        C.POINTER(SqDriveStats)]),
+}
+
+
 class SqExecConfig(C.Structure):
     """struct sq_exec_config (include/sequila_exec.h)"""
     _fields_ = [("device", C.c_int32), ("n_on", C.c_int32), ("on_left", i32p), ("on_right", i32p),
@@ -155,7 +169,7 @@ def lib():
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
                 " (make -C sequila_native_b200/csrc). The cuda interval join has no CPU fallback.")
         L = C.CDLL(LIB_PATH)
-        for name, (res, args) in list(SIGNATURES.items()) + list(EXEC_SIGNATURES.items()) + list(SCAN_SIGNATURES.items()):
+        for name, (res, args) in list(SIGNATURES.items()) + list(EXEC_SIGNATURES.items()) + list(SCAN_SIGNATURES.items()) + list(DRIVER_SIGNATURES.items()):
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args

@@ -1,0 +1,106 @@
+// sq_drive_partitions (include/sequila_driver.h): the partition loop of a host over the public C ABI — what
+// IntervalJoinExec::execute + DataFusion's per-partition tasks do around the stream state machine
+// (interval_join.rs:449-557, 1054-1167).  Uses nothing but sequila_cuda.h.
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "sequila_driver.h"
+
+#define SQ_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+struct Part {
+  sq_stream* st = nullptr;
+  uint64_t pairs = 0, tiles = 0, x = 0;
+  int rc = SQ_OK;
+  std::string err;
+};
+
+}  // namespace
+
+SQ_API int32_t sq_drive_partitions(sq_ctx* ctx, const sq_index* idx, const uint64_t* key_hash, const int32_t* start,
+                                   const int32_t* end, uint64_t n_rows, int32_t n_partitions, int32_t n_tiles,
+                                   uint32_t flags, int32_t checksum, sq_tile_consumer consume, void* user,
+                                   sq_drive_stats* out) {
+  if (!ctx || !idx || !out || n_partitions < 1 || n_tiles < 1) return SQ_EINVAL;
+  memset(out, 0, sizeof *out);
+  const int T = n_partitions;
+  std::vector<Part> parts(static_cast<size_t>(T));
+  for (auto& p : parts) {
+    const int rc = sq_stream_create(ctx, &p.st);
+    if (rc != SQ_OK) {
+      for (auto& q : parts) if (q.st) sq_stream_free(q.st);
+      return rc;
+    }
+  }
+  char dv[16] = "3";
+  sq_ctx_get_option(ctx, "cuda_pipeline_depth", dv, sizeof dv);
+  const size_t depth = size_t(atoi(dv) > 0 ? atoi(dv) : 3);
+  auto bound = [&](int64_t t) { return uint64_t((__int128)n_rows * t / n_tiles); };
+
+  auto work = [&](int w) {
+    Part& p = parts[size_t(w)];
+    std::deque<std::pair<uint64_t, int>> pend;  // (ticket, tile)
+    auto collect_one = [&]() -> bool {
+      const auto [ticket, t] = pend.front();
+      pend.pop_front();
+      sq_tile_out res;
+      const int rc = sq_stream_collect(p.st, ticket, &res);
+      if (rc != SQ_OK) { p.rc = rc; p.err = sq_stream_last_error(p.st); return false; }
+      p.pairs += res.n_pairs;
+      p.tiles += 1;
+      if (checksum && res.left_idx) {
+        uint64_t x = 0;
+        const uint32_t* l = res.left_idx;
+        for (uint64_t k = 0; k < res.n_pairs; ++k) x ^= l[k];
+        p.x ^= x;
+      }
+      if (consume) consume(user, w, bound(t), &res);
+      sq_host_free(ctx, res.left_idx);
+      sq_host_free(ctx, res.right_idx);
+      sq_host_free(ctx, res.counts);
+      return true;
+    };
+    for (int t = w; t < n_tiles; t += T) {
+      if (pend.size() == depth && !collect_one()) return;
+      const uint64_t lo = bound(t), hi = bound(t + 1);
+      uint64_t ticket = 0;
+      const int rc = sq_stream_submit(p.st, idx, key_hash + lo, start + lo, end + lo, uint32_t(hi - lo), flags, &ticket);
+      if (rc != SQ_OK) { p.rc = rc; p.err = sq_stream_last_error(p.st); return; }
+      pend.emplace_back(ticket, t);
+    }
+    while (!pend.empty())
+      if (!collect_one()) return;
+  };
+
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> pool;
+  for (int w = 1; w < T; ++w) pool.emplace_back(work, w);
+  work(0);
+  for (auto& th : pool) th.join();
+  out->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+  int rc = SQ_OK;
+  for (auto& p : parts) {
+    out->n_pairs += p.pairs;
+    out->n_tiles += p.tiles;
+    out->left_xor ^= p.x;
+    double s8[8] = {0};
+    sq_stream_pipeline_stats(p.st, s8);
+    out->h2d_ms += s8[0];
+    out->kernel_ms += s8[1];
+    out->d2h_ms += s8[2];
+    out->h2d_bytes += uint64_t(s8[3]);
+    out->d2h_bytes += uint64_t(s8[4]);
+    out->regrown_tiles += uint64_t(s8[6]);
+    if (p.rc != SQ_OK && rc == SQ_OK) rc = p.rc;
+    sq_stream_free(p.st);
+  }
+  return rc;
+}

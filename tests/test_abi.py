@@ -43,9 +43,13 @@ def test_library_exports_every_declared_symbol():
     missing = [x for x in declared_scan if not hasattr(lib, x)]
     assert not missing, missing
     assert sorted(_native.SCAN_SIGNATURES) == declared_scan
+    # and the native partition loop, include/sequila_driver.h
+    declared_drv = [x for x in header_symbols("sequila_driver.h") if x.startswith("sq_drive_")]
+    assert declared_drv == ["sq_drive_partitions"] and hasattr(lib, "sq_drive_partitions")
+    assert sorted(_native.DRIVER_SIGNATURES) == declared_drv
 
 
-@pytest.mark.parametrize("header", ["sequila_cuda.h", "sequila_exec.h", "sequila_scan.h"])
+@pytest.mark.parametrize("header", ["sequila_cuda.h", "sequila_exec.h", "sequila_scan.h", "sequila_driver.h"])
 def test_headers_are_plain_c(header):
     """the boundary is a C ABI: every header must compile as C11 on its own (what cgo / bindgen / a C host would see)"""
     import shutil
