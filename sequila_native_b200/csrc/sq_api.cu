@@ -411,14 +411,61 @@ SQ_API const uint32_t* sq_stream_counts_device(const sq_stream* s) {
 }
 
 // ---- probe ------------------------------------------------------------------------------------
-// Reads {n_pairs, overflow} written by k_probe_join and closes the count phase.
-static int32_t finish_count(sq_stream* s, bool wrote, uint64_t* n_pairs_out) {
+namespace sq {
+// Which packed-line kernel serves a tile.  The staged kernel (sq_probe_staged.cu) wins by 2-3x on position-local
+// tiles and loses badly on scattered ones (its CTAs then walk global memory thread by thread), so: option on / off
+// force it; auto looks at the order of the tile's host columns when the caller has them (1024 adjacent pairs: same key
+// and non-decreasing start), and otherwise learns from the kernel's own report — result[2] = CTAs that could not
+// stage — backing off exponentially (2, 4, ... 256 tiles) while tiles keep failing.
+bool pick_staged(sq_stream* policy, const sq_index* idx, const uint64_t* host_key, const int32_t* host_start, uint32_t n) {
+  if (!idx->d_lines || n == 0) return false;
+  const int opt = idx->ctx->opt.staged_probe.load(std::memory_order_relaxed);
+  if (opt == 1) return true;
+  if (opt == 2) return false;
+  if (host_key && host_start && n >= 64) {
+    const uint32_t m = n - 1 < 1024u ? n - 1 : 1024u;
+    const uint32_t stride = (n - 1) / m;
+    uint32_t ordered = 0;
+    for (uint32_t k = 0; k < m; ++k) {
+      const size_t a = size_t(k) * stride;
+      ordered += (host_key[a] == host_key[a + 1] && host_start[a] <= host_start[a + 1]) ? 1u : 0u;
+    }
+    if (ordered * 8u < m * 7u) return false;  // not position-ordered: do not even try
+  }
+  if (policy->staged_skip) { policy->staged_skip -= 1; return false; }
+  return true;
+}
+
+void staged_feedback(sq_stream* policy, uint32_t n_rows, uint64_t global_ctas) {
+  const uint64_t ctas = (uint64_t(n_rows) + staged_tile_rows() - 1) / staged_tile_rows();
+  policy->staged_tiles += 1;
+  policy->staged_global_ctas += global_ctas;
+  if (global_ctas * 16 > ctas) {  // more than 1/16 of the CTAs walked global memory: this stream's tiles are scattered
+    policy->staged_backoff = policy->staged_backoff ? (policy->staged_backoff < 128 ? policy->staged_backoff * 2 : 256) : 2;
+    policy->staged_skip = policy->staged_backoff;
+  } else {
+    policy->staged_backoff = 0;
+  }
+}
+
+int launch_packed_any(sq_stream* s, sq_stream* policy, bool staged, const sq_index* idx, const uint64_t* d_key,
+                      const int32_t* d_start, const int32_t* d_end, uint32_t n, uint32_t* d_left, uint32_t* d_right,
+                      uint64_t capacity) {
+  (void)policy;
+  if (staged) return launch_staged(s, idx, d_key, d_start, d_end, n, d_left, d_right, capacity);
+  return launch_packed(s, idx, d_key, d_start, d_end, n, d_left, d_right, capacity);
+}
+}  // namespace sq
+
+// Reads {n_pairs, overflow} written by the probe kernels and closes the count phase.
+static int32_t finish_count(sq_stream* s, bool wrote, uint64_t* n_pairs_out, bool staged = false) {
   ErrorSlot& E = s->err;
   int rc;
   if ((rc = ensure(E, s->h_scalar, 256, true))) return rc;
   auto* h = static_cast<unsigned long long*>(s->h_scalar.p);
-  SQ_CUDA(E, cudaMemcpyAsync(h, s->d_scalar.p, 16, cudaMemcpyDeviceToHost, s->stream));
+  SQ_CUDA(E, cudaMemcpyAsync(h, s->d_scalar.p, 32, cudaMemcpyDeviceToHost, s->stream));
   SQ_CUDA(E, cudaStreamSynchronize(s->stream));
+  if (staged) staged_feedback(s, s->n_rows, h[2]);
   s->n_pairs = h[0];
   s->spec_valid = wrote && h[1] == 0;
   s->counted = true;
@@ -467,15 +514,17 @@ static int32_t empty_tile(sq_stream* s, uint64_t* n_pairs_out) {
 // device tile: one fused pass; writes into (d_left, d_right) when the pairs fit `capacity`
 static int32_t join_device(sq_stream* s, const sq_index* idx, const uint64_t* dk, const int32_t* ds,
                            const int32_t* de, uint32_t n, uint32_t* d_left, uint32_t* d_right, uint64_t capacity,
-                           uint64_t* n_pairs_out) {
+                           uint64_t* n_pairs_out, const uint64_t* host_key = nullptr, const int32_t* host_start = nullptr) {
   begin_tile(s, idx, dk, ds, de, n);
   if (n == 0) return empty_tile(s, n_pairs_out);
   int rc;
   mark(s, 1);
   const bool wrote = d_left != nullptr && capacity > 0;
+  bool staged = false;
   if (use_packed(idx)) {
     // narrow index: ONE kernel searches, counts, scans and (when there is room) writes
-    if ((rc = launch_packed(s, idx, dk, ds, de, n, wrote ? d_left : nullptr, d_right, capacity))) return rc;
+    staged = pick_staged(s, idx, host_key, host_start, n);
+    if ((rc = launch_packed_any(s, s, staged, idx, dk, ds, de, n, wrote ? d_left : nullptr, d_right, capacity))) return rc;
   } else {
     if ((rc = launch_count(s, idx, dk, ds, de, n))) return rc;
     // speculative emit: the write kernel checks n_pairs <= capacity on the device, so the whole
@@ -485,7 +534,7 @@ static int32_t join_device(sq_stream* s, const sq_index* idx, const uint64_t* dk
   mark(s, 2);
   s->d_spec_left = d_left;
   s->d_spec_right = d_right;
-  return finish_count(s, wrote, n_pairs_out);
+  return finish_count(s, wrote, n_pairs_out, staged);
 }
 
 SQ_API int32_t sq_probe_count_device(sq_stream* s, const sq_index* idx, const uint64_t* d_key_hash,
@@ -540,7 +589,7 @@ static int32_t count_host(sq_stream* s, const sq_index* idx, const uint64_t* key
   SQ_CUDA(E, cudaMemcpyAsync(ds, start, n * 4, cudaMemcpyHostToDevice, s->stream));
   SQ_CUDA(E, cudaMemcpyAsync(de, end, n * 4, cudaMemcpyHostToDevice, s->stream));
   return join_device(s, idx, dk, ds, de, n_rows, static_cast<uint32_t*>(s->d_left.p),
-                     static_cast<uint32_t*>(s->d_right.p), cap, n_pairs_out);
+                     static_cast<uint32_t*>(s->d_right.p), cap, n_pairs_out, key_hash, start);
 }
 
 SQ_API int32_t sq_probe_count(sq_stream* s, const sq_index* idx, const uint64_t* key_hash, const int32_t* start,

@@ -207,6 +207,11 @@ struct sq_stream {
   uint64_t pipe_bytes[2] = {0, 0};     // bytes moved h2d / d2h
   uint64_t pipe_tiles = 0, pipe_regrow = 0;
 
+  // which packed-line kernel serves the next tile (sq_api.cu: pick_staged / staged_feedback)
+  uint32_t staged_skip = 0;      // tiles to send to k_probe_packed before the staged kernel is tried again
+  uint32_t staged_backoff = 0;   // grows while tiles keep failing to stage
+  uint64_t staged_tiles = 0, staged_global_ctas = 0;
+
   // state of the tile currently between count and emit
   const sq_index* idx = nullptr;
   const sq_index* l2_window_idx = nullptr;  // index whose directory this stream's L2 window covers
@@ -301,6 +306,18 @@ int launch_narrow_offsets(sq_stream* s, const int64_t* d_in, uint64_t n, int32_t
 int launch_packed(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
                   const int32_t* d_end, uint32_t n, uint32_t* d_left, uint32_t* d_right, uint64_t capacity);
 bool use_packed(const sq_index* idx);
+// probe_staged.cu: the same contract as launch_packed for position-local tiles (build tile staged in shared memory by
+// TMA, one thread per probe row); result[2] = CTAs that could not stage and walked global memory instead
+int launch_staged(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
+                  const int32_t* d_end, uint32_t n, uint32_t* d_left, uint32_t* d_right, uint64_t capacity);
+uint32_t staged_tile_rows();
+// api.cu: adaptive choice between the two (option cuda_staged_probe; `policy` = the stream that keeps the statistics,
+// `host_key` / `host_start` = the tile's host columns when the caller has them: a cheap look at their order)
+bool pick_staged(sq_stream* policy, const sq_index* idx, const uint64_t* host_key, const int32_t* host_start, uint32_t n);
+void staged_feedback(sq_stream* policy, uint32_t n_rows, uint64_t global_ctas);
+int launch_packed_any(sq_stream* s, sq_stream* policy, bool staged, const sq_index* idx, const uint64_t* d_key,
+                      const int32_t* d_start, const int32_t* d_end, uint32_t n, uint32_t* d_left, uint32_t* d_right,
+                      uint64_t capacity);
 
 
 // api.cu: per-tile state of a stream (count -> emit protocol) and the write pass of a counted tile

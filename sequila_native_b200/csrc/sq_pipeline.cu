@@ -36,6 +36,7 @@ struct sq_tile_slot {
   uint64_t h_cap = 0;    // pairs the pinned pair buffers hold
   uint64_t dev_cap = 0;  // pairs the device pair buffers were offered
   uint64_t spec = 0;     // pairs whose copy-out is already enqueued
+  bool staged = false;   // served by the staged kernel: its report feeds the stream's kernel choice
   cudaEvent_t ev[6] = {};  // 0 h2d begin, 1 h2d end, 2 kernels end, 3 scalars + counts arrived, 4 d2h begin, 5 d2h end
   bool ev_ready = false;
 };
@@ -148,7 +149,7 @@ SQ_API int32_t sq_stream_submit(sq_stream* s, const sq_index* idx, const uint64_
   sl->flags = flags;
   sl->idx = idx;
   auto* hs = static_cast<unsigned long long*>(sl->h_scalar.p);
-  hs[0] = hs[1] = 0;
+  hs[0] = hs[1] = hs[2] = 0;
 
   auto* dk = static_cast<uint64_t*>(sub->d_in.p);
   auto* ds = reinterpret_cast<int32_t*>(dk + n);
@@ -166,8 +167,11 @@ SQ_API int32_t sq_stream_submit(sq_stream* s, const sq_index* idx, const uint64_
     SQ_CUDA(E, cudaStreamWaitEvent(s->stream, sl->ev[1], 0));
     uint32_t* d_left = dev_cap ? static_cast<uint32_t*>(sub->d_left.p) : nullptr;
     uint32_t* d_right = want_right ? static_cast<uint32_t*>(sub->d_right.p) : nullptr;
+    sl->staged = false;
     if (use_packed(idx)) {
-      if ((rc = launch_packed(sub, idx, dk, ds, de, n_rows, d_left, d_right, dev_cap))) return fail(E, rc, "%s", sub->err.msg.c_str());
+      sl->staged = pick_staged(s, idx, key_hash, start, n_rows);
+      if ((rc = launch_packed_any(sub, s, sl->staged, idx, dk, ds, de, n_rows, d_left, d_right, dev_cap)))
+        return fail(E, rc, "%s", sub->err.msg.c_str());
     } else {
       if ((rc = launch_count(sub, idx, dk, ds, de, n_rows))) return fail(E, rc, "%s", sub->err.msg.c_str());
       if (d_left && (rc = launch_write(sub, idx, ds, n_rows, d_left, d_right, dev_cap))) return fail(E, rc, "%s", sub->err.msg.c_str());
@@ -178,7 +182,7 @@ SQ_API int32_t sq_stream_submit(sq_stream* s, const sq_index* idx, const uint64_
     // ---- copy-out
     SQ_CUDA(E, cudaStreamWaitEvent(s->stream_out, sl->ev[2], 0));
     SQ_CUDA(E, cudaEventRecord(sl->ev[4], s->stream_out));
-    SQ_CUDA(E, cudaMemcpyAsync(hs, sub->d_scalar.p, 16, cudaMemcpyDeviceToHost, s->stream_out));
+    SQ_CUDA(E, cudaMemcpyAsync(hs, sub->d_scalar.p, 32, cudaMemcpyDeviceToHost, s->stream_out));
     if (sl->h_counts) SQ_CUDA(E, cudaMemcpyAsync(sl->h_counts, sub->d_cnt.p, n * 4, cudaMemcpyDeviceToHost, s->stream_out));
     SQ_CUDA(E, cudaEventRecord(sl->ev[3], s->stream_out));
     if (est) {
@@ -221,6 +225,7 @@ SQ_API int32_t sq_stream_collect(sq_stream* s, uint64_t ticket, sq_tile_out* out
     if (ce != cudaSuccess) return bail(fail(E, SQ_ECUDA, "tile %llu failed on the device: %s", (unsigned long long)ticket, cudaGetErrorString(ce)));
     auto* hs = static_cast<unsigned long long*>(sl->h_scalar.p);
     n_pairs = hs[0];
+    if (sl->staged) staged_feedback(s, sl->n_rows, hs[2]);
     const bool overflow = hs[1] != 0 || n_pairs > sl->dev_cap;
     uint64_t copied = sl->spec;
     if (!count_only && n_pairs) {

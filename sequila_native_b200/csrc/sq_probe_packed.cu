@@ -31,33 +31,6 @@
 namespace sq {
 
 
-struct StartLine {
-  uint32_t line;   // line holding the last row whose start can be <= qe
-  uint32_t first;  // first line of the key segment
-  bool act;        // false: no row of the build side can match
-};
-
-__device__ __forceinline__ StartLine find_start_line(const IndexView& iv, uint32_t id, int32_t qe) {
-  StartLine r{0u, 0u, false};
-  if (id == kNoKey) return r;  // key hash absent from the build side: no rows (interval_join.rs:965)
-  const SegMeta m = iv.meta[id];
-  if (qe < m.min_start) return r;
-  const uint32_t off = uint32_t(qe) - uint32_t(m.min_start);
-  const uint32_t b = m.shift >= 32 ? 0u : (off >> m.shift);
-  // directory entry b + 1 = first row whose bin is > b: every row with start <= qe lies below it, and
-  // dir_line gives the line of the last such row directly
-  const uint2 e = __ldg(iv.dir_line + m.dir_base + (b >= m.nbins ? m.nbins : b + 1u));
-  r.first = m.line_base;
-  // e.y = first start of line e.x: when it lies past qe the line holds no candidate and the walk starts a line earlier
-#ifdef SQ_NO_LINE_SKIP  // A/B builds only
-  r.line = e.x;
-#else
-  r.line = e.x - ((qe < int32_t(e.y) && e.x > r.first) ? 1u : 0u);
-#endif
-  r.act = true;
-  return r;
-}
-
 // kTiles consecutive tiles per CTA: the probe columns and directory words of ALL of them are requested up
 // front, so only the first tile of a CTA waits for those two round trips (count-only launches use 2; see
 // launch_packed_b for why emitting launches use 1).

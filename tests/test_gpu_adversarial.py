@@ -12,11 +12,15 @@ from helpers import canon
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["packed", "soa"])
+@pytest.fixture(autouse=True, params=["packed", "soa", "staged"])
 def probe_layout(request, cuda_ctx):
-    cuda_ctx.set_option("sequila.cuda_probe_layout", request.param)
+    # "staged" = packed lines served by the shared-memory (TMA) staged kernel whatever the probe order: unsorted tiles
+    # then exercise its global-memory path, sorted ones the staged path
+    cuda_ctx.set_option("sequila.cuda_probe_layout", "packed" if request.param == "staged" else request.param)
+    cuda_ctx.set_option("sequila.cuda_staged_probe", "on" if request.param == "staged" else "off")
     yield request.param
     cuda_ctx.set_option("sequila.cuda_probe_layout", "auto")
+    cuda_ctx.set_option("sequila.cuda_staged_probe", "auto")
 
 
 def check(oracle, ctx, b, p):

@@ -92,6 +92,20 @@ def test_cfg5_shard_whole_launch_matches_oracle(cuda_ctx, oracle):
         assert bool((right[1:n] >= right[:n - 1]).all())
         assert np.array_equal(counts_of(st, A.shard_rows), want_counts)
         del left, right
+    # the same rows position-sorted through the staged (TMA) kernel: same multiset of (left, original probe row) pairs
+    order = torch.argsort(probe["contig"].to(torch.int64) * (1 << 32) + probe["start"].to(torch.int64))
+    sp = {k: probe[k][order].contiguous() for k in ("key", "start", "end")}
+    cuda_ctx.set_option("cuda_staged_probe", "on")
+    try:
+        st, n, left, right = device_join(cuda_ctx, idx, sp, True)
+    finally:
+        cuda_ctx.set_option("cuda_staged_probe", "auto")
+    assert n == want_pairs
+    assert bool((right[1:n] >= right[:n - 1]).all())
+    assert np.array_equal(counts_of(st, A.shard_rows), want_counts[order.cpu().numpy()])
+    orig = order.to(torch.int32)[right[:n].long()].contiguous()  # right_idx back in the unsorted numbering
+    dg = st.digest_device(left, orig, n)
+    assert dg[0] == want_pairs and dg[1] == want_digest
 
 
 def test_two_rank_shards_on_one_gpu_cover_the_join(cuda_ctx, oracle):
