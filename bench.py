@@ -389,10 +389,11 @@ def e2e_pipeline(sn, ctx, idx, probe_h, n_pairs_expect, args, T, flags, steps, b
     host probe columns in, pinned host (left_idx, counts) out, fresh output buffers from the library's pool for every
     tile, no pre-pass, `cuda_pipeline_depth` tiles in flight per partition.  T host threads = DataFusion partitions
     over one shared index (PartitionMode::CollectLeft, interval_join.rs:473-487), run by the library's native partition
-    loop (sq_drive_partitions, include/sequila_driver.h: what a compiled host does; a Python loop holds the GIL for
+    loop (sq_driver_run, include/sequila_driver.h: what a compiled host does; a Python loop holds the GIL for
     ~100 us per tile, which at 64 tiles per step is most of the step).  The wire format is verified once, untimed, through
     the Python binding of the same two calls: the host-side pairs digest must equal the device-side one."""
-    from sequila_native_b200.cuda_join import drive_partitions
+    from sequila_native_b200.cuda_join import CudaDriver
+    drv = CudaDriver(ctx, T)
     n_probe = len(probe_h["key"])
     n_tiles = max(T, (args.e2e_tiles // T) * T)
     hk, hs, he = probe_h["key"], probe_h["start"], probe_h["end"]
@@ -420,13 +421,13 @@ def e2e_pipeline(sn, ctx, idx, probe_h, n_pairs_expect, args, T, flags, steps, b
         digest = (cnt, tot)
         del st
     for _ in range(2):
-        got = drive_partitions(ctx, idx, hk, hs, he, T, n_tiles, flags)
+        got = drv.run(idx, hk, hs, he, n_tiles, flags)
         assert got["n_pairs"] == n_pairs_expect, (got, n_pairs_expect)
     barrier()
     e0 = time.perf_counter()
     agg = {"h2d_ms": 0.0, "kernel_ms": 0.0, "d2h_ms": 0.0, "tiles": 0, "regrown": 0, "native_seconds": 0.0}
     for _ in range(steps):
-        r = drive_partitions(ctx, idx, hk, hs, he, T, n_tiles, flags)
+        r = drv.run(idx, hk, hs, he, n_tiles, flags)
         for k, f in (("h2d_ms", "h2d_ms"), ("kernel_ms", "kernel_ms"), ("d2h_ms", "d2h_ms"), ("tiles", "n_tiles"),
                      ("regrown", "regrown_tiles"), ("native_seconds", "seconds")):
             agg[k] += r[f]
@@ -840,7 +841,7 @@ def main():
                     "wire": "in: key hash u64 + start/end i32 per probe row; out: left_idx u32 per pair + per-row counts u32 "
                             "(= rle_right, interval_join.rs:1604; right_idx is their run-length expansion and does not cross PCIe)",
                     "ms_per_step": e_ms_max, "rows_per_step_per_gpu": e2e_rows, "steps": args.e2e_steps,
-                    "api": "sq_stream_submit / sq_stream_collect (host C ABI) driven by sq_drive_partitions (native partition threads): "
+                    "api": "sq_stream_submit / sq_stream_collect (host C ABI) driven by sq_driver_run (native partition threads): "
                            "pinned host inputs, fresh pinned outputs from the library's pool per tile, no pre-pass",
                     "partitions": T, "tiles": n_tiles,
                     "pipeline_depth": int(ctx.get_option("cuda_pipeline_depth")),

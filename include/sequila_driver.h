@@ -2,7 +2,7 @@
  *
  * In the reference DataFusion spawns one task per output partition; each polls its IntervalJoinStream, which
  * fetches a probe batch, joins it and yields one output batch (interval_join.rs:449-557, 1054-1167, 1192-1233).
- * sq_drive_partitions is that loop over the C ABI of sequila_cuda.h for a probe side that already sits in (pinned)
+ * sq_driver_run is that loop over the C ABI of sequila_cuda.h for a probe side that already sits in (pinned)
  * host memory: `n_partitions` OS threads, one sq_stream each, the probe rows cut into `n_tiles` tiles dealt
  * round-robin (tile t -> partition t % n_partitions, as DataFusion's round-robin repartitioning would), every
  * partition keeping `cuda_pipeline_depth` tiles in flight through sq_stream_submit / sq_stream_collect and handing
@@ -33,12 +33,17 @@ typedef struct sq_drive_stats {
   double h2d_ms, kernel_ms, d2h_ms; /* device time summed over tiles */
 } sq_drive_stats;
 
-/* flags = SQ_TILE_* of sq_stream_submit.  `checksum` != 0 makes every partition xor the left_idx of its tiles
- * (reads all output bytes once on the host: a stand-in for a consumer that touches the result). */
-int32_t sq_drive_partitions(sq_ctx* ctx, const sq_index* idx, const uint64_t* key_hash, const int32_t* start,
-                            const int32_t* end, uint64_t n_rows, int32_t n_partitions, int32_t n_tiles,
-                            uint32_t flags, int32_t checksum, sq_tile_consumer consume, void* user,
-                            sq_drive_stats* stats_out);
+/* A driver owns `n_partitions` sq_streams (their device scratch, pinned staging and CUDA streams live as long as it
+ * does, like the IntervalJoinStreams of a running query).  sq_driver_run makes one pass over a probe side:
+ * flags = SQ_TILE_* of sq_stream_submit; `checksum` != 0 makes every partition xor the left_idx of its tiles (reads all
+ * output bytes once on the host: a stand-in for a consumer that touches the result).  One run at a time per driver. */
+typedef struct sq_driver sq_driver;
+int32_t sq_driver_create(sq_ctx* ctx, int32_t n_partitions, sq_driver** out);
+int32_t sq_driver_run(sq_driver* d, const sq_index* idx, const uint64_t* key_hash, const int32_t* start,
+                      const int32_t* end, uint64_t n_rows, int32_t n_tiles, uint32_t flags, int32_t checksum,
+                      sq_tile_consumer consume, void* user, sq_drive_stats* stats_out);
+const char* sq_driver_last_error(const sq_driver* d);
+void sq_driver_free(sq_driver* d);
 
 #ifdef __cplusplus
 }

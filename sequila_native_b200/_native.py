@@ -122,8 +122,11 @@ class SqDriveStats(C.Structure):
 
 # every symbol include/sequila_driver.h declares
 DRIVER_SIGNATURES = {
-    "sq_drive_partitions": (C.c_int32, [vp, vp, vp, vp, vp, C.c_uint64, C.c_int32, C.c_int32, C.c_uint32, C.c_int32, vp, vp,
-                                        C.POINTER(SqDriveStats)]),
+    "sq_driver_create": (C.c_int32, [vp, C.c_int32, C.POINTER(vp)]),
+    "sq_driver_run": (C.c_int32, [vp, vp, vp, vp, vp, C.c_uint64, C.c_int32, C.c_uint32, C.c_int32, vp, vp,
+                                  C.POINTER(SqDriveStats)]),
+    "sq_driver_last_error": (C.c_char_p, [vp]),
+    "sq_driver_free": (None, [vp]),
 }
 
 

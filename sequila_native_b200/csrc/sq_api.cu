@@ -412,17 +412,34 @@ SQ_API const uint32_t* sq_stream_counts_device(const sq_stream* s) {
 
 // ---- probe ------------------------------------------------------------------------------------
 namespace sq {
-// Which packed-line kernel serves a tile.  The staged kernel (sq_probe_staged.cu) wins by 2-3x on position-local
-// tiles and loses badly on scattered ones (its CTAs then walk global memory thread by thread), so: option on / off
-// force it; auto looks at the order of the tile's host columns when the caller has them (1024 adjacent pairs: same key
-// and non-decreasing start), and otherwise learns from the kernel's own report — result[2] = CTAs that could not
-// stage — backing off exponentially (2, 4, ... 256 tiles) while tiles keep failing.
-bool pick_staged(sq_stream* policy, const sq_index* idx, const uint64_t* host_key, const int32_t* host_start, uint32_t n) {
+// Which packed-line kernel serves a tile.  Measured on B200 (12.5M probe rows per launch, 100M-row index; DESIGN.md
+// section 4): on position-sorted tiles as dense as the index (a CTA stages ~13 lines) the staged kernel
+// (sq_probe_staged.cu) counts in 0.33 ms against 0.40 ms for k_probe_packed and joins in 0.76 ms against 0.77 ms; on
+// sorted tiles 8x sparser than the index (73 lines per CTA, every build row decoded for one probe row in eight) it loses
+// (join 0.98 vs 0.84 ms, count 0.50 vs 0.44 ms), and on scattered tiles its CTAs walk global memory thread by thread (3.8 vs
+// 0.98 ms).  So: option on / off force it; auto sends only count-only launches of position-local, dense tiles to it.
+// "Position-local" is judged from the order of the tile's host columns when the caller has them (1024 adjacent pairs:
+// same key, non-decreasing start), from a sampling kernel for device tiles; "dense" from the kernel's own report —
+// result[2] = CTAs that could not stage, result[3] = lines staged — backing off exponentially (2, 4, ... 256 tiles).
+bool pick_staged(sq_stream* policy, const sq_index* idx, const uint64_t* host_key, const int32_t* host_start,
+                 const uint64_t* d_key, const int32_t* d_start, uint32_t n, bool emits) {
   if (!idx->d_lines || n == 0) return false;
   const int opt = idx->ctx->opt.staged_probe.load(std::memory_order_relaxed);
   if (opt == 1) return true;
   if (opt == 2) return false;
-  if (host_key && host_start && n >= 64) {
+  if (n < 64 || emits) return false;
+  if (!host_key && d_key && d_start) {
+    // device tile (the caller synchronises on the result anyway): one 1024-thread sampling kernel, every 32nd tile
+    if (policy->order_age == 0) {
+      uint32_t r[2] = {0, 1};
+      if (sample_order_device(policy, d_key, d_start, n, r) != SQ_OK) return false;
+      policy->order_local = r[0] * 8u >= r[1] * 7u;
+      policy->order_age = 32;
+    }
+    policy->order_age -= 1;
+    if (!policy->order_local) return false;
+  }
+  if (host_key && host_start) {
     const uint32_t m = n - 1 < 1024u ? n - 1 : 1024u;
     const uint32_t stride = (n - 1) / m;
     uint32_t ordered = 0;
@@ -436,11 +453,14 @@ bool pick_staged(sq_stream* policy, const sq_index* idx, const uint64_t* host_ke
   return true;
 }
 
-void staged_feedback(sq_stream* policy, uint32_t n_rows, uint64_t global_ctas) {
+void staged_feedback(sq_stream* policy, uint32_t n_rows, uint64_t global_ctas, uint64_t staged_lines) {
   const uint64_t ctas = (uint64_t(n_rows) + staged_tile_rows() - 1) / staged_tile_rows();
   policy->staged_tiles += 1;
   policy->staged_global_ctas += global_ctas;
-  if (global_ctas * 16 > ctas) {  // more than 1/16 of the CTAs walked global memory: this stream's tiles are scattered
+  // more than 1/16 of the CTAs walked global memory (scattered tiles), or the staged CTAs carried more than 32 lines each
+  // (probe rows much sparser than the index: decoding every build row costs more than the cooperative walk)
+  if (global_ctas * 16 > ctas || staged_lines > 32 * (ctas - global_ctas)) {
+    policy->order_local = false;
     policy->staged_backoff = policy->staged_backoff ? (policy->staged_backoff < 128 ? policy->staged_backoff * 2 : 256) : 2;
     policy->staged_skip = policy->staged_backoff;
   } else {
@@ -465,7 +485,7 @@ static int32_t finish_count(sq_stream* s, bool wrote, uint64_t* n_pairs_out, boo
   auto* h = static_cast<unsigned long long*>(s->h_scalar.p);
   SQ_CUDA(E, cudaMemcpyAsync(h, s->d_scalar.p, 32, cudaMemcpyDeviceToHost, s->stream));
   SQ_CUDA(E, cudaStreamSynchronize(s->stream));
-  if (staged) staged_feedback(s, s->n_rows, h[2]);
+  if (staged) staged_feedback(s, s->n_rows, h[2], h[3]);
   s->n_pairs = h[0];
   s->spec_valid = wrote && h[1] == 0;
   s->counted = true;
@@ -523,7 +543,7 @@ static int32_t join_device(sq_stream* s, const sq_index* idx, const uint64_t* dk
   bool staged = false;
   if (use_packed(idx)) {
     // narrow index: ONE kernel searches, counts, scans and (when there is room) writes
-    staged = pick_staged(s, idx, host_key, host_start, n);
+    staged = pick_staged(s, idx, host_key, host_start, dk, ds, n, wrote);
     if ((rc = launch_packed_any(s, s, staged, idx, dk, ds, de, n, wrote ? d_left : nullptr, d_right, capacity))) return rc;
   } else {
     if ((rc = launch_count(s, idx, dk, ds, de, n))) return rc;

@@ -211,6 +211,8 @@ struct sq_stream {
   uint32_t staged_skip = 0;      // tiles to send to k_probe_packed before the staged kernel is tried again
   uint32_t staged_backoff = 0;   // grows while tiles keep failing to stage
   uint64_t staged_tiles = 0, staged_global_ctas = 0;
+  bool order_local = false;      // verdict of the last look at a device tile's row order
+  uint32_t order_age = 0;        // device tiles until the next look
 
   // state of the tile currently between count and emit
   const sq_index* idx = nullptr;
@@ -313,8 +315,12 @@ int launch_staged(sq_stream* s, const sq_index* idx, const uint64_t* d_key, cons
 uint32_t staged_tile_rows();
 // api.cu: adaptive choice between the two (option cuda_staged_probe; `policy` = the stream that keeps the statistics,
 // `host_key` / `host_start` = the tile's host columns when the caller has them: a cheap look at their order)
-bool pick_staged(sq_stream* policy, const sq_index* idx, const uint64_t* host_key, const int32_t* host_start, uint32_t n);
-void staged_feedback(sq_stream* policy, uint32_t n_rows, uint64_t global_ctas);
+bool pick_staged(sq_stream* policy, const sq_index* idx, const uint64_t* host_key, const int32_t* host_start,
+                 const uint64_t* d_key, const int32_t* d_start, uint32_t n, bool emits);
+// probe_staged.cu: samples up to 1024 adjacent row pairs of a device tile: {pairs with equal key and non-decreasing
+// start, pairs looked at} (synchronises the stream: device entry points only)
+int sample_order_device(sq_stream* s, const uint64_t* d_key, const int32_t* d_start, uint32_t n, uint32_t out2[2]);
+void staged_feedback(sq_stream* policy, uint32_t n_rows, uint64_t global_ctas, uint64_t staged_lines);
 int launch_packed_any(sq_stream* s, sq_stream* policy, bool staged, const sq_index* idx, const uint64_t* d_key,
                       const int32_t* d_start, const int32_t* d_end, uint32_t n, uint32_t* d_left, uint32_t* d_right,
                       uint64_t capacity);

@@ -149,7 +149,7 @@ SQ_API int32_t sq_stream_submit(sq_stream* s, const sq_index* idx, const uint64_
   sl->flags = flags;
   sl->idx = idx;
   auto* hs = static_cast<unsigned long long*>(sl->h_scalar.p);
-  hs[0] = hs[1] = hs[2] = 0;
+  hs[0] = hs[1] = hs[2] = hs[3] = 0;
 
   auto* dk = static_cast<uint64_t*>(sub->d_in.p);
   auto* ds = reinterpret_cast<int32_t*>(dk + n);
@@ -169,7 +169,7 @@ SQ_API int32_t sq_stream_submit(sq_stream* s, const sq_index* idx, const uint64_
     uint32_t* d_right = want_right ? static_cast<uint32_t*>(sub->d_right.p) : nullptr;
     sl->staged = false;
     if (use_packed(idx)) {
-      sl->staged = pick_staged(s, idx, key_hash, start, n_rows);
+      sl->staged = pick_staged(s, idx, key_hash, start, nullptr, nullptr, n_rows, d_left != nullptr);
       if ((rc = launch_packed_any(sub, s, sl->staged, idx, dk, ds, de, n_rows, d_left, d_right, dev_cap)))
         return fail(E, rc, "%s", sub->err.msg.c_str());
     } else {
@@ -225,7 +225,7 @@ SQ_API int32_t sq_stream_collect(sq_stream* s, uint64_t ticket, sq_tile_out* out
     if (ce != cudaSuccess) return bail(fail(E, SQ_ECUDA, "tile %llu failed on the device: %s", (unsigned long long)ticket, cudaGetErrorString(ce)));
     auto* hs = static_cast<unsigned long long*>(sl->h_scalar.p);
     n_pairs = hs[0];
-    if (sl->staged) staged_feedback(s, sl->n_rows, hs[2]);
+    if (sl->staged) staged_feedback(s, sl->n_rows, hs[2], hs[3]);
     const bool overflow = hs[1] != 0 || n_pairs > sl->dev_cap;
     uint64_t copied = sl->spec;
     if (!count_only && n_pairs) {

@@ -87,8 +87,8 @@ k_probe_staged(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* 
   __shared__ __align__(128) uint2 s_raw[kCapLines * 16];
   __shared__ __align__(16) int2 s_er[kCapLines * 16];  // decoded {end, running max of end} per slot (INT32_MIN end: no row)
   __shared__ uint8_t s_nrows[kCapLines];                // rows of each staged line
-  __shared__ uint32_t s_out[EMIT ? kOutWin : 1];        // output window: left_idx
-  __shared__ uint8_t s_own[EMIT ? kOutWin : 1];         // ... and the probe row (thread) that owns each pair
+  __shared__ __align__(16) uint32_t s_out[EMIT ? kOutWin + 4 : 1];  // output window: left_idx (shifted by the output's misalignment)
+  __shared__ __align__(16) uint8_t s_own[EMIT ? kOutWin + 4 : 1];   // ... and the probe row (thread) that owns each pair
   __shared__ __align__(8) unsigned long long s_mbar;
   __shared__ uint32_t s_min[kSWarps], s_max[kSWarps];
   __shared__ uint32_t s_stage_lo, s_nl, s_mode, s_bid;
@@ -136,6 +136,7 @@ k_probe_staged(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* 
       nl = mx - lo + 1u;
       if (nl <= kCapLines) {
         mode = 1;
+        atomicAdd(result + 3, (unsigned long long)nl);  // staged lines, summed: the host learns how dense the tiles are
         const uint32_t bytes = nl * 128u;
         const uint4* src = iv.lines + size_t(lo) * 8;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
@@ -187,27 +188,39 @@ k_probe_staged(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* 
 
   // ---- phase 4: my row's hits ----------------------------------------------------------------------------------
   uint32_t cnt = 0;
+  uint32_t mask = 0;            // bit k <=> staged slot j_hi - k is a hit (the first 32 scanned slots)
   int j_hi = 0, j_stop = 0;     // staged slots (j_stop, j_hi] were scanned
   bool cont = false;            // the walk continues in global memory ...
   uint32_t g_line = 0;          // ... from this line
   auto nothing = [](uint32_t) {};
   if (sl.act) {
     if (mode == 1) {
-      const uint32_t L = sl.line - stage_lo;
-      const int nr = int(s_nrows[L]);
-      const long long d = (long long)qe - (long long)int32_t(s_raw[L * 16].x);
-      const int target = d < 0 ? -1 : (d > 65535 ? 65535 : int(d));
-      int r = 0;  // rows of line L with start <= qe (their 16-bit start offsets ascend)
+      uint32_t L = sl.line - stage_lo;
+      const uint32_t Lmin = sl.first > stage_lo ? sl.first - stage_lo : 0u;
+      int r;  // rows of line L with start <= qe (their 16-bit start offsets ascend)
+      for (;;) {
+        const int nr = int(s_nrows[L]);
+        const long long d = (long long)qe - (long long)int32_t(s_raw[L * 16].x);
+        const int target = d < 0 ? -1 : (d > 65535 ? 65535 : int(d));
+        r = 0;
 #pragma unroll
-      for (int st = 8; st > 0; st >>= 1)
-        if (r + st <= nr && int(s_raw[L * 16 + r + st].x & 0xFFFFu) <= target) r += st;
+        for (int st = 8; st > 0; st >>= 1)
+          if (r + st <= nr && int(s_raw[L * 16 + r + st].x & 0xFFFFu) <= target) r += st;
+        // the directory names the line of the last row of the probe's BIN; when the bin's tail spans whole (short)
+        // lines past qe, the last start <= qe lives further down: every row below the scan's entry point must satisfy
+        // start <= qe, so step down until a line has such a row
+        if (r > 0 || L <= Lmin) break;
+        --L;
+      }
       int j = int(L * 16) + r;
-      const int jmin = sl.first > stage_lo ? int((sl.first - stage_lo) * 16u) : 0;
+      const int jmin = int(Lmin * 16u);
       j_hi = j;
+      uint32_t bit = 1u;  // shifts out after 32 slots: deeper hits are found again by the emit's rescan
       while (j >= jmin) {
         const int2 e = s_er[j];
         if (e.y < qs) break;  // no row at or below j reaches qs
-        cnt += (e.x >= qs) ? 1u : 0u;
+        if (e.x >= qs) { ++cnt; mask |= bit; }
+        bit <<= 1;
         --j;
       }
       j_stop = j;
@@ -256,23 +269,70 @@ k_probe_staged(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* 
   uint32_t* __restrict__ rout = WRITE_RIGHT ? right_out + base : nullptr;
   const uint32_t tile_first = tile * kSB;
   const uint32_t T = uint32_t(cta_tot);
+  // The window is laid out with the output's own misalignment (slot = position + a, a = output index mod 4), so its
+  // body leaves as 16-byte stores: 2 instructions per 4 pairs instead of 8.
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(left_out) | (WRITE_RIGHT ? reinterpret_cast<uintptr_t>(right_out) : 0)) & 15u) == 0;
   for (uint32_t w0 = 0; w0 < T; w0 += kOutWin) {
+    const uint32_t a = vec_ok ? uint32_t((base + w0) & 3ull) : 0u;
     if (cnt && my_off < w0 + kOutWin && my_off + cnt > w0) {
-      uint32_t k = my_off - w0;  // window slot of my next pair (wraps below zero for pairs of earlier windows)
-      auto push = [&](uint32_t id) {
-        if (k < kOutWin) { s_out[k] = id; s_own[k] = uint8_t(tid); }
-        ++k;
-      };
-      if (mode == 1)
-        for (int j = j_hi; j > j_stop; --j)
-          if (s_er[j].x >= qs) push(s_raw[j].y);
-      if (cont) walk_global(iv, g_line, sl.first, qs, qe, push);
+      uint32_t k = my_off - w0;  // window position of my next pair (wraps below zero for pairs of earlier windows)
+      if (mode == 1) {
+        if (my_off >= w0 && k + cnt <= kOutWin && j_hi - j_stop <= 32 && !cont) {
+          // the common case: every hit is in the mask and in this window
+          uint32_t mk = mask;
+          uint32_t o = a + k;
+          while (mk) {
+            const int b = __ffs(int(mk)) - 1;
+            mk &= mk - 1u;
+            s_out[o] = s_raw[j_hi - b].y;
+            s_own[o] = uint8_t(tid);
+            ++o;
+          }
+        } else {
+          for (int j = j_hi; j > j_stop; --j)
+            if (s_er[j].x >= qs) {
+              if (k < kOutWin) { s_out[a + k] = s_raw[j].y; s_own[a + k] = uint8_t(tid); }
+              ++k;
+            }
+        }
+      }
+      if (cont) {
+        auto push = [&](uint32_t id) {
+          if (k < kOutWin) { s_out[a + k] = id; s_own[a + k] = uint8_t(tid); }
+          ++k;
+        };
+        walk_global(iv, g_line, sl.first, qs, qe, push);
+      }
     }
     __syncthreads();
     const uint32_t m = min(kOutWin, T - w0);
-    for (uint32_t t = tid; t < m; t += kSB) {
-      lout[w0 + t] = s_out[t];
-      if (WRITE_RIGHT) rout[w0 + t] = tile_first + s_own[t];
+    if (vec_ok) {
+      // window slots [a, a + m) <-> output elements G0 + slot, G0 = (base + w0) & ~3 (16-byte aligned)
+      uint32_t* __restrict__ lg = left_out + ((base + w0) & ~3ull);
+      uint32_t* __restrict__ rg = WRITE_RIGHT ? right_out + ((base + w0) & ~3ull) : nullptr;
+      const uint32_t lo4 = (a + 3u) >> 2, hi4 = (a + m) >> 2;  // whole 4-slot groups
+      for (uint32_t v = lo4 + tid; v < hi4; v += kSB) {
+        reinterpret_cast<uint4*>(lg)[v] = reinterpret_cast<const uint4*>(s_out)[v];
+        if (WRITE_RIGHT) {
+          const uchar4 o = reinterpret_cast<const uchar4*>(s_own)[v];
+          reinterpret_cast<uint4*>(rg)[v] = make_uint4(tile_first + o.x, tile_first + o.y, tile_first + o.z, tile_first + o.w);
+        }
+      }
+      // ragged head and tail (at most 3 slots each)
+      if (tid < 8) {
+        const uint32_t head_end = min(lo4 * 4u, a + m), tail_begin = max(hi4 * 4u, head_end);
+        const uint32_t sidx = tid < 4 ? a + tid : tail_begin + (tid - 4);
+        const bool on = tid < 4 ? sidx < head_end : sidx < a + m;
+        if (on) {
+          lg[sidx] = s_out[sidx];
+          if (WRITE_RIGHT) rg[sidx] = tile_first + s_own[sidx];
+        }
+      }
+    } else {
+      for (uint32_t t = tid; t < m; t += kSB) {
+        lout[w0 + t] = s_out[t];
+        if (WRITE_RIGHT) rout[w0 + t] = tile_first + s_own[t];
+      }
     }
     __syncthreads();
   }
@@ -310,5 +370,37 @@ int launch_staged(sq_stream* s, const sq_index* idx, const uint64_t* d_key, cons
 }
 
 uint32_t staged_tile_rows() { return kSB; }
+
+// ---------------------------------------------------------------------------------------------
+// Is a device tile position-ordered?  m <= 1024 adjacent row pairs spread over the tile.
+__global__ void __launch_bounds__(1024) k_order_sample(const uint64_t* __restrict__ q_key, const int32_t* __restrict__ q_start,
+                                                       uint32_t m, uint32_t stride, uint32_t* __restrict__ out2) {
+  bool ok = false;
+  if (threadIdx.x < m) {
+    const size_t a = size_t(threadIdx.x) * stride;
+    ok = q_key[a] == q_key[a + 1] && q_start[a] <= q_start[a + 1];
+  }
+  const int c = __syncthreads_count(ok);
+  if (threadIdx.x == 0) { out2[0] = uint32_t(c); out2[1] = m; }
+}
+
+int sample_order_device(sq_stream* s, const uint64_t* d_key, const int32_t* d_start, uint32_t n, uint32_t out2[2]) {
+  ErrorSlot& E = s->err;
+  int rc;
+  if ((rc = ensure(E, s->d_scalar, 256, false))) return rc;
+  if ((rc = ensure(E, s->h_scalar, 256, true))) return rc;
+  auto* d = reinterpret_cast<uint32_t*>(static_cast<char*>(s->d_scalar.p) + 128);
+  auto* h = reinterpret_cast<uint32_t*>(static_cast<char*>(s->h_scalar.p) + 128);
+  const uint32_t m = n - 1 < 1024u ? n - 1 : 1024u;
+  const uint32_t stride = (n - 1) / m;
+  k_order_sample<<<1, 1024, 0, s->stream>>>(d_key, d_start, m, stride, d);
+  SQ_CUDA(E, cudaGetLastError());
+  SQ_CUDA(E, cudaMemcpyAsync(h, d, 8, cudaMemcpyDeviceToHost, s->stream));
+  SQ_CUDA(E, cudaStreamSynchronize(s->stream));
+  out2[0] = h[0];
+  out2[1] = h[1];
+  s->launches += 1;
+  return SQ_OK;
+}
 
 }  // namespace sq

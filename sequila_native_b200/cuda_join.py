@@ -145,17 +145,26 @@ class CudaIndex:
     uses_packed = property(lambda self: bool(self._lib.sq_index_uses_packed(self._h)))
 
 
-def drive_partitions(ctx: CudaContext, index: "CudaIndex", key_hash, start, end, n_partitions: int, n_tiles: int,
-                     flags: int = 0, checksum: bool = False) -> dict:
-    """sq_drive_partitions (include/sequila_driver.h): the partition loop of a host in native threads — one pass of the
-    whole probe side through `n_partitions` streams; the arrays should be pinned (CudaContext.pinned_*)."""
-    k, s, e = _np(key_hash, np.uint64), _np(start, np.int32), _np(end, np.int32)
-    st = N.SqDriveStats()
-    rc = ctx._lib.sq_drive_partitions(ctx._h, index._h, _ptr(k), _ptr(s), _ptr(e), k.shape[0], int(n_partitions), int(n_tiles),
-                                      int(flags), int(bool(checksum)), None, None, C.byref(st))
-    if rc != N.SQ_OK:
-        raise N.SequilaCudaError(rc, f"sq_drive_partitions failed with code {rc}")
-    return {f: getattr(st, f) for f, _ in N.SqDriveStats._fields_}
+class CudaDriver:
+    """sq_driver (include/sequila_driver.h): the partition loop of a host in native threads — `n_partitions` streams that
+    live as long as the driver; run() makes one pass over a probe side (arrays should be pinned, CudaContext.pinned_*)."""
+
+    def __init__(self, ctx: CudaContext, n_partitions: int):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        h = C.c_void_p()
+        _check(self._lib.sq_driver_create(ctx._h, int(n_partitions), C.byref(h)), ctx._err)
+        self._h = h
+        self.n_partitions = int(n_partitions)
+        self._fin = weakref.finalize(self, self._lib.sq_driver_free, h)
+
+    def run(self, index: "CudaIndex", key_hash, start, end, n_tiles: int, flags: int = 0, checksum: bool = False) -> dict:
+        k, s, e = _np(key_hash, np.uint64), _np(start, np.int32), _np(end, np.int32)
+        st = N.SqDriveStats()
+        rc = self._lib.sq_driver_run(self._h, index._h, _ptr(k), _ptr(s), _ptr(e), k.shape[0], int(n_tiles), int(flags),
+                                     int(bool(checksum)), None, None, C.byref(st))
+        _check(rc, lambda: self._lib.sq_driver_last_error(self._h))
+        return {f: getattr(st, f) for f, _ in N.SqDriveStats._fields_}
 
 
 class CudaStream:

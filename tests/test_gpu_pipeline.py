@@ -171,15 +171,16 @@ def test_options_surface(cuda_ctx):
 
 @pytest.mark.parametrize("parts,tiles", [(1, 1), (3, 10), (8, 64)])
 def test_native_partition_loop(cuda_ctx, oracle, parts, tiles):
-    """sq_drive_partitions (include/sequila_driver.h): native partition threads over submit / collect — pair total and
-    the xor of every left_idx that reached the host equal the oracle's"""
-    from sequila_native_b200.cuda_join import drive_partitions
+    """sq_driver_run (include/sequila_driver.h): native partition threads over submit / collect — pair total and
+    the xor of every left_idx that reached the host equal the oracle's, run after run on the same driver"""
+    from sequila_native_b200.cuda_join import CudaDriver
     b, p = sn.synth.cfg5(scale=0.004)
     idx = sn.CudaIndex.build(cuda_ctx, b["key"], b["start"], b["end"])
     ol, _, _ = oracle.join(b["key"], b["start"], b["end"], p["key"], p["start"], p["end"])
     cols = {k: cuda_ctx.pinned_copy(p[k]) for k in ("key", "start", "end")}
-    for flags in (0, N.TILE_COUNT_ONLY | N.TILE_NO_COUNTS):
-        r = drive_partitions(cuda_ctx, idx, cols["key"], cols["start"], cols["end"], parts, tiles, flags, checksum=True)
+    drv = CudaDriver(cuda_ctx, parts)
+    for flags in (0, N.TILE_COUNT_ONLY | N.TILE_NO_COUNTS, 0):
+        r = drv.run(idx, cols["key"], cols["start"], cols["end"], tiles, flags, checksum=True)
         assert r["n_pairs"] == len(ol) and r["n_tiles"] == tiles
         assert r["h2d_bytes"] == 16 * len(p["key"])
         if flags == 0:
