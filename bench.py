@@ -50,8 +50,9 @@ def parse_args():
     ap.add_argument("--shard-rows", type=int, default=SHARD_ROWS)
     ap.add_argument("--total-probe-rows", type=int, default=0, help="strong scaling / contig sharding: rows of the whole probe side (default 8 x shard rows)")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--e2e-partitions", type=int, default=0, help="host threads, one sq_stream each (0 = min(4, host cores / ranks))")
-    ap.add_argument("--e2e-tiles", type=int, default=64, help="probe sub-tiles per step (all partitions)")
+    ap.add_argument("--e2e-partitions", type=int, default=2, help="host threads, one sq_stream each")
+    ap.add_argument("--e2e-tiles", type=int, default=8, help="probe tiles per step (all partitions): 1.56M rows each for the 12.5M-row shard, "
+                    "what a host that coalesces 8192-row batches would submit (profiles/r02_e2e_sweep.json)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-locality", action="store_true", help="skip the position-sorted side measurement")
     ap.add_argument("--no-materialise", action="store_true", help="skip the six-column gather measurement")
@@ -662,7 +663,7 @@ def main():
                              "build_ms": build_best, "index_bytes": index_bytes, "oracle_check": check, **winfo}, device)
 
     # ---- end to end through the host C ABI: pinned host inputs -> H2D -> kernels -> D2H pairs, asynchronous tiles
-    T = args.e2e_partitions or max(1, min(4, len(near) // max(1, world if near == set(all_cpus) else 1)))
+    T = max(1, args.e2e_partitions)
     e2e_rows = min(n_probe, args.shard_rows)  # one launch worth of this rank's rows
     probe_h = {"key": ctx.pinned_copy(probe["key"][:e2e_rows].cpu().numpy().view(np.uint64)),
                "start": ctx.pinned_copy(probe["start"][:e2e_rows].cpu().numpy()),

@@ -63,6 +63,8 @@ int32_t sq_device_count(void);
  *   cuda_l2_persist_mb        integer               L2 set-aside for the probe directory (device-wide limit; default 0)
  *   cuda_scan_dict_capacity   power of two          text scan: initial key-dictionary capacity
  *   cuda_exec_trace           0 | 1                 exec node: per-phase wall times on stderr
+ *   cuda_pipeline_depth       2..8                  sq_stream_submit: tiles in flight per stream (default 3)
+ *   cuda_coalesce_rows        1..2^27               exec node: probe rows that make one tile (default 1048576)
  * Unknown keys and invalid values return SQ_EINVAL with a message; values may be changed between calls. */
 int32_t sq_ctx_set_option(sq_ctx* ctx, const char* key, const char* value);
 int32_t sq_ctx_get_option(sq_ctx* ctx, const char* key, char* value_out, size_t capacity);

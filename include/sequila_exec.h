@@ -93,8 +93,17 @@ int32_t sq_exec_probe(sq_exec* e, int32_t partition, const struct ArrowArray* ba
  * forms a batch of its own).  `batch` must stay valid until sq_exec_probe_next reported *has_more_out = 0. */
 int32_t sq_exec_probe_begin(sq_exec* e, int32_t partition, const struct ArrowArray* batch);
 int32_t sq_exec_probe_next(sq_exec* e, int32_t partition, struct ArrowArray* out, int32_t* has_more_out);
+/* Probe-batch coalescing.  The reference joins every probe batch on its own (<= 8192 rows by default, IJ:1192-1233); a GPU
+ * launch chain and a PCIe round trip per 8192 rows are bound by their latencies, so batches are pushed (ownership moves,
+ * like sq_exec_push_build) and leave as ONE tile once `cuda_coalesce_rows` rows (sq_exec_set_option, default 1048576) are
+ * waiting: *ready_out = 1 then.  sq_exec_probe_pop joins the waiting batches if they reached the target (or if `flush`
+ * != 0: end of the probe stream) and fills *out with ONE output batch for all of them, rows in probe order; *has_out = 0
+ * when nothing was due. */
+int32_t sq_exec_probe_push(sq_exec* e, int32_t partition, struct ArrowArray* batch, int32_t* ready_out);
+int32_t sq_exec_probe_pop(sq_exec* e, int32_t partition, int32_t flush, struct ArrowArray* out, int32_t* has_out);
 /* [0] build_input_batches [1] build_input_rows [2] build_mem_used [3] input_batches [4] input_rows
- * [5] output_batches [6] output_rows [7] build_time_ns [8] join_time_ns [9] index_bytes [10] keys */
+ * [5] output_batches [6] output_rows [7] build_time_ns [8] join_time_ns [9] index_bytes [10] keys
+ * [11] coalesced probe tiles joined */
 int32_t sq_exec_metrics(const sq_exec* e, uint64_t out[16]);
 const char* sq_exec_last_error(const sq_exec* e);
 /* `SET sequila.cuda_<name> TO <value>` for this node's context (keys of sq_ctx_set_option, sequila_cuda.h);

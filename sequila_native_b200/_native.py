@@ -146,6 +146,8 @@ EXEC_SIGNATURES = {
     "sq_exec_finish_build": (C.c_int32, [vp]),
     "sq_exec_output_schema": (C.c_int32, [vp, vp]),
     "sq_exec_probe": (C.c_int32, [vp, C.c_int32, vp, vp]),
+    "sq_exec_probe_push": (C.c_int32, [vp, C.c_int32, vp, i32p]),
+    "sq_exec_probe_pop": (C.c_int32, [vp, C.c_int32, C.c_int32, vp, i32p]),
     "sq_exec_probe_begin": (C.c_int32, [vp, C.c_int32, vp]),
     "sq_exec_probe_next": (C.c_int32, [vp, C.c_int32, vp, i32p]),
     "sq_exec_metrics": (C.c_int32, [vp, u64p]),

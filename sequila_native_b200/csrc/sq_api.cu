@@ -140,6 +140,7 @@ const OptDesc kOpts[] = {
     {"cuda_scan_dict_capacity", &sq_options::scan_dict_capacity, 4, 1 << 30, nullptr},
     {"cuda_exec_trace", &sq_options::exec_trace, 0, 1, nullptr},
     {"cuda_pipeline_depth", &sq_options::pipeline_depth, 2, 8, nullptr},
+    {"cuda_coalesce_rows", &sq_options::coalesce_rows, 1, 1 << 27, nullptr},
 };
 const char* strip_prefix(const char* key) { return strncmp(key, "sequila.", 8) == 0 ? key + 8 : key; }
 }  // namespace

@@ -15,6 +15,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "sequila_cuda.h"
@@ -135,6 +136,12 @@ struct PartState {
   size_t next = 0;
 };
 
+// probe batches of a partition waiting to be joined as ONE tile (sq_exec_probe_push / _pop)
+struct Pending {
+  std::vector<ArrowArray> batches;  // owned (moved in)
+  uint64_t rows = 0;
+};
+
 struct sq_exec {
   sq_exec_config cfg{};
   std::vector<int32_t> on_left, on_right, projection;
@@ -147,6 +154,7 @@ struct sq_exec {
   std::mutex mu;
   std::map<int32_t, sq_stream*> streams;
   std::map<int32_t, PartState> parts;
+  std::map<int32_t, Pending> pending;
   std::string err;
   uint64_t m[16] = {};
   bool built = false;
@@ -263,7 +271,24 @@ inline uint64_t dict_index_limit(const std::string& format) {
   }
 }
 
-// 64-bit hash of the `on` columns of every row (IJ:1037 / IJ:1211 call create_hashes here)
+// rows [lo, hi) of a range, on up to four host threads when the range is large (key hashing of a coalesced probe
+// tile: 4-5 ms per 1M Utf8 rows on one thread was most of the exec node's time per tile)
+template <typename F>
+void parallel_rows(int64_t n, F&& fn) {
+  const int64_t kMin = 1 << 17;
+  int T = int(n / kMin);
+  if (T > 4) T = 4;
+  if (T <= 1) { fn(int64_t(0), n); return; }
+  std::vector<std::thread> pool;
+  for (int t = 1; t < T; ++t) pool.emplace_back([&, t] { fn(n * t / T, n * (t + 1) / T); });
+  fn(int64_t(0), n / T);
+  for (auto& th : pool) th.join();
+}
+
+// 64-bit hash of the `on` columns of every row (IJ:1037 / IJ:1211 call create_hashes here).  A NULL key value
+// contributes nothing to its row's hash, as in create_hashes (which skips null slots): rows whose key is NULL in
+// every `on` column therefore share the seed's hash and only meet each other — never the rows whose value slot
+// happens to hold the same bytes.
 int hash_keys(sq_exec* e, const Side& side, const std::vector<int32_t>& on, const ArrowArray* batch,
               std::vector<uint64_t>* out) {
   const int64_t n = batch->length;
@@ -271,6 +296,17 @@ int hash_keys(sq_exec* e, const Side& side, const std::vector<int32_t>& on, cons
   for (int32_t col : on) {
     const ColType& t = side.cols[size_t(col)];
     const ColView v = view_of(batch, col);
+    const bool has_nulls = v.null_count != 0 && v.validity != nullptr;
+    std::vector<uint64_t> before;
+    if (has_nulls) before = *out;  // null slots get their previous value back below
+    struct Restore {
+      const ColView& v; const std::vector<uint64_t>& before; std::vector<uint64_t>* out; bool on;
+      ~Restore() {
+        if (!on) return;
+        for (int64_t i = 0; i < v.length; ++i)
+          if (!bit_at(v.validity, v.offset + i)) (*out)[size_t(i)] = before[size_t(i)];
+      }
+    } restore{v, before, out, has_nulls};
     if (t.dict) {
       // dictionary-encoded key: hash every dictionary value once, rows look their value's hash up — the same
       // hash a plain Utf8 column of the same strings gets, so a dictionary side and a Utf8 side of one join agree
@@ -278,24 +314,29 @@ int hash_keys(sq_exec* e, const Side& side, const std::vector<int32_t>& on, cons
       dict_strings(batch->children[col]->dictionary, t.dict_large, &strs);
       std::vector<uint64_t> eh(strs.size());
       for (size_t k = 0; k < strs.size(); ++k) eh[k] = string_hash(strs[k].first, strs[k].second);
-      for (int64_t i = 0; i < n; ++i) {
-        const uint32_t ix = dict_index(v.values, v.offset + i, t.width);
-        (*out)[size_t(i)] = sqkey::fold((*out)[size_t(i)], ix < eh.size() ? eh[ix] : 0);
-      }
+      parallel_rows(n, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+          const uint32_t ix = dict_index(v.values, v.offset + i, t.width);
+          (*out)[size_t(i)] = sqkey::fold((*out)[size_t(i)], ix < eh.size() ? eh[ix] : 0);
+        }
+      });
     } else if (t.kind == Kind::Fixed) {
       if (t.width != 1 && t.width != 2 && t.width != 4 && t.width != 8)
         return e->fail(SQ_EINVAL, "key column '%s' has unsupported type '%s'", t.name.c_str(), t.format.c_str());
-      for (int64_t i = 0; i < n; ++i) {
-        uint64_t raw = 0;
-        memcpy(&raw, v.values + (v.offset + i) * t.width, t.width);
-        (*out)[size_t(i)] = sqkey::fold((*out)[size_t(i)], sqkey::of_fixed(raw));
-      }
+      parallel_rows(n, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+          uint64_t raw = 0;
+          memcpy(&raw, v.values + (v.offset + i) * t.width, t.width);
+          (*out)[size_t(i)] = sqkey::fold((*out)[size_t(i)], sqkey::of_fixed(raw));
+        }
+      });
     } else {
       // strings of up to 8 bytes (contig names) hash from one masked 8-byte load; longer ones byte by byte
       const int64_t data_end = n == 0 ? 0
                                : (t.kind == Kind::Utf8 ? int64_t((reinterpret_cast<const int32_t*>(v.values) + v.offset)[n])
                                                        : (reinterpret_cast<const int64_t*>(v.values) + v.offset)[n]);
-      for (int64_t i = 0; i < n; ++i) {
+      parallel_rows(n, [&](int64_t lo_, int64_t hi_) {
+      for (int64_t i = lo_; i < hi_; ++i) {
         int64_t a, b;
         if (t.kind == Kind::Utf8) {
           const int32_t* off = reinterpret_cast<const int32_t*>(v.values) + v.offset;
@@ -321,6 +362,7 @@ int hash_keys(sq_exec* e, const Side& side, const std::vector<int32_t>& on, cons
         }
         (*out)[size_t(i)] = sqkey::fold((*out)[size_t(i)], h);
       }
+      });
     }
   }
   return SQ_OK;
@@ -333,6 +375,14 @@ int eval_i32(sq_exec* e, sq_stream* st, const Side& side, int32_t col, bool minu
   const ColView v = view_of(batch, col);
   const int64_t n = batch->length;
   out->resize(size_t(n));
+  if (v.null_count != 0 && v.validity) {
+    // the reference reads `.value(i)` of the cast column without looking at validity (IJ:1039-1048), i.e. whatever
+    // bytes sit in a null slot; nothing defined can be reproduced, so a NULL coordinate is an error here
+    for (int64_t i = 0; i < n; ++i)
+      if (!bit_at(v.validity, v.offset + i))
+        return e->fail(SQ_EINVAL, "interval column '%s' holds NULL at row %lld: the interval join needs non-null start / end values",
+                       t.name.c_str(), (long long)i);
+  }
   if (t.format == "i") {
     const int32_t* p = reinterpret_cast<const int32_t*>(v.values) + v.offset;
     if (!minus_one) { out->assign(p, p + n); return SQ_OK; }
@@ -914,6 +964,217 @@ SQ_API int32_t sq_exec_probe_next(sq_exec* e, int32_t partition, ArrowArray* out
   return SQ_OK;
 }
 
+// ---- probe-batch coalescing ---------------------------------------------------------------------------------
+namespace {
+
+// One struct array holding the rows of `batches` back to back (what concat_batches does for the build side, IJ:685):
+// fixed-width values and Utf8 offsets / bytes are copied, validity bitmaps are rebuilt, dictionary columns get ONE
+// dictionary (values in order of first occurrence over the batches) with renumbered indices.
+int concat_batches(sq_exec* e, const Side& side, const std::vector<ArrowArray>& batches, ArrowArray* out) {
+  uint64_t n = 0;
+  for (const ArrowArray& b : batches) n += uint64_t(b.length);
+  auto* own = new Owned();
+  own->ctx = e->ctx;
+  out->release = release_array;
+  out->private_data = own;
+  out->dictionary = nullptr;
+  struct Unwind {
+    ArrowArray* a; bool armed;
+    ~Unwind() { if (armed) release_array(a); }
+  } unwind{out, true};
+  for (size_t c = 0; c < side.cols.size(); ++c) {
+    const ColType& t = side.cols[c];
+    auto* child = new ArrowArray();
+    auto* co = new Owned();
+    co->ctx = e->ctx;
+    child->length = int64_t(n);
+    child->offset = 0;
+    child->null_count = 0;
+    child->n_children = 0;
+    child->children = nullptr;
+    child->dictionary = nullptr;
+    child->release = release_array;
+    child->private_data = co;
+    own->children.push_back(child);
+    if (t.width == 0 && t.kind == Kind::Fixed) {  // a type this node never touches: an all-null placeholder of the right length
+      co->buffers = {nullptr, nullptr};
+      child->null_count = int64_t(n);
+      child->n_buffers = 2;
+      child->buffers = co->buffers.data();
+      continue;
+    }
+    uint8_t* validity = nullptr;
+    uint64_t nulls = 0;
+    auto note_nulls = [&](const ColView& v, uint64_t r0) {
+      if (v.null_count == 0 || !v.validity) return;
+      if (!validity) {
+        validity = static_cast<uint8_t*>(malloc((n + 7) / 8 + 1));
+        memset(validity, 0xFF, (n + 7) / 8 + 1);
+        co->heap.push_back(validity);
+      }
+      for (int64_t i = 0; i < v.length; ++i)
+        if (!bit_at(v.validity, v.offset + i)) { validity[(r0 + uint64_t(i)) >> 3] &= uint8_t(~(1u << ((r0 + uint64_t(i)) & 7))); ++nulls; }
+    };
+    if (t.kind == Kind::Fixed) {
+      auto* vals = static_cast<uint8_t*>(malloc(size_t(n) * t.width + 8));
+      co->heap.push_back(vals);
+      uint64_t r = 0;
+      if (t.dict) {
+        std::vector<std::string> gdict;
+        std::map<std::string, uint32_t> gmap;
+        for (const ArrowArray& b : batches) {
+          const ColView v = view_of(&b, int32_t(c));
+          std::vector<StrRef> strs;
+          dict_strings(b.children[c]->dictionary, t.dict_large, &strs);
+          std::vector<uint32_t> remap(strs.size());
+          for (size_t k = 0; k < strs.size(); ++k) {
+            std::string sv(reinterpret_cast<const char*>(strs[k].first), size_t(strs[k].second));
+            auto it = gmap.find(sv);
+            if (it == gmap.end()) { it = gmap.emplace(sv, uint32_t(gdict.size())).first; gdict.push_back(sv); }
+            remap[k] = it->second;
+          }
+          note_nulls(v, r);
+          for (int64_t i = 0; i < v.length; ++i, ++r) {
+            const uint32_t ix = dict_index(v.values, v.offset + i, t.width);
+            const uint32_t nx = ix < remap.size() ? remap[ix] : 0u;
+            memcpy(vals + r * t.width, &nx, t.width);
+          }
+        }
+        if (!gdict.empty() && gdict.size() - 1 > dict_index_limit(t.format))
+          return e->fail(SQ_EINVAL, "column '%s': %zu distinct values over the coalesced probe batches do not fit index type '%s'",
+                         t.name.c_str(), gdict.size(), t.format.c_str());
+        std::vector<StrRef> refs;
+        for (const std::string& sv : gdict) refs.emplace_back(reinterpret_cast<const uint8_t*>(sv.data()), int64_t(sv.size()));
+        child->dictionary = make_dictionary(refs, t.dict_large);
+      } else {
+        for (const ArrowArray& b : batches) {
+          const ColView v = view_of(&b, int32_t(c));
+          note_nulls(v, r);
+          if (v.length) memcpy(vals + r * t.width, v.values + v.offset * t.width, size_t(v.length) * t.width);
+          r += uint64_t(v.length);
+        }
+      }
+      co->buffers = {validity, vals};
+    } else {
+      const bool large = t.kind == Kind::LargeUtf8;
+      uint64_t total = 0;
+      for (const ArrowArray& b : batches) {
+        const ColView v = view_of(&b, int32_t(c));
+        if (!v.length) continue;
+        if (large) { const int64_t* o = reinterpret_cast<const int64_t*>(v.values) + v.offset; total += uint64_t(o[v.length] - o[0]); }
+        else { const int32_t* o = reinterpret_cast<const int32_t*>(v.values) + v.offset; total += uint64_t(o[v.length] - o[0]); }
+      }
+      if (!large && total > 0x7FFFFFFFull)
+        return e->fail(SQ_ECAPACITY, "column '%s': the coalesced probe batches hold %llu string bytes; Utf8 offsets are 32-bit",
+                       t.name.c_str(), (unsigned long long)total);
+      void* off = malloc((size_t(n) + 1) * (large ? 8 : 4));
+      auto* data = static_cast<uint8_t*>(malloc(total ? total : 1));
+      co->heap.push_back(off);
+      co->heap.push_back(data);
+      uint64_t r = 0, at = 0;
+      for (const ArrowArray& b : batches) {
+        const ColView v = view_of(&b, int32_t(c));
+        note_nulls(v, r);
+        for (int64_t i = 0; i < v.length; ++i, ++r) {
+          int64_t a, z;
+          if (large) { const int64_t* o = reinterpret_cast<const int64_t*>(v.values) + v.offset; a = o[i]; z = o[i + 1]; }
+          else { const int32_t* o = reinterpret_cast<const int32_t*>(v.values) + v.offset; a = o[i]; z = o[i + 1]; }
+          if (large) static_cast<int64_t*>(off)[r] = int64_t(at); else static_cast<int32_t*>(off)[r] = int32_t(at);
+          if (z > a) memcpy(data + at, v.data + a, size_t(z - a));
+          at += uint64_t(z - a);
+        }
+      }
+      if (large) static_cast<int64_t*>(off)[n] = int64_t(at); else static_cast<int32_t*>(off)[n] = int32_t(at);
+      co->buffers = {validity, off, data};
+    }
+    child->null_count = int64_t(nulls);
+    child->n_buffers = int64_t(co->buffers.size());
+    child->buffers = co->buffers.data();
+  }
+  own->child_ptrs = own->children;
+  own->buffers = {nullptr};
+  out->length = int64_t(n);
+  out->null_count = 0;
+  out->offset = 0;
+  out->n_buffers = 1;
+  out->buffers = own->buffers.data();
+  out->n_children = int64_t(own->children.size());
+  out->children = own->child_ptrs.data();
+  unwind.armed = false;
+  return SQ_OK;
+}
+
+uint64_t coalesce_target(sq_exec* e) {
+  char v[32] = {0};
+  if (sq_ctx_get_option(e->ctx, "cuda_coalesce_rows", v, sizeof v) != SQ_OK) return 1u << 20;
+  const long long x = atoll(v);
+  return x > 0 ? uint64_t(x) : (1u << 20);
+}
+
+}  // namespace
+
+// The reference's probe child yields batches of at most `batch_size` rows (8192 by default, IJ:1192-1233) and joins each on
+// its own.  One GPU launch chain + one PCIe round trip per 8192 rows is bound by their latencies (measured: 23 M probe
+// rows/s), so the node coalesces: pushed batches wait until `cuda_coalesce_rows` rows (default 1M) are there, then leave as
+// ONE tile and ONE output batch (the order of rows is that of the probe batches: maintains_input_order holds).
+SQ_API int32_t sq_exec_probe_push(sq_exec* e, int32_t partition, ArrowArray* batch, int32_t* ready_out) {
+  if (!e || !batch || !ready_out) return SQ_EINVAL;
+  if (!e->built) return e->fail(SQ_ESTATE, "Expected build side in ready state");  // IJ:1425
+  if (batch->n_children != int64_t(e->right.cols.size())) return e->fail(SQ_EINVAL, "probe batch has %lld columns, schema has %zu",
+                                                                          (long long)batch->n_children, e->right.cols.size());
+  const uint64_t target = coalesce_target(e);
+  std::lock_guard<std::mutex> g(e->mu);
+  Pending& p = e->pending[partition];
+  p.batches.push_back(*batch);  // move
+  p.rows += uint64_t(batch->length);
+  batch->release = nullptr;
+  e->m[3] += 1;
+  e->m[4] += uint64_t(p.batches.back().length);
+  *ready_out = p.rows >= target ? 1 : 0;
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_exec_probe_pop(sq_exec* e, int32_t partition, int32_t flush, ArrowArray* out, int32_t* has_out) {
+  if (!e || !out || !has_out) return SQ_EINVAL;
+  *has_out = 0;
+  const uint64_t target = coalesce_target(e);
+  Pending take;
+  {
+    std::lock_guard<std::mutex> g(e->mu);
+    auto it = e->pending.find(partition);
+    if (it == e->pending.end() || it->second.batches.empty()) return SQ_OK;
+    if (it->second.rows < target && !flush) return SQ_OK;
+    take = std::move(it->second);
+    e->pending.erase(it);
+  }
+  struct Drop {
+    Pending& p;
+    ~Drop() { for (ArrowArray& b : p.batches) if (b.release) b.release(&b); }
+  } drop{take};
+  const auto t0 = Clock::now();
+  sq_stream* st = nullptr;
+  int rc = stream_for(e, partition, &st);
+  if (rc) return rc;
+  ArrowArray joined{};
+  const ArrowArray* tile = &take.batches[0];
+  if (take.batches.size() > 1) {
+    if ((rc = concat_batches(e, e->right, take.batches, &joined))) return rc;
+    tile = &joined;
+  }
+  uint64_t n_pairs = 0;
+  rc = probe_on_device(e, st, tile, &n_pairs);
+  if (rc == SQ_OK) rc = assemble_output(e, st, tile, n_pairs, out);
+  if (joined.release) joined.release(&joined);
+  if (rc) return rc;
+  *has_out = 1;
+  std::lock_guard<std::mutex> g(e->mu);
+  e->m[5] += 1;
+  e->m[6] += n_pairs;
+  e->m[8] += uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - t0).count());
+  e->m[11] += 1;  // tiles joined
+  return SQ_OK;
+}
+
 SQ_API int32_t sq_exec_metrics(const sq_exec* e, uint64_t out[16]) {
   if (!e || !out) return SQ_EINVAL;
   memcpy(out, e->m, sizeof e->m);
@@ -932,6 +1193,8 @@ SQ_API int32_t sq_exec_set_option(sq_exec* e, const char* key, const char* value
 
 SQ_API void sq_exec_free(sq_exec* e) {
   if (!e) return;
+  for (auto& kv : e->pending)
+    for (ArrowArray& b : kv.second.batches) if (b.release) b.release(&b);
   for (auto& kv : e->streams) sq_stream_free(kv.second);
   for (auto& b : e->build_batches) if (b.release) b.release(&b);
   if (e->index) sq_index_free(e->index);

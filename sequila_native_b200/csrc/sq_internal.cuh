@@ -120,6 +120,7 @@ struct sq_options {
   std::atomic<int> scan_dict_capacity{1 << 16};  // text scan: initial capacity of the per-call key dictionary
   std::atomic<int> exec_trace{0};           // exec node: per-phase wall-clock trace on stderr
   std::atomic<int> pipeline_depth{3};       // sq_stream_submit: tiles in flight per stream (2..8)
+  std::atomic<int> coalesce_rows{1 << 20};  // exec node: probe rows that make one tile (sq_exec_probe_push / _pop)
 };
 
 struct sq_ctx {

@@ -268,9 +268,40 @@ class IntervalJoinExec:
         return pa.RecordBatch._import_from_c(C.addressof(out), self.schema())
 
     def probe_batches(self, batches: Iterable, partition: int = 0) -> Iterator:
-        """The probe side of a partition as a stream of batches -> a stream of output batches (full mode)."""
+        """The probe side of a partition as a stream of batches -> a stream of output batches (full mode).  Batches are
+        coalesced into tiles of `sequila.cuda_coalesce_rows` rows (sq_exec_probe_push / _pop): the reference's child yields
+        <= 8192-row batches (IJ:1192-1233), far too small for a launch chain + PCIe round trip each; row order is kept."""
+        import pyarrow as pa
+        lib = self._lib
+
+        def pop(flush):
+            out = _ArrowArray()
+            has = C.c_int32(0)
+            if lib.sq_exec_probe_pop(self._exec, partition, int(flush), C.addressof(out), C.byref(has)) != N.SQ_OK:
+                raise ExecutionError(self._err())
+            return pa.RecordBatch._import_from_c(C.addressof(out), self.schema()) if has.value else None
         for b in batches:
-            yield self.probe_batch(b, partition)
+            arr = _ArrowArray()
+            b._export_to_c(C.addressof(arr))
+            ready = C.c_int32(0)
+            if lib.sq_exec_probe_push(self._exec, partition, C.addressof(arr), C.byref(ready)) != N.SQ_OK:
+                if arr.release:
+                    _RELEASE_ARRAY(arr.release)(C.addressof(arr))
+                raise ExecutionError(self._err())
+            if ready.value:
+                out = pop(False)
+                if out is not None:
+                    yield out
+        out = pop(True)
+        if out is not None:
+            yield out
+
+    def set_option(self, key: str, value) -> None:
+        """`SET sequila.cuda_<name> TO <value>` for this node (sq_exec_set_option)."""
+        if self._exec is None:
+            self._open()
+        if self._lib.sq_exec_set_option(self._exec, str(key).encode(), str(value).encode()) != N.SQ_OK:
+            raise ExecutionError(self._err())
 
     def probe_batch_low_memory(self, batch, partition: int = 0) -> Iterator:
         """process_probe_batch, low-memory mode (IJ:1433-1530): output batches of at most
@@ -292,9 +323,14 @@ class IntervalJoinExec:
             if arr.release:
                 _RELEASE_ARRAY(arr.release)(C.addressof(arr))
 
-    def execute(self, build_batches: Iterable, probe_batches: Iterable, partition: int = 0) -> Iterator:
-        """IJ:449-557: await the build side, then stream the probe side."""
+    def execute(self, build_batches: Iterable, probe_batches: Iterable, partition: int = 0, coalesce: bool = True) -> Iterator:
+        """IJ:449-557: await the build side, then stream the probe side.  Full mode coalesces the probe batches into tiles
+        of `sequila.cuda_coalesce_rows` rows (one output batch per tile); coalesce=False joins every probe batch on its
+        own, one output batch each, as the reference does (IJ:1580-1640)."""
         self.collect_build(build_batches)
+        if not self.low_memory and coalesce:
+            yield from self.probe_batches(probe_batches, partition)
+            return
         for b in probe_batches:
             if self.low_memory:
                 yield from self.probe_batch_low_memory(b, partition)

@@ -26,15 +26,18 @@ def cuda_config():
     return cfg
 
 
-def run_join(left, right, cond, equi=True, batch_rows=None, projection=None):
+def run_join(left, right, cond, equi=True, batch_rows=None, projection=None, coalesce=True):
     f = IV.parse_condition_sql(cond, "a", COLS, "b", COLS)
     on = [("contig", "contig")] if equi else []
     plan = optimize(HashJoinDesc(left.schema, right.schema, on, f, projection=projection), cuda_config())
     assert isinstance(plan, IntervalJoinExec)
     lb = [left] if batch_rows is None else [left.slice(i, batch_rows) for i in range(0, max(left.num_rows, 1), batch_rows)]
     rb = [right] if batch_rows is None else [right.slice(i, batch_rows) for i in range(0, max(right.num_rows, 1), batch_rows)]
-    out = list(plan.execute(lb, rb))
-    assert len(out) == len(rb)  # one output batch per probe batch (interval_join.rs:1580-1640)
+    out = list(plan.execute(lb, rb, coalesce=coalesce))
+    if coalesce:
+        assert 1 <= len(out) <= len(rb)  # probe batches leave as tiles of sequila.cuda_coalesce_rows rows
+    else:
+        assert len(out) == len(rb)  # one output batch per probe batch (interval_join.rs:1580-1640)
     return plan, out
 
 
@@ -73,7 +76,8 @@ def test_closed_and_strict_boundaries(golden):
     assert sort_rows(rows_of(out)) == sort_rows(golden["strict_rows"])
 
 
-def test_many_batches_keep_probe_order_and_match_oracle(oracle):
+@pytest.mark.parametrize("coalesce", [True, False])
+def test_many_batches_keep_probe_order_and_match_oracle(oracle, coalesce):
     rng = np.random.default_rng(11)
     nb, npq = 6000, 5000
     names = np.array(["chr1", "chr2", "chrX", "chrUn_gl000220"])
@@ -87,14 +91,16 @@ def test_many_batches_keep_probe_order_and_match_oracle(oracle):
     pc, ps, pe = side(npq)
     left = pa.record_batch([pa.array(names[bc]), pa.array(bs), pa.array(be)], names=COLS)
     right = pa.record_batch([pa.array(names[pc]), pa.array(ps), pa.array(pe)], names=COLS)
-    _, out = run_join(left, right, Q1, batch_rows=2000)
+    _, out = run_join(left, right, Q1, batch_rows=2000, coalesce=coalesce)
+    if coalesce:
+        assert len(out) == 1  # 5000 probe rows < sequila.cuda_coalesce_rows: one tile, one output batch
     ol, orr, _ = oracle.join(bc.astype(np.uint64), bs, be, pc.astype(np.uint64), ps, pe)
     want = sorted(zip(names[bc][ol].tolist(), bs[ol].tolist(), be[ol].tolist(), names[pc][orr].tolist(), ps[orr].tolist(), pe[orr].tolist()))
     got = [tuple(r) for r in rows_of(out)]
     assert sorted(got) == want
     # probe order preserved inside every output batch: maintains_input_order = [false, true]
     off = 0
-    for b, rb in zip(out, [right.slice(i, 2000) for i in range(0, npq, 2000)]):
+    for b, rb in zip(out, [right] if coalesce else [right.slice(i, 2000) for i in range(0, npq, 2000)]):
         key = list(zip(b.column(3).to_pylist(), b.column(4).to_pylist(), b.column(5).to_pylist()))
         src = list(zip(rb.column(0).to_pylist(), rb.column(1).to_pylist(), rb.column(2).to_pylist()))
         it = iter(src)
@@ -252,3 +258,71 @@ def test_dictionary_index_type_too_small_for_the_unified_build_dictionary():
     with pytest.raises(ExecutionError) as e:
         list(plan.execute(lb, [right]))
     assert "do not fit index type" in str(e.value)
+
+
+def test_coalesced_tiles_equal_per_batch_joins(oracle):
+    """sq_exec_probe_push / _pop: 8192-row probe batches (DataFusion's default batch size, interval_join.rs:1192-1233)
+    leave as tiles of `sequila.cuda_coalesce_rows` rows; the rows — Utf8, dictionary-encoded (a dictionary per batch) and
+    nullable payload columns included — equal those of joining every batch on its own, in the same probe order"""
+    rng = np.random.default_rng(21)
+    b, p = sn.synth.cfg5(scale=0.002)
+    names = np.array(sn.synth.CONTIG_NAMES)
+    left = pa.record_batch([pa.array(names[b["contig"]]), pa.array(b["start"]), pa.array(b["end"])], names=COLS)
+    n = len(p["key"])
+    tag_vals = rng.integers(0, 50, n)
+    tags = pa.array([None if v == 7 else f"t{v}" for v in tag_vals])
+    score = pa.array(np.where(rng.random(n) < 0.1, np.nan, rng.random(n)), mask=rng.random(n) < 0.05)
+    rcols = COLS + ["tag", "score"]
+    f = IV.parse_condition_sql(Q1, "a", COLS, "b", rcols)
+    rbatches = []
+    for i in range(0, n, 8192):
+        sl = slice(i, min(i + 8192, n))
+        tag_b = tags.slice(i, sl.stop - i).dictionary_encode()  # every batch brings its own dictionary
+        rbatches.append(pa.record_batch([pa.array(names[p["contig"][sl]]), pa.array(p["start"][sl]), pa.array(p["end"][sl]),
+                                         tag_b, score.slice(i, sl.stop - i)], names=rcols))
+
+    def run(coalesce, target=None):
+        plan = optimize(HashJoinDesc(left.schema, rbatches[0].schema, [("contig", "contig")], f), cuda_config())
+        if target:
+            plan.set_option("sequila.cuda_coalesce_rows", target)
+        out = list(plan.execute([left], rbatches, coalesce=coalesce))
+        m = plan.metrics()
+        plan.close()
+        return out, m
+    per_batch, m0 = run(False)
+    assert len(per_batch) == len(rbatches)
+    want = rows_of(per_batch)
+    canon_rows = lambda rows: sorted(map(repr, rows))
+    for target in (None, 20000, 50000, 1):
+        out, m = run(True, target)
+        if target == 1:
+            assert len(out) == len(rbatches)  # every pushed batch is due at once: the reference's one batch out per batch in
+        elif target is None:
+            assert len(out) == 1
+        else:
+            assert 1 < len(out) < len(rbatches)
+        got = rows_of(out)
+        assert len(got) == len(want) == m.output_rows
+        assert canon_rows(got) == canon_rows(want)
+        # probe order: the probe-side columns of the output are the same sequence in both modes
+        assert [r[3:6] for r in got] == [r[3:6] for r in want]
+        assert m.input_rows == n and m.input_batches == len(rbatches)
+
+
+def test_null_keys_and_null_coordinates():
+    """create_hashes skips NULL key slots (interval_join.rs:1037, 1211): a NULL contig never meets the rows whose value slot
+    holds the same bytes, only other NULL keys; a NULL start / end is an error here (the reference reads garbage there)"""
+    left = pa.record_batch([pa.array(["", "a", None, "a"]), pa.array([1, 10, 100, 1000], pa.int32()), pa.array([5, 20, 200, 2000], pa.int32())],
+                           names=COLS)
+    right = pa.record_batch([pa.array([None, "", "a"]), pa.array([0, 0, 0], pa.int32()), pa.array([5000, 5000, 5000], pa.int32())], names=COLS)
+    _, out = run_join(left, right, Q1)
+    rows = sorted(map(repr, rows_of(out)))
+    want = sorted(map(repr, [[None, 100, 200, None, 0, 5000], ["", 1, 5, "", 0, 5000], ["a", 10, 20, "a", 0, 5000], ["a", 1000, 2000, "a", 0, 5000]]))
+    assert rows == want
+    bad = pa.record_batch([pa.array(["a"]), pa.array([None], pa.int32()), pa.array([5], pa.int32())], names=COLS)
+    with pytest.raises(ExecutionError) as e:
+        run_join(left, bad, Q1)
+    assert "NULL" in str(e.value) and "pos_start" in str(e.value)
+    with pytest.raises(ExecutionError) as e:
+        run_join(bad, right, Q1)
+    assert "NULL" in str(e.value)
