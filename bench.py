@@ -458,7 +458,7 @@ def sub_config(sn, torch, ctx, name, device, hbm_peak, steps, flush):
     c_ms = timed_steps(torch, lambda: st.probe_count_device(idx, pd["key"], pd["start"], pd["end"]), steps, flush)
     return {"probe_rows": n_probe, "build_rows": len(b["key"]), "pairs": n_pairs, "ms_per_step": ms,
             "value": n_probe / (ms * 1e-3), "pairs_per_s": n_pairs / (ms * 1e-3), "unit": "probe intervals/s",
-            "kernels": "k_probe_packed" if idx.uses_packed else "k_probe_soa",
+            "kernels": "k_probe_packed" if idx.uses_packed else ("k_probe_rank" if idx.uses_rank else "k_probe_count+k_tile_scan+k_probe_write"),
             "roofline_frac": bts / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": bts,
             "count_only_ms": c_ms, "build_ms": idx.build_ms, "digest": {"pairs": dg[0], "sum": dg[1]}}
 
@@ -513,7 +513,8 @@ def source_sha(files):
 
 KERNEL_SOURCES = {"k_probe_packed": ["sq_probe_packed.cu", "sq_packed_common.cuh", "sq_probe_common.cuh"],
                   "k_probe_staged": ["sq_probe_staged.cu", "sq_packed_common.cuh", "sq_probe_common.cuh"],
-                  "k_probe_soa": ["sq_probe.cu", "sq_probe_common.cuh"]}
+                  "k_probe_rank": ["sq_probe_rank.cu", "sq_soa_common.cuh", "sq_probe_common.cuh"],
+                  "k_probe_soa": ["sq_probe.cu", "sq_soa_common.cuh", "sq_probe_common.cuh"]}
 
 
 def ncu_traffic(kernel):
@@ -808,7 +809,7 @@ def main():
         # B_probe of SURVEY.md §8(d) with u64 key hashes consumed on the device:
         # 16 B per probe row (key hash 8 + start 4 + end 4) + 12 B per emitted pair
         # (read the hit's build row id 4, write (left,right) 8).  One launch = one probe tile.
-        dom = "k_probe_packed" if idx.uses_packed else "k_probe_soa"
+        dom = "k_probe_packed" if idx.uses_packed else ("k_probe_rank" if idx.uses_rank else "k_probe_soa")
         rows0 = tiles.bounds[0][1] - tiles.bounds[0][0]
         n_launch = len(tiles.cols)
         b_dom = (16.0 * n_probe + 12.0 * n_pairs) / n_launch

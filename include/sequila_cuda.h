@@ -65,6 +65,7 @@ int32_t sq_device_count(void);
  *   cuda_exec_trace           0 | 1                 exec node: per-phase wall times on stderr
  *   cuda_pipeline_depth       2..8                  sq_stream_submit: tiles in flight per stream (default 3)
  *   cuda_coalesce_rows        1..2^27               exec node: probe rows that make one tile (default 1048576)
+ *   cuda_rank_count           on | off              build: rank structure over the ends (rank-difference count, one walk)
  * Unknown keys and invalid values return SQ_EINVAL with a message; values may be changed between calls. */
 int32_t sq_ctx_set_option(sq_ctx* ctx, const char* key, const char* value);
 int32_t sq_ctx_get_option(sq_ctx* ctx, const char* key, char* value_out, size_t capacity);
@@ -93,6 +94,10 @@ uint64_t sq_index_keys(const sq_index* idx);  /* distinct key hashes = number of
 /* which probe kernels serve this index: 1 = the fused kernel over packed lines (every width < 65536, index
  * far larger than L2 and shallow), 0 = count / scan / write over the SoA arrays */
 int32_t sq_index_uses_packed(const sq_index* idx);
+/* 1 = the index carries the rank structure over the ends (built when the SoA kernels serve it and every build row has
+ * start <= end): the probe is ONE kernel whose count is a rank difference and whose only candidate walk writes the
+ * pairs; 0 = count / scan / write, two walks */
+int32_t sq_index_uses_rank(const sq_index* idx);
 /* device time of the last build's kernels in ms (sort, scan, ...); 0 if unknown */
 float sq_index_build_ms(const sq_index* idx);
 void sq_index_free(sq_index* idx);

@@ -99,13 +99,30 @@ __global__ void __launch_bounds__(256) k_make_sort_keys(const uint64_t* __restri
                                                         const uint32_t* __restrict__ ht_ids,
                                                         uint32_t mask, uint32_t sentinel_id,
                                                         uint64_t* __restrict__ sort_key,
-                                                        uint64_t* __restrict__ sort_val) {
+                                                        uint64_t* __restrict__ sort_val,
+                                                        unsigned int* __restrict__ inverted) {
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  bool inv = false;
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const uint32_t id = ht_lookup(ht_keys, ht_ids, mask, sentinel_id, keys[i]);
     sort_key[i] = (uint64_t(id) << 32) | uint64_t(uint32_t(start[i]) ^ 0x80000000u);
     sort_val[i] = (uint64_t(uint32_t(end[i])) << 32) | uint64_t(uint32_t(i));
+    inv |= end[i] < start[i];
   }
+  if (inv) atomicOr(inverted, 1u);  // some build row has end < start: the rank-difference count does not apply
+}
+
+// (id, end) sort keys of the rows in (id, start) order, and back: the ends sorted inside each key segment
+__global__ void __launch_bounds__(256) k_end_keys(const uint64_t* __restrict__ sorted_key, const int32_t* __restrict__ s_end,
+                                                  uint64_t n, uint64_t* __restrict__ out) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride)
+    out[j] = (sorted_key[j] & 0xFFFFFFFF00000000ull) | uint64_t(uint32_t(s_end[j]) ^ 0x80000000u);
+}
+__global__ void __launch_bounds__(256) k_end_values(const uint64_t* __restrict__ sorted, uint64_t n, int32_t* __restrict__ s_send) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride)
+    s_send[j] = int32_t(uint32_t(sorted[j]) ^ 0x80000000u);
 }
 
 // After the sort: write start[], row[], end[] (unpacked from the sorted key / value words) and the
@@ -400,6 +417,7 @@ void free_index(sq_index* idx) {
   cudaFree(idx->d_meta); cudaFree(idx->d_dir); cudaFree(idx->d_ht_keys); cudaFree(idx->d_ht_ids);
   cudaFree(idx->d_lines);
   cudaFree(idx->d_dir_line);
+  cudaFree(idx->d_send); cudaFree(idx->d_emeta); cudaFree(idx->d_edir);
   for (auto& c : idx->columns) {
     if (c.owned) { cudaFree(c.d_values); cudaFree(c.d_offsets); }
     cudaFree(c.d_validity);
@@ -511,8 +529,9 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     SQ_CUDA(E, tmp.alloc(&d_v1, n * 8));
     SQ_CUDA(E, tmp.alloc(&d_seg_off, (size_t(n_keys) + 1) * 4));
     const int g = grid_for(n, 256, ctx->sm_count);
+    unsigned int* d_inverted = d_counter + 1;  // zeroed with the hash-table status above
     k_make_sort_keys<<<g, 256, 0, st>>>(d_key, d_start, d_end, n, idx->d_ht_keys, idx->d_ht_ids, cap - 1,
-                                        idx->sentinel_id, d_k0, d_v0);
+                                        idx->sentinel_id, d_k0, d_v0, d_inverted);
     SQ_CUDA(E, cudaGetLastError());
 
     int key_bits = 0;
@@ -607,6 +626,51 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
       idx->n_lines = line_total;
       idx->mean_back_lines = float(double(h_pstat[1]) / double(line_total));
       idx->bytes += line_total * 128 + dir_total * 8;
+    }
+
+    // 6. rank structure over the ends, for the indexes the SoA kernels serve (cache-resident, wide or deep ones — the
+    // packed-line kernel never reads it): the same rows' ends sorted inside each key segment plus a bin directory, so
+    // that a probe row's hit count is |{start <= qe}| - |{end < qs}| without touching a candidate (sq_probe_rank.cu).
+    // Needs start <= end on every build row.
+    unsigned int h_inverted = 0;
+    SQ_CUDA(E, cudaMemcpyAsync(&h_inverted, d_inverted, 4, cudaMemcpyDeviceToHost, st));
+    SQ_CUDA(E, cudaStreamSynchronize(st));
+    if (!h_inverted && !use_packed(idx) && ctx->opt.rank_count.load(std::memory_order_relaxed)) {
+      k_end_keys<<<g, 256, 0, st>>>(d_k1, idx->d_end, n, d_k0);
+      SQ_CUDA(E, cudaGetLastError());
+      size_t tb = 0;
+      SQ_CUDA(E, ::sq_cub::cub::DeviceRadixSort::SortKeys(nullptr, tb, d_k0, d_v0, n, 0, end_bit, st));
+      void* d_t2 = nullptr;
+      SQ_CUDA(E, tmp.alloc(&d_t2, tb));
+      SQ_CUDA(E, ::sq_cub::cub::DeviceRadixSort::SortKeys(d_t2, tb, d_k0, d_v0, n, 0, end_bit, st));
+      SQ_CUDA(E, cudaMallocAsync(&idx->d_send, n * 4, st));
+      k_end_values<<<g, 256, 0, st>>>(d_v0, n, idx->d_send);
+      SQ_CUDA(E, cudaGetLastError());
+      SQ_CUDA(E, cudaMallocAsync(&idx->d_emeta, (size_t(n_keys) + 1) * sizeof(SegMeta), st));
+      k_seg_meta<<<(n_keys + 255) / 256, 256, 0, st>>>(d_seg_off, idx->d_send, n_keys, idx->d_emeta, rows_per_bin);
+      SQ_CUDA(E, cudaGetLastError());
+      std::vector<SegMeta> h_em(size_t(n_keys) + 1);
+      SQ_CUDA(E, cudaMemcpyAsync(h_em.data(), idx->d_emeta, size_t(n_keys) * sizeof(SegMeta), cudaMemcpyDeviceToHost, st));
+      SQ_CUDA(E, cudaStreamSynchronize(st));
+      uint64_t edir_total = 0;
+      for (uint32_t k = 0; k < n_keys; ++k) {
+        h_em[k].dir_base = uint32_t(edir_total);
+        edir_total += uint64_t(h_em[k].nbins) + 1;
+      }
+      if (edir_total < 0xFFFFFFFFull) {
+        h_em[n_keys] = SegMeta{};
+        SQ_CUDA(E, cudaMemcpyAsync(idx->d_emeta, h_em.data(), (size_t(n_keys) + 1) * sizeof(SegMeta), cudaMemcpyHostToDevice, st));
+        SQ_CUDA(E, cudaMallocAsync(&idx->d_edir, edir_total * 4, st));
+        k_fill_dir<<<g, 256, 0, st>>>(d_v0, idx->d_send, n, idx->d_emeta, idx->d_edir);
+        SQ_CUDA(E, cudaGetLastError());
+        SQ_CUDA(E, cudaStreamSynchronize(st));  // h_em must outlive its async copy
+        idx->bytes += n * 4 + edir_total * 4 + (uint64_t(n_keys) + 1) * sizeof(SegMeta);
+      } else {
+        cudaFree(idx->d_send);
+        cudaFree(idx->d_emeta);
+        idx->d_send = nullptr;
+        idx->d_emeta = nullptr;
+      }
     }
   }
   SQ_CUDA(E, cudaEventRecord(e1, st));

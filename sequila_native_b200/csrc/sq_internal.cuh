@@ -69,6 +69,12 @@ struct IndexView {
   uint32_t n_rows;
   const uint4* __restrict__ lines;      // packed lines (nullptr when the index is not "narrow")
   const uint2* __restrict__ dir_line;   // directory entry -> {line holding the last row below it, that line's first start}
+  // rank structure over the ENDS (nullptr when not built): the same rows' ends sorted inside each key segment, with
+  // their own bin directory.  For rows with start <= end and a probe with qs <= qe + 1 the hit count is a rank
+  // difference, |{start <= qe}| - |{end < qs}|, no candidate is touched to count
+  const int32_t* __restrict__ send;
+  const SegMeta* __restrict__ emeta;    // min_start = smallest end of the segment; sb / se as in meta
+  const uint32_t* __restrict__ edir;
 };
 
 #ifdef __CUDACC__
@@ -120,6 +126,7 @@ struct sq_options {
   std::atomic<int> scan_dict_capacity{1 << 16};  // text scan: initial capacity of the per-call key dictionary
   std::atomic<int> exec_trace{0};           // exec node: per-phase wall-clock trace on stderr
   std::atomic<int> pipeline_depth{3};       // sq_stream_submit: tiles in flight per stream (2..8)
+  std::atomic<int> rank_count{1};           // build: rank structure over the ends for the indexes the SoA kernels serve
   std::atomic<int> coalesce_rows{1 << 20};  // exec node: probe rows that make one tile (sq_exec_probe_push / _pop)
 };
 
@@ -161,6 +168,9 @@ struct sq_index {
   uint64_t dir_bytes = 0;
   uint4* d_lines = nullptr;    // packed lines, or nullptr (wide / inverted intervals: SoA path only)
   uint2* d_dir_line = nullptr;
+  int32_t* d_send = nullptr;   // ends sorted inside each key segment (rank-difference count), or nullptr
+  sq::SegMeta* d_emeta = nullptr;
+  uint32_t* d_edir = nullptr;
   uint64_t n_lines = 0;
   float mean_back_lines = 0.f; // mean number of extra lines a probe landing on a line's last row walks back
   uint64_t* d_ht_keys = nullptr;
@@ -180,6 +190,9 @@ struct sq_index {
     v.n_keys = n_keys; v.n_rows = uint32_t(n_rows);
     v.lines = d_lines;
     v.dir_line = d_dir_line;
+    v.send = d_send;
+    v.emeta = d_emeta;
+    v.edir = d_edir;
     return v;
   }
 };
@@ -295,6 +308,12 @@ int launch_count(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const
 // K3: pairs from the saved state; sets result[1] instead of writing when n_pairs > capacity
 int launch_write(sq_stream* s, const sq_index* idx, const int32_t* d_start, uint32_t n, uint32_t* d_left,
                  uint32_t* d_right, uint64_t capacity);
+
+// probe_rank.cu: indexes with the rank structure over the ends (idx->d_send): ONE kernel — search, rank-difference count,
+// chained scan, candidate walk + write (count only when d_left == nullptr: no candidate is touched at all).
+// Same outputs as launch_count + launch_write: cnt per row in s->d_cnt, result[0] = n_pairs, result[1] = overflow.
+int launch_rank_join(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
+                     const int32_t* d_end, uint32_t n, uint32_t* d_left, uint32_t* d_right, uint64_t capacity);
 
 // one output row per probe row: an overlapping build row, else the nearest one, else kEmptyRow (NULL)
 int launch_nearest(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,

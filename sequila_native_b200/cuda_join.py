@@ -143,6 +143,7 @@ class CudaIndex:
     keys = property(lambda self: int(self._lib.sq_index_keys(self._h)))
     build_ms = property(lambda self: float(self._lib.sq_index_build_ms(self._h)))
     uses_packed = property(lambda self: bool(self._lib.sq_index_uses_packed(self._h)))
+    uses_rank = property(lambda self: bool(self._lib.sq_index_uses_rank(self._h)))
 
 
 class CudaDriver:
