@@ -130,7 +130,7 @@ struct OptDesc {
 const char* const kLayoutWords[] = {"auto", "packed", "soa", nullptr};
 const char* const kWireWords[] = {"rle", "copy", nullptr};
 const char* const kStagedWords[] = {"auto", "on", "off", nullptr};
-const char* const kOnOffWords[] = {"off", "on", nullptr};
+const char* const kOnOffWords[] = {"off", "on", "force", nullptr};
 const OptDesc kOpts[] = {
     {"cuda_probe_layout", &sq_options::probe_layout, 0, 2, kLayoutWords},
     {"cuda_probe_block", &sq_options::probe_block, 64, 256, nullptr},
@@ -142,7 +142,7 @@ const OptDesc kOpts[] = {
     {"cuda_exec_trace", &sq_options::exec_trace, 0, 1, nullptr},
     {"cuda_pipeline_depth", &sq_options::pipeline_depth, 2, 8, nullptr},
     {"cuda_coalesce_rows", &sq_options::coalesce_rows, 1, 1 << 27, nullptr},
-    {"cuda_rank_count", &sq_options::rank_count, 0, 1, kOnOffWords},
+    {"cuda_rank_count", &sq_options::rank_count, 0, 2, kOnOffWords},
 };
 const char* strip_prefix(const char* key) { return strncmp(key, "sequila.", 8) == 0 ? key + 8 : key; }
 }  // namespace
@@ -301,7 +301,7 @@ SQ_API uint64_t sq_index_bytes(const sq_index* idx) { return idx ? idx->bytes : 
 SQ_API uint64_t sq_index_rows(const sq_index* idx) { return idx ? idx->n_rows : 0; }
 SQ_API uint64_t sq_index_keys(const sq_index* idx) { return idx ? idx->n_keys : 0; }
 SQ_API int32_t sq_index_uses_packed(const sq_index* idx) { return idx && use_packed(idx) ? 1 : 0; }
-SQ_API int32_t sq_index_uses_rank(const sq_index* idx) { return idx && !use_packed(idx) && idx->d_send ? 1 : 0; }
+SQ_API int32_t sq_index_uses_rank(const sq_index* idx) { return idx && use_rank(idx) ? 1 : 0; }
 SQ_API float sq_index_build_ms(const sq_index* idx) { return idx ? idx->build_ms : 0.f; }
 SQ_API void sq_index_free(sq_index* idx) { free_index(idx); }
 
@@ -549,7 +549,7 @@ static int32_t join_device(sq_stream* s, const sq_index* idx, const uint64_t* dk
     // narrow index: ONE kernel searches, counts, scans and (when there is room) writes
     staged = pick_staged(s, idx, host_key, host_start, dk, ds, n, wrote);
     if ((rc = launch_packed_any(s, s, staged, idx, dk, ds, de, n, wrote ? d_left : nullptr, d_right, capacity))) return rc;
-  } else if (idx->d_send) {
+  } else if (use_rank(idx)) {
     // rank structure over the ends: ONE kernel — rank-difference count, chained scan, one walk that writes
     if ((rc = launch_rank_join(s, idx, dk, ds, de, n, wrote ? d_left : nullptr, d_right, capacity))) return rc;
   } else {
@@ -631,7 +631,7 @@ namespace sq {
 int tile_emit(sq_stream* s, uint32_t* d_left, uint32_t* d_right, uint64_t capacity) {
   if (use_packed(s->idx))
     return launch_packed(s, s->idx, s->d_q_key, s->d_q_start, s->d_q_end, s->n_rows, d_left, d_right, capacity);
-  if (s->idx->d_send)
+  if (use_rank(s->idx))
     return launch_rank_join(s, s->idx, s->d_q_key, s->d_q_start, s->d_q_end, s->n_rows, d_left, d_right, capacity);
   return launch_write(s, s->idx, s->d_q_start, s->n_rows, d_left, d_right, capacity);
 }

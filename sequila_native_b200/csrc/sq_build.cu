@@ -112,6 +112,23 @@ __global__ void __launch_bounds__(256) k_make_sort_keys(const uint64_t* __restri
   if (inv) atomicOr(inverted, 1u);  // some build row has end < start: the rank-difference count does not apply
 }
 
+// overlap depth of up to 4096 evenly spaced rows: depth(j) = j - first i of j's segment with runmax[i] >= start[j]
+__global__ void __launch_bounds__(256) k_depth_sample(const uint64_t* __restrict__ sorted_key, const int32_t* __restrict__ s_start,
+                                                      const int32_t* __restrict__ s_runmax, const SegMeta* __restrict__ meta,
+                                                      uint64_t n, uint32_t samples, unsigned long long* __restrict__ sum) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= samples) return;
+  const uint64_t j = uint64_t(t) * n / samples;
+  const uint32_t sb = meta[uint32_t(sorted_key[j] >> 32)].sb;
+  const int32_t st = s_start[j];
+  uint64_t lo = sb, hi = j;  // first i in [sb, j] with runmax[i] >= st (i = j qualifies: end >= start for well-formed rows)
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (s_runmax[mid] < st) lo = mid + 1; else hi = mid;
+  }
+  atomicAdd(sum, (unsigned long long)(j - lo));
+}
+
 // (id, end) sort keys of the rows in (id, start) order, and back: the ends sorted inside each key segment
 __global__ void __launch_bounds__(256) k_end_keys(const uint64_t* __restrict__ sorted_key, const int32_t* __restrict__ s_end,
                                                   uint64_t n, uint64_t* __restrict__ out) {
@@ -635,7 +652,18 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     unsigned int h_inverted = 0;
     SQ_CUDA(E, cudaMemcpyAsync(&h_inverted, d_inverted, 4, cudaMemcpyDeviceToHost, st));
     SQ_CUDA(E, cudaStreamSynchronize(st));
-    if (!h_inverted && !use_packed(idx) && ctx->opt.rank_count.load(std::memory_order_relaxed)) {
+    {
+      const uint32_t samples = uint32_t(n < 4096 ? n : 4096);
+      SQ_CUDA(E, cudaMemsetAsync(d_pstat, 0, 8, st));
+      k_depth_sample<<<(samples + 255) / 256, 256, 0, st>>>(d_k1, idx->d_start, idx->d_runmax, idx->d_meta, n, samples, d_pstat);
+      SQ_CUDA(E, cudaGetLastError());
+      unsigned long long h_sum = 0;
+      SQ_CUDA(E, cudaMemcpyAsync(&h_sum, d_pstat, 8, cudaMemcpyDeviceToHost, st));
+      SQ_CUDA(E, cudaStreamSynchronize(st));
+      idx->mean_depth = float(double(h_sum) / double(samples));
+    }
+    const int rank_opt = ctx->opt.rank_count.load(std::memory_order_relaxed);
+    if (!h_inverted && !use_packed(idx) && (rank_opt == 2 || (rank_opt == 1 && idx->mean_depth >= 48.f))) {
       k_end_keys<<<g, 256, 0, st>>>(d_k1, idx->d_end, n, d_k0);
       SQ_CUDA(E, cudaGetLastError());
       size_t tb = 0;

@@ -126,7 +126,8 @@ struct sq_options {
   std::atomic<int> scan_dict_capacity{1 << 16};  // text scan: initial capacity of the per-call key dictionary
   std::atomic<int> exec_trace{0};           // exec node: per-phase wall-clock trace on stderr
   std::atomic<int> pipeline_depth{3};       // sq_stream_submit: tiles in flight per stream (2..8)
-  std::atomic<int> rank_count{1};           // build: rank structure over the ends for the indexes the SoA kernels serve
+  std::atomic<int> rank_count{1};           // rank-difference kernel for the indexes the SoA kernels serve: 0 off, 1 when the
+                                            // index is deep enough to pay for it (measured crossover), 2 whenever possible
   std::atomic<int> coalesce_rows{1 << 20};  // exec node: probe rows that make one tile (sq_exec_probe_push / _pop)
 };
 
@@ -173,6 +174,7 @@ struct sq_index {
   uint32_t* d_edir = nullptr;
   uint64_t n_lines = 0;
   float mean_back_lines = 0.f; // mean number of extra lines a probe landing on a line's last row walks back
+  float mean_depth = 0.f;      // sampled: rows before a row (same key) whose running max end reaches its start = overlap depth
   uint64_t* d_ht_keys = nullptr;
   uint32_t* d_ht_ids = nullptr;
   uint32_t ht_cap = 0;
@@ -328,6 +330,7 @@ int launch_narrow_offsets(sq_stream* s, const int64_t* d_in, uint64_t n, int32_t
 int launch_packed(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
                   const int32_t* d_end, uint32_t n, uint32_t* d_left, uint32_t* d_right, uint64_t capacity);
 bool use_packed(const sq_index* idx);
+bool use_rank(const sq_index* idx);  // probe_rank.cu: the rank-difference kernel serves this (SoA-served) index
 // probe_staged.cu: the same contract as launch_packed for position-local tiles (build tile staged in shared memory by
 // TMA, one thread per probe row); result[2] = CTAs that could not stage and walked global memory instead
 int launch_staged(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,

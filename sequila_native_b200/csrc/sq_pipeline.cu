@@ -172,7 +172,7 @@ SQ_API int32_t sq_stream_submit(sq_stream* s, const sq_index* idx, const uint64_
       sl->staged = pick_staged(s, idx, key_hash, start, nullptr, nullptr, n_rows, d_left != nullptr);
       if ((rc = launch_packed_any(sub, s, sl->staged, idx, dk, ds, de, n_rows, d_left, d_right, dev_cap)))
         return fail(E, rc, "%s", sub->err.msg.c_str());
-    } else if (idx->d_send) {
+    } else if (use_rank(idx)) {
       if ((rc = launch_rank_join(sub, idx, dk, ds, de, n_rows, d_left, d_right, dev_cap))) return fail(E, rc, "%s", sub->err.msg.c_str());
     } else {
       if ((rc = launch_count(sub, idx, dk, ds, de, n_rows))) return fail(E, rc, "%s", sub->err.msg.c_str());

@@ -27,6 +27,15 @@ namespace sq {
 
 constexpr int kRB = 256;  // probe rows per CTA
 constexpr int kRWarps = kRB / 32;
+// Rows with up to kFlatMax candidates are walked flattened (no lane idles on a short list; ~70 warp instructions per 32
+// candidates for finding each candidate's row and its position); longer rows take the whole warp, one row after the
+// other, 32 candidates per step (~15 instructions per step, but the steps of a warp's rows are dependent load -> ballot
+// round trips in sequence).  Measured on cfg3 (24 candidates per row): flattening up to 32 candidates 1.51 ms, up to 8
+// candidates 1.75 ms.
+#ifndef SQ_RANK_FLAT_MAX
+#define SQ_RANK_FLAT_MAX 32
+#endif
+constexpr uint32_t kFlatMax = SQ_RANK_FLAT_MAX;
 
 // chain_lookback lives in sq_packed_common.cuh together with packed-line helpers; the same protocol, restated here
 // for a CTA's first warp (status word: [63:62] flag, [61:0] value)
@@ -56,7 +65,8 @@ __device__ __forceinline__ unsigned long long rank_lookback(unsigned long long* 
   return excl;
 }
 
-template <bool EMIT, bool WRITE_RIGHT>
+// COMPACT: the searches in their few-instruction form (cache-resident indexes, see sq_soa_common.cuh)
+template <bool EMIT, bool WRITE_RIGHT, bool COMPACT>
 __global__ void __launch_bounds__(kRB, 4)
 k_probe_rank(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __restrict__ q_start,
              const int32_t* __restrict__ q_end, uint32_t n, uint32_t* __restrict__ cnt_out,
@@ -84,12 +94,12 @@ k_probe_rank(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __
     qs = q_start[i];
     const int32_t qe = q_end[i];
     const uint32_t id = ht_lookup(iv.ht_keys, iv.ht_ids, iv.ht_mask, iv.sentinel_id, q_key[i]);
-    c = find_candidates(iv, id, qs, qe);
+    c = find_candidates<COMPACT>(iv, id, qs, qe);
     if (c.nc) {
       if ((long long)qs <= (long long)qe + 1) {
         const SegMeta m = iv.meta[id];
         // rows of the segment with end < qs = first position of the sorted ends with end > qs - 1
-        const uint32_t below = qs == INT32_MIN ? 0u : upper_bound_dir(iv.send, iv.edir, iv.emeta[id], qs - 1) - m.sb;
+        const uint32_t below = qs == INT32_MIN ? 0u : upper_bound_dir<COMPACT>(iv.send, iv.edir, iv.emeta[id], qs - 1) - m.sb;
         cnt = (c.lo + c.nc - m.sb) - below;
       } else {  // inverted probe row: {end < qs} is no subset of {start <= qe}; count the candidates
         for (uint32_t k = 0; k < c.nc; ++k) cnt += __ldg(iv.end + c.lo + k) >= qs ? 1u : 0u;
@@ -131,7 +141,7 @@ k_probe_rank(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __
 
   // ---- phase 3: the walk.  Small rows flattened: candidate t of the warp's concatenated list -> lane t ---------
   {
-    const bool small = cnt != 0 && c.nc <= kSmallMax;
+    const bool small = cnt != 0 && c.nc <= kFlatMax;
     const Flat f = flat_setup(small ? c.nc : 0u, lane, s_inv[warp]);
     const uint32_t r_jbase = __shfl_sync(0xffffffffu, c.lo, f.r_src) - f.r_excl;  // candidate t -> row r_jbase + t
     const int32_t r_qs = __shfl_sync(0xffffffffu, qs, f.r_src);
@@ -160,7 +170,7 @@ k_probe_rank(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __
     }
   }
   // ---- big rows, the whole warp on one row, 32 candidates per step ------------------------------------------------
-  unsigned big = __ballot_sync(0xffffffffu, cnt != 0 && c.nc > kSmallMax);
+  unsigned big = __ballot_sync(0xffffffffu, cnt != 0 && c.nc > kFlatMax);
   while (big) {
     const int p = __ffs(big) - 1;
     big &= big - 1;
@@ -182,6 +192,18 @@ k_probe_rank(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __
   }
 }
 
+// Measured on B200 (profiles/r02_subcfg_rank.json): the rank kernel replaces the count walk by a second directory-guided
+// search.  It wins where candidate lists are long — cfg4 (~100 rows deep): join 0.38 vs 0.50 ms, count(1) 0.12 vs 0.19 ms —
+// and loses where they are short and the searches expensive — cfg3 (~20 deep, starts clustered into crowded directory
+// bins): 1.51 vs 1.32 ms; cfg2 (depth ~0) is launch-bound either way.  The build samples the overlap depth.
+bool use_rank(const sq_index* idx) {
+  if (!idx->d_send || use_packed(idx)) return false;
+  const int opt = idx->ctx->opt.rank_count.load(std::memory_order_relaxed);
+  if (opt == 0) return false;
+  if (opt == 2) return true;
+  return idx->mean_depth >= 48.f;
+}
+
 int launch_rank_join(sq_stream* s, const sq_index* idx, const uint64_t* d_key, const int32_t* d_start,
                      const int32_t* d_end, uint32_t n, uint32_t* d_left, uint32_t* d_right, uint64_t capacity) {
   ErrorSlot& E = s->err;
@@ -198,15 +220,15 @@ int launch_rank_join(sq_stream* s, const sq_index* idx, const uint64_t* d_key, c
   if (d_left) SQ_CUDA(E, cudaMemsetAsync(chain, 0, size_t(n_tiles) * 8 + 16, s->stream));
   const IndexView iv = idx->view();
   const uint32_t backoff = uint32_t(s->ctx->opt.lookback_backoff_ns.load(std::memory_order_relaxed));
-  if (!d_left)
-    k_probe_rank<false, false><<<n_tiles, kRB, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket, result, nullptr,
-                                                               nullptr, 0, n_tiles, 0u);
-  else if (d_right)
-    k_probe_rank<true, true><<<n_tiles, kRB, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket, result, d_left,
-                                                             d_right, capacity, n_tiles, backoff);
-  else
-    k_probe_rank<true, false><<<n_tiles, kRB, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket, result, d_left,
-                                                              nullptr, capacity, n_tiles, backoff);
+  // arrays the searches touch: start, runmax, sorted ends, two directories — in L2 (126 MB) with room for the streams?
+  const bool compact = idx->n_rows * 14ull <= (48ull << 20);
+#define SQ_RANK_LAUNCH(E_, R_, C_)                                                                                       \
+  k_probe_rank<E_, R_, C_><<<n_tiles, kRB, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket, result, \
+                                                          E_ ? d_left : nullptr, R_ ? d_right : nullptr, E_ ? capacity : 0, n_tiles, E_ ? backoff : 0u)
+  if (!d_left) { if (compact) SQ_RANK_LAUNCH(false, false, true); else SQ_RANK_LAUNCH(false, false, false); }
+  else if (d_right) { if (compact) SQ_RANK_LAUNCH(true, true, true); else SQ_RANK_LAUNCH(true, true, false); }
+  else { if (compact) SQ_RANK_LAUNCH(true, false, true); else SQ_RANK_LAUNCH(true, false, false); }
+#undef SQ_RANK_LAUNCH
   SQ_CUDA(E, cudaGetLastError());
   s->launches += 1;
   return SQ_OK;

@@ -7,6 +7,10 @@ namespace sq {
 
 // first j in [m.sb, m.se) with vals[j] > q, for a segment-sorted array `vals` with its bin directory `dir`
 // (one directory load, then one round of independent loads inside the bin)
+// compact: a plain binary search inside the bin — a quarter of the instructions, dependent loads; for cache-resident
+// indexes, where the loads are L1 / L2 hits and the kernels are bound by their instruction stream (cfg3: the thread-per-row
+// searches cost 38 warp instructions per probe row in the latency-oriented form)
+template <bool COMPACT = false>
 __device__ __forceinline__ uint32_t upper_bound_dir(const int32_t* __restrict__ vals, const uint32_t* __restrict__ dir,
                                                     const SegMeta& m, int32_t qe) {
   uint32_t a, len;
@@ -21,6 +25,13 @@ __device__ __forceinline__ uint32_t upper_bound_dir(const int32_t* __restrict__ 
       a = __ldg(dir + m.dir_base + b);
       len = __ldg(dir + m.dir_base + b + 1) - a;
     }
+  }
+  if constexpr (COMPACT) {
+    while (len) {
+      const uint32_t half = len >> 1;
+      if (__ldg(vals + a + half) <= qe) { a += half + 1; len -= half + 1; } else len = half;
+    }
+    return a;
   }
   while (len > 32) {  // crowded bin (skewed data): narrow it the classic way first
     const uint32_t half = len >> 1;
@@ -61,13 +72,31 @@ struct Cand {
 // thread) instead of dependent binary-search steps: every HBM/L2 round trip a probe row waits for
 // is one of (1) the directory entry, (2) the four sampled starts that cover its bin, (3) the five
 // speculative gallop points over runmax; the refinements that follow hit lines already in L1.
+template <bool COMPACT = false>
 __device__ __forceinline__ Cand find_candidates(const IndexView& iv, uint32_t id, int32_t qs, int32_t qe) {
   Cand c{0u, 0u};
   if (id == kNoKey) return c;  // key hash absent from the build side: no rows (interval_join.rs:965)
   const SegMeta m = iv.meta[id];
 
-  const uint32_t hi = upper_bound_dir(iv.start, iv.dir, m, qe);
+  const uint32_t hi = upper_bound_dir<COMPACT>(iv.start, iv.dir, m, qe);
   if (hi == m.sb) return c;
+  if constexpr (COMPACT) {
+    // lo = first j in [sb, hi) with runmax[j] >= qs: gallop back from hi (candidate lists are short), then bisect
+    if (__ldg(iv.runmax + hi - 1) < qs) return c;
+    uint32_t right = hi - 1, step = 1;  // right qualifies
+    uint32_t left = m.sb;
+    while (right - left >= step) {
+      const uint32_t p = right - step;
+      if (__ldg(iv.runmax + p) >= qs) { right = p; step <<= 1; } else { left = p + 1; break; }
+    }
+    while (left < right) {
+      const uint32_t mid = (left + right) >> 1;
+      if (__ldg(iv.runmax + mid) < qs) left = mid + 1; else right = mid;
+    }
+    c.lo = right;
+    c.nc = hi - right;
+    return c;
+  }
 
   // ---- lo = first j in [sb, hi) with runmax[j] >= qs (runmax non-decreasing): speculative gallop
   const uint32_t span = hi - m.sb;  // rows available below hi

@@ -18,7 +18,7 @@ def probe_layout(request, cuda_ctx):
     # then exercise its global-memory path, sorted ones the staged path
     # "soa" = the rank-difference kernel where the build side allows it; "soa_walk" = count / scan / write always
     cuda_ctx.set_option("sequila.cuda_probe_layout", {"staged": "packed", "soa_walk": "soa"}.get(request.param, request.param))
-    cuda_ctx.set_option("sequila.cuda_rank_count", "off" if request.param == "soa_walk" else "on")
+    cuda_ctx.set_option("sequila.cuda_rank_count", "off" if request.param == "soa_walk" else "force")
     cuda_ctx.set_option("sequila.cuda_staged_probe", "on" if request.param == "staged" else "off")
     yield request.param
     cuda_ctx.set_option("sequila.cuda_probe_layout", "auto")

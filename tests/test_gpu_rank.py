@@ -14,9 +14,10 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture()
 def soa(cuda_ctx):
     cuda_ctx.set_option("cuda_probe_layout", "soa")
-    cuda_ctx.set_option("cuda_rank_count", "on")
+    cuda_ctx.set_option("cuda_rank_count", "force")
     yield cuda_ctx
     cuda_ctx.set_option("cuda_probe_layout", "auto")
+    cuda_ctx.set_option("cuda_rank_count", "on")
 
 
 def check(oracle, ctx, b, p, want_rank=True):
@@ -79,10 +80,10 @@ def test_rank_kernel_equals_the_two_walk_chain_on_the_device(cuda_ctx, oracle):
     bd, pd = to(b), to(p)
     ts = torch.cuda.current_stream().cuda_stream
     res = []
-    for rank in ("on", "off"):
+    for rank in ("force", "off"):
         cuda_ctx.set_option("cuda_rank_count", rank)
         idx = sn.CudaIndex.build_device(cuda_ctx, bd["key"], bd["start"], bd["end"], ts)
-        assert idx.uses_rank == (rank == "on")
+        assert idx.uses_rank == (rank == "force")
         st = sn.CudaStream(cuda_ctx, cuda_stream=ts)
         n = st.probe_count_device(idx, pd["key"], pd["start"], pd["end"])
         counts = st.counts()
@@ -96,3 +97,13 @@ def test_rank_kernel_equals_the_two_walk_chain_on_the_device(cuda_ctx, oracle):
     assert np.array_equal(res[0][2], res[1][2]) and np.array_equal(res[0][3], res[1][3])
     oidx = oracle.OracleIndex(b["key"], b["start"], b["end"])
     assert np.array_equal(res[0][2][:100000], oidx.counts(p["key"][:100000], p["start"][:100000], p["end"][:100000]))
+
+
+def test_depth_heuristic_picks_the_kernel(cuda_ctx):
+    """option on (the default): deep indexes (cfg4: ~100 rows reach every start) get the rank kernel, shallow ones keep the
+    count / scan / write chain (measured crossover, sq_probe_rank.cu::use_rank)"""
+    cuda_ctx.set_option("cuda_rank_count", "on")
+    b4, _ = sn.synth.cfg4(scale=0.05)
+    b2, _ = sn.synth.cfg2(scale=0.05)
+    assert sn.CudaIndex.build(cuda_ctx, b4["key"], b4["start"], b4["end"]).uses_rank
+    assert not sn.CudaIndex.build(cuda_ctx, b2["key"], b2["start"], b2["end"]).uses_rank
