@@ -112,6 +112,29 @@ __global__ void __launch_bounds__(256) k_make_sort_keys(const uint64_t* __restri
   if (inv) atomicOr(inverted, 1u);  // some build row has end < start: the rank-difference count does not apply
 }
 
+// block maxima of end: level 1 over 32 sorted rows (one warp per block), levels 2 and 3 over 32 entries of the level below
+__global__ void __launch_bounds__(256) k_block_max_rows(const int32_t* __restrict__ s_end, uint64_t n, uint64_t n_blocks,
+                                                        int32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
+  for (uint64_t b = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; b < n_blocks; b += warps) {
+    const uint64_t j = b * 32 + lane;
+    int32_t v = j < n ? s_end[j] : INT32_MIN;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, d));
+    if (lane == 0) out[b] = v;
+  }
+}
+__global__ void __launch_bounds__(256) k_block_max_up(const int32_t* __restrict__ in, uint64_t n_in, uint64_t n_out,
+                                                      int32_t* __restrict__ out) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t b = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; b < n_out; b += stride) {
+    int32_t v = INT32_MIN;
+    for (uint64_t k = b * 32; k < b * 32 + 32 && k < n_in; ++k) v = max(v, in[k]);
+    out[b] = v;
+  }
+}
+
 // overlap depth of up to 4096 evenly spaced rows: depth(j) = j - first i of j's segment with runmax[i] >= start[j]
 __global__ void __launch_bounds__(256) k_depth_sample(const uint64_t* __restrict__ sorted_key, const int32_t* __restrict__ s_start,
                                                       const int32_t* __restrict__ s_runmax, const SegMeta* __restrict__ meta,
@@ -435,6 +458,7 @@ void free_index(sq_index* idx) {
   cudaFree(idx->d_lines);
   cudaFree(idx->d_dir_line);
   cudaFree(idx->d_send); cudaFree(idx->d_emeta); cudaFree(idx->d_edir);
+  cudaFree(idx->d_bmax);
   for (auto& c : idx->columns) {
     if (c.owned) { cudaFree(c.d_values); cudaFree(c.d_offsets); }
     cudaFree(c.d_validity);
@@ -573,6 +597,21 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     SQ_CUDA(E, cudaGetLastError());
     k_runmax_final<<<n_tiles, kScanThreads, 0, st>>>(d_k1, idx->d_end, n, d_tile, idx->d_runmax);
     SQ_CUDA(E, cudaGetLastError());
+
+    // 3b. block maxima of end (32 / 1024 / 32768 rows): long candidate ranges are walked through them
+    {
+      const uint64_t n1 = (n + 31) / 32, n2 = (n1 + 31) / 32, n3 = (n2 + 31) / 32;
+      SQ_CUDA(E, cudaMallocAsync(&idx->d_bmax, (n1 + n2 + n3) * 4, st));
+      idx->bmax_n1 = n1;
+      idx->bmax_n2 = n2;
+      idx->bytes += (n1 + n2 + n3) * 4;
+      k_block_max_rows<<<grid_for(n1 * 32, 256, ctx->sm_count), 256, 0, st>>>(idx->d_end, n, n1, idx->d_bmax);
+      SQ_CUDA(E, cudaGetLastError());
+      k_block_max_up<<<grid_for(n2, 256, ctx->sm_count), 256, 0, st>>>(idx->d_bmax, n1, n2, idx->d_bmax + n1);
+      SQ_CUDA(E, cudaGetLastError());
+      k_block_max_up<<<grid_for(n3, 256, ctx->sm_count), 256, 0, st>>>(idx->d_bmax + n1, n2, n3, idx->d_bmax + n1 + n2);
+      SQ_CUDA(E, cudaGetLastError());
+    }
 
     // 4. per-segment bin directory (geometry on the device, offsets by a host scan: #keys is small)
     const uint32_t rows_per_bin = uint32_t(ctx->opt.rows_per_bin.load(std::memory_order_relaxed));

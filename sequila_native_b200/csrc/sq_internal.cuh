@@ -72,6 +72,13 @@ struct IndexView {
   // rank structure over the ENDS (nullptr when not built): the same rows' ends sorted inside each key segment, with
   // their own bin directory.  For rows with start <= end and a probe with qs <= qe + 1 the hit count is a rank
   // difference, |{start <= qe}| - |{end < qs}|, no candidate is touched to count
+  // max of end over aligned blocks of 32 / 1024 / 32768 sorted rows (blocks ignore key segments: a superset test).  One
+  // very long build interval keeps runmax >= qs for every later row of its key, so candidate ranges grow to O(segment);
+  // walks over long ranges descend this pyramid and touch only the blocks that hold a hit (coitrees prunes the same
+  // way through subtree_last, CT/nosimd.rs:343-384)
+  const int32_t* __restrict__ bmax1;
+  const int32_t* __restrict__ bmax2;
+  const int32_t* __restrict__ bmax3;
   const int32_t* __restrict__ send;
   const SegMeta* __restrict__ emeta;    // min_start = smallest end of the segment; sb / se as in meta
   const uint32_t* __restrict__ edir;
@@ -169,6 +176,8 @@ struct sq_index {
   uint64_t dir_bytes = 0;
   uint4* d_lines = nullptr;    // packed lines, or nullptr (wide / inverted intervals: SoA path only)
   uint2* d_dir_line = nullptr;
+  int32_t* d_bmax = nullptr;   // block maxima of end: level 1, then level 2, then level 3 (one allocation)
+  uint64_t bmax_n1 = 0, bmax_n2 = 0;
   int32_t* d_send = nullptr;   // ends sorted inside each key segment (rank-difference count), or nullptr
   sq::SegMeta* d_emeta = nullptr;
   uint32_t* d_edir = nullptr;
@@ -192,6 +201,9 @@ struct sq_index {
     v.n_keys = n_keys; v.n_rows = uint32_t(n_rows);
     v.lines = d_lines;
     v.dir_line = d_dir_line;
+    v.bmax1 = d_bmax;
+    v.bmax2 = d_bmax ? d_bmax + bmax_n1 : nullptr;
+    v.bmax3 = d_bmax ? d_bmax + bmax_n1 + bmax_n2 : nullptr;
     v.send = d_send;
     v.emeta = d_emeta;
     v.edir = d_edir;

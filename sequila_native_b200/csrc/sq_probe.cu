@@ -82,10 +82,18 @@ k_probe_count(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* _
     const uint32_t lo_p = __shfl_sync(0xffffffffu, c.lo, p);
     const int32_t qs_p = __shfl_sync(0xffffffffu, qs, p);
     uint32_t tot = 0;
-    for (uint32_t k0 = 0; k0 < nc_p; k0 += 32) {
-      const uint32_t k = k0 + lane;
-      const bool hit = k < nc_p && (__ldg(iv.end + lo_p + k) >= qs_p);
-      tot += __popc(__ballot_sync(0xffffffffu, hit));
+    if (nc_p > kSkipMin) {  // a long range (a very long build interval keeps runmax high behind it): only blocks with a hit
+      for_hit_blocks(iv, lo_p, lo_p + nc_p, qs_p, lane, [&](uint32_t j0) {
+        const uint32_t j = j0 + lane;
+        const bool hit = j >= lo_p && j < lo_p + nc_p && (__ldg(iv.end + j) >= qs_p);
+        tot += __popc(__ballot_sync(0xffffffffu, hit));
+      });
+    } else {
+      for (uint32_t k0 = 0; k0 < nc_p; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        const bool hit = k < nc_p && (__ldg(iv.end + lo_p + k) >= qs_p);
+        tot += __popc(__ballot_sync(0xffffffffu, hit));
+      }
     }
     if (lane == p) cnt = tot;
   }
@@ -247,17 +255,19 @@ k_probe_write(IndexView iv, const int32_t* __restrict__ q_start, uint32_t n, con
     const uint32_t lo_p = __shfl_sync(0xffffffffu, lo, p);
     const int32_t qs_p = __shfl_sync(0xffffffffu, qs, p);
     uint32_t run = __shfl_sync(0xffffffffu, coff, p);
-    for (uint32_t k0 = 0; k0 < nc_p; k0 += 32) {
-      const uint32_t k = k0 + lane;
-      const bool hit = k < nc_p && (__ldg(iv.end + lo_p + k) >= qs_p);
+    auto block = [&](uint32_t j0) {  // rows j0 + lane of [lo_p, lo_p + nc_p)
+      const uint32_t j = j0 + lane;
+      const bool hit = j >= lo_p && j - lo_p < nc_p && (__ldg(iv.end + j) >= qs_p);
       const unsigned m = __ballot_sync(0xffffffffu, hit);
       if (hit) {
         const uint32_t pos = run + __popc(m & ((1u << lane) - 1u));
-        lout[pos] = __ldg(iv.row + lo_p + k);
+        lout[pos] = __ldg(iv.row + j);
         if (WRITE_RIGHT) rout[pos] = tile_first + p;
       }
       run += __popc(m);
-    }
+    };
+    if (nc_p > kSkipMin) for_hit_blocks(iv, lo_p, lo_p + nc_p, qs_p, lane, block);
+    else for (uint32_t k0 = 0; k0 < nc_p; k0 += 32) block(lo_p + k0);
   }
 }
 
@@ -297,10 +307,9 @@ k_probe_nearest(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t*
   const SegMeta m = iv.meta[id];
   // an overlap, if any: walk back from the last start <= qe while some earlier end still reaches qs
   const uint32_t hi = first_start_greater(iv, m, qe);
-  for (uint32_t j = hi; j > m.sb;) {
-    --j;
-    if (__ldg(iv.runmax + j) < qs) break;
-    if (__ldg(iv.end + j) >= qs) { left_out[i] = __ldg(iv.row + j); return; }
+  if (hi > m.sb && __ldg(iv.runmax + hi - 1) >= qs) {  // some row with start <= qe reaches qs: the last such row
+    const uint32_t j = last_hit_below(iv, m.sb, hi, qs);
+    if (j < hi) { left_out[i] = __ldg(iv.row + j); return; }
   }
   // nearest(): `left` = first position with start >= qe in (start, end, row) order
   const uint32_t lb = qe == INT32_MIN ? m.sb : first_start_greater(iv, m, qe - 1);

@@ -102,7 +102,12 @@ k_probe_rank(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __
         const uint32_t below = qs == INT32_MIN ? 0u : upper_bound_dir<COMPACT>(iv.send, iv.edir, iv.emeta[id], qs - 1) - m.sb;
         cnt = (c.lo + c.nc - m.sb) - below;
       } else {  // inverted probe row: {end < qs} is no subset of {start <= qe}; count the candidates
-        for (uint32_t k = 0; k < c.nc; ++k) cnt += __ldg(iv.end + c.lo + k) >= qs ? 1u : 0u;
+        for (uint32_t j = c.lo + c.nc;;) {
+          const uint32_t f = last_hit_below(iv, c.lo, j, qs);  // == j: no further hit below j
+          if (f == j) break;
+          ++cnt;
+          j = f;
+        }
       }
     }
     cnt_out[i] = cnt;  // rle_right (interval_join.rs:1604)
@@ -178,17 +183,19 @@ k_probe_rank(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __
     const uint32_t lo_p = __shfl_sync(0xffffffffu, c.lo, p);
     const int32_t qs_p = __shfl_sync(0xffffffffu, qs, p);
     uint32_t run = __shfl_sync(0xffffffffu, coff, p);
-    for (uint32_t k0 = 0; k0 < nc_p; k0 += 32) {
-      const uint32_t k = k0 + lane;
-      const bool hit = k < nc_p && (__ldg(iv.end + lo_p + k) >= qs_p);
+    auto block = [&](uint32_t j0) {  // rows j0 + lane of [lo_p, lo_p + nc_p)
+      const uint32_t j = j0 + lane;
+      const bool hit = j >= lo_p && j - lo_p < nc_p && (__ldg(iv.end + j) >= qs_p);
       const unsigned m = __ballot_sync(0xffffffffu, hit);
       if (hit) {
         const uint32_t pos = run + __popc(m & ((1u << lane) - 1u));
-        lout[pos] = __ldg(iv.row + lo_p + k);
+        lout[pos] = __ldg(iv.row + j);
         if (WRITE_RIGHT) rout[pos] = tile_first + p;
       }
       run += __popc(m);
-    }
+    };
+    if (nc_p > kSkipMin) for_hit_blocks(iv, lo_p, lo_p + nc_p, qs_p, lane, block);  // long range: only blocks with a hit
+    else for (uint32_t k0 = 0; k0 < nc_p; k0 += 32) block(lo_p + k0);
   }
 }
 

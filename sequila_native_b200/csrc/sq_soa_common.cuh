@@ -63,6 +63,54 @@ __device__ __forceinline__ uint32_t upper_bound_dir(const int32_t* __restrict__ 
   return a;
 }
 
+// Walks of long candidate ranges.  Calls leaf(j0) — by the whole warp — for every aligned block [j0, j0 + 32) of sorted
+// rows that intersects [lo, hi) and whose maximum end reaches qs, in ascending order; blocks without a hit are skipped
+// 32768, 1024 or 32 rows at a time.  A range of 4M rows behind one chromosome-long interval costs a few steps per
+// level instead of 125,000 steps of 32 rows.
+constexpr uint32_t kSkipMin = 2048;  // shorter candidate ranges are walked row by row
+template <typename Leaf>
+__device__ __forceinline__ void for_hit_blocks(const IndexView& iv, uint32_t lo, uint32_t hi, int32_t qs, int lane, Leaf&& leaf) {
+  const uint32_t last = hi - 1;
+  for (uint32_t c3 = lo >> 15; c3 <= (last >> 15); c3 += 32) {
+    const uint32_t b3 = c3 + lane;
+    unsigned m3 = __ballot_sync(0xffffffffu, b3 <= (last >> 15) && __ldg(iv.bmax3 + b3) >= qs);
+    while (m3) {
+      const uint32_t B3 = c3 + uint32_t(__ffs(int(m3)) - 1);
+      m3 &= m3 - 1;
+      const uint32_t b2 = B3 * 32 + lane;
+      unsigned m2 = __ballot_sync(0xffffffffu, b2 >= (lo >> 10) && b2 <= (last >> 10) && __ldg(iv.bmax2 + b2) >= qs);
+      while (m2) {
+        const uint32_t B2 = B3 * 32 + uint32_t(__ffs(int(m2)) - 1);
+        m2 &= m2 - 1;
+        const uint32_t b1 = B2 * 32 + lane;
+        unsigned m1 = __ballot_sync(0xffffffffu, b1 >= (lo >> 5) && b1 <= (last >> 5) && __ldg(iv.bmax1 + b1) >= qs);
+        while (m1) {
+          const uint32_t B1 = B2 * 32 + uint32_t(__ffs(int(m1)) - 1);
+          m1 &= m1 - 1;
+          leaf(B1 * 32);
+        }
+      }
+    }
+  }
+}
+
+// thread-level: the last row j in [lo, hi) with end[j] >= qs, or hi when there is none
+__device__ __forceinline__ uint32_t last_hit_below(const IndexView& iv, uint32_t lo, uint32_t hi, int32_t qs) {
+  uint32_t j = hi;
+  while (j > lo) {
+    if ((j & 31u) == 0 && j - lo >= 32) {  // at a block boundary: whole blocks below j without a hit are skipped
+      if ((j & 1023u) == 0 && j - lo >= 1024) {
+        if ((j & 32767u) == 0 && j - lo >= 32768 && __ldg(iv.bmax3 + (j >> 15) - 1) < qs) { j -= 32768; continue; }
+        if (__ldg(iv.bmax2 + (j >> 10) - 1) < qs) { j -= 1024; continue; }
+      }
+      if (__ldg(iv.bmax1 + (j >> 5) - 1) < qs) { j -= 32; continue; }
+    }
+    --j;
+    if (__ldg(iv.end + j) >= qs) return j;
+  }
+  return hi;
+}
+
 struct Cand {
   uint32_t lo;  // first candidate (absolute position in the sorted arrays)
   uint32_t nc;  // number of candidates
