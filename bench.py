@@ -399,7 +399,7 @@ def e2e_pipeline(sn, ctx, idx, probe_h, n_pairs_expect, args, T, flags, steps, b
     n_tiles = max(T, (args.e2e_tiles // T) * T)
     hk, hs, he = probe_h["key"], probe_h["start"], probe_h["end"]
     digest = None
-    if not flags & 1:
+    if not flags & 1 and probe_h.get("ids") is None:
         bounds = np.linspace(0, n_probe, 9).astype(np.int64)
         st = sn.CudaStream(ctx)
         depth = int(ctx.get_option("cuda_pipeline_depth"))
@@ -424,11 +424,19 @@ def e2e_pipeline(sn, ctx, idx, probe_h, n_pairs_expect, args, T, flags, steps, b
     for _ in range(2):
         got = drv.run(idx, hk, hs, he, n_tiles, flags)
         assert got["n_pairs"] == n_pairs_expect, (got, n_pairs_expect)
+    ids = probe_h.get("ids")
+
+    def one_pass():
+        if ids is not None:  # 12 bytes per probe row: the contig column as dictionary ids (sq_stream_submit_ids)
+            return drv.run_ids(idx, probe_h["dict"], ids, hs, he, n_tiles, flags)
+        return drv.run(idx, hk, hs, he, n_tiles, flags)
+    if ids is not None:
+        assert one_pass()["n_pairs"] == n_pairs_expect
     barrier()
     e0 = time.perf_counter()
     agg = {"h2d_ms": 0.0, "kernel_ms": 0.0, "d2h_ms": 0.0, "tiles": 0, "regrown": 0, "native_seconds": 0.0}
     for _ in range(steps):
-        r = drv.run(idx, hk, hs, he, n_tiles, flags)
+        r = one_pass()
         for k, f in (("h2d_ms", "h2d_ms"), ("kernel_ms", "kernel_ms"), ("d2h_ms", "d2h_ms"), ("tiles", "n_tiles"),
                      ("regrown", "regrown_tiles"), ("native_seconds", "seconds")):
             agg[k] += r[f]
@@ -681,6 +689,20 @@ def main():
     ec_ms, _, _, ec_stats = e2e_pipeline(sn, ctx, idx, probe_h, e_pairs, args, T, N.TILE_COUNT_ONLY | N.TILE_NO_COUNTS,
                                          args.e2e_steps, barrier)
     ec_ms_max, _, _ = reduce_step(ec_ms, 0, 0, device)
+    # ... and with the key column as 4-byte dictionary ids (12 bytes per probe row on the wire), join and count(1)
+    e_ids = None
+    if args.workload == "cfg5_shard":
+        probe_h["ids"] = ctx.pinned_copy(probe["contig"][:e2e_rows].cpu().numpy().astype(np.uint32))
+        probe_h["dict"] = sn.synth.key_hash(np.arange(24))
+        ei_ms, _, _, _ = e2e_pipeline(sn, ctx, idx, probe_h, e_pairs, args, T, N.TILE_COUNT_ONLY | N.TILE_NO_COUNTS, args.e2e_steps, barrier)
+        ej_ms, _, _, _ = e2e_pipeline(sn, ctx, idx, probe_h, e_pairs, args, T, 0, args.e2e_steps, barrier)
+        ej_ms_max, _, _ = reduce_step(ej_ms, 0, 0, device)
+        ei_ms_max, _, _ = reduce_step(ei_ms, 0, 0, device)
+        e_ids = {"api": "sq_stream_submit_ids: key column as u32 ids into a dictionary of key hashes, 12 B per probe row in",
+                 "value": e_rows_total / (ej_ms_max * 1e-3), "unit": "probe intervals/s", "ms_per_step": ej_ms_max,
+                 "h2d_bytes_per_step": 12 * e2e_rows,
+                 "count_only": {"value": e_rows_total / (ei_ms_max * 1e-3), "unit": "probe intervals/s", "ms_per_step": ei_ms_max,
+                                "h2d_bytes_per_step": 12 * e2e_rows, "link_GBps": {"h2d": 12 * e2e_rows / (ei_ms * 1e-3) / 1e9}}}
     del probe_h
 
     # ---- count only: `select count(1) from a join b on ...`; no pair is written
@@ -851,7 +873,7 @@ def main():
                                  "tiles": e_stats["tiles"], "regrown": e_stats["regrown"]},
                     "link_GBps": {"h2d": 16 * e2e_rows / (e_ms * 1e-3) / 1e9,
                                   "d2h": (4 * e_pairs + 4 * e2e_rows) / (e_ms * 1e-3) / 1e9},
-                    "pairs_digest_equals_device": True,
+                    "pairs_digest_equals_device": True, "key_ids": e_ids,
                     "count_only": {"value": e_rows_total / (ec_ms_max * 1e-3), "unit": "probe intervals/s", "ms_per_step": ec_ms_max,
                                    "api": "same pipeline with SQ_TILE_COUNT_ONLY: count(1) of the join, host columns in, one number per tile out",
                                    "h2d_bytes_per_step": 16 * e2e_rows, "d2h_bytes_per_step": 16 * n_tiles,

@@ -183,6 +183,14 @@ typedef struct sq_tile_out {
 } sq_tile_out;
 int32_t sq_stream_submit(sq_stream* s, const sq_index* idx, const uint64_t* key_hash, const int32_t* start,
                          const int32_t* end, uint32_t n_rows, uint32_t flags, uint64_t* ticket_out);
+/* 12 bytes per probe row on the wire instead of 16: the key column travels as 4-byte ids into a dictionary of key hashes
+ * (what a dictionary-encoded contig column already is, queries/q1-coitrees.sql:6-14; hash of dictionary value k =
+ * key_hashes[k], the same hash the build side was given).  The dictionary is uploaded once per stream; an id outside it
+ * — SQ_NULL_INDEX for a NULL key — matches nothing (create_hashes leaves NULL slots out, IJ:1211).  Everything else as
+ * sq_stream_submit. */
+int32_t sq_stream_set_key_dictionary(sq_stream* s, const uint64_t* key_hashes, uint32_t n_entries);
+int32_t sq_stream_submit_ids(sq_stream* s, const sq_index* idx, const uint32_t* key_id, const int32_t* start,
+                             const int32_t* end, uint32_t n_rows, uint32_t flags, uint64_t* ticket_out);
 int32_t sq_stream_collect(sq_stream* s, uint64_t ticket, sq_tile_out* out);
 int32_t sq_stream_in_flight(const sq_stream* s);
 /* gauges of the pipeline since the stream was created (the reference's BuildProbeJoinMetrics, utils.rs:441-495,

@@ -42,6 +42,11 @@ int32_t sq_driver_create(sq_ctx* ctx, int32_t n_partitions, sq_driver** out);
 int32_t sq_driver_run(sq_driver* d, const sq_index* idx, const uint64_t* key_hash, const int32_t* start,
                       const int32_t* end, uint64_t n_rows, int32_t n_tiles, uint32_t flags, int32_t checksum,
                       sq_tile_consumer consume, void* user, sq_drive_stats* stats_out);
+/* the same pass with the key column as 4-byte dictionary ids (sq_stream_submit_ids; 12 bytes per probe row on the wire);
+ * the dictionary is uploaded to every partition's stream first */
+int32_t sq_driver_run_ids(sq_driver* d, const sq_index* idx, const uint64_t* dict_key_hashes, uint32_t dict_entries,
+                          const uint32_t* key_id, const int32_t* start, const int32_t* end, uint64_t n_rows, int32_t n_tiles,
+                          uint32_t flags, int32_t checksum, sq_tile_consumer consume, void* user, sq_drive_stats* stats_out);
 const char* sq_driver_last_error(const sq_driver* d);
 void sq_driver_free(sq_driver* d);
 

@@ -82,6 +82,8 @@ SIGNATURES = {
     "sq_stream_phase_ms": (C.c_int32, [vp, f32p]),
     "sq_stream_launches": (C.c_uint64, [vp]),
     "sq_stream_submit": (C.c_int32, [vp, vp, vp, vp, vp, C.c_uint32, C.c_uint32, u64p]),
+    "sq_stream_set_key_dictionary": (C.c_int32, [vp, vp, C.c_uint32]),
+    "sq_stream_submit_ids": (C.c_int32, [vp, vp, vp, vp, vp, C.c_uint32, C.c_uint32, u64p]),
     "sq_stream_collect": (C.c_int32, [vp, C.c_uint64, C.POINTER(SqTileOut)]),
     "sq_stream_in_flight": (C.c_int32, [vp]),
     "sq_stream_pipeline_stats": (C.c_int32, [vp, C.POINTER(C.c_double)]),
@@ -126,6 +128,8 @@ DRIVER_SIGNATURES = {
     "sq_driver_create": (C.c_int32, [vp, C.c_int32, C.POINTER(vp)]),
     "sq_driver_run": (C.c_int32, [vp, vp, vp, vp, vp, C.c_uint64, C.c_int32, C.c_uint32, C.c_int32, vp, vp,
                                   C.POINTER(SqDriveStats)]),
+    "sq_driver_run_ids": (C.c_int32, [vp, vp, vp, C.c_uint32, vp, vp, vp, C.c_uint64, C.c_int32, C.c_uint32, C.c_int32, vp, vp,
+                                      C.POINTER(SqDriveStats)]),
     "sq_driver_last_error": (C.c_char_p, [vp]),
     "sq_driver_free": (None, [vp]),
 }

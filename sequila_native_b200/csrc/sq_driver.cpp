@@ -54,9 +54,9 @@ struct Part {
 };
 }  // namespace
 
-SQ_API int32_t sq_driver_run(sq_driver* d, const sq_index* idx, const uint64_t* key_hash, const int32_t* start,
-                             const int32_t* end, uint64_t n_rows, int32_t n_tiles, uint32_t flags, int32_t checksum,
-                             sq_tile_consumer consume, void* user, sq_drive_stats* out) {
+static int32_t run_pass(sq_driver* d, const sq_index* idx, const uint64_t* key_hash, const uint32_t* key_id, const int32_t* start,
+                        const int32_t* end, uint64_t n_rows, int32_t n_tiles, uint32_t flags, int32_t checksum,
+                        sq_tile_consumer consume, void* user, sq_drive_stats* out) {
   if (!d || !idx || !out || n_tiles < 1) return SQ_EINVAL;
   memset(out, 0, sizeof *out);
   sq_ctx* ctx = d->ctx;
@@ -109,7 +109,8 @@ SQ_API int32_t sq_driver_run(sq_driver* d, const sq_index* idx, const uint64_t* 
       if (pend.size() == depth && !collect_one()) { drain(); return; }
       const uint64_t lo = bound(t), hi = bound(t + 1);
       uint64_t ticket = 0;
-      const int rc = sq_stream_submit(st, idx, key_hash + lo, start + lo, end + lo, uint32_t(hi - lo), flags, &ticket);
+      const int rc = key_id ? sq_stream_submit_ids(st, idx, key_id + lo, start + lo, end + lo, uint32_t(hi - lo), flags, &ticket)
+                            : sq_stream_submit(st, idx, key_hash + lo, start + lo, end + lo, uint32_t(hi - lo), flags, &ticket);
       if (rc != SQ_OK) { p.rc = rc; p.err = sq_stream_last_error(st); drain(); return; }
       pend.emplace_back(ticket, t);
     }
@@ -142,4 +143,22 @@ SQ_API int32_t sq_driver_run(sq_driver* d, const sq_index* idx, const uint64_t* 
     if (p.rc != SQ_OK && rc == SQ_OK) { rc = p.rc; d->err = p.err; }
   }
   return rc;
+}
+
+SQ_API int32_t sq_driver_run(sq_driver* d, const sq_index* idx, const uint64_t* key_hash, const int32_t* start,
+                             const int32_t* end, uint64_t n_rows, int32_t n_tiles, uint32_t flags, int32_t checksum,
+                             sq_tile_consumer consume, void* user, sq_drive_stats* out) {
+  return run_pass(d, idx, key_hash, nullptr, start, end, n_rows, n_tiles, flags, checksum, consume, user, out);
+}
+
+SQ_API int32_t sq_driver_run_ids(sq_driver* d, const sq_index* idx, const uint64_t* dict_key_hashes, uint32_t dict_entries,
+                                 const uint32_t* key_id, const int32_t* start, const int32_t* end, uint64_t n_rows,
+                                 int32_t n_tiles, uint32_t flags, int32_t checksum, sq_tile_consumer consume, void* user,
+                                 sq_drive_stats* out) {
+  if (!d || !key_id) return SQ_EINVAL;
+  for (sq_stream* st : d->streams) {
+    const int rc = sq_stream_set_key_dictionary(st, dict_key_hashes, dict_entries);
+    if (rc != SQ_OK) { d->err = sq_stream_last_error(st); return rc; }
+  }
+  return run_pass(d, idx, nullptr, key_id, start, end, n_rows, n_tiles, flags, checksum, consume, user, out);
 }

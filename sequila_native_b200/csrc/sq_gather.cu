@@ -458,4 +458,32 @@ int launch_iota(sq_stream* s, uint32_t* d_out, uint64_t n) {
   return SQ_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// sq_stream_submit_ids: the key column crossed PCIe as 4-byte dictionary ids (12 bytes per probe row instead of 16).
+// key = dict[id]; an id outside the dictionary (a NULL key) turns its row into the empty interval
+// [INT32_MAX, INT32_MIN], which no build row overlaps (start <= INT32_MIN && end >= INT32_MAX is outside the domain).
+__global__ void __launch_bounds__(256) k_expand_ids(const uint32_t* __restrict__ ids, const uint64_t* __restrict__ dict, uint32_t dict_n,
+                                                    uint32_t n, uint64_t* __restrict__ key_out, int32_t* __restrict__ start,
+                                                    int32_t* __restrict__ end) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t id = ids[i];
+  if (id < dict_n) {
+    key_out[i] = __ldg(dict + id);
+  } else {
+    key_out[i] = 0;
+    start[i] = INT32_MAX;
+    end[i] = INT32_MIN;
+  }
+}
+
+int launch_expand_ids(sq_stream* s, cudaStream_t st, const uint32_t* d_ids, const uint64_t* d_dict, uint32_t dict_n, uint32_t n,
+                      uint64_t* d_key_out, int32_t* d_start, int32_t* d_end) {
+  if (n == 0) return SQ_OK;
+  k_expand_ids<<<(n + 255) / 256, 256, 0, st>>>(d_ids, d_dict, dict_n, n, d_key_out, d_start, d_end);
+  SQ_CUDA(s->err, cudaGetLastError());
+  s->launches += 1;
+  return SQ_OK;
+}
+
 }  // namespace sq

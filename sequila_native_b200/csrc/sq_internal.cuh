@@ -234,6 +234,8 @@ struct sq_stream {
   double pipe_ms[3] = {0, 0, 0};       // summed device time of h2d / kernels / d2h over collected tiles
   uint64_t pipe_bytes[2] = {0, 0};     // bytes moved h2d / d2h
   uint64_t pipe_tiles = 0, pipe_regrow = 0;
+  sq_buf d_dict;                       // key dictionary of sq_stream_submit_ids: u64 hash per dictionary entry
+  uint32_t dict_n = 0;
 
   // which packed-line kernel serves the next tile (sq_api.cu: pick_staged / staged_feedback)
   uint32_t staged_skip = 0;      // tiles to send to k_probe_packed before the staged kernel is tried again
@@ -364,6 +366,9 @@ int launch_packed_any(sq_stream* s, sq_stream* policy, bool staged, const sq_ind
 // api.cu: per-tile state of a stream (count -> emit protocol) and the write pass of a counted tile
 void tile_begin(sq_stream* s, const sq_index* idx, const uint64_t* dk, const int32_t* ds, const int32_t* de, uint32_t n);
 int tile_emit(sq_stream* s, uint32_t* d_left, uint32_t* d_right, uint64_t capacity);
+// gather.cu: key ids -> key hashes through a stream's dictionary; rows with an id outside it get an interval nothing overlaps
+int launch_expand_ids(sq_stream* s, cudaStream_t st, const uint32_t* d_ids, const uint64_t* d_dict, uint32_t dict_n, uint32_t n,
+                      uint64_t* d_key_out, int32_t* d_start, int32_t* d_end);
 // pipeline.cu
 void pipeline_destroy(sq_stream* s);
 uint64_t pipeline_bytes(const sq_stream* s);

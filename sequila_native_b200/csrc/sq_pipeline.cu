@@ -37,6 +37,7 @@ struct sq_tile_slot {
   uint64_t dev_cap = 0;  // pairs the device pair buffers were offered
   uint64_t spec = 0;     // pairs whose copy-out is already enqueued
   bool staged = false;   // served by the staged kernel: its report feeds the stream's kernel choice
+  uint32_t key_bytes = 8; // bytes per key on the wire (8: hash, 4: dictionary id)
   cudaEvent_t ev[6] = {};  // 0 h2d begin, 1 h2d end, 2 kernels end, 3 scalars + counts arrived, 4 d2h begin, 5 d2h end
   bool ev_ready = false;
 };
@@ -56,6 +57,7 @@ void pipeline_destroy(sq_stream* s) {
     delete sl;
   }
   s->slots.clear();
+  release(s->d_dict);
   if (s->stream_in) cudaStreamDestroy(s->stream_in);
   if (s->stream_out) cudaStreamDestroy(s->stream_out);
   s->stream_in = s->stream_out = nullptr;
@@ -104,12 +106,14 @@ static int32_t pinned(sq_stream* s, size_t bytes, uint32_t** out) {
   return SQ_OK;
 }
 
-SQ_API int32_t sq_stream_submit(sq_stream* s, const sq_index* idx, const uint64_t* key_hash, const int32_t* start,
-                                const int32_t* end, uint32_t n_rows, uint32_t flags, uint64_t* ticket_out) {
+// key_hash: u64 hash per row, or (key_id != nullptr) 4-byte ids into the stream's key dictionary
+static int32_t submit_tile(sq_stream* s, const sq_index* idx, const uint64_t* key_hash, const uint32_t* key_id, const int32_t* start,
+                           const int32_t* end, uint32_t n_rows, uint32_t flags, uint64_t* ticket_out) {
   if (!s) return SQ_EINVAL;
   ErrorSlot& E = s->err;
   if (!idx || !ticket_out) return fail(E, SQ_EINVAL, "null index or ticket pointer");
-  if (n_rows && (!key_hash || !start || !end)) return fail(E, SQ_EINVAL, "null probe column");
+  if (n_rows && ((!key_hash && !key_id) || !start || !end)) return fail(E, SQ_EINVAL, "null probe column");
+  if (key_id && !s->d_dict.p) return fail(E, SQ_ESTATE, "sq_stream_submit_ids without sq_stream_set_key_dictionary");
   if (idx->ctx->device != s->ctx->device)
     return fail(E, SQ_EINVAL, "index lives on device %d, stream on %d", idx->ctx->device, s->ctx->device);
   SQ_CUDA(E, cudaSetDevice(s->ctx->device));
@@ -131,7 +135,7 @@ SQ_API int32_t sq_stream_submit(sq_stream* s, const sq_index* idx, const uint64_
     dev_cap = est ? est + est / 4 + 1024 : n * 8 + 1024;
   }
   if (n) {
-    if ((rc = ensure(E, sub->d_in, n * 16, false))) return rc;
+    if ((rc = ensure(E, sub->d_in, n * (key_id ? 20 : 16), false))) return rc;
     if (dev_cap && (rc = ensure(E, sub->d_left, dev_cap * 4, false))) return rc;
     if (want_right && (rc = ensure(E, sub->d_right, dev_cap * 4, false))) return rc;
   }
@@ -158,18 +162,23 @@ SQ_API int32_t sq_stream_submit(sq_stream* s, const sq_index* idx, const uint64_
   if (n) {
     // ---- copy-in
     SQ_CUDA(E, cudaEventRecord(sl->ev[0], s->stream_in));
-    SQ_CUDA(E, cudaMemcpyAsync(dk, key_hash, n * 8, cudaMemcpyHostToDevice, s->stream_in));
+    auto* d_ids = reinterpret_cast<uint32_t*>(de + n);
+    if (key_id) SQ_CUDA(E, cudaMemcpyAsync(d_ids, key_id, n * 4, cudaMemcpyHostToDevice, s->stream_in));
+    else SQ_CUDA(E, cudaMemcpyAsync(dk, key_hash, n * 8, cudaMemcpyHostToDevice, s->stream_in));
     SQ_CUDA(E, cudaMemcpyAsync(ds, start, n * 4, cudaMemcpyHostToDevice, s->stream_in));
     SQ_CUDA(E, cudaMemcpyAsync(de, end, n * 4, cudaMemcpyHostToDevice, s->stream_in));
     SQ_CUDA(E, cudaEventRecord(sl->ev[1], s->stream_in));
     // ---- kernels: the whole count -> scan -> write chain is enqueued without a host round trip; a tile that does
     // not fit dev_cap reports it in result[1] and is re-emitted at collect
     SQ_CUDA(E, cudaStreamWaitEvent(s->stream, sl->ev[1], 0));
+    if (key_id && (rc = launch_expand_ids(s, s->stream, d_ids, static_cast<const uint64_t*>(s->d_dict.p), s->dict_n, n_rows, dk, ds, de)))
+      return rc;
+    const uint64_t* host_key = key_id ? nullptr : key_hash;  // the staged kernel's look at the row order needs the hashes
     uint32_t* d_left = dev_cap ? static_cast<uint32_t*>(sub->d_left.p) : nullptr;
     uint32_t* d_right = want_right ? static_cast<uint32_t*>(sub->d_right.p) : nullptr;
     sl->staged = false;
     if (use_packed(idx)) {
-      sl->staged = pick_staged(s, idx, key_hash, start, nullptr, nullptr, n_rows, d_left != nullptr);
+      sl->staged = pick_staged(s, idx, host_key, host_key ? start : nullptr, nullptr, nullptr, n_rows, d_left != nullptr);
       if ((rc = launch_packed_any(sub, s, sl->staged, idx, dk, ds, de, n_rows, d_left, d_right, dev_cap)))
         return fail(E, rc, "%s", sub->err.msg.c_str());
     } else if (use_rank(idx)) {
@@ -196,7 +205,32 @@ SQ_API int32_t sq_stream_submit(sq_stream* s, const sq_index* idx, const uint64_
   }
   sl->busy = true;
   sl->ticket = s->next_ticket++;
+  sl->key_bytes = key_id ? 4 : 8;
   *ticket_out = sl->ticket;
+  return SQ_OK;
+}
+
+SQ_API int32_t sq_stream_submit(sq_stream* s, const sq_index* idx, const uint64_t* key_hash, const int32_t* start,
+                                const int32_t* end, uint32_t n_rows, uint32_t flags, uint64_t* ticket_out) {
+  return submit_tile(s, idx, key_hash, nullptr, start, end, n_rows, flags, ticket_out);
+}
+
+SQ_API int32_t sq_stream_submit_ids(sq_stream* s, const sq_index* idx, const uint32_t* key_id, const int32_t* start,
+                                    const int32_t* end, uint32_t n_rows, uint32_t flags, uint64_t* ticket_out) {
+  if (s && n_rows && !key_id) return fail(s->err, SQ_EINVAL, "null probe column");
+  return submit_tile(s, idx, nullptr, key_id, start, end, n_rows, flags, ticket_out);
+}
+
+SQ_API int32_t sq_stream_set_key_dictionary(sq_stream* s, const uint64_t* key_hashes, uint32_t n_entries) {
+  if (!s) return SQ_EINVAL;
+  ErrorSlot& E = s->err;
+  if (n_entries && !key_hashes) return fail(E, SQ_EINVAL, "null key dictionary");
+  if (s->next_ticket != s->oldest_ticket) return fail(E, SQ_ESTATE, "tiles in flight still read the previous dictionary: collect them first");
+  SQ_CUDA(E, cudaSetDevice(s->ctx->device));
+  int rc;
+  if ((rc = ensure(E, s->d_dict, size_t(n_entries ? n_entries : 1) * 8, false))) return rc;
+  if (n_entries) SQ_CUDA(E, cudaMemcpy(s->d_dict.p, key_hashes, size_t(n_entries) * 8, cudaMemcpyHostToDevice));
+  s->dict_n = n_entries;
   return SQ_OK;
 }
 
@@ -271,7 +305,7 @@ SQ_API int32_t sq_stream_collect(sq_stream* s, uint64_t ticket, sq_tile_out* out
     if (cudaEventElapsedTime(&ms, sl->ev[1], sl->ev[2]) == cudaSuccess) s->pipe_ms[1] += ms;
     if (cudaEventElapsedTime(&ms, sl->ev[4], sl->ev[5]) == cudaSuccess) s->pipe_ms[2] += ms;
     cudaGetLastError();
-    s->pipe_bytes[0] += n * 16;
+    s->pipe_bytes[0] += n * (8 + sl->key_bytes);
     s->pipe_bytes[1] += 16 + (sl->h_counts ? n * 4 : 0) + (count_only ? 0 : (want_right ? 8 : 4) * (n_pairs > sl->spec ? n_pairs : sl->spec));
     s->pipe_tiles += 1;
     if (!count_only) s->pairs_per_row = double(n_pairs) / double(n);

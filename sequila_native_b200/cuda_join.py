@@ -168,6 +168,19 @@ class CudaDriver:
         return {f: getattr(st, f) for f, _ in N.SqDriveStats._fields_}
 
 
+def _driver_run_ids(self, index, dict_hashes, key_id, start, end, n_tiles: int, flags: int = 0, checksum: bool = False) -> dict:
+    """sq_driver_run_ids: one pass with the key column as uint32 ids into `dict_hashes` (12 bytes per row on the wire)"""
+    d, k, s, e = _np(dict_hashes, np.uint64), _np(key_id, np.uint32), _np(start, np.int32), _np(end, np.int32)
+    st = N.SqDriveStats()
+    rc = self._lib.sq_driver_run_ids(self._h, index._h, _ptr(d), d.shape[0], _ptr(k), _ptr(s), _ptr(e), k.shape[0], int(n_tiles),
+                                     int(flags), int(bool(checksum)), None, None, C.byref(st))
+    _check(rc, lambda: self._lib.sq_driver_last_error(self._h))
+    return {f: getattr(st, f) for f, _ in N.SqDriveStats._fields_}
+
+
+CudaDriver.run_ids = _driver_run_ids
+
+
 class CudaStream:
     """sq_stream: per-partition probe context (CUDA stream + staging + scratch)."""
 
@@ -237,6 +250,22 @@ class CudaStream:
         k, s, e = _np(key_hash, np.uint64), _np(start, np.int32), _np(end, np.int32)
         t = C.c_uint64(0)
         _check(self._lib.sq_stream_submit(self._h, index._h, _ptr(k), _ptr(s), _ptr(e), k.shape[0], int(flags), C.byref(t)),
+               self._err)
+        self._keep = index
+        self._tiles = getattr(self, "_tiles", {})
+        self._tiles[int(t.value)] = (k, s, e)
+        return int(t.value)
+
+    def set_key_dictionary(self, key_hashes) -> None:
+        """sq_stream_set_key_dictionary: hash of every dictionary value, uploaded once; submit_ids() then sends 4-byte ids"""
+        d = _np(key_hashes, np.uint64)
+        _check(self._lib.sq_stream_set_key_dictionary(self._h, _ptr(d), d.shape[0]), self._err)
+
+    def submit_ids(self, index: CudaIndex, key_id, start, end, flags: int = 0) -> int:
+        """sq_stream_submit_ids: as submit(), the key column as uint32 dictionary ids (12 bytes per row on the wire)"""
+        k, s, e = _np(key_id, np.uint32), _np(start, np.int32), _np(end, np.int32)
+        t = C.c_uint64(0)
+        _check(self._lib.sq_stream_submit_ids(self._h, index._h, _ptr(k), _ptr(s), _ptr(e), k.shape[0], int(flags), C.byref(t)),
                self._err)
         self._keep = index
         self._tiles = getattr(self, "_tiles", {})

@@ -185,3 +185,43 @@ def test_native_partition_loop(cuda_ctx, oracle, parts, tiles):
         assert r["h2d_bytes"] == 16 * len(p["key"])
         if flags == 0:
             assert r["left_xor"] == int(np.bitwise_xor.reduce(ol.astype(np.uint64)))
+
+
+@pytest.mark.parametrize("layout", ["packed", "soa"])
+def test_key_dictionary_ids_on_the_wire(cuda_ctx, oracle, layout):
+    """sq_stream_submit_ids: the key column as 4-byte dictionary ids (12 bytes per probe row) gives the rows the u64 hashes
+    give; ids outside the dictionary (SQ_NULL_INDEX = NULL key) match nothing; the native driver's ids pass agrees"""
+    from sequila_native_b200.cuda_join import CudaDriver
+    cuda_ctx.set_option("cuda_probe_layout", layout)
+    try:
+        b, p = sn.synth.cfg5(scale=0.004)
+        idx = sn.CudaIndex.build(cuda_ctx, b["key"], b["start"], b["end"])
+        dict_hashes = sn.synth.key_hash(np.arange(24))
+        ids = p["contig"].astype(np.uint32).copy()
+        rng = np.random.default_rng(2)
+        nulls = rng.random(len(ids)) < 0.03
+        ids[nulls] = np.where(rng.random(int(nulls.sum())) < 0.5, N.NULL_INDEX, 24 + 5).astype(np.uint32)
+        keys = p["key"].copy()
+        keys[nulls] = np.uint64(0xDEAD)  # a hash the build side never saw: the oracle's picture of a NULL key
+        cols = {"ids": cuda_ctx.pinned_copy(ids), "start": cuda_ctx.pinned_copy(p["start"]), "end": cuda_ctx.pinned_copy(p["end"])}
+        st = sn.CudaStream(cuda_ctx)
+        with pytest.raises(sn.SequilaCudaError) as e:
+            st.submit_ids(idx, cols["ids"][:10], cols["start"][:10], cols["end"][:10])
+        assert e.value.code == N.SQ_ESTATE
+        st.set_key_dictionary(dict_hashes)
+        cuts = tiles_of(p, 5)
+        tickets = [st.submit_ids(idx, cols["ids"][a:z], cols["start"][a:z], cols["end"][a:z]) for a, z in cuts[:3]]
+        out = [st.collect(t) for t in tickets]
+        tickets = [st.submit_ids(idx, cols["ids"][a:z], cols["start"][a:z], cols["end"][a:z]) for a, z in cuts[3:]]
+        out += [st.collect(t) for t in tickets]
+        assert st.pipeline_stats()["h2d_bytes"] == 12 * len(ids)
+        q = dict(p)
+        q["key"] = keys
+        check_tiles(oracle, b, q, 5, out, 0)
+        ol, _, _ = oracle.join(b["key"], b["start"], b["end"], keys, p["start"], p["end"])
+        drv = CudaDriver(cuda_ctx, 3)
+        r = drv.run_ids(idx, dict_hashes, cols["ids"], cols["start"], cols["end"], 7, 0, checksum=True)
+        assert r["n_pairs"] == len(ol) and r["h2d_bytes"] == 12 * len(ids)
+        assert r["left_xor"] == int(np.bitwise_xor.reduce(ol.astype(np.uint64)))
+    finally:
+        cuda_ctx.set_option("cuda_probe_layout", "auto")
