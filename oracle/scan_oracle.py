@@ -104,8 +104,9 @@ def scan_delimited(text: bytes, delimiter: bytes = b"\t", has_header: bool = Fal
         f = raw.split(delimiter)
         if len(f) < need:
             raise ScanError("parse", f"{len(f)} field(s), need {need}: {raw!r}")
-        used = [col_start, col_end] + ([] if col_key is None else [col_key])
-        if any(f[c][:1] == b'"' for c in used):
+        # a quoted field may hide the delimiter (DataFusion's CSV reader honours quotes): every field up to the last one the
+        # table names — the ones skipped on the way included — must be unquoted, else the columns would shift silently
+        if any(f[c][:1] == b'"' for c in range(need)):
             raise ScanError("parse", f"quoted field: {raw!r}")
         vals = []
         for c, minus in ((col_start, start_minus), (col_end, end_minus)):

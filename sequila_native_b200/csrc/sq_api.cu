@@ -117,7 +117,15 @@ SQ_API int32_t sq_ctx_create(int32_t device, sq_ctx** out) {
   return SQ_OK;
 }
 
-SQ_API void sq_ctx_destroy(sq_ctx* ctx) { delete ctx; }
+SQ_API void sq_ctx_destroy(sq_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->pool) {  // indexes must be freed before their context; whatever the pool still caches goes back to the driver
+    cudaSetDevice(ctx->device);
+    cudaMemPoolDestroy(static_cast<cudaMemPool_t>(ctx->pool));
+    cudaGetLastError();
+  }
+  delete ctx;
+}
 
 // ---- options: the `sequila.cuda_*` keys ---------------------------------------------------------
 namespace {

@@ -475,28 +475,35 @@ void free_index(sq_index* idx) {
 // to the driver (cudaMalloc / cudaFree of GB-sized blocks cost tens of milliseconds and synchronise).
 struct TmpFree {
   cudaStream_t st;
+  cudaMemPool_t pool;
   std::vector<void*> ptrs;
-  explicit TmpFree(cudaStream_t s) : st(s) {}
+  TmpFree(cudaStream_t s, cudaMemPool_t pl) : st(s), pool(pl) {}
   ~TmpFree() { for (void* p : ptrs) cudaFreeAsync(p, st); }
   template <class T> cudaError_t alloc(T** p, size_t bytes) {
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(p), bytes ? bytes : 16, st);
+    cudaError_t e = cudaMallocFromPoolAsync(reinterpret_cast<void**>(p), bytes ? bytes : 16, pool, st);
     if (e == cudaSuccess) ptrs.push_back(*p);
     return e;
   }
 };
 
-static void keep_pool_memory(int device) {
-  static std::mutex mu;
-  static std::vector<int> done;
-  std::lock_guard<std::mutex> g(mu);
-  for (int d : done) if (d == device) return;
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    uint64_t keep = ~0ull;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-  }
+// The library's OWN stream-ordered pool on the context's device: index arrays and build temporaries are kept between
+// builds (release threshold = everything) without touching the device's default pool, which belongs to the embedding
+// application (DataFusion, other CUDA libraries in the process).
+static cudaMemPool_t ctx_pool(sq_ctx* ctx) {
+  std::lock_guard<std::mutex> g(ctx->pool_mu);
+  if (ctx->pool) return static_cast<cudaMemPool_t>(ctx->pool);
+  cudaMemPoolProps props{};
+  props.allocType = cudaMemAllocationTypePinned;
+  props.handleTypes = cudaMemHandleTypeNone;
+  props.location.type = cudaMemLocationTypeDevice;
+  props.location.id = ctx->device;
+  cudaMemPool_t pool = nullptr;
+  if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  uint64_t keep = ~0ull;
+  cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
   cudaGetLastError();
-  done.push_back(device);
+  ctx->pool = pool;
+  return pool;
 }
 
 int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_start, const int32_t* d_end,
@@ -510,8 +517,9 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
   idx->ctx = ctx;
   idx->n_rows = n;
   struct Guard { sq_index* p; ~Guard() { if (p) free_index(p); } } guard{idx};
-  keep_pool_memory(ctx->device);
-  TmpFree tmp(st);
+  cudaMemPool_t pool = ctx_pool(ctx);
+  if (!pool) return fail(E, SQ_ECUDA, "cudaMemPoolCreate failed on device %d", ctx->device);
+  TmpFree tmp(st, pool);
 
   cudaEvent_t e0, e1;
   SQ_CUDA(E, cudaEventCreate(&e0));
@@ -526,7 +534,7 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
   uint32_t cap = 4096;
   HtStatus hs{};
   for (;;) {
-    SQ_CUDA(E, cudaMallocAsync(&idx->d_ht_keys, size_t(cap) * 8, st));
+    SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_ht_keys, size_t(cap) * 8, pool, st));
     SQ_CUDA(E, cudaMemsetAsync(idx->d_ht_keys, 0xFF, size_t(cap) * 8, st));
     SQ_CUDA(E, cudaMemsetAsync(d_status, 0, sizeof(HtStatus) + 16, st));
     if (n) {
@@ -545,7 +553,7 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     cap = uint32_t(uint64_t(cap) * 16 > max_cap ? max_cap : uint64_t(cap) * 16);
   }
   idx->ht_cap = cap;
-  SQ_CUDA(E, cudaMallocAsync(&idx->d_ht_ids, size_t(cap) * 4, st));
+  SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_ht_ids, size_t(cap) * 4, pool, st));
   k_ht_assign<<<(cap + 255) / 256, 256, 0, st>>>(idx->d_ht_keys, idx->d_ht_ids, cap, d_counter);
   SQ_CUDA(E, cudaGetLastError());
   uint32_t n_keys = hs.distinct;
@@ -553,11 +561,11 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
   idx->n_keys = n_keys;
 
   // 2. sorted arrays
-  SQ_CUDA(E, cudaMallocAsync(&idx->d_start, (n ? n : 1) * 4, st));
-  SQ_CUDA(E, cudaMallocAsync(&idx->d_runmax, (n ? n : 1) * 4, st));
-  SQ_CUDA(E, cudaMallocAsync(&idx->d_end, (n ? n : 1) * 4, st));
-  SQ_CUDA(E, cudaMallocAsync(&idx->d_row, (n ? n : 1) * 4, st));
-  SQ_CUDA(E, cudaMallocAsync(&idx->d_meta, (size_t(n_keys) + 1) * sizeof(SegMeta), st));
+  SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_start, (n ? n : 1) * 4, pool, st));
+  SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_runmax, (n ? n : 1) * 4, pool, st));
+  SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_end, (n ? n : 1) * 4, pool, st));
+  SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_row, (n ? n : 1) * 4, pool, st));
+  SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_meta, (size_t(n_keys) + 1) * sizeof(SegMeta), pool, st));
   idx->bytes = uint64_t(n ? n : 1) * 16 + (uint64_t(n_keys) + 1) * sizeof(SegMeta) + uint64_t(cap) * 12;
 
   if (n) {
@@ -601,7 +609,7 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     // 3b. block maxima of end (32 / 1024 / 32768 rows): long candidate ranges are walked through them
     {
       const uint64_t n1 = (n + 31) / 32, n2 = (n1 + 31) / 32, n3 = (n2 + 31) / 32;
-      SQ_CUDA(E, cudaMallocAsync(&idx->d_bmax, (n1 + n2 + n3) * 4, st));
+      SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_bmax, (n1 + n2 + n3) * 4, pool, st));
       idx->bmax_n1 = n1;
       idx->bmax_n2 = n2;
       idx->bytes += (n1 + n2 + n3) * 4;
@@ -632,7 +640,7 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     h_meta[n_keys] = SegMeta{};
     h_meta[n_keys].sb = h_meta[n_keys].se = uint32_t(n);
     SQ_CUDA(E, cudaMemcpyAsync(idx->d_meta, h_meta.data(), (size_t(n_keys) + 1) * sizeof(SegMeta), cudaMemcpyHostToDevice, st));
-    SQ_CUDA(E, cudaMallocAsync(&idx->d_dir, dir_total * 4, st));
+    SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_dir, dir_total * 4, pool, st));
     idx->bytes += dir_total * 4;
     idx->dir_bytes = dir_total * 4;
     k_fill_dir<<<g, 256, 0, st>>>(d_k1, idx->d_start, n, idx->d_meta, idx->d_dir);
@@ -658,14 +666,14 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     SQ_CUDA(E, cudaGetLastError());
     k_seg_lines<<<(n_keys + 256) / 256, 256, 0, st>>>(d_line_incl, n_keys, n, idx->d_meta);
     SQ_CUDA(E, cudaGetLastError());
-    SQ_CUDA(E, cudaMallocAsync(&idx->d_dir_line, dir_total * 8, st));
+    SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_dir_line, dir_total * 8, pool, st));
     k_fill_dir_line<<<grid_for(dir_total, 256, ctx->sm_count), 256, 0, st>>>(idx->d_dir, dir_total, d_line_incl, d_line_first,
                                                                              idx->d_start, idx->d_dir_line);
     SQ_CUDA(E, cudaGetLastError());
     unsigned long long* d_pstat = nullptr;
     SQ_CUDA(E, tmp.alloc(&d_pstat, 16));
     SQ_CUDA(E, cudaMemsetAsync(d_pstat, 0, 16, st));
-    SQ_CUDA(E, cudaMallocAsync(&idx->d_lines, line_total * 128, st));
+    SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_lines, line_total * 128, pool, st));
     k_pack_lines<<<unsigned((line_total * 8 + 255) / 256), 256, 0, st>>>(idx->d_start, idx->d_end, idx->d_runmax, idx->d_row,
                                                                           idx->d_meta, n_keys, line_total, d_line_first,
                                                                           d_line_incl, idx->d_lines, d_pstat);
@@ -710,10 +718,10 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
       void* d_t2 = nullptr;
       SQ_CUDA(E, tmp.alloc(&d_t2, tb));
       SQ_CUDA(E, ::sq_cub::cub::DeviceRadixSort::SortKeys(d_t2, tb, d_k0, d_v0, n, 0, end_bit, st));
-      SQ_CUDA(E, cudaMallocAsync(&idx->d_send, n * 4, st));
+      SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_send, n * 4, pool, st));
       k_end_values<<<g, 256, 0, st>>>(d_v0, n, idx->d_send);
       SQ_CUDA(E, cudaGetLastError());
-      SQ_CUDA(E, cudaMallocAsync(&idx->d_emeta, (size_t(n_keys) + 1) * sizeof(SegMeta), st));
+      SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_emeta, (size_t(n_keys) + 1) * sizeof(SegMeta), pool, st));
       k_seg_meta<<<(n_keys + 255) / 256, 256, 0, st>>>(d_seg_off, idx->d_send, n_keys, idx->d_emeta, rows_per_bin);
       SQ_CUDA(E, cudaGetLastError());
       std::vector<SegMeta> h_em(size_t(n_keys) + 1);
@@ -727,7 +735,7 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
       if (edir_total < 0xFFFFFFFFull) {
         h_em[n_keys] = SegMeta{};
         SQ_CUDA(E, cudaMemcpyAsync(idx->d_emeta, h_em.data(), (size_t(n_keys) + 1) * sizeof(SegMeta), cudaMemcpyHostToDevice, st));
-        SQ_CUDA(E, cudaMallocAsync(&idx->d_edir, edir_total * 4, st));
+        SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_edir, edir_total * 4, pool, st));
         k_fill_dir<<<g, 256, 0, st>>>(d_v0, idx->d_send, n, idx->d_emeta, idx->d_edir);
         SQ_CUDA(E, cudaGetLastError());
         SQ_CUDA(E, cudaStreamSynchronize(st));  // h_em must outlive its async copy

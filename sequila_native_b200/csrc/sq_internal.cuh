@@ -146,6 +146,8 @@ struct sq_ctx {
   size_t l2_persist_max = 0;
   sq_options opt;
   sq::ErrorSlot err;
+  std::mutex pool_mu;
+  void* pool = nullptr;  // cudaMemPool_t of this context (sq_build.cu: ctx_pool); destroyed with the context
 };
 
 struct sq_column {

@@ -206,6 +206,9 @@ SQ_HD RowResult parse_row(const Src& src, typename Src::pos_t q, const ScanOpts&
       }
     } else {
       c = src(p);
+      // a skipped field that opens with a quote may hide the delimiter inside it (`id,"a,b",chr1,10,20`): DataFusion's
+      // CSV reader honours quotes, this scanner does not — reject the row instead of shifting its columns
+      if (c == '"' && r.err == kRowOk) r.err = kRowQuoted;
       while (!((c == delim) | (c == '\n') | (c == '\r'))) c = src(++p);
       kind = SQ_END_KIND(c, p);
     }
@@ -264,6 +267,7 @@ SQ_HD RowResult parse_row(const Src& src, typename Src::pos_t q, const ScanOpts&
         }
       }
     } else {
+      if (src(p) == '"' && r.err == kRowOk) r.err = kRowQuoted;  // quoted skipped field: see the fast path above
       for (;; ++p) {
         c = src(p);
         if (SQ_FIELD_ENDS(c, p)) break;

@@ -197,3 +197,18 @@ def test_render_round_trip():
     text = SO.render([names[i] for i in ids], start, end, delimiter=b",", header=b"contig,pos_start,pos_end")
     o = SO.scan_delimited(text, delimiter=b",", has_header=True)
     assert np.array_equal(o["start"], start.astype(np.int32)) and np.array_equal(o["end"], end.astype(np.int32))
+
+
+@pytest.mark.parametrize("text", [b'7,"a,b",chr1,10,20\n', b'id1,x,chr1,10,20\n8,"q",chr2,1,2\n', b'"r",y,chr1,10,20\r\n'])
+def test_quoted_skipped_field_is_rejected_not_shifted(shim, text):
+    """a quoted field BEFORE the named columns may hide the delimiter (`id,"a,b",chr1,10,20`): DataFusion's CSV reader
+    honours quotes; this scanner rejects the row instead of reading shifted columns.  Quotes after the last named column are
+    never looked at."""
+    kw = dict(delimiter=b",", col_key=2, col_start=3, col_end=4)
+    with pytest.raises(SO.ScanError) as eo:
+        SO.scan_delimited(text, **kw)
+    with pytest.raises(SO.ScanError) as eh:
+        host_scan(shim, text, **kw)
+    assert eo.value.kind == eh.value.kind == "parse"
+    ok = b'7,a,chr1,10,20,"trailing, quoted"\n'
+    same(host_scan(shim, ok, **kw), SO.scan_delimited(ok, **kw))
