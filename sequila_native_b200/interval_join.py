@@ -149,6 +149,7 @@ class IntervalJoinExec:
         import os
         self.max_output_rows = int(os.environ.get("SEQUILA_MAX_OUTPUT_ROWS", "1000000"))
         self.device = device
+        self.cuda_options = {}  # sequila.cuda_* keys of the session, applied when the node opens
         self._exec = None
         self._lib = None
         ls, lm = _col_and_minus_one(intervals.left_interval.start, "left start")
@@ -224,6 +225,9 @@ class IntervalJoinExec:
                 lib.sq_exec_free(h)
             raise ExecutionError(msg)
         self._exec = h
+        for k, v in self.cuda_options.items():
+            if lib.sq_exec_set_option(h, k.encode(), str(v).encode()) != N.SQ_OK:
+                raise ExecutionError(self._err())
 
     def close(self):
         if self._exec is not None:
@@ -367,10 +371,13 @@ def optimize(join: HashJoinDesc, config: SequilaConfig, device: int = 0):
     if intervals is None:
         return join  # "Could not build range filter", PP:55-60
     if join.on:      # from_hash_join, PP:105-125
-        return IntervalJoinExec.try_new(join.left_schema, join.right_schema, join.on, join.filter, intervals,
+        node = IntervalJoinExec.try_new(join.left_schema, join.right_schema, join.on, join.filter, intervals,
                                         join.join_type, join.projection, join.partition_mode, join.null_equals_null,
                                         config.interval_join_algorithm, config.interval_join_low_memory, device)
-    # from_nested_loop_join, PP:127-148: on = [(lit(1), lit(1))], no projection, CollectLeft, null_equals_null
-    return IntervalJoinExec.try_new(join.left_schema, join.right_schema, [(Literal(1), Literal(1))], join.filter,
-                                    intervals, join.join_type, None, COLLECT_LEFT, True,
-                                    config.interval_join_algorithm, config.interval_join_low_memory, device)
+    else:
+        # from_nested_loop_join, PP:127-148: on = [(lit(1), lit(1))], no projection, CollectLeft, null_equals_null
+        node = IntervalJoinExec.try_new(join.left_schema, join.right_schema, [(Literal(1), Literal(1))], join.filter,
+                                        intervals, join.join_type, None, COLLECT_LEFT, True,
+                                        config.interval_join_algorithm, config.interval_join_low_memory, device)
+    node.cuda_options = dict(getattr(config, "cuda", {}))
+    return node

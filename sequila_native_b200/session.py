@@ -49,12 +49,22 @@ class Algorithm(enum.Enum):
         return self.value
 
 
+from dataclasses import field  # noqa: E402
+
+# `sequila.cuda_*` keys = the tuning options of the `cuda` algorithm (include/sequila_cuda.h, sq_ctx_set_option); values are
+# validated by the library when the exec node applies them, as ConfigField::set does for the reference's own fields
+CUDA_KEYS = ("cuda_probe_layout", "cuda_staged_probe", "cuda_probe_block", "cuda_lookback_backoff_ns", "cuda_rows_per_bin",
+             "cuda_right_idx_wire", "cuda_l2_persist_mb", "cuda_scan_dict_capacity", "cuda_exec_trace", "cuda_pipeline_depth",
+             "cuda_coalesce_rows", "cuda_rank_count")
+
+
 @dataclass
 class SequilaConfig:
     """SC:50-56.  Keys are addressed as ``sequila.<field>``."""
     prefer_interval_join: bool = True
     interval_join_algorithm: Algorithm = Algorithm.Coitrees
     interval_join_low_memory: bool = False
+    cuda: dict = field(default_factory=dict)  # sequila.cuda_* keys that were SET, applied to the exec node's context
 
     PREFIX = "sequila"
 
@@ -70,6 +80,8 @@ class SequilaConfig:
                 # DataFusion's bool ConfigField: str::parse::<bool>() failure
                 raise ValueError(f"Error parsing {value} as bool")
             setattr(self, key, v == "true")
+        elif key in CUDA_KEYS:
+            self.cuda[key] = value.strip()
         else:
             raise KeyError(f'Config value "{key}" not found on SequilaConfig')
 

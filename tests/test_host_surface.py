@@ -144,3 +144,24 @@ def test_try_new_validation():
     y = IntervalJoinExec.try_new(SCH, SCH, [("contig", "contig")], q1_filter(), ci, partition_mode=AUTO)
     with pytest.raises(PlanError, match="unsupported PartitionMode Auto"):
         y._open()
+
+
+def test_cuda_keys_travel_with_the_session_config():
+    """`SET sequila.cuda_* TO ..` lands in SequilaConfig like the reference's own keys (session_context.rs:50-60, 127-131)
+    and reaches the exec nodes the rule creates; unknown keys are rejected with DataFusion's message"""
+    import pyarrow as pa
+    from sequila_native_b200 import intervals as IV
+    from sequila_native_b200.interval_join import HashJoinDesc, optimize
+    cfg = sn.SequilaConfig()
+    sn.apply_set(cfg, "SET sequila.interval_join_algorithm TO cuda")
+    sn.apply_set(cfg, "SET sequila.cuda_coalesce_rows TO 65536")
+    sn.apply_set(cfg, "set sequila.cuda_probe_layout = 'soa'")
+    assert cfg.cuda == {"cuda_coalesce_rows": "65536", "cuda_probe_layout": "soa"}
+    with pytest.raises(KeyError) as e:
+        sn.apply_set(cfg, "SET sequila.cuda_warp_speed TO 9")
+    assert "not found on SequilaConfig" in str(e.value)
+    cols = ["contig", "pos_start", "pos_end"]
+    sch = pa.schema([("contig", pa.string()), ("pos_start", pa.int32()), ("pos_end", pa.int32())])
+    f = IV.parse_condition_sql("a.pos_start <= b.pos_end AND a.pos_end >= b.pos_start", "a", cols, "b", cols)
+    plan = optimize(HashJoinDesc(sch, sch, [("contig", "contig")], f), cfg)
+    assert plan.cuda_options == cfg.cuda
