@@ -145,9 +145,11 @@ class IntervalJoinExec:
         self.null_equals_null = null_equals_null
         self.algorithm = algorithm
         self.low_memory = low_memory
-        # the reference caps a low-memory output batch at 1M rows (interval_join.rs:1439)
+        # the reference caps a low-memory output batch at 1M rows, overridable with the environment variable
+        # SEQUILA_MAX_OUTPUT_BATCH_SIZE of the HOST process (interval_join.rs:551-555, 1439): same name, same place — the
+        # exec-node mirror; the library itself reads no environment
         import os
-        self.max_output_rows = int(os.environ.get("SEQUILA_MAX_OUTPUT_ROWS", "1000000"))
+        self.max_output_rows = int(os.environ.get("SEQUILA_MAX_OUTPUT_BATCH_SIZE", "1000000"))
         self.device = device
         self.cuda_options = {}  # sequila.cuda_* keys of the session, applied when the node opens
         self._exec = None

@@ -44,7 +44,7 @@ def test_windows_of_the_pair_sequence(cuda_ctx, oracle):
 
 
 def test_exec_low_memory_batches(oracle, monkeypatch):
-    monkeypatch.setenv("SEQUILA_MAX_OUTPUT_ROWS", "700")
+    monkeypatch.setenv("SEQUILA_MAX_OUTPUT_BATCH_SIZE", "700")
     rng = np.random.default_rng(3)
     nb, npq = 3000, 1500
     bs = rng.integers(0, 20000, nb).astype(np.int32); be = (bs + rng.integers(0, 300, nb)).astype(np.int32)
