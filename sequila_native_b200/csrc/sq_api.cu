@@ -434,13 +434,14 @@ namespace sq {
 // same key, non-decreasing start), from a sampling kernel for device tiles; "dense" from the kernel's own report —
 // result[2] = CTAs that could not stage, result[3] = lines staged — backing off exponentially (2, 4, ... 256 tiles).
 bool pick_staged(sq_stream* policy, const sq_index* idx, const uint64_t* host_key, const int32_t* host_start,
-                 const uint64_t* d_key, const int32_t* d_start, uint32_t n, bool emits) {
+                 const uint64_t* d_key, const int32_t* d_start, uint32_t n, bool emits, const uint32_t* host_ids) {
   if (!idx->d_lines || n == 0) return false;
   const int opt = idx->ctx->opt.staged_probe.load(std::memory_order_relaxed);
   if (opt == 1) return true;
   if (opt == 2) return false;
   if (n < 64 || emits) return false;
-  if (!host_key && d_key && d_start) {
+  if (!host_key && !host_ids && !(d_key && d_start)) return false;  // nothing to judge the row order by
+  if (!host_key && !host_ids && d_key && d_start) {
     // device tile (the caller synchronises on the result anyway): one 1024-thread sampling kernel, every 32nd tile
     if (policy->order_age == 0) {
       uint32_t r[2] = {0, 1};
@@ -451,13 +452,14 @@ bool pick_staged(sq_stream* policy, const sq_index* idx, const uint64_t* host_ke
     policy->order_age -= 1;
     if (!policy->order_local) return false;
   }
-  if (host_key && host_start) {
+  if ((host_key || host_ids) && host_start) {
     const uint32_t m = n - 1 < 1024u ? n - 1 : 1024u;
     const uint32_t stride = (n - 1) / m;
     uint32_t ordered = 0;
     for (uint32_t k = 0; k < m; ++k) {
       const size_t a = size_t(k) * stride;
-      ordered += (host_key[a] == host_key[a + 1] && host_start[a] <= host_start[a + 1]) ? 1u : 0u;
+      const bool same = host_key ? host_key[a] == host_key[a + 1] : host_ids[a] == host_ids[a + 1];
+      ordered += (same && host_start[a] <= host_start[a + 1]) ? 1u : 0u;
     }
     if (ordered * 8u < m * 7u) return false;  // not position-ordered: do not even try
   }

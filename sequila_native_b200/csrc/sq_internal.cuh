@@ -355,7 +355,7 @@ uint32_t staged_tile_rows();
 // api.cu: adaptive choice between the two (option cuda_staged_probe; `policy` = the stream that keeps the statistics,
 // `host_key` / `host_start` = the tile's host columns when the caller has them: a cheap look at their order)
 bool pick_staged(sq_stream* policy, const sq_index* idx, const uint64_t* host_key, const int32_t* host_start,
-                 const uint64_t* d_key, const int32_t* d_start, uint32_t n, bool emits);
+                 const uint64_t* d_key, const int32_t* d_start, uint32_t n, bool emits, const uint32_t* host_ids = nullptr);
 // probe_staged.cu: samples up to 1024 adjacent row pairs of a device tile: {pairs with equal key and non-decreasing
 // start, pairs looked at} (synchronises the stream: device entry points only)
 int sample_order_device(sq_stream* s, const uint64_t* d_key, const int32_t* d_start, uint32_t n, uint32_t out2[2]);

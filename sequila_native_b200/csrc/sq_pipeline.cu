@@ -178,7 +178,7 @@ static int32_t submit_tile(sq_stream* s, const sq_index* idx, const uint64_t* ke
     uint32_t* d_right = want_right ? static_cast<uint32_t*>(sub->d_right.p) : nullptr;
     sl->staged = false;
     if (use_packed(idx)) {
-      sl->staged = pick_staged(s, idx, host_key, host_key ? start : nullptr, nullptr, nullptr, n_rows, d_left != nullptr);
+      sl->staged = pick_staged(s, idx, host_key, start, nullptr, nullptr, n_rows, d_left != nullptr, key_id);
       if ((rc = launch_packed_any(sub, s, sl->staged, idx, dk, ds, de, n_rows, d_left, d_right, dev_cap)))
         return fail(E, rc, "%s", sub->err.msg.c_str());
     } else if (use_rank(idx)) {
