@@ -114,6 +114,8 @@ static int32_t submit_tile(sq_stream* s, const sq_index* idx, const uint64_t* ke
   if (!idx || !ticket_out) return fail(E, SQ_EINVAL, "null index or ticket pointer");
   if (n_rows && ((!key_hash && !key_id) || !start || !end)) return fail(E, SQ_EINVAL, "null probe column");
   if (key_id && !s->d_dict.p) return fail(E, SQ_ESTATE, "sq_stream_submit_ids without sq_stream_set_key_dictionary");
+  if (flags & ~(SQ_TILE_COUNT_ONLY | SQ_TILE_RIGHT_IDX | SQ_TILE_EXPAND_RIGHT | SQ_TILE_NO_COUNTS))
+    return fail(E, SQ_EINVAL, "unknown tile flag bits 0x%x", flags);
   if (idx->ctx->device != s->ctx->device)
     return fail(E, SQ_EINVAL, "index lives on device %d, stream on %d", idx->ctx->device, s->ctx->device);
   SQ_CUDA(E, cudaSetDevice(s->ctx->device));

@@ -105,6 +105,9 @@ def test_pipeline_survives_fanout_jumps_and_empty_tiles(cuda_ctx, oracle):
     with pytest.raises(sn.SequilaCudaError) as e:  # a fourth tile does not fit the default depth of 3
         st.submit(idx, pieces[0]["key"], pieces[0]["start"], pieces[0]["end"])
     assert e.value.code == N.SQ_EBUSY
+    with pytest.raises(sn.SequilaCudaError) as e:  # flag bits the library does not know
+        sn.CudaStream(cuda_ctx).submit(idx, pieces[0]["key"], pieces[0]["start"], pieces[0]["end"], flags=64)
+    assert e.value.code == N.SQ_EINVAL
     with pytest.raises(sn.SequilaCudaError) as e:  # tiles are collected in submission order
         st.collect(tickets[1])
     assert e.value.code == N.SQ_ESTATE
