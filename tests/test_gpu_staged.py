@@ -157,3 +157,32 @@ def test_adaptive_kernel_choice(cuda_ctx, oracle):
                 assert np.array_equal(canon(left.cpu().numpy().view(np.uint32), right.cpu().numpy().view(np.uint32)), canon(wl, wr))
     finally:
         cuda_ctx.set_option("cuda_probe_layout", "auto")
+
+
+def test_count_only_tiles_in_auto_mode(cuda_ctx, oracle):
+    """option auto: count-only launches of position-sorted dense tiles go to the staged kernel (host tiles through the
+    pipeline, device tiles through sq_probe_count_device); the per-row counts equal the oracle's either way"""
+    cuda_ctx.set_option("cuda_probe_layout", "packed")
+    try:
+        b, p = sn.synth.cfg5(scale=0.004)
+        q = sort_side(p)
+        idx = sn.CudaIndex.build(cuda_ctx, b["key"], b["start"], b["end"])
+        want = oracle.OracleIndex(b["key"], b["start"], b["end"]).counts(q["key"], q["start"], q["end"])
+        st = sn.CudaStream(cuda_ctx)
+        cols = {k: cuda_ctx.pinned_copy(q[k]) for k in ("key", "start", "end")}
+        cuts = np.linspace(0, len(want), 6).astype(np.int64)
+        got = []
+        for a, z in zip(cuts, cuts[1:]):
+            t = st.submit(idx, cols["key"][a:z], cols["start"][a:z], cols["end"][a:z], N.TILE_COUNT_ONLY)
+            n, left, right, counts = st.collect(t)
+            assert left is None and n == int(want[a:z].sum())
+            got.append(counts.copy())
+        assert np.array_equal(np.concatenate(got), want)
+        dev = torch.device("cuda", 0)
+        d = {k: torch.from_numpy(q[k].view(np.int64) if k == "key" else q[k]).to(dev) for k in ("key", "start", "end")}
+        st2 = sn.CudaStream(cuda_ctx, cuda_stream=torch.cuda.current_stream().cuda_stream)
+        for _ in range(3):
+            assert st2.probe_count_device(idx, d["key"], d["start"], d["end"]) == int(want.sum())
+            assert np.array_equal(st2.counts(), want)
+    finally:
+        cuda_ctx.set_option("cuda_probe_layout", "auto")
