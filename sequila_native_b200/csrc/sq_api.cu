@@ -143,7 +143,7 @@ const OptDesc kOpts[] = {
     {"cuda_probe_layout", &sq_options::probe_layout, 0, 2, kLayoutWords},
     {"cuda_probe_block", &sq_options::probe_block, 64, 256, nullptr},
     {"cuda_lookback_backoff_ns", &sq_options::lookback_backoff_ns, 0, 1 << 20, nullptr},
-    {"cuda_rows_per_bin", &sq_options::rows_per_bin, 1, 1024, nullptr},
+    {"cuda_rows_per_bin", &sq_options::rows_per_bin, 0, 1024, nullptr},
     {"cuda_right_idx_wire", &sq_options::right_idx_wire, 0, 1, kWireWords},
     {"cuda_staged_probe", &sq_options::staged_probe, 0, 2, kStagedWords},
     {"cuda_scan_dict_capacity", &sq_options::scan_dict_capacity, 4, 1 << 30, nullptr},

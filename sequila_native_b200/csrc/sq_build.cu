@@ -622,7 +622,8 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     }
 
     // 4. per-segment bin directory (geometry on the device, offsets by a host scan: #keys is small)
-    const uint32_t rows_per_bin = uint32_t(ctx->opt.rows_per_bin.load(std::memory_order_relaxed));
+    uint32_t rows_per_bin = uint32_t(ctx->opt.rows_per_bin.load(std::memory_order_relaxed));
+    if (rows_per_bin == 0) rows_per_bin = n <= (4u << 20) ? 1u : 8u;
     k_seg_meta<<<(n_keys + 255) / 256, 256, 0, st>>>(d_seg_off, idx->d_start, n_keys, idx->d_meta,
                                                      rows_per_bin);
     SQ_CUDA(E, cudaGetLastError());

@@ -126,7 +126,9 @@ struct sq_options {
   std::atomic<int> probe_layout{0};         // 0 auto, 1 packed lines (when the index has them), 2 SoA arrays
   std::atomic<int> probe_block{128};        // rows per CTA of the packed-line kernels: 64 / 128 / 256
   std::atomic<int> lookback_backoff_ns{64}; // sleep between polls of a predecessor's chained-scan word
-  std::atomic<int> rows_per_bin{8};         // build: target rows per directory bin
+  std::atomic<int> rows_per_bin{0};         // build: target rows per directory bin; 0 = 8, or 1 for indexes of up to 4M rows (the
+                                            // directory then costs 4 B per row of a cache-resident index and every in-bin search
+                                            // is shorter: cfg3 1.32 -> 1.27 ms, profiles/r02_subcfg_rows_per_bin_sweep.txt)
   std::atomic<int> right_idx_wire{0};       // host entry points: 0 = per-row counts cross PCIe and right_idx is expanded on
                                             // the host (IJ:1611-1618), 1 = right_idx itself is copied
   std::atomic<int> staged_probe{0};         // 0 auto (adaptive per stream), 1 always try the staged kernel, 2 never
