@@ -326,3 +326,31 @@ def test_null_keys_and_null_coordinates():
     with pytest.raises(ExecutionError) as e:
         run_join(bad, right, Q1)
     assert "NULL" in str(e.value)
+
+
+def test_concurrent_partitions_of_one_node_with_coalescing(oracle):
+    """four host threads drive four partitions of ONE exec node (one sq_stream each, one shared index), each coalescing its
+    own 4096-row batches: the union of their output rows is the oracle's join"""
+    import concurrent.futures as cf
+    b, p = sn.synth.cfg5(scale=0.002)
+    names = np.array(sn.synth.CONTIG_NAMES)
+    left = pa.record_batch([pa.array(names[b["contig"]]), pa.array(b["start"]), pa.array(b["end"])], names=COLS)
+    right = pa.record_batch([pa.array(names[p["contig"]]), pa.array(p["start"]), pa.array(p["end"])], names=COLS)
+    batches = [right.slice(i, 4096) for i in range(0, right.num_rows, 4096)]
+    f = IV.parse_condition_sql(Q1, "a", COLS, "b", COLS)
+    plan = optimize(HashJoinDesc(left.schema, right.schema, [("contig", "contig")], f), cuda_config())
+    plan.set_option("sequila.cuda_coalesce_rows", 30000)
+    plan.collect_build([left])
+    P = 4
+
+    def drive(part):
+        return rows_of(list(plan.probe_batches(batches[part::P], partition=part)))
+    with cf.ThreadPoolExecutor(P) as pool:
+        got = [r for rows in pool.map(drive, range(P)) for r in rows]
+    ol, orr, _ = oracle.join(b["key"], b["start"], b["end"], p["key"], p["start"], p["end"])
+    want = sorted(zip(names[b["contig"]][ol].tolist(), b["start"][ol].tolist(), b["end"][ol].tolist(),
+                      names[p["contig"]][orr].tolist(), p["start"][orr].tolist(), p["end"][orr].tolist()))
+    assert sorted(tuple(r) for r in got) == want
+    m = plan.metrics()
+    assert m.input_rows == right.num_rows and m.output_rows == len(want)
+    plan.close()
