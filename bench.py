@@ -434,11 +434,11 @@ def e2e_pipeline(sn, ctx, idx, probe_h, n_pairs_expect, args, T, flags, steps, b
         assert one_pass()["n_pairs"] == n_pairs_expect
     barrier()
     e0 = time.perf_counter()
-    agg = {"h2d_ms": 0.0, "kernel_ms": 0.0, "d2h_ms": 0.0, "tiles": 0, "regrown": 0, "native_seconds": 0.0}
+    agg = {"h2d_ms": 0.0, "kernel_ms": 0.0, "d2h_ms": 0.0, "tiles": 0, "regrown": 0, "native_seconds": 0.0, "d2h_bytes": 0, "h2d_bytes": 0}
     for _ in range(steps):
         r = one_pass()
         for k, f in (("h2d_ms", "h2d_ms"), ("kernel_ms", "kernel_ms"), ("d2h_ms", "d2h_ms"), ("tiles", "n_tiles"),
-                     ("regrown", "regrown_tiles"), ("native_seconds", "seconds")):
+                     ("regrown", "regrown_tiles"), ("native_seconds", "seconds"), ("d2h_bytes", "d2h_bytes"), ("h2d_bytes", "h2d_bytes")):
             agg[k] += r[f]
     ms = (time.perf_counter() - e0) * 1e3 / steps
     return ms, n_tiles, digest, agg
@@ -879,6 +879,9 @@ def main():
                       "index_bytes": index_bytes, "keys": idx.keys},
             "e2e": {"value": e2e_value, "unit": "probe intervals/s", "h2d_bytes_per_step": 16 * e2e_rows,
                     "d2h_bytes_per_step": 4 * e_pairs + 4 * e2e_rows + 16 * n_tiles,
+                    # what the pipeline really moved (the speculative copy-out of a tile is sized 2 % above the previous
+                    # tile's fan-out: a little more than the pairs there are)
+                    "d2h_bytes_moved_per_step": e_stats["d2h_bytes"] // max(args.e2e_steps, 1),
                     "wire": "in: key hash u64 + start/end i32 per probe row; out: left_idx u32 per pair + per-row counts u32 "
                             "(= rle_right, interval_join.rs:1604; right_idx is their run-length expansion and does not cross PCIe)",
                     "ms_per_step": e_ms_max, "rows_per_step_per_gpu": e2e_rows, "steps": args.e2e_steps,
