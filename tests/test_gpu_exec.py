@@ -354,3 +354,38 @@ def test_concurrent_partitions_of_one_node_with_coalescing(oracle):
     m = plan.metrics()
     assert m.input_rows == right.num_rows and m.output_rows == len(want)
     plan.close()
+
+
+def test_parquet_tables_through_the_exec_node(golden, oracle, tmp_path):
+    """The reference's benchmarks read Parquet (benches/databio_benchmark.rs:278-283).  Parquet is decoded by the host's
+    Arrow reader — as DataFusion's ParquetExec does — and the RecordBatches it yields (dictionary-encoded contig column,
+    row groups = batches) go through the exec node: the fixture tables give the reference's 16 rows, a cfg5-shaped pair of
+    files the oracle's rows.  (A device-side Parquet decoder is out of scope)"""
+    import pyarrow.parquet as pq
+    reads, targets = table(golden["reads"], pa.int64()), table(golden["targets"], pa.int64())
+    pq.write_table(pa.Table.from_batches([reads]), tmp_path / "reads.parquet", use_dictionary=["contig"])
+    pq.write_table(pa.Table.from_batches([targets]), tmp_path / "targets.parquet", use_dictionary=["contig"])
+    lt = pq.read_table(tmp_path / "reads.parquet", read_dictionary=["contig"])
+    rt = pq.read_table(tmp_path / "targets.parquet", read_dictionary=["contig"])
+    f = IV.parse_condition_sql(Q1, "a", COLS, "b", COLS)
+    plan = optimize(HashJoinDesc(lt.schema, rt.schema, [("contig", "contig")], f), cuda_config())
+    out = list(plan.execute(lt.to_batches(), rt.to_batches()))
+    assert sort_rows(rows_of(out)) == sort_rows(golden["equi_rows"])
+    plan.close()
+
+    b, p = sn.synth.cfg5(scale=0.001)
+    names = np.array(sn.synth.CONTIG_NAMES)
+    for name, side in (("b", b), ("p", p)):
+        t = pa.table([pa.array(names[side["contig"]]), pa.array(side["start"]), pa.array(side["end"])], names=COLS)
+        pq.write_table(t, tmp_path / f"{name}.parquet", row_group_size=8192, use_dictionary=["contig"])
+    lt = pq.ParquetFile(tmp_path / "b.parquet")
+    rt = pq.ParquetFile(tmp_path / "p.parquet")
+    lb = list(lt.iter_batches(batch_size=8192, read_dictionary=["contig"]))
+    rb = list(rt.iter_batches(batch_size=8192, read_dictionary=["contig"]))
+    plan = optimize(HashJoinDesc(lb[0].schema, rb[0].schema, [("contig", "contig")], f), cuda_config())
+    got = sorted(tuple(r) for r in rows_of(list(plan.execute(lb, rb))))
+    ol, orr, _ = oracle.join(b["key"], b["start"], b["end"], p["key"], p["start"], p["end"])
+    want = sorted(zip(names[b["contig"]][ol].tolist(), b["start"][ol].tolist(), b["end"][ol].tolist(),
+                      names[p["contig"]][orr].tolist(), p["start"][orr].tolist(), p["end"][orr].tolist()))
+    assert got == want
+    plan.close()
