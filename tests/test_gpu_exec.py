@@ -378,10 +378,10 @@ def test_parquet_tables_through_the_exec_node(golden, oracle, tmp_path):
     for name, side in (("b", b), ("p", p)):
         t = pa.table([pa.array(names[side["contig"]]), pa.array(side["start"]), pa.array(side["end"])], names=COLS)
         pq.write_table(t, tmp_path / f"{name}.parquet", row_group_size=8192, use_dictionary=["contig"])
-    lt = pq.ParquetFile(tmp_path / "b.parquet")
-    rt = pq.ParquetFile(tmp_path / "p.parquet")
-    lb = list(lt.iter_batches(batch_size=8192, read_dictionary=["contig"]))
-    rb = list(rt.iter_batches(batch_size=8192, read_dictionary=["contig"]))
+    lt = pq.ParquetFile(tmp_path / "b.parquet", read_dictionary=["contig"])
+    rt = pq.ParquetFile(tmp_path / "p.parquet", read_dictionary=["contig"])
+    lb = list(lt.iter_batches(batch_size=8192))
+    rb = list(rt.iter_batches(batch_size=8192))
     plan = optimize(HashJoinDesc(lb[0].schema, rb[0].schema, [("contig", "contig")], f), cuda_config())
     got = sorted(tuple(r) for r in rows_of(list(plan.execute(lb, rb))))
     ol, orr, _ = oracle.join(b["key"], b["start"], b["end"], p["key"], p["start"], p["end"])
