@@ -72,8 +72,16 @@ uint64_t pipeline_bytes(const sq_stream* s) {
 
 }  // namespace sq
 
+static int32_t pipeline_init_slots(sq_stream* s);
+
 static int32_t pipeline_init(sq_stream* s) {
   if (!s->slots.empty()) return SQ_OK;
+  const int32_t rc = pipeline_init_slots(s);
+  if (rc != SQ_OK) pipeline_destroy(s);  // never leave half-built slots behind: the next submit starts over
+  return rc;
+}
+
+static int32_t pipeline_init_slots(sq_stream* s) {
   ErrorSlot& E = s->err;
   SQ_CUDA(E, cudaStreamCreateWithFlags(&s->stream_in, cudaStreamNonBlocking));
   SQ_CUDA(E, cudaStreamCreateWithFlags(&s->stream_out, cudaStreamNonBlocking));
