@@ -134,6 +134,19 @@ static int32_t submit_tile(sq_stream* s, const sq_index* idx, const uint64_t* ke
     return fail(E, SQ_EBUSY, "%zu tiles in flight: collect ticket %llu first", depth, (unsigned long long)s->oldest_ticket);
   sq_tile_slot* sl = s->slots[s->next_ticket % depth];
   sq_stream* sub = sl->sub;
+  // a call that fails half-way may have enqueued work on this slot's buffers: drain the streams before the slot can be
+  // handed out again (the slot is only marked busy on success)
+  struct Drain {
+    sq_stream* s;
+    bool armed;
+    ~Drain() {
+      if (!armed) return;
+      cudaStreamSynchronize(s->stream_in);
+      cudaStreamSynchronize(s->stream);
+      cudaStreamSynchronize(s->stream_out);
+      cudaGetLastError();
+    }
+  } drain{s, true};
   const bool count_only = (flags & SQ_TILE_COUNT_ONLY) != 0;
   const bool want_right = !count_only && (flags & SQ_TILE_RIGHT_IDX) != 0;
   const size_t n = n_rows;
@@ -213,6 +226,7 @@ static int32_t submit_tile(sq_stream* s, const sq_index* idx, const uint64_t* ke
     }
     SQ_CUDA(E, cudaEventRecord(sl->ev[5], s->stream_out));
   }
+  drain.armed = false;
   sl->busy = true;
   sl->ticket = s->next_ticket++;
   sl->key_bytes = key_id ? 4 : 8;
