@@ -31,7 +31,9 @@ constexpr int kRWarps = kRB / 32;
 // candidates for finding each candidate's row and its position); longer rows take the whole warp, one row after the
 // other, 32 candidates per step (~15 instructions per step, but the steps of a warp's rows are dependent load -> ballot
 // round trips in sequence).  Measured on cfg3 (24 candidates per row): flattening up to 32 candidates 1.51 ms, up to 8
-// candidates 1.75 ms.
+// candidates 1.75 ms.  Taking four steps at a time (all end[] loads, then the ballots, then all row[] loads, then the stores:
+// two L2 round trips per group instead of per step) was measured too: cfg4 0.48-0.51 ms instead of 0.38-0.40 ms, cfg3 1.53
+// instead of 1.51 ms — 61 registers instead of 48 and the guards of partial groups cost more than the shorter chains save.
 #ifndef SQ_RANK_FLAT_MAX
 #define SQ_RANK_FLAT_MAX 32
 #endif
