@@ -828,8 +828,17 @@ int assemble_output(sq_exec* e, sq_stream* st, const ArrowArray* batch, uint64_t
       uint64_t pbytes = 0;
       if (side == 1) {
         poff.resize(size_t(n) + 1);
-        if (t.kind == Kind::Utf8) { const int32_t* o = reinterpret_cast<const int32_t*>(pv.values) + pv.offset; for (uint64_t i = 0; i <= n; ++i) poff[i] = o[i] - o[0]; pdata = pv.data + o[0]; pbytes = uint64_t(o[n] - o[0]); }
-        else { const int64_t* o = reinterpret_cast<const int64_t*>(pv.values) + pv.offset; for (uint64_t i = 0; i <= n; ++i) poff[i] = o[i] - o[0]; pdata = pv.data + o[0]; pbytes = uint64_t(o[n] - o[0]); }
+        if (t.kind == Kind::Utf8) {
+          const int32_t* o = reinterpret_cast<const int32_t*>(pv.values) + pv.offset;
+          parallel_rows(int64_t(n) + 1, [&](int64_t lo, int64_t hi) { for (int64_t i = lo; i < hi; ++i) poff[size_t(i)] = o[i] - o[0]; });
+          pdata = pv.data + o[0];
+          pbytes = uint64_t(o[n] - o[0]);
+        } else {
+          const int64_t* o = reinterpret_cast<const int64_t*>(pv.values) + pv.offset;
+          parallel_rows(int64_t(n) + 1, [&](int64_t lo, int64_t hi) { for (int64_t i = lo; i < hi; ++i) poff[size_t(i)] = o[i] - o[0]; });
+          pdata = pv.data + o[0];
+          pbytes = uint64_t(o[n] - o[0]);
+        }
       }
       void* off32 = pinned((size_t(n_pairs) + 1) * 4);
       if (!off32) return e->fail(SQ_ENOMEM, "pinned allocation failed");
@@ -1072,17 +1081,26 @@ int concat_batches(sq_exec* e, const Side& side, const std::vector<ArrowArray>& 
       co->heap.push_back(off);
       co->heap.push_back(data);
       uint64_t r = 0, at = 0;
-      for (const ArrowArray& b : batches) {
+      for (const ArrowArray& b : batches) {  // per batch: ONE copy of its byte range, offsets rebased in a plain loop
         const ColView v = view_of(&b, int32_t(c));
         note_nulls(v, r);
-        for (int64_t i = 0; i < v.length; ++i, ++r) {
-          int64_t a, z;
-          if (large) { const int64_t* o = reinterpret_cast<const int64_t*>(v.values) + v.offset; a = o[i]; z = o[i + 1]; }
-          else { const int32_t* o = reinterpret_cast<const int32_t*>(v.values) + v.offset; a = o[i]; z = o[i + 1]; }
-          if (large) static_cast<int64_t*>(off)[r] = int64_t(at); else static_cast<int32_t*>(off)[r] = int32_t(at);
-          if (z > a) memcpy(data + at, v.data + a, size_t(z - a));
-          at += uint64_t(z - a);
+        if (!v.length) continue;
+        if (large) {
+          const int64_t* o = reinterpret_cast<const int64_t*>(v.values) + v.offset;
+          const int64_t base = o[0];
+          memcpy(data + at, v.data + base, size_t(o[v.length] - base));
+          auto* dst = static_cast<int64_t*>(off) + r;
+          for (int64_t i = 0; i < v.length; ++i) dst[i] = int64_t(at) + (o[i] - base);
+          at += uint64_t(o[v.length] - base);
+        } else {
+          const int32_t* o = reinterpret_cast<const int32_t*>(v.values) + v.offset;
+          const int32_t base = o[0];
+          memcpy(data + at, v.data + base, size_t(o[v.length] - base));
+          auto* dst = static_cast<int32_t*>(off) + r;
+          for (int64_t i = 0; i < v.length; ++i) dst[i] = int32_t(at) + (o[i] - base);
+          at += uint64_t(o[v.length] - base);
         }
+        r += uint64_t(v.length);
       }
       if (large) static_cast<int64_t*>(off)[n] = int64_t(at); else static_cast<int32_t*>(off)[n] = int32_t(at);
       co->buffers = {validity, off, data};
@@ -1158,8 +1176,10 @@ SQ_API int32_t sq_exec_probe_pop(sq_exec* e, int32_t partition, int32_t flush, A
   ArrowArray joined{};
   const ArrowArray* tile = &take.batches[0];
   if (take.batches.size() > 1) {
+    Trace tr(e->ctx);
     if ((rc = concat_batches(e, e->right, take.batches, &joined))) return rc;
     tile = &joined;
+    tr.lap("concat batches");
   }
   uint64_t n_pairs = 0;
   rc = probe_on_device(e, st, tile, &n_pairs);
