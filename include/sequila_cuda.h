@@ -56,6 +56,7 @@ int32_t sq_device_count(void);
  *   cuda_probe_layout         auto | packed | soa   which probe kernels serve an index that has both layouts
  *   cuda_staged_probe         auto | on | off       shared-memory (TMA) staged kernel for position-local probe tiles
  *   cuda_probe_block          64 | 128 | 256        probe rows per CTA of the packed-line kernels
+ *   cuda_probe_tiles          1 | 2                 tiles per CTA of an emitting packed-line launch (default 1; 2 measured slower)
  *   cuda_lookback_backoff_ns  integer               sleep between polls of the chained scan's look-back
  *   cuda_rows_per_bin         0..1024               build: target rows per directory bin (0 = automatic: 1 up to 4M rows, else 8)
  *   cuda_right_idx_wire       rle | copy            host entry points: right_idx crosses PCIe as per-row counts (default)

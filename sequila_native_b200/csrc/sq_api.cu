@@ -142,6 +142,7 @@ const char* const kOnOffWords[] = {"off", "on", "force", nullptr};
 const OptDesc kOpts[] = {
     {"cuda_probe_layout", &sq_options::probe_layout, 0, 2, kLayoutWords},
     {"cuda_probe_block", &sq_options::probe_block, 64, 256, nullptr},
+    {"cuda_probe_tiles", &sq_options::probe_tiles, 1, 2, nullptr},
     {"cuda_lookback_backoff_ns", &sq_options::lookback_backoff_ns, 0, 1 << 20, nullptr},
     {"cuda_rows_per_bin", &sq_options::rows_per_bin, 0, 1024, nullptr},
     {"cuda_right_idx_wire", &sq_options::right_idx_wire, 0, 1, kWireWords},

@@ -124,6 +124,7 @@ struct HostPool {
 // while partitions probe on others; every reader takes one consistent value per call.
 struct sq_options {
   std::atomic<int> probe_layout{0};         // 0 auto, 1 packed lines (when the index has them), 2 SoA arrays
+  std::atomic<int> probe_tiles{1};          // tiles per CTA of an emitting packed-line launch: 1 / 2
   std::atomic<int> probe_block{128};        // rows per CTA of the packed-line kernels: 64 / 128 / 256
   std::atomic<int> lookback_backoff_ns{64}; // sleep between polls of a predecessor's chained-scan word
   std::atomic<int> rows_per_bin{0};         // build: target rows per directory bin; 0 = 8, or 1 for indexes of up to 4M rows (the

@@ -38,16 +38,17 @@ namespace sq {
 #define SQ_PACKED_THREADS_PER_SM 1024  // resident threads per SM the kernel is compiled for (register budget)
 #endif
 template <bool EMIT, bool WRITE_RIGHT, int kPBlock, int kTiles>
-__global__ void __launch_bounds__(kPBlock, SQ_PACKED_THREADS_PER_SM / kPBlock)
+__global__ void __launch_bounds__(kPBlock, (EMIT && kTiles > 1 ? 768 : SQ_PACKED_THREADS_PER_SM) / kPBlock)
 k_probe_packed(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* __restrict__ q_start,
                const int32_t* __restrict__ q_end, uint32_t n, uint32_t* __restrict__ cnt_out,
                unsigned long long* chain_state, unsigned int* ticket, unsigned long long* result,
                uint32_t* __restrict__ left_out, uint32_t* __restrict__ right_out, uint64_t capacity,
                uint32_t n_tiles, uint32_t backoff_ns) {
   constexpr int kPWarps = kPBlock / 32;
-  __shared__ uint32_t s_stash[EMIT ? kPWarps * 32 * kStride : 1];
-  __shared__ unsigned long long s_wtot[2][kPWarps];
-  __shared__ unsigned long long s_base[2];
+  constexpr int kStashRow = kPWarps * 32 * kStride;  // one tile's stash: every tile of the CTA keeps its own until the emit
+  __shared__ uint32_t s_stash[EMIT ? kTiles * kStashRow : 1];
+  __shared__ unsigned long long s_wtot[kTiles][kPWarps];
+  __shared__ unsigned long long s_base[kTiles];
   __shared__ uint32_t s_bid;
   __shared__ __align__(8) uint8_t s_inv[kPWarps][32];
   __shared__ WalkShared s_walk[kPWarps];
@@ -86,64 +87,84 @@ k_probe_packed(IndexView iv, const uint64_t* __restrict__ q_key, const int32_t* 
     }
   }
 
+  // ---- phase 2 of every tile: walk in compacted rounds (sq_packed_common.cuh) --------------------------
+  // All walks come before any look-back: the CTA publishes the totals of ALL its tiles at once, so a later
+  // CTA never waits for this one's stores (walking tile 2b+1 only after emitting tile 2b serialised the grid).
+  uint32_t t_cnt[kTiles], t_cincl[kTiles];
 #pragma unroll
   for (int t = 0; t < kTiles; ++t) {
-    const uint32_t tile = bid * kTiles + t;
-    if (tile >= n_tiles) break;  // CTA-uniform
-    const uint64_t i = uint64_t(tile) * kPBlock + threadIdx.x;
-    const uint32_t tile_first = tile * kPBlock + warp * 32;
-    const int32_t my_qs = t_qs[t], my_qe = t_qe[t];
-    const StartLine sl = t_sl[t];
-
-    // ---- phase 2: walk in compacted rounds (sq_packed_common.cuh) ---------------------------------
-    uint32_t* stash = s_stash + (EMIT ? warp * 32 * kStride : 0);
-    bool walking = sl.act;
-    uint32_t ln = sl.line;  // next line of my row
-    uint32_t cnt = 0;       // hits of my row so far
-    walk_rounds<EMIT>(iv, stash, s_walk[warp], my_qs, my_qe, sl.first, walking, ln, cnt);
+    const uint64_t i = (uint64_t(bid) * kTiles + t) * kPBlock + threadIdx.x;  // rows past n / tiles past n_tiles: not walking
+    uint32_t* stash = s_stash + (EMIT ? t * kStashRow + warp * 32 * kStride : 0);
+    bool walking = t_sl[t].act;
+    uint32_t ln = t_sl[t].line;  // next line of my row
+    uint32_t cnt = 0;            // hits of my row so far
+    walk_rounds<EMIT>(iv, stash, s_walk[warp], t_qs[t], t_qe[t], t_sl[t].first, walking, ln, cnt);
     if (i < n) cnt_out[i] = cnt;  // rle_right (interval_join.rs:1604)
-
-    const uint32_t cincl = warp_incl_sum(cnt);  // a warp emits < 2^32 pairs unless rows hit > 2^27 builds each
-    const uint32_t wtot = __shfl_sync(0xffffffffu, cincl, 31);
-    const int buf = t & 1;  // totals of consecutive tiles alternate buffers: one barrier separates reuse
-    if (lane == 0) s_wtot[buf][warp] = wtot;
-    __syncthreads();
-    if (!EMIT) {  // count only: the grand total is order-free; one atomic per CTA and tile (same-address
-                  // atomics serialise at ~2.5 ns each: one per warp would cost 1 ms per 12.5M rows by itself)
-      if (threadIdx.x == 0) {
-        unsigned long long tot = 0;
+    t_cnt[t] = cnt;
+    t_cincl[t] = warp_incl_sum(cnt);  // a warp emits < 2^32 pairs unless rows hit > 2^27 builds each
+    const uint32_t wtot = __shfl_sync(0xffffffffu, t_cincl[t], 31);
+    if (lane == 0) s_wtot[t][warp] = wtot;
+  }
+  __syncthreads();
+  if (!EMIT) {  // count only: the grand total is order-free; one atomic per CTA (same-address atomics
+                // serialise at ~2.5 ns each: one per warp would cost 1 ms per 12.5M rows by itself)
+    if (threadIdx.x == 0) {
+      unsigned long long tot = 0;
 #pragma unroll
-        for (int w = 0; w < kPWarps; ++w) tot += s_wtot[buf][w];
-        if (tot) atomicAdd(result, tot);
-      }
-      continue;
-    }
-
-    // ---- phase 3: CTA total -> chained scan ---------------------------------------------------------
-    if (warp == 0) {
-      unsigned long long agg = 0;
+      for (int t = 0; t < kTiles; ++t)
 #pragma unroll
-      for (int w = 0; w < kPWarps; ++w) agg += s_wtot[buf][w];
-      const unsigned long long excl = chain_lookback(chain_state, tile, agg, backoff_ns);
-      if (lane == 0) {
-        s_base[buf] = excl;
-        if (tile == n_tiles - 1) result[0] = excl + agg;
-        if (excl + agg > capacity) result[1] = 1;  // the caller's buffers are too small: report, write nothing here
+        for (int w = 0; w < kPWarps; ++w) tot += s_wtot[t][w];
+      if (tot) atomicAdd(result, tot);
+    }
+    return;
+  }
+
+  // ---- phase 3: tile totals -> chained scan ------------------------------------------------------------
+  const uint32_t tile0 = bid * kTiles;
+  if (warp == 0) {
+    unsigned long long agg[kTiles];
+#pragma unroll
+    for (int t = 0; t < kTiles; ++t) {
+      agg[t] = 0;
+#pragma unroll
+      for (int w = 0; w < kPWarps; ++w) agg[t] += s_wtot[t][w];
+    }
+    // later tiles of this CTA first, as aggregates: a successor's look-back passes over them at once
+#pragma unroll
+    for (int t = 1; t < kTiles; ++t)
+      if (lane == 0 && tile0 + t < n_tiles) atomicExch(chain_state + tile0 + t, kFlagAgg | agg[t]);
+    unsigned long long run = chain_lookback(chain_state, tile0, agg[0], backoff_ns);
+    if (lane == 0) {
+#pragma unroll
+      for (int t = 0; t < kTiles; ++t) {
+        if (tile0 + t >= n_tiles) break;
+        s_base[t] = run;
+        run += agg[t];
+        if (t > 0) atomicExch(chain_state + tile0 + t, kFlagInc | run);
+        if (tile0 + t == n_tiles - 1) result[0] = run;
+        if (run > capacity) result[1] = 1;  // the caller's buffers are too small: report, write nothing here
       }
     }
-    __syncthreads();
-    uint64_t base = s_base[buf];
+  }
+  __syncthreads();
+  // ---- phase 4: ordered emit (stash -> flattened coalesced stores; rows with > 32 hits re-walked) -------
+#pragma unroll
+  for (int t = 0; t < kTiles; ++t) {
+    if (tile0 + t >= n_tiles) break;  // CTA-uniform
+    const uint32_t tile_first = (tile0 + t) * kPBlock + warp * 32;
+    uint64_t base = s_base[t];
     unsigned long long cta_tot = 0;
 #pragma unroll
     for (int w = 0; w < kPWarps; ++w) {
-      if (w < warp) base += s_wtot[buf][w];
-      cta_tot += s_wtot[buf][w];
+      if (w < warp) base += s_wtot[t][w];
+      cta_tot += s_wtot[t][w];
     }
-    // ---- phase 4: ordered emit (stash -> flattened coalesced stores; rows with > 32 hits re-walked) ----
-    if (wtot != 0 && s_base[buf] + cta_tot <= capacity)
-      emit_rows<WRITE_RIGHT>(iv, stash, s_inv[warp], cnt, cincl - cnt, my_qs, my_qe, sl.line, sl.first, left_out + base,
+    const uint32_t wtot = uint32_t(s_wtot[t][warp]);
+    if (wtot != 0 && s_base[t] + cta_tot <= capacity)
+      emit_rows<WRITE_RIGHT>(iv, s_stash + t * kStashRow + warp * 32 * kStride, s_inv[warp], t_cnt[t], t_cincl[t] - t_cnt[t],
+                             t_qs[t], t_qe[t], t_sl[t].line, t_sl[t].first, left_out + base,
                              WRITE_RIGHT ? right_out + base : nullptr, tile_first);
-    __syncwarp();  // the stash is reused by the next tile
+    __syncwarp();  // s_inv is reused by the next tile
   }
 }
 
@@ -163,10 +184,10 @@ bool use_packed(const sq_index* idx) {
   return idx->n_lines * 128ull > (64ull << 20) && idx->mean_back_lines <= 1.5f;
 }
 
-// Count-only launches give every CTA two consecutive tiles (measured: 0.69 vs 0.77 ms per 12.5M rows, the
-// second tile's probe columns and directory word are already there).  Emitting launches must not: tile
-// 2b+2 could only finish its look-back after CTA b has published its SECOND tile, i.e. after CTA b has
-// waited for and written its first one — the chained scan would serialise the whole grid (measured: 400 ms).
+// Every CTA takes two consecutive tiles (count-only measured 0.69 vs 0.77 ms per 12.5M rows: the second tile's probe
+// columns and directory word are already there).  An emitting CTA walks BOTH tiles before it joins the chained scan and
+// publishes both totals together; emitting tile 2b before walking tile 2b+1 would make CTA b+1's look-back wait for
+// CTA b's stores and serialise the grid (measured: 400 ms).  Option cuda_probe_tiles picks 1 or 2 for emitting launches.
 template <int B>
 static void launch_packed_b(sq_stream* s, const IndexView& iv, const uint64_t* d_key, const int32_t* d_start,
                             const int32_t* d_end, uint32_t n, uint32_t* cnt, unsigned long long* chain, unsigned int* ticket,
@@ -176,7 +197,15 @@ static void launch_packed_b(sq_stream* s, const IndexView& iv, const uint64_t* d
   if (!d_left)
     k_probe_packed<false, false, B, 2><<<(n_tiles + 1) / 2, B, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket,
                                                                                 result, nullptr, nullptr, 0, n_tiles, 0u);
-  else if (d_right)
+  else if (B <= 128 && s->ctx->opt.probe_tiles.load(std::memory_order_relaxed) == 2) {  // two stashes of 256 rows: > 48 KB
+    constexpr int B2 = B <= 128 ? B : 128;
+    if (d_right)
+      k_probe_packed<true, true, B2, 2><<<(n_tiles + 1) / 2, B2, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket,
+                                                                                result, d_left, d_right, capacity, n_tiles, backoff);
+    else
+      k_probe_packed<true, false, B2, 2><<<(n_tiles + 1) / 2, B2, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket,
+                                                                                 result, d_left, nullptr, capacity, n_tiles, backoff);
+  } else if (d_right)
     k_probe_packed<true, true, B, 1><<<n_tiles, B, 0, s->stream>>>(iv, d_key, d_start, d_end, n, cnt, chain, ticket, result,
                                                                     d_left, d_right, capacity, n_tiles, backoff);
   else

@@ -9,18 +9,21 @@ from helpers import canon, encode_tables, rows_from_pairs, sort_rows
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["packed", "soa", "staged", "soa_walk"])
+@pytest.fixture(autouse=True, params=["packed", "packed2", "soa", "staged", "soa_walk"])
 def probe_layout(request, cuda_ctx):
     """Every parity test runs against both probe implementations: the fused kernel over packed
     lines (narrow indexes) and the count/scan/write kernels over the SoA arrays (option
     sequila.cuda_probe_layout, sq_probe_packed.cu::use_packed)."""
     # "staged" = packed lines served by the shared-memory (TMA) staged kernel whatever the probe order: unsorted tiles
     # then exercise its global-memory path, sorted ones the staged path
+    # "packed2" = the packed-line kernel with two tiles per CTA (option cuda_probe_tiles)
     # "soa" = the rank-difference kernel where the build side allows it; "soa_walk" = count / scan / write always
-    cuda_ctx.set_option("sequila.cuda_probe_layout", {"staged": "packed", "soa_walk": "soa"}.get(request.param, request.param))
+    cuda_ctx.set_option("sequila.cuda_probe_layout", {"staged": "packed", "packed2": "packed", "soa_walk": "soa"}.get(request.param, request.param))
     cuda_ctx.set_option("sequila.cuda_rank_count", "off" if request.param == "soa_walk" else "force")
     cuda_ctx.set_option("sequila.cuda_staged_probe", "on" if request.param == "staged" else "off")
+    cuda_ctx.set_option("sequila.cuda_probe_tiles", 2 if request.param == "packed2" else 1)
     yield request.param
+    cuda_ctx.set_option("sequila.cuda_probe_tiles", 1)
     cuda_ctx.set_option("sequila.cuda_probe_layout", "auto")
     cuda_ctx.set_option("sequila.cuda_staged_probe", "auto")
     cuda_ctx.set_option("sequila.cuda_rank_count", "on")
