@@ -471,7 +471,7 @@ def sub_config(sn, torch, ctx, name, device, hbm_peak, steps, flush):
             "count_only_ms": c_ms, "build_ms": idx.build_ms, "digest": {"pairs": dg[0], "sum": dg[1]}}
 
 
-def exec_node_line(sn, args, n_build=2_000_000, n_probe=2_000_000, batch_rows=8192):
+def exec_node_line(sn, args, n_build=2_000_000, n_probe=2_000_000, batch_rows=8192, build_ids=None):
     """The layer a DataFusion user hits (IntervalJoinExec over Arrow RecordBatches, interval_join.rs:1192-1233,
     1580-1640): cfg5-shaped rows at 2 % scale, Utf8 contig column, probe side fed in 8192-row batches (DataFusion's
     default batch size), the six joined columns out."""
@@ -491,9 +491,13 @@ def exec_node_line(sn, args, n_build=2_000_000, n_probe=2_000_000, batch_rows=81
     L, R = table(b), table(p)
     cfg = sn.SequilaConfig()
     sn.apply_set(cfg, "SET sequila.interval_join_algorithm TO cuda")
+    if build_ids:  # A/B runs (tools/time_exec_ids.py); the node's own default is position ids
+        sn.apply_set(cfg, f"SET sequila.cuda_build_ids TO {build_ids}")
     f = IV.parse_condition_sql("a.pos_start <= b.pos_end AND a.pos_end >= b.pos_start", "a", cols, "b", cols)
     plan = optimize(HashJoinDesc(L.schema, R.schema, [("contig", "contig")], f), cfg)
+    t0 = time.perf_counter()
     plan.collect_build([L])
+    build_s = time.perf_counter() - t0
     batches = [R.slice(i, batch_rows) for i in range(0, R.num_rows, batch_rows)]
     best = None
     rows = 0
@@ -529,7 +533,7 @@ def exec_node_line(sn, args, n_build=2_000_000, n_probe=2_000_000, batch_rows=81
             "value": n_probe / best, "unit": "probe intervals/s", "output_rows_per_s": rows / best,
             "columns_out": 6, "key_column": "Utf8",
             "partitions_4": {"seconds": best_p, "value": n_probe / best_p, "output_rows_per_s": rows / best_p},
-            "library_ms": lib_ms,
+            "library_ms": lib_ms, "collect_build_seconds": build_s,
             "note": "seconds = wall time of the Python host loop of the best one-thread pass (244 pushes through pyarrow's C Data "
                     "export); library_ms = join_time of the node's metrics for that pass (utils.rs:441-495): concat + hash + cast + "
                     "probe + take inside the library"}
@@ -744,43 +748,73 @@ def main():
     # ---- materialise (process_probe_batch's `take` per output column, interval_join.rs:1620-1632): the six output
     # columns of SURVEY §8(d) — contig (dictionary id, int32), pos_start, pos_end of both sides — gathered on the
     # device from the pairs of the last launch; B_gather = 8 B pair read + 2 x 4 B per column = 56 B per pair.
+    # Headline: an index built with position ids (cuda_build_ids = positions, what the exec node does): payload in the
+    # index's sorted order, the hits of a probe row are neighbouring rows of the row-wise pack.  Beside it the same
+    # gathers with row ids (payload in build-row order: one random row per pair) and `take` column by column.
     materialise = None
     if not args.no_materialise and rank == 0:
         c0 = tiles.cols[0]
         lo0, hi0 = tiles.bounds[0]
         np0 = tile_pairs[0]
-        assert run_tile(c0) == np0
-        cols = [idx.add_column_device(build[k]) for k in ("contig", "start", "end")]
-        outs = [torch.empty(max(np0, 1), dtype=torch.int32, device=device) for _ in range(6)]
-        pack = idx.pack_columns(cols)  # the three build columns row-wise: one random read per pair serves all
         pvals = [probe[k][lo0:hi0] for k in ("contig", "start", "end")]
+        ctx.set_option("cuda_build_ids", "positions")
+        idx_p = sn.CudaIndex.build_device(ctx, build["key"], build["start"], build["end"], tstream)
+        ctx.set_option("cuda_build_ids", "rows")
+        st_p = sn.CudaStream(ctx, cuda_stream=tstream)
+        left_p = torch.empty(max(np0, 1), dtype=torch.int32, device=device)
 
-        def gather_step():  # two launches: build pack, probe columns
-            st.gather_pack_device(pack, outs[:3])
-            st.gather_probe_columns_device(pvals, outs[3:])
+        def prepare(index, stream, lbuf):
+            assert stream.probe_join_device(index, c0[0], c0[1], c0[2], lbuf, right) == np0
+            cols = [index.add_column_device(build[k]) for k in ("contig", "start", "end")]
+            pack = index.pack_columns(cols)  # the three build columns row-wise: one read per pair serves all
+            outs = [torch.empty(max(np0, 1), dtype=torch.int32, device=device) for _ in range(6)]
 
-        def take_step():  # `take` column by column, what the reference's loop does (six launches)
-            for c, o in zip(cols, outs[:3]):
-                st.gather_build_device(c, o)
-            for v, o in zip(pvals, outs[3:]):
-                st.gather_probe_device(v, o)
+            def gather_step():  # two launches: build pack, probe columns
+                stream.gather_pack_device(pack, outs[:3])
+                stream.gather_probe_columns_device(pvals, outs[3:])
 
-        for fn in (take_step, gather_step):
-            fn()
-        take_ms = timed_steps(torch, take_step, min(args.steps, 10), flush)
-        g_ms = timed_steps(torch, gather_step, min(args.steps, 10), flush)
-        # spot check against torch indexing (same device data)
+            def take_step():  # `take` column by column, what the reference's loop does (six launches)
+                for c, o in zip(cols, outs[:3]):
+                    stream.gather_build_device(c, o)
+                for v, o in zip(pvals, outs[3:]):
+                    stream.gather_probe_device(v, o)
+
+            def pack_only():
+                stream.gather_pack_device(pack, outs[:3])
+            return gather_step, take_step, pack_only, outs
+
+        res = {}
+        for mode, (index, stream, lbuf) in (("rows", (idx, st, left)), ("positions", (idx_p, st_p, left_p))):
+            gather_step, take_step, pack_only, outs = prepare(index, stream, lbuf)
+            for fn in (take_step, gather_step):
+                fn()
+            take_ms = timed_steps(torch, take_step, min(args.steps, 10), flush)
+            pack_ms = timed_steps(torch, pack_only, min(args.steps, 10), flush)
+            g_ms = timed_steps(torch, gather_step, min(args.steps, 10), flush)
+            res[mode] = {"ms": g_ms, "take_per_column_ms": take_ms, "build_pack_ms": pack_ms, "outs": outs}
+        # rows mode against torch indexing (same device data); positions mode against rows mode, every value
         stride = max(np0 // 100000, 1)
         li = left[:np0].long()[::stride]
-        assert torch.equal(outs[1][:np0][::stride], build["start"][li])
+        assert torch.equal(res["rows"]["outs"][1][:np0][::stride], build["start"][li])
         ri = right[:np0].long()[::stride]
-        assert torch.equal(outs[5][:np0][::stride], pvals[2][ri])
+        assert torch.equal(res["rows"]["outs"][5][:np0][::stride], pvals[2][ri])
+        for a_, b_ in zip(res["rows"]["outs"], res["positions"]["outs"]):
+            assert torch.equal(a_[:np0], b_[:np0])
         g_bytes = 56.0 * np0
+        g_ms = res["positions"]["ms"]
+        frac = lambda ms: g_bytes / (ms * 1e-3) / 1e9 / hbm_peak if ms else None
         materialise = {"columns": 6, "ms": g_ms, "pairs_per_s": np0 / (g_ms * 1e-3) if g_ms else None,
-                       "algorithmic_bytes": g_bytes, "roofline_frac": g_bytes / (g_ms * 1e-3) / 1e9 / hbm_peak if g_ms else None,
-                       "launches": 2, "how": "build columns packed row-wise (16 B per build row): one random read per pair; "
-                       "probe columns in one pass over right_idx", "take_per_column_ms": take_ms}
-        del outs
+                       "algorithmic_bytes": g_bytes, "roofline_frac": frac(g_ms), "launches": 2,
+                       "how": "index built with position ids (sequila.cuda_build_ids = positions, the exec node's default): build "
+                       "columns kept in the index's sorted order and packed row-wise (16 B per build row), the hits of a probe "
+                       "row are neighbouring rows; probe columns in one pass over right_idx",
+                       "build_pack_ms": res["positions"]["build_pack_ms"], "take_per_column_ms": res["positions"]["take_per_column_ms"],
+                       "values_equal_row_ids": True,
+                       "row_ids": {"ms": res["rows"]["ms"], "roofline_frac": frac(res["rows"]["ms"]),
+                                   "build_pack_ms": res["rows"]["build_pack_ms"], "take_per_column_ms": res["rows"]["take_per_column_ms"],
+                                   "how": "payload in build-row order: one random 16-byte read per pair"}}
+        del res, idx_p, st_p, left_p
+        assert run_tile(c0) == np0  # the sections below read left / right of the first launch
 
     # ---- same rows in position order (what BAM / BED inputs look like), N=1 only
     locality = None

@@ -72,6 +72,9 @@ extern "C" {
     pub fn sq_index_keys(idx: *const sq_index) -> u64;
     pub fn sq_index_uses_packed(idx: *const sq_index) -> i32;
     pub fn sq_index_uses_rank(idx: *const sq_index) -> i32;
+    pub fn sq_index_uses_positions(idx: *const sq_index) -> i32;
+    pub fn sq_index_position_rows(idx: *const sq_index, rows_out: *mut u32) -> i32;
+    pub fn sq_index_position_rows_device(idx: *const sq_index) -> *const u32;
     pub fn sq_index_build_ms(idx: *const sq_index) -> f32;
     pub fn sq_index_free(idx: *mut sq_index);
     pub fn sq_index_add_column(idx: *mut sq_index, values: *const c_void, width: u32, col_id_out: *mut i32) -> i32;

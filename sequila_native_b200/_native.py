@@ -44,6 +44,9 @@ SIGNATURES = {
     "sq_index_keys": (C.c_uint64, [vp]),
     "sq_index_uses_packed": (C.c_int32, [vp]),
     "sq_index_uses_rank": (C.c_int32, [vp]),
+    "sq_index_uses_positions": (C.c_int32, [vp]),
+    "sq_index_position_rows": (C.c_int32, [vp, vp]),
+    "sq_index_position_rows_device": (vp, [vp]),
     "sq_index_build_ms": (C.c_float, [vp]),
     "sq_index_free": (None, [vp]),
     "sq_index_add_column": (C.c_int32, [vp, vp, C.c_uint32, C.POINTER(C.c_int32)]),

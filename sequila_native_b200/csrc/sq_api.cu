@@ -139,6 +139,7 @@ const char* const kLayoutWords[] = {"auto", "packed", "soa", nullptr};
 const char* const kWireWords[] = {"rle", "copy", nullptr};
 const char* const kStagedWords[] = {"auto", "on", "off", nullptr};
 const char* const kOnOffWords[] = {"off", "on", "force", nullptr};
+const char* const kIdsWords[] = {"rows", "positions", nullptr};
 const OptDesc kOpts[] = {
     {"cuda_probe_layout", &sq_options::probe_layout, 0, 2, kLayoutWords},
     {"cuda_probe_block", &sq_options::probe_block, 64, 256, nullptr},
@@ -152,6 +153,7 @@ const OptDesc kOpts[] = {
     {"cuda_pipeline_depth", &sq_options::pipeline_depth, 2, 8, nullptr},
     {"cuda_coalesce_rows", &sq_options::coalesce_rows, 1, 1 << 27, nullptr},
     {"cuda_rank_count", &sq_options::rank_count, 0, 2, kOnOffWords},
+    {"cuda_build_ids", &sq_options::build_ids, 0, 1, kIdsWords},
 };
 const char* strip_prefix(const char* key) { return strncmp(key, "sequila.", 8) == 0 ? key + 8 : key; }
 }  // namespace
@@ -314,6 +316,104 @@ SQ_API int32_t sq_index_uses_rank(const sq_index* idx) { return idx && use_rank(
 SQ_API float sq_index_build_ms(const sq_index* idx) { return idx ? idx->build_ms : 0.f; }
 SQ_API void sq_index_free(sq_index* idx) { free_index(idx); }
 
+SQ_API int32_t sq_index_uses_positions(const sq_index* idx) { return idx && idx->pos_ids ? 1 : 0; }
+
+SQ_API int32_t sq_index_position_rows(const sq_index* idx, uint32_t* rows_out) {
+  if (!idx) return SQ_EINVAL;
+  ErrorSlot& E = idx->ctx->err;
+  if (!idx->pos_ids) return fail(E, SQ_ESTATE, "the index hands out build rows, not positions (option cuda_build_ids)");
+  if (idx->n_rows && !rows_out) return fail(E, SQ_EINVAL, "null rows_out");
+  SQ_CUDA(E, cudaSetDevice(idx->ctx->device));
+  if (idx->n_rows) SQ_CUDA(E, cudaMemcpy(rows_out, idx->d_perm, size_t(idx->n_rows) * 4, cudaMemcpyDeviceToHost));
+  return SQ_OK;
+}
+
+SQ_API const uint32_t* sq_index_position_rows_device(const sq_index* idx) { return idx && idx->pos_ids ? idx->d_perm : nullptr; }
+
+static int32_t stream_create(sq_ctx* ctx, cudaStream_t ext, bool use_ext, sq_stream** out);
+
+// Position ids (option cuda_build_ids positions): payload is kept in the index's sorted order, value of position j =
+// value of build row perm[j], so that gathers by the ids the probe kernels emit read neighbouring rows.  The columns are
+// permuted once, when they are registered, with the take kernels themselves (indices = perm).
+namespace {
+// one scratch stream per index, created at the first permutation and kept (its pinned scalar slot and device scratch
+// cost more to allocate than a small column costs to permute)
+struct ScratchStream {
+  sq_index* idx;
+  std::unique_lock<std::mutex> lock;
+  sq_stream* s = nullptr;
+  explicit ScratchStream(sq_index* i) : idx(i), lock(i->perm_mu) {}
+  int32_t open() {
+    if (!idx->perm_stream) {
+      const int32_t rc = stream_create(idx->ctx, nullptr, false, &idx->perm_stream);  // its message is in the context's slot
+      if (rc) return rc;
+    }
+    s = idx->perm_stream;
+    return SQ_OK;
+  }
+  int32_t done(int32_t rc) {
+    if (rc == SQ_OK && cudaStreamSynchronize(s->stream) != cudaSuccess) rc = SQ_ECUDA;
+    return rc ? fail(idx->ctx->err, rc, "permuting a payload column: %s", sq_stream_last_error(s)) : SQ_OK;
+  }
+};
+
+// *d_values (n_rows values in build-row order) -> a new allocation in position order; the old one is freed when owned
+int32_t permute_fixed(sq_index* idx, void** d_values, uint32_t width, bool owned) {
+  ErrorSlot& E = idx->ctx->err;
+  ScratchStream t(idx);
+  int32_t rc = t.open();
+  if (rc) return rc;
+  void* d_new = nullptr;
+  SQ_CUDA(E, cudaMalloc(&d_new, size_t(idx->n_rows ? idx->n_rows : 1) * width));
+  rc = t.done(launch_gather(t.s, *d_values, idx->d_perm, idx->n_rows, width, d_new));
+  if (rc) { cudaFree(d_new); return rc; }
+  if (owned) cudaFree(*d_values);
+  *d_values = d_new;
+  return SQ_OK;
+}
+
+int32_t permute_utf8(sq_index* idx, int64_t** d_offsets, void** d_data, uint64_t data_bytes) {
+  ErrorSlot& E = idx->ctx->err;
+  ScratchStream t(idx);
+  int32_t rc = t.open();
+  if (rc) return rc;
+  const size_t n = size_t(idx->n_rows);
+  int64_t* d_off = nullptr;
+  uint8_t* d_new = nullptr;
+  SQ_CUDA(E, cudaMalloc(&d_off, (n + 1) * 8));
+  cudaError_t e = cudaMalloc(&d_new, data_bytes ? data_bytes : 16);
+  if (e != cudaSuccess) { cudaFree(d_off); return fail(E, SQ_ECUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
+  uint64_t total = 0;
+  rc = launch_str_offsets(t.s, *d_offsets, idx->d_perm, n, d_off, &total);
+  if (rc == SQ_OK && total != data_bytes) rc = fail(t.s->err, SQ_EINVAL, "utf8 offsets cover %llu bytes, %llu given",
+                                                    (unsigned long long)total, (unsigned long long)data_bytes);
+  if (rc == SQ_OK) rc = launch_str_copy(t.s, *d_offsets, static_cast<const uint8_t*>(*d_data), idx->d_perm, n, d_off, d_new);
+  rc = t.done(rc);
+  if (rc) { cudaFree(d_off); cudaFree(d_new); return rc; }
+  cudaFree(*d_offsets);
+  cudaFree(*d_data);
+  *d_offsets = d_off;
+  *d_data = d_new;
+  return SQ_OK;
+}
+
+int32_t permute_bits(sq_index* idx, uint8_t** d_bitmap) {
+  ErrorSlot& E = idx->ctx->err;
+  ScratchStream t(idx);
+  int32_t rc = t.open();
+  if (rc) return rc;
+  const size_t bytes = (size_t(idx->n_rows) + 7) / 8;
+  uint8_t* d_new = nullptr;
+  SQ_CUDA(E, cudaMalloc(&d_new, bytes ? bytes : 16));
+  uint64_t nulls = 0;
+  rc = t.done(launch_gather_bits(t.s, *d_bitmap, idx->d_perm, idx->n_rows, d_new, &nulls));
+  if (rc) { cudaFree(d_new); return rc; }
+  cudaFree(*d_bitmap);
+  *d_bitmap = d_new;
+  return SQ_OK;
+}
+}  // namespace
+
 SQ_API int32_t sq_index_add_column(sq_index* idx, const void* values, uint32_t width, int32_t* col_id_out) {
   if (!idx || !col_id_out) return SQ_EINVAL;
   ErrorSlot& E = idx->ctx->err;
@@ -328,6 +428,10 @@ SQ_API int32_t sq_index_add_column(sq_index* idx, const void* values, uint32_t w
   if (idx->n_rows) {
     cudaError_t e = cudaMemcpy(c.d_values, values, size_t(idx->n_rows) * width, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(c.d_values); return fail(E, SQ_ECUDA, "H2D copy of build column: %s", cudaGetErrorString(e)); }
+  }
+  if (idx->pos_ids && idx->n_rows) {
+    const int32_t rc = permute_fixed(idx, &c.d_values, width, true);
+    if (rc) { cudaFree(c.d_values); return rc; }
   }
   std::lock_guard<std::mutex> g(idx->col_mu);
   idx->bytes += bytes;
@@ -344,7 +448,15 @@ SQ_API int32_t sq_index_add_column_device(sq_index* idx, const void* d_values, u
   c.width = width;
   c.owned = false;
   c.d_values = const_cast<void*>(d_values);
+  if (idx->pos_ids && idx->n_rows) {  // the index keeps its own copy in position order
+    if (!d_values) return fail(E, SQ_EINVAL, "null column values");
+    SQ_CUDA(E, cudaSetDevice(idx->ctx->device));
+    const int32_t rc = permute_fixed(idx, &c.d_values, width, false);
+    if (rc) return rc;
+    c.owned = true;
+  }
   std::lock_guard<std::mutex> g(idx->col_mu);
+  if (c.owned) idx->bytes += size_t(idx->n_rows) * width;
   idx->columns.push_back(c);
   *col_id_out = int32_t(idx->columns.size() - 1);
   return SQ_OK;
@@ -974,6 +1086,10 @@ SQ_API int32_t sq_index_add_utf8_column(sq_index* idx, const int64_t* offsets, c
     cudaFree(c.d_offsets); cudaFree(c.d_values);
     return fail(E, SQ_ECUDA, "H2D copy of utf8 build column: %s", cudaGetErrorString(e));
   }
+  if (idx->pos_ids && n) {
+    const int32_t rc = permute_utf8(idx, &c.d_offsets, &c.d_values, data_bytes);
+    if (rc) { cudaFree(c.d_offsets); cudaFree(c.d_values); return rc; }
+  }
   std::lock_guard<std::mutex> g(idx->col_mu);
   idx->bytes += (n + 1) * 8 + data_bytes;
   idx->columns.push_back(c);
@@ -993,6 +1109,10 @@ SQ_API int32_t sq_index_set_validity(sq_index* idx, int32_t col_id, const uint8_
   SQ_CUDA(E, cudaMalloc(&d, bytes ? bytes : 16));
   cudaError_t e = cudaMemcpy(d, bitmap, bytes, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { cudaFree(d); return fail(E, SQ_ECUDA, "H2D copy of validity: %s", cudaGetErrorString(e)); }
+  if (idx->pos_ids && idx->n_rows) {
+    const int32_t rc = permute_bits(idx, &d);
+    if (rc) { cudaFree(d); return rc; }
+  }
   if (idx->columns[col_id].d_validity) cudaFree(idx->columns[col_id].d_validity);
   idx->columns[col_id].d_validity = d;
   idx->bytes += bytes;

@@ -166,18 +166,22 @@ __global__ void __launch_bounds__(256) k_end_values(const uint64_t* __restrict__
 }
 
 // After the sort: write start[], row[], end[] (unpacked from the sorted key / value words) and the
-// segment boundaries seg_off[id] = first sorted position of key id.
+// segment boundaries seg_off[id] = first sorted position of key id.  With s_perm the ids the index hands out are the
+// sorted positions themselves (row[j] = j) and s_perm[j] keeps the build row: payload stored in that order is read
+// with locality by the gathers (the hits of a probe row are neighbours).
 __global__ void __launch_bounds__(256) k_finalize(const uint64_t* __restrict__ sorted_key,
                                                   const uint64_t* __restrict__ sorted_val, uint64_t n,
                                                   int32_t* __restrict__ s_start, int32_t* __restrict__ s_end,
-                                                  uint32_t* __restrict__ s_row,
+                                                  uint32_t* __restrict__ s_row, uint32_t* __restrict__ s_perm,
                                                   uint32_t* __restrict__ seg_off, uint32_t n_keys) {
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
   for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride) {
     const uint64_t k = sorted_key[j];
     const uint64_t v = sorted_val[j];
     s_start[j] = int32_t(uint32_t(k) ^ 0x80000000u);
-    s_row[j] = uint32_t(v);
+    // position ids (option cuda_build_ids positions): the probe kernels hand out j itself, the build row goes to perm[]
+    s_row[j] = s_perm ? uint32_t(j) : uint32_t(v);
+    if (s_perm) s_perm[j] = uint32_t(v);
     s_end[j] = int32_t(uint32_t(v >> 32));
     const uint32_t id = uint32_t(k >> 32);
     if (j == 0 || uint32_t(sorted_key[j - 1] >> 32) != id) seg_off[id] = uint32_t(j);
@@ -453,7 +457,8 @@ static inline int grid_for(uint64_t n, int threads, int sm_count, int per_sm = 8
 void free_index(sq_index* idx) {
   if (!idx) return;
   cudaSetDevice(idx->ctx->device);
-  cudaFree(idx->d_start); cudaFree(idx->d_runmax); cudaFree(idx->d_end); cudaFree(idx->d_row);
+  if (idx->perm_stream) sq_stream_free(idx->perm_stream);
+  cudaFree(idx->d_start); cudaFree(idx->d_runmax); cudaFree(idx->d_end); cudaFree(idx->d_row); cudaFree(idx->d_perm);
   cudaFree(idx->d_meta); cudaFree(idx->d_dir); cudaFree(idx->d_ht_keys); cudaFree(idx->d_ht_ids);
   cudaFree(idx->d_lines);
   cudaFree(idx->d_dir_line);
@@ -566,7 +571,9 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
   SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_end, (n ? n : 1) * 4, pool, st));
   SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_row, (n ? n : 1) * 4, pool, st));
   SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_meta, (size_t(n_keys) + 1) * sizeof(SegMeta), pool, st));
-  idx->bytes = uint64_t(n ? n : 1) * 16 + (uint64_t(n_keys) + 1) * sizeof(SegMeta) + uint64_t(cap) * 12;
+  idx->pos_ids = ctx->opt.build_ids.load(std::memory_order_relaxed) == 1;
+  if (idx->pos_ids) SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_perm, (n ? n : 1) * 4, pool, st));
+  idx->bytes = uint64_t(n ? n : 1) * (idx->pos_ids ? 20 : 16) + (uint64_t(n_keys) + 1) * sizeof(SegMeta) + uint64_t(cap) * 12;
 
   if (n) {
     uint64_t *d_k0 = nullptr, *d_k1 = nullptr;
@@ -592,7 +599,7 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     SQ_CUDA(E, tmp.alloc(&d_temp, temp_bytes));
     SQ_CUDA(E, ::sq_cub::cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_k0, d_k1, d_v0, d_v1, n, 0, end_bit, st));
 
-    k_finalize<<<g, 256, 0, st>>>(d_k1, d_v1, n, idx->d_start, idx->d_end, idx->d_row, d_seg_off, n_keys);
+    k_finalize<<<g, 256, 0, st>>>(d_k1, d_v1, n, idx->d_start, idx->d_end, idx->d_row, idx->d_perm, d_seg_off, n_keys);
     SQ_CUDA(E, cudaGetLastError());
 
     // 3. running max of end inside each key segment

@@ -535,6 +535,10 @@ SQ_API int32_t sq_exec_create(const sq_exec_config* cfg, const ArrowSchema* left
     e.release();
     return rc;
   }
+  // the build table is the node's own concatenation of the build batches: its payload is kept in the index's sorted order
+  // and the pairs carry positions, so every `take` of a build column reads neighbouring rows (a SET of
+  // sequila.cuda_build_ids before the build overrides this)
+  sq_ctx_set_option(e->ctx, "cuda_build_ids", "positions");
   e.release();
   return SQ_OK;
 }

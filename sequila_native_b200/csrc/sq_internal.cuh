@@ -124,6 +124,7 @@ struct HostPool {
 // while partitions probe on others; every reader takes one consistent value per call.
 struct sq_options {
   std::atomic<int> probe_layout{0};         // 0 auto, 1 packed lines (when the index has them), 2 SoA arrays
+  std::atomic<int> build_ids{0};            // ids an index hands out: 0 build rows, 1 sorted positions (payload kept in that order)
   std::atomic<int> probe_tiles{1};          // tiles per CTA of an emitting packed-line launch: 1 / 2
   std::atomic<int> probe_block{128};        // rows per CTA of the packed-line kernels: 64 / 128 / 256
   std::atomic<int> lookback_backoff_ns{64}; // sleep between polls of a predecessor's chained-scan word
@@ -176,6 +177,10 @@ struct sq_index {
   int32_t* d_runmax = nullptr;
   int32_t* d_end = nullptr;
   uint32_t* d_row = nullptr;
+  bool pos_ids = false;        // option cuda_build_ids positions: d_row[j] = j, payload columns are stored in sorted order
+  uint32_t* d_perm = nullptr;  // pos_ids: sorted position -> build row
+  std::mutex perm_mu;          // pos_ids: payload columns are permuted one at a time on perm_stream
+  struct sq_stream* perm_stream = nullptr;
   sq::SegMeta* d_meta = nullptr;
   uint32_t* d_dir = nullptr;
   uint64_t dir_bytes = 0;

@@ -144,6 +144,16 @@ class CudaIndex:
     build_ms = property(lambda self: float(self._lib.sq_index_build_ms(self._h)))
     uses_packed = property(lambda self: bool(self._lib.sq_index_uses_packed(self._h)))
     uses_rank = property(lambda self: bool(self._lib.sq_index_uses_rank(self._h)))
+    uses_positions = property(lambda self: bool(self._lib.sq_index_uses_positions(self._h)))
+
+    def position_rows(self) -> np.ndarray:
+        """sq_index_position_rows: build row of every position (indexes built with cuda_build_ids = positions)"""
+        out = np.empty(self.rows, dtype=np.uint32)
+        _check(self._lib.sq_index_position_rows(self._h, out.ctypes.data_as(C.c_void_p)), self.ctx._err)
+        return out
+
+    def position_rows_device_ptr(self) -> int:
+        return int(self._lib.sq_index_position_rows_device(self._h) or 0)
 
 
 class CudaDriver:

@@ -20,9 +20,23 @@ def table(rows, int_type=pa.int32(), str_type=pa.string()):
                             pa.array([r[2] for r in rows], int_type)], names=COLS)
 
 
+BUILD_IDS = [None]
+
+
+@pytest.fixture(autouse=True, params=["positions", "rows"])
+def build_ids(request):
+    """Every test runs with the node's default (position ids: build payload kept in the index's sorted order) and with
+    `SET sequila.cuda_build_ids TO rows` (payload in build-row order): the output must not depend on it."""
+    BUILD_IDS[0] = request.param
+    yield request.param
+    BUILD_IDS[0] = None
+
+
 def cuda_config():
     cfg = sn.SequilaConfig()
     sn.apply_set(cfg, "SET sequila.interval_join_algorithm TO cuda")
+    if BUILD_IDS[0] == "rows":  # "positions" is what the node picks by itself
+        sn.apply_set(cfg, "SET sequila.cuda_build_ids TO rows")
     return cfg
 
 
