@@ -67,6 +67,7 @@ int32_t sq_device_count(void);
  *   cuda_pipeline_depth       2..8                  sq_stream_submit: tiles in flight per stream (default 3)
  *   cuda_coalesce_rows        1..2^27               exec node: probe rows that make one tile (default 1048576)
  *   cuda_rank_count           on | off              build: rank structure over the ends (rank-difference count, one walk)
+ *   cuda_build_sort           auto | wide           build: 32-bit sort keys when they fit (see sq_index_sort_key_bits) or always 64-bit
  *   cuda_build_ids            rows | positions      build: what left_idx means (see sq_index_uses_positions; default rows)
  * Unknown keys and invalid values return SQ_EINVAL with a message; values may be changed between calls. */
 int32_t sq_ctx_set_option(sq_ctx* ctx, const char* key, const char* value);
@@ -111,6 +112,10 @@ int32_t sq_index_uses_rank(const sq_index* idx);
 int32_t sq_index_uses_positions(const sq_index* idx);
 int32_t sq_index_position_rows(const sq_index* idx, uint32_t* rows_out);
 const uint32_t* sq_index_position_rows_device(const sq_index* idx); /* device pointer, NULL unless position ids */
+/* width of the build's sort keys: 32 when the keys' start ranges laid end to end fit 32 bits (at most 4096 keys; a
+ * genome's contigs do) — four radix passes over 12-byte pairs — else 64 (key id : start); option cuda_build_sort = wide
+ * forces 64.  The index is the same either way. */
+int32_t sq_index_sort_key_bits(const sq_index* idx);
 /* device time of the last build's kernels in ms (sort, scan, ...); 0 if unknown */
 float sq_index_build_ms(const sq_index* idx);
 void sq_index_free(sq_index* idx);

@@ -72,6 +72,7 @@ extern "C" {
     pub fn sq_index_keys(idx: *const sq_index) -> u64;
     pub fn sq_index_uses_packed(idx: *const sq_index) -> i32;
     pub fn sq_index_uses_rank(idx: *const sq_index) -> i32;
+    pub fn sq_index_sort_key_bits(idx: *const sq_index) -> i32;
     pub fn sq_index_uses_positions(idx: *const sq_index) -> i32;
     pub fn sq_index_position_rows(idx: *const sq_index, rows_out: *mut u32) -> i32;
     pub fn sq_index_position_rows_device(idx: *const sq_index) -> *const u32;

@@ -44,6 +44,7 @@ SIGNATURES = {
     "sq_index_keys": (C.c_uint64, [vp]),
     "sq_index_uses_packed": (C.c_int32, [vp]),
     "sq_index_uses_rank": (C.c_int32, [vp]),
+    "sq_index_sort_key_bits": (C.c_int32, [vp]),
     "sq_index_uses_positions": (C.c_int32, [vp]),
     "sq_index_position_rows": (C.c_int32, [vp, vp]),
     "sq_index_position_rows_device": (vp, [vp]),

@@ -140,6 +140,7 @@ const char* const kWireWords[] = {"rle", "copy", nullptr};
 const char* const kStagedWords[] = {"auto", "on", "off", nullptr};
 const char* const kOnOffWords[] = {"off", "on", "force", nullptr};
 const char* const kIdsWords[] = {"rows", "positions", nullptr};
+const char* const kSortWords[] = {"auto", "wide", nullptr};
 const OptDesc kOpts[] = {
     {"cuda_probe_layout", &sq_options::probe_layout, 0, 2, kLayoutWords},
     {"cuda_probe_block", &sq_options::probe_block, 64, 256, nullptr},
@@ -154,6 +155,7 @@ const OptDesc kOpts[] = {
     {"cuda_coalesce_rows", &sq_options::coalesce_rows, 1, 1 << 27, nullptr},
     {"cuda_rank_count", &sq_options::rank_count, 0, 2, kOnOffWords},
     {"cuda_build_ids", &sq_options::build_ids, 0, 1, kIdsWords},
+    {"cuda_build_sort", &sq_options::build_sort, 0, 1, kSortWords},
 };
 const char* strip_prefix(const char* key) { return strncmp(key, "sequila.", 8) == 0 ? key + 8 : key; }
 }  // namespace
@@ -316,6 +318,7 @@ SQ_API int32_t sq_index_uses_rank(const sq_index* idx) { return idx && use_rank(
 SQ_API float sq_index_build_ms(const sq_index* idx) { return idx ? idx->build_ms : 0.f; }
 SQ_API void sq_index_free(sq_index* idx) { free_index(idx); }
 
+SQ_API int32_t sq_index_sort_key_bits(const sq_index* idx) { return idx ? (idx->narrow_sort ? 32 : 64) : 0; }
 SQ_API int32_t sq_index_uses_positions(const sq_index* idx) { return idx && idx->pos_ids ? 1 : 0; }
 
 SQ_API int32_t sq_index_position_rows(const sq_index* idx, uint32_t* rows_out) {

@@ -45,39 +45,48 @@ __global__ void __launch_bounds__(256) k_ht_insert(const uint64_t* __restrict__ 
   __shared__ uint64_t s_seen[256];
   s_seen[threadIdx.x] = kEmptyKey;
   __syncthreads();
-  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
-  // warp-uniform trip count so that the whole warp reaches the ballot together
-  const uint64_t first = uint64_t(blockIdx.x) * blockDim.x + (threadIdx.x & ~31u);
-  for (uint64_t i0 = first; i0 < n; i0 += stride) {
-    const uint64_t i = i0 + (threadIdx.x & 31);
-    const bool valid = i < n;
-    const uint64_t key = valid ? keys[i] : kEmptyKey;
-    if (valid && key == kEmptyKey) st->has_sentinel = 1;
-    const uint32_t h = uint32_t(mix64(key));
-    const bool miss = key != kEmptyKey && *reinterpret_cast<volatile uint64_t*>(&s_seen[h & 255u]) != key;
-    const unsigned mm = __ballot_sync(0xffffffffu, miss);
-    if (!miss) continue;
-    // one lane per distinct missing key in the warp does the table work
-    const unsigned peers = __match_any_sync(mm, key);
-    if ((__ffs(peers) - 1) != int(threadIdx.x & 31)) continue;
-    uint32_t slot = h & mask;
-    for (uint32_t step = 0; step <= mask; ++step) {
-      uint64_t cur = *reinterpret_cast<volatile uint64_t*>(ht_keys + slot);
-      if (cur == key) break;
-      if (cur == kEmptyKey) {
-        const uint64_t old = atomicCAS(reinterpret_cast<unsigned long long*>(ht_keys + slot),
-                                       (unsigned long long)kEmptyKey, (unsigned long long)key);
-        if (old == kEmptyKey) {
-          const unsigned d = atomicAdd(&st->distinct, 1u) + 1u;
-          if (d > (mask + 1u) / 2u) st->overflow = 1;  // keep load factor <= 1/2
-          break;
-        }
-        if (old == key) break;
-      }
-      slot = (slot + 1) & mask;
-      if (step == mask) st->overflow = 1;
+  // kU rows per thread and trip, their loads issued together (one 8-byte load per thread in flight is latency-bound:
+  // 0.54 ms per 100M keys); warp-uniform trip count so that the whole warp reaches the ballots together
+  constexpr int kU = 4;
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x * kU;
+  const uint64_t first = (uint64_t(blockIdx.x) * blockDim.x + (threadIdx.x & ~31u)) * kU + (threadIdx.x & 31);
+  for (uint64_t i0 = first; i0 - (threadIdx.x & 31) < n; i0 += stride) {
+    uint64_t ks[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const uint64_t i = i0 + uint64_t(u) * 32;
+      ks[u] = i < n ? keys[i] : kEmptyKey;
+      if (i < n && ks[u] == kEmptyKey) st->has_sentinel = 1;
     }
-    *reinterpret_cast<volatile uint64_t*>(&s_seen[h & 255u]) = key;  // in the table now (or the table overflowed)
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const uint64_t key = ks[u];
+      const uint32_t h = uint32_t(mix64(key));
+      const bool miss = key != kEmptyKey && *reinterpret_cast<volatile uint64_t*>(&s_seen[h & 255u]) != key;
+      const unsigned mm = __ballot_sync(0xffffffffu, miss);
+      if (!miss) continue;
+      // one lane per distinct missing key in the warp does the table work
+      const unsigned peers = __match_any_sync(mm, key);
+      if ((__ffs(peers) - 1) != int(threadIdx.x & 31)) continue;
+      uint32_t slot = h & mask;
+      for (uint32_t step = 0; step <= mask; ++step) {
+        uint64_t cur = *reinterpret_cast<volatile uint64_t*>(ht_keys + slot);
+        if (cur == key) break;
+        if (cur == kEmptyKey) {
+          const uint64_t old = atomicCAS(reinterpret_cast<unsigned long long*>(ht_keys + slot),
+                                         (unsigned long long)kEmptyKey, (unsigned long long)key);
+          if (old == kEmptyKey) {
+            const unsigned d = atomicAdd(&st->distinct, 1u) + 1u;
+            if (d > (mask + 1u) / 2u) st->overflow = 1;  // keep load factor <= 1/2
+            break;
+          }
+          if (old == key) break;
+        }
+        slot = (slot + 1) & mask;
+        if (step == mask) st->overflow = 1;
+      }
+      *reinterpret_cast<volatile uint64_t*>(&s_seen[h & 255u]) = key;  // in the table now (or the table overflowed)
+    }
   }
 }
 
@@ -112,19 +121,95 @@ __global__ void __launch_bounds__(256) k_make_sort_keys(const uint64_t* __restri
   if (inv) atomicOr(inverted, 1u);  // some build row has end < start: the rank-difference count does not apply
 }
 
-// block maxima of end: level 1 over 32 sorted rows (one warp per block), levels 2 and 3 over 32 entries of the level below
-__global__ void __launch_bounds__(256) k_block_max_rows(const int32_t* __restrict__ s_end, uint64_t n, uint64_t n_blocks,
-                                                        int32_t* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const uint64_t warps = (uint64_t(gridDim.x) * blockDim.x) >> 5;
-  for (uint64_t b = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; b < n_blocks; b += warps) {
-    const uint64_t j = b * 32 + lane;
-    int32_t v = j < n ? s_end[j] : INT32_MIN;
+// ---------------------------------------------------------------------------------------------
+// Narrow sort keys.  With few keys (<= kNarrowMaxKeys) whose start ranges, laid end to end, fit 32 bits (a genome's
+// contigs: hg38 = 3.1e9 positions), the sort key is ONE 32-bit word, key32 = base[id] + (start - min_start[id]) with
+// base = exclusive sum of the per-key spans: 4 radix passes over 12-byte pairs instead of 5 over 16-byte ones.
+//   k_key_ranges      dense id of every build row + per-key min / max of start (shared-memory aggregation per CTA,
+//                     one pair of global atomics per key and CTA)
+//   (host)            spans -> bases; anything that does not fit falls back to the 64-bit keys above
+//   k_make_sort_keys32
+//   k_finalize32      id of a sorted row = the segment its key32 falls into (binary search over <= 4096 bases in
+//                     shared memory), start = key32 - base + min_start
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kNarrowMaxKeys = 4096;
+struct KeyBase {
+  uint32_t base;      // first key32 of this key id
+  int32_t min_start;  // smallest start of this key id
+};
+
+__global__ void __launch_bounds__(256) k_key_ranges(const uint64_t* __restrict__ keys, const int32_t* __restrict__ start,
+                                                    uint64_t n, const uint64_t* __restrict__ ht_keys,
+                                                    const uint32_t* __restrict__ ht_ids, uint32_t mask, uint32_t sentinel_id,
+                                                    uint32_t n_keys, uint32_t* __restrict__ row_id,
+                                                    int32_t* __restrict__ key_min, int32_t* __restrict__ key_max) {
+  extern __shared__ int32_t s_rng[];  // [n_keys] min, [n_keys] max
+  int32_t* s_min = s_rng;
+  int32_t* s_max = s_rng + n_keys;
+  for (uint32_t k = threadIdx.x; k < n_keys; k += blockDim.x) { s_min[k] = INT32_MAX; s_max[k] = INT32_MIN; }
+  __syncthreads();
+  // kU rows per thread and trip (loads issued together: one 12-byte row per thread in flight is latency-bound); the trip
+  // count is warp-uniform.  The table is read first as a filter — its values only move outwards, so a stale read can
+  // only ask for an update that is not needed — and after a CTA's first few thousand rows almost no row passes it on
+  // unsorted input; sorted input (one key per warp, every row a new maximum) takes the whole-warp reduction.
+  constexpr int kU = 4;
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x * kU;
+  const uint64_t first = (uint64_t(blockIdx.x) * blockDim.x + (threadIdx.x & ~31u)) * kU + (threadIdx.x & 31);
+  for (uint64_t i0 = first; i0 - (threadIdx.x & 31) < n; i0 += stride) {
+    uint64_t key[kU];
+    int32_t st[kU];
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, d));
-    if (lane == 0) out[b] = v;
+    for (int u = 0; u < kU; ++u) {
+      const uint64_t i = i0 + uint64_t(u) * 32;
+      key[u] = i < n ? keys[i] : 0;
+      st[u] = i < n ? start[i] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const uint64_t i = i0 + uint64_t(u) * 32;
+      const bool valid = i < n;
+      const unsigned act = __ballot_sync(0xffffffffu, valid);
+      if (!valid) continue;
+      const uint32_t id = ht_lookup(ht_keys, ht_ids, mask, sentinel_id, key[u]);
+      row_id[i] = id;
+      const bool need = st[u] < s_min[id] || st[u] > s_max[id];
+      if (!__any_sync(act, need)) continue;
+      const uint32_t id0 = __shfl_sync(act, id, __ffs(act) - 1);
+      unsigned peers = act;
+      if (!__all_sync(act, id == id0)) peers = __match_any_sync(act, id);  // one lane per distinct key of the warp
+      const int32_t mn = __reduce_min_sync(peers, st[u]);
+      const int32_t mx = __reduce_max_sync(peers, st[u]);
+      if ((__ffs(peers) - 1) == int(threadIdx.x & 31)) {
+        if (mn < s_min[id]) atomicMin(&s_min[id], mn);
+        if (mx > s_max[id]) atomicMax(&s_max[id], mx);
+      }
+    }
   }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < n_keys; k += blockDim.x)
+    if (s_min[k] <= s_max[k]) {
+      atomicMin(key_min + k, s_min[k]);
+      atomicMax(key_max + k, s_max[k]);
+    }
 }
+
+__global__ void __launch_bounds__(256) k_make_sort_keys32(const uint32_t* __restrict__ row_id, const int32_t* __restrict__ start,
+                                                          const int32_t* __restrict__ end, uint64_t n,
+                                                          const KeyBase* __restrict__ kb, uint32_t* __restrict__ sort_key,
+                                                          uint64_t* __restrict__ sort_val, unsigned int* __restrict__ inverted) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  bool inv = false;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const KeyBase b = kb[row_id[i]];
+    const int32_t st = start[i], en = end[i];
+    sort_key[i] = b.base + (uint32_t(st) - uint32_t(b.min_start));
+    sort_val[i] = (uint64_t(uint32_t(en)) << 32) | uint64_t(uint32_t(i));
+    inv |= en < st;
+  }
+  if (inv) atomicOr(inverted, 1u);
+}
+
+// block maxima of end: level 1 over 32 sorted rows (one warp per block), levels 2 and 3 over 32 entries of the level below
 __global__ void __launch_bounds__(256) k_block_max_up(const int32_t* __restrict__ in, uint64_t n_in, uint64_t n_out,
                                                       int32_t* __restrict__ out) {
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
@@ -136,13 +221,13 @@ __global__ void __launch_bounds__(256) k_block_max_up(const int32_t* __restrict_
 }
 
 // overlap depth of up to 4096 evenly spaced rows: depth(j) = j - first i of j's segment with runmax[i] >= start[j]
-__global__ void __launch_bounds__(256) k_depth_sample(const uint64_t* __restrict__ sorted_key, const int32_t* __restrict__ s_start,
+__global__ void __launch_bounds__(256) k_depth_sample(const uint32_t* __restrict__ s_id, const int32_t* __restrict__ s_start,
                                                       const int32_t* __restrict__ s_runmax, const SegMeta* __restrict__ meta,
                                                       uint64_t n, uint32_t samples, unsigned long long* __restrict__ sum) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= samples) return;
   const uint64_t j = uint64_t(t) * n / samples;
-  const uint32_t sb = meta[uint32_t(sorted_key[j] >> 32)].sb;
+  const uint32_t sb = meta[s_id[j]].sb;
   const int32_t st = s_start[j];
   uint64_t lo = sb, hi = j;  // first i in [sb, j] with runmax[i] >= st (i = j qualifies: end >= start for well-formed rows)
   while (lo < hi) {
@@ -153,11 +238,11 @@ __global__ void __launch_bounds__(256) k_depth_sample(const uint64_t* __restrict
 }
 
 // (id, end) sort keys of the rows in (id, start) order, and back: the ends sorted inside each key segment
-__global__ void __launch_bounds__(256) k_end_keys(const uint64_t* __restrict__ sorted_key, const int32_t* __restrict__ s_end,
+__global__ void __launch_bounds__(256) k_end_keys(const uint32_t* __restrict__ s_id, const int32_t* __restrict__ s_end,
                                                   uint64_t n, uint64_t* __restrict__ out) {
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
   for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride)
-    out[j] = (sorted_key[j] & 0xFFFFFFFF00000000ull) | uint64_t(uint32_t(s_end[j]) ^ 0x80000000u);
+    out[j] = (uint64_t(s_id[j]) << 32) | uint64_t(uint32_t(s_end[j]) ^ 0x80000000u);
 }
 __global__ void __launch_bounds__(256) k_end_values(const uint64_t* __restrict__ sorted, uint64_t n, int32_t* __restrict__ s_send) {
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
@@ -165,28 +250,98 @@ __global__ void __launch_bounds__(256) k_end_values(const uint64_t* __restrict__
     s_send[j] = int32_t(uint32_t(sorted[j]) ^ 0x80000000u);
 }
 
-// After the sort: write start[], row[], end[] (unpacked from the sorted key / value words) and the
-// segment boundaries seg_off[id] = first sorted position of key id.  With s_perm the ids the index hands out are the
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+// word of the segmented running max (see k_runmax_*): id in the high half, end (order-preserving) in the low half
+__device__ __forceinline__ uint64_t scan_word(uint32_t id, int32_t end) {
+  return (uint64_t(id) << 32) | uint64_t(uint32_t(end) ^ 0x80000000u);
+}
+
+__device__ __forceinline__ void tile_max_store(uint64_t m, uint64_t* __restrict__ tile_max) {
+  __shared__ uint64_t wmax[kScanThreads / 32];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t r = 0;
+    for (int w = 0; w < kScanThreads / 32; ++w) r = max(r, wmax[w]);
+    tile_max[blockIdx.x] = r;
+  }
+}
+
+// After the sort, one CTA per tile of kScanTile sorted rows: write start[], row[], end[], id[] (unpacked from the sorted
+// key / value words), the segment boundaries seg_off[id] = first sorted position of key id, and the tile's maximum
+// scan word (the reduce half of the segmented running max below).  With s_perm the ids the index hands out are the
 // sorted positions themselves (row[j] = j) and s_perm[j] keeps the build row: payload stored in that order is read
 // with locality by the gathers (the hits of a probe row are neighbours).
-__global__ void __launch_bounds__(256) k_finalize(const uint64_t* __restrict__ sorted_key,
-                                                  const uint64_t* __restrict__ sorted_val, uint64_t n,
-                                                  int32_t* __restrict__ s_start, int32_t* __restrict__ s_end,
-                                                  uint32_t* __restrict__ s_row, uint32_t* __restrict__ s_perm,
-                                                  uint32_t* __restrict__ seg_off, uint32_t n_keys) {
-  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
-  for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride) {
-    const uint64_t k = sorted_key[j];
+__global__ void __launch_bounds__(kScanThreads) k_finalize(const uint64_t* __restrict__ sorted_key,
+                                                           const uint64_t* __restrict__ sorted_val, uint64_t n,
+                                                           int32_t* __restrict__ s_start, int32_t* __restrict__ s_end,
+                                                           uint32_t* __restrict__ s_row, uint32_t* __restrict__ s_perm,
+                                                           uint32_t* __restrict__ s_id, uint32_t* __restrict__ seg_off,
+                                                           uint32_t n_keys, uint64_t* __restrict__ tile_max) {
+  const uint64_t base = uint64_t(blockIdx.x) * kScanTile;
+  uint64_t m = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const uint64_t j = base + uint64_t(k) * kScanThreads + threadIdx.x;
+    if (j >= n) continue;
+    const uint64_t key = sorted_key[j];
     const uint64_t v = sorted_val[j];
-    s_start[j] = int32_t(uint32_t(k) ^ 0x80000000u);
+    const uint32_t id = uint32_t(key >> 32);
+    const int32_t en = int32_t(uint32_t(v >> 32));
+    s_start[j] = int32_t(uint32_t(key) ^ 0x80000000u);
     // position ids (option cuda_build_ids positions): the probe kernels hand out j itself, the build row goes to perm[]
     s_row[j] = s_perm ? uint32_t(j) : uint32_t(v);
     if (s_perm) s_perm[j] = uint32_t(v);
-    s_end[j] = int32_t(uint32_t(v >> 32));
-    const uint32_t id = uint32_t(k >> 32);
+    s_end[j] = en;
+    s_id[j] = id;
     if (j == 0 || uint32_t(sorted_key[j - 1] >> 32) != id) seg_off[id] = uint32_t(j);
     if (j == n - 1) seg_off[n_keys] = uint32_t(n);
+    m = max(m, scan_word(id, en));
   }
+  tile_max_store(m, tile_max);
+}
+
+// the same for narrow sort keys: id = the key whose [base, next base) holds key32
+__global__ void __launch_bounds__(kScanThreads) k_finalize32(const uint32_t* __restrict__ sorted_key,
+                                                             const uint64_t* __restrict__ sorted_val, uint64_t n,
+                                                             const KeyBase* __restrict__ kb, uint32_t n_keys,
+                                                             int32_t* __restrict__ s_start, int32_t* __restrict__ s_end,
+                                                             uint32_t* __restrict__ s_row, uint32_t* __restrict__ s_perm,
+                                                             uint32_t* __restrict__ s_id, uint32_t* __restrict__ seg_off,
+                                                             uint64_t* __restrict__ tile_max) {
+  extern __shared__ uint32_t s_base[];  // [n_keys]
+  for (uint32_t k = threadIdx.x; k < n_keys; k += blockDim.x) s_base[k] = kb[k].base;
+  __syncthreads();
+  const uint64_t base = uint64_t(blockIdx.x) * kScanTile;
+  uint64_t m = 0;
+#pragma unroll 2
+  for (int k = 0; k < kScanItems; ++k) {
+    const uint64_t j = base + uint64_t(k) * kScanThreads + threadIdx.x;
+    if (j >= n) continue;
+    const uint32_t key = sorted_key[j];
+    const uint64_t v = sorted_val[j];
+    uint32_t lo = 0, len = n_keys;  // last id with base <= key (base[0] = 0)
+    while (len > 1) {
+      const uint32_t half = len >> 1;
+      if (s_base[lo + half] <= key) { lo += half; len -= half; } else len = half;
+    }
+    const uint32_t id = lo;
+    const int32_t en = int32_t(uint32_t(v >> 32));
+    s_start[j] = int32_t(key - s_base[id] + uint32_t(kb[id].min_start));
+    s_row[j] = s_perm ? uint32_t(j) : uint32_t(v);
+    if (s_perm) s_perm[j] = uint32_t(v);
+    s_end[j] = en;
+    s_id[j] = id;
+    if (j == 0 || sorted_key[j - 1] < s_base[id]) seg_off[id] = uint32_t(j);  // every key id has at least one row
+    if (j == n - 1) seg_off[n_keys] = uint32_t(n);
+    m = max(m, scan_word(id, en));
+  }
+  tile_max_store(m, tile_max);
 }
 
 // One thread per key segment: bin geometry (power-of-two bin width, 8-16 rows per bin when the
@@ -213,22 +368,31 @@ __global__ void __launch_bounds__(256) k_seg_meta(const uint32_t* __restrict__ s
   meta[id] = m;
 }
 
-// dir[dir_base + b] = first row of the segment whose bin >= b; dir[dir_base + nbins] = se
-__global__ void __launch_bounds__(256) k_fill_dir(const uint64_t* __restrict__ sorted_key,
+__device__ __forceinline__ uint32_t start_window(int32_t x) { return (uint32_t(x) ^ 0x80000000u) >> 16; }
+
+// dir[dir_base + b] = first row of the segment whose bin >= b; dir[dir_base + nbins] = se.  With `flag` the same pass
+// marks the rows that start a packed line (see "Packed lines" below): it already holds start[j], start[j - 1] and the
+// segment's first row.
+__global__ void __launch_bounds__(256) k_fill_dir(const uint32_t* __restrict__ s_id,
                                                   const int32_t* __restrict__ s_start, uint64_t n,
                                                   const SegMeta* __restrict__ meta,
-                                                  uint32_t* __restrict__ dir) {
+                                                  uint32_t* __restrict__ dir, uint32_t* __restrict__ flag) {
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
   for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride) {
-    const uint32_t id = uint32_t(sorted_key[j] >> 32);
+    const uint32_t id = s_id[j];
     const SegMeta m = meta[id];
     const uint32_t sh = m.shift;
-    const uint32_t bin = sh >= 32 ? 0u : ((uint32_t(s_start[j]) - uint32_t(m.min_start)) >> sh);
+    const int32_t st = s_start[j];
+    const uint32_t bin = sh >= 32 ? 0u : ((uint32_t(st) - uint32_t(m.min_start)) >> sh);
     uint32_t from = 0;
+    bool line_start = true;
     if (j > m.sb) {
-      const uint32_t prev = sh >= 32 ? 0u : ((uint32_t(s_start[j - 1]) - uint32_t(m.min_start)) >> sh);
+      const int32_t pst = s_start[j - 1];
+      const uint32_t prev = sh >= 32 ? 0u : ((uint32_t(pst) - uint32_t(m.min_start)) >> sh);
       from = prev + 1;
+      line_start = (j - m.sb) % kLineRows == 0 || start_window(st) != start_window(pst);
     }
+    if (flag) flag[j] = line_start ? 1u : 0u;
     for (uint32_t b = from; b <= bin; ++b) dir[m.dir_base + b] = uint32_t(j);
     if (j == uint64_t(m.se) - 1) dir[m.dir_base + m.nbins] = m.se;
   }
@@ -243,15 +407,6 @@ __global__ void __launch_bounds__(256) k_fill_dir(const uint64_t* __restrict__ s
 // Directory bins hold 8-16 rows for evenly spread starts: measured on B200 (100M-row index, random
 // probes) 8 beats 16 and 32 (1.87 / 1.98 / 2.15 ms per 12.5M probes) and costs n/2 bytes of directory.
 
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
-constexpr int kScanTile = kScanThreads * kScanItems;
-
-__device__ __forceinline__ uint64_t scan_word(const uint64_t* __restrict__ sorted_key,
-                                              const int32_t* __restrict__ s_end, uint64_t j) {
-  return (sorted_key[j] & 0xFFFFFFFF00000000ull) | uint64_t(uint32_t(s_end[j]) ^ 0x80000000u);
-}
-
 __device__ __forceinline__ uint64_t warp_incl_max(uint64_t v) {
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -259,28 +414,6 @@ __device__ __forceinline__ uint64_t warp_incl_max(uint64_t v) {
     if (int(threadIdx.x & 31) >= d) v = max(v, o);
   }
   return v;
-}
-
-__global__ void __launch_bounds__(kScanThreads) k_runmax_reduce(const uint64_t* __restrict__ sorted_key,
-                                                                const int32_t* __restrict__ s_end,
-                                                                uint64_t n, uint64_t* __restrict__ tile_max) {
-  __shared__ uint64_t wmax[kScanThreads / 32];
-  const uint64_t base = uint64_t(blockIdx.x) * kScanTile;
-  uint64_t m = 0;
-#pragma unroll
-  for (int k = 0; k < kScanItems; ++k) {
-    const uint64_t j = base + uint64_t(k) * kScanThreads + threadIdx.x;
-    if (j < n) m = max(m, scan_word(sorted_key, s_end, j));
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
-  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint64_t r = 0;
-    for (int w = 0; w < kScanThreads / 32; ++w) r = max(r, wmax[w]);
-    tile_max[blockIdx.x] = r;
-  }
 }
 
 // exclusive prefix max over tile_max[0..n_tiles), in place, one CTA of 1024 threads
@@ -313,29 +446,61 @@ __global__ void __launch_bounds__(1024) k_runmax_mid(uint64_t* __restrict__ tile
   }
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_runmax_final(const uint64_t* __restrict__ sorted_key,
+// per-tile rescan, kScanItems consecutive rows per thread (one scan and one barrier per tile; the row-per-thread
+// arrangement needed kScanItems of each: 0.77 ms per 100M rows against 1.6 GB of traffic).  Four threads' rows are exactly
+// one block of the first level of block maxima, written in the same pass.
+__global__ void __launch_bounds__(kScanThreads) k_runmax_final(const uint32_t* __restrict__ s_id,
                                                                const int32_t* __restrict__ s_end, uint64_t n,
                                                                const uint64_t* __restrict__ tile_excl,
-                                                               int32_t* __restrict__ runmax) {
+                                                               int32_t* __restrict__ runmax, int32_t* __restrict__ bmax1) {
+  static_assert(kScanItems == 8, "two 16-byte vectors per thread and array");
   __shared__ uint64_t wtot[kScanThreads / 32];
-  const uint64_t base = uint64_t(blockIdx.x) * kScanTile;
-  uint64_t carry = tile_excl[blockIdx.x];
-  // blocked over k: each pass scans kScanThreads consecutive rows, carry moves to the next pass
-#pragma unroll 1
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t base = uint64_t(blockIdx.x) * kScanTile + uint64_t(threadIdx.x) * kScanItems;
+  int32_t en[kScanItems];
+  uint32_t id[kScanItems];
+  if (base + kScanItems <= n) {  // base is a multiple of 8 rows: 32-byte aligned in both arrays
+    const int4 e0 = *reinterpret_cast<const int4*>(s_end + base), e1 = *reinterpret_cast<const int4*>(s_end + base + 4);
+    const uint4 i0 = *reinterpret_cast<const uint4*>(s_id + base), i1 = *reinterpret_cast<const uint4*>(s_id + base + 4);
+    en[0] = e0.x; en[1] = e0.y; en[2] = e0.z; en[3] = e0.w; en[4] = e1.x; en[5] = e1.y; en[6] = e1.z; en[7] = e1.w;
+    id[0] = i0.x; id[1] = i0.y; id[2] = i0.z; id[3] = i0.w; id[4] = i1.x; id[5] = i1.y; id[6] = i1.z; id[7] = i1.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      en[k] = base + k < n ? s_end[base + k] : INT32_MIN;
+      id[k] = base + k < n ? s_id[base + k] : 0u;
+    }
+  }
+  uint64_t w[kScanItems];
+  uint64_t run = 0;
+  int32_t bm = INT32_MIN;
+#pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
-    const uint64_t j = base + uint64_t(k) * kScanThreads + threadIdx.x;
-    const uint64_t v = j < n ? scan_word(sorted_key, s_end, j) : 0;
-    uint64_t inc = warp_incl_max(v);
-    if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = inc;
-    __syncthreads();
-    uint64_t pre = carry;
-    for (int w = 0; w < int(threadIdx.x >> 5); ++w) pre = max(pre, wtot[w]);
-    inc = max(inc, pre);
-    if (j < n) runmax[j] = int32_t(uint32_t(inc) ^ 0x80000000u);
-    uint64_t tot = carry;
-    for (int w = 0; w < kScanThreads / 32; ++w) tot = max(tot, wtot[w]);
-    carry = tot;
-    __syncthreads();
+    run = max(run, base + k < n ? scan_word(id[k], en[k]) : uint64_t(0));
+    w[k] = run;  // inclusive inside the thread
+    bm = max(bm, en[k]);
+  }
+  bm = max(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
+  bm = max(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
+  if ((lane & 3) == 0 && base < n) bmax1[base >> 5] = bm;
+  const uint64_t inc = warp_incl_max(run);
+  if (lane == 31) wtot[warp] = inc;
+  uint64_t excl = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) excl = 0;
+  __syncthreads();
+  uint64_t pre = tile_excl[blockIdx.x];
+  for (int q = 0; q < warp; ++q) pre = max(pre, wtot[q]);
+  excl = max(excl, pre);
+  int32_t out[kScanItems];
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) out[k] = int32_t(uint32_t(max(w[k], excl)) ^ 0x80000000u);
+  if (base + kScanItems <= n) {
+    *reinterpret_cast<int4*>(runmax + base) = make_int4(out[0], out[1], out[2], out[3]);
+    *reinterpret_cast<int4*>(runmax + base + 4) = make_int4(out[4], out[5], out[6], out[7]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+      if (base + k < n) runmax[base + k] = out[k];
   }
 }
 
@@ -350,17 +515,6 @@ __global__ void __launch_bounds__(kScanThreads) k_runmax_final(const uint64_t* _
 // status[0] |= 1 when some width does not fit 16 bits (the index then keeps only the SoA arrays);
 // status[1] += lines a probe ending at this line's last start would walk back.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t start_window(int32_t x) { return (uint32_t(x) ^ 0x80000000u) >> 16; }
-
-__global__ void __launch_bounds__(256) k_line_flags(const uint64_t* __restrict__ sorted_key, const int32_t* __restrict__ s_start,
-                                                    uint64_t n, const SegMeta* __restrict__ meta, uint32_t* __restrict__ flag) {
-  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
-  for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride) {
-    const uint32_t sb = meta[uint32_t(sorted_key[j] >> 32)].sb;
-    flag[j] = (j == sb || (j - sb) % kLineRows == 0 || start_window(s_start[j]) != start_window(s_start[j - 1])) ? 1u : 0u;
-  }
-}
-
 __global__ void __launch_bounds__(256) k_line_first(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ line_incl,
                                                     uint64_t n, uint32_t* __restrict__ line_first) {
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
@@ -399,20 +553,13 @@ __global__ void __launch_bounds__(256) k_fill_dir_line(const uint32_t* __restric
 
 __global__ void __launch_bounds__(256) k_pack_lines(const int32_t* __restrict__ s_start, const int32_t* __restrict__ s_end,
                                                     const int32_t* __restrict__ s_runmax, const uint32_t* __restrict__ s_row,
-                                                    const SegMeta* __restrict__ meta, uint32_t n_keys, uint64_t n_lines,
+                                                    const uint32_t* __restrict__ s_id, const SegMeta* __restrict__ meta, uint64_t n_lines,
                                                     const uint32_t* __restrict__ line_first, const uint32_t* __restrict__ line_incl,
-                                                    uint4* __restrict__ lines, unsigned long long* status) {
+                                                    uint4* __restrict__ lines, unsigned long long* status, uint32_t stat_every) {
   const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const uint64_t line = t >> 3;
   const uint32_t sub = uint32_t(t & 7);
   if (line >= n_lines) return;
-  // key segment of this line: last id with line_base <= line (meta[n_keys].line_base = n_lines)
-  uint32_t lo = 0, hi = n_keys;
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (uint64_t(meta[mid].line_base) <= line) lo = mid; else hi = mid;
-  }
-  const SegMeta m = meta[lo];
   const uint32_t j0 = line_first[line];
   const uint32_t rows = line_first[line + 1] - j0;  // 1..15
   const int32_t base = s_start[j0];
@@ -429,16 +576,22 @@ __global__ void __launch_bounds__(256) k_pack_lines(const int32_t* __restrict__ 
   uint4 v;
   if (sub == 0) {
     v.x = uint32_t(base);
-    v.y = uint32_t(j0 > m.sb ? s_runmax[j0 - 1] : INT32_MIN);
+    const uint32_t id = s_id[j0];
+    const bool seg_first = j0 == 0 || s_id[j0 - 1] != id;  // no earlier row of this key
+    v.y = uint32_t(seg_first ? INT32_MIN : s_runmax[j0 - 1]);
     enc(0, &v.z, &v.w);
-    // statistic: how many earlier lines does a probe starting at this line's last start visit?
-    const int32_t qs = s_start[j0 + rows - 1];
-    uint32_t a = m.sb, len = j0 - m.sb;  // first row in [sb, j0) with runmax >= qs
-    while (len) {
-      const uint32_t half = len >> 1;
-      if (s_runmax[a + half] < qs) { a += half + 1; len -= half + 1; } else len = half;
+    // statistic, on every stat_every-th line (a binary search of ~20 dependent loads: on every line it cost half of this
+    // kernel): how many earlier lines does a probe starting at this line's last start visit?
+    if (line % stat_every == 0) {
+      const int32_t qs = s_start[j0 + rows - 1];
+      const uint32_t sb = meta[id].sb;
+      uint32_t a = sb, len = j0 - sb;  // first row in [sb, j0) with runmax >= qs
+      while (len) {
+        const uint32_t half = len >> 1;
+        if (s_runmax[a + half] < qs) { a += half + 1; len -= half + 1; } else len = half;
+      }
+      if (a < j0) atomicAdd(status + 1, (unsigned long long)(uint32_t(line) - (line_incl[a] - 1u)));
     }
-    if (a < j0) atomicAdd(status + 1, (unsigned long long)(uint32_t(line) - (line_incl[a] - 1u)));
   } else {
     enc(2 * sub - 1, &v.x, &v.y);
     enc(2 * sub, &v.z, &v.w);
@@ -586,47 +739,92 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     SQ_CUDA(E, tmp.alloc(&d_seg_off, (size_t(n_keys) + 1) * 4));
     const int g = grid_for(n, 256, ctx->sm_count);
     unsigned int* d_inverted = d_counter + 1;  // zeroed with the hash-table status above
-    k_make_sort_keys<<<g, 256, 0, st>>>(d_key, d_start, d_end, n, idx->d_ht_keys, idx->d_ht_ids, cap - 1,
-                                        idx->sentinel_id, d_k0, d_v0, d_inverted);
-    SQ_CUDA(E, cudaGetLastError());
-
-    int key_bits = 0;
-    while ((1ull << key_bits) < uint64_t(n_keys)) ++key_bits;
-    const int end_bit = 32 + key_bits;
-    size_t temp_bytes = 0;
-    SQ_CUDA(E, ::sq_cub::cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_k0, d_k1, d_v0, d_v1, n, 0, end_bit, st));
-    void* d_temp = nullptr;
-    SQ_CUDA(E, tmp.alloc(&d_temp, temp_bytes));
-    SQ_CUDA(E, ::sq_cub::cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_k0, d_k1, d_v0, d_v1, n, 0, end_bit, st));
-
-    k_finalize<<<g, 256, 0, st>>>(d_k1, d_v1, n, idx->d_start, idx->d_end, idx->d_row, idx->d_perm, d_seg_off, n_keys);
-    SQ_CUDA(E, cudaGetLastError());
-
-    // 3. running max of end inside each key segment
     const uint32_t n_tiles = uint32_t((n + kScanTile - 1) / kScanTile);
     uint64_t* d_tile = nullptr;
+    uint32_t* d_sid = nullptr;  // key id of every sorted row
     SQ_CUDA(E, tmp.alloc(&d_tile, size_t(n_tiles) * 8));
-    k_runmax_reduce<<<n_tiles, kScanThreads, 0, st>>>(d_k1, idx->d_end, n, d_tile);
-    SQ_CUDA(E, cudaGetLastError());
-    k_runmax_mid<<<1, 1024, 0, st>>>(d_tile, n_tiles);
-    SQ_CUDA(E, cudaGetLastError());
-    k_runmax_final<<<n_tiles, kScanThreads, 0, st>>>(d_k1, idx->d_end, n, d_tile, idx->d_runmax);
-    SQ_CUDA(E, cudaGetLastError());
+    SQ_CUDA(E, tmp.alloc(&d_sid, n * 4));
 
-    // 3b. block maxima of end (32 / 1024 / 32768 rows): long candidate ranges are walked through them
-    {
-      const uint64_t n1 = (n + 31) / 32, n2 = (n1 + 31) / 32, n3 = (n2 + 31) / 32;
-      SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_bmax, (n1 + n2 + n3) * 4, pool, st));
-      idx->bmax_n1 = n1;
-      idx->bmax_n2 = n2;
-      idx->bytes += (n1 + n2 + n3) * 4;
-      k_block_max_rows<<<grid_for(n1 * 32, 256, ctx->sm_count), 256, 0, st>>>(idx->d_end, n, n1, idx->d_bmax);
+    // narrow (32-bit) sort keys when the key ranges laid end to end fit 32 bits (option cuda_build_sort wide: never)
+    bool narrow = false;
+    KeyBase* d_kb = nullptr;
+    int end_bit = 32;
+    uint32_t* d_rid = reinterpret_cast<uint32_t*>(d_k1);  // id of every build row: lives in the sort's second key buffer
+    if (n_keys <= kNarrowMaxKeys && ctx->opt.build_sort.load(std::memory_order_relaxed) == 0) {
+      int32_t* d_rng = nullptr;  // [n_keys] min, [n_keys] max
+      SQ_CUDA(E, tmp.alloc(&d_rng, size_t(n_keys) * 8));
+      SQ_CUDA(E, tmp.alloc(&d_kb, size_t(n_keys) * sizeof(KeyBase)));
+      std::vector<int32_t> h_rng(size_t(n_keys) * 2);
+      for (uint32_t k = 0; k < n_keys; ++k) { h_rng[k] = INT32_MAX; h_rng[n_keys + k] = INT32_MIN; }
+      SQ_CUDA(E, cudaMemcpyAsync(d_rng, h_rng.data(), h_rng.size() * 4, cudaMemcpyHostToDevice, st));
+      k_key_ranges<<<grid_for(n, 256, ctx->sm_count), 256, size_t(n_keys) * 8, st>>>(
+          d_key, d_start, n, idx->d_ht_keys, idx->d_ht_ids, cap - 1, idx->sentinel_id, n_keys, d_rid, d_rng, d_rng + n_keys);
       SQ_CUDA(E, cudaGetLastError());
-      k_block_max_up<<<grid_for(n2, 256, ctx->sm_count), 256, 0, st>>>(idx->d_bmax, n1, n2, idx->d_bmax + n1);
+      SQ_CUDA(E, cudaMemcpyAsync(h_rng.data(), d_rng, h_rng.size() * 4, cudaMemcpyDeviceToHost, st));
+      SQ_CUDA(E, cudaStreamSynchronize(st));
+      std::vector<KeyBase> h_kb(n_keys);
+      uint64_t acc = 0;
+      for (uint32_t k = 0; k < n_keys; ++k) {
+        h_kb[k].base = uint32_t(acc);
+        h_kb[k].min_start = h_rng[k];
+        acc += uint64_t(int64_t(h_rng[n_keys + k]) - int64_t(h_rng[k])) + 1ull;
+        if (acc > (1ull << 32)) break;
+      }
+      if (acc <= (1ull << 32)) {
+        narrow = true;
+        end_bit = 1;
+        while (end_bit < 32 && (1ull << end_bit) < acc) ++end_bit;
+        SQ_CUDA(E, cudaMemcpyAsync(d_kb, h_kb.data(), size_t(n_keys) * sizeof(KeyBase), cudaMemcpyHostToDevice, st));
+        SQ_CUDA(E, cudaStreamSynchronize(st));  // h_kb goes out of scope below
+      }
+    }
+    if (narrow) {
+      // the 32-bit keys and their double buffer share d_k0 (n * 8 bytes)
+      uint32_t* d_n0 = reinterpret_cast<uint32_t*>(d_k0);
+      uint32_t* d_n1 = d_n0 + n;
+      k_make_sort_keys32<<<g, 256, 0, st>>>(d_rid, d_start, d_end, n, d_kb, d_n0, d_v0, d_inverted);
       SQ_CUDA(E, cudaGetLastError());
-      k_block_max_up<<<grid_for(n3, 256, ctx->sm_count), 256, 0, st>>>(idx->d_bmax + n1, n2, n3, idx->d_bmax + n1 + n2);
+      size_t temp_bytes = 0;
+      SQ_CUDA(E, ::sq_cub::cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_n0, d_n1, d_v0, d_v1, n, 0, end_bit, st));
+      void* d_temp = nullptr;
+      SQ_CUDA(E, tmp.alloc(&d_temp, temp_bytes));
+      SQ_CUDA(E, ::sq_cub::cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_n0, d_n1, d_v0, d_v1, n, 0, end_bit, st));
+      k_finalize32<<<n_tiles, kScanThreads, size_t(n_keys) * 4, st>>>(d_n1, d_v1, n, d_kb, n_keys, idx->d_start, idx->d_end,
+                                                                       idx->d_row, idx->d_perm, d_sid, d_seg_off, d_tile);
+      SQ_CUDA(E, cudaGetLastError());
+    } else {
+      k_make_sort_keys<<<g, 256, 0, st>>>(d_key, d_start, d_end, n, idx->d_ht_keys, idx->d_ht_ids, cap - 1,
+                                          idx->sentinel_id, d_k0, d_v0, d_inverted);
+      SQ_CUDA(E, cudaGetLastError());
+      int key_bits = 0;
+      while ((1ull << key_bits) < uint64_t(n_keys)) ++key_bits;
+      end_bit = 32 + key_bits;
+      size_t temp_bytes = 0;
+      SQ_CUDA(E, ::sq_cub::cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_k0, d_k1, d_v0, d_v1, n, 0, end_bit, st));
+      void* d_temp = nullptr;
+      SQ_CUDA(E, tmp.alloc(&d_temp, temp_bytes));
+      SQ_CUDA(E, ::sq_cub::cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_k0, d_k1, d_v0, d_v1, n, 0, end_bit, st));
+      k_finalize<<<n_tiles, kScanThreads, 0, st>>>(d_k1, d_v1, n, idx->d_start, idx->d_end, idx->d_row, idx->d_perm, d_sid,
+                                                   d_seg_off, n_keys, d_tile);
       SQ_CUDA(E, cudaGetLastError());
     }
+    idx->narrow_sort = narrow;
+
+    // 3. running max of end inside each key segment (the per-tile maxima came out of the finalize pass), and the block
+    // maxima of end (32 / 1024 / 32768 rows): long candidate ranges are walked through them
+    const uint64_t n1 = (n + 31) / 32, n2 = (n1 + 31) / 32, n3 = (n2 + 31) / 32;
+    SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_bmax, (n1 + n2 + n3) * 4, pool, st));
+    idx->bmax_n1 = n1;
+    idx->bmax_n2 = n2;
+    idx->bytes += (n1 + n2 + n3) * 4;
+    k_runmax_mid<<<1, 1024, 0, st>>>(d_tile, n_tiles);
+    SQ_CUDA(E, cudaGetLastError());
+    k_runmax_final<<<n_tiles, kScanThreads, 0, st>>>(d_sid, idx->d_end, n, d_tile, idx->d_runmax, idx->d_bmax);
+    SQ_CUDA(E, cudaGetLastError());
+    k_block_max_up<<<grid_for(n2, 256, ctx->sm_count), 256, 0, st>>>(idx->d_bmax, n1, n2, idx->d_bmax + n1);
+    SQ_CUDA(E, cudaGetLastError());
+    k_block_max_up<<<grid_for(n3, 256, ctx->sm_count), 256, 0, st>>>(idx->d_bmax + n1, n2, n3, idx->d_bmax + n1 + n2);
+    SQ_CUDA(E, cudaGetLastError());
 
     // 4. per-segment bin directory (geometry on the device, offsets by a host scan: #keys is small)
     uint32_t rows_per_bin = uint32_t(ctx->opt.rows_per_bin.load(std::memory_order_relaxed));
@@ -651,15 +849,13 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_dir, dir_total * 4, pool, st));
     idx->bytes += dir_total * 4;
     idx->dir_bytes = dir_total * 4;
-    k_fill_dir<<<g, 256, 0, st>>>(d_k1, idx->d_start, n, idx->d_meta, idx->d_dir);
-    SQ_CUDA(E, cudaGetLastError());
-
-    // 5. packed lines for narrow indexes (every width < 65536)
     uint32_t *d_flag = nullptr, *d_line_incl = nullptr, *d_line_first = nullptr;
     SQ_CUDA(E, tmp.alloc(&d_flag, n * 4));
     SQ_CUDA(E, tmp.alloc(&d_line_incl, n * 4));
-    k_line_flags<<<g, 256, 0, st>>>(d_k1, idx->d_start, n, idx->d_meta, d_flag);
+    k_fill_dir<<<g, 256, 0, st>>>(d_sid, idx->d_start, n, idx->d_meta, idx->d_dir, d_flag);  // + the line-start flags of step 5
     SQ_CUDA(E, cudaGetLastError());
+
+    // 5. packed lines for narrow indexes (every width < 65536)
     size_t scan_bytes = 0;
     SQ_CUDA(E, ::sq_cub::cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, d_flag, d_line_incl, n, st));
     void* d_scan_tmp = nullptr;
@@ -679,16 +875,25 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
                                                                              idx->d_start, idx->d_dir_line);
     SQ_CUDA(E, cudaGetLastError());
     unsigned long long* d_pstat = nullptr;
-    SQ_CUDA(E, tmp.alloc(&d_pstat, 16));
-    SQ_CUDA(E, cudaMemsetAsync(d_pstat, 0, 16, st));
+    SQ_CUDA(E, tmp.alloc(&d_pstat, 32));
+    SQ_CUDA(E, cudaMemsetAsync(d_pstat, 0, 32, st));
     SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_lines, line_total * 128, pool, st));
+    const uint32_t stat_every = line_total > (1u << 16) ? 32u : 1u;
     k_pack_lines<<<unsigned((line_total * 8 + 255) / 256), 256, 0, st>>>(idx->d_start, idx->d_end, idx->d_runmax, idx->d_row,
-                                                                          idx->d_meta, n_keys, line_total, d_line_first,
-                                                                          d_line_incl, idx->d_lines, d_pstat);
+                                                                          d_sid, idx->d_meta, line_total, d_line_first,
+                                                                          d_line_incl, idx->d_lines, d_pstat, stat_every);
     SQ_CUDA(E, cudaGetLastError());
-    unsigned long long h_pstat[2] = {0, 0};
-    SQ_CUDA(E, cudaMemcpyAsync(h_pstat, d_pstat, 16, cudaMemcpyDeviceToHost, st));
+    // the sampled overlap depth (step 6 decides on it) and the "some row has end < start" flag come back with the line
+    // statistics: one copy, one wait
+    const uint32_t samples = uint32_t(n < 4096 ? n : 4096);
+    k_depth_sample<<<(samples + 255) / 256, 256, 0, st>>>(d_sid, idx->d_start, idx->d_runmax, idx->d_meta, n, samples, d_pstat + 2);
+    SQ_CUDA(E, cudaGetLastError());
+    unsigned long long h_pstat[4] = {0, 0, 0, 0};
+    unsigned int h_inverted = 0;
+    SQ_CUDA(E, cudaMemcpyAsync(h_pstat, d_pstat, 32, cudaMemcpyDeviceToHost, st));
+    SQ_CUDA(E, cudaMemcpyAsync(&h_inverted, d_inverted, 4, cudaMemcpyDeviceToHost, st));
     SQ_CUDA(E, cudaStreamSynchronize(st));
+    idx->mean_depth = float(double(h_pstat[2]) / double(samples));
     if (h_pstat[0]) {  // wide or inverted intervals: the SoA arrays serve this index
       cudaFree(idx->d_lines);
       cudaFree(idx->d_dir_line);
@@ -696,7 +901,7 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
       idx->d_dir_line = nullptr;
     } else {
       idx->n_lines = line_total;
-      idx->mean_back_lines = float(double(h_pstat[1]) / double(line_total));
+      idx->mean_back_lines = float(double(h_pstat[1]) / double((line_total + stat_every - 1) / stat_every));
       idx->bytes += line_total * 128 + dir_total * 8;
     }
 
@@ -704,23 +909,13 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     // packed-line kernel never reads it): the same rows' ends sorted inside each key segment plus a bin directory, so
     // that a probe row's hit count is |{start <= qe}| - |{end < qs}| without touching a candidate (sq_probe_rank.cu).
     // Needs start <= end on every build row.
-    unsigned int h_inverted = 0;
-    SQ_CUDA(E, cudaMemcpyAsync(&h_inverted, d_inverted, 4, cudaMemcpyDeviceToHost, st));
-    SQ_CUDA(E, cudaStreamSynchronize(st));
-    {
-      const uint32_t samples = uint32_t(n < 4096 ? n : 4096);
-      SQ_CUDA(E, cudaMemsetAsync(d_pstat, 0, 8, st));
-      k_depth_sample<<<(samples + 255) / 256, 256, 0, st>>>(d_k1, idx->d_start, idx->d_runmax, idx->d_meta, n, samples, d_pstat);
-      SQ_CUDA(E, cudaGetLastError());
-      unsigned long long h_sum = 0;
-      SQ_CUDA(E, cudaMemcpyAsync(&h_sum, d_pstat, 8, cudaMemcpyDeviceToHost, st));
-      SQ_CUDA(E, cudaStreamSynchronize(st));
-      idx->mean_depth = float(double(h_sum) / double(samples));
-    }
     const int rank_opt = ctx->opt.rank_count.load(std::memory_order_relaxed);
     if (!h_inverted && !use_packed(idx) && (rank_opt == 2 || (rank_opt == 1 && idx->mean_depth >= 48.f))) {
-      k_end_keys<<<g, 256, 0, st>>>(d_k1, idx->d_end, n, d_k0);
+      k_end_keys<<<g, 256, 0, st>>>(d_sid, idx->d_end, n, d_k0);
       SQ_CUDA(E, cudaGetLastError());
+      int key_bits = 0;
+      while ((1ull << key_bits) < uint64_t(n_keys)) ++key_bits;
+      end_bit = 32 + key_bits;  // (id, end) words are 64-bit whatever the first sort used
       size_t tb = 0;
       SQ_CUDA(E, ::sq_cub::cub::DeviceRadixSort::SortKeys(nullptr, tb, d_k0, d_v0, n, 0, end_bit, st));
       void* d_t2 = nullptr;
@@ -744,7 +939,7 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
         h_em[n_keys] = SegMeta{};
         SQ_CUDA(E, cudaMemcpyAsync(idx->d_emeta, h_em.data(), (size_t(n_keys) + 1) * sizeof(SegMeta), cudaMemcpyHostToDevice, st));
         SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_edir, edir_total * 4, pool, st));
-        k_fill_dir<<<g, 256, 0, st>>>(d_v0, idx->d_send, n, idx->d_emeta, idx->d_edir);
+        k_fill_dir<<<g, 256, 0, st>>>(d_sid, idx->d_send, n, idx->d_emeta, idx->d_edir, nullptr);  // same segments, same ids
         SQ_CUDA(E, cudaGetLastError());
         SQ_CUDA(E, cudaStreamSynchronize(st));  // h_em must outlive its async copy
         idx->bytes += n * 4 + edir_total * 4 + (uint64_t(n_keys) + 1) * sizeof(SegMeta);

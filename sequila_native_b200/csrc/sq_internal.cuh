@@ -124,6 +124,7 @@ struct HostPool {
 // while partitions probe on others; every reader takes one consistent value per call.
 struct sq_options {
   std::atomic<int> probe_layout{0};         // 0 auto, 1 packed lines (when the index has them), 2 SoA arrays
+  std::atomic<int> build_sort{0};           // sort keys of the build: 0 auto (32-bit when the key ranges fit), 1 always 64-bit
   std::atomic<int> build_ids{0};            // ids an index hands out: 0 build rows, 1 sorted positions (payload kept in that order)
   std::atomic<int> probe_tiles{1};          // tiles per CTA of an emitting packed-line launch: 1 / 2
   std::atomic<int> probe_block{128};        // rows per CTA of the packed-line kernels: 64 / 128 / 256
@@ -177,6 +178,7 @@ struct sq_index {
   int32_t* d_runmax = nullptr;
   int32_t* d_end = nullptr;
   uint32_t* d_row = nullptr;
+  bool narrow_sort = false;    // the build sorted 32-bit keys (key ranges laid end to end)
   bool pos_ids = false;        // option cuda_build_ids positions: d_row[j] = j, payload columns are stored in sorted order
   uint32_t* d_perm = nullptr;  // pos_ids: sorted position -> build row
   std::mutex perm_mu;          // pos_ids: payload columns are permuted one at a time on perm_stream

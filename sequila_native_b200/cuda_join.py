@@ -144,6 +144,7 @@ class CudaIndex:
     build_ms = property(lambda self: float(self._lib.sq_index_build_ms(self._h)))
     uses_packed = property(lambda self: bool(self._lib.sq_index_uses_packed(self._h)))
     uses_rank = property(lambda self: bool(self._lib.sq_index_uses_rank(self._h)))
+    sort_key_bits = property(lambda self: int(self._lib.sq_index_sort_key_bits(self._h)))
     uses_positions = property(lambda self: bool(self._lib.sq_index_uses_positions(self._h)))
 
     def position_rows(self) -> np.ndarray:

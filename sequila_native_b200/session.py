@@ -55,7 +55,7 @@ from dataclasses import field  # noqa: E402
 # validated by the library when the exec node applies them, as ConfigField::set does for the reference's own fields
 CUDA_KEYS = ("cuda_probe_layout", "cuda_staged_probe", "cuda_probe_block", "cuda_probe_tiles", "cuda_lookback_backoff_ns", "cuda_rows_per_bin",
              "cuda_right_idx_wire", "cuda_l2_persist_mb", "cuda_scan_dict_capacity", "cuda_exec_trace", "cuda_pipeline_depth",
-             "cuda_coalesce_rows", "cuda_rank_count", "cuda_build_ids")
+             "cuda_coalesce_rows", "cuda_rank_count", "cuda_build_ids", "cuda_build_sort")
 
 
 @dataclass
