@@ -471,7 +471,7 @@ def sub_config(sn, torch, ctx, name, device, hbm_peak, steps, flush):
             "count_only_ms": c_ms, "build_ms": idx.build_ms, "digest": {"pairs": dg[0], "sum": dg[1]}}
 
 
-def exec_node_line(sn, args, n_build=2_000_000, n_probe=2_000_000, batch_rows=8192, build_ids=None):
+def exec_node_line(sn, args, n_build=2_000_000, n_probe=2_000_000, batch_rows=8192, build_ids=None, options=None):
     """The layer a DataFusion user hits (IntervalJoinExec over Arrow RecordBatches, interval_join.rs:1192-1233,
     1580-1640): cfg5-shaped rows at 2 % scale, Utf8 contig column, probe side fed in 8192-row batches (DataFusion's
     default batch size), the six joined columns out."""
@@ -487,12 +487,16 @@ def exec_node_line(sn, args, n_build=2_000_000, n_probe=2_000_000, batch_rows=81
     cols = ["contig", "pos_start", "pos_end"]
 
     def table(s):
-        return pa.record_batch([pa.array(names[s["contig"]]), pa.array(s["start"]), pa.array(s["end"])], names=cols)
+        # `take` of the 24 names: pa.array() of a big numpy string array comes back chunked
+        contig = pa.array(names.tolist(), pa.string()).take(pa.array(s["contig"].astype(np.int32)))
+        return pa.record_batch([contig, pa.array(s["start"]), pa.array(s["end"])], names=cols)
     L, R = table(b), table(p)
     cfg = sn.SequilaConfig()
     sn.apply_set(cfg, "SET sequila.interval_join_algorithm TO cuda")
     if build_ids:  # A/B runs (tools/time_exec_ids.py); the node's own default is position ids
         sn.apply_set(cfg, f"SET sequila.cuda_build_ids TO {build_ids}")
+    for k, v in (options or {}).items():
+        sn.apply_set(cfg, f"SET sequila.{k} TO {v}")
     f = IV.parse_condition_sql("a.pos_start <= b.pos_end AND a.pos_end >= b.pos_start", "a", cols, "b", cols)
     plan = optimize(HashJoinDesc(L.schema, R.schema, [("contig", "contig")], f), cfg)
     t0 = time.perf_counter()

@@ -65,7 +65,7 @@ int32_t sq_device_count(void);
  *   cuda_scan_dict_capacity   power of two          text scan: initial key-dictionary capacity
  *   cuda_exec_trace           0 | 1                 exec node: per-phase wall times on stderr
  *   cuda_pipeline_depth       2..8                  sq_stream_submit: tiles in flight per stream (default 3)
- *   cuda_coalesce_rows        1..2^27               exec node: probe rows that make one tile (default 1048576)
+ *   cuda_coalesce_rows        1..2^27               exec node: probe rows that make one tile (default 524288)
  *   cuda_rank_count           on | off              build: rank structure over the ends (rank-difference count, one walk)
  *   cuda_build_sort           auto | wide           build: 32-bit sort keys when they fit (see sq_index_sort_key_bits) or always 64-bit
  *   cuda_build_ids            rows | positions      build: what left_idx means (see sq_index_uses_positions; default rows)

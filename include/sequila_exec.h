@@ -95,10 +95,13 @@ int32_t sq_exec_probe_begin(sq_exec* e, int32_t partition, const struct ArrowArr
 int32_t sq_exec_probe_next(sq_exec* e, int32_t partition, struct ArrowArray* out, int32_t* has_more_out);
 /* Probe-batch coalescing.  The reference joins every probe batch on its own (<= 8192 rows by default, IJ:1192-1233); a GPU
  * launch chain and a PCIe round trip per 8192 rows are bound by their latencies, so batches are pushed (ownership moves,
- * like sq_exec_push_build) and leave as ONE tile once `cuda_coalesce_rows` rows (sq_exec_set_option, default 1048576) are
- * waiting: *ready_out = 1 then.  sq_exec_probe_pop joins the waiting batches if they reached the target (or if `flush`
- * != 0: end of the probe stream) and fills *out with ONE output batch for all of them, rows in probe order; *has_out = 0
- * when nothing was due. */
+ * like sq_exec_push_build) and leave as ONE tile once `cuda_coalesce_rows` rows (sq_exec_set_option, default 524288) are
+ * waiting: *ready_out = 1 then.  sq_exec_probe_pop takes the waiting batches as a tile if they reached the target (or if
+ * `flush` != 0: end of the probe stream).  Tiles are pipelined two deep per partition: the call concatenates, hashes and
+ * casts the new tile on the calling thread while a worker thread still runs the previous tile on the GPU, then fills *out
+ * with the PREVIOUS tile's output batch (ONE batch per tile, rows in probe order, *has_out = 1) and starts the worker of the
+ * new one; *has_out = 0 when no finished tile was due.  At the end of the probe stream call it with flush != 0 until
+ * *has_out = 0. */
 int32_t sq_exec_probe_push(sq_exec* e, int32_t partition, struct ArrowArray* batch, int32_t* ready_out);
 int32_t sq_exec_probe_pop(sq_exec* e, int32_t partition, int32_t flush, struct ArrowArray* out, int32_t* has_out);
 /* [0] build_input_batches [1] build_input_rows [2] build_mem_used [3] input_batches [4] input_rows

@@ -142,6 +142,27 @@ struct Pending {
   uint64_t rows = 0;
 };
 
+// One coalesced tile on its way through the GPU.  The caller's thread concatenates, hashes and casts the tile (prep),
+// a worker thread runs the probe and assembles the output batch; while it does, the caller pushes and preps the next tile.
+struct TileJob {
+  std::thread th;
+  Pending take;             // the batches the tile was made of (owned)
+  ArrowArray joined{};      // their concatenation when there is more than one
+  const ArrowArray* tile = nullptr;
+  std::vector<uint64_t> keys;
+  std::vector<int32_t> start, end;
+  ArrowArray out{};
+  uint64_t n_pairs = 0;
+  uint64_t worker_ns = 0;
+  int rc = 0;
+  ~TileJob() {
+    if (th.joinable()) th.join();
+    if (joined.release) joined.release(&joined);
+    for (ArrowArray& b : take.batches) if (b.release) b.release(&b);
+    if (out.release) out.release(&out);  // an output nobody collected
+  }
+};
+
 struct sq_exec {
   sq_exec_config cfg{};
   std::vector<int32_t> on_left, on_right, projection;
@@ -155,6 +176,7 @@ struct sq_exec {
   std::map<int32_t, sq_stream*> streams;
   std::map<int32_t, PartState> parts;
   std::map<int32_t, Pending> pending;
+  std::map<int32_t, std::unique_ptr<TileJob>> jobs;  // partition -> the tile its worker thread is joining
   std::string err;
   uint64_t m[16] = {};
   bool built = false;
@@ -692,18 +714,27 @@ namespace {
 
 // hashes the keys, casts the interval columns and runs the probe of one batch on the GPU; the result stays
 // on the device.  *n_out = output rows of the whole batch.
-int probe_on_device(sq_exec* e, sq_stream* st, const ArrowArray* batch, uint64_t* n_out) {
-  const uint64_t n = uint64_t(batch->length);
-  if (n > 0xFFFFFFFFull) return e->fail(SQ_EINVAL, "probe batch too large");
-  std::vector<uint64_t> keys;
-  std::vector<int32_t> start, end;
+// host half: key hashes and the i32 view of the interval columns of one probe tile (`cast` is the stream a BIGINT column is
+// cast on: the partition's own, or its second one when a worker thread is using the first)
+int prep_tile(sq_exec* e, sq_stream* cast, const ArrowArray* batch, std::vector<uint64_t>* keys, std::vector<int32_t>* start,
+              std::vector<int32_t>* end) {
+  if (uint64_t(batch->length) > 0xFFFFFFFFull) return e->fail(SQ_EINVAL, "probe batch too large");
   int rc;
   Trace tr(e->ctx);
-  if ((rc = hash_keys(e, e->right, e->on_right, batch, &keys))) return rc;
+  if ((rc = hash_keys(e, e->right, e->on_right, batch, keys))) return rc;
   tr.lap("hash_keys");
-  if ((rc = eval_i32(e, st, e->right, e->cfg.right_start, false, batch, &start))) return rc;
-  if ((rc = eval_i32(e, st, e->right, e->cfg.right_end, e->cfg.right_end_minus_one != 0, batch, &end))) return rc;
+  if ((rc = eval_i32(e, cast, e->right, e->cfg.right_start, false, batch, start))) return rc;
+  if ((rc = eval_i32(e, cast, e->right, e->cfg.right_end, e->cfg.right_end_minus_one != 0, batch, end))) return rc;
   tr.lap("eval_i32 x2");
+  return SQ_OK;
+}
+
+// device half: the probe of one prepared tile; the result stays on the device.  *n_out = output rows of the whole tile.
+int probe_tile(sq_exec* e, sq_stream* st, const std::vector<uint64_t>& keys, const std::vector<int32_t>& start,
+               const std::vector<int32_t>& end, uint64_t* n_out) {
+  const uint64_t n = keys.size();
+  int rc;
+  Trace tr(e->ctx);
   uint64_t n_pairs = 0;
   if (e->cfg.algorithm == SQ_EXEC_NEAREST) {  // one output row per probe row; the left side may be NULL (IJ:1593-1602)
     rc = sq_probe_nearest(st, e->index, keys.data(), start.data(), end.data(), uint32_t(n), nullptr);
@@ -723,6 +754,15 @@ int probe_on_device(sq_exec* e, sq_stream* st, const ArrowArray* batch, uint64_t
   tr.lap("probe on device");
   *n_out = n_pairs;
   return SQ_OK;
+}
+
+// hashes the keys, casts the interval columns and runs the probe of one batch on the GPU
+int probe_on_device(sq_exec* e, sq_stream* st, const ArrowArray* batch, uint64_t* n_out) {
+  std::vector<uint64_t> keys;
+  std::vector<int32_t> start, end;
+  int rc = prep_tile(e, st, batch, &keys, &start, &end);
+  if (rc) return rc;
+  return probe_tile(e, st, keys, start, end, n_out);
 }
 
 // one output RecordBatch = `take` of every projected column over the stream's current pair window
@@ -1156,46 +1196,101 @@ SQ_API int32_t sq_exec_probe_push(sq_exec* e, int32_t partition, ArrowArray* bat
   return SQ_OK;
 }
 
+// Tiles are pipelined two deep per partition.  A call that finds a tile ready preps it on the calling thread while the
+// previous tile's worker thread is still on the GPU, then collects the previous tile's output and starts the worker of the
+// new one; the output of a tile therefore leaves one call later than the tile went in (at the latest with flush, which
+// the caller repeats until nothing comes back).  Row order across output batches is the probe order, as before.
 SQ_API int32_t sq_exec_probe_pop(sq_exec* e, int32_t partition, int32_t flush, ArrowArray* out, int32_t* has_out) {
   if (!e || !out || !has_out) return SQ_EINVAL;
   *has_out = 0;
   const uint64_t target = coalesce_target(e);
-  Pending take;
+  std::unique_ptr<TileJob> prev, next;
   {
     std::lock_guard<std::mutex> g(e->mu);
+    auto jt = e->jobs.find(partition);
+    if (jt != e->jobs.end()) { prev = std::move(jt->second); e->jobs.erase(jt); }
     auto it = e->pending.find(partition);
-    if (it == e->pending.end() || it->second.batches.empty()) return SQ_OK;
-    if (it->second.rows < target && !flush) return SQ_OK;
-    take = std::move(it->second);
-    e->pending.erase(it);
+    if (it != e->pending.end() && !it->second.batches.empty() && (it->second.rows >= target || flush)) {
+      next.reset(new TileJob());
+      next->take = std::move(it->second);
+      e->pending.erase(it);
+    }
   }
-  struct Drop {
-    Pending& p;
-    ~Drop() { for (ArrowArray& b : p.batches) if (b.release) b.release(&b); }
-  } drop{take};
+  if (!prev && !next) return SQ_OK;
   const auto t0 = Clock::now();
-  sq_stream* st = nullptr;
-  int rc = stream_for(e, partition, &st);
-  if (rc) return rc;
-  ArrowArray joined{};
-  const ArrowArray* tile = &take.batches[0];
-  if (take.batches.size() > 1) {
-    Trace tr(e->ctx);
-    if ((rc = concat_batches(e, e->right, take.batches, &joined))) return rc;
-    tile = &joined;
-    tr.lap("concat batches");
+  auto put_back = [&](std::unique_ptr<TileJob>& j) {
+    std::lock_guard<std::mutex> g(e->mu);
+    e->jobs[partition] = std::move(j);
+  };
+  int rc = SQ_OK;
+  if (next) {  // host half of the new tile, beside the worker of the previous one
+    sq_stream* cast = nullptr;
+    if ((rc = stream_for(e, partition + (1 << 20), &cast)) == SQ_OK) {
+      next->tile = &next->take.batches[0];
+      if (next->take.batches.size() > 1) {
+        Trace tr(e->ctx);
+        rc = concat_batches(e, e->right, next->take.batches, &next->joined);
+        next->tile = &next->joined;
+        tr.lap("concat batches");
+      }
+      if (rc == SQ_OK) rc = prep_tile(e, cast, next->tile, &next->keys, &next->start, &next->end);
+    }
+    if (rc) {  // the new tile is dropped with its error; the previous one stays collectable
+      if (prev) put_back(prev);
+      return rc;
+    }
   }
-  uint64_t n_pairs = 0;
-  rc = probe_on_device(e, st, tile, &n_pairs);
-  if (rc == SQ_OK) rc = assemble_output(e, st, tile, n_pairs, out);
-  if (joined.release) joined.release(&joined);
-  if (rc) return rc;
-  *has_out = 1;
+  const uint64_t host_ns = uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - t0).count());
+  uint64_t worker_ns = 0, n_pairs = 0;
+  bool have = false;
+  if (prev) {
+    prev->th.join();
+    rc = prev->rc;
+    worker_ns = prev->worker_ns;
+    n_pairs = prev->n_pairs;
+    if (rc == SQ_OK) {
+      *out = prev->out;  // move
+      prev->out.release = nullptr;
+      have = true;
+    }
+    prev.reset();
+    if (rc) return rc;  // its message is in e->err; `next` is dropped
+  }
+  if (next) {
+    sq_stream* st = nullptr;
+    if ((rc = stream_for(e, partition, &st))) { if (have && out->release) out->release(out); return rc; }
+    TileJob* j = next.get();
+    j->th = std::thread([e, st, j]() {
+      const auto w0 = Clock::now();
+      j->rc = probe_tile(e, st, j->keys, j->start, j->end, &j->n_pairs);
+      if (j->rc == SQ_OK) j->rc = assemble_output(e, st, j->tile, j->n_pairs, &j->out);
+      j->worker_ns = uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - w0).count());
+    });
+    if (!have && flush) {  // nothing older to hand out: this tile's own output
+      j->th.join();
+      rc = j->rc;
+      worker_ns += j->worker_ns;
+      n_pairs = j->n_pairs;
+      if (rc == SQ_OK) {
+        *out = j->out;
+        j->out.release = nullptr;
+        have = true;
+      }
+      next.reset();
+      if (rc) return rc;
+    } else {
+      put_back(next);
+    }
+  }
   std::lock_guard<std::mutex> g(e->mu);
-  e->m[5] += 1;
-  e->m[6] += n_pairs;
-  e->m[8] += uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - t0).count());
-  e->m[11] += 1;  // tiles joined
+  // join_time = the library's own work: this call's host half plus the collected tile's worker (they overlap in wall time)
+  e->m[8] += host_ns + worker_ns;
+  if (have) {
+    *has_out = 1;
+    e->m[5] += 1;
+    e->m[6] += n_pairs;
+    e->m[11] += 1;  // tiles joined
+  }
   return SQ_OK;
 }
 
@@ -1217,6 +1312,7 @@ SQ_API int32_t sq_exec_set_option(sq_exec* e, const char* key, const char* value
 
 SQ_API void sq_exec_free(sq_exec* e) {
   if (!e) return;
+  e->jobs.clear();  // joins the workers, releases what they hold
   for (auto& kv : e->pending)
     for (ArrowArray& b : kv.second.batches) if (b.release) b.release(&b);
   for (auto& kv : e->streams) sq_stream_free(kv.second);

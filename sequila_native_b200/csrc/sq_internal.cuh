@@ -140,7 +140,7 @@ struct sq_options {
   std::atomic<int> pipeline_depth{3};       // sq_stream_submit: tiles in flight per stream (2..8)
   std::atomic<int> rank_count{1};           // rank-difference kernel for the indexes the SoA kernels serve: 0 off, 1 when the
                                             // index is deep enough to pay for it (measured crossover), 2 whenever possible
-  std::atomic<int> coalesce_rows{1 << 20};  // exec node: probe rows that make one tile (sq_exec_probe_push / _pop)
+  std::atomic<int> coalesce_rows{1 << 19};  // exec node: probe rows that make one tile (sq_exec_probe_push / _pop)
 };
 
 struct sq_ctx {

@@ -298,8 +298,10 @@ class IntervalJoinExec:
                 out = pop(False)
                 if out is not None:
                     yield out
-        out = pop(True)
-        if out is not None:
+        while True:  # the tile in flight, then whatever is still waiting (tiles are pipelined two deep)
+            out = pop(True)
+            if out is None:
+                break
             yield out
 
     def set_option(self, key: str, value) -> None:
