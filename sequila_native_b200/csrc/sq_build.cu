@@ -17,11 +17,11 @@
 // Kernels here are HBM-bound streaming passes; the sort is CUB's radix sort (library code, like
 // cuBLAS for a GEMM) restricted to the significant bits 32 + ceil(log2(#keys)).
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 
 #include <cstdlib>
 
 #include "sq_internal.cuh"
+#include "sq_packed_common.cuh"  // chain_lookback: the chained scan with decoupled look-back
 
 namespace sq {
 
@@ -370,29 +370,21 @@ __global__ void __launch_bounds__(256) k_seg_meta(const uint32_t* __restrict__ s
 
 __device__ __forceinline__ uint32_t start_window(int32_t x) { return (uint32_t(x) ^ 0x80000000u) >> 16; }
 
-// dir[dir_base + b] = first row of the segment whose bin >= b; dir[dir_base + nbins] = se.  With `flag` the same pass
-// marks the rows that start a packed line (see "Packed lines" below): it already holds start[j], start[j - 1] and the
-// segment's first row.
+// dir[dir_base + b] = first row of the segment whose bin >= b; dir[dir_base + nbins] = se
 __global__ void __launch_bounds__(256) k_fill_dir(const uint32_t* __restrict__ s_id,
                                                   const int32_t* __restrict__ s_start, uint64_t n,
-                                                  const SegMeta* __restrict__ meta,
-                                                  uint32_t* __restrict__ dir, uint32_t* __restrict__ flag) {
+                                                  const SegMeta* __restrict__ meta, uint32_t* __restrict__ dir) {
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
   for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride) {
     const uint32_t id = s_id[j];
     const SegMeta m = meta[id];
     const uint32_t sh = m.shift;
-    const int32_t st = s_start[j];
-    const uint32_t bin = sh >= 32 ? 0u : ((uint32_t(st) - uint32_t(m.min_start)) >> sh);
+    const uint32_t bin = sh >= 32 ? 0u : ((uint32_t(s_start[j]) - uint32_t(m.min_start)) >> sh);
     uint32_t from = 0;
-    bool line_start = true;
     if (j > m.sb) {
-      const int32_t pst = s_start[j - 1];
-      const uint32_t prev = sh >= 32 ? 0u : ((uint32_t(pst) - uint32_t(m.min_start)) >> sh);
+      const uint32_t prev = sh >= 32 ? 0u : ((uint32_t(s_start[j - 1]) - uint32_t(m.min_start)) >> sh);
       from = prev + 1;
-      line_start = (j - m.sb) % kLineRows == 0 || start_window(st) != start_window(pst);
     }
-    if (flag) flag[j] = line_start ? 1u : 0u;
     for (uint32_t b = from; b <= bin; ++b) dir[m.dir_base + b] = uint32_t(j);
     if (j == uint64_t(m.se) - 1) dir[m.dir_base + m.nbins] = m.se;
   }
@@ -509,18 +501,100 @@ __global__ void __launch_bounds__(kScanThreads) k_runmax_final(const uint32_t* _
 // Packed lines (see sq_internal.cuh).  A line starts at the first row of a key segment, wherever the
 // start crosses a 65536-wide window (so every in-line start offset fits 16 bits whatever the gaps in the
 // data) and every 15 rows after the segment start: lines hold 1..15 rows, the lines of a segment are
-// contiguous.  k_line_flags marks line starts, an inclusive sum numbers the lines, k_line_first inverts
+// contiguous.  k_line_number marks line starts, numbers the lines and inverts
 // that, k_seg_lines / k_fill_dir_line translate segment starts and directory entries from rows to lines,
 // k_pack_lines writes the lines (8 threads per line, each its 16 bytes).
 // status[0] |= 1 when some width does not fit 16 bits (the index then keeps only the SoA arrays);
 // status[1] += lines a probe ending at this line's last start would walk back.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_line_first(const uint32_t* __restrict__ flag, const uint32_t* __restrict__ line_incl,
-                                                    uint64_t n, uint32_t* __restrict__ line_first) {
-  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
-  for (uint64_t j = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride) {
-    if (flag[j]) line_first[line_incl[j] - 1u] = uint32_t(j);
-    if (j == n - 1) line_first[line_incl[j]] = uint32_t(n);
+// Numbers the packed lines in ONE pass (it was: flags written by the directory pass, a library scan, an inversion pass):
+// every thread flags its 8 consecutive rows, the tile's count goes through the chained scan with decoupled look-back
+// (tiles in ticket order, as in the probe kernels), and line_incl[j] = lines started up to and including row j,
+// line_first[line] = its first row come out of the same registers.  result[0] = number of lines.
+__global__ void __launch_bounds__(kScanThreads) k_line_number(const uint32_t* __restrict__ s_id, const int32_t* __restrict__ s_start,
+                                                              uint64_t n, const SegMeta* __restrict__ meta,
+                                                              unsigned long long* chain_state, unsigned int* ticket,
+                                                              uint32_t* __restrict__ line_incl, uint32_t* __restrict__ line_first,
+                                                              unsigned long long* result) {
+  static_assert(kScanItems == 8, "two 16-byte vectors per thread and array");
+  __shared__ uint32_t s_tile;
+  __shared__ uint32_t wtot[kScanThreads / 32];
+  __shared__ unsigned long long s_excl;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t base = uint64_t(tile) * kScanTile + uint64_t(threadIdx.x) * kScanItems;
+  uint32_t id[kScanItems];
+  int32_t st[kScanItems];
+  if (base + kScanItems <= n) {
+    const uint4 i0 = *reinterpret_cast<const uint4*>(s_id + base), i1 = *reinterpret_cast<const uint4*>(s_id + base + 4);
+    const int4 a0 = *reinterpret_cast<const int4*>(s_start + base), a1 = *reinterpret_cast<const int4*>(s_start + base + 4);
+    id[0] = i0.x; id[1] = i0.y; id[2] = i0.z; id[3] = i0.w; id[4] = i1.x; id[5] = i1.y; id[6] = i1.z; id[7] = i1.w;
+    st[0] = a0.x; st[1] = a0.y; st[2] = a0.z; st[3] = a0.w; st[4] = a1.x; st[5] = a1.y; st[6] = a1.z; st[7] = a1.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      id[k] = base + k < n ? s_id[base + k] : 0u;
+      st[k] = base + k < n ? s_start[base + k] : 0;
+    }
+  }
+  int32_t prev = base > 0 && base < n ? s_start[base - 1] : 0;
+  uint32_t sb = base < n ? meta[id[0]].sb : 0u, sb_id = id[0];
+  uint32_t flags = 0, cnt = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const uint64_t j = base + k;
+    if (j < n) {
+      if (id[k] != sb_id) { sb_id = id[k]; sb = meta[sb_id].sb; }
+      const bool f = j == sb || (j - sb) % kLineRows == 0 || start_window(st[k]) != start_window(prev);
+      flags |= uint32_t(f) << k;
+      cnt += f;
+    }
+    prev = st[k];
+  }
+  // exclusive prefix of cnt over the tile's threads
+  uint32_t inc = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) wtot[warp] = inc;
+  __syncthreads();
+  uint32_t pre = 0, tot = 0;
+#pragma unroll
+  for (int q = 0; q < kScanThreads / 32; ++q) {
+    if (q < warp) pre += wtot[q];
+    tot += wtot[q];
+  }
+  if (warp == 0) {
+    const unsigned long long excl = chain_lookback(chain_state, tile, (unsigned long long)tot);
+    if (lane == 0) {
+      s_excl = excl;
+      if (uint64_t(tile + 1) * kScanTile >= n) result[0] = excl + tot;  // the last tile
+    }
+  }
+  __syncthreads();
+  uint32_t run = uint32_t(s_excl) + pre + inc - cnt;  // lines started before this thread's first row
+  uint32_t out[kScanItems];
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    const uint64_t j = base + k;
+    if ((flags >> k) & 1u) {
+      line_first[run] = uint32_t(j);
+      run += 1;
+    }
+    out[k] = run;
+    if (j == n - 1) line_first[run] = uint32_t(n);
+  }
+  if (base + kScanItems <= n) {
+    *reinterpret_cast<uint4*>(line_incl + base) = make_uint4(out[0], out[1], out[2], out[3]);
+    *reinterpret_cast<uint4*>(line_incl + base + 4) = make_uint4(out[4], out[5], out[6], out[7]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+      if (base + k < n) line_incl[base + k] = out[k];
   }
 }
 
@@ -849,25 +923,24 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_dir, dir_total * 4, pool, st));
     idx->bytes += dir_total * 4;
     idx->dir_bytes = dir_total * 4;
-    uint32_t *d_flag = nullptr, *d_line_incl = nullptr, *d_line_first = nullptr;
-    SQ_CUDA(E, tmp.alloc(&d_flag, n * 4));
-    SQ_CUDA(E, tmp.alloc(&d_line_incl, n * 4));
-    k_fill_dir<<<g, 256, 0, st>>>(d_sid, idx->d_start, n, idx->d_meta, idx->d_dir, d_flag);  // + the line-start flags of step 5
+    k_fill_dir<<<g, 256, 0, st>>>(d_sid, idx->d_start, n, idx->d_meta, idx->d_dir);
     SQ_CUDA(E, cudaGetLastError());
 
     // 5. packed lines for narrow indexes (every width < 65536)
-    size_t scan_bytes = 0;
-    SQ_CUDA(E, ::sq_cub::cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, d_flag, d_line_incl, n, st));
-    void* d_scan_tmp = nullptr;
-    SQ_CUDA(E, tmp.alloc(&d_scan_tmp, scan_bytes));
-    SQ_CUDA(E, ::sq_cub::cub::DeviceScan::InclusiveSum(d_scan_tmp, scan_bytes, d_flag, d_line_incl, n, st));
-    uint32_t h_lines = 0;
-    SQ_CUDA(E, cudaMemcpyAsync(&h_lines, d_line_incl + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    uint32_t *d_line_incl = nullptr, *d_line_first = nullptr;
+    unsigned long long* d_lchain = nullptr;  // [n_tiles] chained-scan words, ticket, line total
+    SQ_CUDA(E, tmp.alloc(&d_line_incl, n * 4));
+    SQ_CUDA(E, tmp.alloc(&d_line_first, (n + 1) * 4));  // at most one line per row
+    SQ_CUDA(E, tmp.alloc(&d_lchain, (size_t(n_tiles) + 2) * 8));
+    SQ_CUDA(E, cudaMemsetAsync(d_lchain, 0, (size_t(n_tiles) + 2) * 8, st));
+    k_line_number<<<n_tiles, kScanThreads, 0, st>>>(d_sid, idx->d_start, n, idx->d_meta, d_lchain,
+                                                    reinterpret_cast<unsigned int*>(d_lchain + n_tiles), d_line_incl, d_line_first,
+                                                    d_lchain + n_tiles + 1);
+    SQ_CUDA(E, cudaGetLastError());
+    unsigned long long h_lines = 0;
+    SQ_CUDA(E, cudaMemcpyAsync(&h_lines, d_lchain + n_tiles + 1, 8, cudaMemcpyDeviceToHost, st));
     SQ_CUDA(E, cudaStreamSynchronize(st));  // also: h_meta must outlive its async copy
     const uint64_t line_total = h_lines;
-    SQ_CUDA(E, tmp.alloc(&d_line_first, (line_total + 1) * 4));
-    k_line_first<<<g, 256, 0, st>>>(d_flag, d_line_incl, n, d_line_first);
-    SQ_CUDA(E, cudaGetLastError());
     k_seg_lines<<<(n_keys + 256) / 256, 256, 0, st>>>(d_line_incl, n_keys, n, idx->d_meta);
     SQ_CUDA(E, cudaGetLastError());
     SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_dir_line, dir_total * 8, pool, st));
@@ -939,7 +1012,7 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
         h_em[n_keys] = SegMeta{};
         SQ_CUDA(E, cudaMemcpyAsync(idx->d_emeta, h_em.data(), (size_t(n_keys) + 1) * sizeof(SegMeta), cudaMemcpyHostToDevice, st));
         SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_edir, edir_total * 4, pool, st));
-        k_fill_dir<<<g, 256, 0, st>>>(d_sid, idx->d_send, n, idx->d_emeta, idx->d_edir, nullptr);  // same segments, same ids
+        k_fill_dir<<<g, 256, 0, st>>>(d_sid, idx->d_send, n, idx->d_emeta, idx->d_edir);  // same segments, same ids
         SQ_CUDA(E, cudaGetLastError());
         SQ_CUDA(E, cudaStreamSynchronize(st));  // h_em must outlive its async copy
         idx->bytes += n * 4 + edir_total * 4 + (uint64_t(n_keys) + 1) * sizeof(SegMeta);
