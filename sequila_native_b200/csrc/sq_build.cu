@@ -98,6 +98,87 @@ __global__ void __launch_bounds__(256) k_ht_assign(const uint64_t* __restrict__ 
   ht_ids[slot] = (ht_keys[slot] != kEmptyKey) ? atomicAdd(counter, 1u) : kNoKey;
 }
 
+// The first attempt at the key table (kFirstCap slots: up to 2048 keys) also collects what the narrow sort keys below need:
+// the table slot of every build row and the range of start per slot.  The slot a key lands in indexes the CTA's range table in
+// shared memory directly — the global table has resolved the collisions — which is read first as a filter: ranges only
+// widen, so a stale read can only ask for an update that is not needed, and after a CTA's first rows almost no row passes it
+// on unsorted input; sorted input (one key per warp, every row a new maximum) takes the whole-warp reduction.  The key
+// whose hash equals the empty marker gets the extra slot kFirstCap.
+constexpr uint32_t kFirstCap = 4096;
+
+__global__ void __launch_bounds__(256) k_ht_insert_ranges(const uint64_t* __restrict__ keys, const int32_t* __restrict__ start,
+                                                          uint64_t n, uint64_t* __restrict__ ht_keys, HtStatus* st,
+                                                          uint32_t* __restrict__ row_slot, int32_t* __restrict__ slot_min,
+                                                          int32_t* __restrict__ slot_max) {
+  __shared__ int32_t s_min[kFirstCap + 1], s_max[kFirstCap + 1];
+  for (uint32_t k = threadIdx.x; k <= kFirstCap; k += blockDim.x) { s_min[k] = INT32_MAX; s_max[k] = INT32_MIN; }
+  __syncthreads();
+  constexpr uint32_t mask = kFirstCap - 1;
+  constexpr int kU = 4;  // rows per thread and trip, their loads issued together; warp-uniform trip count
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x * kU;
+  const uint64_t first = (uint64_t(blockIdx.x) * blockDim.x + (threadIdx.x & ~31u)) * kU + (threadIdx.x & 31);
+  for (uint64_t i0 = first; i0 - (threadIdx.x & 31) < n; i0 += stride) {
+    uint64_t ks[kU];
+    int32_t ss[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const uint64_t i = i0 + uint64_t(u) * 32;
+      ks[u] = i < n ? keys[i] : 0;
+      ss[u] = i < n ? start[i] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const uint64_t i = i0 + uint64_t(u) * 32;
+      const bool valid = i < n;
+      const unsigned act = __ballot_sync(0xffffffffu, valid);
+      if (!valid) continue;
+      const uint64_t key = ks[u];
+      uint32_t slot = kFirstCap;
+      if (key == kEmptyKey) {
+        st->has_sentinel = 1;
+      } else {  // find the key or put it there
+        slot = uint32_t(mix64(key)) & mask;
+        for (uint32_t step = 0;; ++step) {
+          // a cached read: a slot never changes once it holds a key, so only "empty" can be stale — and the CAS that
+          // follows an empty read returns the truth
+          uint64_t cur = ht_keys[slot];
+          if (cur == kEmptyKey) {
+            cur = atomicCAS(reinterpret_cast<unsigned long long*>(ht_keys + slot), (unsigned long long)kEmptyKey,
+                            (unsigned long long)key);
+            if (cur == kEmptyKey) {
+              const unsigned d = atomicAdd(&st->distinct, 1u) + 1u;
+              if (d > kFirstCap / 2u) st->overflow = 1;  // keep load factor <= 1/2
+              break;
+            }
+          }
+          if (cur == key) break;
+          if (step == mask) { st->overflow = 1; break; }
+          slot = (slot + 1) & mask;
+        }
+      }
+      row_slot[i] = slot;
+      const int32_t sv = ss[u];
+      const bool need = sv < s_min[slot] || sv > s_max[slot];
+      if (!__any_sync(act, need)) continue;
+      const uint32_t slot0 = __shfl_sync(act, slot, __ffs(act) - 1);
+      unsigned peers = act;
+      if (!__all_sync(act, slot == slot0)) peers = __match_any_sync(act, slot);  // one lane per distinct key of the warp
+      const int32_t mn = __reduce_min_sync(peers, sv);
+      const int32_t mx = __reduce_max_sync(peers, sv);
+      if ((__ffs(peers) - 1) == int(threadIdx.x & 31)) {
+        if (mn < s_min[slot]) atomicMin(&s_min[slot], mn);
+        if (mx > s_max[slot]) atomicMax(&s_max[slot], mx);
+      }
+    }
+  }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k <= kFirstCap; k += blockDim.x)
+    if (s_min[k] <= s_max[k]) {
+      atomicMin(slot_min + k, s_min[k]);
+      atomicMax(slot_max + k, s_max[k]);
+    }
+}
+
 // sort key = (key id << 32) | (start with the sign bit flipped), value = (end << 32) | build row: the end
 // travels with the row through the sort (a gather of end[] through the permutation afterwards would be
 // 100M random 4-byte reads, 2 ms; 4 more bytes per row and pass in the sort cost a third of that)
@@ -507,7 +588,8 @@ __global__ void __launch_bounds__(kScanThreads) k_runmax_final(const uint32_t* _
 // status[0] |= 1 when some width does not fit 16 bits (the index then keeps only the SoA arrays);
 // status[1] += lines a probe ending at this line's last start would walk back.
 // ---------------------------------------------------------------------------------------------
-// Numbers the packed lines in ONE pass (it was: flags written by the directory pass, a library scan, an inversion pass):
+// Numbers the packed lines and fills the bin directory in ONE pass (it was: a directory pass that also wrote line flags, a
+// library scan, an inversion pass):
 // every thread flags its 8 consecutive rows, the tile's count goes through the chained scan with decoupled look-back
 // (tiles in ticket order, as in the probe kernels), and line_incl[j] = lines started up to and including row j,
 // line_first[line] = its first row come out of the same registers.  result[0] = number of lines.
@@ -515,7 +597,7 @@ __global__ void __launch_bounds__(kScanThreads) k_line_number(const uint32_t* __
                                                               uint64_t n, const SegMeta* __restrict__ meta,
                                                               unsigned long long* chain_state, unsigned int* ticket,
                                                               uint32_t* __restrict__ line_incl, uint32_t* __restrict__ line_first,
-                                                              unsigned long long* result) {
+                                                              unsigned long long* result, uint32_t* __restrict__ dir) {
   static_assert(kScanItems == 8, "two 16-byte vectors per thread and array");
   __shared__ uint32_t s_tile;
   __shared__ uint32_t wtot[kScanThreads / 32];
@@ -540,16 +622,24 @@ __global__ void __launch_bounds__(kScanThreads) k_line_number(const uint32_t* __
     }
   }
   int32_t prev = base > 0 && base < n ? s_start[base - 1] : 0;
-  uint32_t sb = base < n ? meta[id[0]].sb : 0u, sb_id = id[0];
+  SegMeta m = meta[base < n ? id[0] : 0u];
+  uint32_t m_id = id[0];
   uint32_t flags = 0, cnt = 0;
 #pragma unroll
   for (int k = 0; k < kScanItems; ++k) {
     const uint64_t j = base + k;
     if (j < n) {
-      if (id[k] != sb_id) { sb_id = id[k]; sb = meta[sb_id].sb; }
-      const bool f = j == sb || (j - sb) % kLineRows == 0 || start_window(st[k]) != start_window(prev);
+      if (id[k] != m_id) { m_id = id[k]; m = meta[m_id]; }
+      const bool f = j == m.sb || (j - m.sb) % kLineRows == 0 || start_window(st[k]) != start_window(prev);
       flags |= uint32_t(f) << k;
       cnt += f;
+      // the bin directory of the row searches (the former k_fill_dir pass): dir[dir_base + b] = first row of the segment
+      // whose bin >= b; dir[dir_base + nbins] = se
+      const uint32_t sh = m.shift;
+      const uint32_t bin = sh >= 32 ? 0u : ((uint32_t(st[k]) - uint32_t(m.min_start)) >> sh);
+      const uint32_t from = j > m.sb ? (sh >= 32 ? 0u : ((uint32_t(prev) - uint32_t(m.min_start)) >> sh)) + 1u : 0u;
+      for (uint32_t b = from; b <= bin; ++b) dir[m.dir_base + b] = uint32_t(j);
+      if (j == uint64_t(m.se) - 1) dir[m.dir_base + m.nbins] = m.se;
     }
     prev = st[k];
   }
@@ -709,10 +799,30 @@ struct TmpFree {
   cudaStream_t st;
   cudaMemPool_t pool;
   std::vector<void*> ptrs;
+  // ONE block for the temporaries whose sizes follow from the row count (sort double buffers, per-row ids, line numbering:
+  // 48 bytes per row), handed out by a bump pointer: a build is then a dozen pool operations instead of forty, and the
+  // next build finds the same block again (with forty blocks of mixed sizes coming and going the stream-ordered pool
+  // re-maps memory every few builds: 10-60 ms hiccups on a 7 ms build).  What does not fit is allocated on its own.
+  char* arena = nullptr;
+  size_t arena_cap = 0, arena_used = 0;
   TmpFree(cudaStream_t s, cudaMemPool_t pl) : st(s), pool(pl) {}
   ~TmpFree() { for (void* p : ptrs) cudaFreeAsync(p, st); }
+  cudaError_t reserve(size_t bytes) {
+    cudaError_t e = cudaMallocFromPoolAsync(reinterpret_cast<void**>(&arena), bytes, pool, st);
+    if (e != cudaSuccess) { arena = nullptr; return e; }
+    ptrs.push_back(arena);
+    arena_cap = bytes;
+    return cudaSuccess;
+  }
   template <class T> cudaError_t alloc(T** p, size_t bytes) {
-    cudaError_t e = cudaMallocFromPoolAsync(reinterpret_cast<void**>(p), bytes ? bytes : 16, pool, st);
+    bytes = bytes ? bytes : 16;
+    const size_t need = (bytes + 255) & ~size_t(255);
+    if (arena && arena_used + need <= arena_cap) {
+      *p = reinterpret_cast<T*>(arena + arena_used);
+      arena_used += need;
+      return cudaSuccess;
+    }
+    cudaError_t e = cudaMallocFromPoolAsync(reinterpret_cast<void**>(p), bytes, pool, st);
     if (e == cudaSuccess) ptrs.push_back(*p);
     return e;
   }
@@ -752,6 +862,7 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
   cudaMemPool_t pool = ctx_pool(ctx);
   if (!pool) return fail(E, SQ_ECUDA, "cudaMemPoolCreate failed on device %d", ctx->device);
   TmpFree tmp(st, pool);
+  if (n) SQ_CUDA(E, tmp.reserve(size_t(n) * 48 + std::min<size_t>(size_t(16) << 20, size_t(n) * 16 + (size_t(256) << 10))));
 
   cudaEvent_t e0, e1;
   SQ_CUDA(E, cudaEventCreate(&e0));
@@ -759,22 +870,41 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
   struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{e0, e1};
   SQ_CUDA(E, cudaEventRecord(e0, st));
 
-  // 1. key hash table (grow until the load factor fits)
+  // 1. key hash table (grow until the load factor fits).  The first attempt, kFirstCap slots, also records the table slot
+  // of every row and the range of start per slot (narrow sort keys, step 2); bigger tables are filled by k_ht_insert alone.
   HtStatus* d_status = nullptr;
   SQ_CUDA(E, tmp.alloc(&d_status, sizeof(HtStatus) + sizeof(unsigned int) * 4));
   unsigned int* d_counter = reinterpret_cast<unsigned int*>(d_status + 1);
-  uint32_t cap = 4096;
+  int32_t* d_srng = nullptr;  // [kFirstCap + 1] min of start per slot, [kFirstCap + 1] max
+  const bool want_narrow = n && ctx->opt.build_sort.load(std::memory_order_relaxed) == 0;
+  bool slot_ranges = false;
+  uint32_t* d_rid = nullptr;  // table slot / key id of every build row (narrow sort keys)
+  if (want_narrow) SQ_CUDA(E, tmp.alloc(&d_rid, n * 4));
+  uint32_t cap = kFirstCap;
   HtStatus hs{};
   for (;;) {
     SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_ht_keys, size_t(cap) * 8, pool, st));
     SQ_CUDA(E, cudaMemsetAsync(idx->d_ht_keys, 0xFF, size_t(cap) * 8, st));
     SQ_CUDA(E, cudaMemsetAsync(d_status, 0, sizeof(HtStatus) + 16, st));
-    if (n) {
-      k_ht_insert<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(d_key, n, idx->d_ht_keys, cap - 1, d_status);
+    if (n && cap == kFirstCap && want_narrow) {
+      std::vector<int32_t> init(2 * (kFirstCap + 1));
+      for (uint32_t k = 0; k <= kFirstCap; ++k) { init[k] = INT32_MAX; init[kFirstCap + 1 + k] = INT32_MIN; }
+      SQ_CUDA(E, tmp.alloc(&d_srng, init.size() * 4));
+      SQ_CUDA(E, cudaMemcpyAsync(d_srng, init.data(), init.size() * 4, cudaMemcpyHostToDevice, st));
+      k_ht_insert_ranges<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(d_key, d_start, n, idx->d_ht_keys, d_status, d_rid,
+                                                                           d_srng, d_srng + kFirstCap + 1);
       SQ_CUDA(E, cudaGetLastError());
+      SQ_CUDA(E, cudaMemcpyAsync(&hs, d_status, sizeof(hs), cudaMemcpyDeviceToHost, st));
+      SQ_CUDA(E, cudaStreamSynchronize(st));  // also: `init` goes out of scope
+      slot_ranges = !hs.overflow;
+    } else {
+      if (n) {
+        k_ht_insert<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(d_key, n, idx->d_ht_keys, cap - 1, d_status);
+        SQ_CUDA(E, cudaGetLastError());
+      }
+      SQ_CUDA(E, cudaMemcpyAsync(&hs, d_status, sizeof(hs), cudaMemcpyDeviceToHost, st));
+      SQ_CUDA(E, cudaStreamSynchronize(st));
     }
-    SQ_CUDA(E, cudaMemcpyAsync(&hs, d_status, sizeof(hs), cudaMemcpyDeviceToHost, st));
-    SQ_CUDA(E, cudaStreamSynchronize(st));
     if (!hs.overflow) break;
     cudaFree(idx->d_ht_keys);
     idx->d_ht_keys = nullptr;
@@ -819,44 +949,69 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     SQ_CUDA(E, tmp.alloc(&d_tile, size_t(n_tiles) * 8));
     SQ_CUDA(E, tmp.alloc(&d_sid, n * 4));
 
-    // narrow (32-bit) sort keys when the key ranges laid end to end fit 32 bits (option cuda_build_sort wide: never)
+    // narrow (32-bit) sort keys when the key ranges laid end to end fit 32 bits (option cuda_build_sort wide: never).
+    // d_rid tags every build row with its table slot (first-attempt table: the ranges came with the insert) or its key id
+    // (bigger table: k_key_ranges); d_tagkb maps the tag to the key's base, d_kb the key id.
     bool narrow = false;
-    KeyBase* d_kb = nullptr;
+    KeyBase *d_kb = nullptr, *d_tagkb = nullptr;
     int end_bit = 32;
-    uint32_t* d_rid = reinterpret_cast<uint32_t*>(d_k1);  // id of every build row: lives in the sort's second key buffer
-    if (n_keys <= kNarrowMaxKeys && ctx->opt.build_sort.load(std::memory_order_relaxed) == 0) {
-      int32_t* d_rng = nullptr;  // [n_keys] min, [n_keys] max
-      SQ_CUDA(E, tmp.alloc(&d_rng, size_t(n_keys) * 8));
-      SQ_CUDA(E, tmp.alloc(&d_kb, size_t(n_keys) * sizeof(KeyBase)));
-      std::vector<int32_t> h_rng(size_t(n_keys) * 2);
-      for (uint32_t k = 0; k < n_keys; ++k) { h_rng[k] = INT32_MAX; h_rng[n_keys + k] = INT32_MIN; }
-      SQ_CUDA(E, cudaMemcpyAsync(d_rng, h_rng.data(), h_rng.size() * 4, cudaMemcpyHostToDevice, st));
-      k_key_ranges<<<grid_for(n, 256, ctx->sm_count), 256, size_t(n_keys) * 8, st>>>(
-          d_key, d_start, n, idx->d_ht_keys, idx->d_ht_ids, cap - 1, idx->sentinel_id, n_keys, d_rid, d_rng, d_rng + n_keys);
-      SQ_CUDA(E, cudaGetLastError());
-      SQ_CUDA(E, cudaMemcpyAsync(h_rng.data(), d_rng, h_rng.size() * 4, cudaMemcpyDeviceToHost, st));
-      SQ_CUDA(E, cudaStreamSynchronize(st));
+    if (n_keys <= kNarrowMaxKeys && want_narrow) {
+      std::vector<int32_t> h_min(n_keys), h_max(n_keys);  // per key id
+      std::vector<uint32_t> h_ids;                        // slot -> key id (slot_ranges)
+      if (slot_ranges) {
+        std::vector<int32_t> h_srng(2 * (kFirstCap + 1));
+        h_ids.resize(kFirstCap);
+        SQ_CUDA(E, cudaMemcpyAsync(h_srng.data(), d_srng, h_srng.size() * 4, cudaMemcpyDeviceToHost, st));
+        SQ_CUDA(E, cudaMemcpyAsync(h_ids.data(), idx->d_ht_ids, size_t(kFirstCap) * 4, cudaMemcpyDeviceToHost, st));
+        SQ_CUDA(E, cudaStreamSynchronize(st));
+        for (uint32_t sl = 0; sl < kFirstCap; ++sl)
+          if (h_ids[sl] != kNoKey) { h_min[h_ids[sl]] = h_srng[sl]; h_max[h_ids[sl]] = h_srng[kFirstCap + 1 + sl]; }
+        if (idx->sentinel_id != kNoKey) { h_min[idx->sentinel_id] = h_srng[kFirstCap]; h_max[idx->sentinel_id] = h_srng[2 * kFirstCap + 1]; }
+      } else {
+        int32_t* d_rng = nullptr;  // [n_keys] min, [n_keys] max
+        SQ_CUDA(E, tmp.alloc(&d_rng, size_t(n_keys) * 8));
+        std::vector<int32_t> h_rng(size_t(n_keys) * 2);
+        for (uint32_t k = 0; k < n_keys; ++k) { h_rng[k] = INT32_MAX; h_rng[n_keys + k] = INT32_MIN; }
+        SQ_CUDA(E, cudaMemcpyAsync(d_rng, h_rng.data(), h_rng.size() * 4, cudaMemcpyHostToDevice, st));
+        k_key_ranges<<<grid_for(n, 256, ctx->sm_count), 256, size_t(n_keys) * 8, st>>>(
+            d_key, d_start, n, idx->d_ht_keys, idx->d_ht_ids, cap - 1, idx->sentinel_id, n_keys, d_rid, d_rng, d_rng + n_keys);
+        SQ_CUDA(E, cudaGetLastError());
+        SQ_CUDA(E, cudaMemcpyAsync(h_rng.data(), d_rng, h_rng.size() * 4, cudaMemcpyDeviceToHost, st));
+        SQ_CUDA(E, cudaStreamSynchronize(st));
+        for (uint32_t k = 0; k < n_keys; ++k) { h_min[k] = h_rng[k]; h_max[k] = h_rng[n_keys + k]; }
+      }
       std::vector<KeyBase> h_kb(n_keys);
       uint64_t acc = 0;
       for (uint32_t k = 0; k < n_keys; ++k) {
         h_kb[k].base = uint32_t(acc);
-        h_kb[k].min_start = h_rng[k];
-        acc += uint64_t(int64_t(h_rng[n_keys + k]) - int64_t(h_rng[k])) + 1ull;
+        h_kb[k].min_start = h_min[k];
+        acc += uint64_t(int64_t(h_max[k]) - int64_t(h_min[k])) + 1ull;  // every key id has at least one row
         if (acc > (1ull << 32)) break;
       }
       if (acc <= (1ull << 32)) {
         narrow = true;
         end_bit = 1;
         while (end_bit < 32 && (1ull << end_bit) < acc) ++end_bit;
+        SQ_CUDA(E, tmp.alloc(&d_kb, size_t(n_keys) * sizeof(KeyBase)));
         SQ_CUDA(E, cudaMemcpyAsync(d_kb, h_kb.data(), size_t(n_keys) * sizeof(KeyBase), cudaMemcpyHostToDevice, st));
-        SQ_CUDA(E, cudaStreamSynchronize(st));  // h_kb goes out of scope below
+        std::vector<KeyBase> h_tag;
+        d_tagkb = d_kb;
+        if (slot_ranges) {
+          h_tag.assign(kFirstCap + 1, KeyBase{0u, 0});
+          for (uint32_t sl = 0; sl < kFirstCap; ++sl)
+            if (h_ids[sl] != kNoKey) h_tag[sl] = h_kb[h_ids[sl]];
+          if (idx->sentinel_id != kNoKey) h_tag[kFirstCap] = h_kb[idx->sentinel_id];
+          SQ_CUDA(E, tmp.alloc(&d_tagkb, h_tag.size() * sizeof(KeyBase)));
+          SQ_CUDA(E, cudaMemcpyAsync(d_tagkb, h_tag.data(), h_tag.size() * sizeof(KeyBase), cudaMemcpyHostToDevice, st));
+        }
+        SQ_CUDA(E, cudaStreamSynchronize(st));  // h_kb / h_tag go out of scope below
       }
     }
     if (narrow) {
       // the 32-bit keys and their double buffer share d_k0 (n * 8 bytes)
       uint32_t* d_n0 = reinterpret_cast<uint32_t*>(d_k0);
       uint32_t* d_n1 = d_n0 + n;
-      k_make_sort_keys32<<<g, 256, 0, st>>>(d_rid, d_start, d_end, n, d_kb, d_n0, d_v0, d_inverted);
+      k_make_sort_keys32<<<g, 256, 0, st>>>(d_rid, d_start, d_end, n, d_tagkb, d_n0, d_v0, d_inverted);
       SQ_CUDA(E, cudaGetLastError());
       size_t temp_bytes = 0;
       SQ_CUDA(E, ::sq_cub::cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, d_n0, d_n1, d_v0, d_v1, n, 0, end_bit, st));
@@ -923,8 +1078,7 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     SQ_CUDA(E, cudaMallocFromPoolAsync(&idx->d_dir, dir_total * 4, pool, st));
     idx->bytes += dir_total * 4;
     idx->dir_bytes = dir_total * 4;
-    k_fill_dir<<<g, 256, 0, st>>>(d_sid, idx->d_start, n, idx->d_meta, idx->d_dir);
-    SQ_CUDA(E, cudaGetLastError());
+    // (the directory is filled by the line-numbering pass below: it reads the same rows)
 
     // 5. packed lines for narrow indexes (every width < 65536)
     uint32_t *d_line_incl = nullptr, *d_line_first = nullptr;
@@ -935,7 +1089,7 @@ int build_index_device(sq_ctx* ctx, const uint64_t* d_key, const int32_t* d_star
     SQ_CUDA(E, cudaMemsetAsync(d_lchain, 0, (size_t(n_tiles) + 2) * 8, st));
     k_line_number<<<n_tiles, kScanThreads, 0, st>>>(d_sid, idx->d_start, n, idx->d_meta, d_lchain,
                                                     reinterpret_cast<unsigned int*>(d_lchain + n_tiles), d_line_incl, d_line_first,
-                                                    d_lchain + n_tiles + 1);
+                                                    d_lchain + n_tiles + 1, idx->d_dir);
     SQ_CUDA(E, cudaGetLastError());
     unsigned long long h_lines = 0;
     SQ_CUDA(E, cudaMemcpyAsync(&h_lines, d_lchain + n_tiles + 1, 8, cudaMemcpyDeviceToHost, st));
