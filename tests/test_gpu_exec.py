@@ -342,6 +342,35 @@ def test_null_keys_and_null_coordinates():
     assert "NULL" in str(e.value)
 
 
+def test_pipelined_tiles_many_small_tiles_and_an_error_behind_a_tile_in_flight(oracle):
+    """tiles are pipelined two deep (sq_exec_probe_pop): the output of a tile leaves one call after the tile went in, in
+    probe order; a tile that fails on the host half (NULL coordinate) reports its error while the previous tile's worker is
+    still on the GPU, and closing the node afterwards joins that worker"""
+    b, p = sn.synth.cfg5(scale=0.0005)
+    names = np.array(sn.synth.CONTIG_NAMES)
+    tab = lambda s: pa.record_batch([pa.array(names[s["contig"]].tolist()), pa.array(s["start"]), pa.array(s["end"])], names=COLS)
+    left, right = tab(b), tab(p)
+    f = IV.parse_condition_sql(Q1, "a", COLS, "b", COLS)
+    plan = optimize(HashJoinDesc(left.schema, right.schema, [("contig", "contig")], f), cuda_config())
+    plan.set_option("cuda_coalesce_rows", 3000)
+    plan.collect_build([left])
+    rbatches = [right.slice(i, 1000) for i in range(0, right.num_rows, 1000)]
+    out = list(plan.probe_batches(rbatches))
+    assert len(out) == -(-right.num_rows // 3000)  # one output batch per tile of three batches
+    ol, orr, _ = oracle.join(b["key"], b["start"], b["end"], p["key"], p["start"], p["end"])
+    got = rows_of(out)
+    assert len(got) == len(ol)
+    want_right = p["start"][np.sort(orr, kind="stable")]
+    assert [r[4] for r in got] == want_right.tolist()  # right side in probe order across all tiles
+    # an error in the fourth tile while the third is in flight
+    bad = pa.record_batch([pa.array(["chr1"]), pa.array([None], pa.int32()), pa.array([5], pa.int32())], names=COLS)
+    seq = rbatches[:9] + [bad] + rbatches[9:12]
+    with pytest.raises(ExecutionError) as e:
+        list(plan.probe_batches(seq, partition=1))
+    assert "NULL" in str(e.value)
+    plan.close()
+
+
 def test_concurrent_partitions_of_one_node_with_coalescing(oracle):
     """four host threads drive four partitions of ONE exec node (one sq_stream each, one shared index), each coalescing its
     own 4096-row batches: the union of their output rows is the oracle's join"""
