@@ -648,9 +648,18 @@ SQ_API int32_t sq_exec_finish_build(sq_exec* e) {
       uint64_t r = 0;
       for (auto& b : e->build_batches) {
         const ColView v = view_of(&b, col);
+        const bool nulls = v.null_count != 0 && v.validity;
+        if (w == t.width) {  // one copy per batch; only batches that hold NULLs are walked row by row
+          if (v.length) memcpy(buf.data() + r * w, v.values + v.offset * t.width, size_t(v.length) * w);
+          if (nulls)
+            for (int64_t i = 0; i < v.length; ++i)
+              if (!bit_at(v.validity, v.offset + i)) { validity[(r + i) >> 3] &= uint8_t(~(1u << ((r + i) & 7))); any_null = true; }
+          r += uint64_t(v.length);
+          continue;
+        }
         for (int64_t i = 0; i < v.length; ++i, ++r) {
           memcpy(buf.data() + r * w, v.values + (v.offset + i) * t.width, t.width);
-          if (v.null_count != 0 && v.validity && !bit_at(v.validity, v.offset + i)) { validity[r >> 3] &= uint8_t(~(1u << (r & 7))); any_null = true; }
+          if (nulls && !bit_at(v.validity, v.offset + i)) { validity[r >> 3] &= uint8_t(~(1u << (r & 7))); any_null = true; }
         }
       }
       rc = sq_index_add_column(e->index, buf.data(), w, &id);
@@ -658,16 +667,26 @@ SQ_API int32_t sq_exec_finish_build(sq_exec* e) {
       std::vector<int64_t> off(size_t(n) + 1, 0);
       std::vector<uint8_t> data;
       uint64_t r = 0;
-      for (auto& b : e->build_batches) {
+      for (auto& b : e->build_batches) {  // per batch: one copy of the bytes, the offsets shifted onto the running total
         const ColView v = view_of(&b, col);
-        for (int64_t i = 0; i < v.length; ++i, ++r) {
-          int64_t a, z;
-          if (t.kind == Kind::Utf8) { const int32_t* o = reinterpret_cast<const int32_t*>(v.values) + v.offset; a = o[i]; z = o[i + 1]; }
-          else { const int64_t* o = reinterpret_cast<const int64_t*>(v.values) + v.offset; a = o[i]; z = o[i + 1]; }
-          data.insert(data.end(), v.data + a, v.data + z);
-          off[r + 1] = int64_t(data.size());
-          if (v.null_count != 0 && v.validity && !bit_at(v.validity, v.offset + i)) { validity[r >> 3] &= uint8_t(~(1u << (r & 7))); any_null = true; }
+        if (!v.length) continue;
+        const bool nulls = v.null_count != 0 && v.validity;
+        const int64_t base = int64_t(data.size());
+        int64_t first, last;
+        if (t.kind == Kind::Utf8) {
+          const int32_t* o = reinterpret_cast<const int32_t*>(v.values) + v.offset;
+          first = o[0]; last = o[v.length];
+          parallel_rows(v.length, [&](int64_t lo, int64_t hi) { for (int64_t i = lo; i < hi; ++i) off[r + 1 + uint64_t(i)] = base + (int64_t(o[i + 1]) - first); });
+        } else {
+          const int64_t* o = reinterpret_cast<const int64_t*>(v.values) + v.offset;
+          first = o[0]; last = o[v.length];
+          parallel_rows(v.length, [&](int64_t lo, int64_t hi) { for (int64_t i = lo; i < hi; ++i) off[r + 1 + uint64_t(i)] = base + (o[i + 1] - first); });
         }
+        data.insert(data.end(), v.data + first, v.data + last);
+        if (nulls)
+          for (int64_t i = 0; i < v.length; ++i)
+            if (!bit_at(v.validity, v.offset + i)) { validity[(r + i) >> 3] &= uint8_t(~(1u << ((r + i) & 7))); any_null = true; }
+        r += uint64_t(v.length);
       }
       rc = sq_index_add_utf8_column(e->index, off.data(), data.data(), data.size(), &id);
     }
