@@ -108,6 +108,9 @@ def test_sentinel_key_single_rows_and_equal_starts(cuda_ctx, oracle):
     same_key = {k: v.copy() for k, v in b.items()}
     same_key["key"][:] = 7
     check(cuda_ctx, oracle, same_key, p, 32)
+    only_sentinel = {k: v.copy() for k, v in b.items()}
+    only_sentinel["key"][:] = EMPTY_KEY
+    check(cuda_ctx, oracle, only_sentinel, p, 32)
 
 
 def test_inverted_rows_and_position_ids(cuda_ctx, oracle):
