@@ -15,6 +15,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -1263,7 +1264,7 @@ SQ_API int32_t sq_exec_probe_pop(sq_exec* e, int32_t partition, int32_t flush, A
   uint64_t worker_ns = 0, n_pairs = 0;
   bool have = false;
   if (prev) {
-    prev->th.join();
+    if (prev->th.joinable()) prev->th.join();
     rc = prev->rc;
     worker_ns = prev->worker_ns;
     n_pairs = prev->n_pairs;
@@ -1279,14 +1280,19 @@ SQ_API int32_t sq_exec_probe_pop(sq_exec* e, int32_t partition, int32_t flush, A
     sq_stream* st = nullptr;
     if ((rc = stream_for(e, partition, &st))) { if (have && out->release) out->release(out); return rc; }
     TileJob* j = next.get();
-    j->th = std::thread([e, st, j]() {
+    auto work = [e, st, j]() {
       const auto w0 = Clock::now();
       j->rc = probe_tile(e, st, j->keys, j->start, j->end, &j->n_pairs);
       if (j->rc == SQ_OK) j->rc = assemble_output(e, st, j->tile, j->n_pairs, &j->out);
       j->worker_ns = uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - w0).count());
-    });
+    };
+    try {
+      j->th = std::thread(work);
+    } catch (const std::system_error&) {
+      work();  // no thread to be had: the tile is joined on the calling thread, its output leaves with the next call
+    }
     if (!have && flush) {  // nothing older to hand out: this tile's own output
-      j->th.join();
+      if (j->th.joinable()) j->th.join();
       rc = j->rc;
       worker_ns += j->worker_ns;
       n_pairs = j->n_pairs;
