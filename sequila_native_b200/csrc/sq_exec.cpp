@@ -948,6 +948,16 @@ int assemble_output(sq_exec* e, sq_stream* st, const ArrowArray* batch, uint64_t
 
 }  // namespace
 
+namespace {
+// the per-batch entry points use the partition's stream themselves: not while a pipelined tile's worker thread does
+int no_tile_in_flight(sq_exec* e, int32_t partition) {
+  std::lock_guard<std::mutex> g(e->mu);
+  if (e->jobs.find(partition) == e->jobs.end()) return SQ_OK;
+  e->err = "a pushed tile of this partition is still being joined: collect it with sq_exec_probe_pop(flush) first";
+  return SQ_ESTATE;
+}
+}  // namespace
+
 SQ_API int32_t sq_exec_probe(sq_exec* e, int32_t partition, const ArrowArray* batch, ArrowArray* out) {
   if (!e || !batch || !out) return SQ_EINVAL;
   if (!e->built) return e->fail(SQ_ESTATE, "Expected build side in ready state");  // IJ:1425
@@ -955,8 +965,9 @@ SQ_API int32_t sq_exec_probe(sq_exec* e, int32_t partition, const ArrowArray* ba
                                                                           (long long)batch->n_children, e->right.cols.size());
   const auto t0 = Clock::now();
   sq_stream* st = nullptr;
-  int rc = stream_for(e, partition, &st);
+  int rc = no_tile_in_flight(e, partition);
   if (rc) return rc;
+  if ((rc = stream_for(e, partition, &st))) return rc;
   uint64_t n_pairs = 0;
   if ((rc = probe_on_device(e, st, batch, &n_pairs))) return rc;
   if ((rc = assemble_output(e, st, batch, n_pairs, out))) return rc;
@@ -979,8 +990,9 @@ SQ_API int32_t sq_exec_probe_begin(sq_exec* e, int32_t partition, const ArrowArr
                                                                           (long long)batch->n_children, e->right.cols.size());
   const auto t0 = Clock::now();
   sq_stream* st = nullptr;
-  int rc = stream_for(e, partition, &st);
+  int rc = no_tile_in_flight(e, partition);
   if (rc) return rc;
+  if ((rc = stream_for(e, partition, &st))) return rc;
   uint64_t n_pairs = 0;
   if ((rc = probe_on_device(e, st, batch, &n_pairs))) return rc;
   PartState ps;
