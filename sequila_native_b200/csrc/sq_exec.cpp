@@ -44,6 +44,26 @@ struct Trace {
   }
 };
 
+// std::vector storage in pinned host memory from the library's pool.  The probe columns of a tile (key hashes, starts,
+// ends, the columns the probe side contributes to the output) go to the device with cudaMemcpyAsync: from pageable memory
+// that copy is staged through the driver's bounce buffer at a fraction of the link rate and is not asynchronous at all.
+template <class T>
+struct PinnedAlloc {
+  using value_type = T;
+  sq_ctx* ctx = nullptr;
+  explicit PinnedAlloc(sq_ctx* c) : ctx(c) {}
+  template <class U> PinnedAlloc(const PinnedAlloc<U>& o) : ctx(o.ctx) {}
+  T* allocate(size_t n) {
+    void* p = nullptr;
+    if (sq_host_alloc(ctx, n * sizeof(T), &p) != SQ_OK) throw std::bad_alloc();
+    return static_cast<T*>(p);
+  }
+  void deallocate(T* p, size_t) { sq_host_free(ctx, p); }
+  template <class U> bool operator==(const PinnedAlloc<U>& o) const { return ctx == o.ctx; }
+  template <class U> bool operator!=(const PinnedAlloc<U>& o) const { return ctx != o.ctx; }
+};
+template <class T> using PinnedVec = std::vector<T, PinnedAlloc<T>>;
+
 using sqkey::mix64;  // the key hash is defined once, in sq_keyhash.h (shared with the device-side scanner)
 
 enum class Kind { Fixed, Utf8, LargeUtf8 };
@@ -150,12 +170,13 @@ struct TileJob {
   Pending take;             // the batches the tile was made of (owned)
   ArrowArray joined{};      // their concatenation when there is more than one
   const ArrowArray* tile = nullptr;
-  std::vector<uint64_t> keys;
-  std::vector<int32_t> start, end;
+  PinnedVec<uint64_t> keys;
+  PinnedVec<int32_t> start, end;
   ArrowArray out{};
   uint64_t n_pairs = 0;
   uint64_t worker_ns = 0;
   int rc = 0;
+  explicit TileJob(sq_ctx* ctx) : keys(PinnedAlloc<uint64_t>(ctx)), start(PinnedAlloc<int32_t>(ctx)), end(PinnedAlloc<int32_t>(ctx)) {}
   ~TileJob() {
     if (th.joinable()) th.join();
     if (joined.release) joined.release(&joined);
@@ -312,8 +333,8 @@ void parallel_rows(int64_t n, F&& fn) {
 // contributes nothing to its row's hash, as in create_hashes (which skips null slots): rows whose key is NULL in
 // every `on` column therefore share the seed's hash and only meet each other — never the rows whose value slot
 // happens to hold the same bytes.
-int hash_keys(sq_exec* e, const Side& side, const std::vector<int32_t>& on, const ArrowArray* batch,
-              std::vector<uint64_t>* out) {
+template <class V64>  // std::vector<uint64_t> or PinnedVec<uint64_t>
+int hash_keys(sq_exec* e, const Side& side, const std::vector<int32_t>& on, const ArrowArray* batch, V64* out) {
   const int64_t n = batch->length;
   out->assign(size_t(n), sqkey::seed());  // on=[(1,1)]: every row carries the constant's hash
   for (int32_t col : on) {
@@ -321,9 +342,9 @@ int hash_keys(sq_exec* e, const Side& side, const std::vector<int32_t>& on, cons
     const ColView v = view_of(batch, col);
     const bool has_nulls = v.null_count != 0 && v.validity != nullptr;
     std::vector<uint64_t> before;
-    if (has_nulls) before = *out;  // null slots get their previous value back below
+    if (has_nulls) before.assign(out->begin(), out->end());  // null slots get their previous value back below
     struct Restore {
-      const ColView& v; const std::vector<uint64_t>& before; std::vector<uint64_t>* out; bool on;
+      const ColView& v; const std::vector<uint64_t>& before; V64* out; bool on;
       ~Restore() {
         if (!on) return;
         for (int64_t i = 0; i < v.length; ++i)
@@ -392,8 +413,8 @@ int hash_keys(sq_exec* e, const Side& side, const std::vector<int32_t>& on, cons
 }
 
 // evaluate_as_i32 (IJ:1661-1672): the interval column (or `column - 1`) as Int32, overflow is an error
-int eval_i32(sq_exec* e, sq_stream* st, const Side& side, int32_t col, bool minus_one, const ArrowArray* batch,
-             std::vector<int32_t>* out) {
+template <class V32>  // std::vector<int32_t> or PinnedVec<int32_t>
+int eval_i32(sq_exec* e, sq_stream* st, const Side& side, int32_t col, bool minus_one, const ArrowArray* batch, V32* out) {
   const ColType& t = side.cols[size_t(col)];
   const ColView v = view_of(batch, col);
   const int64_t n = batch->length;
@@ -736,8 +757,8 @@ namespace {
 // on the device.  *n_out = output rows of the whole batch.
 // host half: key hashes and the i32 view of the interval columns of one probe tile (`cast` is the stream a BIGINT column is
 // cast on: the partition's own, or its second one when a worker thread is using the first)
-int prep_tile(sq_exec* e, sq_stream* cast, const ArrowArray* batch, std::vector<uint64_t>* keys, std::vector<int32_t>* start,
-              std::vector<int32_t>* end) {
+template <class V64, class V32>
+int prep_tile(sq_exec* e, sq_stream* cast, const ArrowArray* batch, V64* keys, V32* start, V32* end) {
   if (uint64_t(batch->length) > 0xFFFFFFFFull) return e->fail(SQ_EINVAL, "probe batch too large");
   int rc;
   Trace tr(e->ctx);
@@ -750,8 +771,8 @@ int prep_tile(sq_exec* e, sq_stream* cast, const ArrowArray* batch, std::vector<
 }
 
 // device half: the probe of one prepared tile; the result stays on the device.  *n_out = output rows of the whole tile.
-int probe_tile(sq_exec* e, sq_stream* st, const std::vector<uint64_t>& keys, const std::vector<int32_t>& start,
-               const std::vector<int32_t>& end, uint64_t* n_out) {
+template <class V64, class V32>
+int probe_tile(sq_exec* e, sq_stream* st, const V64& keys, const V32& start, const V32& end, uint64_t* n_out) {
   const uint64_t n = keys.size();
   int rc;
   Trace tr(e->ctx);
@@ -887,7 +908,7 @@ int assemble_output(sq_exec* e, sq_stream* st, const ArrowArray* batch, uint64_t
       }
     } else {
       // Utf8 / LargeUtf8: offsets first (gives the byte total), then the bytes
-      std::vector<int64_t> poff;
+      PinnedVec<int64_t> poff{PinnedAlloc<int64_t>(e->ctx)};
       const uint8_t* pdata = nullptr;
       uint64_t pbytes = 0;
       if (side == 1) {
@@ -1055,6 +1076,15 @@ namespace {
 // One struct array holding the rows of `batches` back to back (what concat_batches does for the build side, IJ:685):
 // fixed-width values and Utf8 offsets / bytes are copied, validity bitmaps are rebuilt, dictionary columns get ONE
 // dictionary (values in order of first occurrence over the batches) with renumbered indices.
+// buffer of a concatenated tile: pinned, so that the columns the probe side contributes to the output reach the device at
+// link speed (released with the tile through Owned::pinned); nullptr when the pool cannot serve it
+void* tile_buffer(sq_exec* e, Owned* co, size_t bytes) {
+  void* p = nullptr;
+  if (sq_host_alloc(e->ctx, bytes ? bytes : 8, &p) != SQ_OK) return nullptr;
+  co->pinned.push_back(p);
+  return p;
+}
+
 int concat_batches(sq_exec* e, const Side& side, const std::vector<ArrowArray>& batches, ArrowArray* out) {
   uint64_t n = 0;
   for (const ArrowArray& b : batches) n += uint64_t(b.length);
@@ -1101,8 +1131,8 @@ int concat_batches(sq_exec* e, const Side& side, const std::vector<ArrowArray>& 
         if (!bit_at(v.validity, v.offset + i)) { validity[(r0 + uint64_t(i)) >> 3] &= uint8_t(~(1u << ((r0 + uint64_t(i)) & 7))); ++nulls; }
     };
     if (t.kind == Kind::Fixed) {
-      auto* vals = static_cast<uint8_t*>(malloc(size_t(n) * t.width + 8));
-      co->heap.push_back(vals);
+      auto* vals = static_cast<uint8_t*>(tile_buffer(e, co, size_t(n) * t.width + 8));
+      if (!vals) return e->fail(SQ_ECUDA, "%s", sq_last_error(e->ctx));
       uint64_t r = 0;
       if (t.dict) {
         std::vector<std::string> gdict;
@@ -1152,10 +1182,9 @@ int concat_batches(sq_exec* e, const Side& side, const std::vector<ArrowArray>& 
       if (!large && total > 0x7FFFFFFFull)
         return e->fail(SQ_ECAPACITY, "column '%s': the coalesced probe batches hold %llu string bytes; Utf8 offsets are 32-bit",
                        t.name.c_str(), (unsigned long long)total);
-      void* off = malloc((size_t(n) + 1) * (large ? 8 : 4));
-      auto* data = static_cast<uint8_t*>(malloc(total ? total : 1));
-      co->heap.push_back(off);
-      co->heap.push_back(data);
+      void* off = tile_buffer(e, co, (size_t(n) + 1) * (large ? 8 : 4));
+      auto* data = static_cast<uint8_t*>(tile_buffer(e, co, total));
+      if (!off || !data) return e->fail(SQ_ECUDA, "%s", sq_last_error(e->ctx));
       uint64_t r = 0, at = 0;
       for (const ArrowArray& b : batches) {  // per batch: ONE copy of its byte range, offsets rebased in a plain loop
         const ColView v = view_of(&b, int32_t(c));
@@ -1243,7 +1272,7 @@ SQ_API int32_t sq_exec_probe_pop(sq_exec* e, int32_t partition, int32_t flush, A
     if (jt != e->jobs.end()) { prev = std::move(jt->second); e->jobs.erase(jt); }
     auto it = e->pending.find(partition);
     if (it != e->pending.end() && !it->second.batches.empty() && (it->second.rows >= target || flush)) {
-      next.reset(new TileJob());
+      next.reset(new TileJob(e->ctx));
       next->take = std::move(it->second);
       e->pending.erase(it);
     }
