@@ -58,6 +58,19 @@ impl CudaIndex {
     }
     /// `build_mem_used` gauge / `MemoryReservation::try_grow` (interval_join.rs:629-631)
     pub fn bytes(&self) -> usize { unsafe { sys::sq_index_bytes(self.ptr.as_ptr()) as usize } }
+    /// `SET sequila.cuda_build_ids TO positions` was in force at build time: `left_idx` holds positions in the index's
+    /// (key, start) order and the payload columns registered with the index live in that order on the device.  The patch of
+    /// interval_join.rs keeps `take` on the host and therefore builds with `rows`; a stream that moves `take` onto the
+    /// device (sequila_exec.h does) switches this on and never looks at `left_idx` itself.
+    pub fn uses_positions(&self) -> bool { unsafe { sys::sq_index_uses_positions(self.ptr.as_ptr()) != 0 } }
+    /// position -> build row, for a caller that wants both the locality and the rows
+    pub fn position_rows(&self) -> Result<Vec<u32>> {
+        let n = unsafe { sys::sq_index_rows(self.ptr.as_ptr()) } as usize;
+        let mut rows = vec![0u32; n];
+        let rc = unsafe { sys::sq_index_position_rows(self.ptr.as_ptr(), rows.as_mut_ptr()) };
+        if rc != sys::SQ_OK { return Err(exec_err(unsafe { sys::sq_last_error(self.ctx.0.as_ptr()) })); }
+        Ok(rows)
+    }
 }
 impl Drop for CudaIndex { fn drop(&mut self) { unsafe { sys::sq_index_free(self.ptr.as_ptr()) } } }
 
