@@ -170,6 +170,16 @@ def test_options_surface(cuda_ctx):
         assert e.value.code == N.SQ_EINVAL and key.split(".")[-1] in str(e.value)
     c.set_option("cuda_l2_persist_mb", 0)
     assert c.get_option("cuda_l2_persist_mb") == "0"
+    # every key the session layer accepts (session.CUDA_KEYS, what `SET sequila.cuda_* TO ...` stores) is a key the library
+    # knows, documented in the header, and can be set back to the value it reports
+    from sequila_native_b200.session import CUDA_KEYS
+    import os
+    header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "sequila_cuda.h")).read()
+    for key in CUDA_KEYS:
+        v = c.get_option("sequila." + key)
+        c.set_option(key, v)
+        assert c.get_option(key) == v
+        assert key in header, key
 
 
 @pytest.mark.parametrize("parts,tiles", [(1, 1), (3, 10), (8, 64)])
