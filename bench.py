@@ -716,6 +716,11 @@ def main():
     assert e_digest == (d0[0], d0[1]), "host-side pairs of the pipeline differ from the device-side pairs"
     e_ms_max, e_rows_total, _ = reduce_step(e_ms, e2e_rows, 0, device)
     e2e_value = e_rows_total / (e_ms_max * 1e-3)
+    # the same with the counts as one byte per probe row (SQ_TILE_COUNTS_U8: every count of a cfg5 tile fits; a tile with a
+    # bigger one falls back to 4-byte counts by itself)
+    eu_ms, _, eu_digest, eu_stats = e2e_pipeline(sn, ctx, idx, probe_h, e_pairs, args, T, N.TILE_COUNTS_U8, args.e2e_steps, barrier)
+    assert eu_digest == (d0[0], d0[1]), "host-side pairs of the pipeline (byte counts) differ from the device-side pairs"
+    eu_ms_max, _, _ = reduce_step(eu_ms, 0, 0, device)
     # the same as `select count(1)`: host columns in, one number per tile out — the query shape of the reference's own
     # benchmarks (queries/q1-coitrees.sql:16-19); only the H2D copy is left on the wire
     ec_ms, _, _, ec_stats = e2e_pipeline(sn, ctx, idx, probe_h, e_pairs, args, T, N.TILE_COUNT_ONLY | N.TILE_NO_COUNTS,
@@ -939,6 +944,12 @@ def main():
                     "link_GBps": {"h2d": 16 * e2e_rows / (e_ms * 1e-3) / 1e9,
                                   "d2h": (4 * e_pairs + 4 * e2e_rows) / (e_ms * 1e-3) / 1e9},
                     "pairs_digest_equals_device": True, "key_ids": e_ids,
+                    "counts_u8": {"api": "the same with SQ_TILE_COUNTS_U8: per-row counts as one byte each (4-byte counts for a tile "
+                                         "in which some row has more than 255 hits)",
+                                  "value": e_rows_total / (eu_ms_max * 1e-3), "unit": "probe intervals/s", "ms_per_step": eu_ms_max,
+                                  "d2h_bytes_per_step": 4 * e_pairs + e2e_rows + 16 * n_tiles,
+                                  "d2h_bytes_moved_per_step": eu_stats["d2h_bytes"] // max(args.e2e_steps, 1),
+                                  "pairs_digest_equals_device": True},
                     "count_only": {"value": e_rows_total / (ec_ms_max * 1e-3), "unit": "probe intervals/s", "ms_per_step": ec_ms_max,
                                    "api": "same pipeline with SQ_TILE_COUNT_ONLY: count(1) of the join, host columns in, one number per tile out",
                                    "h2d_bytes_per_step": 16 * e2e_rows, "d2h_bytes_per_step": 16 * n_tiles,

@@ -191,10 +191,13 @@ int32_t sq_probe_join(sq_stream* s, const sq_index* idx, const uint64_t* key_has
 #define SQ_TILE_RIGHT_IDX 2u    /* also copy right_idx from the device (8 B per pair on the wire instead of 4)  */
 #define SQ_TILE_EXPAND_RIGHT 4u /* expand right_idx from the counts on the collecting thread                    */
 #define SQ_TILE_NO_COUNTS 8u    /* do not move the per-row counts (count-only callers that want the total only) */
+#define SQ_TILE_COUNTS_U8 16u   /* counts travel as one byte per probe row when every count of the tile is < 256 (a tenth of
+                                 * the cfg5 result's bytes); a tile with a bigger count hands over 4-byte counts as usual:
+                                 * read sq_tile_out.counts_width */
 typedef struct sq_tile_out {
   uint64_t n_pairs;
   uint32_t n_rows;
-  uint32_t reserved;
+  uint32_t counts_width;  /* bytes per element of `counts`: 4, or 1 (SQ_TILE_COUNTS_U8; `counts` then points at bytes); 0: no counts */
   uint32_t* left_idx;
   uint32_t* right_idx;
   uint32_t* counts;

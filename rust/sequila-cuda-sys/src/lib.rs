@@ -30,6 +30,7 @@ pub const SQ_TILE_COUNT_ONLY: u32 = 1;
 pub const SQ_TILE_RIGHT_IDX: u32 = 2;
 pub const SQ_TILE_EXPAND_RIGHT: u32 = 4;
 pub const SQ_TILE_NO_COUNTS: u32 = 8;
+pub const SQ_TILE_COUNTS_U8: u32 = 16;
 
 /// `struct sq_tile_out`: result of one collected tile; the three buffers are pinned host memory owned by the
 /// caller after `sq_stream_collect` and go back to the pool with `sq_host_free`.
@@ -37,7 +38,7 @@ pub const SQ_TILE_NO_COUNTS: u32 = 8;
 pub struct sq_tile_out {
     pub n_pairs: u64,
     pub n_rows: u32,
-    pub reserved: u32,
+    pub counts_width: u32, // bytes per element of `counts`: 4, or 1 with SQ_TILE_COUNTS_U8; 0: no counts
     pub left_idx: *mut u32,
     pub right_idx: *mut u32,
     pub counts: *mut u32,

@@ -82,7 +82,10 @@ unsafe impl Send for Tile {}
 impl Tile {
     pub fn n_pairs(&self) -> usize { self.out.n_pairs as usize }
     pub fn left_idx(&self) -> &[u32] { if self.out.left_idx.is_null() { &[] } else { unsafe { std::slice::from_raw_parts(self.out.left_idx, self.n_pairs()) } } }
-    pub fn counts(&self) -> &[u32] { if self.out.counts.is_null() { &[] } else { unsafe { std::slice::from_raw_parts(self.out.counts, self.out.n_rows as usize) } } }
+    /// 4-byte counts (tiles submitted without SQ_TILE_COUNTS_U8, or a tile in which some row has more than 255 hits)
+    pub fn counts(&self) -> &[u32] { if self.out.counts.is_null() || self.out.counts_width != 4 { &[] } else { unsafe { std::slice::from_raw_parts(self.out.counts, self.out.n_rows as usize) } } }
+    /// one-byte counts (SQ_TILE_COUNTS_U8 and every count of the tile < 256): `rle_right` expands from either width
+    pub fn counts_u8(&self) -> &[u8] { if self.out.counts.is_null() || self.out.counts_width != 1 { &[] } else { unsafe { std::slice::from_raw_parts(self.out.counts as *const u8, self.out.n_rows as usize) } } }
 }
 impl Drop for Tile {
     fn drop(&mut self) {
@@ -117,7 +120,7 @@ impl CudaStream {
     pub fn in_flight(&self) -> usize { unsafe { sys::sq_stream_in_flight(self.ptr.as_ptr()) as usize } }
     /// Wait for the oldest ticket.
     pub fn collect(&mut self, ticket: u64) -> Result<Tile> {
-        let mut out = sys::sq_tile_out { n_pairs: 0, n_rows: 0, reserved: 0, left_idx: null_mut(), right_idx: null_mut(), counts: null_mut() };
+        let mut out = sys::sq_tile_out { n_pairs: 0, n_rows: 0, counts_width: 0, left_idx: null_mut(), right_idx: null_mut(), counts: null_mut() };
         let rc = unsafe { sys::sq_stream_collect(self.ptr.as_ptr(), ticket, &mut out) };
         if rc != sys::SQ_OK { return Err(self.err()); }
         Ok(Tile { out, ctx: self.ctx.clone() })

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SQ_LIB_PATH") or os.path.join(_HERE, "libsequila_cuda.so")  # SQ_LIB_PATH: A/B experiments only
 
 SQ_OK, SQ_EINVAL, SQ_ECUDA, SQ_ENOMEM, SQ_ESTATE, SQ_ECAPACITY, SQ_ECAST, SQ_EPARSE, SQ_EBUSY = range(9)
-TILE_COUNT_ONLY, TILE_RIGHT_IDX, TILE_EXPAND_RIGHT, TILE_NO_COUNTS = 1, 2, 4, 8  # SQ_TILE_* flags
+TILE_COUNT_ONLY, TILE_RIGHT_IDX, TILE_EXPAND_RIGHT, TILE_NO_COUNTS, TILE_COUNTS_U8 = 1, 2, 4, 8, 16  # SQ_TILE_* flags
 NULL_INDEX = 0xFFFFFFFF  # SQ_NULL_INDEX
 
 u64p = C.POINTER(C.c_uint64)
@@ -22,7 +22,7 @@ vp = C.c_void_p
 
 class SqTileOut(C.Structure):
     """struct sq_tile_out (include/sequila_cuda.h)"""
-    _fields_ = [("n_pairs", C.c_uint64), ("n_rows", C.c_uint32), ("reserved", C.c_uint32),
+    _fields_ = [("n_pairs", C.c_uint64), ("n_rows", C.c_uint32), ("counts_width", C.c_uint32),
                 ("left_idx", C.c_void_p), ("right_idx", C.c_void_p), ("counts", C.c_void_p)]
 
 

@@ -493,7 +493,7 @@ SQ_API void sq_stream_free(sq_stream* s) {
   cudaSetDevice(s->ctx->device);
   cudaStreamSynchronize(s->stream);
   pipeline_destroy(s);
-  for (sq_buf* b : {&s->d_in, &s->d_cnt, &s->d_state, &s->d_tile, &s->d_scalar, &s->d_left,
+  for (sq_buf* b : {&s->d_in, &s->d_cnt, &s->d_cnt8, &s->d_state, &s->d_tile, &s->d_scalar, &s->d_left,
                     &s->d_right, &s->d_gather, &s->d_gather2, &s->d_chain, &s->d_strblk, &s->d_strdata, &s->h_in, &s->h_out, &s->h_scalar, &s->h_scan})
     release(*b);
   if (s->ev_ready) for (auto& e : s->ev) cudaEventDestroy(e);

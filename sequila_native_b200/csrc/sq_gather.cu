@@ -445,6 +445,33 @@ int launch_narrow_offsets(sq_stream* s, const int64_t* d_in, uint64_t n, int32_t
   return SQ_OK;
 }
 
+// SQ_TILE_COUNTS_U8: the per-row hit counts of a tile as bytes (a quarter of the bytes over PCIe); *too_big is set when some
+// count does not fit, and the caller then moves the 4-byte counts after all
+__global__ void __launch_bounds__(256) k_narrow_counts(const uint32_t* __restrict__ cnt, uint32_t n, uint8_t* __restrict__ out,
+                                                       unsigned long long* too_big) {
+  const uint32_t i4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  uint32_t c[4] = {0, 0, 0, 0};
+  if (i4 + 4 <= n) {
+    const uint4 v = *reinterpret_cast<const uint4*>(cnt + i4);
+    c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+    *reinterpret_cast<uint32_t*>(out + i4) = (c[0] & 255u) | ((c[1] & 255u) << 8) | ((c[2] & 255u) << 16) | ((c[3] & 255u) << 24);
+  } else {
+    for (uint32_t k = 0; i4 + k < n; ++k) { c[k] = cnt[i4 + k]; out[i4 + k] = uint8_t(c[k]); }
+  }
+  if ((c[0] | c[1] | c[2] | c[3]) > 255u) *too_big = 1ull;
+}
+
+int launch_narrow_counts(sq_stream* s, cudaStream_t st, const uint32_t* d_cnt, uint32_t n, uint8_t* d_out, unsigned long long* d_too_big) {
+  ErrorSlot& E = s->err;
+  SQ_CUDA(E, cudaMemsetAsync(d_too_big, 0, 8, st));
+  if (n == 0) return SQ_OK;
+  k_narrow_counts<<<(n / 4 + 256) / 256, 256, 0, st>>>(d_cnt, n, d_out, d_too_big);
+  SQ_CUDA(E, cudaGetLastError());
+  s->launches += 1;
+  return SQ_OK;
+}
+
 __global__ void __launch_bounds__(256) k_iota(uint32_t* __restrict__ out, uint64_t n) {
   const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = uint32_t(i);

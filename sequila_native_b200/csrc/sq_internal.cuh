@@ -277,6 +277,7 @@ struct sq_stream {
   // device scratch
   sq_buf d_in;       // staged probe key/start/end (host entry points)
   sq_buf d_cnt;      // hit count per probe row (rle_right)
+  sq_buf d_cnt8;     // the same as bytes (SQ_TILE_COUNTS_U8)
   sq_buf d_state;    // per probe row: lo, nc, hit mask (3 x u32 arrays)
   sq_buf d_tile;     // per-CTA pair totals -> offsets, + chained-scan words
   sq_buf d_scalar;   // n_pairs, ticket counter, cast-error slot, digest
@@ -348,6 +349,7 @@ int launch_nearest(sq_stream* s, const sq_index* idx, const uint64_t* d_key, con
                    const int32_t* d_end, uint32_t n, uint32_t* d_left);
 // right_idx of a one-row-per-probe-row result: 0, 1, ..., n-1
 int launch_iota(sq_stream* s, uint32_t* d_out, uint64_t n);
+int launch_narrow_counts(sq_stream* s, cudaStream_t st, const uint32_t* d_cnt, uint32_t n, uint8_t* d_out, unsigned long long* d_too_big);
 int launch_narrow_offsets(sq_stream* s, const int64_t* d_in, uint64_t n, int32_t* d_out);
 
 // probe_packed.cu: one fused pass over the packed lines (count + chained scan + write when

@@ -122,8 +122,10 @@ static int32_t submit_tile(sq_stream* s, const sq_index* idx, const uint64_t* ke
   if (!idx || !ticket_out) return fail(E, SQ_EINVAL, "null index or ticket pointer");
   if (n_rows && ((!key_hash && !key_id) || !start || !end)) return fail(E, SQ_EINVAL, "null probe column");
   if (key_id && !s->d_dict.p) return fail(E, SQ_ESTATE, "sq_stream_submit_ids without sq_stream_set_key_dictionary");
-  if (flags & ~(SQ_TILE_COUNT_ONLY | SQ_TILE_RIGHT_IDX | SQ_TILE_EXPAND_RIGHT | SQ_TILE_NO_COUNTS))
+  if (flags & ~(SQ_TILE_COUNT_ONLY | SQ_TILE_RIGHT_IDX | SQ_TILE_EXPAND_RIGHT | SQ_TILE_NO_COUNTS | SQ_TILE_COUNTS_U8))
     return fail(E, SQ_EINVAL, "unknown tile flag bits 0x%x", flags);
+  if ((flags & SQ_TILE_COUNTS_U8) && (flags & (SQ_TILE_EXPAND_RIGHT | SQ_TILE_NO_COUNTS)))
+    return fail(E, SQ_EINVAL, "SQ_TILE_COUNTS_U8 goes with neither SQ_TILE_EXPAND_RIGHT (it reads 4-byte counts) nor SQ_TILE_NO_COUNTS");
   if (idx->ctx->device != s->ctx->device)
     return fail(E, SQ_EINVAL, "index lives on device %d, stream on %d", idx->ctx->device, s->ctx->device);
   SQ_CUDA(E, cudaSetDevice(s->ctx->device));
@@ -149,6 +151,7 @@ static int32_t submit_tile(sq_stream* s, const sq_index* idx, const uint64_t* ke
   } drain{s, true};
   const bool count_only = (flags & SQ_TILE_COUNT_ONLY) != 0;
   const bool want_right = !count_only && (flags & SQ_TILE_RIGHT_IDX) != 0;
+  const bool counts_u8 = (flags & SQ_TILE_COUNTS_U8) != 0;
   const size_t n = n_rows;
 
   // buffers of this tile, sized from the fan-out of the last collected tile (first tile: a guess, nothing speculative)
@@ -161,6 +164,7 @@ static int32_t submit_tile(sq_stream* s, const sq_index* idx, const uint64_t* ke
     if ((rc = ensure(E, sub->d_in, n * (key_id ? 20 : 16), false))) return rc;
     if (dev_cap && (rc = ensure(E, sub->d_left, dev_cap * 4, false))) return rc;
     if (want_right && (rc = ensure(E, sub->d_right, dev_cap * 4, false))) return rc;
+    if (counts_u8 && (rc = ensure(E, sub->d_cnt8, n + 16, false))) return rc;
   }
   drop_outputs(s, sl);
   if ((flags & SQ_TILE_NO_COUNTS) == 0 && n && (rc = pinned(s, n * 4, &sl->h_counts))) return rc;
@@ -176,7 +180,7 @@ static int32_t submit_tile(sq_stream* s, const sq_index* idx, const uint64_t* ke
   sl->flags = flags;
   sl->idx = idx;
   auto* hs = static_cast<unsigned long long*>(sl->h_scalar.p);
-  hs[0] = hs[1] = hs[2] = hs[3] = 0;
+  hs[0] = hs[1] = hs[2] = hs[3] = hs[4] = 0;
 
   auto* dk = static_cast<uint64_t*>(sub->d_in.p);
   auto* ds = reinterpret_cast<int32_t*>(dk + n);
@@ -210,14 +214,20 @@ static int32_t submit_tile(sq_stream* s, const sq_index* idx, const uint64_t* ke
       if ((rc = launch_count(sub, idx, dk, ds, de, n_rows))) return fail(E, rc, "%s", sub->err.msg.c_str());
       if (d_left && (rc = launch_write(sub, idx, ds, n_rows, d_left, d_right, dev_cap))) return fail(E, rc, "%s", sub->err.msg.c_str());
     }
+    // counts as bytes: the pinned buffer still has room for the 4-byte counts, which follow at collect if a count overflows
+    if (counts_u8 && (rc = launch_narrow_counts(sub, s->stream, static_cast<const uint32_t*>(sub->d_cnt.p), n_rows,
+                                               static_cast<uint8_t*>(sub->d_cnt8.p),
+                                               static_cast<unsigned long long*>(sub->d_scalar.p) + 4)))
+      return fail(E, rc, "%s", sub->err.msg.c_str());
     s->launches += sub->launches;
     sub->launches = 0;
     SQ_CUDA(E, cudaEventRecord(sl->ev[2], s->stream));
     // ---- copy-out
     SQ_CUDA(E, cudaStreamWaitEvent(s->stream_out, sl->ev[2], 0));
     SQ_CUDA(E, cudaEventRecord(sl->ev[4], s->stream_out));
-    SQ_CUDA(E, cudaMemcpyAsync(hs, sub->d_scalar.p, 32, cudaMemcpyDeviceToHost, s->stream_out));
-    if (sl->h_counts) SQ_CUDA(E, cudaMemcpyAsync(sl->h_counts, sub->d_cnt.p, n * 4, cudaMemcpyDeviceToHost, s->stream_out));
+    SQ_CUDA(E, cudaMemcpyAsync(hs, sub->d_scalar.p, 40, cudaMemcpyDeviceToHost, s->stream_out));
+    if (sl->h_counts && counts_u8) SQ_CUDA(E, cudaMemcpyAsync(sl->h_counts, sub->d_cnt8.p, n, cudaMemcpyDeviceToHost, s->stream_out));
+    else if (sl->h_counts) SQ_CUDA(E, cudaMemcpyAsync(sl->h_counts, sub->d_cnt.p, n * 4, cudaMemcpyDeviceToHost, s->stream_out));
     SQ_CUDA(E, cudaEventRecord(sl->ev[3], s->stream_out));
     if (est) {
       SQ_CUDA(E, cudaMemcpyAsync(sl->h_left, d_left, est * 4, cudaMemcpyDeviceToHost, s->stream_out));
@@ -273,6 +283,7 @@ SQ_API int32_t sq_stream_collect(sq_stream* s, uint64_t ticket, sq_tile_out* out
   const bool count_only = (sl->flags & SQ_TILE_COUNT_ONLY) != 0;
   const bool want_right = !count_only && (sl->flags & SQ_TILE_RIGHT_IDX) != 0;
   uint64_t n_pairs = 0;
+  uint32_t counts_width = 4;
   int rc = SQ_OK;
   auto bail = [&](int code) {  // the tile is gone either way: free its slot and its buffers
     drop_outputs(s, sl);
@@ -288,6 +299,15 @@ SQ_API int32_t sq_stream_collect(sq_stream* s, uint64_t ticket, sq_tile_out* out
     if (sl->staged) staged_feedback(s, sl->n_rows, hs[2], hs[3]);
     const bool overflow = hs[1] != 0 || n_pairs > sl->dev_cap;
     uint64_t copied = sl->spec;
+    if ((sl->flags & SQ_TILE_COUNTS_U8) && sl->h_counts) {
+      counts_width = 1;
+      if (hs[4]) {  // some row has more than 255 hits: the 4-byte counts after all (they are still in the slot's scratch)
+        ce = cudaMemcpyAsync(sl->h_counts, sub->d_cnt.p, n * 4, cudaMemcpyDeviceToHost, s->stream_out);
+        if (ce == cudaSuccess) ce = cudaEventRecord(sl->ev[5], s->stream_out);
+        if (ce != cudaSuccess) return bail(fail(E, SQ_ECUDA, "D2H copy of the counts: %s", cudaGetErrorString(ce)));
+        counts_width = 4;
+      }
+    }
     if (!count_only && n_pairs) {
       if (overflow) {  // the device buffers were too small for this tile: grow them, re-run only the write pass
         if ((rc = ensure(E, sub->d_left, n_pairs * 4, false))) return bail(rc);
@@ -330,7 +350,7 @@ SQ_API int32_t sq_stream_collect(sq_stream* s, uint64_t ticket, sq_tile_out* out
     if (cudaEventElapsedTime(&ms, sl->ev[4], sl->ev[5]) == cudaSuccess) s->pipe_ms[2] += ms;
     cudaGetLastError();
     s->pipe_bytes[0] += n * (8 + sl->key_bytes);
-    s->pipe_bytes[1] += 16 + (sl->h_counts ? n * 4 : 0) + (count_only ? 0 : (want_right ? 8 : 4) * (n_pairs > sl->spec ? n_pairs : sl->spec));
+    s->pipe_bytes[1] += 16 + (sl->h_counts ? n * ((sl->flags & SQ_TILE_COUNTS_U8) ? (counts_width == 4 ? 5 : 1) : 4) : 0) + (count_only ? 0 : (want_right ? 8 : 4) * (n_pairs > sl->spec ? n_pairs : sl->spec));
     s->pipe_tiles += 1;
     if (!count_only) s->pairs_per_row = double(n_pairs) / double(n);
   }
@@ -345,6 +365,7 @@ SQ_API int32_t sq_stream_collect(sq_stream* s, uint64_t ticket, sq_tile_out* out
   out->left_idx = sl->h_left;
   out->right_idx = sl->h_right;
   out->counts = sl->h_counts;
+  out->counts_width = sl->h_counts ? counts_width : 0;
   sl->h_left = sl->h_right = sl->h_counts = nullptr;  // the caller owns them now (sq_host_free)
   sl->h_cap = 0;
   sl->busy = false;

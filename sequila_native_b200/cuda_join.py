@@ -291,16 +291,18 @@ class CudaStream:
         getattr(self, "_tiles", {}).pop(int(ticket), None)
         _check(rc, self._err)
 
-        def view(addr, n):
+        def view(addr, n, width=4):
             if not addr:
                 return None
-            buf = (C.c_uint32 * max(int(n), 1)).from_address(addr)
-            arr = np.frombuffer(buf, dtype=np.uint32, count=int(n))
+            ct, dt = (C.c_uint8, np.uint8) if width == 1 else (C.c_uint32, np.uint32)
+            buf = (ct * max(int(n), 1)).from_address(addr)
+            arr = np.frombuffer(buf, dtype=dt, count=int(n))
             weakref.finalize(buf, self._lib.sq_host_free, self.ctx._h, C.c_void_p(addr))
             return arr
         self.n_rows, self.n_pairs = int(out.n_rows), int(out.n_pairs)
+        # counts: uint32, or uint8 for a tile submitted with TILE_COUNTS_U8 whose counts all fit a byte (sq_tile_out.counts_width)
         return (int(out.n_pairs), view(out.left_idx, out.n_pairs), view(out.right_idx, out.n_pairs),
-                view(out.counts, out.n_rows))
+                view(out.counts, out.n_rows, int(out.counts_width)))
 
     @property
     def in_flight(self) -> int:

@@ -57,7 +57,8 @@ def check_tiles(oracle, b, p, n_tiles, out, flags):
 
 @pytest.mark.parametrize("layout", ["packed", "soa"])
 @pytest.mark.parametrize("flags", [0, N.TILE_RIGHT_IDX, N.TILE_EXPAND_RIGHT, N.TILE_COUNT_ONLY,
-                                   N.TILE_COUNT_ONLY | N.TILE_NO_COUNTS])
+                                   N.TILE_COUNT_ONLY | N.TILE_NO_COUNTS, N.TILE_COUNTS_U8, N.TILE_COUNTS_U8 | N.TILE_RIGHT_IDX,
+                                   N.TILE_COUNTS_U8 | N.TILE_COUNT_ONLY])
 def test_pipeline_matches_oracle(cuda_ctx, oracle, layout, flags):
     cuda_ctx.set_option("cuda_probe_layout", layout)
     try:
@@ -67,6 +68,8 @@ def test_pipeline_matches_oracle(cuda_ctx, oracle, layout, flags):
         check_tiles(oracle, b, p, 9, out, flags)
         stats = st.pipeline_stats()
         assert stats["tiles"] == 9 and stats["h2d_bytes"] == 16 * len(p["key"])
+        if flags & N.TILE_COUNTS_U8:  # cfg5: a handful of hits per row, every tile's counts travel as bytes
+            assert all(o[3].dtype == np.uint8 for o in out)
         if not flags & N.TILE_COUNT_ONLY:
             assert stats["regrown"] <= 1  # only the first tile may have been sized blind
     finally:
@@ -120,6 +123,39 @@ def test_pipeline_survives_fanout_jumps_and_empty_tiles(cuda_ctx, oracle):
             assert np.array_equal(canon(left, np.repeat(np.arange(len(oc), dtype=np.uint32), counts)), canon(ol, orr))
     assert got[6][0] == 0 and got[4][0] == 0
     assert st.pipeline_stats()["regrown"] >= 2
+
+
+def test_byte_counts_fall_back_tile_by_tile(cuda_ctx, oracle):
+    """SQ_TILE_COUNTS_U8: tiles whose counts all fit a byte hand over uint8 counts, a tile with a row of more than 255 hits
+    hands over the usual 4-byte counts (sq_tile_out.counts_width); the pairs are the oracle's either way"""
+    rng = np.random.default_rng(9)
+    n = 40_000
+    start = np.sort(rng.integers(0, 4_000_000, n)).astype(np.int32)
+    b = {"key": np.full(n, 77, np.uint64), "start": start, "end": (start + rng.integers(10, 60, n)).astype(np.int32)}
+    b["start"][:400] = 1_000_000 + np.arange(400, dtype=np.int32)  # 400 rows piled over one spot
+    b["end"][:400] = 1_000_600
+    idx = sn.CudaIndex.build(cuda_ctx, b["key"], b["start"], b["end"])
+    q = rng.integers(0, 4_000_000, 30_000)
+    p = {"key": np.full(30_000, 77, np.uint64), "start": q.astype(np.int32), "end": (q + 100).astype(np.int32)}
+    p["start"][12_345] = 1_000_100  # one probe row under the pile: > 255 hits, in the second of three tiles
+    p["end"][12_345] = 1_000_500
+    p["start"][10_000:10_050] = 3_999_000  # keep the rest of that tile's rows ordinary
+    p["end"][10_000:10_050] = 3_999_050
+    far = (p["end"] < 999_000) | (p["start"] > 1_001_000)
+    far[12_345] = True
+    p = {k: v[far] for k, v in p.items()}
+    at = int(np.flatnonzero((p["start"] == 1_000_100) & (p["end"] == 1_000_500))[0])
+    for flags in (N.TILE_COUNTS_U8, N.TILE_COUNTS_U8 | N.TILE_COUNT_ONLY):
+        st, out = run_pipeline(cuda_ctx, idx, p, 3, flags)
+        check_tiles(oracle, b, p, 3, out, flags)
+        widths = [o[3].dtype.itemsize for o in out]
+        hot = [lo <= at < hi for lo, hi in tiles_of(p, 3)]
+        assert widths == [4 if h else 1 for h in hot] and sum(hot) == 1
+        assert int(out[hot.index(True)][3].max()) >= 400
+    with pytest.raises(sn.SequilaCudaError) as e:  # the host-side expansion reads 4-byte counts
+        sn.CudaStream(cuda_ctx).submit(idx, cuda_ctx.pinned_copy(p["key"]), cuda_ctx.pinned_copy(p["start"]), cuda_ctx.pinned_copy(p["end"]),
+                                       flags=N.TILE_COUNTS_U8 | N.TILE_EXPAND_RIGHT)
+    assert e.value.code == N.SQ_EINVAL
 
 
 def test_pipeline_many_streams_concurrently(cuda_ctx, oracle):

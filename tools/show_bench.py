@@ -5,6 +5,7 @@ print("value %.3f G rows/s  ms/step %.4f  launches %s  clocks %s" % (d["value"] 
 r = d["roofline"]; print("roofline frac %.4f  kernel %s  avg_launch_ms %.4f traffic %s (%s)" % (r["frac"], r["kernel"], r["avg_launch_ms"], r["traffic"], r.get("traffic_source")))
 print("build", d["build"])
 e = d["e2e"]; print("e2e %.3f G rows/s  ms %.3f  T=%s tiles=%s link %s phase %s" % (e["value"] / 1e9, e["ms_per_step"], e["partitions"], e["tiles"], e["link_GBps"], e["phase_ms"]))
+if e.get("counts_u8"): print("e2e counts_u8 %.3f G rows/s ms %.3f" % (e["counts_u8"]["value"] / 1e9, e["counts_u8"]["ms_per_step"]))
 c = e["count_only"]; print("e2e count-only %.3f G rows/s ms %.3f link %s" % (c["value"] / 1e9, c["ms_per_step"], c["link_GBps"]))
 for k in ("locality", "count_only", "materialise", "full_config", "exec_node", "oracle_check", "balance"):
     if d.get(k): print(k, json.dumps(d[k])[:600])
