@@ -543,6 +543,18 @@ def exec_node_line(sn, args, n_build=2_000_000, n_probe=2_000_000, batch_rows=81
                     "probe + take inside the library"}
 
 
+def link_ceiling():
+    """what the host link of a 1-GPU box of this pool moves with pinned memory (profiles/r02_pcie_ubench.json, 64 MiB copies,
+    tools/ubench_pcie.py): the ceiling the end-to-end lines are read against"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_pcie_ubench.json")) as f:
+            r = json.load(f)["64MiB"]
+        return {"h2d_alone": r["h2d_GBps"], "d2h_alone": r["d2h_GBps"], "each_way_under_duplex_load": r["duplex_each_GBps"],
+                "source": "profiles/r02_pcie_ubench.json (tools/ubench_pcie.py, 64 MiB pinned copies)"}
+    except Exception:
+        return None
+
+
 def source_sha(files):
     h = hashlib.sha256()
     for f in files:
@@ -944,6 +956,7 @@ def main():
                     "link_GBps": {"h2d": 16 * e2e_rows / (e_ms * 1e-3) / 1e9,
                                   "d2h": (4 * e_pairs + 4 * e2e_rows) / (e_ms * 1e-3) / 1e9},
                     "pairs_digest_equals_device": True, "key_ids": e_ids,
+                    "link_ceiling_GBps": link_ceiling(),
                     "counts_u8": {"api": "the same with SQ_TILE_COUNTS_U8: per-row counts as one byte each (4-byte counts for a tile "
                                          "in which some row has more than 255 hits)",
                                   "value": e_rows_total / (eu_ms_max * 1e-3), "unit": "probe intervals/s", "ms_per_step": eu_ms_max,
